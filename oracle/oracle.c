@@ -1,0 +1,858 @@
+/*
+ * oracle.c -- CPU restatement of the Integrals.jl hot path.  TEST INFRASTRUCTURE ONLY
+ * (see oracle.h).  Plain C99; compile with -ffp-contract=off so that a*b+c stays a
+ * separate multiply and add exactly where the reference (Julia, no auto-FMA) has them.
+ * Where this file wants a fused multiply-add (the registered integrand family, which is
+ * OUR definition and is mirrored instruction-for-instruction by the device code) it
+ * calls fma() explicitly.
+ */
+#include "oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define ORC_MAXDIM 16
+
+/* ------------------------------------------------------------------------------------------
+ * Registered integrand family (not in the reference -- the reference only
+ * cites Genz & Malik at src/algorithms.jl:96-98).  Parameter layouts (doubles per problem):
+ *   0 SINXP      [p]                         sin(x*p)                      (README.md:30-40)
+ *   1 OSC        [a_1..a_d, u_1..u_d]        cos(2 pi u_1 + sum a_i x_i)
+ *   2 PRODPEAK   [a, u]                      1 / prod(a_i^-2 + (x_i-u_i)^2)
+ *   3 CORNER     [a, u]                      (1 + sum a_i x_i)^-(d+1)
+ *   4 GAUSS      [a, u]                      exp(-sum a_i^2 (x_i-u_i)^2)
+ *   5 C0         [a, u]                      exp(-sum a_i |x_i-u_i|)
+ *   6 DISCONT    [a, u]                      0 if x_1>u_1 or x_2>u_2 else exp(sum a_i x_i)
+ *   7 COSPROD    [p_1..p_d]                  prod cos(p_i x_i)             (test/quadrule_tests.jl:6)
+ *   8 GAUSSPOLY  [a, u, k_1..k_d, c]         c * prod x_i^k_i * exp(-sum a_i^2 (x_i-u_i)^2)
+ *   9 EXPLIN     [a_1..a_d]                  exp(sum a_i x_i)              (test/alt_transformation_tests.jl:22,28)
+ *  10 GLTEST     [p]                         5x + sin(x) - p*exp(x)        (test/gaussian_quadrature_tests.jl:48)
+ * The evaluation order below is the definition; csrc/family.cuh mirrors it.
+ * ------------------------------------------------------------------------------------------ */
+int orc_family_nparam(int fam, int dim)
+{
+    switch (fam) {
+    case ORC_FAM_SINXP: case ORC_FAM_GLTEST: return 1;
+    case ORC_FAM_GENZ_OSC: case ORC_FAM_GENZ_PRODPEAK: case ORC_FAM_GENZ_CORNER:
+    case ORC_FAM_GENZ_GAUSS: case ORC_FAM_GENZ_C0: case ORC_FAM_GENZ_DISCONT: return 2 * dim;
+    case ORC_FAM_COSPROD: case ORC_FAM_EXPLIN: return dim;
+    case ORC_FAM_GAUSSPOLY: return 3 * dim + 1;
+    default: return -1;
+    }
+}
+
+static const double ORC_TWO_PI = 6.283185307179586476925286766559;
+
+double orc_family_eval(int fam, int dim, const double *x, const double *par)
+{
+    const double *a = par, *u = par + dim;
+    switch (fam) {
+    case ORC_FAM_SINXP:
+        return sin(x[0] * par[0]);
+    case ORC_FAM_GENZ_OSC: {
+        double s = ORC_TWO_PI * u[0];
+        for (int i = 0; i < dim; i++) s = fma(a[i], x[i], s);
+        return cos(s);
+    }
+    case ORC_FAM_GENZ_PRODPEAK: {
+        double pr = 1.0;
+        for (int i = 0; i < dim; i++) {
+            double t = x[i] - u[i];
+            double ainv2 = 1.0 / (a[i] * a[i]);
+            pr *= fma(t, t, ainv2);
+        }
+        return 1.0 / pr;
+    }
+    case ORC_FAM_GENZ_CORNER: {
+        double s = 1.0;
+        for (int i = 0; i < dim; i++) s = fma(a[i], x[i], s);
+        double r = 1.0 / s, pw = r;
+        for (int i = 0; i < dim; i++) pw *= r;
+        return pw;
+    }
+    case ORC_FAM_GENZ_GAUSS: {
+        double s = 0.0;
+        for (int i = 0; i < dim; i++) {
+            double t = a[i] * (x[i] - u[i]);
+            s = fma(t, t, s);
+        }
+        return exp(-s);
+    }
+    case ORC_FAM_GENZ_C0: {
+        double s = 0.0;
+        for (int i = 0; i < dim; i++) s = fma(a[i], fabs(x[i] - u[i]), s);
+        return exp(-s);
+    }
+    case ORC_FAM_GENZ_DISCONT: {
+        if (x[0] > u[0]) return 0.0;
+        if (dim > 1 && x[1] > u[1]) return 0.0;
+        double s = 0.0;
+        for (int i = 0; i < dim; i++) s = fma(a[i], x[i], s);
+        return exp(s);
+    }
+    case ORC_FAM_COSPROD: {
+        double pr = 1.0;
+        for (int i = 0; i < dim; i++) pr *= cos(par[i] * x[i]);
+        return pr;
+    }
+    case ORC_FAM_GAUSSPOLY: {
+        const double *k = par + 2 * dim;
+        double s = 0.0, pr = par[3 * dim];
+        for (int i = 0; i < dim; i++) {
+            double t = a[i] * (x[i] - u[i]);
+            s = fma(t, t, s);
+            int ki = (int)k[i];
+            for (int j = 0; j < ki; j++) pr *= x[i];
+        }
+        return pr * exp(-s);
+    }
+    case ORC_FAM_EXPLIN: {
+        double s = 0.0;
+        for (int i = 0; i < dim; i++) s = fma(par[i], x[i], s);
+        return exp(s);
+    }
+    case ORC_FAM_GLTEST:
+        return fma(5.0, x[0], sin(x[0])) - par[0] * exp(x[0]);
+    default:
+        return NAN;
+    }
+}
+
+double orc_family_integrand(const double *x, int dim, void *user)
+{
+    const orc_family_user *fu = (const orc_family_user *)user;
+    return orc_family_eval(fu->fam, dim, x, fu->par);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Transforms -- src/infinity_handling.jl
+ * ------------------------------------------------------------------------------------------ */
+static inline double flipsign(double x, double y) { return signbit(y) ? -x : x; }
+
+/* infinity_handling.jl:91-107 */
+void orc_u2t(double lb, double ub, double *tlb, double *tub)
+{
+    if (isinf(lb) && isinf(ub)) { *tlb = flipsign(1.0, lb); *tub = flipsign(1.0, ub); }
+    else if (isinf(lb))         { *tlb = flipsign(1.0, lb); *tub = 0.0; }
+    else if (isinf(ub))         { *tlb = 0.0;               *tub = flipsign(1.0, ub); }
+    else                        { *tlb = -1.0;              *tub = 1.0; }
+}
+
+static const double ORC_HALF_PI = 1.5707963267948966; /* Float64(pi/2) */
+
+/* infinity_handling.jl:109-125, 201-237, 312-356 */
+void orc_t2ujac(int tr, double t, double lb, double ub, double *u, double *jac)
+{
+    int il = isinf(lb), iu = isinf(ub);
+    if (!il && !iu) {                         /* :121-124 -- same in all three transforms */
+        double den = (ub - lb) * 0.5;
+        *u = lb + (1.0 + t) * den;
+        *jac = den;
+        return;
+    }
+    if (tr == ORC_TR_IF_INF) {
+        if (il && iu) {                       /* :112-114 */
+            double den = 1.0 / (1.0 - t * t);
+            *u = t * den;
+            *jac = (1.0 + t * t) * (den * den);
+        } else if (il) {                      /* :115-117 */
+            double den = 1.0 / (1.0 - flipsign(t, lb));
+            *u = ub + t * den;
+            *jac = den * den;
+        } else {                              /* :118-120 */
+            double den = 1.0 / (1.0 - flipsign(t, ub));
+            *u = lb + t * den;
+            *jac = den * den;
+        }
+        return;
+    }
+    if (tr == ORC_TR_COT && !il && iu) {      /* :338-351 */
+        double arg = ORC_HALF_PI * (1.0 - t);
+        double c = 1.0 / tan(arg);            /* Julia: cot(x) = inv(tan(x)) */
+        double csc2 = 1.0 + c * c;
+        *u = lb + c;
+        *jac = ORC_HALF_PI * csc2;
+        return;
+    }
+    /* tan map (:203-232) -- also what the cot transform uses for the other two cases (:314-337) */
+    {
+        double arg = ORC_HALF_PI * t;
+        double tv = tan(arg);
+        double sec2 = 1.0 + tv * tv;
+        double base = (il && iu) ? 0.0 : (il ? ub : lb);
+        *u = (il && iu) ? tv : base + tv;
+        *jac = ORC_HALF_PI * sec2;
+    }
+}
+
+/* infinity_handling.jl:11-25: u,jac per coordinate; jac = prod left to right; f(u,p)*jac */
+double orc_cov_eval(const double *t, int dim, void *vc)
+{
+    const orc_cov *c = (const orc_cov *)vc;
+    double u[ORC_MAXDIM], jac = 1.0;
+    for (int i = 0; i < dim; i++) {
+        double ji;
+        orc_t2ujac(c->tr, t[i], c->lb[i], c->ub[i], &u[i], &ji);
+        jac = (i == 0) ? ji : jac * ji;
+    }
+    return c->f(u, dim, c->user) * jac;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Fixed rules -- src/quadrules.jl:1-19 and ext/IntegralsFastGaussQuadratureExt.jl:11-32
+ * ------------------------------------------------------------------------------------------ */
+double orc_evalrule(orc_integrand f, void *user, int dim, const double *lb, const double *ub,
+                    const double *nodes, const double *weights, int64_t N)
+{
+    double scale[ORC_MAXDIM], shift[ORC_MAXDIM], x[ORC_MAXDIM];
+    for (int k = 0; k < dim; k++) { scale[k] = (ub[k] - lb[k]) / 2; shift[k] = (lb[k] + ub[k]) / 2; }
+    if (N <= 0) return NAN; /* reference throws ArgumentError("empty quadrature rule") */
+    double I = 0.0;
+    for (int64_t i = 0; i < N; i++) {
+        for (int k = 0; k < dim; k++) x[k] = scale[k] * nodes[i * dim + k] + shift[k];
+        double v = weights[i] * f(x, dim, user);
+        I = (i == 0) ? v : I + v;
+    }
+    double ps = scale[0];
+    for (int k = 1; k < dim; k++) ps *= scale[k];
+    return ps * I;
+}
+
+double orc_evalrule_tensor(orc_integrand f, void *user, int dim, const double *lb, const double *ub,
+                           const double *x1d, const double *w1d, int n1d)
+{
+    double scale[ORC_MAXDIM], shift[ORC_MAXDIM], x[ORC_MAXDIM];
+    int idx[ORC_MAXDIM];
+    for (int k = 0; k < dim; k++) { scale[k] = (ub[k] - lb[k]) / 2; shift[k] = (lb[k] + ub[k]) / 2; idx[k] = 0; }
+    if (n1d <= 0) return NAN;
+    double I = 0.0; int first = 1;
+    for (;;) {
+        double w = w1d[idx[0]];
+        for (int k = 1; k < dim; k++) w *= w1d[idx[k]];
+        for (int k = 0; k < dim; k++) x[k] = scale[k] * x1d[idx[k]] + shift[k];
+        double v = w * f(x, dim, user);
+        I = first ? v : I + v; first = 0;
+        int k = 0;
+        while (k < dim && ++idx[k] == n1d) { idx[k] = 0; k++; }
+        if (k == dim) break;
+    }
+    double ps = scale[0];
+    for (int k = 1; k < dim; k++) ps *= scale[k];
+    return ps * I;
+}
+
+double orc_gauss_legendre(orc_integrand f, void *user, double lb, double ub,
+                          const double *nodes, const double *weights, int n)
+{
+    double scale = (ub - lb) / 2, shift = (lb + ub) / 2, x;
+    x = scale * nodes[0] + shift;
+    double I = weights[0] * f(&x, 1, user);
+    for (int i = 1; i < n; i++) {
+        x = scale * nodes[i] + shift;
+        I += weights[i] * f(&x, 1, user);
+    }
+    return scale * I;
+}
+
+double orc_composite_gauss_legendre(orc_integrand f, void *user, double lb, double ub,
+                                    const double *nodes, const double *weights, int n, int subintervals)
+{
+    double h = (ub - lb) / subintervals;
+    double I = orc_gauss_legendre(f, user, lb, lb + h, nodes, weights, n);
+    for (int i = 1; i < subintervals; i++) {
+        double _lb = lb + i * h, _ub = _lb + h;
+        I += orc_gauss_legendre(f, user, _lb, _ub, nodes, weights, n);
+    }
+    return I;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Sampled rules -- src/trapezoidal.jl, src/simpsons.jl, src/sampled.jl   (i is 1-based)
+ * ------------------------------------------------------------------------------------------ */
+double orc_trap_uniform_w(int64_t n, double h, int64_t i)      /* trapezoidal.jl:16-20 */
+{
+    return (i == 1 || i == n) ? h / 2 : h;
+}
+double orc_trap_nonuniform_w(const double *x0, int64_t n, int64_t i) /* trapezoidal.jl:35-40 */
+{
+    const double *x = x0 - 1; /* 1-based view */
+    if (i == 1) return (x[i + 1] - x[i]) / 2;
+    if (i == n) return (x[i] - x[i - 1]) / 2;
+    return (x[i + 1] - x[i - 1]) / 2;
+}
+double orc_simpson_uniform_w(int64_t n, double h, int64_t i)   /* simpsons.jl:16-25 */
+{
+    if (i == 1 || i == n) return 17 * h / 48;
+    if (i == 2 || i == n - 1) return 59 * h / 48;
+    if (i == 3 || i == n - 2) return 43 * h / 48;
+    if (i == 4 || i == n - 3) return 49 * h / 48;
+    return h;
+}
+static inline double cube(double v) { return v * v * v; } /* Julia x^3 -> x*x*x */
+double orc_simpson_nonuniform_w(const double *x0, int64_t n, int64_t i) /* simpsons.jl:40-82 */
+{
+    /* B(k) = x[begin+k]; E(k) = x[end-k] */
+#define B(k) x0[(k)]
+#define E(k) x0[n - 1 - (k)]
+    int64_t j = i - 1;
+    if (i == 1)
+        return (B(2) - B(0)) / 6 * (2 - (B(2) - B(1)) / (B(1) - B(0)));
+    if (n & 1) { /* even number of subintervals */
+        if (i == n)
+            return (E(0) - E(2)) / 6 * (2 - (E(1) - E(2)) / (E(0) - E(1)));
+    } else {
+        if (i == n)
+            return (E(0) - E(1)) * (2 * (E(0) - E(1)) + 3 * (E(1) - E(2))) / (E(0) - E(2)) / 6;
+        if (i == n - 1)
+            return (E(1) - E(3)) / 6 * (2 - (E(2) - E(3)) / (E(1) - E(2))) +
+                   (E(0) - E(1)) * ((E(0) - E(1)) + 3 * (E(1) - E(2))) / (E(1) - E(2)) / 6;
+        if (i == n - 2)
+            return cube(E(1) - E(3)) / (E(2) - E(3)) / (E(1) - E(2)) / 6 -
+                   cube(E(0) - E(1)) / (E(1) - E(2)) / (E(0) - E(2)) / 6;
+    }
+    if (j & 1)
+        return cube(B(j + 1) - B(j - 1)) / (B(j) - B(j - 1)) / (B(j + 1) - B(j)) / 6;
+    return (B(j) - B(j - 2)) / 6 * (2 - (B(j - 1) - B(j - 2)) / (B(j) - B(j - 1))) +
+           (B(j + 2) - B(j)) / 6 * (2 - (B(j + 2) - B(j + 1)) / (B(j + 1) - B(j)));
+#undef B
+#undef E
+}
+
+int orc_sampled_weights(int rule, int64_t n, double h, const double *x, double *w)
+{
+    if (rule != 0 && rule != 1) return -1;
+    if (x && rule == 1 && n <= 2) return -2; /* simpsons.jl:46 assertion */
+    if (x && rule == 0 && n < 2) return -2;
+    for (int64_t i = 1; i <= n; i++) {
+        if (!x) w[i - 1] = rule == 0 ? orc_trap_uniform_w(n, h, i) : orc_simpson_uniform_w(n, h, i);
+        else    w[i - 1] = rule == 0 ? orc_trap_nonuniform_w(x, n, i) : orc_simpson_nonuniform_w(x, n, i);
+    }
+    return 0;
+}
+
+/* sampled.jl:51-64 (vector), :68-96 (matrix, dim = last), :103-124 (general): always
+   out = w1*f1 then out += wi*fi in increasing i, separate multiply and add. */
+int orc_sampled_evalrule(int rule, const double *y, int64_t inner, int64_t n, int64_t outer,
+                         double h, const double *x, double *out, int nthreads)
+{
+    if (n == 0) return -3; /* ArgumentError("No points to integrate") */
+    double *w = (double *)malloc(sizeof(double) * (size_t)n);
+    if (!w) return -4;
+    int rc = orc_sampled_weights(rule, n, h, x, w);
+    if (rc) { free(w); return rc; }
+    if (nthreads < 1) nthreads = 1;
+    /* each (o, block of inner) is independent; order within every output is sequential in i */
+    const int64_t BLK = 512;
+    int64_t nblk = (inner + BLK - 1) / BLK;
+#pragma omp parallel for collapse(2) schedule(static) num_threads(nthreads)
+    for (int64_t o = 0; o < outer; o++) {
+        for (int64_t b = 0; b < nblk; b++) {
+            int64_t j0 = b * BLK, j1 = j0 + BLK < inner ? j0 + BLK : inner;
+            const double *yo = y + o * n * inner;
+            double *oo = out + o * inner;
+            for (int64_t j = j0; j < j1; j++) oo[j] = w[0] * yo[j];
+            for (int64_t i = 1; i < n; i++) {
+                double wi = w[i];
+                const double *yi = yo + i * inner;
+                for (int64_t j = j0; j < j1; j++) oo[j] += wi * yi[j];
+            }
+        }
+    }
+    free(w);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * QuadGK.jl (un-vendored dependency; compat "2.11", Project.toml:65), called at
+ * src/Integrals.jl:327-335 with order = 7.  Restated from the package's published algorithm
+ * (SURVEY Appendix A.1): Kronrod table = QUADPACK qk15 constants.
+ * ------------------------------------------------------------------------------------------ */
+static const double GK_X[8] = {
+    -0.991455371120812639206854697526329, -0.949107912342758524526189684047851,
+    -0.864864423359769072789712788640926, -0.741531185599394439863864773280788,
+    -0.586087235467691130294144838258730, -0.405845151377397166906606412076961,
+    -0.207784955007898467600689403773245, 0.0};
+static const double GK_W[8] = {
+    0.022935322010529224963732008058970, 0.063092092629978553290700663189204,
+    0.104790010322250183839876322541518, 0.140653259715525918745189590510238,
+    0.169004726639267902826583426598550, 0.190350578064785409913256402421014,
+    0.204432940075298892414161999234649, 0.209482141084727828012999174891714};
+static const double GK_WG[4] = {
+    0.129484966168869693270611432679082, 0.279705391489276667901467771423780,
+    0.381830050505118944950369775488975, 0.417959183673469387755102040816327};
+
+typedef struct { double a, b, I, E; } orc_seg;
+
+static inline double f1d(orc_integrand f, void *user, double x) { return f(&x, 1, user); }
+
+/* QuadGK evalrule (n = 7, odd): symmetric pairs are added before weighting */
+static orc_seg gk_evalrule(orc_integrand f, void *user, double a, double b)
+{
+    /* X(i), W(i), WG(i): 1-based like the Julia source */
+#define X(i) GK_X[(i) - 1]
+#define W(i) GK_W[(i) - 1]
+#define WG(i) GK_WG[(i) - 1]
+    double s = 0.5 * (b - a);
+    double fg = f1d(f, user, a + (1 + X(2)) * s) + f1d(f, user, a + (1 - X(2)) * s);
+    double fk = f1d(f, user, a + (1 + X(1)) * s) + f1d(f, user, a + (1 - X(1)) * s);
+    double Ig = fg * WG(1);
+    double Ik = fg * W(2) + fk * W(1);
+    for (int i = 2; i <= 3; i++) {
+        fg = f1d(f, user, a + (1 + X(2 * i)) * s) + f1d(f, user, a + (1 - X(2 * i)) * s);
+        fk = f1d(f, user, a + (1 + X(2 * i - 1)) * s) + f1d(f, user, a + (1 - X(2 * i - 1)) * s);
+        Ig += fg * WG(i);
+        Ik += fg * W(2 * i) + fk * W(2 * i - 1);
+    }
+    double f0 = f1d(f, user, a + s);
+    Ig += f0 * WG(4);
+    Ik += f0 * W(8) + (f1d(f, user, a + (1 + X(7)) * s) + f1d(f, user, a + (1 - X(7)) * s)) * W(7);
+#undef X
+#undef W
+#undef WG
+    orc_seg r;
+    r.a = a; r.b = b; r.I = Ik * s; r.E = fabs(Ik * s - Ig * s);
+    return r;
+}
+
+void orc_gk15(orc_integrand f, void *user, double a, double b, double *I, double *E)
+{
+    orc_seg s = gk_evalrule(f, user, a, b);
+    *I = s.I; *E = s.E;
+}
+
+/* binary max-heap on E with the DataStructures.jl/QuadGK percolate semantics (1-based) */
+static void seg_percolate_down(orc_seg *xs, int64_t i, orc_seg x, int64_t len)
+{
+    int64_t l;
+    while ((l = 2 * i) <= len) {
+        int64_t r = l + 1;
+        int64_t j = (r > len || xs[l].E > xs[r].E) ? l : r;
+        if (!(xs[j].E > x.E)) break;
+        xs[i] = xs[j];
+        i = j;
+    }
+    xs[i] = x;
+}
+static void seg_percolate_up(orc_seg *xs, int64_t i, orc_seg x)
+{
+    int64_t j;
+    while ((j = i / 2) >= 1 && x.E > xs[j].E) { xs[i] = xs[j]; i = j; }
+    xs[i] = x;
+}
+
+static int gk_endpoint_roundoff(double a, double b)
+{
+    double c = 0.5 * (b - a);
+    int at_a = (a == a + (1 + GK_X[0]) * c);
+    int at_b = (b == a + (1 - GK_X[0]) * c);
+    return at_a || at_b;
+}
+
+int orc_quadgk(orc_integrand f, void *user, double a, double b, double rtol, double atol,
+               int64_t maxevals, double *Iout, double *Eout, int64_t *nevals_out, int64_t *nsegs_out)
+{
+    int status = 0;
+    orc_seg s0 = gk_evalrule(f, user, a, b);
+    double I = s0.I, E = s0.E;
+    int64_t numevals = 15, cap = 64, len = 1;
+    if (rtol == 0 && atol == 0) rtol = sqrt(2.220446049250313e-16);
+    if (isnan(E) || isinf(E)) { *Iout = I; *Eout = E; if (nevals_out) *nevals_out = numevals; if (nsegs_out) *nsegs_out = 1; return 2; }
+    if (numevals >= maxevals || E <= atol || E <= rtol * fabs(I)) {
+        *Iout = I; *Eout = E;
+        if (nevals_out) *nevals_out = numevals;
+        if (nsegs_out) *nsegs_out = 1;
+        return (E <= atol || E <= rtol * fabs(I)) ? 0 : 1;
+    }
+    orc_seg *segs = (orc_seg *)malloc(sizeof(orc_seg) * (size_t)(cap + 1)); /* 1-based */
+    segs[1] = s0;
+    while (E > atol && E > rtol * fabs(I) && numevals < maxevals) {
+        /* refine(): pop the biggest-error segment and bisect */
+        orc_seg s = segs[1];
+        orc_seg y = segs[len--];
+        if (len >= 1) seg_percolate_down(segs, 1, y, len);
+        double mid = (s.a + s.b) / 2;
+        if (gk_endpoint_roundoff(s.a, mid) || gk_endpoint_roundoff(mid, s.b)) {
+            len++; seg_percolate_up(segs, len, s);
+            status = 3;
+            break;
+        }
+        orc_seg s1 = gk_evalrule(f, user, s.a, mid);
+        orc_seg s2 = gk_evalrule(f, user, mid, s.b);
+        I = (I - s.I) + s1.I + s2.I;
+        E = (E - s.E) + s1.E + s2.E;
+        numevals += 30;
+        if (isnan(s1.E) || isinf(s1.E) || isnan(s2.E) || isinf(s2.E)) status = 2;
+        if (len + 2 > cap) { cap *= 2; segs = (orc_seg *)realloc(segs, sizeof(orc_seg) * (size_t)(cap + 1)); }
+        len++; seg_percolate_up(segs, len, s1);
+        len++; seg_percolate_up(segs, len, s2);
+        if (status == 2) break;
+    }
+    /* resum(): storage order */
+    I = segs[1].I; E = segs[1].E;
+    for (int64_t i = 2; i <= len; i++) { I += segs[i].I; E += segs[i].E; }
+    free(segs);
+    if (status == 0 && !(E <= atol || E <= rtol * fabs(I)) && numevals >= maxevals) status = 1;
+    *Iout = I; *Eout = E;
+    if (nevals_out) *nevals_out = numevals;
+    if (nsegs_out) *nsegs_out = len;
+    return status;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * HCubature.jl (un-vendored dependency; compat "1.7", Project.toml:60), called at
+ * src/Integrals.jl:380-393.  Restated from the published algorithm:
+ * Genz-Malik degree-7 rule with embedded degree-5 rule for dim>=2, GK(7,15) for dim==1,
+ * binary max-heap of boxes, bisection along the largest fourth difference.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct { double a[ORC_MAXDIM], b[ORC_MAXDIM], I, E; int kdiv; } orc_box;
+
+static void gm_rule(orc_integrand f, void *user, int n, const double *a, const double *b,
+                    double *Iout, double *Eout, int *kdiv_out)
+{
+    const double l2 = sqrt(9.0 / 70.0), l3 = sqrt(9.0 / 10.0), l4 = l3, l5 = sqrt(9.0 / 19.0);
+    const double twon = (double)(1 << n);
+    const double w1 = twon * ((12824 - 9120 * n + 400 * n * n) / 19683.0);
+    const double w2 = twon * (980 / 6561.0);
+    const double w3 = twon * ((1820 - 400 * n) / 19683.0);
+    const double w4 = twon * (200 / 19683.0);
+    const double w5 = 6859 / 19683.0;
+    const double w4p = twon * (25 / 729.0);
+    const double w3p = twon * ((265 - 100 * n) / 1458.0);
+    const double w2p = twon * (245 / 486.0);
+    const double w1p = twon * ((729 - 950 * n + 50 * n * n) / 729.0);
+
+    double c[ORC_MAXDIM], d[ORC_MAXDIM], x[ORC_MAXDIM], divdiff[ORC_MAXDIM];
+    double V = 1.0;
+    for (int i = 0; i < n; i++) {
+        c[i] = 0.5 * (a[i] + b[i]);
+        d[i] = 0.5 * fabs(b[i] - a[i]);
+        V = (i == 0) ? d[i] : V * d[i];
+    }
+    for (int i = 0; i < n; i++) x[i] = c[i];
+    double f1 = f(x, n, user), f2 = 0.0, f3 = 0.0;
+    double twelvef1 = 12 * f1;
+    for (int i = 0; i < n; i++) {
+        double p2 = d[i] * l2, p3 = d[i] * l3;
+        x[i] = c[i] + p2; double fa = f(x, n, user);
+        x[i] = c[i] - p2; double f2i = fa + f(x, n, user);
+        x[i] = c[i] + p3; fa = f(x, n, user);
+        x[i] = c[i] - p3; double f3i = fa + f(x, n, user);
+        x[i] = c[i];
+        f2 += f2i; f3 += f3i;
+        divdiff[i] = fabs(f3i + twelvef1 - 7 * f2i);
+    }
+    double f4 = 0.0;
+    for (int i = 0; i < n - 1; i++)
+        for (int j = i + 1; j < n; j++) {
+            double pi_ = d[i] * l4, pj = d[j] * l4;
+            for (int s = 0; s < 4; s++) {
+                x[i] = (s & 2) ? c[i] - pi_ : c[i] + pi_;
+                x[j] = (s & 1) ? c[j] - pj : c[j] + pj;
+                f4 += f(x, n, user);
+            }
+            x[i] = c[i]; x[j] = c[j];
+        }
+    double f5 = 0.0;
+    for (int s = 0; s < (1 << n); s++) {
+        for (int i = 0; i < n; i++) {
+            double p = d[i] * l5;
+            x[i] = ((s >> i) & 1) ? c[i] - p : c[i] + p;
+        }
+        f5 += f(x, n, user);
+    }
+    double I = V * (w1 * f1 + w2 * f2 + w3 * f3 + w4 * f4 + w5 * f5);
+    double Ip = V * (w1p * f1 + w2p * f2 + w3p * f3 + w4p * f4);
+    double E = fabs(I - Ip);
+    int kdiv = 0;
+    double maxdivdiff = 0.0;
+    double deltaf = E / (pow(10.0, n) * V);
+    for (int i = 0; i < n; i++) {
+        double delta = divdiff[i] - maxdivdiff;
+        if (delta > deltaf) { kdiv = i; maxdivdiff = divdiff[i]; }
+        else if (fabs(delta) <= deltaf && d[i] > d[kdiv]) kdiv = i;
+    }
+    *Iout = I; *Eout = E; *kdiv_out = kdiv;
+}
+
+/* HCubature's 1-D rule: GK(7,15) about the centre, signed half-width */
+static void gk_rule_hc(orc_integrand f, void *user, double a, double b, double *Iout, double *Eout, int *kdiv)
+{
+    double c = (a + b) * 0.5, D = (b - a) * 0.5;
+    double fx0 = f1d(f, user, c);
+    double I = fx0 * GK_W[7], Ip = fx0 * GK_WG[3];
+    for (int i = 1; i <= 7; i++) {
+        double Dx = D * GK_X[i - 1];
+        double fx = f1d(f, user, c + Dx) + f1d(f, user, c - Dx);
+        I += fx * GK_W[i - 1];
+        if ((i & 1) == 0) Ip += fx * GK_WG[(i >> 1) - 1];
+    }
+    I *= D; Ip *= D;
+    *Iout = I; *Eout = fabs(I - Ip); *kdiv = 0;
+}
+
+void orc_cubrule(orc_integrand f, void *user, int dim, const double *a, const double *b,
+                 double *I, double *E, int *kdiv)
+{
+    if (dim == 1) gk_rule_hc(f, user, a[0], b[0], I, E, kdiv);
+    else gm_rule(f, user, dim, a, b, I, E, kdiv);
+}
+
+/* DataStructures.jl BinaryMaxHeap bubble semantics (1-based valtree) */
+static void box_bubble_up(orc_box *t, int64_t i)
+{
+    orc_box v = t[i];
+    while (i > 1) {
+        int64_t p = i >> 1;
+        if (!(v.E > t[p].E)) break;
+        t[i] = t[p]; i = p;
+    }
+    t[i] = v;
+}
+static void box_bubble_down(orc_box *t, int64_t i, int64_t n)
+{
+    orc_box v = t[i];
+    int swapped = 1;
+    int64_t last_parent = n >> 1;
+    while (swapped && i <= last_parent) {
+        int64_t lc = i << 1;
+        if (lc < n) {
+            int64_t rc = lc + 1;
+            if (t[rc].E > t[lc].E) {
+                if (t[rc].E > v.E) { t[i] = t[rc]; i = rc; } else swapped = 0;
+            } else {
+                if (t[lc].E > v.E) { t[i] = t[lc]; i = lc; } else swapped = 0;
+            }
+        } else {
+            if (t[lc].E > v.E) { t[i] = t[lc]; i = lc; } else swapped = 0;
+        }
+    }
+    t[i] = v;
+}
+
+int orc_hcubature(orc_integrand f, void *user, int dim, const double *a, const double *b,
+                  double rtol, double atol, int64_t maxevals, int initdiv,
+                  double *Iout, double *Eout, int64_t *nevals_out, int64_t *nboxes_out)
+{
+    if (dim < 1 || dim > ORC_MAXDIM || initdiv < 1 || rtol < 0 || atol < 0 || maxevals < 0) return -1;
+    if (rtol == 0 && atol == 0) rtol = sqrt(2.220446049250313e-16);
+    const int64_t evals_per_box = dim == 1 ? 15 : 1 + 4 * dim + 2 * dim * (dim - 1) + (1 << dim);
+    int64_t numevals = evals_per_box, cap = 256, len = 0;
+    double Delta[ORC_MAXDIM];
+    orc_box first;
+    double prodD = 1.0;
+    for (int i = 0; i < dim; i++) {
+        Delta[i] = (b[i] - a[i]) / initdiv;
+        prodD *= Delta[i];
+        first.a[i] = a[i];
+        first.b[i] = initdiv == 1 ? b[i] : a[i] + Delta[i];
+    }
+    orc_cubrule(f, user, dim, first.a, first.b, &first.I, &first.E, &first.kdiv);
+    double I = first.I, E = first.E;
+    if (prodD == 0.0) { *Iout = I; *Eout = E; if (nevals_out) *nevals_out = numevals; if (nboxes_out) *nboxes_out = 1; return 0; }
+    orc_box *t = (orc_box *)malloc(sizeof(orc_box) * (size_t)(cap + 1));
+    t[++len] = first;
+    if (initdiv > 1) {
+        int c[ORC_MAXDIM] = {0};
+        int64_t total = 1;
+        for (int i = 0; i < dim; i++) total *= initdiv;
+        for (int64_t q = 1; q < total; q++) { /* CartesianIndices order, first index fastest; skip the first box */
+            int k = 0;
+            while (++c[k] == initdiv) { c[k] = 0; k++; }
+            orc_box bx;
+            for (int i = 0; i < dim; i++) {
+                bx.a[i] = a[i] + c[i] * Delta[i];
+                bx.b[i] = (c[i] == initdiv - 1) ? b[i] : bx.a[i] + Delta[i];
+            }
+            orc_cubrule(f, user, dim, bx.a, bx.b, &bx.I, &bx.E, &bx.kdiv);
+            I += bx.I; E += bx.E; numevals += evals_per_box;
+            if (len + 1 > cap) { cap *= 2; t = (orc_box *)realloc(t, sizeof(orc_box) * (size_t)(cap + 1)); }
+            t[++len] = bx; box_bubble_up(t, len);
+        }
+    }
+    int status = 0;
+    for (;;) {
+        if (E <= fmax(rtol * fabs(I), atol)) break;
+        if (numevals >= maxevals) { status = 1; break; }
+        if (!isfinite(E)) { status = 2; break; }
+        /* pop the box with the largest error */
+        orc_box box = t[1];
+        if (len == 1) len = 0;
+        else { t[1] = t[len--]; box_bubble_down(t, 1, len); }
+        int k = box.kdiv;
+        double w = (box.b[k] - box.a[k]) * 0.5;
+        orc_box b1 = box, b2 = box;
+        b1.a[k] = box.a[k] + w;            /* upper half first */
+        orc_cubrule(f, user, dim, b1.a, b1.b, &b1.I, &b1.E, &b1.kdiv);
+        b2.b[k] = box.b[k] - w;
+        orc_cubrule(f, user, dim, b2.a, b2.b, &b2.I, &b2.E, &b2.kdiv);
+        numevals += 2 * evals_per_box;
+        I += b1.I + b2.I - box.I;
+        E += b1.E + b2.E - box.E;
+        if (len + 2 > cap) { cap *= 2; t = (orc_box *)realloc(t, sizeof(orc_box) * (size_t)(cap + 1)); }
+        t[++len] = b1; box_bubble_up(t, len);
+        t[++len] = b2; box_bubble_up(t, len);
+    }
+    /* roundoff paranoia: re-sum in storage order */
+    I = 0.0; E = 0.0;
+    for (int64_t i = 1; i <= len; i++) { I += t[i].I; E += t[i].E; }
+    free(t);
+    *Iout = I; *Eout = E;
+    if (nevals_out) *nevals_out = numevals;
+    if (nboxes_out) *nboxes_out = len;
+    return status;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Integrals.jl-level solves: init wraps every tuple-domain alg in
+ * ChangeOfVariables(transformation_if_inf, alg) (src/common.jl:97-103); __solve maps the
+ * domain with u2t and the integrand with t2ujac (src/Integrals.jl:192-224,
+ * src/infinity_handling.jl:165-170) and re-dispatches to the back-end.
+ * ------------------------------------------------------------------------------------------ */
+int orc_solve_quadgk(orc_integrand f, void *user, double lb, double ub, int tr,
+                     double reltol, double abstol, int64_t maxiters,
+                     double *I, double *E, int64_t *nevals)
+{
+    orc_cov c = {f, user, 1, tr, &lb, &ub};
+    double tl, tu;
+    orc_u2t(lb, ub, &tl, &tu);
+    return orc_quadgk(orc_cov_eval, &c, tl, tu, reltol, abstol, maxiters, I, E, nevals, NULL);
+}
+
+int orc_solve_hcubature(orc_integrand f, void *user, int dim, const double *lb, const double *ub, int tr,
+                        double reltol, double abstol, int64_t maxiters, int initdiv,
+                        double *I, double *E, int64_t *nevals)
+{
+    orc_cov c = {f, user, dim, tr, lb, ub};
+    double tl[ORC_MAXDIM], tu[ORC_MAXDIM];
+    for (int i = 0; i < dim; i++) orc_u2t(lb[i], ub[i], &tl[i], &tu[i]);
+    return orc_hcubature(orc_cov_eval, &c, dim, tl, tu, reltol, abstol, maxiters, initdiv, I, E, nevals, NULL);
+}
+
+double orc_solve_quadrule(orc_integrand f, void *user, int dim, const double *lb, const double *ub, int tr,
+                          const double *nodes, const double *weights, int64_t N)
+{
+    orc_cov c = {f, user, dim, tr, lb, ub};
+    double tl[ORC_MAXDIM], tu[ORC_MAXDIM];
+    for (int i = 0; i < dim; i++) orc_u2t(lb[i], ub[i], &tl[i], &tu[i]);
+    return orc_evalrule(orc_cov_eval, &c, dim, tl, tu, nodes, weights, N);
+}
+
+double orc_solve_quadrule_tensor(orc_integrand f, void *user, int dim, const double *lb, const double *ub, int tr,
+                                 const double *x1d, const double *w1d, int n1d)
+{
+    orc_cov c = {f, user, dim, tr, lb, ub};
+    double tl[ORC_MAXDIM], tu[ORC_MAXDIM];
+    for (int i = 0; i < dim; i++) orc_u2t(lb[i], ub[i], &tl[i], &tu[i]);
+    return orc_evalrule_tensor(orc_cov_eval, &c, dim, tl, tu, x1d, w1d, n1d);
+}
+
+double orc_solve_gauss_legendre(orc_integrand f, void *user, double lb, double ub, int tr,
+                                const double *nodes, const double *weights, int n, int subintervals)
+{
+    orc_cov c = {f, user, 1, tr, &lb, &ub};
+    double tl, tu;
+    orc_u2t(lb, ub, &tl, &tu);
+    /* ext/IntegralsFastGaussQuadratureExt.jl:47-71: composite iff the alg was built with subintervals>1 */
+    if (subintervals > 1) return orc_composite_gauss_legendre(orc_cov_eval, &c, tl, tu, nodes, weights, n, subintervals);
+    return orc_gauss_legendre(orc_cov_eval, &c, tl, tu, nodes, weights, n);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Batch drivers (CPU baseline): a threaded loop of independent solve() calls, the stand-in
+ * for `Threads.@threads for k: solve(remake(prob, p = ps[:,k]), alg)`.
+ * ------------------------------------------------------------------------------------------ */
+int orc_max_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+int orc_quadgk_batch(int fam, const double *lb, const double *ub, int bpp, int tr,
+                     const double *params, int nparam, int64_t nprob,
+                     double reltol, double abstol, int64_t maxiters,
+                     double *I, double *E, int64_t *nevals, int32_t *status, int nthreads)
+{
+    if (orc_family_nparam(fam, 1) != nparam) return -1;
+    if (nthreads < 1) nthreads = 1;
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads)
+    for (int64_t k = 0; k < nprob; k++) {
+        orc_family_user fu = {fam, 1, params + k * nparam};
+        double l = bpp ? lb[k] : lb[0], u = bpp ? ub[k] : ub[0];
+        int64_t ne = 0;
+        int st = orc_solve_quadgk(orc_family_integrand, &fu, l, u, tr, reltol, abstol, maxiters, &I[k], &E[k], &ne);
+        if (nevals) nevals[k] = ne;
+        if (status) status[k] = st;
+    }
+    return 0;
+}
+
+int orc_hcubature_batch(int fam, int dim, const double *lb, const double *ub, int bpp, int tr,
+                        const double *params, int nparam, int64_t nprob,
+                        double reltol, double abstol, int64_t maxiters, int initdiv,
+                        double *I, double *E, int64_t *nevals, int32_t *status, int nthreads)
+{
+    if (orc_family_nparam(fam, dim) != nparam) return -1;
+    if (nthreads < 1) nthreads = 1;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+    for (int64_t k = 0; k < nprob; k++) {
+        orc_family_user fu = {fam, dim, params + k * nparam};
+        const double *l = bpp ? lb + k * dim : lb, *u = bpp ? ub + k * dim : ub;
+        int64_t ne = 0;
+        int st = orc_solve_hcubature(orc_family_integrand, &fu, dim, l, u, tr, reltol, abstol, maxiters, initdiv, &I[k], &E[k], &ne);
+        if (nevals) nevals[k] = ne;
+        if (status) status[k] = st;
+    }
+    return 0;
+}
+
+int orc_fixed_tensor_batch(int fam, int dim, const double *lb, const double *ub, int bpp, int tr,
+                           const double *params, int nparam, int64_t nprob,
+                           const double *x1d, const double *w1d, int n1d, double *I, int nthreads)
+{
+    if (orc_family_nparam(fam, dim) != nparam) return -1;
+    if (nthreads < 1) nthreads = 1;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+    for (int64_t k = 0; k < nprob; k++) {
+        orc_family_user fu = {fam, dim, params + k * nparam};
+        const double *l = bpp ? lb + k * dim : lb, *u = bpp ? ub + k * dim : ub;
+        I[k] = orc_solve_quadrule_tensor(orc_family_integrand, &fu, dim, l, u, tr, x1d, w1d, n1d);
+    }
+    return 0;
+}
+
+int orc_fixed_nodes_batch(int fam, int dim, const double *lb, const double *ub, int bpp, int tr,
+                          const double *params, int nparam, int64_t nprob,
+                          const double *nodes, const double *weights, int64_t N, double *I, int nthreads)
+{
+    if (orc_family_nparam(fam, dim) != nparam) return -1;
+    if (nthreads < 1) nthreads = 1;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+    for (int64_t k = 0; k < nprob; k++) {
+        orc_family_user fu = {fam, dim, params + k * nparam};
+        const double *l = bpp ? lb + k * dim : lb, *u = bpp ? ub + k * dim : ub;
+        I[k] = orc_solve_quadrule(orc_family_integrand, &fu, dim, l, u, tr, nodes, weights, N);
+    }
+    return 0;
+}
+
+int orc_gauss_legendre_batch(int fam, const double *lb, const double *ub, int bpp, int tr,
+                             const double *params, int nparam, int64_t nprob,
+                             const double *nodes, const double *weights, int n, int subintervals,
+                             double *I, int nthreads)
+{
+    if (orc_family_nparam(fam, 1) != nparam) return -1;
+    if (nthreads < 1) nthreads = 1;
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads)
+    for (int64_t k = 0; k < nprob; k++) {
+        orc_family_user fu = {fam, 1, params + k * nparam};
+        double l = bpp ? lb[k] : lb[0], u = bpp ? ub[k] : ub[0];
+        I[k] = orc_solve_gauss_legendre(orc_family_integrand, &fu, l, u, tr, nodes, weights, n, subintervals);
+    }
+    return 0;
+}

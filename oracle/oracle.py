@@ -1,0 +1,295 @@
+"""ctypes binding of the C oracle (TEST INFRASTRUCTURE ONLY -- see oracle.h)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+FAM = dict(sinxp=0, osc=1, prodpeak=2, corner=3, gauss=4, c0=5, discont=6,
+           cosprod=7, gausspoly=8, explin=9, gltest=10)
+TR = dict(if_inf=0, tan=1, cot=2)
+
+_INTEGRAND = C.CFUNCTYPE(C.c_double, C.POINTER(C.c_double), C.c_int, C.c_void_p)
+_dp = C.POINTER(C.c_double)
+_i64p = C.POINTER(C.c_int64)
+_i32p = C.POINTER(C.c_int32)
+
+
+def build(force=False):
+    """Compile oracle/liboracle.so with the committed Makefile (gcc; a second or two)."""
+    so = os.path.join(_HERE, "liboracle.so")
+    src_m = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("oracle.c", "oracle.h", "Makefile"))
+    if force or not os.path.exists(so) or os.path.getmtime(so) < src_m:
+        subprocess.check_call(["make", "-C", _HERE, "-s"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        L.orc_family_eval.restype = C.c_double
+        L.orc_family_eval.argtypes = [C.c_int, C.c_int, _dp, _dp]
+        L.orc_family_nparam.restype = C.c_int
+        L.orc_trap_uniform_w.restype = C.c_double
+        L.orc_trap_uniform_w.argtypes = [C.c_int64, C.c_double, C.c_int64]
+        L.orc_simpson_uniform_w.restype = C.c_double
+        L.orc_simpson_uniform_w.argtypes = [C.c_int64, C.c_double, C.c_int64]
+        L.orc_trap_nonuniform_w.restype = C.c_double
+        L.orc_trap_nonuniform_w.argtypes = [_dp, C.c_int64, C.c_int64]
+        L.orc_simpson_nonuniform_w.restype = C.c_double
+        L.orc_simpson_nonuniform_w.argtypes = [_dp, C.c_int64, C.c_int64]
+        L.orc_sampled_weights.argtypes = [C.c_int, C.c_int64, C.c_double, _dp, _dp]
+        L.orc_sampled_evalrule.argtypes = [C.c_int, _dp, C.c_int64, C.c_int64, C.c_int64, C.c_double, _dp, _dp, C.c_int]
+        L.orc_evalrule.restype = C.c_double
+        L.orc_evalrule.argtypes = [_INTEGRAND, C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, C.c_int64]
+        L.orc_solve_quadrule.restype = C.c_double
+        L.orc_solve_quadrule.argtypes = [_INTEGRAND, C.c_void_p, C.c_int, _dp, _dp, C.c_int, _dp, _dp, C.c_int64]
+        L.orc_solve_quadrule_tensor.restype = C.c_double
+        L.orc_solve_quadrule_tensor.argtypes = [_INTEGRAND, C.c_void_p, C.c_int, _dp, _dp, C.c_int, _dp, _dp, C.c_int]
+        L.orc_solve_gauss_legendre.restype = C.c_double
+        L.orc_solve_gauss_legendre.argtypes = [_INTEGRAND, C.c_void_p, C.c_double, C.c_double, C.c_int, _dp, _dp, C.c_int, C.c_int]
+        L.orc_solve_quadgk.argtypes = [_INTEGRAND, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double,
+                                       C.c_int64, _dp, _dp, _i64p]
+        L.orc_solve_hcubature.argtypes = [_INTEGRAND, C.c_void_p, C.c_int, _dp, _dp, C.c_int, C.c_double, C.c_double,
+                                          C.c_int64, C.c_int, _dp, _dp, _i64p]
+        L.orc_quadgk.argtypes = [_INTEGRAND, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64,
+                                 _dp, _dp, _i64p, _i64p]
+        L.orc_hcubature.argtypes = [_INTEGRAND, C.c_void_p, C.c_int, _dp, _dp, C.c_double, C.c_double, C.c_int64,
+                                    C.c_int, _dp, _dp, _i64p, _i64p]
+        L.orc_cubrule.argtypes = [_INTEGRAND, C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, C.POINTER(C.c_int)]
+        L.orc_gk15.argtypes = [_INTEGRAND, C.c_void_p, C.c_double, C.c_double, _dp, _dp]
+        L.orc_u2t.argtypes = [C.c_double, C.c_double, _dp, _dp]
+        L.orc_t2ujac.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, _dp, _dp]
+        L.orc_quadgk_batch.argtypes = [C.c_int, _dp, _dp, C.c_int, C.c_int, _dp, C.c_int, C.c_int64, C.c_double,
+                                       C.c_double, C.c_int64, _dp, _dp, _i64p, _i32p, C.c_int]
+        L.orc_hcubature_batch.argtypes = [C.c_int, C.c_int, _dp, _dp, C.c_int, C.c_int, _dp, C.c_int, C.c_int64,
+                                          C.c_double, C.c_double, C.c_int64, C.c_int, _dp, _dp, _i64p, _i32p, C.c_int]
+        L.orc_fixed_tensor_batch.argtypes = [C.c_int, C.c_int, _dp, _dp, C.c_int, C.c_int, _dp, C.c_int, C.c_int64,
+                                             _dp, _dp, C.c_int, _dp, C.c_int]
+        L.orc_fixed_nodes_batch.argtypes = [C.c_int, C.c_int, _dp, _dp, C.c_int, C.c_int, _dp, C.c_int, C.c_int64,
+                                            _dp, _dp, C.c_int64, _dp, C.c_int]
+        L.orc_gauss_legendre_batch.argtypes = [C.c_int, _dp, _dp, C.c_int, C.c_int, _dp, C.c_int, C.c_int64,
+                                               _dp, _dp, C.c_int, C.c_int, _dp, C.c_int]
+        L.orc_max_threads.restype = C.c_int
+        _LIB = L
+    return _LIB
+
+
+def _arr(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _wrap(f):
+    """Python callable f(x: ndarray[dim]) -> float as a C integrand (1-D: x is a float)."""
+    def cb(xp, dim, _user):
+        x = np.ctypeslib.as_array(xp, shape=(dim,))
+        return float(f(x[0] if dim == 1 else x.copy()))
+    return _INTEGRAND(cb)
+
+
+def max_threads():
+    return lib().orc_max_threads()
+
+
+# ---- registered family ---------------------------------------------------------------------
+def family_nparam(fam, dim):
+    return lib().orc_family_nparam(FAM[fam] if isinstance(fam, str) else fam, dim)
+
+
+def family_eval(fam, x, par):
+    x = _arr(np.atleast_1d(x)); par = _arr(np.atleast_1d(par))
+    return lib().orc_family_eval(FAM[fam] if isinstance(fam, str) else fam, x.size, _p(x), _p(par))
+
+
+# ---- transforms ------------------------------------------------------------------------------
+def u2t(lb, ub):
+    a = C.c_double(); b = C.c_double()
+    lib().orc_u2t(lb, ub, C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+def t2ujac(tr, t, lb, ub):
+    a = C.c_double(); b = C.c_double()
+    lib().orc_t2ujac(TR[tr] if isinstance(tr, str) else tr, t, lb, ub, C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+# ---- sampled ---------------------------------------------------------------------------------
+def sampled_weights(rule, n, h=None, x=None):
+    """rule: 'trapezoid'|'simpson'.  x None -> uniform (n, h) like an AbstractRange grid."""
+    w = np.empty(n)
+    xx = None if x is None else _arr(x)
+    rc = lib().orc_sampled_weights(0 if rule.startswith("trap") else 1, n, 0.0 if h is None else h,
+                                   None if xx is None else _p(xx), _p(w))
+    if rc:
+        raise ValueError(f"orc_sampled_weights rc={rc}")
+    return w
+
+
+def sampled_evalrule(rule, y, x=None, h=None, dim=-1, nthreads=1):
+    """y: numpy array in *Julia column-major semantics* given as a Fortran-ordered array;
+    integrates along axis `dim` (0-based, default last).  Returns array without that axis."""
+    y = np.asfortranarray(y, dtype=np.float64)
+    dim = dim % y.ndim
+    n = y.shape[dim]
+    inner = int(np.prod(y.shape[:dim], dtype=np.int64))
+    outer = int(np.prod(y.shape[dim + 1:], dtype=np.int64))
+    out_shape = y.shape[:dim] + y.shape[dim + 1:]
+    out = np.empty(max(inner * outer, 1))
+    xx = None if x is None else _arr(x)
+    rc = lib().orc_sampled_evalrule(0 if rule.startswith("trap") else 1, y.ctypes.data_as(_dp), inner, n, outer,
+                                    0.0 if h is None else h, None if xx is None else _p(xx), _p(out), nthreads)
+    if rc == -3:
+        raise ValueError("No points to integrate")
+    if rc:
+        raise ValueError(f"orc_sampled_evalrule rc={rc}")
+    out = out[:inner * outer].reshape(out_shape, order="F")
+    return out if out.ndim else float(out)
+
+
+# ---- generic-callback solves (pin the oracle against the reference's own tests) --------------
+def _bounds(lb, ub):
+    lb = _arr(np.atleast_1d(lb)); ub = _arr(np.atleast_1d(ub))
+    return lb, ub, lb.size
+
+
+def solve_quadgk(f, lb, ub, tr="if_inf", reltol=1e-8, abstol=1e-8, maxiters=2**62):
+    cb = _wrap(f)
+    I = C.c_double(); E = C.c_double(); ne = C.c_int64()
+    st = lib().orc_solve_quadgk(cb, None, lb, ub, TR[tr], reltol, abstol, maxiters, C.byref(I), C.byref(E), C.byref(ne))
+    return I.value, E.value, ne.value, st
+
+
+def solve_hcubature(f, lb, ub, tr="if_inf", reltol=1e-8, abstol=1e-8, maxiters=2**62, initdiv=1):
+    cb = _wrap(f)
+    lb, ub, d = _bounds(lb, ub)
+    I = C.c_double(); E = C.c_double(); ne = C.c_int64()
+    st = lib().orc_solve_hcubature(cb, None, d, _p(lb), _p(ub), TR[tr], reltol, abstol, maxiters, initdiv,
+                                   C.byref(I), C.byref(E), C.byref(ne))
+    return I.value, E.value, ne.value, st
+
+
+def solve_quadrule(f, lb, ub, nodes, weights, tr="if_inf"):
+    cb = _wrap(f)
+    lb, ub, d = _bounds(lb, ub)
+    nodes = _arr(nodes).reshape(-1, d); weights = _arr(weights).ravel()
+    return lib().orc_solve_quadrule(cb, None, d, _p(lb), _p(ub), TR[tr], _p(nodes), _p(weights), weights.size)
+
+
+def solve_quadrule_tensor(f, lb, ub, x1d, w1d, tr="if_inf"):
+    cb = _wrap(f)
+    lb, ub, d = _bounds(lb, ub)
+    x1d = _arr(x1d); w1d = _arr(w1d)
+    return lib().orc_solve_quadrule_tensor(cb, None, d, _p(lb), _p(ub), TR[tr], _p(x1d), _p(w1d), x1d.size)
+
+
+def solve_gauss_legendre(f, lb, ub, nodes, weights, subintervals=1, tr="if_inf"):
+    cb = _wrap(f)
+    nodes = _arr(nodes); weights = _arr(weights)
+    return lib().orc_solve_gauss_legendre(cb, None, lb, ub, TR[tr], _p(nodes), _p(weights), nodes.size, subintervals)
+
+
+def quadgk(f, a, b, rtol=0.0, atol=0.0, maxevals=10**7):
+    """Bare QuadGK.quadgk (no change of variables)."""
+    cb = _wrap(f)
+    I = C.c_double(); E = C.c_double(); ne = C.c_int64(); ns = C.c_int64()
+    st = lib().orc_quadgk(cb, None, a, b, rtol, atol, maxevals, C.byref(I), C.byref(E), C.byref(ne), C.byref(ns))
+    return I.value, E.value, ne.value, ns.value, st
+
+
+def hcubature(f, a, b, rtol=0.0, atol=0.0, maxevals=2**62, initdiv=1):
+    """Bare HCubature.hcubature (no change of variables)."""
+    cb = _wrap(f)
+    a, b, d = _bounds(a, b)
+    I = C.c_double(); E = C.c_double(); ne = C.c_int64(); nb = C.c_int64()
+    st = lib().orc_hcubature(cb, None, d, _p(a), _p(b), rtol, atol, maxevals, initdiv,
+                             C.byref(I), C.byref(E), C.byref(ne), C.byref(nb))
+    return I.value, E.value, ne.value, nb.value, st
+
+
+def cubrule(f, a, b):
+    cb = _wrap(f)
+    a, b, d = _bounds(a, b)
+    I = C.c_double(); E = C.c_double(); k = C.c_int()
+    lib().orc_cubrule(cb, None, d, _p(a), _p(b), C.byref(I), C.byref(E), C.byref(k))
+    return I.value, E.value, k.value
+
+
+def gk15(f, a, b):
+    cb = _wrap(f)
+    I = C.c_double(); E = C.c_double()
+    lib().orc_gk15(cb, None, a, b, C.byref(I), C.byref(E))
+    return I.value, E.value
+
+
+# ---- batch drivers over the registered family (CPU baseline legs) ----------------------------
+def _batch_common(fam, dim, lb, ub, params):
+    fam = FAM[fam] if isinstance(fam, str) else fam
+    params = np.asfortranarray(params, dtype=np.float64)
+    if params.ndim == 1:
+        params = params.reshape(-1, 1, order="F")
+    nparam, nprob = params.shape
+    lb = np.asfortranarray(lb, dtype=np.float64); ub = np.asfortranarray(ub, dtype=np.float64)
+    bpp = 1 if lb.ndim == 2 or (dim == 1 and lb.ndim == 1 and lb.size == nprob and nprob > 1) else 0
+    return fam, params, nparam, nprob, lb, ub, bpp
+
+
+def quadgk_batch(fam, lb, ub, params, tr="if_inf", reltol=1e-8, abstol=1e-8, maxiters=2**62, nthreads=1):
+    fam, params, nparam, nprob, lb, ub, bpp = _batch_common(fam, 1, np.atleast_1d(lb), np.atleast_1d(ub), params)
+    I = np.empty(nprob); E = np.empty(nprob); ne = np.empty(nprob, np.int64); st = np.empty(nprob, np.int32)
+    rc = lib().orc_quadgk_batch(fam, _p(lb), _p(ub), bpp, TR[tr], params.ctypes.data_as(_dp), nparam, nprob,
+                                reltol, abstol, maxiters, _p(I), _p(E), ne.ctypes.data_as(_i64p),
+                                st.ctypes.data_as(_i32p), nthreads)
+    assert rc == 0, rc
+    return I, E, ne, st
+
+
+def hcubature_batch(fam, lb, ub, params, tr="if_inf", reltol=1e-8, abstol=1e-8, maxiters=2**62, initdiv=1, nthreads=1):
+    lb = np.asarray(lb, dtype=np.float64); dim = lb.shape[0]
+    fam, params, nparam, nprob, lb, ub, bpp = _batch_common(fam, dim, lb, ub, params)
+    I = np.empty(nprob); E = np.empty(nprob); ne = np.empty(nprob, np.int64); st = np.empty(nprob, np.int32)
+    rc = lib().orc_hcubature_batch(fam, dim, _p(lb), _p(ub), bpp, TR[tr], params.ctypes.data_as(_dp), nparam, nprob,
+                                   reltol, abstol, maxiters, initdiv, _p(I), _p(E), ne.ctypes.data_as(_i64p),
+                                   st.ctypes.data_as(_i32p), nthreads)
+    assert rc == 0, rc
+    return I, E, ne, st
+
+
+def fixed_tensor_batch(fam, lb, ub, params, x1d, w1d, tr="if_inf", nthreads=1):
+    lb = np.asarray(lb, dtype=np.float64); dim = lb.shape[0]
+    fam, params, nparam, nprob, lb, ub, bpp = _batch_common(fam, dim, lb, ub, params)
+    x1d = _arr(x1d); w1d = _arr(w1d)
+    I = np.empty(nprob)
+    rc = lib().orc_fixed_tensor_batch(fam, dim, _p(lb), _p(ub), bpp, TR[tr], params.ctypes.data_as(_dp), nparam, nprob,
+                                      _p(x1d), _p(w1d), x1d.size, _p(I), nthreads)
+    assert rc == 0, rc
+    return I
+
+
+def fixed_nodes_batch(fam, lb, ub, params, nodes, weights, tr="if_inf", nthreads=1):
+    lb = np.asarray(lb, dtype=np.float64); dim = lb.shape[0]
+    fam, params, nparam, nprob, lb, ub, bpp = _batch_common(fam, dim, lb, ub, params)
+    nodes = _arr(nodes).reshape(-1, dim); weights = _arr(weights).ravel()
+    I = np.empty(nprob)
+    rc = lib().orc_fixed_nodes_batch(fam, dim, _p(lb), _p(ub), bpp, TR[tr], params.ctypes.data_as(_dp), nparam, nprob,
+                                     _p(nodes), _p(weights), weights.size, _p(I), nthreads)
+    assert rc == 0, rc
+    return I
+
+
+def gauss_legendre_batch(fam, lb, ub, params, nodes, weights, subintervals=1, tr="if_inf", nthreads=1):
+    fam, params, nparam, nprob, lb, ub, bpp = _batch_common(fam, 1, np.atleast_1d(lb), np.atleast_1d(ub), params)
+    nodes = _arr(nodes); weights = _arr(weights)
+    I = np.empty(nprob)
+    rc = lib().orc_gauss_legendre_batch(fam, _p(lb), _p(ub), bpp, TR[tr], params.ctypes.data_as(_dp), nparam, nprob,
+                                        _p(nodes), _p(weights), nodes.size, subintervals, _p(I), nthreads)
+    assert rc == 0, rc
+    return I

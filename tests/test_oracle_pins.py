@@ -1,0 +1,279 @@
+"""Pins the CPU oracle (oracle/oracle.c) against every known answer the reference's own tests
+hold for the hot path: the reference has no golden files, every
+expected value is a closed form written inline in test/*.jl -- reproduced here with the file:line.
+Also checks the degree-of-exactness identities of the restated QuadGK / HCubature rules.
+"""
+import math
+
+import numpy as np
+import pytest
+
+import oracle as O
+
+INF = math.inf
+
+
+# ---------------------------------------------------------------- README.md:30-40
+def test_readme_example_quadgk():
+    I, E, ne, st = O.solve_quadgk(lambda x: math.sin(1.7 * x), -2.0, 5.0, reltol=1e-10)
+    exact = (math.cos(-3.4) - math.cos(8.5)) / 1.7
+    assert st == 0
+    assert I == pytest.approx(exact, rel=1e-14)
+    # restated QuadGK: 3 segments, 75 evaluations, E = 5.69e-9
+    assert ne == 75 and E == pytest.approx(5.688e-9, rel=1e-3)
+
+
+# ---------------------------------------------------------------- test/sampled_tests.jl:3-30
+@pytest.mark.parametrize("rule", ["trapezoid", "simpson"])
+@pytest.mark.parametrize("gridkind", ["range", "rand_even", "rand_odd"])
+def test_sampled_closed_forms(rule, gridkind):
+    lb, ub, npoints = 0.4, 1.1, 1000
+    rng = np.random.default_rng(7)
+    if gridkind == "range":
+        x = None
+        grid = np.linspace(lb, ub, npoints)
+        h = (ub - lb) / (npoints - 1)
+    else:
+        k = npoints if gridkind == "rand_even" else npoints + 1
+        grid = np.concatenate([[lb], np.sort(rng.random(k) * (ub - lb) + lb), [ub]])
+        x, h = grid, None
+    exact = [(ub ** 6 - lb ** 6) / 6, math.sin(ub) - math.sin(lb)]
+    for f, ex in zip([lambda v: v ** 5, np.cos], exact):
+        y = f(grid)
+        err = O.sampled_evalrule(rule, y, x=x, h=h) - ex
+        assert abs(err) < 1e-4           # reference asserts the one-sided `error .< 10^-4`
+        y2 = np.asfortranarray(np.stack([y, y], axis=0))   # f.([grid grid]') : 2 x n, dim = 2
+        out = O.sampled_evalrule(rule, y2, x=x, h=h, dim=1)
+        assert out.shape == (2,) and np.all(np.abs(out - ex) < 1e-4)
+
+
+def test_sampled_ones_exact():  # test/sampled_tests.jl:35-43 (units dropped)
+    out = O.sampled_evalrule("trapezoid", np.ones((2, 3), order="F"), x=np.array([0.0, 1.0, 2.0]), dim=1)
+    assert np.array_equal(out, [2.0, 2.0])
+
+
+def test_sampled_dim1_vs_dim2():  # test/sampled_tests.jl:69-82
+    x = np.arange(0.0, 1.0001, 0.1)
+    y = np.asfortranarray(np.sin(x)[:, None] * np.cos(x)[None, :])
+    a = O.sampled_evalrule("trapezoid", y, h=0.1, dim=0)
+    b = O.sampled_evalrule("trapezoid", np.asfortranarray(y.T), h=0.1, dim=1)
+    assert np.allclose(a, b, rtol=0, atol=1e-15)
+
+
+def test_sampled_weights_exactness():
+    # Simpson-uniform (simpsons.jl:16-25) integrates cubics exactly; trapezoid integrates lines exactly
+    n, h = 23, 0.37
+    xs = np.arange(n) * h
+    w = O.sampled_weights("simpson", n, h=h)
+    for k in range(4):
+        assert w @ xs ** k == pytest.approx(xs[-1] ** (k + 1) / (k + 1), rel=1e-13)
+    # non-uniform Simpson (simpsons.jl:40-82) integrates quadratics exactly, odd and even lengths
+    rng = np.random.default_rng(3)
+    for n in (3, 4, 5, 6, 7, 8, 101, 102):
+        x = np.sort(rng.random(n)) * 2.0 + 0.5
+        w = O.sampled_weights("simpson", n, x=x)
+        for k in range(3):
+            assert w @ x ** k == pytest.approx((x[-1] ** (k + 1) - x[0] ** (k + 1)) / (k + 1), rel=1e-11)
+        w = O.sampled_weights("trapezoid", n, x=x)
+        for k in range(2):
+            assert w @ x ** k == pytest.approx((x[-1] ** (k + 1) - x[0] ** (k + 1)) / (k + 1), rel=1e-12)
+    # first-match-wins for short uniform Simpson grids (simpsons.jl:20-24)
+    assert np.allclose(O.sampled_weights("simpson", 3, h=48.0), [17, 59, 17])
+    assert np.allclose(O.sampled_weights("simpson", 5, h=48.0), [17, 59, 43, 59, 17])
+
+
+def test_sampled_empty_raises():  # sampled.jl:55,72,106
+    with pytest.raises(ValueError, match="No points"):
+        O.sampled_evalrule("trapezoid", np.zeros((3, 0), order="F"), h=1.0, dim=1)
+
+
+# ---------------------------------------------------------------- test/quadrule_tests.jl
+def _trapz(n):  # quadrule_tests.jl:17-25
+    x = np.linspace(-1, 1, n)
+    h = x[1] - x[0]
+    w = np.full(n, h); w[0] = w[-1] = h / 2
+    return x, w
+
+
+def _exact_cosprod(lb, ub, p):  # quadrule_tests.jl:7
+    return math.prod((math.sin(p * u) - math.sin(p * l)) / p for l, u in zip(lb, ub))
+
+
+def test_quadrule_1d_trapz():  # quadrule_tests.jl:27-36
+    x, w = _trapz(1000)
+    u = O.solve_quadrule(lambda v: math.cos(2.0 * v), -1.2, 3.5, x, w)
+    assert u == pytest.approx(_exact_cosprod([-1.2], [3.5], 2.0), rel=1e-3)
+
+
+def test_quadrule_2d_tensor():  # quadrule_tests.jl:41-55
+    x, w = _trapz(100)
+    lb, ub, p = [-1.2, -1.0], [3.5, 3.7], 1.2
+    f = lambda v: math.cos(p * v[0]) * math.cos(p * v[1])
+    u = O.solve_quadrule_tensor(f, lb, ub, x, w)
+    assert u == pytest.approx(_exact_cosprod(lb, ub, p), rel=1e-3)
+    # explicit node list in Iterators.product order (first index fastest) gives the same sum
+    nodes = np.array([[x[i], x[j]] for j in range(100) for i in range(100)])
+    wts = np.array([w[i] * w[j] for j in range(100) for i in range(100)])
+    u2 = O.solve_quadrule(f, lb, ub, nodes, wts)
+    assert u2 == pytest.approx(u, rel=1e-15)
+
+
+def test_quadrule_lorentzian_inf(gl):  # quadrule_tests.jl:59-69
+    x, w = gl(1000)
+    assert O.solve_quadrule(lambda v: 1.0 / (v * v + 1.0), -INF, INF, x, w) == pytest.approx(math.pi, rel=1e-4)
+    assert O.solve_quadrule(lambda v: 1.3 / (v * v + 1.69), -INF, INF, x, w) == pytest.approx(math.pi, rel=1e-4)
+
+
+# ---------------------------------------------------------------- test/gaussian_quadrature_tests.jl
+def test_gauss_legendre_known_values(gl):
+    x, w = gl(250)                                      # GaussLegendre() default n = 250
+    f = lambda v: 5 * v + math.sin(v) - 3.3 * math.exp(v)
+    exact = -math.exp(3) * 3.3 + 3.3 / math.exp(5) - 40 + math.cos(5) - math.cos(3)   # :57
+    assert O.solve_gauss_legendre(f, -5.0, 3.0, x, w) == pytest.approx(exact, rel=1.5e-8)
+    assert O.solve_gauss_legendre(f, -5.0, 3.0, x, w, subintervals=7) == pytest.approx(exact, rel=1.5e-8)  # :60
+    g = lambda v: math.exp(-v * v)
+    for sub in (1, 17):                                 # :62-88
+        assert O.solve_gauss_legendre(g, 0.0, INF, x, w, subintervals=sub) == pytest.approx(math.sqrt(math.pi) / 2, rel=1.5e-8)
+        assert O.solve_gauss_legendre(g, -INF, INF, x, w, subintervals=sub) == pytest.approx(math.sqrt(math.pi), rel=1.5e-8)
+        assert O.solve_gauss_legendre(g, -INF, 0.0, x, w, subintervals=sub) == pytest.approx(math.sqrt(math.pi) / 2, rel=1.5e-8)
+    p = [0.3, 1.3, -0.5]                                # :91-99
+    h = lambda v: 1 + v + v ** p[0] - math.cos(v * p[1]) + math.exp(v) * p[2]
+    assert O.solve_gauss_legendre(h, 2.0, 6.3, x, w) == pytest.approx(-240.25235266303063249920743158729, rel=1.5e-8)
+    x5, w5 = gl(500)
+    assert O.solve_gauss_legendre(h, 2.0, 6.3, x5, w5, subintervals=17) == pytest.approx(-240.25235266303063249920743158729, rel=1.5e-8)
+
+
+def test_gauss_legendre_commented_block(gl):  # gaussian_quadrature_tests.jl:4-20 (kept as documentation there)
+    x, w = gl(250)
+    f = lambda v: v ** 3 * math.sin(5 * v)
+    exact = 2 / 625 * (69 * math.sin(5) - 95 * math.cos(5))
+    assert O.solve_gauss_legendre(f, -1.0, 1.0, x, w) == pytest.approx(exact, rel=1e-12)
+    assert O.solve_gauss_legendre(f, -1.0, 1.0, x, w, subintervals=2) == pytest.approx(exact, rel=1e-12)
+
+
+# ---------------------------------------------------------------- test/inf_integral_tests.jl:42-163
+_mvn = lambda x: math.exp(-(x[0] ** 2 + x[1] ** 2) / 0.8) / (2 * math.pi * 0.4)
+_npdf = lambda x: math.exp(-x * x / 2) / math.sqrt(2 * math.pi)
+_npdf_q = lambda x: _npdf(x[0]) * x[1] ** 2
+_lor = lambda x: 1 / (x * x + 1)
+_lor2 = lambda x: 1 / ((x - 2) ** 2 + 1)
+INF_PROBLEMS = [
+    (_mvn, [-INF, -INF], [INF, INF], 1.0), (_mvn, [INF, INF], [-INF, -INF], 1.0),
+    (_mvn, [-INF, 0], [INF, INF], 0.5), (_mvn, [-INF, -INF], [INF, 0], 0.5),
+    (_npdf_q, [-INF, 1], [INF, 4], 21.0), (_npdf_q, [0.0, 1], [INF, 4], 10.5), (_npdf_q, [-INF, 1], [0.0, 4], 10.5),
+    (_npdf, -INF, INF, 1.0), (_npdf, INF, -INF, -1.0), (_npdf, 0.0, INF, 0.5), (_npdf, 0.0, -INF, -0.5),
+    (_npdf, -INF, 0.0, 0.5), (_npdf, INF, 0.0, -0.5),
+    (_lor, -INF, INF, math.pi), (_lor2, -INF, 2, math.pi / 2), (_lor2, 2, INF, math.pi / 2),
+    (_lor2, INF, 2, -math.pi / 2), (_lor2, 2, -INF, -math.pi / 2),
+    (lambda x: x * x, 1, 4, 21.0), (lambda x: x * x, 4, 1, -21.0),
+]
+
+
+@pytest.mark.parametrize("k", range(len(INF_PROBLEMS)))
+def test_inf_integrals(k, gl):
+    f, lb, ub, sol = INF_PROBLEMS[k]
+    tol = 1e-3                                          # reltol = 0, abstol = 1e-3 (:3-4,182)
+    if isinstance(lb, list):
+        I, E, ne, st = O.solve_hcubature(f, lb, ub, reltol=0.0, abstol=tol)
+        assert abs(I - sol) < tol
+    else:
+        lb, ub = float(lb), float(ub)
+        I, *_ = O.solve_quadgk(f, lb, ub, reltol=0.0, abstol=tol)
+        assert abs(I - sol) < tol
+        I, *_ = O.solve_hcubature(f, [lb], [ub], reltol=0.0, abstol=tol)
+        assert abs(I - sol) < tol
+        x, w = gl(50)                                   # QuadratureRule(gausslegendre, n = 50)
+        assert abs(O.solve_quadrule(f, lb, ub, x, w) - sol) < tol
+
+
+# ---------------------------------------------------------------- test/alt_transformation_tests.jl
+@pytest.mark.parametrize("tr", ["tan", "cot"])
+def test_alt_transformations(tr):
+    kw = dict(tr=tr, reltol=1e-6, abstol=1e-6)
+    s = lambda *a, **k: O.solve_quadgk(*a, **k)[0]
+    assert s(lambda x: math.exp(-x * x), -INF, INF, **kw) == pytest.approx(math.sqrt(math.pi), rel=1e-5)
+    assert s(lambda x: 1 / (1 + x * x), -INF, INF, **kw) == pytest.approx(math.pi, rel=1e-5)
+    if tr == "tan":
+        assert s(lambda x: math.exp(-x), 0.0, INF, **kw) == pytest.approx(1.0, rel=1e-4)
+        assert s(lambda x: math.exp(x), -INF, 0.0, **kw) == pytest.approx(1.0, rel=1e-4)
+        assert s(lambda x: 1 / ((x - 2) ** 2 + 1), 2.0, INF, **kw) == pytest.approx(math.pi / 2, rel=1e-4)
+        assert s(lambda x: math.exp(x), -INF, -1.0, **kw) == pytest.approx(math.exp(-1), rel=1e-4)
+    else:
+        kw2 = dict(tr=tr, reltol=1e-4, abstol=1e-4)
+        assert s(lambda x: math.exp(-x), 0.0, INF, **kw2) == pytest.approx(1.0, rel=1e-3)
+        assert s(lambda x: math.exp(x), -INF, 0.0, **kw2) == pytest.approx(1.0, rel=1e-3)
+        assert s(lambda x: math.exp(-x * x), 0.0, INF, **kw2) == pytest.approx(math.sqrt(math.pi) / 2, rel=1e-3)
+    # finite domains unchanged (:72-90); flipped limits (:92-101); HCubature 1-D (:103-111)
+    assert s(lambda x: x * x, 0.0, 1.0, tr=tr, reltol=1e-10, abstol=1e-10) == pytest.approx(1 / 3, rel=1e-8)
+    assert s(lambda x: math.exp(-x * x), INF, -INF, **kw) == pytest.approx(-math.sqrt(math.pi), rel=1e-5)
+    I, *_ = O.solve_hcubature(lambda x: math.exp(-x * x), [-INF], [INF], tr=tr, reltol=1e-6, abstol=1e-6)
+    assert I == pytest.approx(math.sqrt(math.pi), rel=1e-4)
+
+
+# ---------------------------------------------------------------- test/interface_tests.jl:129-187
+@pytest.mark.parametrize("dim", [1, 2])
+def test_interface_integrands(dim):
+    lb, ub = [1.0] * dim, [3.0] * dim
+    exact1 = 2.0 ** dim
+    exactc = (math.sin(3) - math.sin(1)) ** dim
+    one = lambda x: 1.0
+    cosp = (lambda x: math.cos(x)) if dim == 1 else (lambda x: math.cos(x[0]) * math.cos(x[1]))
+    I, *_ = O.solve_hcubature(one, lb, ub, reltol=1e-5, abstol=1e-5)
+    assert I == pytest.approx(exact1, rel=1e-2)
+    I, *_ = O.solve_hcubature(cosp, lb, ub, reltol=1e-5, abstol=1e-5)
+    assert I == pytest.approx(exactc, rel=1e-2)
+    if dim == 1:
+        assert O.solve_quadgk(one, 1.0, 3.0, reltol=1e-5, abstol=1e-5)[0] == pytest.approx(exact1, rel=1e-2)
+        assert O.solve_quadgk(cosp, 1.0, 3.0, reltol=1e-5, abstol=1e-5)[0] == pytest.approx(exactc, rel=1e-2)
+
+
+# ---------------------------------------------------------------- rule identities
+def test_gk15_degree_of_exactness():
+    for k in range(0, 23):      # Kronrod-15 exact through degree 22
+        I, E = O.gk15(lambda x, k=k: x ** k, -0.3, 1.7)
+        exact = (1.7 ** (k + 1) - (-0.3) ** (k + 1)) / (k + 1)
+        assert I == pytest.approx(exact, rel=2e-13)
+        if k <= 13:             # embedded Gauss-7 exact through degree 13 -> E ~ 0
+            assert E <= 1e-12 * max(1.0, abs(exact))
+    I, E = O.gk15(lambda x: x ** 14, -0.3, 1.7)
+    assert E > 1e-9             # Gauss-7 is NOT exact at degree 14
+
+
+def test_genz_malik_degree_and_counts():
+    for n, npts in [(2, 17), (3, 33), (4, 57), (8, 401)]:
+        cnt = [0]
+
+        def one(x, cnt=cnt):
+            cnt[0] += 1
+            return 1.0
+        I, E, k = O.cubrule(one, [0.0] * n, [1.0] * n)
+        assert cnt[0] == npts and I == pytest.approx(1.0, rel=1e-14) and E < 1e-13
+    a, b = [0.2, -1.0, 0.5], [1.3, 0.4, 2.0]
+    rng = np.random.default_rng(5)
+    for _ in range(12):
+        e = rng.multinomial(7, [1 / 3] * 3)   # total degree 7 monomial
+        f = lambda x, e=e: x[0] ** e[0] * x[1] ** e[1] * x[2] ** e[2]
+        exact = math.prod((b[i] ** (e[i] + 1) - a[i] ** (e[i] + 1)) / (e[i] + 1) for i in range(3))
+        I, E, k = O.cubrule(f, a, b)
+        assert I == pytest.approx(exact, rel=1e-12, abs=1e-13)
+    # degree-5 monomials: embedded rule exact too -> E ~ 0
+    I, E, k = O.cubrule(lambda x: x[0] ** 3 * x[1] ** 2, a, b)
+    assert E < 1e-12
+    # split axis = largest fourth difference
+    I, E, k = O.cubrule(lambda x: math.cos(7 * x[1]) + x[0] + x[2], a, b)
+    assert k == 1
+
+
+def test_hcubature_converges_to_closed_form():
+    a = np.array([5.0, 3.0, 4.0]); u = np.array([0.3, 0.6, 0.5])
+    par = np.concatenate([a, u])
+    exact = math.prod(math.sqrt(math.pi) / (2 * a[i]) * (math.erf(a[i] * (1 - u[i])) + math.erf(a[i] * u[i])) for i in range(3))
+    I, E, ne, st = O.hcubature_batch("gauss", [0.0] * 3, [1.0] * 3, par, reltol=1e-7, abstol=0.0)
+    assert st[0] == 0 and abs(I[0] - exact) <= 1e-7 * exact and E[0] <= 1e-7 * abs(I[0])
+
+
+def test_issue242_abstol_is_an_absolute_stop():  # interface_tests.jl:446-454 semantics: abstol honoured
+    # |I| ~ 0.03 for p = 64: with the default abstol = 1e-8 the absolute test, not reltol, stops QuadGK
+    I1, E1, n1, _ = O.solve_quadgk(lambda x: math.sin(64 * x), -2.0, 5.0, reltol=1e-10, abstol=1e-8)
+    I2, E2, n2, _ = O.solve_quadgk(lambda x: math.sin(64 * x), -2.0, 5.0, reltol=1e-10, abstol=0.0)
+    assert E1 <= 1e-8 and n2 > n1 and E2 <= 1e-10 * abs(I2)
