@@ -1,0 +1,141 @@
+/*
+ * integrals_b200.h -- C ABI of libintegrals_b200.so (CUDA, sm_100a).
+ *
+ * This is the drop-in boundary for the Integrals.jl hot path: each entry point is what a
+ * Julia `ccall` from the new algorithm types (QuadGKB200, HCubatureB200, QuadratureRuleB200 /
+ * GaussLegendreB200, TrapezoidalB200 / SimpsonsB200) binds, and it replaces the reference
+ * function cited beside it (paths relative to the Integrals.jl v5.4.4 tree).  INTEGRATION.md
+ * shows the Julia-side binding.  Plain C types only; no callbacks into the caller.
+ *
+ * Conventions
+ *  - Every call returns 0 on success or a negative IB200_ERR_* code; the message is available
+ *    from ib200_last_error(ctx).  No C++ exception crosses the boundary.
+ *  - Data pointers may be HOST or DEVICE pointers (resolved per pointer with
+ *    cudaPointerGetAttributes).  Host inputs are staged to the device inside the call and host
+ *    outputs are copied back before it returns.  When every output pointer is a device pointer
+ *    the call is asynchronous on the context's stream (ib200_synchronize to wait).
+ *  - The caller owns all buffers; the library keeps no caller pointer after a call returns.
+ *  - `params` is nparam x nprob, column-major (Julia Matrix): problem k's parameters are the
+ *    contiguous doubles params[k*nparam .. (k+1)*nparam).  See ib200_family_nparam.
+ *  - `lb`,`ub` are `dim` doubles shared by all problems, or dim x nprob column-major when
+ *    bounds_per_problem != 0.  +-INFINITY selects the infinity_handling.jl variable change.
+ *  - `transform`: which ChangeOfVariables map the reference would apply (src/common.jl:97-103):
+ *    0 transformation_if_inf, 1 transformation_tan_inf, 2 transformation_cot_inf
+ *    (src/infinity_handling.jl:165-170, 277-282, 405-410).  Applied on the device.
+ *  - One context is bound to one GPU and may be used by one host thread at a time
+ *    (one process per GPU; multi-GPU jobs shard problems across processes).
+ */
+#ifndef INTEGRALS_B200_H
+#define INTEGRALS_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ib200_ctx ib200_ctx;
+
+#define IB200_OK               0
+#define IB200_ERR_INVALID     (-1)  /* bad argument (message says which)                     */
+#define IB200_ERR_CUDA        (-2)  /* CUDA runtime error                                     */
+#define IB200_ERR_OOM         (-3)  /* device memory exhausted                                */
+#define IB200_ERR_UNSUPPORTED (-4)  /* family/dimension/transform combination not compiled in */
+#define IB200_ERR_NCCL        (-5)  /* NCCL error (multi-GPU single-domain solve)             */
+
+/* registered device-side integrand families; x in R^dim, per-problem params */
+#define IB200_FAM_SINXP      0   /* [p]               sin(x*p)                         dim 1   */
+#define IB200_FAM_GENZ_OSC   1   /* [a(d),u(d)]       cos(2 pi u1 + sum a_i x_i)               */
+#define IB200_FAM_GENZ_PROD  2   /* [a,u]             1/prod(a_i^-2 + (x_i-u_i)^2)             */
+#define IB200_FAM_GENZ_CORN  3   /* [a,u]             (1 + sum a_i x_i)^-(d+1)                 */
+#define IB200_FAM_GENZ_GAUSS 4   /* [a,u]             exp(-sum a_i^2 (x_i-u_i)^2)              */
+#define IB200_FAM_GENZ_C0    5   /* [a,u]             exp(-sum a_i |x_i-u_i|)                  */
+#define IB200_FAM_GENZ_DISC  6   /* [a,u]             0 if x1>u1 or x2>u2 else exp(sum a_i x_i) */
+#define IB200_FAM_COSPROD    7   /* [p(d)]            prod cos(p_i x_i)                        */
+#define IB200_FAM_GAUSSPOLY  8   /* [a,u,k(d),c]      c prod x_i^k_i exp(-sum a_i^2 (x_i-u_i)^2) */
+#define IB200_FAM_EXPLIN     9   /* [a(d)]            exp(sum a_i x_i)                         */
+#define IB200_FAM_GLTEST     10  /* [p]               5x + sin(x) - p exp(x)            dim 1  */
+#define IB200_FAM_COUNT      11
+#define IB200_MAX_DIM        8
+
+#define IB200_TR_IF_INF 0
+#define IB200_TR_TAN    1
+#define IB200_TR_COT    2
+
+#define IB200_RULE_TRAPEZOID 0
+#define IB200_RULE_SIMPSON   1
+
+/* per-problem status of the adaptive solves */
+#define IB200_ST_CONVERGED  0  /* E <= max(abstol, reltol*|I|) (QuadGK: E<=abstol || E<=reltol*|I|) */
+#define IB200_ST_MAXEVALS   1  /* evaluation budget (maxiters) or region capacity exhausted         */
+#define IB200_ST_NONFINITE  2  /* non-finite error estimate (QuadGK DomainError / HCubature stop)   */
+#define IB200_ST_ROUNDOFF   3  /* QuadGK: segment can no longer be bisected                          */
+
+int32_t     ib200_version(void);
+/* context: device ordinal, stream, reusable device scratch (the analogue of QuadGK's segbuf,
+   src/Integrals.jl:241-250, and HCubature's buffer, :341-346, kept in cache.cacheval) */
+int32_t     ib200_create(int32_t device, ib200_ctx **out);
+void        ib200_destroy(ib200_ctx *ctx);
+const char *ib200_last_error(ib200_ctx *ctx);            /* ctx may be NULL (create failures) */
+int32_t     ib200_set_stream(ib200_ctx *ctx, void *cuda_stream);   /* NULL -> ctx's own stream */
+int32_t     ib200_synchronize(ib200_ctx *ctx);
+int64_t     ib200_kernel_launches(ib200_ctx *ctx);       /* kernels launched so far (bench)   */
+int32_t     ib200_family_nparam(int32_t family, int32_t dim);   /* doubles per problem, <0 bad */
+/* timing of the most recent call's kernels on the context's stream, ms (CUDA events) */
+double      ib200_last_kernel_ms(ib200_ctx *ctx);
+/* optional knobs: key in {"adaptive_warps_per_sm","hcub_capacity","sampled_slabs"} */
+int32_t     ib200_set_option(ib200_ctx *ctx, const char *key, int64_t value);
+
+/* -- sampled data: replaces evalrule(data, weights, dim) src/sampled.jl:51-124 with the weights of
+      src/trapezoidal.jl:16-45 / src/simpsons.jl:16-87, as dispatched by
+      __solvebp_call(::SampledIntegralCache) src/sampled.jl:135-168.
+      y is column-major [inner, n, outer] (the array with the integration axis in the middle:
+      inner = prod(size(y)[1:dim-1]), outer = prod(size(y)[dim+1:end])); out is [inner, outer].
+      x == NULL: uniform grid with step h (AbstractRange branch, trapezoidal.jl:43, simpsons.jl:85);
+      else x holds the n grid points and h is ignored.  n == 0 -> IB200_ERR_INVALID
+      ("No points to integrate", sampled.jl:55). */
+int32_t ib200_sampled(ib200_ctx *ctx, int32_t rule, const double *y, int64_t inner, int64_t n,
+                      int64_t outer, double h, const double *x, double *out);
+
+/* -- fixed rules: replaces evalrule(f,p,lb,ub,nodes,weights) src/quadrules.jl:1-19 under the
+      automatic ChangeOfVariables (src/Integrals.jl:192-224), for a batch of problems.
+      tensor: the rule is the dim-fold tensor product of (x1d, w1d), n1d^dim nodes
+      (test/quadrule_tests.jl:41-44).  nodes: explicit N x dim row-major nodes, N weights. */
+int32_t ib200_fixed_rule_tensor_batch(ib200_ctx *ctx, int32_t family, int32_t dim, int32_t transform,
+                                      const double *lb, const double *ub, int32_t bounds_per_problem,
+                                      const double *params, int32_t nparam, int64_t nprob,
+                                      const double *x1d, const double *w1d, int32_t n1d, double *out_I);
+int32_t ib200_fixed_rule_nodes_batch(ib200_ctx *ctx, int32_t family, int32_t dim, int32_t transform,
+                                     const double *lb, const double *ub, int32_t bounds_per_problem,
+                                     const double *params, int32_t nparam, int64_t nprob,
+                                     const double *nodes, const double *weights, int64_t N, double *out_I);
+/* -- 1-D (composite) Gauss-Legendre: replaces gauss_legendre / composite_gauss_legendre
+      ext/IntegralsFastGaussQuadratureExt.jl:11-32 as called from :34-76. */
+int32_t ib200_gauss_legendre_batch(ib200_ctx *ctx, int32_t family, int32_t transform,
+                                   const double *lb, const double *ub, int32_t bounds_per_problem,
+                                   const double *params, int32_t nparam, int64_t nprob,
+                                   const double *nodes, const double *weights, int32_t n,
+                                   int32_t subintervals, double *out_I);
+
+/* -- adaptive 1-D: replaces QuadGK.quadgk(f, lb, ub; rtol, atol, maxevals, order = 7) as called at
+      src/Integrals.jl:327-335 (scalar out-of-place branch of __solvebp_call(::QuadGKJL) :252-339).
+      out_E, out_nevals, out_status may be NULL. */
+int32_t ib200_quadgk_batch(ib200_ctx *ctx, int32_t family, int32_t transform,
+                           const double *lb, const double *ub, int32_t bounds_per_problem,
+                           const double *params, int32_t nparam, int64_t nprob,
+                           double reltol, double abstol, int64_t maxevals,
+                           double *out_I, double *out_E, int64_t *out_nevals, int32_t *out_status);
+/* -- adaptive N-D: replaces HCubature.hcubature / hquadrature(f, lb, ub; rtol, atol, maxevals,
+      initdiv) as called at src/Integrals.jl:380-393 (__solvebp_call(::HCubatureJL) :347-397). */
+int32_t ib200_hcubature_batch(ib200_ctx *ctx, int32_t family, int32_t dim, int32_t transform,
+                              const double *lb, const double *ub, int32_t bounds_per_problem,
+                              const double *params, int32_t nparam, int64_t nprob,
+                              double reltol, double abstol, int64_t maxevals, int32_t initdiv,
+                              double *out_I, double *out_E, int64_t *out_nevals, int32_t *out_status);
+
+/* -- measurement helper: dependency-free DFMA chains on every SM; returns TFLOP/s (2 flops/DFMA).
+      This is the FP64 roofline denominator. */
+int32_t ib200_measure_fp64_peak(ib200_ctx *ctx, double *tflops, double *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,250 @@
+"""ctypes binding of libintegrals_b200.so (the C ABI declared in include/integrals_b200.h).
+
+There is no CPU fallback: if the shared library is missing, or no B200 is visible, creating an
+Engine raises.  Arrays may be numpy arrays (host; staged by the library) or torch CUDA tensors /
+anything with ``data_ptr()`` (device; used in place).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libintegrals_b200.so")
+
+FAMILY_IDS = dict(sinxp=0, genz_oscillatory=1, genz_product_peak=2, genz_corner_peak=3, genz_gaussian=4,
+                  genz_c0=5, genz_discontinuous=6, cosprod=7, gausspoly=8, explin=9, gltest=10)
+TRANSFORM_IDS = dict(transformation_if_inf=0, transformation_tan_inf=1, transformation_cot_inf=2)
+RULE_IDS = dict(trapezoid=0, simpson=1)
+
+ERR_NAMES = {-1: "IB200_ERR_INVALID", -2: "IB200_ERR_CUDA", -3: "IB200_ERR_OOM", -4: "IB200_ERR_UNSUPPORTED",
+             -5: "IB200_ERR_NCCL"}
+
+# every symbol include/integrals_b200.h declares (tests check the .so exports all of them)
+SYMBOLS = ["ib200_version", "ib200_create", "ib200_destroy", "ib200_last_error", "ib200_set_stream",
+           "ib200_synchronize", "ib200_kernel_launches", "ib200_family_nparam", "ib200_last_kernel_ms",
+           "ib200_set_option", "ib200_sampled", "ib200_fixed_rule_tensor_batch", "ib200_fixed_rule_nodes_batch",
+           "ib200_gauss_legendre_batch", "ib200_quadgk_batch", "ib200_hcubature_batch", "ib200_measure_fp64_peak"]
+
+
+class IB200Error(RuntimeError):
+    """A non-zero return code from libintegrals_b200.so."""
+
+    def __init__(self, code, msg):
+        super().__init__(f"{ERR_NAMES.get(code, code)}: {msg}")
+        self.code = code
+        self.msg = msg
+
+
+_lib = None
+
+
+def load_library():
+    """Load libintegrals_b200.so; raises ImportError if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "or `make -C integrals.jl_b200/csrc` (there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, dp, i32, i64 = C.c_void_p, C.c_double, C.c_int32, C.c_int64
+    L.ib200_version.restype = i32
+    L.ib200_create.argtypes = [i32, C.POINTER(vp)]; L.ib200_create.restype = i32
+    L.ib200_destroy.argtypes = [vp]; L.ib200_destroy.restype = None
+    L.ib200_last_error.argtypes = [vp]; L.ib200_last_error.restype = C.c_char_p
+    L.ib200_set_stream.argtypes = [vp, vp]; L.ib200_set_stream.restype = i32
+    L.ib200_synchronize.argtypes = [vp]; L.ib200_synchronize.restype = i32
+    L.ib200_kernel_launches.argtypes = [vp]; L.ib200_kernel_launches.restype = i64
+    L.ib200_family_nparam.argtypes = [i32, i32]; L.ib200_family_nparam.restype = i32
+    L.ib200_last_kernel_ms.argtypes = [vp]; L.ib200_last_kernel_ms.restype = dp
+    L.ib200_set_option.argtypes = [vp, C.c_char_p, i64]; L.ib200_set_option.restype = i32
+    L.ib200_sampled.argtypes = [vp, i32, vp, i64, i64, i64, dp, vp, vp]; L.ib200_sampled.restype = i32
+    L.ib200_fixed_rule_tensor_batch.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp, i32, i64, vp, vp, i32, vp]
+    L.ib200_fixed_rule_tensor_batch.restype = i32
+    L.ib200_fixed_rule_nodes_batch.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp, i32, i64, vp, vp, i64, vp]
+    L.ib200_fixed_rule_nodes_batch.restype = i32
+    L.ib200_gauss_legendre_batch.argtypes = [vp, i32, i32, vp, vp, i32, vp, i32, i64, vp, vp, i32, i32, vp]
+    L.ib200_gauss_legendre_batch.restype = i32
+    L.ib200_quadgk_batch.argtypes = [vp, i32, i32, vp, vp, i32, vp, i32, i64, dp, dp, i64, vp, vp, vp, vp]
+    L.ib200_quadgk_batch.restype = i32
+    L.ib200_hcubature_batch.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp, i32, i64, dp, dp, i64, i32, vp, vp, vp, vp]
+    L.ib200_hcubature_batch.restype = i32
+    L.ib200_measure_fp64_peak.argtypes = [vp, C.POINTER(dp), C.POINTER(dp)]; L.ib200_measure_fp64_peak.restype = i32
+    _lib = L
+    return L
+
+
+def _is_device(a):
+    return hasattr(a, "data_ptr") and getattr(a, "is_cuda", False)
+
+
+def _ptr(a):
+    """(address, keepalive) for a numpy array, a torch tensor or None."""
+    if a is None:
+        return None, None
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr(), a
+    return a.ctypes.data, a
+
+
+def _f64(a, order="F"):
+    """Host arrays are made float64 column-major; device tensors are passed through."""
+    if a is None or hasattr(a, "data_ptr"):
+        return a
+    return np.asarray(a, dtype=np.float64, order=order)
+
+
+MAXEVALS_UNBOUNDED = 2 ** 62   # the reference passes typemax(Int) (src/Integrals.jl:255,350)
+
+
+class Engine:
+    """One context = one GPU (one process per GPU).  Owns the library handle, a stream and the
+    reusable device scratch (the cacheval analogue of QuadGK's segbuf / HCubature's buffer)."""
+
+    def __init__(self, device=0):
+        self.L = load_library()
+        h = C.c_void_p()
+        rc = self.L.ib200_create(int(device), C.byref(h))
+        if rc != 0:
+            raise IB200Error(rc, self.L.ib200_last_error(None).decode())
+        self.h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.ib200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise IB200Error(rc, self.L.ib200_last_error(self.h).decode())
+
+    # ---- misc --------------------------------------------------------------------------------
+    def synchronize(self):
+        self._check(self.L.ib200_synchronize(self.h))
+
+    def set_stream(self, stream_ptr):
+        self._check(self.L.ib200_set_stream(self.h, stream_ptr))
+
+    def set_option(self, key, value):
+        self._check(self.L.ib200_set_option(self.h, key.encode(), int(value)))
+
+    @property
+    def kernel_launches(self):
+        return int(self.L.ib200_kernel_launches(self.h))
+
+    @property
+    def last_kernel_ms(self):
+        return float(self.L.ib200_last_kernel_ms(self.h))
+
+    def fp64_peak(self):
+        t = C.c_double(); ms = C.c_double()
+        self._check(self.L.ib200_measure_fp64_peak(self.h, C.byref(t), C.byref(ms)))
+        return t.value, ms.value
+
+    # ---- helpers -----------------------------------------------------------------------------
+    def _out(self, out, n, dtype=np.float64):
+        if out is None:
+            out = np.empty(n, dtype=dtype)
+        return out
+
+    @staticmethod
+    def _batch_shapes(params, lb, ub, dim):
+        if hasattr(params, "data_ptr"):
+            # torch tensor in Julia column-major convention: shape (nprob, nparam) row-major == nparam x nprob col-major
+            nprob, nparam = (params.shape[0], params.shape[1]) if params.dim() == 2 else (1, params.shape[0])
+        else:
+            if params.ndim == 1:
+                params = params.reshape(-1, 1, order="F")
+            nparam, nprob = params.shape
+        if hasattr(lb, "data_ptr"):
+            bpp = 1 if lb.dim() == 2 else 0
+        else:
+            bpp = 1 if lb.ndim == 2 else 0
+        return params, nparam, nprob, bpp
+
+    # ---- sampled -----------------------------------------------------------------------------
+    def sampled(self, rule, y, inner, n, outer, h=0.0, x=None, out=None):
+        y = _f64(y); x = _f64(x)
+        out = self._out(out, max(inner * outer, 1))
+        yp, _k1 = _ptr(y); xp, _k2 = _ptr(x); op, _k3 = _ptr(out)
+        self._check(self.L.ib200_sampled(self.h, RULE_IDS[rule] if isinstance(rule, str) else rule, yp, inner, n, outer,
+                                         float(h), xp, op))
+        return out
+
+    # ---- fixed rules ---------------------------------------------------------------------------
+    def fixed_rule_tensor_batch(self, family, dim, lb, ub, params, x1d, w1d, transform=0, out=None):
+        lb = _f64(lb); ub = _f64(ub); params = _f64(params); x1d = _f64(x1d); w1d = _f64(w1d)
+        params, nparam, nprob, bpp = self._batch_shapes(params, lb, ub, dim)
+        out = self._out(out, nprob)
+        a = [_ptr(v) for v in (lb, ub, params, x1d, w1d, out)]
+        n1d = x1d.shape[0]
+        self._check(self.L.ib200_fixed_rule_tensor_batch(self.h, family, dim, transform, a[0][0], a[1][0], bpp, a[2][0],
+                                                         nparam, nprob, a[3][0], a[4][0], n1d, a[5][0]))
+        return out
+
+    def fixed_rule_nodes_batch(self, family, dim, lb, ub, params, nodes, weights, transform=0, out=None):
+        lb = _f64(lb); ub = _f64(ub); params = _f64(params)
+        nodes = _f64(nodes, order="C"); weights = _f64(weights)
+        params, nparam, nprob, bpp = self._batch_shapes(params, lb, ub, dim)
+        out = self._out(out, nprob)
+        N = weights.shape[0]
+        a = [_ptr(v) for v in (lb, ub, params, nodes, weights, out)]
+        self._check(self.L.ib200_fixed_rule_nodes_batch(self.h, family, dim, transform, a[0][0], a[1][0], bpp, a[2][0],
+                                                        nparam, nprob, a[3][0], a[4][0], N, a[5][0]))
+        return out
+
+    def gauss_legendre_batch(self, family, lb, ub, params, nodes, weights, subintervals=1, transform=0, out=None):
+        lb = _f64(lb); ub = _f64(ub); params = _f64(params)
+        nodes = np.ascontiguousarray(nodes, dtype=np.float64); weights = np.ascontiguousarray(weights, dtype=np.float64)
+        params, nparam, nprob, bpp = self._batch_shapes(params, lb, ub, 1)
+        out = self._out(out, nprob)
+        a = [_ptr(v) for v in (lb, ub, params, nodes, weights, out)]
+        self._check(self.L.ib200_gauss_legendre_batch(self.h, family, transform, a[0][0], a[1][0], bpp, a[2][0], nparam,
+                                                      nprob, a[3][0], a[4][0], nodes.shape[0], subintervals, a[5][0]))
+        return out
+
+    # ---- adaptive ------------------------------------------------------------------------------
+    def quadgk_batch(self, family, lb, ub, params, reltol=1e-8, abstol=1e-8, maxevals=MAXEVALS_UNBOUNDED, transform=0,
+                     out_I=None, out_E=None, out_nevals=None, out_status=None):
+        lb = _f64(lb); ub = _f64(ub); params = _f64(params)
+        params, nparam, nprob, bpp = self._batch_shapes(params, lb, ub, 1)
+        out_I = self._out(out_I, nprob); out_E = self._out(out_E, nprob)
+        out_nevals = self._out(out_nevals, nprob, np.int64); out_status = self._out(out_status, nprob, np.int32)
+        a = [_ptr(v) for v in (lb, ub, params, out_I, out_E, out_nevals, out_status)]
+        self._check(self.L.ib200_quadgk_batch(self.h, family, transform, a[0][0], a[1][0], bpp, a[2][0], nparam, nprob,
+                                              float(reltol), float(abstol), int(min(maxevals, MAXEVALS_UNBOUNDED)),
+                                              a[3][0], a[4][0], a[5][0], a[6][0]))
+        return out_I, out_E, out_nevals, out_status
+
+    def hcubature_batch(self, family, dim, lb, ub, params, reltol=1e-8, abstol=1e-8, maxevals=MAXEVALS_UNBOUNDED,
+                        initdiv=1, transform=0, out_I=None, out_E=None, out_nevals=None, out_status=None):
+        lb = _f64(lb); ub = _f64(ub); params = _f64(params)
+        params, nparam, nprob, bpp = self._batch_shapes(params, lb, ub, dim)
+        out_I = self._out(out_I, nprob); out_E = self._out(out_E, nprob)
+        out_nevals = self._out(out_nevals, nprob, np.int64); out_status = self._out(out_status, nprob, np.int32)
+        a = [_ptr(v) for v in (lb, ub, params, out_I, out_E, out_nevals, out_status)]
+        self._check(self.L.ib200_hcubature_batch(self.h, family, dim, transform, a[0][0], a[1][0], bpp, a[2][0], nparam,
+                                                 nprob, float(reltol), float(abstol),
+                                                 int(min(maxevals, MAXEVALS_UNBOUNDED)), int(initdiv),
+                                                 a[3][0], a[4][0], a[5][0], a[6][0]))
+        return out_I, out_E, out_nevals, out_status
+
+
+_default_engines = {}
+
+
+def default_engine(device=None):
+    """Process-wide Engine for `device` (default: LOCAL_RANK, else 0)."""
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    if device not in _default_engines:
+        _default_engines[device] = Engine(device)
+    return _default_engines[device]

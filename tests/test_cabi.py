@@ -1,0 +1,54 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/integrals_b200.h declares, and fails loudly (no fallback) when there is no GPU."""
+import os
+import re
+
+import pytest
+
+import integrals_b200 as ib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    txt = open(os.path.join(ROOT, "include", "integrals_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(ib200_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_symbols_all_exported():
+    L = ib.load_library()
+    syms = _header_symbols()
+    assert len(syms) >= 17
+    missing = [s for s in syms if not hasattr(L, s)]
+    assert not missing, f"declared in the header but not exported: {missing}"
+    assert sorted(ib.SYMBOLS) == syms, "python binding list and header disagree"
+
+
+def test_version_and_family_table():
+    L = ib.load_library()
+    assert L.ib200_version() == 100
+    assert L.ib200_family_nparam(ib.FAMILY_IDS["sinxp"], 1) == 1
+    assert L.ib200_family_nparam(ib.FAMILY_IDS["sinxp"], 2) == -1      # 1-D only
+    assert L.ib200_family_nparam(ib.FAMILY_IDS["genz_gaussian"], 4) == 8
+    assert L.ib200_family_nparam(ib.FAMILY_IDS["gausspoly"], 2) == 7
+    assert L.ib200_family_nparam(99, 1) == -1
+    assert L.ib200_family_nparam(1, 9) == -1
+
+
+def test_family_table_matches_oracle():
+    import oracle as O
+    L = ib.load_library()
+    for name, fid in ib.FAMILY_IDS.items():
+        for d in range(1, 9):
+            got = L.ib200_family_nparam(fid, d)
+            if got >= 0:
+                assert got == O.family_nparam(fid, d), (name, d)
+
+
+def test_no_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(ib.IB200Error, match="no CUDA device|no CPU fallback"):
+        ib.Engine(0)

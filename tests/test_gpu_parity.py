@@ -1,0 +1,281 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes), against the CPU oracle on
+the same seeded inputs, and against closed forms.  Tolerances (north star): <= 1e-12 relative to
+sum|w_i f_i| for fixed rules and sampled sums; adaptive solves within the requested tolerance of the
+oracle and of the closed form, error estimates within a factor 4 of each other."""
+import math
+
+import numpy as np
+import pytest
+
+import integrals_b200 as ib
+from util_gpu import F, ORC_FAM, GENZ, genz_params, genz_exact
+
+pytestmark = pytest.mark.gpu
+INF = math.inf
+
+
+@pytest.fixture(scope="module")
+def eng():
+    return ib.Engine(0)
+
+
+@pytest.fixture(scope="module")
+def O():
+    import oracle
+    return oracle
+
+
+# ------------------------------------------------------------------------------------- sampled
+@pytest.mark.parametrize("rule", ["trapezoid", "simpson"])
+@pytest.mark.parametrize("shape,dim", [((1000,), 0), ((2, 1000), 1), ((257, 1001), 1), ((1001, 130), 0),
+                                        ((6, 333, 5), 1), ((4096, 2048), 1), ((3, 7), 1), ((1, 5), 1), ((5, 1), 1)])
+@pytest.mark.parametrize("uniform", [True, False])
+def test_sampled_matches_oracle(eng, O, rule, shape, dim, uniform):
+    rng = np.random.default_rng(11)
+    n = shape[dim]
+    if not uniform and ((rule == "simpson" and n <= 2) or n < 2):
+        pytest.skip("grid too short for the non-uniform rule")
+    y = np.asfortranarray(rng.standard_normal(shape) + 1.5)
+    x = None if uniform else np.sort(rng.random(n)) * 2.0 + 0.1
+    h = 0.37 if uniform else None
+    ref = np.atleast_1d(O.sampled_evalrule(rule, y, x=x, h=h, dim=dim))
+    inner = int(np.prod(shape[:dim], dtype=np.int64)); outer = int(np.prod(shape[dim + 1:], dtype=np.int64))
+    got = eng.sampled(rule, y, inner, n, outer, h=h or 0.0, x=x)[:inner * outer]
+    w = O.sampled_weights(rule, n, h=h, x=x)
+    scale = np.atleast_1d(np.tensordot(np.abs(y), np.abs(w), axes=([dim], [0]))).ravel(order="F")
+    assert np.all(np.abs(got - ref.ravel(order="F")) <= 1e-12 * scale)
+
+
+def test_sampled_reference_known_answers(eng):
+    # test/sampled_tests.jl:14-29: x^5 and cos on [0.4, 1.1], 1000 points
+    lb, ub, n = 0.4, 1.1, 1000
+    grid = np.linspace(lb, ub, n); h = (ub - lb) / (n - 1)
+    for rule in ("trapezoid", "simpson"):
+        for f, ex in ((lambda v: v ** 5, (ub ** 6 - lb ** 6) / 6), (np.cos, math.sin(ub) - math.sin(lb))):
+            assert abs(eng.sampled(rule, f(grid), 1, n, 1, h=h)[0] - ex) < 1e-4
+    out = eng.sampled("trapezoid", np.ones((2, 3), order="F"), 2, 3, 1, x=np.array([0.0, 1.0, 2.0]))   # :35-43
+    assert np.array_equal(out[:2], [2.0, 2.0])
+
+
+def test_sampled_errors(eng):
+    with pytest.raises(ib.IB200Error, match="No points to integrate"):
+        eng.sampled("trapezoid", np.zeros((3, 0), order="F"), 3, 0, 1, h=1.0)
+    with pytest.raises(ib.IB200Error, match="must exceed 2"):
+        eng.sampled("simpson", np.zeros(2), 1, 2, 1, x=np.array([0.0, 1.0]))
+
+
+def test_sampled_device_pointers(eng, O):
+    import torch
+    rng = np.random.default_rng(5)
+    m, n = 512, 4096
+    y = np.asfortranarray(rng.random((m, n)) + 0.5)
+    yt = torch.from_numpy(np.ascontiguousarray(y.T)).cuda()      # row-major [n, m] == column-major [m, n]
+    out = torch.empty(m, dtype=torch.float64, device="cuda")
+    eng.sampled("simpson", yt, m, n, 1, h=1e-3, out=out)
+    eng.synchronize()
+    ref = O.sampled_evalrule("simpson", y, h=1e-3, dim=1)
+    assert np.allclose(out.cpu().numpy(), ref, rtol=1e-13, atol=0)
+
+
+# ------------------------------------------------------------------------------------- fixed rules
+@pytest.mark.parametrize("family", GENZ + ["cosprod", "explin"])
+@pytest.mark.parametrize("dim,n1d", [(1, 64), (2, 24), (3, 16)])
+def test_tensor_rule_matches_oracle(eng, O, gl, family, dim, n1d):
+    nprob = 33
+    x, w = gl(n1d)
+    if family in GENZ:
+        par = genz_params(family, dim, nprob, scale=0.5)
+    else:
+        par = np.asfortranarray(np.random.default_rng(3).random((dim, nprob)) * 3.0 - 1.0)
+    lb, ub = np.zeros(dim), np.ones(dim)
+    got = eng.fixed_rule_tensor_batch(F[family], dim, lb, ub, par, x, w)
+    ref = O.fixed_tensor_batch(ORC_FAM[family], lb, ub, par, x, w)
+    # condition-aware scale: sum |w f| <= vol * max|f|; use |ref| + a floor from the family's magnitude
+    scale = np.maximum(np.abs(ref), 1e-3 * np.max(np.abs(ref)))
+    assert np.all(np.abs(got - ref) <= 2e-12 * scale), np.max(np.abs(got - ref) / scale)
+
+
+def test_tensor_rule_closed_form_oscillatory(eng, gl):
+    # n = 64 tensor Gauss-Legendre in 3-D vs cos(2 pi u1 + sum a/2) prod 2 sin(a_i/2)/a_i
+    x, w = gl(64)
+    par = genz_params("genz_oscillatory", 3, 64)
+    got = eng.fixed_rule_tensor_batch(F["genz_oscillatory"], 3, np.zeros(3), np.ones(3), par, x, w)
+    exact = np.array([genz_exact("genz_oscillatory", par[:, k], 3) for k in range(par.shape[1])])
+    assert np.all(np.abs(got - exact) <= 1e-10)
+
+
+@pytest.mark.parametrize("tr", [0, 1, 2])
+def test_tensor_rule_infinite_domains(eng, O, gl, tr):
+    x, w = gl(40)
+    par = np.asfortranarray(np.array([[1.3, 0.8, 0.2, -0.1]]).T.repeat(5, axis=1))      # gauss: a1,a2,u1,u2
+    lb = np.array([-INF, 0.5]); ub = np.array([INF, INF])
+    got = eng.fixed_rule_tensor_batch(F["genz_gaussian"], 2, lb, ub, par, x, w, transform=tr)
+    ref = O.fixed_tensor_batch("gauss", lb, ub, par, x, w, tr=["if_inf", "tan", "cot"][tr])
+    assert np.all(np.abs(got - ref) <= 1e-12 * np.abs(ref))
+
+
+@pytest.mark.parametrize("family,dim", [("cosprod", 1), ("cosprod", 2), ("genz_gaussian", 3), ("genz_product_peak", 4)])
+def test_nodes_rule_matches_oracle(eng, O, family, dim):
+    rng = np.random.default_rng(9)
+    N = 5000 if dim > 1 else 300
+    nodes = rng.random((N, dim)) * 2 - 1
+    wts = rng.random(N) * 2.0 / N
+    nprob = 21
+    par = genz_params(family, dim, nprob, scale=0.3) if family in GENZ else np.asfortranarray(rng.random((dim, nprob)) * 2)
+    lb = rng.random((dim, nprob)) - 1.0; ub = lb + 0.5 + rng.random((dim, nprob))     # per-problem bounds
+    lb = np.asfortranarray(lb); ub = np.asfortranarray(ub)
+    got = eng.fixed_rule_nodes_batch(F[family], dim, lb, ub, par, nodes, wts)
+    ref = O.fixed_nodes_batch(ORC_FAM[family], lb, ub, par, nodes, wts)
+    scale = np.maximum(np.abs(ref), 1e-3 * np.max(np.abs(ref)))
+    assert np.all(np.abs(got - ref) <= 2e-12 * scale)
+
+
+def test_quadrule_reference_known_answers(eng, gl):
+    # test/quadrule_tests.jl:27-36 (1-D trapz rule, n = 1000) and :41-55 (2-D tensor trapz, n = 100)
+    def trapz(n):
+        x = np.linspace(-1, 1, n); h = x[1] - x[0]
+        w = np.full(n, h); w[0] = w[-1] = h / 2
+        return x, w
+    x, w = trapz(1000)
+    got = eng.fixed_rule_nodes_batch(F["cosprod"], 1, np.array([-1.2]), np.array([3.5]), np.array([[2.0]]), x.reshape(-1, 1), w)
+    assert got[0] == pytest.approx((math.sin(2 * 3.5) - math.sin(2 * -1.2)) / 2, rel=1e-3)
+    x, w = trapz(100)
+    lb, ub, p = np.array([-1.2, -1.0]), np.array([3.5, 3.7]), 1.2
+    got = eng.fixed_rule_tensor_batch(F["cosprod"], 2, lb, ub, np.array([[p], [p]]), x, w)
+    exact = math.prod((math.sin(p * u) - math.sin(p * l)) / p for l, u in zip(lb, ub))
+    assert got[0] == pytest.approx(exact, rel=1e-3)
+    # :59-69 Lorentzian p/(x^2+p^2) on (-inf, inf) with gausslegendre(1000): product peak a = 1/p, u = 0, times 1/p
+    x, w = gl(1000)
+    got = eng.fixed_rule_nodes_batch(F["genz_product_peak"], 1, np.array([-INF]), np.array([INF]),
+                                     np.array([[1.0], [0.0]]), x.reshape(-1, 1), w)
+    assert got[0] == pytest.approx(math.pi, rel=1e-4)
+
+
+def test_gauss_legendre_reference_known_answers(eng, O, gl):
+    # test/gaussian_quadrature_tests.jl:48-60: 5x + sin x - p e^x on (-5, 3), p = 3.3, n = 250, subintervals 1 and 7
+    x, w = gl(250)
+    exact = -math.exp(3) * 3.3 + 3.3 / math.exp(5) - 40 + math.cos(5) - math.cos(3)
+    for sub in (1, 7):
+        got = eng.gauss_legendre_batch(F["gltest"], np.array([-5.0]), np.array([3.0]), np.array([[3.3]]), x, w, subintervals=sub)
+        assert got[0] == pytest.approx(exact, rel=1.5e-8)
+        ref = O.gauss_legendre_batch("gltest", -5.0, 3.0, np.array([[3.3]]), x, w, subintervals=sub)
+        assert abs(got[0] - ref[0]) <= 1e-12 * 300
+    # :62-88 exp(-x^2) on half / whole line, subintervals 1 and 17  (gaussian a = 1, u = 0)
+    par = np.array([[1.0], [0.0]])
+    for sub in (1, 17):
+        for lb, ub, ex in ((0.0, INF, math.sqrt(math.pi) / 2), (-INF, INF, math.sqrt(math.pi)), (-INF, 0.0, math.sqrt(math.pi) / 2)):
+            got = eng.gauss_legendre_batch(F["genz_gaussian"], np.array([lb]), np.array([ub]), par, x, w, subintervals=sub)
+            assert got[0] == pytest.approx(ex, rel=1.5e-8)
+
+
+# ------------------------------------------------------------------------------------- QuadGK
+def _check_adaptive(I, E, st, Iref, Eref, reltol, abstol, exact=None):
+    tol = np.maximum(abstol, reltol * np.abs(Iref))
+    assert np.all(st == 0)
+    assert np.all(np.abs(I - Iref) <= tol)
+    if exact is not None:
+        assert np.all(np.abs(I - exact) <= tol)
+    ok = (E <= 4 * Eref + 1e-300) & (Eref <= 4 * E + 1e-300)
+    assert np.all(ok | ((E <= 1e-14 * np.abs(I)) & (Eref <= 1e-14 * np.abs(Iref))))
+
+
+def test_quadgk_readme_example(eng):
+    I, E, ne, st = eng.quadgk_batch(F["sinxp"], np.array([-2.0]), np.array([5.0]), np.array([[1.7]]), reltol=1e-10)
+    assert st[0] == 0 and ne[0] == 75
+    assert I[0] == pytest.approx((math.cos(-3.4) - math.cos(8.5)) / 1.7, rel=1e-14)
+    assert E[0] == pytest.approx(5.688e-9, rel=1e-3)
+
+
+@pytest.mark.parametrize("abstol", [1e-8, 1e-12])
+def test_quadgk_sweep_matches_oracle(eng, O, abstol):
+    # config C1 at reduced size: p_k = 0.1 + 63.9 k/(n-1)
+    n = 2048
+    p = (0.1 + 63.9 * np.arange(n) / (n - 1)).reshape(1, n)
+    I, E, ne, st = eng.quadgk_batch(F["sinxp"], np.array([-2.0]), np.array([5.0]), p, reltol=1e-10, abstol=abstol)
+    Ir, Er, ner, str_ = O.quadgk_batch("sinxp", -2.0, 5.0, p, reltol=1e-10, abstol=abstol, nthreads=O.max_threads())
+    exact = (np.cos(-2 * p[0]) - np.cos(5 * p[0])) / p[0]
+    _check_adaptive(I, E, st, Ir, Er, 1e-10, abstol, exact)
+    assert np.mean(ne == ner) > 0.98          # same refinement sequence except for rounding-level ties
+    assert np.all(np.abs(I - Ir) <= 1e-13 * np.maximum(np.abs(Ir), 1e-2))
+
+
+@pytest.mark.parametrize("tr", [0, 1, 2])
+def test_quadgk_infinite_domains(eng, O, tr):
+    trn = ["if_inf", "tan", "cot"][tr]
+    cases = [(-INF, INF), (INF, -INF), (0.0, INF), (0.0, -INF), (-INF, 0.0), (INF, 0.0), (2.0, INF), (-INF, 2.0), (1.0, 4.0), (4.0, 1.0)]
+    lb = np.array([c[0] for c in cases]); ub = np.array([c[1] for c in cases])
+    for fam, par in (("genz_gaussian", [0.7, 0.3]), ("genz_product_peak", [1.0, 2.0])):
+        P = np.asfortranarray(np.array([par] * len(cases)).T)
+        I, E, ne, st = eng.quadgk_batch(F[fam], lb, ub, P, reltol=1e-9, abstol=1e-12, transform=tr)
+        Ir, Er, ner, _ = O.quadgk_batch(ORC_FAM[fam], lb, ub, P, tr=trn, reltol=1e-9, abstol=1e-12)
+        _check_adaptive(I, E, st, Ir, Er, 1e-9, 1e-12)
+        assert np.all(np.abs(I - Ir) <= 1e-12 * np.abs(Ir))
+    # known answers: test/inf_integral_tests.jl:85-150 (normal pdf, Lorentzians) via the registered families
+    I, *_ = eng.quadgk_batch(F["genz_product_peak"], np.array([-INF]), np.array([INF]), np.array([[1.0], [0.0]]), reltol=0.0, abstol=1e-3, transform=tr)
+    assert abs(I[0] - math.pi) < 1e-3
+    I, *_ = eng.quadgk_batch(F["gausspoly"], np.array([INF]), np.array([-INF]),
+                             np.array([[math.sqrt(0.5)], [0.0], [0.0], [1 / math.sqrt(2 * math.pi)]]), reltol=0.0, abstol=1e-3, transform=tr)
+    assert abs(I[0] + 1.0) < 1e-3
+
+
+def test_quadgk_maxevals_and_status(eng, O):
+    p = np.array([[50.0, 60.0]])
+    I, E, ne, st = eng.quadgk_batch(F["sinxp"], np.array([-2.0]), np.array([5.0]), p, reltol=1e-12, abstol=0.0, maxevals=300)
+    Ir, Er, ner, str_ = O.quadgk_batch("sinxp", -2.0, 5.0, p, reltol=1e-12, abstol=0.0, maxiters=300)
+    assert np.all(st == 1) and np.all(str_ == 1) and np.array_equal(ne, ner)
+    assert np.allclose(I, Ir, rtol=1e-12, atol=1e-14)
+    with pytest.raises(ib.IB200Error, match="one-dimensional"):
+        eng.quadgk_batch(F["genz_gaussian"], np.zeros(1), np.ones(1), np.zeros((4, 1)))
+
+
+# ------------------------------------------------------------------------------------- HCubature
+@pytest.mark.parametrize("family", GENZ)
+@pytest.mark.parametrize("dim", [2, 3, 4])
+def test_hcubature_matches_oracle(eng, O, family, dim):
+    nprob = 24
+    par = genz_params(family, dim, nprob, scale=0.25)
+    lb, ub = np.zeros(dim), np.ones(dim)
+    reltol, abstol, cap = 1e-6, 1e-8, 400000
+    I, E, ne, st = eng.hcubature_batch(F[family], dim, lb, ub, par, reltol=reltol, abstol=abstol, maxevals=cap)
+    Ir, Er, ner, str_ = O.hcubature_batch(ORC_FAM[family], lb, ub, par, reltol=reltol, abstol=abstol, maxiters=cap,
+                                          nthreads=O.max_threads())
+    assert np.array_equal(st, str_)
+    conv = st == 0
+    tol = np.maximum(abstol, reltol * np.abs(Ir))
+    assert np.all(np.abs(I - Ir)[conv] <= tol[conv])
+    assert np.all((E <= 4 * Er + 1e-300) & (Er <= 4 * E + 1e-300))
+    if family != "genz_discontinuous":      # GM on a discontinuity: parity with the reference, not accuracy
+        exact = np.array([genz_exact(family, par[:, k], dim) for k in range(nprob)])
+        assert np.all(np.abs(I - exact)[conv] <= 10 * tol[conv])
+    assert np.mean(ne == ner) > 0.7         # identical refinement sequences except at rounding-level ties
+
+
+def test_hcubature_1d_and_infinite(eng, O):
+    cases = [(-INF, INF), (INF, -INF), (0.0, INF), (-INF, 0.0), (1.0, 4.0), (4.0, 1.0)]
+    lb = np.array([[c[0]] for c in cases]).T; ub = np.array([[c[1]] for c in cases]).T
+    P = np.asfortranarray(np.array([[0.9, 0.2]] * len(cases)).T)
+    for tr, trn in enumerate(["if_inf", "tan", "cot"]):
+        I, E, ne, st = eng.hcubature_batch(F["genz_gaussian"], 1, np.asfortranarray(lb), np.asfortranarray(ub), P,
+                                           reltol=1e-8, abstol=1e-12, transform=tr)
+        Ir, Er, ner, _ = O.hcubature_batch("gauss", np.asfortranarray(lb), np.asfortranarray(ub), P, tr=trn, reltol=1e-8, abstol=1e-12)
+        assert np.all(st == 0) and np.all(np.abs(I - Ir) <= 1e-8 * np.abs(Ir))
+    # 2-D Gaussians over infinite / semi-infinite / flipped domains: test/inf_integral_tests.jl:42-66
+    s = 1 / math.sqrt(0.8)
+    par = np.array([[s], [s], [0.0], [0.0]])
+    for lbv, ubv, sol in (([-INF, -INF], [INF, INF], 1.0), ([INF, INF], [-INF, -INF], 1.0),
+                          ([-INF, 0.0], [INF, INF], 0.5), ([-INF, -INF], [INF, 0.0], 0.5)):
+        I, E, ne, st = eng.hcubature_batch(F["genz_gaussian"], 2, np.array(lbv), np.array(ubv), par, reltol=0.0, abstol=1e-3)
+        assert abs(I[0] / (2 * math.pi * 0.4) - sol) < 1e-3
+        Ir, *_ = O.hcubature_batch("gauss", np.array(lbv), np.array(ubv), par, reltol=0.0, abstol=1e-3)
+        assert abs(I[0] - Ir[0]) <= 1e-3
+
+
+def test_hcubature_initdiv_and_budget(eng, O):
+    par = genz_params("genz_gaussian", 3, 8, scale=0.5)
+    lb, ub = np.zeros(3), np.ones(3)
+    I, E, ne, st = eng.hcubature_batch(F["genz_gaussian"], 3, lb, ub, par, reltol=1e-7, abstol=0.0, initdiv=3)
+    Ir, Er, ner, str_ = O.hcubature_batch("gauss", lb, ub, par, reltol=1e-7, abstol=0.0, initdiv=3)
+    assert np.all(st == 0) and np.all(np.abs(I - Ir) <= 1e-7 * np.abs(Ir))
+    I, E, ne, st = eng.hcubature_batch(F["genz_oscillatory"], 3, lb, ub, genz_params("genz_oscillatory", 3, 4),
+                                       reltol=1e-13, abstol=0.0, maxevals=5000)
+    assert np.all(st == 1) and np.all(ne >= 5000) and np.all(ne < 5000 + 66)
