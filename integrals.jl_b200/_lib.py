@@ -164,10 +164,17 @@ class Engine:
             if params.ndim == 1:
                 params = params.reshape(-1, 1, order="F")
             nparam, nprob = params.shape
-        if hasattr(lb, "data_ptr"):
-            bpp = 1 if lb.dim() == 2 else 0
+        # bounds: `dim` numbers shared by all problems, or dim x nprob (1-D problems: a vector of nprob)
+        nd = lb.dim() if hasattr(lb, "data_ptr") else lb.ndim
+        nel = lb.numel() if hasattr(lb, "data_ptr") else lb.size
+        if nd == 2:
+            bpp = 1
+        elif nel == dim:
+            bpp = 0
+        elif dim == 1 and nel == nprob:
+            bpp = 1
         else:
-            bpp = 1 if lb.ndim == 2 else 0
+            raise ValueError(f"bounds must have {dim} entries or be {dim} x {nprob}; got {nel}")
         return params, nparam, nprob, bpp
 
     # ---- sampled -----------------------------------------------------------------------------

@@ -9,18 +9,21 @@
 // error, halve it along the axis of largest fourth difference, apply the rule to both halves,
 // update I and E by difference; finally re-sum I and E over all boxes.
 //
-// B200 mapping
-//   * persistent warps pull problems from a global atomic counter;
-//   * the 2*NP points of the two child boxes are spread over the 32 lanes (4-D: 114 points in 4
-//     passes); every lane keeps weighted partial sums of both rules, the warp combines them with
-//     xor-shuffles; the 1+4D axis values needed for the fourth differences go through a small
-//     shared-memory stage;
-//   * the reference's binary heap is replaced by a two-level tournament per warp: the error keys of
-//     all boxes live in global memory in groups of 64, the maximum of every group lives in shared
-//     memory.  Selecting the worst box = strided scan of the shared level + REDUX arg-max, one
-//     coalesced 512-byte key-group load + REDUX arg-max, one broadcast record load.  Child 1
-//     overwrites the parent's slot, child 2 is appended.  Same selection order as the reference
-//     (largest error first; ties -> lowest slot).
+// B200 mapping (everything per warp; a persistent grid pulls problems from an atomic counter)
+//   * Rule evaluation in two phases.  The Genz-Malik points of a box only use 7 abscissae per axis
+//     (centre, +-l2, +-l3, +-l5 half-widths), and every registered integrand has the separable form
+//     f(x) = finish(init (+|*) term_1(x_1) ... term_d(x_d)) (family.cuh).  Phase 1 tabulates the
+//     2 boxes x d axes x 7 abscissae per-axis terms (variable transform included) in shared memory;
+//     phase 2 spreads the 2*NP points over the lanes, each folding d table entries and applying
+//     finish (the transcendental) once.  The integrand is still evaluated at every point of the rule.
+//   * Weighted sums of both rules are combined with xor-shuffles so that lanes 0-15 end up with
+//     child 0 and lanes 16-31 with child 1; each half-warp then forms (I, E) and picks the split
+//     axis of its child from the fourth differences.
+//   * The reference's binary heap is replaced by a two-level tournament: error keys of all boxes in
+//     global memory in groups of 64, the maximum of every group in shared memory.  Selecting the
+//     worst box = strided scan of the shared level + REDUX arg-max, one coalesced 512-byte key-group
+//     load + REDUX arg-max.  Child 0 overwrites the parent's slot, child 1 is appended.  Selection
+//     order is the reference's (largest error first; ties -> lowest slot).
 #pragma once
 #include "common.cuh"
 #include "family.cuh"
@@ -36,13 +39,15 @@ struct Params {
     const double *lb, *ub; int bpp, tr;
     double rtol, atol; int64_t maxevals; int initdiv;
     int cap;                    // boxes per warp (multiple of kGroup)
-    double *keys;               // [warps][cap]
-    double *recs;               // [warps][cap][RECW]
+    double *keys;               // [warps][cap]        error of every box
+    double *ivals;              // [warps][cap]        integral of every box
+    double *recs;               // [warps][cap][RECW]  a[D], b[D], kdiv
     unsigned long long *counter;
     double *out_I, *out_E; int64_t *out_nevals; int32_t *out_status;
 };
 
 __host__ __device__ constexpr int gm_npoints(int d) { return d == 1 ? 15 : 1 + 4 * d + 2 * d * (d - 1) + (1 << d); }
+__host__ __device__ constexpr int rec_width(int d) { return 2 * d + 1; }
 
 __constant__ double c_x[8] = {
     -0.991455371120812639206854697526329, -0.949107912342758524526189684047851,
@@ -77,53 +82,75 @@ __device__ __forceinline__ unsigned long long warp_max_key(unsigned long long ke
 }
 __device__ __forceinline__ unsigned long long dkey(double e) { return (unsigned long long)__double_as_longlong(e); }
 
+// per-warp shared-memory footprint in doubles (besides the tournament level)
+template <int D> __host__ __device__ constexpr int warp_stage_doubles() {
+    // tabT[2][D][7] + tabJ[2][D][7] + fst[2][1+4D] + hs[2][D] + box[2][2D] + par[3D+1] + lb[D] + ub[D] + den[D]
+    return 14 * D + 14 * D + 2 * (1 + 4 * D) + 2 * D + 4 * D + (3 * D + 1) + 3 * D;
+}
+
 template <int FAM, int D, bool ALLFIN>
 __global__ void __launch_bounds__(kBlock)
 hcub_kernel(const Params p) {
+    using F = ib::Family<FAM, D>;
     constexpr int NP = gm_npoints(D);
-    constexpr int RECW = 2 * D + 3;            // a[D], b[D], I, E, kdiv
+    constexpr int RECW = rec_width(D);
     constexpr int NAX = 1 + 4 * D;             // centre + lambda2/lambda3 axis points (D >= 2)
+    constexpr int NPAR = ib::fam_nparam(FAM, D);
     extern __shared__ double sm[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t gwarp = (int64_t)blockIdx.x * kWarpsPerBlock + wib;
     const int ngroups = p.cap / kGroup;
-    // shared layout: [warps][ngroups] group maxima ; [warps][2][NAX] axis-value stage ; point table
+    // shared layout: [warps][ngroups] group maxima ; [warps] stage ; weights[10] ; point table
     unsigned long long *L1 = reinterpret_cast<unsigned long long *>(sm) + (size_t)wib * ngroups;
-    double *fst = sm + (size_t)kWarpsPerBlock * ngroups + (size_t)wib * 2 * NAX;
-    unsigned *pt = reinterpret_cast<unsigned *>(sm + (size_t)kWarpsPerBlock * ngroups + (size_t)kWarpsPerBlock * 2 * NAX);
+    double *stage = sm + (size_t)kWarpsPerBlock * ngroups + (size_t)wib * warp_stage_doubles<D>();
+    double *tabT = stage;                      // [2][D][7]
+    double *tabJ = tabT + 14 * D;              // [2][D][7]
+    double *fst = tabJ + 14 * D;               // [2][NAX]
+    double *hs = fst + 2 * NAX;                // [2][D]
+    double *box = hs + 2 * D;                  // [2][2D]  a[D], b[D] of the two boxes under evaluation
+    double *par = box + 4 * D;                 // [NPAR] (<= 3D+1)
+    double *lbs = par + (3 * D + 1);           // [D]
+    double *ubs = lbs + D;                     // [D]
+    double *dens = ubs + D;                    // [D]  (ALLFIN) (ub-lb)*0.5
+    double *wtab = sm + (size_t)kWarpsPerBlock * ngroups + (size_t)kWarpsPerBlock * warp_stage_doubles<D>();  // [10]
+    unsigned *pt = reinterpret_cast<unsigned *>(wtab + 10);
     double *keys = p.keys + (size_t)gwarp * p.cap;
+    double *ivals = p.ivals + (size_t)gwarp * p.cap;
     double *recs = p.recs + (size_t)gwarp * p.cap * RECW;
 
-    // ---- Genz-Malik constants (HCubature.jl genz-malik.jl; oracle gm_rule)
     const double l2 = sqrt(9.0 / 70.0), l3 = sqrt(9.0 / 10.0), l5 = sqrt(9.0 / 19.0);
-    const double twon = (double)(1 << D);
-    double wcls[5], wpcls[5];
-    wcls[0] = twon * ((12824 - 9120 * D + 400 * D * D) / 19683.0);
-    wcls[1] = twon * (980 / 6561.0);
-    wcls[2] = twon * ((1820 - 400 * D) / 19683.0);
-    wcls[3] = twon * (200 / 19683.0);
-    wcls[4] = 6859 / 19683.0;
-    wpcls[0] = twon * ((729 - 950 * D + 50 * D * D) / 729.0);
-    wpcls[1] = twon * (245 / 486.0);
-    wpcls[2] = twon * ((265 - 100 * D) / 1458.0);
-    wpcls[3] = twon * (25 / 729.0);
-    wpcls[4] = 0.0;
-
-    // ---- point table: bits 0-7 axes with an offset, 8-15 negative-sign axes, 16-18 class
     if (D >= 2) {
+        // Genz-Malik weights (HCubature.jl genz-malik.jl; oracle gm_rule): wtab[cls], wtab[5 + cls]
+        if (threadIdx.x == 0) {
+            const double twon = (double)(1 << D);
+            wtab[0] = twon * ((12824 - 9120 * D + 400 * D * D) / 19683.0);
+            wtab[1] = twon * (980 / 6561.0);
+            wtab[2] = twon * ((1820 - 400 * D) / 19683.0);
+            wtab[3] = twon * (200 / 19683.0);
+            wtab[4] = 6859 / 19683.0;
+            wtab[5] = twon * ((729 - 950 * D + 50 * D * D) / 729.0);
+            wtab[6] = twon * (245 / 486.0);
+            wtab[7] = twon * ((265 - 100 * D) / 1458.0);
+            wtab[8] = twon * (25 / 729.0);
+            wtab[9] = 0.0;
+        }
+        // point table: 3 bits per axis = abscissa index (0 centre, 1/2 +-l2, 3/4 +-l3, 5/6 +-l5); class in bits 24-26
         for (int q = threadIdx.x; q < NP; q += kBlock) {
-            unsigned m = 0, sg = 0, cls = 0;
+            unsigned e = 0, cls = 0;
             if (q == 0) { cls = 0; }
-            else if (q < 1 + 2 * D) { const int r = q - 1; cls = 1; m = 1u << (r >> 1); sg = (r & 1) ? m : 0; }
-            else if (q < 1 + 4 * D) { const int r = q - 1 - 2 * D; cls = 2; m = 1u << (r >> 1); sg = (r & 1) ? m : 0; }
+            else if (q < 1 + 2 * D) { const int r = q - 1; cls = 1; e = (1u + (r & 1)) << (3 * (r >> 1)); }
+            else if (q < 1 + 4 * D) { const int r = q - 1 - 2 * D; cls = 2; e = (3u + (r & 1)) << (3 * (r >> 1)); }
             else if (q < 1 + 4 * D + 2 * D * (D - 1)) {
                 int r = q - 1 - 4 * D; const int s = r & 3; r >>= 2;
                 int i = 0, j = 1;
                 for (int cnt = 0; cnt < r; cnt++) { if (++j == D) { ++i; j = i + 1; } }
-                cls = 3; m = (1u << i) | (1u << j);
-                sg = ((s & 2) ? (1u << i) : 0) | ((s & 1) ? (1u << j) : 0);
-            } else { const unsigned r = q - (1 + 4 * D + 2 * D * (D - 1)); cls = 4; m = (1u << D) - 1; sg = r; }
-            pt[q] = m | (sg << 8) | (cls << 16);
+                cls = 3;
+                e = ((3u + ((s >> 1) & 1)) << (3 * i)) | ((3u + (s & 1)) << (3 * j));
+            } else {
+                const unsigned r = q - (1 + 4 * D + 2 * D * (D - 1)); cls = 4;
+                for (int k = 0; k < D; k++) e |= (5u + ((r >> k) & 1u)) << (3 * k);
+            }
+            pt[q] = e | (cls << 24);
         }
     }
     __syncthreads();
@@ -139,25 +166,43 @@ hcub_kernel(const Params p) {
         if ((int64_t)pidx >= p.nprob) break;
         const int64_t prob = (int64_t)pidx;
 
-        ib::Problem<FAM, D, ALLFIN> P;
-        const double *lbp = p.bpp ? p.lb + prob * D : p.lb;
-        const double *ubp = p.bpp ? p.ub + prob * D : p.ub;
-        P.load(p.params + prob * p.nparam, lbp, ubp, p.tr);
+        // ---- problem data -> shared
+        __syncwarp();
+        if (lane < NPAR) par[lane] = p.params[prob * p.nparam + lane];
+        if (lane < D) {
+            const double l = p.bpp ? p.lb[prob * D + lane] : p.lb[lane];
+            const double u = p.bpp ? p.ub[prob * D + lane] : p.ub[lane];
+            lbs[lane] = l; ubs[lane] = u; dens[lane] = (u - l) * 0.5;
+        }
+        __syncwarp();
+        double jacc = 1.0;                      // ALLFIN: constant Jacobian prod_k den_k
+        if (ALLFIN) {
+#pragma unroll
+            for (int k = 0; k < D; k++) jacc = (k == 0) ? dens[0] : jacc * dens[k];
+        }
+        const double finit = F::sep_init(par);
 
-        // rule on two boxes: (A0,B0) and (A1,B1); results uniform in all lanes
-        auto rule2 = [&](const double (&A0)[D], const double (&B0)[D], const double (&A1)[D], const double (&B1)[D],
-                         bool second, double &I0, double &E0, int &k0, double &I1, double &E1, int &k1) {
+        // t -> (u, jac) on axis k
+        auto map_axis = [&](int k, double t, double &u, double &jac) {
+            if (ALLFIN) { u = lbs[k] + (1.0 + t) * dens[k]; jac = 1.0; }
+            else { ib::AxisMap m; ib::make_axis(lbs[k], ubs[k], m); ib::t2ujac(p.tr, t, m, u, jac); }
+        };
+
+        // rule on the two boxes staged in box[0], box[1]; results uniform in all lanes
+        auto rule2 = [&](bool second, double &I0, double &E0, int &k0, double &I1, double &E1, int &k1) {
             if constexpr (D == 1) {
                 // HCubature's 1-D rule: GK(7,15) about the centre with signed half-width
-                const bool hi = lane >= 16;
-                const int j = lane & 15;
-                const double a = hi ? A1[0] : A0[0], b = hi ? B1[0] : B0[0];
+                const int ch = lane >> 4, j = lane & 15;
+                const double a = box[2 * ch], b = box[2 * ch + 1];
                 const double c = (a + b) * 0.5, Dl = (b - a) * 0.5;
                 double g = 0.0;
-                if (j < 15 && (second || !hi)) {
+                if (j < 15 && (second || ch == 0)) {
                     const double dx = j < 14 ? Dl * c_x[j < 7 ? j : j - 7] : 0.0;
-                    double t[1] = {j < 7 ? c + dx : (j < 14 ? c - dx : c)};
-                    g = P(t);
+                    const double t = j < 7 ? c + dx : (j < 14 ? c - dx : c);
+                    double u, jac;
+                    map_axis(0, t, u, jac);
+                    const double T = F::sep_term(0, u, par);
+                    g = F::sep_finish(F::kProd ? finit * T : finit + T, par) * (ALLFIN ? jacc : jac);
                 }
                 const double partner = __shfl_down_sync(0xffffffffu, g, 7);
                 const double v = j < 7 ? g + partner : g;
@@ -173,87 +218,98 @@ hcub_kernel(const Params p) {
                 I1 = __shfl_sync(0xffffffffu, Ik, 16); E1 = __shfl_sync(0xffffffffu, Er, 16);
                 k0 = 0; k1 = 0;
             } else {
-                double sI[2] = {0.0, 0.0}, sP[2] = {0.0, 0.0};
+                // phase 1: per-axis term tables  idx = (ch*D + k)*7 + o
+                const int ntask = second ? 14 * D : 7 * D;
+                for (int idx = lane; idx < ntask; idx += 32) {
+                    const int ch = idx >= 7 * D;
+                    const int r = idx - ch * 7 * D;
+                    const int k = r / 7, o = r - 7 * k;
+                    const double a = box[ch * 2 * D + k], b = box[ch * 2 * D + D + k];
+                    const double c = 0.5 * (a + b), h = 0.5 * fabs(b - a);
+                    const double lam = o == 0 ? 0.0 : (o <= 2 ? l2 : (o <= 4 ? l3 : l5));
+                    const double dl = h * lam;
+                    const double t = o == 0 ? c : ((o & 1) ? c + dl : c - dl);
+                    double u, jac;
+                    map_axis(k, t, u, jac);
+                    tabT[idx] = F::sep_term(k, u, par);
+                    if (!ALLFIN) tabJ[idx] = jac;
+                    if (o == 0) hs[ch * D + k] = h;
+                }
+                __syncwarp();
+                // phase 2: the points
+                double sI0 = 0.0, sP0 = 0.0, sI1 = 0.0, sP1 = 0.0;
                 const int total = second ? 2 * NP : NP;
                 for (int w = lane; w < total; w += 32) {
                     const int ch = w >= NP;
                     const int q = w - ch * NP;
                     const unsigned e = pt[q];
-                    const unsigned cls = (e >> 16) & 7u;
-                    const double lam = cls == 1 ? l2 : (cls == 4 ? l5 : l3);
-                    double t[D];
+                    const double *tT = tabT + ch * 7 * D;
+                    const double *tJ = tabJ + ch * 7 * D;
+                    double acc = finit, jac = 1.0;
 #pragma unroll
                     for (int k = 0; k < D; k++) {
-                        const double a = ch ? A1[k] : A0[k], b = ch ? B1[k] : B0[k];
-                        const double c = 0.5 * (a + b);
-                        double x = c;
-                        if ((e >> k) & 1u) {
-                            const double dl = (0.5 * fabs(b - a)) * lam;
-                            x = ((e >> (8 + k)) & 1u) ? c - dl : c + dl;
-                        }
-                        t[k] = x;
+                        const int sel = (e >> (3 * k)) & 7u;
+                        const double T = tT[7 * k + sel];
+                        acc = F::kProd ? acc * T : acc + T;
+                        if (!ALLFIN) { const double J = tJ[7 * k + sel]; jac = (k == 0) ? J : jac * J; }
                     }
-                    const double f = P(t);
+                    const double f = F::sep_finish(acc, par) * (ALLFIN ? jacc : jac);
                     if (q < NAX) fst[ch * NAX + q] = f;
-                    sI[ch] = fma(wcls[cls], f, sI[ch]);
-                    sP[ch] = fma(wpcls[cls], f, sP[ch]);
+                    const unsigned cls = e >> 24;
+                    const double wI = wtab[cls], wP = wtab[5 + cls];
+                    if (ch) { sI1 = fma(wI, f, sI1); sP1 = fma(wP, f, sP1); }
+                    else    { sI0 = fma(wI, f, sI0); sP0 = fma(wP, f, sP0); }
                 }
+                // combine: lanes 0-15 keep child 0, lanes 16-31 keep child 1
+                const bool hi = lane >= 16;
+                double kI = hi ? sI1 : sI0, kP = hi ? sP1 : sP0;
+                kI += __shfl_xor_sync(0xffffffffu, hi ? sI0 : sI1, 16);
+                kP += __shfl_xor_sync(0xffffffffu, hi ? sP0 : sP1, 16);
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    sI[0] += __shfl_xor_sync(0xffffffffu, sI[0], off);
-                    sP[0] += __shfl_xor_sync(0xffffffffu, sP[0], off);
-                    sI[1] += __shfl_xor_sync(0xffffffffu, sI[1], off);
-                    sP[1] += __shfl_xor_sync(0xffffffffu, sP[1], off);
+                for (int off = 8; off > 0; off >>= 1) {
+                    kI += __shfl_xor_sync(0xffffffffu, kI, off);
+                    kP += __shfl_xor_sync(0xffffffffu, kP, off);
                 }
                 __syncwarp();
+                // per half-warp: volume, I, E, split axis (largest fourth difference, HCubature's tie fuzz)
+                const int ch = hi ? 1 : 0;
+                const double *hh = hs + ch * D;
+                const double *ff = fst + ch * NAX;
+                double V = hh[0];
 #pragma unroll
-                for (int ch = 0; ch < 2; ch++) {
-                    double V = 1.0;
+                for (int k = 1; k < D; k++) V *= hh[k];
+                const double Iv = V * kI, Ip = V * kP;
+                const double Er = fabs(Iv - Ip);
+                double p10 = 1.0;
 #pragma unroll
-                    for (int k = 0; k < D; k++) {
-                        const double dk = 0.5 * fabs((ch ? B1[k] : B0[k]) - (ch ? A1[k] : A0[k]));
-                        V = (k == 0) ? dk : V * dk;
-                    }
-                    const double I = V * sI[ch], Ip = V * sP[ch];
-                    const double Er = fabs(I - Ip);
-                    // split axis: largest fourth difference with HCubature's tie fuzz
-                    const double f1 = fst[ch * NAX];
-                    const double twelvef1 = 12 * f1;
-                    double p10 = 1.0;
+                for (int k = 0; k < D; k++) p10 *= 10.0;
+                const double deltaf = Er / (p10 * V);
+                const double twelvef1 = 12 * ff[0];
+                int kd = 0; double maxdd = 0.0, hkd = hh[0];
 #pragma unroll
-                    for (int k = 0; k < D; k++) p10 *= 10.0;
-                    const double deltaf = Er / (p10 * V);
-                    int kd = 0; double maxdd = 0.0, dkd = 0.5 * fabs((ch ? B1[0] : B0[0]) - (ch ? A1[0] : A0[0]));
-#pragma unroll
-                    for (int k = 0; k < D; k++) {
-                        const double f2k = fst[ch * NAX + 1 + 2 * k] + fst[ch * NAX + 2 + 2 * k];
-                        const double f3k = fst[ch * NAX + 1 + 2 * D + 2 * k] + fst[ch * NAX + 2 + 2 * D + 2 * k];
-                        const double dd = fabs(f3k + twelvef1 - 7 * f2k);
-                        const double dk = 0.5 * fabs((ch ? B1[k] : B0[k]) - (ch ? A1[k] : A0[k]));
-                        const double delta = dd - maxdd;
-                        if (delta > deltaf) { kd = k; maxdd = dd; dkd = dk; }
-                        else if (fabs(delta) <= deltaf && dk > dkd) { kd = k; dkd = dk; }
-                    }
-                    if (ch == 0) { I0 = I; E0 = Er; k0 = kd; } else { I1 = I; E1 = Er; k1 = kd; }
+                for (int k = 0; k < D; k++) {
+                    const double f2k = ff[1 + 2 * k] + ff[2 + 2 * k];
+                    const double f3k = ff[1 + 2 * D + 2 * k] + ff[2 + 2 * D + 2 * k];
+                    const double dd = fabs(f3k + twelvef1 - 7 * f2k);
+                    const double delta = dd - maxdd;
+                    if (delta > deltaf) { kd = k; maxdd = dd; hkd = hh[k]; }
+                    else if (fabs(delta) <= deltaf && hh[k] > hkd) { kd = k; hkd = hh[k]; }
                 }
+                I0 = __shfl_sync(0xffffffffu, Iv, 0);  E0 = __shfl_sync(0xffffffffu, Er, 0);  k0 = __shfl_sync(0xffffffffu, kd, 0);
+                I1 = __shfl_sync(0xffffffffu, Iv, 16); E1 = __shfl_sync(0xffffffffu, Er, 16); k1 = __shfl_sync(0xffffffffu, kd, 16);
                 __syncwarp();
             }
         };
 
-        // ---- pool helpers (uniform control flow; lane 0 writes)
+        // ---- pool helpers (uniform control flow)
         int nbox = 0;
-        auto write_rec = [&](int slot, const double (&A)[D], const double (&B)[D], double I, double E, int kd) {
-            if (lane == 0) {
-                double *r = recs + (size_t)slot * RECW;
-#pragma unroll
-                for (int k = 0; k < D; k++) { r[k] = A[k]; r[D + k] = B[k]; }
-                r[2 * D] = I; r[2 * D + 1] = E; r[2 * D + 2] = (double)kd;
-                keys[slot] = E;
-            }
+        auto write_box = [&](int slot, int ch, double I, double E, int kd) {
+            if (lane < RECW) recs[(size_t)slot * RECW + lane] = lane < 2 * D ? box[ch * 2 * D + lane] : (double)kd;
+            if (lane == 0) { keys[slot] = E; ivals[slot] = I; }
         };
-        auto append = [&](const double (&A)[D], const double (&B)[D], double I, double E, int kd) {
+        auto append = [&](int ch, double I, double E, int kd) {
             const int slot = nbox;
-            write_rec(slot, A, B, I, E, kd);
+            write_box(slot, ch, I, E, kd);
             if (lane == 0) {
                 const int g = slot / kGroup;
                 const unsigned long long k = dkey(E);
@@ -263,52 +319,50 @@ hcub_kernel(const Params p) {
             __syncwarp();
         };
 
-        // ---- initial box(es)
-        double a0[D], b0[D];
-        double tl[D], th[D];
-#pragma unroll
-        for (int k = 0; k < D; k++) {
-            tl[k] = ALLFIN ? -1.0 : P.ax[ALLFIN ? 0 : k].tlo;
-            th[k] = ALLFIN ? 1.0 : P.ax[ALLFIN ? 0 : k].thi;
-        }
+        // ---- initial box(es): HCubature's initdiv grid, CartesianIndices order (first index fastest)
         double I = 0.0, E = 0.0;
         int64_t nev = 0;
         int status = IB200_ST_CONVERGED;
         bool degenerate = false;
         {
             const int initdiv = p.initdiv;
-            double Dl[D]; double prodD = 1.0;
-#pragma unroll
-            for (int k = 0; k < D; k++) { Dl[k] = (th[k] - tl[k]) / initdiv; prodD *= Dl[k]; }
             int64_t total = 1;
+            double prodD = 1.0;
 #pragma unroll
-            for (int k = 0; k < D; k++) total *= initdiv;
-            if (prodD == 0.0) total = 1;           // HCubature returns after the first box
-            for (int64_t q = 0; q < total; q += 2) {   // CartesianIndices order, first index fastest
-                double A1[D], B1[D];
-                const bool second = q + 1 < total;
-                int64_t r0 = q, r1 = q + 1;
-#pragma unroll
-                for (int k = 0; k < D; k++) {
-                    const int c0 = (int)(r0 % initdiv), c1 = (int)(r1 % initdiv);
-                    r0 /= initdiv; r1 /= initdiv;
-                    a0[k] = tl[k] + c0 * Dl[k];
-                    b0[k] = (c0 == initdiv - 1) ? th[k] : a0[k] + Dl[k];
-                    A1[k] = tl[k] + c1 * Dl[k];
-                    B1[k] = (c1 == initdiv - 1) ? th[k] : A1[k] + Dl[k];
-                }
-                double I0, E0, I1, E1; int k0, k1;
-                rule2(a0, b0, A1, B1, second, I0, E0, k0, I1, E1, k1);
-                if (q == 0) { I = I0; E = E0; } else { I += I0; E += E0; }
-                nev += NP;
-                append(a0, b0, I0, E0, k0);
-                if (second) { I += I1; E += E1; nev += NP; append(A1, B1, I1, E1, k1); }
+            for (int k = 0; k < D; k++) {
+                total *= initdiv;
+                double tl, th;
+                if (ALLFIN) { tl = -1.0; th = 1.0; } else { ib::AxisMap m; ib::make_axis(lbs[k], ubs[k], m); tl = m.tlo; th = m.thi; }
+                prodD *= (th - tl) / initdiv;
             }
             degenerate = (prodD == 0.0);
+            if (degenerate) total = 1;              // HCubature returns after the first box
+            for (int64_t q = 0; q < total; q += 2) {
+                const bool second = q + 1 < total;
+                if (lane < 2 * D) {                 // lane -> (box, axis)
+                    const int ch = lane >= D, k = lane - ch * D;
+                    int64_t r = q + ch;
+                    for (int kk = 0; kk < k; kk++) r /= initdiv;
+                    const int c = (int)(r % initdiv);
+                    double tl, th;
+                    if (ALLFIN) { tl = -1.0; th = 1.0; } else { ib::AxisMap m; ib::make_axis(lbs[k], ubs[k], m); tl = m.tlo; th = m.thi; }
+                    const double Dl = (th - tl) / initdiv;
+                    const double a = tl + c * Dl;
+                    const double b = (c == initdiv - 1) ? th : a + Dl;
+                    box[ch * 2 * D + k] = a; box[ch * 2 * D + D + k] = b;
+                }
+                __syncwarp();
+                double I0, E0, I1, E1; int k0, k1;
+                rule2(second, I0, E0, k0, I1, E1, k1);
+                if (q == 0) { I = I0; E = E0; } else { I += I0; E += E0; }
+                nev += NP;
+                append(0, I0, E0, k0);
+                if (second) { I += I1; E += E1; nev += NP; append(1, I1, E1, k1); }
+            }
         }
 
         // ---- adaptive loop
-        if (!degenerate && status == IB200_ST_CONVERGED) {
+        if (!degenerate) {
             for (;;) {
                 if (E <= fmax(rtol * fabs(I), atol)) break;
                 if (nev >= p.maxevals) { status = IB200_ST_MAXEVALS; break; }
@@ -328,28 +382,29 @@ hcub_kernel(const Params p) {
                 unsigned long long kk = klo; int ki = s_lo < nbox ? s_lo : 0x7fffffff;
                 if (s_hi < nbox && khi > kk) { kk = khi; ki = s_hi; }
                 const int slot = warp_argmax(kk, ki);
-                // parent record (broadcast loads)
-                const double *r = recs + (size_t)slot * RECW;
-                double A[D], B[D];
-#pragma unroll
-                for (int k = 0; k < D; k++) { A[k] = r[k]; B[k] = r[D + k]; }
-                const double Ibox = r[2 * D], Ebox = r[2 * D + 1];
-                const int kd = (int)r[2 * D + 2];
-                // children: upper half first (ma = a with a[k] += w), then lower half (mb = b with b[k] -= w)
-                double A1[D], B2[D];
-#pragma unroll
-                for (int k = 0; k < D; k++) {
-                    const double w = (B[k] - A[k]) * 0.5;
-                    A1[k] = (k == kd) ? A[k] + w : A[k];
-                    B2[k] = (k == kd) ? B[k] - w : B[k];
+                // parent: error = its key, integral from ivals, geometry from the record
+                const double Ebox = __longlong_as_double((long long)warp_max_key(ki == slot ? kk : 0ULL));
+                const double Ibox = ivals[slot];
+                double rv = 0.0;
+                if (lane < RECW) rv = recs[(size_t)slot * RECW + lane];
+                const int kd = (int)__shfl_sync(0xffffffffu, rv, 2 * D);
+                // children: child 0 = upper half (a[kd] += w), child 1 = lower half (b[kd] -= w)
+                {
+                    const double akd = __shfl_sync(0xffffffffu, rv, kd), bkd = __shfl_sync(0xffffffffu, rv, D + kd);
+                    const double w = (bkd - akd) * 0.5;
+                    if (lane < 2 * D) {
+                        box[lane] = (lane == kd) ? akd + w : rv;
+                        box[2 * D + lane] = (lane == D + kd) ? bkd - w : rv;
+                    }
                 }
+                __syncwarp();
                 double I1, E1, I2, E2; int k1, k2;
-                rule2(A1, B, A, B2, true, I1, E1, k1, I2, E2, k2);
+                rule2(true, I1, E1, k1, I2, E2, k2);
                 nev += 2 * NP;
                 I += I1 + I2 - Ibox;
                 E += E1 + E2 - Ebox;
-                // child 1 replaces the parent's slot: recompute the group maximum from the keys in registers
-                write_rec(slot, A1, B, I1, E1, k1);
+                // child 0 replaces the parent's slot: recompute the group maximum from the keys in registers
+                write_box(slot, 0, I1, E1, k1);
                 {
                     const unsigned long long e1 = dkey(E1);
                     const unsigned long long nlo = (s_lo == slot) ? e1 : klo, nhi = (s_hi == slot) ? e1 : khi;
@@ -357,17 +412,14 @@ hcub_kernel(const Params p) {
                     if (lane == 0) L1[g] = gm;
                 }
                 __syncwarp();
-                append(A, B2, I2, E2, k2);
+                append(1, I2, E2, k2);
             }
         }
 
         // ---- re-sum over all boxes (HCubature's "roundoff paranoia"): lane-strided, then xor tree
         {
             double pI = 0.0, pE = 0.0;
-            for (int s = lane; s < nbox; s += 32) {
-                const double *r = recs + (size_t)s * RECW;
-                pI += r[2 * D]; pE += r[2 * D + 1];
-            }
+            for (int s = lane; s < nbox; s += 32) { pI += ivals[s]; pE += keys[s]; }
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
                 pI += __shfl_xor_sync(0xffffffffu, pI, off);
@@ -387,8 +439,7 @@ hcub_kernel(const Params p) {
 
 template <int D>
 inline size_t smem_bytes(int cap) {
-    constexpr int NAX = 1 + 4 * D;
-    return ((size_t)kWarpsPerBlock * (cap / kGroup) + (size_t)kWarpsPerBlock * 2 * NAX) * sizeof(double) +
+    return ((size_t)kWarpsPerBlock * (cap / kGroup) + (size_t)kWarpsPerBlock * warp_stage_doubles<D>() + 10) * sizeof(double) +
            (size_t)gm_npoints(D) * sizeof(unsigned) + 16;
 }
 
@@ -399,7 +450,7 @@ int32_t launch(ib200_ctx *ctx, int family, bool allfin, Params &p);
 
 template <int D>
 int32_t launch_impl(ib200_ctx *ctx, int family, bool allfin, Params &p) {
-    constexpr int RECW = 2 * D + 3;
+    constexpr int RECW = rec_width(D);
     const size_t smem = smem_bytes<D>(p.cap);
     if (smem > ctx->smem_optin) return ib200_fail(ctx, IB200_ERR_INVALID, "ib200_hcubature_batch: box capacity too large for shared memory");
     int32_t rc = IB200_ERR_UNSUPPORTED;
@@ -419,8 +470,10 @@ int32_t launch_impl(ib200_ctx *ctx, int family, bool allfin, Params &p) {
                 if (blocks > (int64_t)ctx->sm_count * occ) blocks = (int64_t)ctx->sm_count * occ;
                 const size_t warps = (size_t)blocks * kWarpsPerBlock;
                 p.keys = (double *)ctx->get(SL_WORK0, warps * p.cap * sizeof(double));
+                p.ivals = (double *)ctx->get(SL_WORK3, warps * p.cap * sizeof(double));
                 p.recs = (double *)ctx->get(SL_WORK2, warps * p.cap * RECW * sizeof(double));
-                if (!p.keys || !p.recs) return ib200_fail(ctx, IB200_ERR_OOM, "ib200_hcubature_batch: box pool allocation failed (lower maxiters or the hcub_capacity option)");
+                if (!p.keys || !p.ivals || !p.recs)
+                    return ib200_fail(ctx, IB200_ERR_OOM, "ib200_hcubature_batch: box pool allocation failed (lower maxiters or the hcub_capacity option)");
                 kern<<<(unsigned)blocks, kBlock, smem, ctx->stream>>>(p);
                 IB_LAUNCH_CHECK(ctx);
                 return IB200_OK;

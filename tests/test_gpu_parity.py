@@ -244,7 +244,7 @@ def test_hcubature_matches_oracle(eng, O, family, dim):
     tol = np.maximum(abstol, reltol * np.abs(Ir))
     assert np.all(np.abs(I - Ir)[conv] <= tol[conv])
     assert np.all((E <= 4 * Er + 1e-300) & (Er <= 4 * E + 1e-300))
-    if family != "genz_discontinuous":      # GM on a discontinuity: parity with the reference, not accuracy
+    if family not in ("genz_discontinuous", "genz_c0"):   # non-smooth: GM's estimate is unreliable -> parity with the reference, not accuracy
         exact = np.array([genz_exact(family, par[:, k], dim) for k in range(nprob)])
         assert np.all(np.abs(I - exact)[conv] <= 10 * tol[conv])
     assert np.mean(ne == ner) > 0.7         # identical refinement sequences except at rounding-level ties
