@@ -1,0 +1,479 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path of integrals.jl_b200 on BASELINE.json's metric.
+
+    python bench.py --gpus N --steps K --warmup W [--workload c4|c1|c2|c3] [--impl b200|reference]
+
+Default workload (the configuration the metric "fp64 integrals/sec at 1/2/4/8 B200 (batched
+GK/Genz-Malik)" is quoted on, BASELINE.json configs[3]): the HCubature Genz suite -- 6 families, 4-D,
+2^18 parameter sets per family, reltol 1e-6, abstol 1e-8 (reference default), evaluation cap 4e6
+(SURVEY 8(d) C4).  One step = one pass of ib200_hcubature_batch over the 6 x 2^18 problems.
+N > 1: one process per GPU (torchrun), every rank solves its own 6 x 2^18 problems (weak scaling, no
+data-path collective); `value` = all ranks' integrals / max-over-ranks time.
+
+Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM, CUDA-event timed.  `e2e`: the same
+step through the public solve() interface with host (pinned) inputs and host outputs, copies inside
+the timed region.  `roofline`: the dominant kernel against the FP64 DFMA peak measured live (this
+path is FP64-pipe bound; the sampled workload c2 is HBM bound against MEASURED_PEAKS.json).
+`cpu_baseline` / `--impl reference`: the CPU oracle (oracle/, a C restatement of the reference's
+algorithms -- Julia is not available) on all host cores over a bounded sample.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = {"c4": ("fp64 integrals/sec (batched Genz-Malik HCubature, Genz suite 4-D)", "integrals/s"),
+          "c1": ("fp64 integrals/sec (batched GK(7,15) QuadGK, sin(x*p) sweep)", "integrals/s"),
+          "c3": ("fp64 integrals/sec (fixed tensor Gauss-Legendre n=64 3-D, Genz oscillatory)", "integrals/s"),
+          "c2": ("sampled GB/s (trapezoid + Simpson over 4096 x 1048576 fp64)", "GB/s")}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c4", choices=list(METRIC))
+    ap.add_argument("--nprob", type=int, default=0, help="override the problems per family/batch (smoke runs only)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the short c1/c2/c3 side measurements")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks: nvidia-smi sampled DURING the timed region (B200_PROFILING.md)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (oracle): cpu_baseline of the b200 arm and the whole --impl reference arm
+# ------------------------------------------------------------------------------------------------
+def cpu_c4_sample(O, WL, nper, threads):
+    """Oracle HCubature (OpenMP over problems) on the first `nper` problems of every family."""
+    c = WL.C4
+    t0 = time.perf_counter()
+    for fam in WL.GENZ:
+        par = WL.genz_params(fam, c["dim"], nper)
+        O.hcubature_batch(FAM_ORC[fam], np.zeros(c["dim"]), np.ones(c["dim"]), par, reltol=c["reltol"], abstol=c["abstol"],
+                          maxiters=c["maxiters"], initdiv=c["initdiv"], nthreads=threads)
+    return 6 * nper, time.perf_counter() - t0
+
+
+def cpu_c1_sample(O, WL, nprob, threads):
+    c = WL.C1
+    par = WL.c1_params(c["nprob"])[:, :nprob]
+    t0 = time.perf_counter()
+    O.quadgk_batch("sinxp", c["lb"], c["ub"], par, reltol=c["reltol"], abstol=c["abstol"], nthreads=threads)
+    return nprob, time.perf_counter() - t0
+
+
+def cpu_c3_sample(O, WL, nprob, threads):
+    c = WL.C3
+    x, w = np.polynomial.legendre.leggauss(c["n1d"])
+    par = WL.genz_params(c["family"], c["dim"], nprob)
+    t0 = time.perf_counter()
+    O.fixed_tensor_batch(FAM_ORC[c["family"]], np.zeros(3), np.ones(3), par, x, w, nthreads=threads)
+    return nprob, time.perf_counter() - t0
+
+
+def cpu_c2_sample(O, WL, n, threads):
+    m = WL.C2["m"]
+    rng = np.random.default_rng(WL.SEED)
+    y = np.asfortranarray(rng.random((m, n)) + 1.0)
+    t0 = time.perf_counter()
+    for rule in ("trapezoid", "simpson"):
+        O.sampled_evalrule(rule, y, h=1.0 / (n - 1), dim=1, nthreads=threads)
+    dt = time.perf_counter() - t0
+    return 2 * (8.0 * m * n + 8 * m) / 1e9, dt        # GB
+
+
+FAM_ORC = {"sinxp": "sinxp", "genz_oscillatory": "osc", "genz_product_peak": "prodpeak", "genz_corner_peak": "corner",
+           "genz_gaussian": "gauss", "genz_c0": "c0", "genz_discontinuous": "discont"}
+
+
+def cpu_leg(workload, scale=1.0):
+    """-> (units, seconds, cores, sample description).  Sized for ~10-30 s of CPU work at scale 1."""
+    import oracle as O
+    import integrals_b200.workloads as WL
+    cores = O.max_threads()
+    if workload == "c4":
+        nper = max(8, int(32 * cores * scale))
+        units, dt = cpu_c4_sample(O, WL, nper, cores)
+        return units, dt, cores, f"first {nper} problems of each of the 6 families (same seeds, tolerances and 4e6 cap)"
+    if workload == "c1":
+        n = WL.C1["nprob"]
+        units, dt = cpu_c1_sample(O, WL, n, cores)
+        return units, dt, cores, f"all {n} problems"
+    if workload == "c3":
+        n = max(8, int(256 * cores * scale))
+        units, dt = cpu_c3_sample(O, WL, n, cores)
+        return units, dt, cores, f"first {n} problems (262,144 nodes each)"
+    n = 1 << 15
+    units, dt = cpu_c2_sample(O, WL, n, cores)
+    return units, dt, cores, f"4096 x {n} fp64 (1 GiB), trapezoid + Simpson"
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  Julia is not in this image, so this is
+    the oracle port (C, OpenMP over problems, all host threads), each step a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    metric, unit = METRIC[args.workload]
+    for _ in range(args.warmup):
+        cpu_leg(args.workload, 0.25)
+    tot_u = tot_t = 0.0
+    for _ in range(args.steps):
+        u, dt, cores, sample = cpu_leg(args.workload, 0.25)
+        tot_u += u; tot_t += dt
+    v = tot_u / tot_t
+    print(json.dumps({"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
+                      "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True,
+                      "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                      "config": workload_config(args.workload, args, sample=sample),
+                      "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+                      "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def workload_config(w, args, **extra):
+    import integrals_b200.workloads as WL
+    if w == "c4":
+        c = dict(WL.C4)
+        cfg = {"workload": "C4: HCubature Genz suite, 6 families x 2^18 parameter sets, 4-D, [0,1]^4",
+               "families": WL.GENZ, "reltol": c["reltol"], "abstol": c["abstol"], "maxiters_evals": c["maxiters"],
+               "nprob_per_family_per_gpu": args.nprob or c["nprob_per_family"], "parallelism": f"problems sharded x{args.gpus}, no collective"}
+    elif w == "c1":
+        cfg = {"workload": "C1: QuadGK int_-2^5 sin(x p) dx, 65,536 p in [0.1, 64]", "reltol": 1e-10, "abstol": 1e-8,
+               "nprob_per_gpu": args.nprob or WL.C1["nprob"]}
+    elif w == "c3":
+        cfg = {"workload": "C3: tensor Gauss-Legendre n=64 in 3-D, 2^20 Genz oscillatory parameter sets",
+               "nprob_per_gpu": args.nprob or WL.C3["nprob"]}
+    else:
+        cfg = {"workload": "C2: TrapezoidalRule + SimpsonsRule on 4096 x 1,048,576 fp64 along dim 2 (32 GiB, > L2)",
+               "n_per_gpu": args.nprob or WL.C2["n"]}
+    cfg["l2"] = "256 MB buffer written between timed steps (L2 flush)"
+    cfg.update(extra)
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import integrals_b200 as ib
+    import integrals_b200.workloads as WL
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback (use --impl reference for the CPU leg)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    eng = ib.Engine(local)
+    # one explicit stream for torch and the engine, so torch.cuda.Event brackets the engine's kernels
+    # (the legacy default stream has handle 0, which ib200_set_stream reads as "the context's own stream")
+    bench_stream = torch.cuda.Stream()
+    torch.cuda.set_stream(bench_stream)
+    assert bench_stream.cuda_stream != 0
+    eng.set_stream(bench_stream.cuda_stream)
+    F = ib.FAMILY_IDS
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    fp64_peak, _ = eng.fp64_peak()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxrank(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # -------------------------------------------------------------------------------- workloads
+    def make_c4():
+        c = WL.C4; d = c["dim"]
+        nper = args.nprob or c["nprob_per_family"]
+        host, dev = {}, {}
+        for fam in WL.GENZ:
+            par = WL.genz_params(fam, d, nper, seed=WL.SEED + 1000 * rank)
+            pinned = torch.from_numpy(np.ascontiguousarray(par.T)).pin_memory()        # [nprob, 2d] == 2d x nprob col-major
+            host[fam] = pinned
+            dev[fam] = dict(par=pinned.cuda(), I=torch.empty(nper, dtype=torch.float64, device="cuda"),
+                            E=torch.empty(nper, dtype=torch.float64, device="cuda"),
+                            N=torch.empty(nper, dtype=torch.int64, device="cuda"),
+                            S=torch.empty(nper, dtype=torch.int32, device="cuda"))
+        lb, ub = np.zeros(d), np.ones(d)
+        kms = {fam: 0.0 for fam in WL.GENZ}
+
+        def step(record=False):
+            for fam in WL.GENZ:
+                b = dev[fam]
+                eng.hcubature_batch(F[fam], d, lb, ub, b["par"], reltol=c["reltol"], abstol=c["abstol"], maxevals=c["maxiters"],
+                                    initdiv=c["initdiv"], out_I=b["I"], out_E=b["E"], out_nevals=b["N"], out_status=b["S"])
+                if record:
+                    kms[fam] += eng.last_kernel_ms
+
+        def e2e_step():
+            res = 0.0
+            for fam in WL.GENZ:
+                prob = ib.IntegralProblem(getattr(ib, ib_marker[fam])(), (lb, ub), host[fam].numpy().T)
+                sol = ib.solve(prob, ib.HCubatureB200(initdiv=c["initdiv"]), engine=eng, reltol=c["reltol"], abstol=c["abstol"],
+                               maxiters=c["maxiters"])
+                res += float(sol.u[0])
+            return res
+
+        def finish(kernel_ms_total):
+            fl = 0.0; ev = 0; per = {}
+            for fam in WL.GENZ:
+                n_ev = int(dev[fam]["N"].sum().item())
+                ev += n_ev
+                fl += n_ev * WL.hcubature_flops_per_eval(fam, d)
+                per[fam] = {"kernel_ms": kms[fam] / args.steps, "integrals_per_s": nper / (kms[fam] / args.steps * 1e-3),
+                            "mean_evals": n_ev / nper, "frac_maxevals": float((dev[fam]["S"] == 1).double().mean().item())}
+            return dict(units=6 * nper, launches=6, flops=fl, evals=ev, per_family=per,
+                        h2d=6 * nper * 2 * d * 8 + 6 * 2 * d * 8, d2h=6 * nper * (8 + 8 + 8 + 4),
+                        kernel="hcub_kernel<FAM,4,true> (6 launches per step, one per family)")
+        return step, e2e_step, finish
+
+    ib_marker = {"genz_oscillatory": "GenzOscillatory", "genz_product_peak": "GenzProductPeak", "genz_corner_peak": "GenzCornerPeak",
+                 "genz_gaussian": "GenzGaussian", "genz_c0": "GenzC0", "genz_discontinuous": "GenzDiscontinuous"}
+
+    def make_c1():
+        c = WL.C1
+        n = args.nprob or c["nprob"]
+        par = WL.c1_params(c["nprob"])[:, :n]
+        pinned = torch.from_numpy(np.ascontiguousarray(par.T)).pin_memory()
+        dpar = pinned.cuda()
+        oI = torch.empty(n, dtype=torch.float64, device="cuda"); oE = torch.empty_like(oI)
+        oN = torch.empty(n, dtype=torch.int64, device="cuda"); oS = torch.empty(n, dtype=torch.int32, device="cuda")
+        lb, ub = np.array([c["lb"]]), np.array([c["ub"]])
+
+        def step(record=False):
+            eng.quadgk_batch(F["sinxp"], lb, ub, dpar, reltol=c["reltol"], abstol=c["abstol"], out_I=oI, out_E=oE, out_nevals=oN, out_status=oS)
+
+        def e2e_step():
+            sol = ib.solve(ib.IntegralProblem(ib.SinXP(), (c["lb"], c["ub"]), pinned.numpy().T), ib.QuadGKB200(), engine=eng,
+                           reltol=c["reltol"])
+            return float(sol.u[0])
+
+        def finish(kernel_ms_total):
+            ev = int(oN.sum().item())
+            return dict(units=n, launches=1, flops=ev * WL.quadgk_flops_per_eval(), evals=ev, h2d=n * 8 + 16, d2h=n * 28,
+                        kernel="quadgk_kernel<SINXP,true>")
+        return step, e2e_step, finish
+
+    def make_c3():
+        c = WL.C3
+        n = args.nprob or c["nprob"]
+        x, w = np.polynomial.legendre.leggauss(c["n1d"])
+        par = WL.genz_params(c["family"], c["dim"], n, seed=WL.SEED + 1000 * rank)
+        pinned = torch.from_numpy(np.ascontiguousarray(par.T)).pin_memory()
+        dpar = pinned.cuda()
+        out = torch.empty(n, dtype=torch.float64, device="cuda")
+        lb, ub = np.zeros(3), np.ones(3)
+
+        def step(record=False):
+            eng.fixed_rule_tensor_batch(F[c["family"]], 3, lb, ub, dpar, x, w, out=out)
+
+        def e2e_step():
+            sol = ib.solve(ib.IntegralProblem(ib.GenzOscillatory(), (lb, ub), pinned.numpy().T),
+                           ib.QuadratureRuleB200(lambda k: (x, w), n=c["n1d"], tensor=True), engine=eng)
+            return float(sol.u[0])
+
+        def finish(kernel_ms_total):
+            ev = n * c["n1d"] ** 3
+            return dict(units=n, launches=1, flops=ev * WL.fixed_tensor_flops_per_eval(c["family"], 3), evals=ev,
+                        h2d=n * 6 * 8, d2h=n * 8, kernel="tensor_kernel<GENZ_OSC,3>")
+        return step, e2e_step, finish
+
+    def make_c2():
+        m = WL.C2["m"]; n = args.nprob or WL.C2["n"]
+        y = torch.empty((n, m), dtype=torch.float64, device="cuda")         # row-major [n, m] == column-major m x n
+        xs = torch.linspace(0, 1, n, dtype=torch.float64, device="cuda")
+        jj = 1.0 + torch.arange(1, m + 1, dtype=torch.float64, device="cuda") / m
+        for i0 in range(0, n, 1 << 16):
+            i1 = min(n, i0 + (1 << 16))
+            y[i0:i1] = torch.sin(xs[i0:i1, None] * jj[None, :]) + 1.5
+        out = torch.empty(m, dtype=torch.float64, device="cuda")
+        h = 1.0 / (n - 1)
+        ne2e = min(n, 1 << 16)                                              # e2e on a 2 GiB host block (PCIe bound)
+        yh = y[:ne2e].cpu().pin_memory()
+
+        def step(record=False):
+            eng.sampled("trapezoid", y, m, n, 1, h=h, out=out)
+            eng.sampled("simpson", y, m, n, 1, h=h, out=out)
+
+        def e2e_step():
+            r = 0.0
+            for alg in (ib.TrapezoidalB200(), ib.SimpsonsB200()):
+                sol = ib.solve(ib.SampledIntegralProblem(yh.numpy().T, ib.Range(0.0, h * (ne2e - 1), ne2e), dim=1), alg, engine=eng)
+                r += float(sol.u[0])
+            return r
+
+        def finish(kernel_ms_total):
+            by = 2 * (8.0 * m * n + 8 * m)
+            return dict(units=by / 1e9, launches=6, bytes=by, h2d=2 * 8 * m * ne2e, d2h=2 * 8 * m, e2e_units=2 * (8.0 * m * ne2e + 8 * m) / 1e9,
+                        kernel="strided_kernel<2,8> (2 launches per step: trapezoid, Simpson; + weights and finish kernels)")
+        return step, e2e_step, finish
+
+    makers = {"c4": make_c4, "c1": make_c1, "c2": make_c2, "c3": make_c3}
+
+    def run(workload, steps, warmup, with_e2e=True, sample_clocks=False):
+        step, e2e_step, finish = makers[workload]()
+        for _ in range(warmup):
+            step()
+        barrier()
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        l0 = eng.kernel_launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            flush.fill_(1)                                  # L2 flush (inside the timed region; ~0.05 ms)
+            step(record=True)
+        e1.record()
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        ms = maxrank(e0.elapsed_time(e1))
+        launches = eng.kernel_launches - l0
+        info = finish(ms)
+        res = dict(ms_per_step=ms / steps, value=world * info["units"] / (ms / steps * 1e-3), launches=launches, info=info, clocks=clocks)
+        if with_e2e:
+            e2e_step()                                      # warm-up (pinned staging buffers, scratch growth)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                e2e_step()
+            torch.cuda.synchronize()
+            dt = maxrank(time.perf_counter() - t0)
+            res["e2e_value"] = world * info.get("e2e_units", info["units"]) / (dt / steps)
+        return res
+
+    w = args.workload
+    metric, unit = METRIC[w]
+    r = run(w, args.steps, args.warmup, with_e2e=True, sample_clocks=True)
+    info = r["info"]
+    # roofline of the dominant kernel: algorithmic flops (or bytes) per launch / mean launch duration (CUDA events)
+    if w == "c2":
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        peak = peaks.get("hbm_gbs", 6650.0)
+        ach = info["bytes"] / (r["ms_per_step"] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6.65 TB/s (of fallback)", "kernel": info["kernel"]}
+    else:
+        ach = info["flops"] / (r["ms_per_step"] * 1e-3) / 1e12
+        roof = {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": None,
+                "peak_source": "DFMA-chain microbenchmark run live on this GPU (ib200_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
+                "flops_model": "SURVEY 8(d) nominal FP64 operations per integrand evaluation x evaluations (DESIGN.md)",
+                "evals_per_step": info["evals"], "gevals_per_s": info["evals"] / (r["ms_per_step"] * 1e-3) / 1e9, "kernel": info["kernel"]}
+    line = {"metric": metric, "value": r["value"], "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(w, args), "clocks": r["clocks"],
+            "e2e": {"value": r["e2e_value"], "unit": unit, "h2d_bytes_per_step": info["h2d"], "d2h_bytes_per_step": info["d2h"],
+                    "api": "integrals_b200.solve(IntegralProblem | SampledIntegralProblem, alg) with host numpy (pinned) inputs and host outputs"},
+            "gpu_launches": r["launches"], "roofline": roof}
+    if "per_family" in info:
+        line["per_family"] = info["per_family"]
+
+    if rank == 0 and world == 1 and not args.no_secondary:
+        sec = {}
+        for sw in METRIC:
+            if sw == w:
+                continue
+            if sw == "c2" and torch.cuda.mem_get_info()[0] < (40 << 30):
+                continue
+            try:
+                s = run(sw, 2, 3, with_e2e=False)
+                e = {"value": s["value"], "unit": METRIC[sw][1], "ms_per_step": s["ms_per_step"]}
+                if sw == "c2":
+                    e["frac_of_measured_hbm"] = s["value"] / 6535.7
+                else:
+                    e["fp64_tflops_nominal"] = s["info"]["flops"] / (s["ms_per_step"] * 1e-3) / 1e12
+                    e["frac_of_fp64_peak"] = e["fp64_tflops_nominal"] / fp64_peak
+                sec[sw] = e
+            except Exception as ex:                          # a side measurement must not lose the headline
+                sec[sw] = {"error": str(ex)[:200]}
+            torch.cuda.empty_cache()
+        line["secondary"] = sec
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        units, dt, cores, sample = cpu_leg(w)
+        line["cpu_baseline"] = {"value": units / dt, "unit": unit, "cores": cores, "kind": "port", "sample": sample,
+                                "seconds": dt}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,372 @@
+"""Host-side mirror of the Integrals.jl problem / algorithm / solve interface for the B200 engine.
+
+The reference toolchain (Julia) is absent from this image, so the caller above the C ABI is
+written in Python with the reference's names, argument meaning and error behaviour; the Julia
+extension a maintainer would add is in INTEGRATION.md.  What mirrors what:
+
+  IntegralProblem(f, domain, p; kwargs...)        SciMLBase type re-exported at src/Integrals.jl:7-10
+  SampledIntegralProblem(y, x; dim)               same; src/common.jl:319-343
+  init / solve / solve_cache (= solve!)           src/common.jl:79-133, 216-222, 248-253, 376-410
+  kwarg whitelist (reltol, abstol, maxiters)      src/Integrals.jl:142-179 (CommonKwargError)
+  ChangeOfVariables + transformation_*_inf        src/algorithms_meta.jl:67-71, src/common.jl:97-103
+  QuadGKB200 / HCubatureB200                      QuadGKJL / HCubatureJL, src/algorithms.jl:51-56, 108-115
+  QuadratureRuleB200 / GaussLegendreB200          src/algorithms.jl:229-249, 289-298
+  TrapezoidalB200 / SimpsonsB200                  src/algorithms_sampled.jl:44, 71
+  IntegralSolution(u, resid, retcode, chi)        SciMLBase.build_solution call sites Integrals.jl:338, 396
+
+Differences from the reference, all forced by "CUDA cannot run host closures":
+  * `prob.f` must be a registered integrand marker (integrands.py);
+  * batches: `p` may be a matrix nparam x nprob (one problem per column) and the bounds may be
+    dim x nprob; then `sol.u` and `sol.resid` are vectors of length nprob;
+  * `sol.stats` carries the per-problem evaluation counts and status codes the engine returns.
+There is no CPU solve path: every solve goes through libintegrals_b200.so on a B200.
+"""
+import math
+
+import numpy as np
+
+from . import _lib
+from .integrands import RegisteredIntegrand
+
+ALLOWED_KEYWORDS = ("maxiters", "abstol", "reltol")          # src/Integrals.jl:142
+
+
+class CommonKwargError(TypeError):
+    """Unrecognized keyword arguments passed to `solve` (src/Integrals.jl:163-179)."""
+
+    def __init__(self, kwargs):
+        self.kwargs = dict(kwargs)
+        bad = [k for k in self.kwargs if k not in ALLOWED_KEYWORDS]
+        super().__init__("Unrecognized keyword arguments found.\nThe only allowed keyword arguments to `solve` are:\n"
+                         f"{ALLOWED_KEYWORDS}\nUnrecognized keyword arguments: {bad}")
+
+
+def checkkwargs(kwargs):
+    if any(k not in ALLOWED_KEYWORDS for k in kwargs):
+        raise CommonKwargError(kwargs)
+
+
+class ReturnCode:
+    Success = "Success"
+    MaxIters = "MaxIters"
+    Failure = "Failure"
+
+
+# ---------------------------------------------------------------------------------------------
+# transformations (markers; the formulas run on the device, csrc/family.cuh t2ujac)
+# ---------------------------------------------------------------------------------------------
+class _Transformation:
+    def __init__(self, name):
+        self.name = name
+        self.id = _lib.TRANSFORM_IDS[name]
+
+    def __repr__(self):
+        return self.name
+
+
+transformation_if_inf = _Transformation("transformation_if_inf")     # src/infinity_handling.jl:165-170
+transformation_tan_inf = _Transformation("transformation_tan_inf")   # :277-282
+transformation_cot_inf = _Transformation("transformation_cot_inf")   # :405-410
+
+
+# ---------------------------------------------------------------------------------------------
+# problems
+# ---------------------------------------------------------------------------------------------
+class IntegralProblem:
+    """IntegralProblem(f, domain, p=None, **kwargs).  domain = (lb, ub): scalars (1-D), vectors of
+    length dim, or dim x nprob arrays (per-problem bounds).  p: nparam numbers or nparam x nprob."""
+
+    def __init__(self, f, domain, p=None, **kwargs):
+        if not isinstance(f, RegisteredIntegrand):
+            raise TypeError("the B200 engine integrates registered device-side integrands only "
+                            "(integrals_b200.integrands); arbitrary host closures cannot run on the device")
+        if not (isinstance(domain, (tuple, list)) and len(domain) == 2):
+            raise TypeError("domain must be a tuple (lb, ub)")
+        self.f = f
+        self.domain = (domain[0], domain[1])
+        self.p = p
+        self.kwargs = dict(kwargs)
+
+    def remake(self, **changes):
+        new = IntegralProblem(self.f, self.domain, self.p, **self.kwargs)
+        for k, v in changes.items():
+            setattr(new, k, v)
+        return new
+
+
+class Range:
+    """Uniform grid, the analogue of Julia's `range(start, stop, length=n)`: selects the uniform
+    weight types (src/trapezoidal.jl:43, src/simpsons.jl:85)."""
+
+    def __init__(self, start, stop, length):
+        self.start, self.stop, self.length = float(start), float(stop), int(length)
+        self.step = (self.stop - self.start) / (self.length - 1) if self.length > 1 else 0.0
+
+    def __len__(self):
+        return self.length
+
+    def toarray(self):
+        return np.linspace(self.start, self.stop, self.length)
+
+
+class SampledIntegralProblem:
+    """SampledIntegralProblem(y, x, dim=-1): integrate samples y along axis `dim` (0-based; default the
+    last axis, like the reference's `dim = ndims(y)`).  y: numpy array or torch CUDA tensor."""
+
+    def __init__(self, y, x, dim=-1):
+        nd = y.dim() if hasattr(y, "data_ptr") else np.ndim(y)
+        if not -nd <= dim < nd:
+            raise ValueError("dim out of range")
+        self.y, self.x, self.dim = y, x, dim % nd
+        if len(x) != y.shape[self.dim]:
+            raise ValueError("The integrand y must have the same length as the sampling points x along the integrated dimension.")
+
+
+class IntegralSolution:
+    def __init__(self, u, resid, prob, alg, retcode=ReturnCode.Success, chi=None, stats=None):
+        self.u, self.resid, self.prob, self.alg, self.retcode, self.chi, self.stats = u, resid, prob, alg, retcode, chi, stats
+
+    def __repr__(self):
+        return f"IntegralSolution(u={self.u!r}, resid={self.resid!r}, retcode={self.retcode})"
+
+
+# ---------------------------------------------------------------------------------------------
+# algorithms
+# ---------------------------------------------------------------------------------------------
+class AbstractB200Algorithm:
+    pass
+
+
+class QuadGKB200(AbstractB200Algorithm):
+    """Adaptive Gauss-Kronrod, drop-in for QuadGKJL (src/algorithms.jl:51-56); order 7 only."""
+
+    def __init__(self, order=7):
+        if order != 7:
+            raise ValueError("QuadGKB200 implements the (7,15) Gauss-Kronrod pair only")
+        self.order = order
+
+
+class HCubatureB200(AbstractB200Algorithm):
+    """Adaptive Genz-Malik cubature, drop-in for HCubatureJL (src/algorithms.jl:108-115)."""
+
+    def __init__(self, initdiv=1):
+        self.initdiv = int(initdiv)
+
+
+class QuadratureRuleB200(AbstractB200Algorithm):
+    """Fixed rule, drop-in for QuadratureRule(q; n) (src/algorithms.jl:289-298): q(n) returns
+    (nodes, weights) on [-1,1]^dim; nodes of shape (N,) or (N, dim).  tensor=True: q(n) is a 1-D rule
+    and the dim-fold tensor product is meant (test/quadrule_tests.jl:41-44) without materialising it."""
+
+    def __init__(self, q, n=250, tensor=False):
+        if n <= 0:
+            raise ValueError("number of nodes must be positive")          # src/algorithms.jl:293-295
+        self.q, self.n, self.tensor = q, int(n), bool(tensor)
+
+
+class GaussLegendreB200(AbstractB200Algorithm):
+    """1-D (composite) Gauss-Legendre, drop-in for GaussLegendre (src/algorithms.jl:229-249)."""
+
+    def __init__(self, n=250, subintervals=1, nodes=None, weights=None):
+        if subintervals <= 0:
+            raise ValueError("Need at least 1 subinterval")
+        if nodes is None or weights is None:
+            nodes, weights = np.polynomial.legendre.leggauss(int(n))
+        self.nodes = np.ascontiguousarray(nodes, dtype=np.float64)
+        self.weights = np.ascontiguousarray(weights, dtype=np.float64)
+        self.subintervals = int(subintervals)
+
+
+class AbstractSampledB200Algorithm:
+    rule = None
+
+
+class TrapezoidalB200(AbstractSampledB200Algorithm):
+    rule = "trapezoid"
+
+
+class SimpsonsB200(AbstractSampledB200Algorithm):
+    rule = "simpson"
+
+
+class ChangeOfVariables:
+    """ChangeOfVariables(fu2gv, alg) (src/algorithms_meta.jl:67-71); fu2gv must be one of the three
+    registered transformations."""
+
+    def __init__(self, fu2gv, alg):
+        if not isinstance(fu2gv, _Transformation):
+            raise TypeError("the B200 engine supports transformation_if_inf, transformation_tan_inf and "
+                            "transformation_cot_inf only")
+        self.fu2gv, self.alg = fu2gv, alg
+
+
+# ---------------------------------------------------------------------------------------------
+# caches and solve
+# ---------------------------------------------------------------------------------------------
+def _problem_shapes(prob):
+    """-> dim, lb, ub (float64, column-major), params (nparam x nprob), nprob, scalar_problem."""
+    lb, ub = prob.domain
+    lb = np.asarray(lb, dtype=np.float64) if not hasattr(lb, "data_ptr") else lb
+    ub = np.asarray(ub, dtype=np.float64) if not hasattr(ub, "data_ptr") else ub
+    p = prob.p
+    if p is None:
+        raise ValueError("registered integrands need parameters p")
+    if hasattr(p, "data_ptr"):
+        nprob = p.shape[0] if p.dim() == 2 else 1
+        scalar = p.dim() < 2
+    else:
+        p = np.asarray(p, dtype=np.float64)
+        scalar = p.ndim < 2
+        p = np.asfortranarray(p.reshape(-1, 1) if scalar else p)
+        nprob = p.shape[1]
+    nd = lb.dim() if hasattr(lb, "data_ptr") else lb.ndim
+    dim = 1 if nd == 0 else (lb.shape[1] if hasattr(lb, "data_ptr") and nd == 2 else lb.shape[0])
+    if nd == 0:
+        lb = np.atleast_1d(lb); ub = np.atleast_1d(ub)
+    return dim, lb, ub, p, nprob, scalar
+
+
+class IntegralCache:
+    """init(prob, alg; kwargs...) result (src/common.jl:1-12).  `cacheval` is the engine context: its
+    device scratch is reused by every solve (QuadGK segbuf / HCubature buffer analogue)."""
+
+    def __init__(self, prob, alg, kwargs, engine):
+        self.f, self.domain, self.p = prob.f, prob.domain, prob.p
+        self.prob_kwargs = prob.kwargs
+        self.alg, self.kwargs, self.cacheval = alg, kwargs, engine
+
+    @property
+    def lb(self):
+        return self.domain[0]
+
+    @property
+    def ub(self):
+        return self.domain[1]
+
+    def solve(self):
+        return solve_cache(self)
+
+
+def init(prob, alg, engine=None, **kws):
+    if isinstance(prob, SampledIntegralProblem):
+        return _init_sampled(prob, alg, engine, **kws)
+    kwargs = {**prob.kwargs, **kws}                      # problem kwargs under solve kwargs, common.jl:87
+    checkkwargs(kwargs)
+    if alg is None:
+        raise ValueError("No integration algorithm `alg` was supplied as the second positional argument.")  # common.jl:163-177
+    if not isinstance(alg, ChangeOfVariables):
+        alg = ChangeOfVariables(transformation_if_inf, alg)   # always for tuple domains, common.jl:97-103
+    if not isinstance(alg.alg, AbstractB200Algorithm):
+        raise TypeError(f"{type(alg.alg).__name__} is not a B200 integration algorithm")
+    return IntegralCache(prob, alg, kwargs, engine or _lib.default_engine())
+
+
+def solve(prob, alg=None, engine=None, **kws):
+    """solve(prob, alg; reltol, abstol, maxiters) = solve!(init(prob, alg; ...)) (src/common.jl:216-222)."""
+    return solve_cache(init(prob, alg, engine, **kws))
+
+
+def solve_cache(cache):
+    """solve!(cache) (src/common.jl:248-253, 408-410)."""
+    if isinstance(cache, SampledIntegralCache):
+        return _solve_sampled(cache)
+    eng = cache.cacheval
+    prob = IntegralProblem(cache.f, cache.domain, cache.p, **cache.prob_kwargs)     # build_problem, common.jl:255-257
+    inner, tr = cache.alg.alg, cache.alg.fu2gv.id
+    dim, lb, ub, p, nprob, scalar = _problem_shapes(prob)
+    fam = cache.f.family
+    if not cache.f.supports_dim(dim):
+        raise ValueError(f"{cache.f!r} is not defined in {dim} dimensions")
+    kw = cache.kwargs
+    reltol = kw.get("reltol", 1e-8)                      # defaults of src/Integrals.jl:254-255, 349-350
+    abstol = kw.get("abstol", 1e-8)
+    maxiters = kw.get("maxiters", _lib.MAXEVALS_UNBOUNDED)
+    stats = None
+    if isinstance(inner, QuadGKB200):
+        if dim != 1:
+            raise ValueError("QuadGKB200 only accepts one-dimensional quadrature problems.")    # Integrals.jl:263-266
+        I, E, ne, st = eng.quadgk_batch(fam, lb, ub, p, reltol=reltol, abstol=abstol, maxevals=maxiters, transform=tr)
+        stats = dict(nevals=ne, status=st)
+    elif isinstance(inner, HCubatureB200):
+        I, E, ne, st = eng.hcubature_batch(fam, dim, lb, ub, p, reltol=reltol, abstol=abstol, maxevals=maxiters,
+                                           initdiv=inner.initdiv, transform=tr)
+        stats = dict(nevals=ne, status=st)
+    elif isinstance(inner, QuadratureRuleB200):
+        nodes, weights = inner.q(inner.n)                # init_cacheval, src/quadrules.jl:21-23
+        if inner.tensor:
+            I = eng.fixed_rule_tensor_batch(fam, dim, lb, ub, p, nodes, weights, transform=tr)
+        else:
+            nodes = np.asarray(nodes, dtype=np.float64).reshape(len(weights), -1)
+            if nodes.shape[1] != dim:
+                raise ValueError("quadrature nodes and domain have different dimensions")
+            I = eng.fixed_rule_nodes_batch(fam, dim, lb, ub, p, nodes, weights, transform=tr)
+        E = None                                         # resid = nothing, quadrules.jl:50-51
+    elif isinstance(inner, GaussLegendreB200):
+        if dim != 1:
+            raise ValueError("GaussLegendreB200 only accepts one-dimensional quadrature problems.")   # ext/…FastGaussQuadratureExt.jl:41-43
+        I = eng.gauss_legendre_batch(fam, lb, ub, p, inner.nodes, inner.weights, subintervals=inner.subintervals, transform=tr)
+        E = None
+    else:
+        raise TypeError(f"unsupported algorithm {type(inner).__name__}")
+    if scalar and not hasattr(I, "data_ptr"):
+        I = float(I[0]); E = None if E is None else float(E[0])
+    return IntegralSolution(I, E, prob, inner, ReturnCode.Success, None, stats)   # Success unconditionally, Integrals.jl:338,396
+
+
+# ---------------------------------------------------------------------------------------------
+# sampled problems
+# ---------------------------------------------------------------------------------------------
+class SampledIntegralCache:
+    """src/common.jl:264-281: assigning `x` marks the weights stale (isfresh)."""
+
+    def __init__(self, prob, alg, engine):
+        object.__setattr__(self, "isfresh", False)
+        self.y, self.x, self.dim, self.alg, self.cacheval = prob.y, prob.x, prob.dim, alg, engine
+
+    def __setattr__(self, name, value):
+        if name == "x":
+            object.__setattr__(self, "isfresh", True)
+        object.__setattr__(self, name, value)
+
+    def solve(self):
+        return solve_cache(self)
+
+
+def _init_sampled(prob, alg, engine=None, **kws):
+    if kws:
+        raise ValueError("There are no keyword arguments allowed to `solve`")     # common.jl:325-326
+    if not isinstance(alg, AbstractSampledB200Algorithm):
+        raise TypeError(f"{type(alg).__name__} is not a sampled B200 integration algorithm")
+    return SampledIntegralCache(prob, alg, engine or _lib.default_engine())
+
+
+def _solve_sampled(cache):
+    eng, y, x, dim = cache.cacheval, cache.y, cache.x, cache.dim
+    object.__setattr__(cache, "isfresh", False)          # weights are recomputed on the device every solve
+    if hasattr(y, "data_ptr"):
+        # torch tensor (row-major): axes after `dim` are the contiguous ones == column-major `inner`
+        if not y.is_contiguous():
+            raise ValueError("device samples must be a contiguous tensor")
+        shape = tuple(y.shape)
+        inner = int(np.prod(shape[dim + 1:], dtype=np.int64)); outer = int(np.prod(shape[:dim], dtype=np.int64))
+        out_shape = shape[:dim] + shape[dim + 1:]
+    else:
+        y = np.asfortranarray(y, dtype=np.float64)
+        shape = y.shape
+        inner = int(np.prod(shape[:dim], dtype=np.int64)); outer = int(np.prod(shape[dim + 1:], dtype=np.int64))
+        out_shape = shape[:dim] + shape[dim + 1:]
+    n = shape[dim]
+    if isinstance(x, Range):
+        h, xs = x.step, None
+    else:
+        h, xs = 0.0, np.ascontiguousarray(x, dtype=np.float64) if not hasattr(x, "data_ptr") else x
+    if hasattr(y, "data_ptr"):
+        import torch
+        out = torch.empty(max(inner * outer, 1), dtype=torch.float64, device=y.device)
+        eng.sampled(cache.alg.rule, y, inner, n, outer, h=h, x=xs, out=out)
+        u = out[:inner * outer].reshape(out_shape) if out_shape else out[0]
+    else:
+        out = eng.sampled(cache.alg.rule, y, inner, n, outer, h=h, x=xs)[:inner * outer]
+        u = out.reshape(out_shape, order="F") if out_shape else float(out[0])
+    prob = SampledIntegralProblem(cache.y, cache.x, dim)
+    return IntegralSolution(u, None, prob, cache.alg, ReturnCode.Success)          # sampled.jl:166-167

@@ -1,0 +1,67 @@
+"""Multi-GPU execution of batched problems: one process per GPU, problems split across ranks.
+
+Batches of independent integrals (QuadGK / HCubature / fixed-rule batches) need no data-path
+collective: rank r solves the contiguous block shard_range(nprob, r, world) on its own GPU and the
+blocks are concatenated with one all_gather of the results (control plane; torch.distributed over
+NCCL on the GPUs, gloo in the CPU tests).  The reference has no counterpart: a sweep
+over p is a serial loop of solve calls (docs/src/tutorials/caching_interface.md:32-47).
+"""
+import numpy as np
+
+
+def shard_range(nprob, rank, world):
+    """[lo, hi) of the problems rank `rank` owns: contiguous blocks whose sizes differ by at most 1."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError("bad rank/world")
+    base, rem = divmod(int(nprob), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def _slice_problem(prob, lo, hi):
+    lb, ub = prob.domain
+    p = np.asarray(prob.p, dtype=np.float64)
+    if p.ndim < 2:
+        raise ValueError("solve_sharded needs a batch: p must be nparam x nprob")
+    lb = np.asarray(lb, dtype=np.float64); ub = np.asarray(ub, dtype=np.float64)
+    if lb.ndim == 2:
+        lb, ub = lb[:, lo:hi], ub[:, lo:hi]
+    return prob.remake(p=np.asfortranarray(p[:, lo:hi]), domain=(lb, ub))
+
+
+def solve_sharded(prob, alg, group=None, local_solve=None, **kws):
+    """solve(prob, alg; kws...) with the columns of prob.p split across the ranks of `group`.
+    Every rank returns the full solution (u, resid, stats concatenated in problem order).
+    `local_solve(prob_block, alg, **kws)` defaults to interface.solve on this rank's GPU."""
+    import torch
+    import torch.distributed as dist
+    from . import interface
+    if local_solve is None:
+        local_solve = interface.solve
+    if not dist.is_initialized():
+        return local_solve(prob, alg, **kws)
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    nprob = np.asarray(prob.p).shape[1]
+    lo, hi = shard_range(nprob, rank, world)
+    sol = local_solve(_slice_problem(prob, lo, hi), alg, **kws)
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    # pack [u, resid, nevals, status] per problem into one padded buffer -> one all_gather
+    maxn = max(shard_range(nprob, r, world)[1] - shard_range(nprob, r, world)[0] for r in range(world))
+    pack = np.zeros((4, maxn))
+    n = hi - lo
+    pack[0, :n] = np.atleast_1d(sol.u)
+    pack[1, :n] = np.nan if sol.resid is None else np.atleast_1d(sol.resid)
+    if sol.stats is not None:
+        pack[2, :n] = sol.stats["nevals"]; pack[3, :n] = sol.stats["status"]
+    mine = torch.from_numpy(pack).to(dev)
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine, group=group)
+    cols = []
+    for r, t in enumerate(parts):
+        a, b = shard_range(nprob, r, world)
+        cols.append(t.cpu().numpy()[:, :b - a])
+    full = np.concatenate(cols, axis=1)
+    resid = None if sol.resid is None else full[1]
+    stats = None if sol.stats is None else dict(nevals=full[2].astype(np.int64), status=full[3].astype(np.int32))
+    return interface.IntegralSolution(full[0], resid, prob, sol.alg, sol.retcode, None, stats)

@@ -9,20 +9,7 @@ F = ib.FAMILY_IDS
 ORC_FAM = {"sinxp": "sinxp", "genz_oscillatory": "osc", "genz_product_peak": "prodpeak", "genz_corner_peak": "corner",
            "genz_gaussian": "gauss", "genz_c0": "c0", "genz_discontinuous": "discont", "cosprod": "cosprod",
            "gausspoly": "gausspoly", "explin": "explin", "gltest": "gltest"}
-GENZ = ["genz_oscillatory", "genz_product_peak", "genz_corner_peak", "genz_gaussian", "genz_c0", "genz_discontinuous"]
-# Genz standard difficulties (h, e): sum a_i = h / d^e  (SURVEY 8(d), C4)
-GENZ_DIFFICULTY = {"genz_oscillatory": (110.0, 1.5), "genz_product_peak": (600.0, 2.0), "genz_corner_peak": (600.0, 2.0),
-                   "genz_gaussian": (100.0, 1.0), "genz_c0": (150.0, 2.0), "genz_discontinuous": (100.0, 2.0)}
-
-
-def genz_params(family, dim, nprob, seed=20261019, scale=1.0):
-    """[a; u] per column (2*dim x nprob, column-major): u ~ U[0,1), a = r * (h/d^e) / sum r."""
-    rng = np.random.default_rng(seed + F[family])
-    h, e = GENZ_DIFFICULTY[family]
-    u = rng.random((dim, nprob))
-    r = rng.random((dim, nprob))
-    a = r * (scale * h / dim ** e) / r.sum(axis=0, keepdims=True)
-    return np.asfortranarray(np.concatenate([a, u], axis=0))
+from integrals_b200.workloads import GENZ, GENZ_DIFFICULTY, genz_params  # noqa: E402,F401
 
 
 def genz_exact(family, par, dim):
