@@ -81,7 +81,7 @@ int64_t     ib200_kernel_launches(ib200_ctx *ctx);       /* kernels launched so 
 int32_t     ib200_family_nparam(int32_t family, int32_t dim);   /* doubles per problem, <0 bad */
 /* timing of the most recent call's kernels on the context's stream, ms (CUDA events) */
 double      ib200_last_kernel_ms(ib200_ctx *ctx);
-/* optional knobs: key in {"adaptive_warps_per_sm","hcub_capacity","sampled_slabs"} */
+/* optional knobs: key in {"adaptive_warps_per_sm","hcub_capacity","sampled_slabs","hcub_mode"} */
 int32_t     ib200_set_option(ib200_ctx *ctx, const char *key, int64_t value);
 
 /* -- sampled data: replaces evalrule(data, weights, dim) src/sampled.jl:51-124 with the weights of

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libintegrals_b200.so")
+LIB_PATH = os.environ.get("IB200_LIB", os.path.join(_HERE, "libintegrals_b200.so"))   # IB200_LIB: alternative build (kernel experiments)
 
 FAMILY_IDS = dict(sinxp=0, genz_oscillatory=1, genz_product_peak=2, genz_corner_peak=3, genz_gaussian=4,
                   genz_c0=5, genz_discontinuous=6, cosprod=7, gausspoly=8, explin=9, gltest=10)

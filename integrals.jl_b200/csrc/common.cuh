@@ -12,7 +12,7 @@
 #define IB200_VERSION 100
 
 enum ScratchSlot { SL_IN0 = 0, SL_IN1, SL_IN2, SL_IN3, SL_IN4, SL_IN5, SL_OUT0, SL_OUT1, SL_OUT2, SL_OUT3,
-                   SL_WORK0, SL_WORK1, SL_WORK2, SL_WORK3, SL_COUNT };
+                   SL_WORK0, SL_WORK1, SL_WORK2, SL_WORK3, SL_WORK4, SL_WORK5, SL_COUNT };
 
 struct ib200_ctx {
     int device = 0;
@@ -30,6 +30,7 @@ struct ib200_ctx {
     int64_t opt_adaptive_warps_per_sm = 0;   // 0 = kernel default
     int64_t opt_hcub_capacity = 0;           // boxes per in-flight problem, 0 = derive from maxevals
     int64_t opt_sampled_slabs = 0;           // 0 = auto
+    int64_t opt_hcub_mode = 0;               // 0 = auto, 1 = warp per problem, 2 = pair mode (thread per box)
 
     // grow-only device scratch (the cacheval analogue: reused across calls)
     void *get(ScratchSlot s, size_t bytes) {

@@ -87,6 +87,7 @@ extern "C" int32_t ib200_set_option(ib200_ctx *ctx, const char *key, int64_t val
     if (k == "adaptive_warps_per_sm") ctx->opt_adaptive_warps_per_sm = value;
     else if (k == "hcub_capacity") ctx->opt_hcub_capacity = value;
     else if (k == "sampled_slabs") ctx->opt_sampled_slabs = value;
+    else if (k == "hcub_mode") ctx->opt_hcub_mode = value;
     else return ib200_fail(ctx, IB200_ERR_INVALID, "ib200_set_option: unknown key " + k);
     return IB200_OK;
 }

@@ -25,6 +25,140 @@ __host__ __device__ constexpr bool fam_dim_ok(int fam, int d) {
 #define IB_HALF_PI 1.5707963267948966
 
 // ------------------------------------------------------------------------------------------------
+// Branch-free exp for the integrand inner loops.  CUDA's exp() carries a data-dependent branch
+// (the |x| > 708 slow path) in every call, which fences the instruction scheduler: consecutive,
+// independent evaluations of a rule cannot be interleaved and the FP64 pipe idles on the 13-deep
+// Horner chain (ncu: "wait" stalls, profiles/r01_*).  Same construction as libm (Cody-Waite
+// reduction by ln2, degree-13 polynomial, exponent reconstruction in two halves so that gradual
+// underflow is honoured), extremes handled by selects.  Maximum error 0.99 ulp over [-750, 700]
+// (measured against long double, 2e7 samples); exp_bf(-inf) = 0, exp_bf(+inf) = inf, NaN -> NaN.
+// ------------------------------------------------------------------------------------------------
+#ifndef IB200_LIBM_EXP
+__device__ __forceinline__ double exp_bf(double x) {
+    const double MG = 6755399441055744.0;                       // 1.5 * 2^52: round to nearest integer
+    const double t = fma(x, 1.4426950408889634074, MG);
+    int k = __double2loint(t);
+    const double kf = t - MG;
+    double r = fma(kf, -6.93147180369123816490e-01, x);
+    r = fma(kf, -1.90821492927058770002e-10, r);
+    double q = 1.6059043836821613e-10;                          // 1/13! ... 1/2!
+    q = fma(q, r, 2.08767569878681e-09);
+    q = fma(q, r, 2.505210838544172e-08);
+    q = fma(q, r, 2.755731922398589e-07);
+    q = fma(q, r, 2.7557319223985893e-06);
+    q = fma(q, r, 2.48015873015873e-05);
+    q = fma(q, r, 1.984126984126984e-04);
+    q = fma(q, r, 1.388888888888889e-03);
+    q = fma(q, r, 8.333333333333333e-03);
+    q = fma(q, r, 4.1666666666666664e-02);
+    q = fma(q, r, 1.6666666666666666e-01);
+    q = fma(q, r, 0.5);
+    const double p = fma(q, r * r, r) + 1.0;
+    k = max(-2000, min(2000, k));
+    const int k1 = k >> 1, k2 = k - k1;
+    double res = (p * __hiloint2double((k1 + 1023) << 20, 0)) * __hiloint2double((k2 + 1023) << 20, 0);
+    res = x < -745.2 ? 0.0 : res;
+    res = x > 709.79 ? __longlong_as_double(0x7ff0000000000000LL) : res;
+    return res;
+}
+#else
+__device__ __forceinline__ double exp_bf(double x) { return exp(x); }
+#endif
+
+// N independent evaluations in lock step.  ptxas schedules a lone Horner chain as back-to-back
+// dependent DFMAs (each waits out the FP64 latency); writing the N chains side by side in the source
+// gives it N independent instructions between dependent ones (ncu: "wait" stall, profiles/r01_*).
+template <int N>
+__device__ __forceinline__ void exp_bfN(const double (&x)[N], double (&out)[N]) {
+#ifdef IB200_LIBM_EXP
+#pragma unroll
+    for (int j = 0; j < N; j++) out[j] = exp(x[j]);
+#else
+    const double MG = 6755399441055744.0;
+    double t[N], kf[N], r[N], q[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) t[j] = fma(x[j], 1.4426950408889634074, MG);
+#pragma unroll
+    for (int j = 0; j < N; j++) kf[j] = t[j] - MG;
+#pragma unroll
+    for (int j = 0; j < N; j++) r[j] = fma(kf[j], -6.93147180369123816490e-01, x[j]);
+#pragma unroll
+    for (int j = 0; j < N; j++) r[j] = fma(kf[j], -1.90821492927058770002e-10, r[j]);
+#pragma unroll
+    for (int j = 0; j < N; j++) q[j] = fma(1.6059043836821613e-10, r[j], 2.08767569878681e-09);
+#define IB_STEP(c) _Pragma("unroll") for (int j = 0; j < N; j++) q[j] = fma(q[j], r[j], c);
+    IB_STEP(2.505210838544172e-08) IB_STEP(2.755731922398589e-07) IB_STEP(2.7557319223985893e-06)
+    IB_STEP(2.48015873015873e-05) IB_STEP(1.984126984126984e-04) IB_STEP(1.388888888888889e-03)
+    IB_STEP(8.333333333333333e-03) IB_STEP(4.1666666666666664e-02) IB_STEP(1.6666666666666666e-01) IB_STEP(0.5)
+#undef IB_STEP
+    double pp[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) pp[j] = r[j] * r[j];
+#pragma unroll
+    for (int j = 0; j < N; j++) pp[j] = fma(q[j], pp[j], r[j]);
+#pragma unroll
+    for (int j = 0; j < N; j++) pp[j] = pp[j] + 1.0;
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        int k = max(-2000, min(2000, __double2loint(t[j])));
+        const int k1 = k >> 1, k2 = k - k1;
+        double res = (pp[j] * __hiloint2double((k1 + 1023) << 20, 0)) * __hiloint2double((k2 + 1023) << 20, 0);
+        res = x[j] < -745.2 ? 0.0 : res;
+        out[j] = x[j] > 709.79 ? __longlong_as_double(0x7ff0000000000000LL) : res;
+    }
+#endif
+}
+
+// Branch-free cos for |x| < 2^30 (3-term Cody-Waite reduction by pi/2 with FMA, fdlibm kernel
+// polynomials chosen per quadrant by selects; max error 1.5 ulp measured against long double); larger
+// arguments take libm's Payne-Hanek path.
+template <int N>
+__device__ __forceinline__ void cos_bfN(const double (&x)[N], double (&out)[N]) {
+#ifdef IB200_LIBM_EXP
+#pragma unroll
+    for (int j = 0; j < N; j++) out[j] = cos(x[j]);
+#else
+    const double MG = 6755399441055744.0;
+    double t[N], kf[N], r[N], z[N], p[N];
+    bool big = false;
+#pragma unroll
+    for (int j = 0; j < N; j++) { t[j] = fma(x[j], 0.63661977236758134308, MG); big = big || !(fabs(x[j]) < 1073741824.0); }
+#pragma unroll
+    for (int j = 0; j < N; j++) kf[j] = t[j] - MG;
+#pragma unroll
+    for (int j = 0; j < N; j++) r[j] = fma(kf[j], -1.5707963267948966, x[j]);
+#pragma unroll
+    for (int j = 0; j < N; j++) r[j] = fma(kf[j], -6.123233995736766e-17, r[j]);
+#pragma unroll
+    for (int j = 0; j < N; j++) r[j] = fma(kf[j], 1.4973849048591698e-33, r[j]);
+    int iq[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) { iq[j] = __double2loint(t[j]) + 1; z[j] = r[j] * r[j]; }
+#pragma unroll
+    for (int j = 0; j < N; j++) p[j] = (iq[j] & 1) ? -1.13596475577881948265e-11 : 1.58969099521155010221e-10;
+#define IB_STEP(cc, cs) _Pragma("unroll") for (int j = 0; j < N; j++) p[j] = fma(p[j], z[j], (iq[j] & 1) ? (cc) : (cs));
+    IB_STEP(2.08757232129817482790e-09, -2.50507602534068634195e-08)
+    IB_STEP(-2.75573143513906633035e-07, 2.75573137070700676789e-06)
+    IB_STEP(2.48015872894767294178e-05, -1.98412698298579493134e-04)
+    IB_STEP(-1.38888888888741095749e-03, 8.33333333332248946124e-03)
+    IB_STEP(4.16666666666666019037e-02, -1.66666666666666324348e-01)
+#undef IB_STEP
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        const double sres = fma(r[j] * z[j], p[j], r[j]);
+        const double hz = 0.5 * z[j], w = 1.0 - hz;
+        const double cres = w + (((1.0 - w) - hz) + (z[j] * z[j]) * p[j]);
+        const double res = (iq[j] & 1) ? cres : sres;
+        out[j] = (iq[j] & 2) ? -res : res;
+    }
+    if (big) {
+#pragma unroll
+        for (int j = 0; j < N; j++) out[j] = cos(x[j]);
+    }
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
 // Axis map: one coordinate of the ChangeOfVariables the reference applies to every tuple-domain
 // problem (src/common.jl:97-103).  kind: 0 finite, 1 only lb infinite, 2 only ub infinite, 3 both.
 // ------------------------------------------------------------------------------------------------
@@ -90,6 +224,15 @@ __device__ __forceinline__ void t2ujac(int tr, double t, const AxisMap &m, doubl
 // ------------------------------------------------------------------------------------------------
 template <int FAM, int D> struct Family;
 
+__device__ __forceinline__ double cos_bf(double x) { double xi[1] = {x}, o[1]; cos_bfN<1>(xi, o); return o[0]; }
+
+// finish on N independent accumulators in lock step (families with a vectorised transcendental override sep_finishN)
+template <typename F, int N>
+__device__ __forceinline__ void finishN_default(const double (&acc)[N], const double *par, double (&out)[N]) {
+#pragma unroll
+    for (int j = 0; j < N; j++) out[j] = F::sep_finish(acc[j], par);
+}
+
 template <int D> struct Family<IB200_FAM_SINXP, D> {
     static constexpr int NQ = 1; static constexpr bool kProd = true;
     __device__ static void prepare(const double *par, double (&q)[NQ]) { q[0] = par[0]; }
@@ -97,17 +240,23 @@ template <int D> struct Family<IB200_FAM_SINXP, D> {
     __device__ static double sep_init(const double *) { return 1.0; }
     __device__ static double sep_term(int, double x, const double *par) { return sin(x * par[0]); }
     __device__ static double sep_finish(double acc, const double *) { return acc; }
+    template <int N> __device__ static void sep_finishN(const double (&acc)[N], const double *par, double (&out)[N]) {
+        finishN_default<Family<IB200_FAM_SINXP, D>, N>(acc, par, out);
+    }
 };
 
 template <int D> struct Family<IB200_FAM_GLTEST, D> {
     static constexpr int NQ = 1; static constexpr bool kProd = true;
     __device__ static void prepare(const double *par, double (&q)[NQ]) { q[0] = par[0]; }
     __device__ static double eval(const double (&x)[D], const double (&q)[NQ]) {
-        return fma(5.0, x[0], sin(x[0])) - q[0] * exp(x[0]);
+        return fma(5.0, x[0], sin(x[0])) - q[0] * exp_bf(x[0]);
     }
     __device__ static double sep_init(const double *) { return 1.0; }
-    __device__ static double sep_term(int, double x, const double *par) { return fma(5.0, x, sin(x)) - par[0] * exp(x); }
+    __device__ static double sep_term(int, double x, const double *par) { return fma(5.0, x, sin(x)) - par[0] * exp_bf(x); }
     __device__ static double sep_finish(double acc, const double *) { return acc; }
+    template <int N> __device__ static void sep_finishN(const double (&acc)[N], const double *par, double (&out)[N]) {
+        finishN_default<Family<IB200_FAM_GLTEST, D>, N>(acc, par, out);
+    }
 };
 
 template <int D> struct Family<IB200_FAM_GENZ_OSC, D> {
@@ -121,11 +270,14 @@ template <int D> struct Family<IB200_FAM_GENZ_OSC, D> {
         double s = q[0];
 #pragma unroll
         for (int i = 0; i < D; i++) s = fma(q[1 + i], x[i], s);
-        return cos(s);
+        return cos_bf(s);
     }
     __device__ static double sep_init(const double *par) { return IB_TWO_PI * par[D]; }
     __device__ static double sep_term(int k, double x, const double *par) { return par[k] * x; }
-    __device__ static double sep_finish(double acc, const double *) { return cos(acc); }
+    __device__ static double sep_finish(double acc, const double *) { return cos_bf(acc); }
+    template <int N> __device__ static void sep_finishN(const double (&acc)[N], const double *par, double (&out)[N]) {
+        cos_bfN<N>(acc, out);
+    }
 };
 
 template <int D> struct Family<IB200_FAM_GENZ_PROD, D> {
@@ -146,6 +298,9 @@ template <int D> struct Family<IB200_FAM_GENZ_PROD, D> {
         return 1.0 / fma(t, t, 1.0 / (par[k] * par[k]));
     }
     __device__ static double sep_finish(double acc, const double *) { return acc; }
+    template <int N> __device__ static void sep_finishN(const double (&acc)[N], const double *par, double (&out)[N]) {
+        finishN_default<Family<IB200_FAM_GENZ_PROD, D>, N>(acc, par, out);
+    }
 };
 
 template <int D> struct Family<IB200_FAM_GENZ_CORN, D> {
@@ -169,6 +324,9 @@ template <int D> struct Family<IB200_FAM_GENZ_CORN, D> {
     __device__ static double sep_init(const double *) { return 1.0; }
     __device__ static double sep_term(int k, double x, const double *par) { return par[k] * x; }
     __device__ static double sep_finish(double acc, const double *) { return pw(acc); }
+    template <int N> __device__ static void sep_finishN(const double (&acc)[N], const double *par, double (&out)[N]) {
+        finishN_default<Family<IB200_FAM_GENZ_CORN, D>, N>(acc, par, out);
+    }
 };
 
 template <int D> struct Family<IB200_FAM_GENZ_GAUSS, D> {
@@ -181,11 +339,16 @@ template <int D> struct Family<IB200_FAM_GENZ_GAUSS, D> {
         double s = 0.0;
 #pragma unroll
         for (int i = 0; i < D; i++) { const double t = q[i] * (x[i] - q[D + i]); s = fma(t, t, s); }
-        return exp(-s);
+        return exp_bf(-s);
     }
     __device__ static double sep_init(const double *) { return 0.0; }
     __device__ static double sep_term(int k, double x, const double *par) { const double t = par[k] * (x - par[D + k]); return t * t; }
-    __device__ static double sep_finish(double acc, const double *) { return exp(-acc); }
+    __device__ static double sep_finish(double acc, const double *) { return exp_bf(-acc); }
+    template <int N> __device__ static void sep_finishN(const double (&acc)[N], const double *par, double (&out)[N]) {
+        double x[N];
+        _Pragma("unroll") for (int j = 0; j < N; j++) x[j] = -acc[j];
+        exp_bfN<N>(x, out);
+    }
 };
 
 template <int D> struct Family<IB200_FAM_GENZ_C0, D> {
@@ -198,11 +361,16 @@ template <int D> struct Family<IB200_FAM_GENZ_C0, D> {
         double s = 0.0;
 #pragma unroll
         for (int i = 0; i < D; i++) s = fma(q[i], fabs(x[i] - q[D + i]), s);
-        return exp(-s);
+        return exp_bf(-s);
     }
     __device__ static double sep_init(const double *) { return 0.0; }
     __device__ static double sep_term(int k, double x, const double *par) { return par[k] * fabs(x - par[D + k]); }
-    __device__ static double sep_finish(double acc, const double *) { return exp(-acc); }
+    __device__ static double sep_finish(double acc, const double *) { return exp_bf(-acc); }
+    template <int N> __device__ static void sep_finishN(const double (&acc)[N], const double *par, double (&out)[N]) {
+        double x[N];
+        _Pragma("unroll") for (int j = 0; j < N; j++) x[j] = -acc[j];
+        exp_bfN<N>(x, out);
+    }
 };
 
 template <int D> struct Family<IB200_FAM_GENZ_DISC, D> {
@@ -217,13 +385,16 @@ template <int D> struct Family<IB200_FAM_GENZ_DISC, D> {
         double s = 0.0;
 #pragma unroll
         for (int i = 0; i < D; i++) s = fma(q[i], x[i], s);
-        return zero ? 0.0 : exp(s);
+        return zero ? 0.0 : exp_bf(s);
     }
     __device__ static double sep_init(const double *) { return 0.0; }
     __device__ static double sep_term(int k, double x, const double *par) {
-        return (k < 2 && x > par[D + k]) ? -INFINITY : par[k] * x;   // exp(-inf) == 0
+        return (k < 2 && x > par[D + k]) ? -INFINITY : par[k] * x;   // exp_bf(-inf) == 0
     }
-    __device__ static double sep_finish(double acc, const double *) { return exp(acc); }
+    __device__ static double sep_finish(double acc, const double *) { return exp_bf(acc); }
+    template <int N> __device__ static void sep_finishN(const double (&acc)[N], const double *par, double (&out)[N]) {
+        exp_bfN<N>(acc, out);
+    }
 };
 
 template <int D> struct Family<IB200_FAM_COSPROD, D> {
@@ -241,6 +412,9 @@ template <int D> struct Family<IB200_FAM_COSPROD, D> {
     __device__ static double sep_init(const double *) { return 1.0; }
     __device__ static double sep_term(int k, double x, const double *par) { return cos(par[k] * x); }
     __device__ static double sep_finish(double acc, const double *) { return acc; }
+    template <int N> __device__ static void sep_finishN(const double (&acc)[N], const double *par, double (&out)[N]) {
+        finishN_default<Family<IB200_FAM_COSPROD, D>, N>(acc, par, out);
+    }
 };
 
 template <int D> struct Family<IB200_FAM_GAUSSPOLY, D> {
@@ -258,7 +432,7 @@ template <int D> struct Family<IB200_FAM_GAUSSPOLY, D> {
             const int ki = (int)q[2 * D + i];
             for (int j = 0; j < ki; j++) pr *= x[i];
         }
-        return pr * exp(-s);
+        return pr * exp_bf(-s);
     }
     __device__ static double sep_init(const double *par) { return par[3 * D]; }
     __device__ static double sep_term(int k, double x, const double *par) {
@@ -266,9 +440,12 @@ template <int D> struct Family<IB200_FAM_GAUSSPOLY, D> {
         double pr = 1.0;
         const int ki = (int)par[2 * D + k];
         for (int j = 0; j < ki; j++) pr *= x;
-        return pr * exp(-(t * t));
+        return pr * exp_bf(-(t * t));
     }
     __device__ static double sep_finish(double acc, const double *) { return acc; }
+    template <int N> __device__ static void sep_finishN(const double (&acc)[N], const double *par, double (&out)[N]) {
+        finishN_default<Family<IB200_FAM_GAUSSPOLY, D>, N>(acc, par, out);
+    }
 };
 
 template <int D> struct Family<IB200_FAM_EXPLIN, D> {
@@ -281,11 +458,14 @@ template <int D> struct Family<IB200_FAM_EXPLIN, D> {
         double s = 0.0;
 #pragma unroll
         for (int i = 0; i < D; i++) s = fma(q[i], x[i], s);
-        return exp(s);
+        return exp_bf(s);
     }
     __device__ static double sep_init(const double *) { return 0.0; }
     __device__ static double sep_term(int k, double x, const double *par) { return par[k] * x; }
-    __device__ static double sep_finish(double acc, const double *) { return exp(acc); }
+    __device__ static double sep_finish(double acc, const double *) { return exp_bf(acc); }
+    template <int N> __device__ static void sep_finishN(const double (&acc)[N], const double *par, double (&out)[N]) {
+        exp_bfN<N>(acc, out);
+    }
 };
 
 // ------------------------------------------------------------------------------------------------

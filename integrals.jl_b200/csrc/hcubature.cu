@@ -1,5 +1,6 @@
 // hcubature.cu -- C entry point of the batched adaptive cubature (kernels: hcubature_impl.cuh)
 #include "hcubature_impl.cuh"
+#include "hcubature_pair.cuh"
 
 namespace hc {
 template <> int32_t launch<1>(ib200_ctx *, int, bool, Params &);
@@ -10,6 +11,12 @@ template <> int32_t launch<5>(ib200_ctx *, int, bool, Params &);
 template <> int32_t launch<6>(ib200_ctx *, int, bool, Params &);
 template <> int32_t launch<7>(ib200_ctx *, int, bool, Params &);
 template <> int32_t launch<8>(ib200_ctx *, int, bool, Params &);
+}
+namespace hp {
+template <> int32_t launch<2>(ib200_ctx *, int, bool, Params &);
+template <> int32_t launch<3>(ib200_ctx *, int, bool, Params &);
+template <> int32_t launch<4>(ib200_ctx *, int, bool, Params &);
+template <> int32_t launch<5>(ib200_ctx *, int, bool, Params &);
 }
 
 extern "C" int32_t ib200_hcubature_batch(ib200_ctx *ctx, int32_t family, int32_t dim, int32_t transform,
@@ -70,6 +77,30 @@ extern "C" int32_t ib200_hcubature_batch(ib200_ctx *ctx, int32_t family, int32_t
     p.out_I = oI.d; p.out_E = oE.d; p.out_nevals = oN.d; p.out_status = oS.d;
 
     ctx->err.clear();
+    // pair mode (thread per box, hcubature_pair.cuh) for 2 <= dim <= 5 when the batch can fill the GPU's pair slots;
+    // warp-per-problem mode (hcubature_impl.cuh) for 1-D, dim >= 6 and small batches
+    const bool pair_ok = dim >= 2 && dim <= 5 && cap <= 65536 - 1023;
+    const bool use_pair = pair_ok && (ctx->opt_hcub_mode == 2 || (ctx->opt_hcub_mode == 0 && nprob >= 4096));
+    if (use_pair) {
+        hp::Params q;
+        q.params = dpar.d; q.nparam = nparam; q.nprob = nprob; q.lb = dlb.d; q.ub = dub.d; q.bpp = bpp; q.tr = transform;
+        q.rtol = reltol; q.atol = abstol; q.maxevals = maxevals; q.initdiv = initdiv;
+        q.cap = (int)((cap + 1023) / 1024 * 1024);
+        q.keys = q.l1 = q.rec = nullptr; q.l1off = nullptr; q.counter = counter;
+        q.out_I = oI.d; q.out_E = oE.d; q.out_nevals = oN.d; q.out_status = oS.d;
+        ib200_time_begin(ctx);
+        switch (dim) {
+        case 2: rc = hp::launch<2>(ctx, family, allfin, q); break;
+        case 3: rc = hp::launch<3>(ctx, family, allfin, q); break;
+        case 4: rc = hp::launch<4>(ctx, family, allfin, q); break;
+        default: rc = hp::launch<5>(ctx, family, allfin, q); break;
+        }
+        if (rc) return rc;
+        ib200_time_end(ctx);
+        if ((rc = oI.finish(ctx)) || (rc = oE.finish(ctx)) || (rc = oN.finish(ctx)) || (rc = oS.finish(ctx))) return rc;
+        if (oI.is_host() || oE.is_host() || oN.is_host() || oS.is_host()) IB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return IB200_OK;
+    }
     ib200_time_begin(ctx);
     switch (dim) {
     case 1: rc = hc::launch<1>(ctx, family, allfin, p); break;

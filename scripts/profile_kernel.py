@@ -7,6 +7,8 @@ import numpy as np, torch
 import integrals_b200 as ib
 import integrals_b200.workloads as WL
 eng = ib.Engine(0); F = ib.FAMILY_IDS
+MAXEV = int(os.environ.get("PK_MAXEVALS", "4000000"))
+if os.environ.get("PK_HCUB_MODE"): eng.set_option("hcub_mode", int(os.environ["PK_HCUB_MODE"]))
 kind = sys.argv[1]
 reps = 2
 for rep in range(reps):
@@ -14,7 +16,7 @@ for rep in range(reps):
         fam, nprob = sys.argv[2], int(sys.argv[3]); d = int(sys.argv[4]) if len(sys.argv) > 4 else 4
         par = torch.from_numpy(np.ascontiguousarray(WL.genz_params(fam, d, nprob).T)).cuda()
         oI = torch.empty(nprob, dtype=torch.float64, device="cuda")
-        eng.hcubature_batch(F[fam], d, np.zeros(d), np.ones(d), par, reltol=1e-6, abstol=1e-8, maxevals=4_000_000, out_I=oI,
+        eng.hcubature_batch(F[fam], d, np.zeros(d), np.ones(d), par, reltol=1e-6, abstol=1e-8, maxevals=MAXEV, out_I=oI,
                             out_E=torch.empty_like(oI), out_nevals=torch.empty(nprob, dtype=torch.int64, device="cuda"),
                             out_status=torch.empty(nprob, dtype=torch.int32, device="cuda"))
     elif kind == "quadgk":

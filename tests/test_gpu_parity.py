@@ -229,9 +229,17 @@ def test_quadgk_maxevals_and_status(eng, O):
 
 
 # ------------------------------------------------------------------------------------- HCubature
+@pytest.fixture(params=[1, 2], ids=["warp_mode", "pair_mode"])
+def hcub_mode(request, eng):
+    """run the test under both HCubature kernels: 1 = warp per problem, 2 = pair mode (thread per box)"""
+    eng.set_option("hcub_mode", request.param)
+    yield request.param
+    eng.set_option("hcub_mode", 0)
+
+
 @pytest.mark.parametrize("family", GENZ)
 @pytest.mark.parametrize("dim", [2, 3, 4])
-def test_hcubature_matches_oracle(eng, O, family, dim):
+def test_hcubature_matches_oracle(eng, O, family, dim, hcub_mode):
     nprob = 24
     par = genz_params(family, dim, nprob, scale=0.25)
     lb, ub = np.zeros(dim), np.ones(dim)
@@ -250,7 +258,7 @@ def test_hcubature_matches_oracle(eng, O, family, dim):
     assert np.mean(ne == ner) > 0.7         # identical refinement sequences except at rounding-level ties
 
 
-def test_hcubature_1d_and_infinite(eng, O):
+def test_hcubature_1d_and_infinite(eng, O, hcub_mode):
     cases = [(-INF, INF), (INF, -INF), (0.0, INF), (-INF, 0.0), (1.0, 4.0), (4.0, 1.0)]
     lb = np.array([[c[0]] for c in cases]).T; ub = np.array([[c[1]] for c in cases]).T
     P = np.asfortranarray(np.array([[0.9, 0.2]] * len(cases)).T)
@@ -270,7 +278,7 @@ def test_hcubature_1d_and_infinite(eng, O):
         assert abs(I[0] - Ir[0]) <= 1e-3
 
 
-def test_hcubature_initdiv_and_budget(eng, O):
+def test_hcubature_initdiv_and_budget(eng, O, hcub_mode):
     par = genz_params("genz_gaussian", 3, 8, scale=0.5)
     lb, ub = np.zeros(3), np.ones(3)
     I, E, ne, st = eng.hcubature_batch(F["genz_gaussian"], 3, lb, ub, par, reltol=1e-7, abstol=0.0, initdiv=3)
