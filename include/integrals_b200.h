@@ -131,6 +131,25 @@ int32_t ib200_hcubature_batch(ib200_ctx *ctx, int32_t family, int32_t dim, int32
                               double reltol, double abstol, int64_t maxevals, int32_t initdiv,
                               double *out_I, double *out_E, int64_t *out_nevals, int32_t *out_status);
 
+/* -- one large domain (BASELINE config 5): the same HCubature call, src/Integrals.jl:386-393, for a single
+      integral that is too expensive for one warp: region-parallel rounds on a device-resident box queue
+      (csrc/hcub_single.cu).  With a communicator (ib200_comm_init) every rank of the job calls this with the
+      same arguments; the domain is partitioned by region and the ranks exchange (integral, error) partial sums
+      once per refinement round over NCCL.  max_boxes: budget of rule applications over all ranks (the analogue
+      of maxiters / points-per-rule); store_boxes: per-GPU box capacity, 0 = derive from the budget and free HBM.
+      out_stats (may be NULL): int64[6] = integrand evaluations, rule applications, boxes stored, rounds,
+      status (IB200_ST_*), world size. */
+int32_t ib200_hcubature_single(ib200_ctx *ctx, int32_t family, int32_t dim, int32_t transform,
+                               const double *lb, const double *ub, const double *params, int32_t nparam,
+                               double reltol, double abstol, int64_t max_boxes, int64_t store_boxes,
+                               double *out_I, double *out_E, int64_t *out_stats);
+/* multi-GPU plumbing for ib200_hcubature_single: one process per GPU.  Rank 0 obtains a 128-byte id
+   (ncclUniqueId) and distributes it by any means (torch.distributed / MPI broadcast); every rank then
+   calls ib200_comm_init on its own context.  NCCL is loaded at run time (dlopen of libnccl.so.2). */
+int32_t ib200_comm_unique_id(void *id128);
+int32_t ib200_comm_init(ib200_ctx *ctx, int32_t nranks, int32_t rank, const void *id128);
+int32_t ib200_comm_destroy(ib200_ctx *ctx);
+
 /* -- measurement helper: dependency-free DFMA chains on every SM; returns TFLOP/s (2 flops/DFMA).
       This is the FP64 roofline denominator. */
 int32_t ib200_measure_fp64_peak(ib200_ctx *ctx, double *tflops, double *ms);

@@ -24,7 +24,8 @@ ERR_NAMES = {-1: "IB200_ERR_INVALID", -2: "IB200_ERR_CUDA", -3: "IB200_ERR_OOM",
 SYMBOLS = ["ib200_version", "ib200_create", "ib200_destroy", "ib200_last_error", "ib200_set_stream",
            "ib200_synchronize", "ib200_kernel_launches", "ib200_family_nparam", "ib200_last_kernel_ms",
            "ib200_set_option", "ib200_sampled", "ib200_fixed_rule_tensor_batch", "ib200_fixed_rule_nodes_batch",
-           "ib200_gauss_legendre_batch", "ib200_quadgk_batch", "ib200_hcubature_batch", "ib200_measure_fp64_peak"]
+           "ib200_gauss_legendre_batch", "ib200_quadgk_batch", "ib200_hcubature_batch", "ib200_measure_fp64_peak",
+           "ib200_hcubature_single", "ib200_comm_unique_id", "ib200_comm_init", "ib200_comm_destroy"]
 
 
 class IB200Error(RuntimeError):
@@ -70,6 +71,11 @@ def load_library():
     L.ib200_quadgk_batch.restype = i32
     L.ib200_hcubature_batch.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp, i32, i64, dp, dp, i64, i32, vp, vp, vp, vp]
     L.ib200_hcubature_batch.restype = i32
+    L.ib200_hcubature_single.argtypes = [vp, i32, i32, i32, vp, vp, vp, i32, dp, dp, i64, i64, C.POINTER(dp), C.POINTER(dp), vp]
+    L.ib200_hcubature_single.restype = i32
+    L.ib200_comm_unique_id.argtypes = [vp]; L.ib200_comm_unique_id.restype = i32
+    L.ib200_comm_init.argtypes = [vp, i32, i32, vp]; L.ib200_comm_init.restype = i32
+    L.ib200_comm_destroy.argtypes = [vp]; L.ib200_comm_destroy.restype = i32
     L.ib200_measure_fp64_peak.argtypes = [vp, C.POINTER(dp), C.POINTER(dp)]; L.ib200_measure_fp64_peak.restype = i32
     _lib = L
     return L
@@ -243,6 +249,48 @@ class Engine:
                                                  int(min(maxevals, MAXEVALS_UNBOUNDED)), int(initdiv),
                                                  a[3][0], a[4][0], a[5][0], a[6][0]))
         return out_I, out_E, out_nevals, out_status
+
+
+    def hcubature_single(self, family, dim, lb, ub, params, reltol=1e-8, abstol=1e-8, max_boxes=1 << 24, store_boxes=0,
+                         transform=0):
+        """One large domain, region-parallel rounds (all ranks of the communicator call this together).
+        Returns (I, E, stats dict)."""
+        lb = np.ascontiguousarray(lb, dtype=np.float64); ub = np.ascontiguousarray(ub, dtype=np.float64)
+        params = np.ascontiguousarray(np.ravel(params), dtype=np.float64)
+        I = C.c_double(); E = C.c_double(); st = np.zeros(6, dtype=np.int64)
+        self._check(self.L.ib200_hcubature_single(self.h, family, dim, transform, lb.ctypes.data, ub.ctypes.data, params.ctypes.data,
+                                                  params.size, float(reltol), float(abstol), int(max_boxes), int(store_boxes),
+                                                  C.byref(I), C.byref(E), st.ctypes.data))
+        return I.value, E.value, dict(nevals=int(st[0]), rule_applications=int(st[1]), boxes=int(st[2]), rounds=int(st[3]),
+                                      status=int(st[4]), world=int(st[5]))
+
+    # ---- multi-GPU communicator (single-domain solve) ------------------------------------------
+    def comm_unique_id(self):
+        buf = C.create_string_buffer(128)
+        rc = self.L.ib200_comm_unique_id(buf)
+        if rc != 0:
+            raise IB200Error(rc, self.L.ib200_last_error(None).decode())
+        return buf.raw
+
+    def comm_init(self, nranks, rank, id128):
+        self._keep_id = C.create_string_buffer(bytes(id128), 128)
+        self._check(self.L.ib200_comm_init(self.h, int(nranks), int(rank), self._keep_id))
+
+    def comm_init_from_torch(self, group=None):
+        """Build the library's NCCL communicator over the ranks of a torch.distributed group: rank 0 creates the
+        id, torch broadcasts the 128 bytes (control plane)."""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        dev = torch.device("cuda", self.device) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+        t = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            t = torch.frombuffer(bytearray(self.comm_unique_id()), dtype=torch.uint8).to(dev)
+        dist.broadcast(t, src=0, group=group)
+        self.comm_init(world, rank, bytes(t.cpu().numpy().tobytes()))
+
+    def comm_destroy(self):
+        self._check(self.L.ib200_comm_destroy(self.h))
 
 
 _default_engines = {}

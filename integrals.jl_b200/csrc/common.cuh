@@ -25,6 +25,8 @@ struct ib200_ctx {
     double last_ms = 0.0;
     int64_t launches = 0;
     std::string err;
+    void *comm = nullptr;                    // ncclComm_t of the multi-GPU single-domain solve (hcub_single.cu)
+    int comm_rank = 0, comm_world = 1;
     struct Buf { void *p = nullptr; size_t cap = 0; } scratch[SL_COUNT];
     // options
     int64_t opt_adaptive_warps_per_sm = 0;   // 0 = kernel default
