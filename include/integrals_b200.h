@@ -81,7 +81,8 @@ int64_t     ib200_kernel_launches(ib200_ctx *ctx);       /* kernels launched so 
 int32_t     ib200_family_nparam(int32_t family, int32_t dim);   /* doubles per problem, <0 bad */
 /* timing of the most recent call's kernels on the context's stream, ms (CUDA events) */
 double      ib200_last_kernel_ms(ib200_ctx *ctx);
-/* optional knobs: key in {"adaptive_warps_per_sm","hcub_capacity","sampled_slabs","hcub_mode"} */
+/* optional knobs: key in {"adaptive_warps_per_sm","hcub_capacity","sampled_slabs","hcub_mode",
+   "single_round_percent"} */
 int32_t     ib200_set_option(ib200_ctx *ctx, const char *key, int64_t value);
 
 /* -- sampled data: replaces evalrule(data, weights, dim) src/sampled.jl:51-124 with the weights of
@@ -136,7 +137,8 @@ int32_t ib200_hcubature_batch(ib200_ctx *ctx, int32_t family, int32_t dim, int32
       (csrc/hcub_single.cu).  With a communicator (ib200_comm_init) every rank of the job calls this with the
       same arguments; the domain is partitioned by region and the ranks exchange (integral, error) partial sums
       once per refinement round over NCCL.  max_boxes: budget of rule applications over all ranks (the analogue
-      of maxiters / points-per-rule); store_boxes: per-GPU box capacity, 0 = derive from the budget and free HBM.
+      of maxiters / points-per-rule); store_boxes: per-GPU box capacity; 0 = what the budget can create on
+      one rank, at most 2^26 boxes and 70 % of the free HBM (a full store ends the solve with IB200_ST_MAXEVALS).
       out_stats (may be NULL): int64[6] = integrand evaluations, rule applications, boxes stored, rounds,
       status (IB200_ST_*), world size. */
 int32_t ib200_hcubature_single(ib200_ctx *ctx, int32_t family, int32_t dim, int32_t transform,

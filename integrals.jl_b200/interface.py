@@ -147,10 +147,15 @@ class QuadGKB200(AbstractB200Algorithm):
 
 
 class HCubatureB200(AbstractB200Algorithm):
-    """Adaptive Genz-Malik cubature, drop-in for HCubatureJL (src/algorithms.jl:108-115)."""
+    """Adaptive Genz-Malik cubature, drop-in for HCubatureJL (src/algorithms.jl:108-115).
+    single_domain=True sends ONE expensive integral (scalar problem, dim >= 2) to the region-parallel driver
+    (ib200_hcubature_single; all ranks of the engine's communicator take part); `maxiters` then bounds the
+    integrand evaluations summed over all ranks, as it does for HCubatureJL."""
 
-    def __init__(self, initdiv=1):
+    def __init__(self, initdiv=1, single_domain=False, store_boxes=0):
         self.initdiv = int(initdiv)
+        self.single_domain = bool(single_domain)
+        self.store_boxes = int(store_boxes)
 
 
 class QuadratureRuleB200(AbstractB200Algorithm):
@@ -287,6 +292,16 @@ def solve_cache(cache):
             raise ValueError("QuadGKB200 only accepts one-dimensional quadrature problems.")    # Integrals.jl:263-266
         I, E, ne, st = eng.quadgk_batch(fam, lb, ub, p, reltol=reltol, abstol=abstol, maxevals=maxiters, transform=tr)
         stats = dict(nevals=ne, status=st)
+    elif isinstance(inner, HCubatureB200) and inner.single_domain:
+        if not scalar or dim < 2:
+            raise ValueError("HCubatureB200(single_domain=True) solves one problem of dimension >= 2 per call")
+        if inner.initdiv != 1:
+            raise ValueError("HCubatureB200(single_domain=True) does not take initdiv")
+        npts = 1 + 4 * dim + 2 * dim * (dim - 1) + (1 << dim)
+        max_boxes = max(1, min(int(maxiters), _lib.MAXEVALS_UNBOUNDED) // npts)
+        Iv, Ev, stats = eng.hcubature_single(fam, dim, lb, ub, p[:, 0], reltol=reltol, abstol=abstol, max_boxes=max_boxes,
+                                             store_boxes=inner.store_boxes, transform=tr)
+        return IntegralSolution(Iv, Ev, prob, inner, ReturnCode.Success, None, stats)
     elif isinstance(inner, HCubatureB200):
         I, E, ne, st = eng.hcubature_batch(fam, dim, lb, ub, p, reltol=reltol, abstol=abstol, maxevals=maxiters,
                                            initdiv=inner.initdiv, transform=tr)

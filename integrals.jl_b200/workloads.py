@@ -60,3 +60,19 @@ C1 = dict(lb=-2.0, ub=5.0, reltol=1e-10, abstol=1e-8, nprob=65536)
 C2 = dict(m=4096, n=1 << 20)
 C3 = dict(family="genz_oscillatory", dim=3, n1d=64, nprob=1 << 20)
 C4 = dict(dim=4, nprob_per_family=1 << 18, reltol=1e-6, abstol=1e-8, maxiters=4_000_000, initdiv=1)
+C5 = dict(dim=8, reltol=1e-9, abstol=0.0, sum_a=12.5, seed=1)
+
+
+def c5_problem():
+    """-> lb, ub, params [a; u], exact.  8-D Genz Gaussian exp(-sum a_i^2 (x_i-u_i)^2), sum a_i = 12.5, seed 1; axes 1-2 on
+    (-inf, inf) (transformation_if_inf), axes 3-8 on [0, 1].  Closed form: prod sqrt(pi)/a_i over the
+    infinite axes times prod sqrt(pi)/(2 a_i) (erf(a_i (1-u_i)) + erf(a_i u_i)) over the finite ones."""
+    import math
+    rng = np.random.default_rng(C5["seed"])
+    d = C5["dim"]
+    u = rng.random(d); r = rng.random(d)
+    a = r * C5["sum_a"] / r.sum()
+    lb = np.array([-np.inf, -np.inf] + [0.0] * (d - 2)); ub = np.array([np.inf, np.inf] + [1.0] * (d - 2))
+    exact = math.prod(math.sqrt(math.pi) / ai for ai in a[:2]) * math.prod(
+        math.sqrt(math.pi) / (2 * ai) * (math.erf(ai * (1 - ui)) + math.erf(ai * ui)) for ai, ui in zip(a[2:], u[2:]))
+    return lb, ub, np.concatenate([a, u]), exact

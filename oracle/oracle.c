@@ -706,6 +706,124 @@ int orc_hcubature(orc_integrand f, void *user, int dim, const double *a, const d
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Round-synchronous variant of the HCubature loop (NOT in the reference): the checker for
+ * ib200_hcubature_single (csrc/hcub_single.cu), which replaces the strictly sequential "pop the
+ * worst box" order of HCubature.hcubature (call site src/Integrals.jl:386-393) by rounds --
+ * every box whose error is >= half the current upper bound of the largest box error is bisected
+ * in the same round; the threshold is lowered further to the exponent-histogram bound below which the
+ * reference would provably not refine either.  Same rule (gm_rule), same split axis, same stopping test, same final
+ * re-sum; only the ORDER in which boxes are refined differs, so (I, E) agree with orc_hcubature
+ * within the requested tolerance, and with the CUDA path to summation-order rounding.
+ * m0: the domain is pre-bisected m0 times (axis = level mod dim), as the multi-GPU driver does
+ * before dealing sub-boxes to the ranks.  max_boxes: budget of rule applications.
+ * ------------------------------------------------------------------------------------------ */
+double orc_round_fraction = 0.5;
+int orc_hcubature_rounds(orc_integrand f, void *user, int dim, const double *a, const double *b,
+                         double rtol, double atol, int64_t max_boxes, int m0,
+                         double *Iout, double *Eout, int64_t *napplied_out, int64_t *nboxes_out, int64_t *rounds_out)
+{
+    if (dim < 2 || dim > ORC_MAXDIM || rtol < 0 || atol < 0 || max_boxes < 1 || m0 < 0 || m0 > 30) return -1;
+    if (rtol == 0 && atol == 0) rtol = sqrt(2.220446049250313e-16);
+    int64_t cap = (1LL << m0) + 1024, len = 0, ntodo = 0, applied = 0, rounds = 0;
+    orc_box *t = (orc_box *)malloc(sizeof(orc_box) * (size_t)cap);
+    int64_t *todo = (int64_t *)malloc(sizeof(int64_t) * (size_t)cap);
+    for (int64_t q = 0; q < (1LL << m0); q++) {
+        orc_box bx;
+        for (int i = 0; i < dim; i++) { bx.a[i] = a[i]; bx.b[i] = b[i]; }
+        for (int lev = 0; lev < m0; lev++) {
+            int k = lev % dim;
+            double w = (bx.b[k] - bx.a[k]) * 0.5;
+            if ((q >> lev) & 1) bx.a[k] = bx.a[k] + w; else bx.b[k] = bx.b[k] - w;
+        }
+        bx.I = 0.0; bx.E = 0.0; bx.kdiv = 0;
+        t[len] = bx; todo[ntodo++] = len; len++;
+    }
+    double I = 0.0, E = 0.0, theta = 0.0;
+    int status = 0;
+    for (;;) {
+        double mx = 0.0;
+        for (int64_t j = 0; j < ntodo; j++) {
+            orc_box *bx = &t[todo[j]];
+            gm_rule(f, user, dim, bx->a, bx->b, &bx->I, &bx->E, &bx->kdiv);
+            I += bx->I; E += bx->E; if (bx->E > mx) mx = bx->E;
+        }
+        applied += ntodo; rounds++; ntodo = 0;
+        if (E <= fmax(rtol * fabs(I), atol)) break;
+        if (!isfinite(E)) { status = 2; break; }
+        if (applied >= max_boxes) { status = 1; break; }
+        theta = 0.5 * fmax(mx, theta);
+        {   /* threshold from the exponent histogram (see the header comment of csrc/hcub_single.cu) */
+            double cnt[2048];
+            for (int b2 = 0; b2 < 2048; b2++) cnt[b2] = 0.0;
+            for (int64_t i = 0; i < len; i++) { uint64_t bits; memcpy(&bits, &t[i].E, 8); cnt[(bits >> 52) & 0x7ff] += 1.0; }
+            const double tol = fmax(rtol * fabs(I), atol);
+            int bh = -1; double low = 0.0;
+            for (int b2 = 0; b2 < 2047; b2++) {
+                if (cnt[b2] != 0.0) { low += cnt[b2] * (b2 == 0 ? 0.0 : scalbn(1.0, b2 - 1023)); if (!(low <= tol)) break; }
+                bh = b2;
+            }
+            const double remaining = (double)max_boxes - (double)applied;
+            int bb = 2047; double above = 0.0;
+            for (int b2 = 2046; b2 >= 0; b2--) { above += cnt[b2]; if (2.0 * above > remaining) break; bb = b2; }
+            /* (3) selectivity: at most ORC_ROUND_FRACTION of the stored boxes per round (the largest errors first) */
+            int bf = 2047; double top = 0.0;
+            for (int b2 = 2046; b2 >= 0; b2--) { top += cnt[b2]; if (top > orc_round_fraction * (double)len) break; bf = b2; }
+            if (bf > bb) bb = bf;
+            const int bs = (bh + 1 > bb) ? bh + 1 : bb;
+            const double theta_h = bs <= 0 ? 0.0 : (bs >= 2047 ? 1.7976931348623157e308 : scalbn(1.0, bs - 1023));
+            theta = fmin(theta, theta_h);
+        }
+        int64_t nsplit = 0;
+        for (int64_t i = 0; i < len; i++) if (t[i].E >= theta) nsplit++;
+        if (len + nsplit > cap) {
+            cap = 2 * (len + nsplit);
+            t = (orc_box *)realloc(t, sizeof(orc_box) * (size_t)cap);
+            todo = (int64_t *)realloc(todo, sizeof(int64_t) * (size_t)cap);
+        }
+        const int64_t n0 = len;
+        for (int64_t i = 0; i < n0; i++) {
+            if (!(t[i].E >= theta)) continue;
+            orc_box box = t[i];
+            I -= box.I; E -= box.E;
+            int k = box.kdiv;
+            double w = (box.b[k] - box.a[k]) * 0.5;
+            orc_box b1 = box, b2 = box;
+            b1.a[k] = box.a[k] + w; b1.I = 0.0; b1.E = 0.0;
+            b2.b[k] = box.b[k] - w; b2.I = 0.0; b2.E = 0.0;
+            t[i] = b1; t[len] = b2;
+            todo[ntodo++] = i; todo[ntodo++] = len; len++;
+        }
+    }
+    I = 0.0; E = 0.0;
+    for (int64_t i = 0; i < len; i++) { I += t[i].I; E += t[i].E; }
+    free(t); free(todo);
+    *Iout = I; *Eout = E;
+    if (napplied_out) *napplied_out = applied;
+    if (nboxes_out) *nboxes_out = len;
+    if (rounds_out) *rounds_out = rounds;
+    return status;
+}
+
+int orc_solve_hcubature_rounds(orc_integrand f, void *user, int dim, const double *lb, const double *ub, int tr,
+                               double reltol, double abstol, int64_t max_boxes, int m0,
+                               double *I, double *E, int64_t *napplied, int64_t *nboxes, int64_t *rounds)
+{
+    orc_cov c = {f, user, dim, tr, lb, ub};
+    double tl[ORC_MAXDIM], tu[ORC_MAXDIM];
+    for (int i = 0; i < dim; i++) orc_u2t(lb[i], ub[i], &tl[i], &tu[i]);
+    return orc_hcubature_rounds(orc_cov_eval, &c, dim, tl, tu, reltol, abstol, max_boxes, m0, I, E, napplied, nboxes, rounds);
+}
+
+int orc_hcubature_rounds_family(int fam, int dim, const double *lb, const double *ub, int tr, const double *params,
+                                double reltol, double abstol, int64_t max_boxes, int m0,
+                                double *I, double *E, int64_t *napplied, int64_t *nboxes, int64_t *rounds)
+{
+    orc_family_user u = {fam, dim, params};
+    return orc_solve_hcubature_rounds(orc_family_integrand, &u, dim, lb, ub, tr, reltol, abstol, max_boxes, m0,
+                                      I, E, napplied, nboxes, rounds);
+}
+
+/* ------------------------------------------------------------------------------------------
  * Integrals.jl-level solves: init wraps every tuple-domain alg in
  * ChangeOfVariables(transformation_if_inf, alg) (src/common.jl:97-103); __solve maps the
  * domain with u2t and the integrand with t2ujac (src/Integrals.jl:192-224,

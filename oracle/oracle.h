@@ -92,6 +92,16 @@ int orc_hcubature(orc_integrand f, void *user, int dim, const double *a, const d
 void orc_cubrule(orc_integrand f, void *user, int dim, const double *a, const double *b,
                  double *I, double *E, int *kdiv);
 void orc_gk15(orc_integrand f, void *user, double a, double b, double *I, double *E);
+/* round-synchronous refinement (checker for ib200_hcubature_single; not in the reference -- see oracle.c) */
+int orc_hcubature_rounds(orc_integrand f, void *user, int dim, const double *a, const double *b,
+                         double rtol, double atol, int64_t max_boxes, int m0,
+                         double *I, double *E, int64_t *napplied, int64_t *nboxes, int64_t *rounds);
+int orc_solve_hcubature_rounds(orc_integrand f, void *user, int dim, const double *lb, const double *ub, int tr,
+                               double reltol, double abstol, int64_t max_boxes, int m0,
+                               double *I, double *E, int64_t *napplied, int64_t *nboxes, int64_t *rounds);
+int orc_hcubature_rounds_family(int fam, int dim, const double *lb, const double *ub, int tr, const double *params,
+                                double reltol, double abstol, int64_t max_boxes, int m0,
+                                double *I, double *E, int64_t *napplied, int64_t *nboxes, int64_t *rounds);
 
 /* --- Integrals.jl-level solves with the automatic ChangeOfVariables (common.jl:97-103,
        Integrals.jl:192-224): domain mapped by u2t, integrand by t2ujac, then back-end --- */

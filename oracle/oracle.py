@@ -75,6 +75,8 @@ def lib():
         L.orc_gauss_legendre_batch.argtypes = [C.c_int, _dp, _dp, C.c_int, C.c_int, _dp, C.c_int, C.c_int64,
                                                _dp, _dp, C.c_int, C.c_int, _dp, C.c_int]
         L.orc_max_threads.restype = C.c_int
+        L.orc_hcubature_rounds_family.argtypes = [C.c_int, C.c_int, _dp, _dp, C.c_int, _dp, C.c_double, C.c_double,
+                                                  C.c_int64, C.c_int, _dp, _dp, _i64p, _i64p, _i64p]
         _LIB = L
     return _LIB
 
@@ -261,6 +263,18 @@ def hcubature_batch(fam, lb, ub, params, tr="if_inf", reltol=1e-8, abstol=1e-8, 
                                    st.ctypes.data_as(_i32p), nthreads)
     assert rc == 0, rc
     return I, E, ne, st
+
+
+def hcubature_rounds(fam, lb, ub, params, tr="if_inf", reltol=1e-8, abstol=1e-8, max_boxes=1 << 24, m0=0):
+    """Round-synchronous refinement of ONE integral (checker for Engine.hcubature_single).
+    -> I, E, dict(rule_applications, boxes, rounds, status)."""
+    lb = _arr(lb); ub = _arr(ub); params = _arr(np.ravel(params))
+    fam = FAM[fam] if isinstance(fam, str) else fam
+    I = C.c_double(); E = C.c_double(); na = C.c_int64(); nb = C.c_int64(); nr = C.c_int64()
+    st = lib().orc_hcubature_rounds_family(fam, lb.size, _p(lb), _p(ub), TR[tr], _p(params), reltol, abstol, max_boxes, m0,
+                                           C.byref(I), C.byref(E), C.byref(na), C.byref(nb), C.byref(nr))
+    assert st >= 0, st
+    return I.value, E.value, dict(rule_applications=na.value, boxes=nb.value, rounds=nr.value, status=st)
 
 
 def fixed_tensor_batch(fam, lb, ub, params, x1d, w1d, tr="if_inf", nthreads=1):

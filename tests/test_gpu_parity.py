@@ -287,3 +287,109 @@ def test_hcubature_initdiv_and_budget(eng, O, hcub_mode):
     I, E, ne, st = eng.hcubature_batch(F["genz_oscillatory"], 3, lb, ub, genz_params("genz_oscillatory", 3, 4),
                                        reltol=1e-13, abstol=0.0, maxevals=5000)
     assert np.all(st == 1) and np.all(ne >= 5000) and np.all(ne < 5000 + 66)
+
+
+# ------------------------------------------------------------------------------------- committed golden fixtures
+import json   # noqa: E402
+import os     # noqa: E402
+
+GOLD = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden.json")))
+
+
+def _gb(v):
+    return np.array([INF if x == "inf" else -INF if x == "-inf" else x for x in v], dtype=np.float64)
+
+
+@pytest.mark.parametrize("rec", GOLD["tensor_gauss_legendre_rule"], ids=lambda r: f"{r['family']}-{r['dim']}d-n{r['n1d']}")
+def test_golden_tensor_rule(eng, rec):
+    x, w = np.polynomial.legendre.leggauss(rec["n1d"])
+    got = eng.fixed_rule_tensor_batch(F[rec["family"]], rec["dim"], np.array(rec["lb"]), np.array(rec["ub"]),
+                                      np.array(rec["params"]).reshape(-1, 1), x, w)[0]
+    assert abs(got - rec["value"]) <= 1e-12 * rec["abs_sum"]
+
+
+@pytest.mark.parametrize("rec", GOLD["sampled_rules"], ids=lambda r: f"n{r['n']}")
+def test_golden_sampled_rules(eng, O, rec):
+    y, x, h, n = np.array(rec["y"]), np.array(rec["x"]), rec["h"], rec["n"]
+    for key, rule, kw in (("trapezoid_uniform", "trapezoid", dict(h=h)), ("trapezoid_nonuniform", "trapezoid", dict(x=x)),
+                          ("simpson_uniform", "simpson", dict(h=h)), ("simpson_nonuniform", "simpson", dict(x=x))):
+        if key not in rec:
+            continue
+        w = O.sampled_weights(rule, n, **kw)
+        got = eng.sampled(rule, y, 1, n, 1, **kw)[0]
+        assert abs(got - rec[key]) <= 1e-12 * np.sum(np.abs(w * y)), key
+
+
+@pytest.mark.parametrize("rec", [r for r in GOLD["exact_unit_cube"] if r["family"] not in ("genz_c0", "genz_discontinuous")],
+                         ids=lambda r: f"{r['family']}-{r['dim']}d")
+def test_golden_hcubature_closed_forms(eng, rec, hcub_mode):
+    d = rec["dim"]
+    reltol = 1e-8 if d <= 3 else 1e-6
+    I, E, ne, st = eng.hcubature_batch(F[rec["family"]], d, np.zeros(d), np.ones(d), np.array(rec["params"]).reshape(-1, 1),
+                                       reltol=reltol, abstol=0.0, maxevals=30_000_000)
+    assert st[0] == 0 and abs(I[0] - rec["exact"]) <= 10 * reltol * abs(rec["exact"])
+
+
+@pytest.mark.parametrize("rec", GOLD["exact_sinxp"], ids=lambda r: f"p{r['p']}")
+def test_golden_quadgk_closed_forms(eng, rec):
+    I, E, ne, st = eng.quadgk_batch(F["sinxp"], np.array([-2.0]), np.array([5.0]), np.array([[rec["p"]]]), reltol=1e-10, abstol=1e-13)
+    assert st[0] == 0 and abs(I[0] - rec["exact"]) <= max(1e-13, 1e-10 * abs(rec["exact"]))
+
+
+# ------------------------------------------------------------------------------------- one large domain (region-parallel rounds)
+@pytest.mark.parametrize("family,dim,reltol", [("genz_gaussian", 2, 1e-9), ("genz_gaussian", 4, 1e-8), ("genz_oscillatory", 3, 1e-9),
+                                               ("genz_product_peak", 3, 1e-8), ("genz_corner_peak", 5, 1e-6), ("genz_c0", 3, 1e-5),
+                                               ("genz_gaussian", 6, 1e-6), ("genz_gaussian", 8, 1e-4)])
+def test_hcubature_single_matches_round_oracle(eng, O, family, dim, reltol):
+    """ib200_hcubature_single against the round-synchronous oracle (same rule, same threshold sequence): identical
+    refinement (same number of rule applications and rounds) and (I, E) equal to summation-order rounding; and against
+    the reference-order oracle (one box at a time) within the requested tolerance."""
+    par = genz_params(family, dim, 1, seed=77, scale=0.5)[:, 0]
+    lb, ub = np.zeros(dim), np.ones(dim)
+    I, E, s = eng.hcubature_single(F[family], dim, lb, ub, par, reltol=reltol, abstol=0.0, max_boxes=1 << 22)
+    Ir, Er, sr = O.hcubature_rounds(ORC_FAM[family], lb, ub, par, reltol=reltol, abstol=0.0, max_boxes=1 << 22)
+    assert s["status"] == sr["status"] == 0
+    assert s["rounds"] == sr["rounds"] and s["rule_applications"] == sr["rule_applications"] and s["boxes"] == sr["boxes"]
+    assert abs(I - Ir) <= 1e-12 * abs(Ir) and abs(E - Er) <= 1e-9 * Er + 1e-15 * abs(Ir)
+    if dim <= 5:
+        Ih, Eh, neh, sth = O.hcubature_batch(ORC_FAM[family], lb, ub, par.reshape(-1, 1), reltol=reltol, abstol=0.0)
+        assert abs(I - Ih[0]) <= reltol * abs(Ih[0]) and E <= reltol * abs(I) and Eh[0] <= reltol * abs(Ih[0])
+        assert 0.5 < s["nevals"] / neh[0] < 2.0
+    if family not in ("genz_c0",):
+        assert abs(I - genz_exact(family, par, dim)) <= 10 * reltol * abs(I)
+
+
+@pytest.mark.parametrize("rec", GOLD["exact_gaussian_two_infinite_axes"], ids=lambda r: f"{r['dim']}d")
+@pytest.mark.parametrize("tr", [0, 1, 2])
+def test_hcubature_single_infinite_axes(eng, O, rec, tr):
+    d, par = rec["dim"], np.array(rec["params"])
+    lb, ub = _gb(rec["lb"]), _gb(rec["ub"])
+    reltol = 1e-6
+    I, E, s = eng.hcubature_single(F["genz_gaussian"], d, lb, ub, par, reltol=reltol, abstol=0.0, max_boxes=1 << 22, transform=tr)
+    Ir, Er, sr = O.hcubature_rounds("gauss", lb, ub, par, tr=["if_inf", "tan", "cot"][tr], reltol=reltol, abstol=0.0, max_boxes=1 << 22)
+    assert s["status"] == 0 and abs(I - rec["exact"]) <= reltol * abs(rec["exact"]) and E <= reltol * abs(I)
+    assert abs(I - Ir) <= reltol * abs(Ir)
+    assert abs(s["rule_applications"] - sr["rule_applications"]) <= 0.02 * sr["rule_applications"]
+
+
+def test_hcubature_single_budget_and_store(eng):
+    par = genz_params("genz_gaussian", 4, 1, seed=3)[:, 0]
+    lb, ub = np.zeros(4), np.ones(4)
+    I, E, s = eng.hcubature_single(F["genz_gaussian"], 4, lb, ub, par, reltol=1e-13, abstol=0.0, max_boxes=20000)
+    assert s["status"] == 1 and 20000 <= s["rule_applications"] < 80000 and s["nevals"] == 57 * s["rule_applications"]
+    assert abs(I - genz_exact("genz_gaussian", par, 4)) <= 10 * E
+    # a store too small for the refinement: stops with the budget status, result still the sum over the stored boxes
+    I2, E2, s2 = eng.hcubature_single(F["genz_gaussian"], 4, lb, ub, par, reltol=1e-13, abstol=0.0, max_boxes=1 << 30, store_boxes=5000)
+    assert s2["status"] == 1 and s2["boxes"] <= 5000 and abs(I2 - I) <= 10 * (E + E2)
+    with pytest.raises(ib.IB200Error, match="dim"):
+        eng.hcubature_single(F["genz_gaussian"], 1, np.zeros(1), np.ones(1), np.array([1.0, 0.5]))
+
+
+def test_solve_interface_single_domain(eng):
+    """solve(IntegralProblem, HCubatureB200(single_domain=True)) routes one expensive integral to the region-parallel driver."""
+    par = genz_params("genz_gaussian", 5, 1, seed=9, scale=0.5)[:, 0]
+    prob = ib.IntegralProblem(ib.GenzGaussian(), (np.zeros(5), np.ones(5)), par)
+    sol = ib.solve(prob, ib.HCubatureB200(single_domain=True), engine=eng, reltol=1e-7, abstol=0.0, maxiters=10 ** 9)
+    assert sol.retcode == ib.ReturnCode.Success and isinstance(sol.u, float)
+    assert abs(sol.u - genz_exact("genz_gaussian", par, 5)) <= 1e-6 * abs(sol.u) and sol.resid <= 1e-7 * abs(sol.u)
+    assert sol.stats["status"] == 0 and sol.stats["rounds"] > 3

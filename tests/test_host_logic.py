@@ -1,0 +1,140 @@
+"""Host-side mirror of the reference's solve interface (integrals.jl_b200/interface.py) without a GPU: argument
+merging, the kwarg whitelist, automatic ChangeOfVariables, error behaviour, shapes handed to the engine.  A recording
+stub stands in for the engine, so no kernel runs here (GPU behaviour: tests/test_gpu_parity.py)."""
+import math
+
+import numpy as np
+import pytest
+
+import integrals_b200 as ib
+from integrals_b200 import interface
+
+
+class StubEngine:
+    def __init__(self):
+        self.calls = []
+
+    def _rec(self, name, *a, **k):
+        self.calls.append((name, a, k))
+
+    def quadgk_batch(self, fam, lb, ub, p, **k):
+        self._rec("quadgk", fam, lb, ub, p, **k); n = p.shape[1]
+        return np.zeros(n), np.zeros(n), np.zeros(n, np.int64), np.zeros(n, np.int32)
+
+    def hcubature_batch(self, fam, dim, lb, ub, p, **k):
+        self._rec("hcubature", fam, dim, lb, ub, p, **k); n = p.shape[1]
+        return np.zeros(n), np.zeros(n), np.zeros(n, np.int64), np.zeros(n, np.int32)
+
+    def hcubature_single(self, fam, dim, lb, ub, p, **k):
+        self._rec("hcubature_single", fam, dim, lb, ub, p, **k)
+        return 0.0, 0.0, dict(status=0)
+
+    def fixed_rule_tensor_batch(self, fam, dim, lb, ub, p, x, w, **k):
+        self._rec("tensor", fam, dim, lb, ub, p, x, w, **k); return np.zeros(p.shape[1])
+
+    def fixed_rule_nodes_batch(self, fam, dim, lb, ub, p, x, w, **k):
+        self._rec("nodes", fam, dim, lb, ub, p, x, w, **k); return np.zeros(p.shape[1])
+
+    def gauss_legendre_batch(self, fam, lb, ub, p, x, w, **k):
+        self._rec("gl", fam, lb, ub, p, x, w, **k); return np.zeros(p.shape[1])
+
+    def sampled(self, rule, y, inner, n, outer, h=0.0, x=None, out=None):
+        self._rec("sampled", rule, inner, n, outer, h=h, x=x); return np.zeros(max(inner * outer, 1))
+
+
+def test_kwarg_whitelist():      # src/Integrals.jl:142-179
+    prob = ib.IntegralProblem(ib.SinXP(), (-2.0, 5.0), 1.7)
+    with pytest.raises(ib.CommonKwargError, match="Unrecognized keyword arguments"):
+        ib.solve(prob, ib.QuadGKB200(), engine=StubEngine(), rtol=1e-3)
+    with pytest.raises(ib.CommonKwargError):
+        ib.solve(ib.IntegralProblem(ib.SinXP(), (-2.0, 5.0), 1.7, tol=1.0), ib.QuadGKB200(), engine=StubEngine())
+    with pytest.raises(ValueError, match="No integration algorithm"):      # src/common.jl:163-177
+        ib.solve(prob, None, engine=StubEngine())
+
+
+def test_defaults_and_kwarg_merge():   # defaults src/Integrals.jl:254-255; problem kwargs under solve kwargs, src/common.jl:87
+    e = StubEngine()
+    prob = ib.IntegralProblem(ib.SinXP(), (-2.0, 5.0), 1.7, reltol=1e-5)
+    sol = ib.solve(prob, ib.QuadGKB200(), engine=e)
+    k = e.calls[-1][2]
+    assert k["reltol"] == 1e-5 and k["abstol"] == 1e-8 and k["maxevals"] == ib.MAXEVALS_UNBOUNDED and k["transform"] == 0
+    assert isinstance(sol.u, float) and sol.retcode == ib.ReturnCode.Success and sol.chi is None
+    ib.solve(prob, ib.QuadGKB200(), engine=e, reltol=1e-9, maxiters=1000)
+    k = e.calls[-1][2]
+    assert k["reltol"] == 1e-9 and k["maxevals"] == 1000
+
+
+def test_automatic_change_of_variables_and_explicit():   # src/common.jl:97-103, src/algorithms_meta.jl:67-71
+    e = StubEngine()
+    prob = ib.IntegralProblem(ib.GenzGaussian(), ([-math.inf, 0.0], [math.inf, 1.0]), [1.0, 2.0, 0.0, 0.5])
+    cache = ib.init(prob, ib.HCubatureB200(), engine=e)
+    assert isinstance(cache.alg, ib.ChangeOfVariables) and cache.alg.fu2gv is ib.transformation_if_inf
+    cache.solve()
+    name, a, k = e.calls[-1]
+    assert name == "hcubature" and a[1] == 2 and k["transform"] == 0 and np.isinf(a[2][0])   # ORIGINAL bounds go to the device
+    ib.solve(prob, ib.ChangeOfVariables(ib.transformation_tan_inf, ib.HCubatureB200()), engine=e)
+    assert e.calls[-1][2]["transform"] == 1
+    ib.solve(prob, ib.ChangeOfVariables(ib.transformation_cot_inf, ib.HCubatureB200(initdiv=2)), engine=e)
+    assert e.calls[-1][2]["transform"] == 2 and e.calls[-1][2]["initdiv"] == 2
+    with pytest.raises(TypeError):
+        ib.ChangeOfVariables(lambda f, d: (f, d), ib.HCubatureB200())
+
+
+def test_dimension_errors():     # src/Integrals.jl:263-266; ext/IntegralsFastGaussQuadratureExt.jl:41-43
+    e = StubEngine()
+    prob2 = ib.IntegralProblem(ib.GenzGaussian(), (np.zeros(2), np.ones(2)), [1.0, 2.0, 0.0, 0.5])
+    with pytest.raises(ValueError, match="one-dimensional"):
+        ib.solve(prob2, ib.QuadGKB200(), engine=e)
+    with pytest.raises(ValueError, match="one-dimensional"):
+        ib.solve(prob2, ib.GaussLegendreB200(n=8), engine=e)
+    with pytest.raises(TypeError, match="registered"):
+        ib.IntegralProblem(lambda x, p: x, (0.0, 1.0), 1.0)
+    with pytest.raises(ValueError):
+        ib.QuadratureRuleB200(lambda n: None, n=0)             # src/algorithms.jl:293-295
+    with pytest.raises(ValueError, match="at least 1 subinterval"):
+        ib.GaussLegendreB200(n=4, subintervals=0)
+
+
+def test_batches_and_cache_reuse():   # caching interface: docs/src/tutorials/caching_interface.md:32-47
+    e = StubEngine()
+    P = np.asfortranarray(np.random.default_rng(0).random((1, 11)))
+    cache = ib.init(ib.IntegralProblem(ib.SinXP(), (-2.0, 5.0), P), ib.QuadGKB200(), engine=e, reltol=1e-10)
+    sol = cache.solve()
+    assert sol.u.shape == (11,) and sol.resid.shape == (11,)
+    cache.p = P[:, :3]                                          # cache.p = ...; solve!(cache)
+    assert cache.solve().u.shape == (3,)
+    cache.domain = (0.0, 1.0)
+    cache.solve()
+    assert float(e.calls[-1][1][1][0]) == 0.0 and float(e.calls[-1][1][2][0]) == 1.0
+
+
+def test_single_domain_routing():
+    e = StubEngine()
+    prob = ib.IntegralProblem(ib.GenzGaussian(), (np.zeros(8), np.ones(8)), np.ones(16))
+    ib.solve(prob, ib.HCubatureB200(single_domain=True), engine=e, reltol=1e-9, abstol=0.0, maxiters=401 * 1000)
+    name, a, k = e.calls[-1]
+    assert name == "hcubature_single" and k["max_boxes"] == 1000 and k["abstol"] == 0.0
+    with pytest.raises(ValueError, match="one problem"):
+        ib.solve(ib.IntegralProblem(ib.GenzGaussian(), (np.zeros(2), np.ones(2)), np.ones((4, 3))), ib.HCubatureB200(single_domain=True), engine=e)
+
+
+def test_sampled_problem_shapes_and_errors():   # src/common.jl:319-343, src/sampled.jl:135-168
+    e = StubEngine()
+    y = np.zeros((4, 10, 3))
+    sol = ib.solve(ib.SampledIntegralProblem(y, ib.Range(0.0, 1.0, 10), dim=1), ib.TrapezoidalB200(), engine=e)
+    name, a, k = e.calls[-1]
+    assert a[1:] == (4, 10, 3) and k["h"] == pytest.approx(1 / 9) and k["x"] is None and sol.u.shape == (4, 3)
+    sol = ib.solve(ib.SampledIntegralProblem(y, np.linspace(0, 1, 3) ** 2, dim=-1), ib.SimpsonsB200(), engine=e)
+    assert e.calls[-1][1][1:] == (40, 3, 1) and e.calls[-1][2]["x"] is not None and sol.u.shape == (4, 10) and sol.resid is None
+    with pytest.raises(ValueError, match="same length"):
+        ib.SampledIntegralProblem(y, np.zeros(7), dim=1)
+    with pytest.raises(ValueError, match="no keyword arguments"):
+        ib.solve(ib.SampledIntegralProblem(y, ib.Range(0, 1, 3)), ib.TrapezoidalB200(), engine=e, reltol=1e-3)
+    cache = ib.init(ib.SampledIntegralProblem(y, ib.Range(0, 1, 3)), ib.SimpsonsB200(), engine=e)
+    assert cache.isfresh is True                                 # init: isfresh = true, src/common.jl:330
+    cache.solve()
+    assert cache.isfresh is False
+    cache.x = ib.Range(0, 2, 3)                                  # src/common.jl:276-281: marks the weights stale
+    assert cache.isfresh is True
+    cache.solve()
+    assert cache.isfresh is False and e.calls[-1][2]["h"] == 1.0

@@ -1,0 +1,93 @@
+"""Multi-rank host logic on CPU: world_size-2 gloo groups.  The per-rank GPU solve is replaced by
+the CPU oracle (tests may call it), so what is under test is the partitioning, the result gather and the initial
+domain split of the single-domain driver -- not the kernels."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import integrals_b200 as ib
+from integrals_b200 import sharding
+
+
+def test_shard_range_partitions():
+    for n in (0, 1, 7, 8, 65536, 2 ** 18 + 3):
+        for w in (1, 2, 3, 8):
+            spans = [sharding.shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[r][1] == spans[r + 1][0] for r in range(w - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        sharding.shard_range(10, 2, 2)
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _oracle_solve(prob, alg, **kw):
+    """stand-in for interface.solve on a rank without a GPU: same problem block through the CPU oracle"""
+    import oracle as O
+    from integrals_b200 import interface
+    lb, ub = prob.domain
+    p = np.asarray(prob.p)
+    if isinstance(alg, ib.QuadGKB200):
+        I, E, ne, st = O.quadgk_batch("sinxp", lb, ub, p, reltol=kw.get("reltol", 1e-8), abstol=kw.get("abstol", 1e-8))
+    else:
+        I, E, ne, st = O.hcubature_batch("gauss", np.asarray(lb), np.asarray(ub), p, reltol=kw.get("reltol", 1e-8), abstol=kw.get("abstol", 1e-8))
+    return interface.IntegralSolution(I, E, prob, alg, interface.ReturnCode.Success, None, dict(nevals=ne, status=st))
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        p = (0.1 + 20.0 * np.arange(37) / 36).reshape(1, -1)
+        prob = ib.IntegralProblem(ib.SinXP(), (-2.0, 5.0), p)
+        sol = sharding.solve_sharded(prob, ib.QuadGKB200(), local_solve=_oracle_solve, reltol=1e-10)
+        par = np.asfortranarray(np.vstack([np.linspace(1, 3, 9), np.linspace(2, 1, 9), np.full(9, .3), np.full(9, .6)]))
+        prob2 = ib.IntegralProblem(ib.GenzGaussian(), (np.zeros(2), np.ones(2)), par)
+        sol2 = sharding.solve_sharded(prob2, ib.HCubatureB200(), local_solve=_oracle_solve, reltol=1e-7)
+        q.put((rank, sol.u, sol.resid, sol.stats["nevals"], sol2.u, sol2.stats["status"]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_solve_sharded_world2_gloo():
+    import torch.multiprocessing as mp
+    import oracle as O
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for pr in procs:
+        pr.join(60)
+        assert pr.exitcode == 0
+    p = (0.1 + 20.0 * np.arange(37) / 36).reshape(1, -1)
+    I, E, ne, st = O.quadgk_batch("sinxp", -2.0, 5.0, p, reltol=1e-10)
+    par = np.asfortranarray(np.vstack([np.linspace(1, 3, 9), np.linspace(2, 1, 9), np.full(9, .3), np.full(9, .6)]))
+    I2, *_ = O.hcubature_batch("gauss", np.zeros(2), np.ones(2), par, reltol=1e-7)
+    for rank, u, resid, nev, u2, st2 in res:            # every rank holds the full, ordered result
+        assert np.array_equal(u, I) and np.array_equal(resid, E) and np.array_equal(nev, ne)
+        assert np.array_equal(u2, I2) and np.all(st2 == 0)
+
+
+def test_single_domain_initial_split_is_rank_independent():
+    """the single-domain driver pre-bisects the domain m0 times and deals sub-boxes round-robin: the union over ranks is
+    the same box set whatever the world size, so the oracle with the same m0 is the checker for any number of GPUs."""
+    import oracle as O
+    par = np.array([2.0, 3.0, 1.5, 0.3, 0.6, 0.5])
+    base = O.hcubature_rounds("gauss", np.zeros(3), np.ones(3), par, reltol=1e-7, abstol=0.0, m0=0)
+    for world in (2, 4, 8):
+        m0 = 0
+        while (1 << m0) < 8 * world:
+            m0 += 1
+        I, E, s = O.hcubature_rounds("gauss", np.zeros(3), np.ones(3), par, reltol=1e-7, abstol=0.0, m0=m0)
+        assert s["status"] == 0 and abs(I - base[0]) <= 1e-7 * abs(I) and E <= 1e-7 * abs(I)
