@@ -35,7 +35,8 @@ import numpy as np  # noqa: E402
 METRIC = {"c4": ("fp64 integrals/sec (batched Genz-Malik HCubature, Genz suite 4-D)", "integrals/s"),
           "c1": ("fp64 integrals/sec (batched GK(7,15) QuadGK, sin(x*p) sweep)", "integrals/s"),
           "c3": ("fp64 integrals/sec (fixed tensor Gauss-Legendre n=64 3-D, Genz oscillatory)", "integrals/s"),
-          "c2": ("sampled GB/s (trapezoid + Simpson over 4096 x 1048576 fp64)", "GB/s")}
+          "c2": ("sampled GB/s (trapezoid + Simpson over 4096 x 1048576 fp64)", "GB/s"),
+          "c5": ("fp64 Genz-Malik rule applications/sec (one 8-D Genz Gaussian, region-parallel adaptive solve at a fixed box budget)", "boxes/s")}
 
 
 def parse():
@@ -142,6 +143,9 @@ def cpu_c2_sample(O, WL, n, threads):
     return 2 * (8.0 * m * n + 8 * m) / 1e9, dt        # GB
 
 
+# DRAM traffic per launch (bytes) of the dominant kernels at the default workload sizes, from `ncu --set full` (profiles/README.md)
+NCU_TRAFFIC = {"hp::hcub_pair_kernel<genz_product_peak,4,true>": 4.663001e12 + 1.771830e12}
+
 FAM_ORC = {"sinxp": "sinxp", "genz_oscillatory": "osc", "genz_product_peak": "prodpeak", "genz_corner_peak": "corner",
            "genz_gaussian": "gauss", "genz_c0": "c0", "genz_discontinuous": "discont"}
 
@@ -163,6 +167,13 @@ def cpu_leg(workload, scale=1.0):
         n = max(8, int(256 * cores * scale))
         units, dt = cpu_c3_sample(O, WL, n, cores)
         return units, dt, cores, f"first {n} problems (262,144 nodes each)"
+    if workload == "c5":
+        lb, ub, par, _ = WL.c5_problem()
+        nb = max(1 << 12, int((1 << 17) * scale))
+        t0 = time.perf_counter()
+        _, _, ne, _ = O.hcubature_batch("gauss", lb, ub, par.reshape(-1, 1), reltol=WL.C5["reltol"], abstol=WL.C5["abstol"], maxiters=nb * 401, nthreads=1)
+        return int(ne[0]) // 401, time.perf_counter() - t0, 1, (f"the same integral at a budget of {nb} boxes, reference order (one box at a time, "
+                                                                 "heap): a single HCubature solve is sequential, so 1 thread")
     n = 1 << 15
     units, dt = cpu_c2_sample(O, WL, n, cores)
     return units, dt, cores, f"4096 x {n} fp64 (1 GiB), trapezoid + Simpson"
@@ -184,7 +195,7 @@ def run_reference(args):
     v = tot_u / tot_t
     print(json.dumps({"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
                       "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True,
-                      "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                      "scaling": "strong" if args.workload == "c5" else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                       "config": workload_config(args.workload, args, sample=sample),
                       "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
                       "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
@@ -203,6 +214,9 @@ def workload_config(w, args, **extra):
     elif w == "c3":
         cfg = {"workload": "C3: tensor Gauss-Legendre n=64 in 3-D, 2^20 Genz oscillatory parameter sets",
                "nprob_per_gpu": args.nprob or WL.C3["nprob"]}
+    elif w == "c5":
+        cfg = {"workload": "C5: one 8-D Genz Gaussian, axes 1-2 on (-inf, inf), axes 3-8 on [0,1], reltol 1e-9, abstol 0, fixed box budget",
+               "log2_box_budget": args.nprob or 26, "parallelism": f"one domain region-partitioned x{args.gpus}, one NCCL all-gather of 2056 words per round"}
     else:
         cfg = {"workload": "C2: TrapezoidalRule + SimpsonsRule on 4096 x 1,048,576 fp64 along dim 2 (32 GiB, > L2)",
                "n_per_gpu": args.nprob or WL.C2["n"]}
@@ -233,6 +247,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     eng = ib.Engine(local)
+    if world > 1 and args.workload == "c5":
+        eng.comm_init_from_torch()                       # the library's own NCCL communicator (one rank per GPU)
     # one explicit stream for torch and the engine, so torch.cuda.Event brackets the engine's kernels
     # (the legacy default stream has handle 0, which ib200_set_stream reads as "the context's own stream")
     bench_stream = torch.cuda.Stream()
@@ -297,9 +313,15 @@ def main():
                 fl += n_ev * WL.hcubature_flops_per_eval(fam, d)
                 per[fam] = {"kernel_ms": kms[fam] / args.steps, "integrals_per_s": nper / (kms[fam] / args.steps * 1e-3),
                             "mean_evals": n_ev / nper, "frac_maxevals": float((dev[fam]["S"] == 1).double().mean().item())}
+            dom = max(WL.GENZ, key=lambda f: kms[f])
+            dom_ev = int(dev[dom]["N"].sum().item())
             return dict(units=6 * nper, launches=6, flops=fl, evals=ev, per_family=per,
                         h2d=6 * nper * 2 * d * 8 + 6 * 2 * d * 8, d2h=6 * nper * (8 + 8 + 8 + 4),
-                        kernel="hcub_kernel<FAM,4,true> (6 launches per step, one per family)")
+                        kernel="hp::hcub_pair_kernel<FAM,4,true> (6 launches per step, one per family)",
+                        dominant=dict(kernel=f"hp::hcub_pair_kernel<{dom},4,true>", ms=kms[dom] / args.steps, evals=dom_ev,
+                                      flops=dom_ev * WL.hcubature_flops_per_eval(dom, d),
+                                      share_of_step=kms[dom] / max(sum(kms.values()), 1e-9),
+                                      default_size=(nper == c["nprob_per_family"])))
         return step, e2e_step, finish
 
     ib_marker = {"genz_oscillatory": "GenzOscillatory", "genz_product_peak": "GenzProductPeak", "genz_corner_peak": "GenzCornerPeak",
@@ -383,7 +405,30 @@ def main():
                         kernel="strided_kernel<2,8> (2 launches per step: trapezoid, Simpson; + weights and finish kernels)")
         return step, e2e_step, finish
 
-    makers = {"c4": make_c4, "c1": make_c1, "c2": make_c2, "c3": make_c3}
+    def make_c5():
+        lb, ub, par, exact = WL.c5_problem()
+        budget = 1 << (args.nprob or 26)                # --nprob overrides log2 of the box budget
+        last = {}
+
+        def step(record=False):
+            I, E, st = eng.hcubature_single(F["genz_gaussian"], 8, lb, ub, par, reltol=WL.C5["reltol"], abstol=WL.C5["abstol"], max_boxes=budget)
+            last.update(I=I, E=E, **st)
+
+        def e2e_step():
+            sol = ib.solve(ib.IntegralProblem(ib.GenzGaussian(), (lb, ub), par), ib.HCubatureB200(single_domain=True), engine=eng,
+                           reltol=WL.C5["reltol"], abstol=WL.C5["abstol"], maxiters=budget * 401)
+            return float(sol.u)
+
+        def finish(kernel_ms_total):
+            ev = last["nevals"]
+            return dict(units=last["rule_applications"], global_units=True, launches=8 * last["rounds"] + 4, evals=ev,
+                        flops=ev * (WL.FAMILY_FLOPS["genz_gaussian"](8) + 2 * 20 + 6 * 4 + 2 * 8 + 1 + 30.0 / 401), h2d=8 * 32, d2h=8 * 8,
+                        kernel="hs::eval_kernel<genz_gaussian,8,false> (+ 7 bookkeeping kernels per refinement round)",
+                        result=dict(I=last["I"], E=last["E"], rel_E=last["E"] / abs(last["I"]), true_rel_err=abs(last["I"] - exact) / abs(exact),
+                                    rounds=last["rounds"], boxes_stored=last["boxes"], status=last["status"], box_budget=budget))
+        return step, e2e_step, finish
+
+    makers = {"c4": make_c4, "c1": make_c1, "c2": make_c2, "c3": make_c3, "c5": make_c5}
 
     def run(workload, steps, warmup, with_e2e=True, sample_clocks=False):
         step, e2e_step, finish = makers[workload]()
@@ -406,7 +451,8 @@ def main():
         ms = maxrank(e0.elapsed_time(e1))
         launches = eng.kernel_launches - l0
         info = finish(ms)
-        res = dict(ms_per_step=ms / steps, value=world * info["units"] / (ms / steps * 1e-3), launches=launches, info=info, clocks=clocks)
+        mult = 1 if info.get("global_units") else world      # c5: one domain over all ranks (units are already global)
+        res = dict(ms_per_step=ms / steps, value=mult * info["units"] / (ms / steps * 1e-3), launches=launches, info=info, clocks=clocks)
         if with_e2e:
             e2e_step()                                      # warm-up (pinned staging buffers, scratch growth)
             barrier()
@@ -415,7 +461,7 @@ def main():
                 e2e_step()
             torch.cuda.synchronize()
             dt = maxrank(time.perf_counter() - t0)
-            res["e2e_value"] = world * info.get("e2e_units", info["units"]) / (dt / steps)
+            res["e2e_value"] = mult * info.get("e2e_units", info["units"]) / (dt / steps)
         return res
 
     w = args.workload
@@ -430,19 +476,33 @@ def main():
         roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6.65 TB/s (of fallback)", "kernel": info["kernel"]}
     else:
-        ach = info["flops"] / (r["ms_per_step"] * 1e-3) / 1e12
-        roof = {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": None,
+        ach_step = info["flops"] / (r["ms_per_step"] * 1e-3) / 1e12
+        dom = info.get("dominant")
+        if dom:                         # the dominant kernel of the step: one launch, CUDA-event timed on the launching stream
+            ach, kname, kev, kms_ = dom["flops"] / (dom["ms"] * 1e-3) / 1e12, dom["kernel"], dom["evals"], dom["ms"]
+        else:
+            ach, kname, kev, kms_ = ach_step, info["kernel"], info["evals"], r["ms_per_step"]
+        # DRAM bytes of one launch of that kernel from the committed `ncu --set full` capture (profiles/); only valid at the default size
+        traffic = NCU_TRAFFIC.get(kname) if (dom is None or dom.get("default_size")) else None
+        roof = {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": traffic,
+                "traffic_source": "profiles/r01_hcub_pair_prod_c4_full_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum, one launch)" if traffic else None,
                 "peak_source": "DFMA-chain microbenchmark run live on this GPU (ib200_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
-                "flops_model": "SURVEY 8(d) nominal FP64 operations per integrand evaluation x evaluations (DESIGN.md)",
-                "evals_per_step": info["evals"], "gevals_per_s": info["evals"] / (r["ms_per_step"] * 1e-3) / 1e9, "kernel": info["kernel"]}
+                "flops_model": "SURVEY 8(d) nominal FP64 operations per integrand evaluation x evaluations (DESIGN.md); the kernels execute fewer "
+                               "(separable-term tables), so the executed-instruction FP64 pipe utilisation is the ncu figure in profiles/",
+                "kernel": kname, "kernel_ms": kms_, "evals_per_launch": kev, "gevals_per_s": kev / (kms_ * 1e-3) / 1e9,
+                "share_of_step": dom["share_of_step"] if dom else 1.0,
+                "whole_step": {"achieved": ach_step, "frac": ach_step / fp64_peak, "evals": info["evals"],
+                               "gevals_per_s": info["evals"] / (r["ms_per_step"] * 1e-3) / 1e9}}
     line = {"metric": metric, "value": r["value"], "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong" if w == "c5" else "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(w, args), "clocks": r["clocks"],
             "e2e": {"value": r["e2e_value"], "unit": unit, "h2d_bytes_per_step": info["h2d"], "d2h_bytes_per_step": info["d2h"],
                     "api": "integrals_b200.solve(IntegralProblem | SampledIntegralProblem, alg) with host numpy (pinned) inputs and host outputs"},
             "gpu_launches": r["launches"], "roofline": roof}
     if "per_family" in info:
         line["per_family"] = info["per_family"]
+    if "result" in info:
+        line["result"] = info["result"]
 
     if rank == 0 and world == 1 and not args.no_secondary:
         sec = {}
@@ -454,6 +514,8 @@ def main():
             try:
                 s = run(sw, 2, 3, with_e2e=False)
                 e = {"value": s["value"], "unit": METRIC[sw][1], "ms_per_step": s["ms_per_step"]}
+                if "result" in s["info"]:
+                    e["result"] = s["info"]["result"]
                 if sw == "c2":
                     e["frac_of_measured_hbm"] = s["value"] / 6535.7
                 else:
