@@ -329,8 +329,14 @@ template <int D> struct Family<IB200_FAM_GENZ_CORN, D> {
     }
 };
 
+// Separable form of the three exponential families: exp(sum_k t_k) = prod_k exp(t_k).  The rule kernels tabulate the
+// per-axis FACTORS exp(t_k) at the few abscissae a rule uses on each axis (7 for Genz-Malik, n for a tensor rule) and
+// form every point as a product of table entries: 7 D exponentials per Genz-Malik box instead of 2^D + 2 D^2 + 2 D + 1
+// (SURVEY 8(d) strength-reduction caveat: the integrand is still taken at every point of the reference's rule; the
+// value of a point differs from exp-of-the-sum by a few ulp).  eval() keeps the reference's form for the kernels that
+// evaluate points one by one (QuadGK, explicit node lists).
 template <int D> struct Family<IB200_FAM_GENZ_GAUSS, D> {
-    static constexpr int NQ = 2 * D; static constexpr bool kProd = false;
+    static constexpr int NQ = 2 * D; static constexpr bool kProd = true;
     __device__ static void prepare(const double *par, double (&q)[NQ]) {
 #pragma unroll
         for (int i = 0; i < 2 * D; i++) q[i] = par[i];
@@ -341,18 +347,16 @@ template <int D> struct Family<IB200_FAM_GENZ_GAUSS, D> {
         for (int i = 0; i < D; i++) { const double t = q[i] * (x[i] - q[D + i]); s = fma(t, t, s); }
         return exp_bf(-s);
     }
-    __device__ static double sep_init(const double *) { return 0.0; }
-    __device__ static double sep_term(int k, double x, const double *par) { const double t = par[k] * (x - par[D + k]); return t * t; }
-    __device__ static double sep_finish(double acc, const double *) { return exp_bf(-acc); }
+    __device__ static double sep_init(const double *) { return 1.0; }
+    __device__ static double sep_term(int k, double x, const double *par) { const double t = par[k] * (x - par[D + k]); return exp_bf(-(t * t)); }
+    __device__ static double sep_finish(double acc, const double *) { return acc; }
     template <int N> __device__ static void sep_finishN(const double (&acc)[N], const double *par, double (&out)[N]) {
-        double x[N];
-        _Pragma("unroll") for (int j = 0; j < N; j++) x[j] = -acc[j];
-        exp_bfN<N>(x, out);
+        finishN_default<Family<IB200_FAM_GENZ_GAUSS, D>, N>(acc, par, out);
     }
 };
 
 template <int D> struct Family<IB200_FAM_GENZ_C0, D> {
-    static constexpr int NQ = 2 * D; static constexpr bool kProd = false;
+    static constexpr int NQ = 2 * D; static constexpr bool kProd = true;
     __device__ static void prepare(const double *par, double (&q)[NQ]) {
 #pragma unroll
         for (int i = 0; i < 2 * D; i++) q[i] = par[i];
@@ -363,18 +367,16 @@ template <int D> struct Family<IB200_FAM_GENZ_C0, D> {
         for (int i = 0; i < D; i++) s = fma(q[i], fabs(x[i] - q[D + i]), s);
         return exp_bf(-s);
     }
-    __device__ static double sep_init(const double *) { return 0.0; }
-    __device__ static double sep_term(int k, double x, const double *par) { return par[k] * fabs(x - par[D + k]); }
-    __device__ static double sep_finish(double acc, const double *) { return exp_bf(-acc); }
+    __device__ static double sep_init(const double *) { return 1.0; }
+    __device__ static double sep_term(int k, double x, const double *par) { return exp_bf(-(par[k] * fabs(x - par[D + k]))); }
+    __device__ static double sep_finish(double acc, const double *) { return acc; }
     template <int N> __device__ static void sep_finishN(const double (&acc)[N], const double *par, double (&out)[N]) {
-        double x[N];
-        _Pragma("unroll") for (int j = 0; j < N; j++) x[j] = -acc[j];
-        exp_bfN<N>(x, out);
+        finishN_default<Family<IB200_FAM_GENZ_C0, D>, N>(acc, par, out);
     }
 };
 
 template <int D> struct Family<IB200_FAM_GENZ_DISC, D> {
-    static constexpr int NQ = 2 * D; static constexpr bool kProd = false;
+    static constexpr int NQ = 2 * D; static constexpr bool kProd = true;
     __device__ static void prepare(const double *par, double (&q)[NQ]) {
 #pragma unroll
         for (int i = 0; i < 2 * D; i++) q[i] = par[i];
@@ -387,13 +389,13 @@ template <int D> struct Family<IB200_FAM_GENZ_DISC, D> {
         for (int i = 0; i < D; i++) s = fma(q[i], x[i], s);
         return zero ? 0.0 : exp_bf(s);
     }
-    __device__ static double sep_init(const double *) { return 0.0; }
+    __device__ static double sep_init(const double *) { return 1.0; }
     __device__ static double sep_term(int k, double x, const double *par) {
-        return (k < 2 && x > par[D + k]) ? -INFINITY : par[k] * x;   // exp_bf(-inf) == 0
+        return (k < 2 && x > par[D + k]) ? 0.0 : exp_bf(par[k] * x);
     }
-    __device__ static double sep_finish(double acc, const double *) { return exp_bf(acc); }
+    __device__ static double sep_finish(double acc, const double *) { return acc; }
     template <int N> __device__ static void sep_finishN(const double (&acc)[N], const double *par, double (&out)[N]) {
-        exp_bfN<N>(acc, out);
+        finishN_default<Family<IB200_FAM_GENZ_DISC, D>, N>(acc, par, out);
     }
 };
 

@@ -45,6 +45,9 @@ tensor_kernel(const double *__restrict__ params, int nparam, int64_t nprob,
     double *par = sm + 2 * (size_t)D * n;
     double *red = par + nparam;
     double *pscale = red + kBlock / 32;
+    // oscillatory family only: {cos, sin} of the innermost axis' phase term, for the angle-addition inner loop
+    double2 *cs = reinterpret_cast<double2 *>(pscale + IB200_MAX_DIM + ((nparam + kBlock / 32 + IB200_MAX_DIM) & 1));
+    constexpr bool kAngle = (FAM == IB200_FAM_GENZ_OSC);
 
     int64_t outer = 1;
 #pragma unroll
@@ -68,7 +71,9 @@ tensor_kernel(const double *__restrict__ params, int nparam, int64_t nprob,
             const double t = sc * x1d[j] + sh;
             double u, jac;
             ib::t2ujac(tr, t, m, u, jac);
-            tab[idx] = make_double2(F::sep_term(k, u, par), w1d[j] * jac);
+            const double term = F::sep_term(k, u, par);
+            tab[idx] = make_double2(term, w1d[j] * jac);
+            if (kAngle && k == D - 1) { double sn, cn; sincos(term, &sn, &cn); cs[j] = make_double2(cn, sn); }
             if (j == 0) pscale[k] = sc;
         }
         __syncthreads();
@@ -89,6 +94,20 @@ tensor_kernel(const double *__restrict__ params, int nparam, int64_t nprob,
             const int k0 = c * chunk, k1 = min(n, k0 + chunk);
             double s0 = 0.0, s1 = 0.0;
             int k = k0;
+            if constexpr (kAngle) {
+                // cos(phi + theta_j) = cos(phi) cos(theta_j) - sin(phi) sin(theta_j): phi (the outer axes' phase) costs one
+                // sincos per item, every node of the innermost axis one multiply and one FMA (angle addition
+                // from per-axis tables; the integrand is still formed at every node of the rule)
+                double qs, qc;
+                sincos(acc, &qs, &qc);
+                for (; k + 1 < k1; k += 2) {
+                    const double2 c0 = cs[k], c1 = cs[k + 1];
+                    const double f0 = fma(qc, c0.x, -(qs * c0.y)), f1 = fma(qc, c1.x, -(qs * c1.y));
+                    s0 = fma(tin[k].y, f0, s0);
+                    s1 = fma(tin[k + 1].y, f1, s1);
+                }
+                if (k < k1) { const double2 c0 = cs[k]; s0 = fma(tin[k].y, fma(qc, c0.x, -(qs * c0.y)), s0); k++; }
+            }
             for (; k + 1 < k1; k += 2) {
                 const double2 e0 = tin[k], e1 = tin[k + 1];
                 const double a0 = F::kProd ? acc * e0.x : acc + e0.x;
@@ -231,7 +250,7 @@ extern "C" int32_t ib200_fixed_rule_tensor_batch(ib200_ctx *ctx, int32_t family,
     DevIn<double> dx, dw;
     if ((rc = dx.init(ctx, x1d, (size_t)n1d, SL_IN3))) return rc;
     if ((rc = dw.init(ctx, w1d, (size_t)n1d, SL_IN4))) return rc;
-    const size_t smem = (2 * (size_t)dim * n1d + nparam + kBlock / 32 + IB200_MAX_DIM) * sizeof(double);
+    const size_t smem = (2 * (size_t)dim * n1d + nparam + kBlock / 32 + IB200_MAX_DIM + 1 + 2 * (size_t)n1d) * sizeof(double);
     IB_REQUIRE(ctx, smem <= ctx->smem_optin, "ib200_fixed_rule_tensor_batch: 1-D rule too long for shared memory");
     int64_t blocks = nprob;
     const int64_t maxb = (int64_t)ctx->sm_count * 4;
