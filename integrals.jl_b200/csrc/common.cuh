@@ -30,6 +30,7 @@ struct ib200_ctx {
     struct Buf { void *p = nullptr; size_t cap = 0; } scratch[SL_COUNT];
     // options
     int64_t opt_adaptive_warps_per_sm = 0;   // 0 = kernel default
+    int64_t opt_hcub_lpt = 1;                // pair-mode HCubature: pilot pass + longest-expected-first ordering
     double opt_single_round_fraction = 0.5;  // hcub_single.cu: share of the stored boxes one round may bisect
     int64_t opt_hcub_capacity = 0;           // boxes per in-flight problem, 0 = derive from maxevals
     int64_t opt_sampled_slabs = 0;           // 0 = auto

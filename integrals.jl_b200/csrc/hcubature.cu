@@ -19,6 +19,30 @@ template <> int32_t launch<4>(ib200_ctx *, int, bool, Params &);
 template <> int32_t launch<5>(ib200_ctx *, int, bool, Params &);
 }
 
+namespace hp {
+__global__ void lpt_hist_kernel(const double *I, const double *E, const int32_t *st, int64_t n, double rtol, double atol, unsigned *hist) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        if (st[i] == IB200_ST_MAXEVALS) atomicAdd(&hist[lpt_bucket(I[i], E[i], rtol, atol)], 1u);
+}
+__global__ void lpt_scan_kernel(unsigned *hist, unsigned *cursor, unsigned long long *norder, unsigned long long *counter) {
+    __shared__ unsigned s[kLptBuckets];
+    for (int b = threadIdx.x; b < kLptBuckets; b += blockDim.x) s[b] = hist[b];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned run = 0;
+        for (int b = 0; b < kLptBuckets; b++) { const unsigned c = s[b]; s[b] = run; run += c; }
+        *norder = run; *counter = 0ULL;
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < kLptBuckets; b += blockDim.x) cursor[b] = s[b];
+}
+__global__ void lpt_scatter_kernel(const double *I, const double *E, const int32_t *st, int64_t n, double rtol, double atol,
+                                   unsigned *cursor, unsigned *order) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        if (st[i] == IB200_ST_MAXEVALS) order[atomicAdd(&cursor[lpt_bucket(I[i], E[i], rtol, atol)], 1u)] = (unsigned)i;
+}
+}  // namespace hp
+
 extern "C" int32_t ib200_hcubature_batch(ib200_ctx *ctx, int32_t family, int32_t dim, int32_t transform,
                                          const double *lb, const double *ub, int32_t bpp,
                                          const double *params, int32_t nparam, int64_t nprob,
@@ -87,14 +111,41 @@ extern "C" int32_t ib200_hcubature_batch(ib200_ctx *ctx, int32_t family, int32_t
         q.rtol = reltol; q.atol = abstol; q.maxevals = maxevals; q.initdiv = initdiv;
         q.cap = (int)((cap + 1023) / 1024 * 1024);
         q.keys = q.l1 = q.rec = nullptr; q.l1off = nullptr; q.counter = counter;
+        q.order = nullptr; q.norder = nullptr;
         q.out_I = oI.d; q.out_E = oE.d; q.out_nevals = oN.d; q.out_status = oS.d;
+        auto run = [&](hp::Params &pp) -> int32_t {
+            switch (dim) {
+            case 2: return hp::launch<2>(ctx, family, allfin, pp);
+            case 3: return hp::launch<3>(ctx, family, allfin, pp);
+            case 4: return hp::launch<4>(ctx, family, allfin, pp);
+            default: return hp::launch<5>(ctx, family, allfin, pp);
+            }
+        };
         ib200_time_begin(ctx);
-        switch (dim) {
-        case 2: rc = hp::launch<2>(ctx, family, allfin, q); break;
-        case 3: rc = hp::launch<3>(ctx, family, allfin, q); break;
-        case 4: rc = hp::launch<4>(ctx, family, allfin, q); break;
-        default: rc = hp::launch<5>(ctx, family, allfin, q); break;
+        // longest-expected-first: pilot pass + counting sort (hcubature_pair.cuh); needs I, E and status of every problem
+        const int64_t pilot_evals = init_boxes * np + 2 * np * 24;
+        const bool lpt = ctx->opt_hcub_lpt != 0 && nprob >= 8192 && nprob < ((int64_t)1 << 32) && maxevals > 16 * pilot_evals &&
+                         oE.d && oS.d;
+        if (lpt) {
+            hp::Params pilot = q;
+            pilot.maxevals = pilot_evals;
+            pilot.cap = (int)((init_boxes + 24 + 1 + 1023) / 1024 * 1024);
+            if ((rc = run(pilot))) return rc;
+            unsigned *lw = (unsigned *)ctx->get(SL_WORK3, ((size_t)nprob + 2 * hp::kLptBuckets + 4) * sizeof(unsigned));
+            if (!lw) return ib200_fail(ctx, IB200_ERR_OOM, "ib200_hcubature_batch: scratch allocation failed");
+            unsigned *hist = lw, *cursor = lw + hp::kLptBuckets;
+            unsigned long long *norder = reinterpret_cast<unsigned long long *>(lw + 2 * hp::kLptBuckets);
+            unsigned *order = lw + 2 * hp::kLptBuckets + 4;
+            IB_CUDA(ctx, cudaMemsetAsync(hist, 0, hp::kLptBuckets * sizeof(unsigned), ctx->stream));
+            const int gb = ctx->sm_count * 4;
+            hp::lpt_hist_kernel<<<gb, 256, 0, ctx->stream>>>(oI.d, oE.d, oS.d, nprob, reltol, abstol, hist);
+            hp::lpt_scan_kernel<<<1, 1024, 0, ctx->stream>>>(hist, cursor, norder, counter);
+            hp::lpt_scatter_kernel<<<gb, 256, 0, ctx->stream>>>(oI.d, oE.d, oS.d, nprob, reltol, abstol, cursor, order);
+            ctx->launches += 3;
+            IB_LAUNCH_CHECK(ctx);
+            q.order = order; q.norder = norder;
         }
+        rc = run(q);
         if (rc) return rc;
         ib200_time_end(ctx);
         if ((rc = oI.finish(ctx)) || (rc = oE.finish(ctx)) || (rc = oN.finish(ctx)) || (rc = oS.finish(ctx))) return rc;

@@ -40,6 +40,8 @@ struct Params {
     unsigned char *l1off;       // [pairs][cap/32]       position (0..31) of that maximum in its group
     double *rec;                // [pairs][cap][2D+2]    a[D], b[D], I, split axis
     unsigned long long *counter;
+    const unsigned *order;      // problem indices in processing order (NULL: 0, 1, 2, ...), see lpt_* below
+    const unsigned long long *norder;   // device-side length of `order` (NULL: nprob)
     double *out_I, *out_E; int64_t *out_nevals; int32_t *out_status;
 };
 
@@ -233,6 +235,35 @@ __device__ __forceinline__ Cand scan_half_excl(const double *arr, int base, int 
     }
     return r;
 }
+// The two 32-entry groups on the selected path are needed only AFTER the rule evaluation (runner-up scans).  They are
+// staged into this lane's shared-memory slot with cp.async while the rule runs, so the scans read shared memory instead
+// of waiting on L2/DRAM (ncu, profiles/r01_hcub_pair_prod_c4_*: 31 % of the stall samples sat on these loads).
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// stage this lane's half (16 doubles) of the group at arr[base ..] (n valid entries overall) into stage[0..16)
+__device__ __forceinline__ void stage_half(double *stage, const double *arr, int base, int n, int half) {
+    const int e0 = base + half * 16;
+#pragma unroll
+    for (int t = 0; t < 8; t++) if (e0 + 2 * t < n) cp_async16(stage + 2 * t, arr + e0 + 2 * t);
+}
+// scan_half_excl on staged data
+__device__ __forceinline__ Cand scan_staged_excl(const double *stage, int base, int n, int half, int excl) {
+    Cand r; r.k = 0ULL; r.idx = NONE;
+    const int e0 = base + half * 16;
+    const double2 *p = reinterpret_cast<const double2 *>(stage);
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+        const int ia = half * 16 + 2 * t, ib_ = ia + 1;
+        const double2 v = p[t];
+        if (e0 + 2 * t < n && ia != excl) { const unsigned long long k = dk(v.x); if (r.idx == NONE || k > r.k) { r.k = k; r.idx = ia; } }
+        if (e0 + 2 * t + 1 < n && ib_ != excl) { const unsigned long long k = dk(v.y); if (r.idx == NONE || k > r.k) { r.k = k; r.idx = ib_; } }
+    }
+    return r;
+}
 // combine the two halves of a pair; identical result in both lanes
 __device__ __forceinline__ Cand combine_pair(unsigned pm, const Cand &mine) {
     Cand o;
@@ -263,6 +294,8 @@ hcub_pair_kernel(const Params p) {
     int *tops = reinterpret_cast<int *>(topk + n2max);
     double *pc = topk + n2max + (n2max + 1) / 2;
     double *par = pc, *lbs = pc + NPAR, *aux = lbs + D;
+    double *stage = sm + (size_t)kPairs * row_doubles(n2max, PCD) + (size_t)threadIdx.x * 32;          // [keys half | l1 half]
+    unsigned char *stage_off = reinterpret_cast<unsigned char *>(sm + (size_t)kPairs * row_doubles(n2max, PCD) + (size_t)kBlock * 32) + pib * 32;
 
     double *keys = p.keys + (size_t)gpair * p.cap;
     double *l1 = p.l1 + (size_t)gpair * (p.cap / kFan);
@@ -273,6 +306,7 @@ hcub_pair_kernel(const Params p) {
     const double atol = p.atol;
     if (rtol == 0.0 && atol == 0.0) rtol = 1.4901161193847656e-08;   // sqrt(eps), HCubature default
 
+    const int64_t nwork = p.norder ? (int64_t)*p.norder : p.nprob;
     // pair state (identical in both lanes)
     int state = ST_NEED, nbox = 0, status = 0;
     int64_t prob = -1, nev = 0, q = 0, qtotal = 0;
@@ -330,9 +364,9 @@ hcub_pair_kernel(const Params p) {
             unsigned long long pidx = 0;
             if (half == 0) pidx = atomicAdd(p.counter, 1ULL);
             pidx = __shfl_sync(pm, pidx, lane & ~1);
-            if ((int64_t)pidx >= p.nprob) state = ST_EXHAUSTED;
+            if ((int64_t)pidx >= nwork) state = ST_EXHAUSTED;
             else {
-                prob = (int64_t)pidx;
+                prob = p.order ? (int64_t)p.order[pidx] : (int64_t)pidx;
                 __syncwarp(pm);
                 for (int t = half; t < NPAR; t += 2) par[t] = p.params[prob * p.nparam + t];
                 for (int k = half; k < D; k += 2) {
@@ -397,12 +431,13 @@ hcub_pair_kernel(const Params p) {
             double r[RECW];
 #pragma unroll
             for (int t = 0; t < D + 1; t++) { const double2 v = __ldcg(src + t); r[2 * t] = v.x; r[2 * t + 1] = v.y; }
-            // bring the two groups on the selected path into L2 for the runner-up scans after the evaluation
+            // start staging the two groups on the selected path (+ the block's 32 position bytes) for the runner-up scans
             {
                 const int i = slot >> 5, j = slot >> 10;
-                prefetch_l2(keys + (i << 5) + half * 16);
-                prefetch_l2(l1 + (j << 5) + half * 16);
-                if (half == 0) prefetch_l2(l1off + (j << 5));
+                stage_half(stage, keys, i << 5, nbox, half);
+                stage_half(stage + 16, l1, j << 5, (nbox + 31) >> 5, half);
+                cp_async16(stage_off + half * 16, l1off + (j << 5) + half * 16);
+                cp_async_commit();
             }
             if (nbox & 31) { app_k = dk(__ldcg(l1 + (nbox >> 5))); app_off = __ldcg(l1off + (nbox >> 5)); }
             Ibox = r[2 * D];
@@ -457,10 +492,12 @@ hcub_pair_kernel(const Params p) {
                 const int s2 = nbox;
                 const int i = slot >> 5, j = slot >> 10, i2 = s2 >> 5, j2 = s2 >> 10;
                 // runner-ups of the two groups on the selected path (data prefetched into L2 before the evaluation)
-                Cand ru0 = combine_pair(pm, scan_half_excl(keys, i << 5, nbox, half, slot & 31));
-                Cand ru1 = combine_pair(pm, scan_half_excl(l1, j << 5, (nbox + 31) >> 5, half, i & 31));
+                cp_async_wait_all();
+                __syncwarp(pm);                                                           // the position bytes are read across the pair
+                Cand ru0 = combine_pair(pm, scan_staged_excl(stage, i << 5, nbox, half, slot & 31));
+                Cand ru1 = combine_pair(pm, scan_staged_excl(stage + 16, j << 5, (nbox + 31) >> 5, half, i & 31));
                 if (ru0.idx != NONE) ru0.idx += i << 5;                                   // -> slot
-                if (ru1.idx != NONE) ru1.idx = (((j << 5) + ru1.idx) << 5) + __ldcg(l1off + (j << 5) + ru1.idx);   // -> slot of that group's maximum
+                if (ru1.idx != NONE) ru1.idx = (((j << 5) + ru1.idx) << 5) + stage_off[ru1.idx];   // -> slot of that group's maximum
                 write_box(half == 0 ? slot : s2);
                 // group i: runner-up, child 0 at `slot`, child 1 if it lands in the same group
                 Cand g0; g0.k = dk(E1); g0.idx = slot;
@@ -503,6 +540,25 @@ hcub_pair_kernel(const Params p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Longest-expected-first ordering.  Problem costs in one batch differ by 10^3 (BASELINE config 4: 10^4 .. 4*10^6
+// evaluations) and a problem is a strictly sequential chain of refinement steps, so a late-starting expensive problem
+// leaves the rest of the GPU idle (measured: ~0.4 s of a 1.4 s launch).  A pilot pass gives every problem a few
+// refinement steps; the ones that do not converge are re-run from scratch in order of decreasing E / tol after the
+// pilot (rank correlation with the final cost 0.6-0.9 on the Genz families), found by a counting sort on the top
+// 16 bits of that ratio.  Results are unaffected: every problem is refined exactly as before, only its start time moves.
+// ------------------------------------------------------------------------------------------------
+constexpr int kLptBuckets = 4096;
+__device__ __forceinline__ int lpt_bucket(double I, double E, double rtol, double atol) {
+    const double tol = fmax(rtol * fabs(I), atol);
+    const double ratio = E / tol;                                     // > 1 for an unconverged problem; NaN/inf -> first bucket
+    if (!(ratio < 1.0e300)) return 0;
+    long long b = (__double_as_longlong(fmax(ratio, 1.0)) >> 47) - (1023LL << 5);   // 32 buckets per octave
+    b = b < 0 ? 0 : (b > kLptBuckets - 1 ? kLptBuckets - 1 : b);
+    return kLptBuckets - 1 - (int)b;                                  // descending ratio
+}
+// (lpt_hist_kernel / lpt_scan_kernel / lpt_scatter_kernel: hcubature.cu)
+
 // bytes of box pool per pair
 inline size_t pool_bytes_per_pair(int D, int cap) {
     return (size_t)cap * (8 + 8 * (2 * (size_t)D + 2)) + (size_t)(cap / kFan) * 9;
@@ -518,7 +574,7 @@ int32_t launch_impl(ib200_ctx *ctx, int family, bool allfin, Params &p) {
         constexpr int FAM = decltype(famc)::value;
         if constexpr (ib::fam_dim_ok(FAM, D) && D >= 2) {
             auto go = [&](auto kern) -> int32_t {
-                const size_t smem = (size_t)kPairs * row_doubles(p.cap >> 10, pc_doubles<FAM, D>()) * sizeof(double);
+                const size_t smem = ((size_t)kPairs * row_doubles(p.cap >> 10, pc_doubles<FAM, D>()) + (size_t)kBlock * 32 + (size_t)kPairs * 4) * sizeof(double);
                 if (smem > ctx->smem_optin) return ib200_fail(ctx, IB200_ERR_INVALID, "ib200_hcubature_batch: box capacity too large for shared memory");
                 IB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 int occ = 0;
