@@ -12,7 +12,9 @@
 #define IB200_VERSION 100
 
 enum ScratchSlot { SL_IN0 = 0, SL_IN1, SL_IN2, SL_IN3, SL_IN4, SL_IN5, SL_OUT0, SL_OUT1, SL_OUT2, SL_OUT3,
-                   SL_WORK0, SL_WORK1, SL_WORK2, SL_WORK3, SL_WORK4, SL_WORK5, SL_COUNT };
+                   SL_WORK0, SL_WORK1, SL_WORK2, SL_WORK3, SL_WORK4, SL_WORK5,
+                   SL_STORE0, SL_STORE1,     // hcub_single.cu box store: exported to the peer ranks (CUDA IPC), never shared with other calls
+                   SL_COUNT };
 
 struct ib200_ctx {
     int device = 0;
@@ -27,6 +29,7 @@ struct ib200_ctx {
     std::string err;
     void *comm = nullptr;                    // ncclComm_t of the multi-GPU single-domain solve (hcub_single.cu)
     int comm_rank = 0, comm_world = 1;
+    void *single_peers = nullptr;            // hcub_single.cu: CUDA IPC mappings of the peers' box stores
     struct Buf { void *p = nullptr; size_t cap = 0; } scratch[SL_COUNT];
     // options
     int64_t opt_adaptive_warps_per_sm = 0;   // 0 = kernel default

@@ -33,9 +33,17 @@
 // Everything a round needs (counts, sums, threshold, stop flag) lives in a device-side state block;
 // kernels read their extents from it and return immediately once the stop flag is set.  The host
 // enqueues rounds back to back and looks at the stop flag once every kRoundsPerCheck rounds, so there is
-// no host round trip per refinement iteration.  Multi-GPU: the unit cube of the transformed domain is
-// pre-split into >= 8*world equal sub-boxes dealt round-robin; every rank refines its own boxes against
-// the GLOBAL threshold; the only collective is the per-round all-gather of 8 + 2048 words.
+// no host round trip per refinement iteration.
+//
+// Multi-GPU (one process per GPU): the box store is REPLICATED, the evaluation is PARTITIONED.  Every rank holds the
+// whole store and runs the (cheap, HBM-streaming) histogram / decide / split bookkeeping redundantly on identical
+// data, so the stores stay bit-identical without any box migration.  The expensive part -- the rule on the round's
+// new boxes -- is dealt out box by box (todo index mod world), and the evaluation kernel writes each result (integral,
+// error, split axis: 24 bytes) straight into EVERY rank's store through peer pointers over NVLink (CUDA IPC mappings
+// of the peers' stores): compute and exchange are one kernel, the transfer overlaps the arithmetic box by box.  The
+// round's only collective is an 8-double NCCL all-gather of the partial sums, which doubles as the barrier that makes
+// the peer stores visible before the bookkeeping reads them.  The load is balanced by construction (every box costs
+// the same number of evaluations), whatever the shape of the integrand.
 //
 // Selection differs from the reference (all boxes above a threshold instead of the single worst), so
 // the evaluation count differs; parity is on (I, E): |I - I_ref| within the requested tolerance and
@@ -43,6 +51,7 @@
 // this round scheme on the CPU and refines identically).
 #include "hcubature_impl.cuh"
 #include <dlfcn.h>
+#include <vector>
 
 namespace hs {
 
@@ -50,7 +59,8 @@ constexpr int kBlock = 256;
 constexpr int kWarps = kBlock / 32;
 constexpr int kRoundsPerCheck = 4;
 constexpr int kBins = 2048;                   // one bin per binary exponent of a double
-constexpr int kXchg = 8 + kBins;              // 8-byte words exchanged per rank per round
+constexpr int kXchg = 8;                      // doubles exchanged per rank per round
+constexpr int kMaxWorld = 8;
 constexpr int kFin = 1024;                    // threads of the single-block bookkeeping kernels
 
 struct State {
@@ -78,7 +88,9 @@ struct Params {
     unsigned long long *hist;  // [kBins]    local exponent histogram of err[0..nbox)
     double *sendbuf, *recvbuf;
     State *st;
-    int rank, world, m0;     // m0: initial bisection depth (2^m0 sub-boxes over all ranks)
+    int rank, world;
+    double *rec_peer[kMaxWorld];   // every rank's box store (own entry = rec), CUDA IPC mappings
+    double *err_peer[kMaxWorld];
     int grid;
 };
 
@@ -112,35 +124,22 @@ struct Nccl {
 static Nccl g_nccl;
 
 // ---- kernels ---------------------------------------------------------------------------------------
-// initial boxes: the transformed domain bisected m0 times (axis = level mod D); sub-box q belongs to rank q % world
+// the initial box: the whole transformed domain (identical on every rank)
 template <int D, bool ALLFIN>
 __global__ void init_kernel(Params p) {
     State *st = p.st;
-    const long long nsub = 1LL << p.m0;
-    long long mine = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        for (long long q = p.rank; q < nsub; q += p.world) {
-            double *r = p.rec + mine * (2 * D + 2);
-            double a[D], b[D];
+        double *r = p.rec;
 #pragma unroll
-            for (int k = 0; k < D; k++) {
-                if (ALLFIN) { a[k] = -1.0; b[k] = 1.0; }
-                else { ib::AxisMap m; ib::make_axis(p.lb[k], p.ub[k], m); a[k] = m.tlo; b[k] = m.thi; }
-            }
-            for (int lev = 0; lev < p.m0; lev++) {           // bit `lev` of q picks the half on axis lev % D
-                const int k = lev % D;
-                const double w = (b[k] - a[k]) * 0.5;
-#pragma unroll
-                for (int kk = 0; kk < D; kk++) if (kk == k) { if ((q >> lev) & 1) a[kk] = a[kk] + w; else b[kk] = b[kk] - w; }
-            }
-#pragma unroll
-            for (int k = 0; k < D; k++) { r[k] = a[k]; r[D + k] = b[k]; }
-            r[2 * D] = 0.0; r[2 * D + 1] = 0.0;
-            p.err[mine] = 0.0;
-            p.todo[mine] = (unsigned)mine;
-            mine++;
+        for (int k = 0; k < D; k++) {
+            double a = -1.0, b = 1.0;
+            if (!ALLFIN) { ib::AxisMap m; ib::make_axis(p.lb[k], p.ub[k], m); a = m.tlo; b = m.thi; }
+            r[k] = a; r[D + k] = b;
         }
-        st->nbox = mine; st->ntodo = mine; st->nsplit = 0; st->napplied = 0;
+        r[2 * D] = 0.0; r[2 * D + 1] = 0.0;
+        p.err[0] = 0.0;
+        p.todo[0] = 0u;
+        st->nbox = 1; st->ntodo = 1; st->nsplit = 0; st->napplied = 0;
         st->I = 0.0; st->E = 0.0; st->I_g = 0.0; st->E_g = 0.0; st->gapplied = 0.0;
         st->bound = 0.0; st->theta = 0.0; st->done = 0; st->status = 0; st->full = 0; st->round = 0;
     }
@@ -220,7 +219,7 @@ eval_kernel(Params p) {
     double sumI = 0.0, sumE = 0.0, maxE = 0.0;           // lane 0 accumulates this warp's boxes in todo order
     const long long ntodo = st->ntodo;
     const long long nwarps = (long long)gridDim.x * kWarps;
-    for (long long t = (long long)blockIdx.x * kWarps + wib; t < ntodo; t += nwarps) {
+    for (long long t = ((long long)blockIdx.x * kWarps + wib) * p.world + p.rank; t < ntodo; t += nwarps * p.world) {
         const unsigned slot = p.todo[t];
         double *r = p.rec + (size_t)slot * RECW;
         __syncwarp();
@@ -282,8 +281,11 @@ eval_kernel(Params p) {
                 if (delta > deltaf) { kd = k; maxdd = dd; hkd = hh[k]; }
                 else if (fabs(delta) <= deltaf && hh[k] > hkd) { kd = k; hkd = hh[k]; }
             }
-            r[2 * D] = Iv; r[2 * D + 1] = (double)kd;
-            p.err[slot] = Er;
+            for (int q = 0; q < p.world; q++) {                  // the result goes into every rank's store (NVLink peer stores)
+                double *rq = p.rec_peer[q] + (size_t)slot * RECW;
+                rq[2 * D] = Iv; rq[2 * D + 1] = (double)kd;
+                p.err_peer[q][slot] = Er;
+            }
             sumI += Iv; sumE += Er; maxE = fmax(maxE, Er);       // fmax drops NaN: non-finite E is caught through sumE
         }
     }
@@ -329,7 +331,7 @@ __device__ __forceinline__ void fin_reduce3(double &v0, double &v1, double &v2, 
     }
 }
 
-// fold the block partials into the state and fill the exchange buffer (one block of kFin threads)
+// fold the block partials of this rank's share of the round into the exchange buffer (one block of kFin threads)
 __global__ void __launch_bounds__(kFin)
 eval_finish_kernel(Params p) {
     State *st = p.st;
@@ -338,15 +340,11 @@ eval_finish_kernel(Params p) {
     double sI = 0.0, sE = 0.0, mE = 0.0;
     for (int b = threadIdx.x; b < p.grid; b += kFin) { sI += p.partial[4 * b]; sE += p.partial[4 * b + 1]; mE = fmax(mE, p.partial[4 * b + 2]); }
     fin_reduce3(sI, sE, mE, sh);
-    double *s = p.sendbuf;
     if (threadIdx.x == 0) {
-        st->I += sI; st->E += sE;
-        st->napplied += st->ntodo;
-        s[0] = st->I; s[1] = st->E; s[2] = mE; s[3] = (double)st->napplied; s[4] = (double)st->full; s[5] = (double)st->nbox; s[6] = 0.0; s[7] = 0.0;
+        double *s = p.sendbuf;
+        s[0] = sI; s[1] = sE; s[2] = mE; s[3] = 0.0; s[4] = 0.0; s[5] = 0.0; s[6] = 0.0; s[7] = 0.0;
+        if (p.world == 1) { for (int k = 0; k < kXchg; k++) p.recvbuf[k] = s[k]; }
     }
-    for (int b = threadIdx.x; b < kBins; b += kFin) { s[8 + b] = __longlong_as_double((long long)p.hist[b]); p.hist[b] = 0ull; }
-    __syncthreads();
-    if (p.world == 1) { for (int k = threadIdx.x; k < kXchg; k += kFin) p.recvbuf[k] = s[k]; }
 }
 
 // global reduction in rank order + HCubature's stopping test + next threshold (one block of kFin threads)
@@ -355,18 +353,17 @@ decide_kernel(Params p) {
     State *st = p.st;
     if (st->done) return;
     __shared__ double s_cnt[kBins];
-    for (int b = threadIdx.x; b < kBins; b += kFin) {
-        unsigned long long c = 0ull;
-        for (int r = 0; r < p.world; r++) c += (unsigned long long)__double_as_longlong(p.recvbuf[(size_t)r * kXchg + 8 + b]);
-        s_cnt[b] = (double)c;
-    }
+    for (int b = threadIdx.x; b < kBins; b += kFin) { s_cnt[b] = (double)p.hist[b]; p.hist[b] = 0ull; }   // replicated store: local == global
     __syncthreads();
     if (threadIdx.x != 0) return;
-    double I = 0.0, E = 0.0, mx = 0.0, ap = 0.0, full = 0.0, nb = 0.0;
-    for (int r = 0; r < p.world; r++) {
+    double dI = 0.0, dE = 0.0, mx = 0.0;
+    for (int r = 0; r < p.world; r++) {                      // rank order: the same sums on every rank
         const double *v = p.recvbuf + (size_t)r * kXchg;
-        I += v[0]; E += v[1]; mx = fmax(mx, v[2]); ap += v[3]; full = fmax(full, v[4]); nb += v[5];
+        dI += v[0]; dE += v[1]; mx = fmax(mx, v[2]);
     }
+    st->I += dI; st->E += dE;
+    st->napplied += st->ntodo;
+    const double I = st->I, E = st->E, ap = (double)st->napplied, full = (double)st->full, nb = (double)st->nbox;
     st->I_g = I; st->E_g = E; st->gapplied = ap;
     st->round++;
     st->ntodo = 0;
@@ -549,28 +546,86 @@ resum_kernel(Params p) {
     if (threadIdx.x == 0) { double *o = p.partial + (size_t)blockIdx.x * 4; o[0] = sI; o[1] = sE; }
 }
 __global__ void __launch_bounds__(kFin)
-resum_finish_kernel(Params p) {
+resum_finish_kernel(Params p, double *out /* I, E, applied, boxes, rounds, status */) {
     State *st = p.st;
     __shared__ double sh[96];
     double sI = 0.0, sE = 0.0, d = 0.0;
     for (int b = threadIdx.x; b < p.grid; b += kFin) { sI += p.partial[4 * b]; sE += p.partial[4 * b + 1]; }
     fin_reduce3(sI, sE, d, sh);
-    double *s = p.sendbuf;
     if (threadIdx.x == 0) {
-        st->I = sI; st->E = sE;
-        s[0] = sI; s[1] = sE; s[2] = 0.0; s[3] = (double)st->napplied; s[4] = (double)st->full; s[5] = (double)st->nbox; s[6] = 0.0; s[7] = 0.0;
+        out[0] = sI; out[1] = sE; out[2] = (double)st->napplied; out[3] = (double)st->nbox; out[4] = (double)st->round; out[5] = (double)st->status;
     }
-    __syncthreads();
-    if (p.world == 1) { for (int k = threadIdx.x; k < 8; k += kFin) p.recvbuf[k] = s[k]; }
-}
-__global__ void final_kernel(Params p, double *out /* I, E, applied, boxes, rounds, status */) {
-    if (threadIdx.x != 0) return;
-    double I = 0.0, E = 0.0, ap = 0.0, nb = 0.0;
-    for (int r = 0; r < p.world; r++) { const double *v = p.recvbuf + (size_t)r * kXchg; I += v[0]; E += v[1]; ap += v[3]; nb += v[5]; }
-    out[0] = I; out[1] = E; out[2] = ap; out[3] = nb; out[4] = (double)p.st->round; out[5] = (double)p.st->status;
 }
 
 }  // namespace hs
+
+// ---- peer mappings of the replicated stores -----------------------------------------------------------------
+// Every rank exports its two store allocations (scratch slots SL_STORE0/1, used by nothing else) with CUDA IPC; the
+// handles travel in one NCCL all-gather.  Opening a mapping costs tens of milliseconds, so mappings are kept across
+// solves.  Exported memory must not be freed while a peer maps it: before a solve the ranks exchange "I have to
+// re-allocate my store" flags, and if any is set EVERY rank closes its mappings (and says so in a second all-gather)
+// before anyone re-allocates.  ib200_comm_destroy is collective for the same reason.
+struct hs_peer_maps {
+    void *ptr[2][hs::kMaxWorld];
+    bool valid;
+    hs_peer_maps() { memset(this, 0, sizeof(*this)); }
+};
+static void hs_close_peers(ib200_ctx *ctx) {
+    hs_peer_maps *pc = static_cast<hs_peer_maps *>(ctx->single_peers);
+    if (!pc) return;
+    for (int k = 0; k < 2; k++) for (int q = 0; q < hs::kMaxWorld; q++) if (pc->ptr[k][q]) { cudaIpcCloseMemHandle(pc->ptr[k][q]); pc->ptr[k][q] = nullptr; }
+    pc->valid = false;
+}
+// all-gather one double per rank through the exchange buffer and bring the result to the host (synchronises the stream)
+static int32_t hs_gather1(ib200_ctx *ctx, double *xb, int world, double mine, std::vector<double> &all) {
+    using namespace hs;
+    all.assign((size_t)world, 0.0);
+    IB_CUDA(ctx, cudaMemcpyAsync(xb, &mine, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    const int r = g_nccl.AllGather(xb, xb + 1, 1, /*ncclDouble*/ 8, (ncclComm_t)ctx->comm, ctx->stream);
+    if (r != 0) return ib200_fail(ctx, IB200_ERR_NCCL, std::string("ncclAllGather: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"));
+    IB_CUDA(ctx, cudaMemcpyAsync(all.data(), xb + 1, sizeof(double) * (size_t)world, cudaMemcpyDeviceToHost, ctx->stream));
+    IB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return IB200_OK;
+}
+static int32_t hs_map_peers(ib200_ctx *ctx, hs::Params &p) {
+    using namespace hs;
+    hs_peer_maps *pc = static_cast<hs_peer_maps *>(ctx->single_peers);
+    if (!pc->valid) {
+        struct Msg { cudaIpcMemHandle_t h[2]; };
+        static_assert(sizeof(Msg) % 8 == 0, "message is sent as doubles");
+        Msg mine; memset(&mine, 0, sizeof(mine));
+        IB_CUDA(ctx, cudaIpcGetMemHandle(&mine.h[0], p.rec));
+        IB_CUDA(ctx, cudaIpcGetMemHandle(&mine.h[1], p.err));
+        char *dbuf = (char *)ctx->get(SL_IN4, sizeof(Msg) * (size_t)(p.world + 1));
+        if (!dbuf) return ib200_fail(ctx, IB200_ERR_OOM, "ib200_hcubature_single: scratch allocation failed");
+        std::vector<Msg> all((size_t)p.world);
+        IB_CUDA(ctx, cudaMemcpyAsync(dbuf, &mine, sizeof(Msg), cudaMemcpyHostToDevice, ctx->stream));
+        const int r = g_nccl.AllGather(dbuf, dbuf + sizeof(Msg), sizeof(Msg) / 8, /*ncclDouble*/ 8, (ncclComm_t)ctx->comm, ctx->stream);
+        if (r != 0) return ib200_fail(ctx, IB200_ERR_NCCL, std::string("ncclAllGather: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"));
+        IB_CUDA(ctx, cudaMemcpyAsync(all.data(), dbuf + sizeof(Msg), sizeof(Msg) * (size_t)p.world, cudaMemcpyDeviceToHost, ctx->stream));
+        IB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int q = 0; q < p.world; q++) {
+            if (q == p.rank) continue;
+            for (int k = 0; k < 2; k++) {
+                void *ptr = nullptr;
+                const cudaError_t e = cudaIpcOpenMemHandle(&ptr, all[q].h[k], cudaIpcMemLazyEnablePeerAccess);
+                if (e != cudaSuccess) {
+                    cudaGetLastError();
+                    return ib200_fail(ctx, IB200_ERR_CUDA, std::string("ib200_hcubature_single: cudaIpcOpenMemHandle (peer store of rank ") +
+                                                              std::to_string(q) + "): " + cudaGetErrorString(e));
+                }
+                pc->ptr[k][q] = ptr;
+            }
+        }
+        pc->valid = true;
+    }
+    for (int q = 0; q < p.world; q++) {
+        if (q == p.rank) continue;
+        p.rec_peer[q] = static_cast<double *>(pc->ptr[0][q]);
+        p.err_peer[q] = static_cast<double *>(pc->ptr[1][q]);
+    }
+    return IB200_OK;
+}
 
 // ---- communicator management -------------------------------------------------------------------------
 extern "C" int32_t ib200_comm_unique_id(void *id128) {
@@ -590,7 +645,7 @@ extern "C" int32_t ib200_comm_init(ib200_ctx *ctx, int32_t nranks, int32_t rank,
     std::string why;
     if (!hs::g_nccl.load(why)) return ib200_fail(ctx, IB200_ERR_NCCL, "ib200_comm_init: " + why);
     IB_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (ctx->comm) { hs::g_nccl.CommDestroy((hs::ncclComm_t)ctx->comm); ctx->comm = nullptr; }
+    if (ctx->comm) { ib200_comm_destroy(ctx); }
     hs::ncclUniqueId id;
     memcpy(&id, id128, 128);
     hs::ncclComm_t comm = nullptr;
@@ -602,6 +657,18 @@ extern "C" int32_t ib200_comm_init(ib200_ctx *ctx, int32_t nranks, int32_t rank,
 
 extern "C" int32_t ib200_comm_destroy(ib200_ctx *ctx) {
     IB_REQUIRE(ctx, ctx != nullptr, "ib200_comm_destroy: ctx is NULL");
+    if (ctx->single_peers) {
+        hs_peer_maps *pc = static_cast<hs_peer_maps *>(ctx->single_peers);
+        const bool had = pc->valid;
+        hs_close_peers(ctx);
+        delete pc; ctx->single_peers = nullptr;
+        // collective: nobody frees an exported store before every rank has closed its mappings
+        double *xb = (double *)ctx->scratch[SL_WORK1].p;
+        if (had && ctx->comm && hs::g_nccl.h && xb && ctx->scratch[SL_WORK1].cap >= (size_t)(ctx->comm_world + 1) * sizeof(double)) {
+            std::vector<double> all;
+            hs_gather1(ctx, xb, ctx->comm_world, 1.0, all);
+        }
+    }
     if (ctx->comm && hs::g_nccl.h) hs::g_nccl.CommDestroy((hs::ncclComm_t)ctx->comm);
     ctx->comm = nullptr; ctx->comm_rank = 0; ctx->comm_world = 1;
     return IB200_OK;
@@ -627,17 +694,26 @@ static int32_t hs_run(ib200_ctx *ctx, hs::Params &p, double *out6_host) {
         }
         return IB200_OK;
     };
+    auto barrier = [&]() -> int32_t {
+        if (p.world > 1) {
+            const int r = g_nccl.AllGather(p.sendbuf + kXchg, p.recvbuf + (size_t)kXchg * p.world, 1, /*ncclDouble*/ 8, (ncclComm_t)ctx->comm, s);
+            if (r != 0) return ib200_fail(ctx, IB200_ERR_NCCL, std::string("ncclAllGather: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"));
+        }
+        return IB200_OK;
+    };
+    if ((rc = barrier())) { cudaFreeHost(done_h); return rc; }       // every rank's init_kernel has run before results arrive in its store
     for (long long iter = 0; iter < (1LL << 40); iter++) {
         for (int r = 0; r < kRoundsPerCheck; r++) {
-            eval_kernel<FAM, D, ALLFIN><<<grid, kBlock, 0, s>>>(p);
-            hist_kernel<<<grid, kBlock, 0, s>>>(p);
+            eval_kernel<FAM, D, ALLFIN><<<grid, kBlock, 0, s>>>(p);          // + peer stores of the results
             eval_finish_kernel<<<1, kFin, 0, s>>>(p);
-            if ((rc = exchange())) { cudaFreeHost(done_h); return rc; }
+            if ((rc = exchange())) { cudaFreeHost(done_h); return rc; }      // partial sums; barrier: every rank's results have landed
+            hist_kernel<<<grid, kBlock, 0, s>>>(p);
             decide_kernel<<<1, kFin, 0, s>>>(p);
             count_kernel<D><<<grid, kBlock, 0, s>>>(p);
             scan_kernel<<<1, kFin, 0, s>>>(p);
             scatter_kernel<D><<<grid, kBlock, 0, s>>>(p);
             split_finish_kernel<<<1, 32, 0, s>>>(p);
+            if ((rc = barrier())) { cudaFreeHost(done_h); return rc; }       // nobody writes results into a store that is still being split
             ctx->launches += 8;
         }
         if (cudaGetLastError() != cudaSuccess) { cudaFreeHost(done_h); return ib200_fail(ctx, IB200_ERR_CUDA, "ib200_hcubature_single: kernel launch failed"); }
@@ -651,13 +727,11 @@ static int32_t hs_run(ib200_ctx *ctx, hs::Params &p, double *out6_host) {
         if (iter * kRoundsPerCheck > 400000) { cudaFreeHost(done_h); return ib200_fail(ctx, IB200_ERR_CUDA, "ib200_hcubature_single: refinement did not terminate (internal error)"); }
     }
     cudaFreeHost(done_h);
-    resum_kernel<D><<<grid, kBlock, 0, s>>>(p);
-    resum_finish_kernel<<<1, kFin, 0, s>>>(p);
-    if ((rc = exchange())) return rc;
     double *out6 = (double *)ctx->get(SL_OUT0, 8 * sizeof(double));
     if (!out6) return ib200_fail(ctx, IB200_ERR_OOM, "scratch allocation failed");
-    final_kernel<<<1, 32, 0, s>>>(p, out6);
-    ctx->launches += 3;
+    resum_kernel<D><<<grid, kBlock, 0, s>>>(p);                              // replicated store: the closing sum is local
+    resum_finish_kernel<<<1, kFin, 0, s>>>(p, out6);
+    ctx->launches += 2;
     IB_LAUNCH_CHECK(ctx);
     IB_CUDA(ctx, cudaMemcpyAsync(out6_host, out6, 6 * sizeof(double), cudaMemcpyDeviceToHost, s));
     IB_CUDA(ctx, cudaStreamSynchronize(s));
@@ -689,35 +763,58 @@ extern "C" int32_t ib200_hcubature_single(ib200_ctx *ctx, int32_t family, int32_
     hs::Params p;
     p.par = dpar.d; p.lb = dlb.d; p.ub = dub.d; p.tr = transform; p.rtol = reltol; p.atol = abstol; p.max_boxes = max_boxes;
     p.rank = ctx->comm ? ctx->comm_rank : 0; p.world = ctx->comm ? ctx->comm_world : 1;
-    p.m0 = 0;
     p.frac = ctx->opt_single_round_fraction;
-    if (p.world > 1) { while ((1LL << p.m0) < 8LL * p.world) p.m0++; }
+    IB_REQUIRE(ctx, p.world <= hs::kMaxWorld, "ib200_hcubature_single: at most 8 ranks (one box of GPUs)");
     p.grid = ctx->sm_count * 4;
     if (p.grid > hs::kFin) p.grid = hs::kFin;              // scan_kernel scans the block counts in one block
     // box store: as many boxes as asked for, else what the budget can create, bounded by 70% of the free HBM
     const size_t per_box = (size_t)(2 * dim + 2) * 8 + 8 + 4;
     size_t fr = 0, tot = 0;
     IB_CUDA(ctx, cudaMemGetInfo(&fr, &tot));
-    size_t held = ctx->scratch[SL_WORK0].cap + ctx->scratch[SL_WORK2].cap + ctx->scratch[SL_WORK3].cap;
+    size_t held = ctx->scratch[SL_STORE0].cap + ctx->scratch[SL_STORE1].cap + ctx->scratch[SL_WORK3].cap;
     long long cap_mem = (long long)(((double)(fr + held) * 0.7) / (double)per_box);
     // default store: what the budget can create on this rank (with 2x slack for imbalance), at most 2^26 boxes
     // (~10 GB in 8-D) unless the caller asks for more through store_boxes
-    long long want = store_boxes > 0 ? store_boxes : (max_boxes < (1LL << 40) ? max_boxes / p.world * 2 + (1LL << p.m0) + 1024 : (1LL << 26));
-    if (store_boxes <= 0 && want > (1LL << 26)) want = 1LL << 26;
+    long long want = store_boxes > 0 ? store_boxes : (max_boxes < (1LL << 40) ? max_boxes + 1024 : (1LL << 26));
+    if (store_boxes <= 0 && want > (1LL << 28)) want = 1LL << 28;
     if (want > cap_mem) want = cap_mem;
     if (want > 4000000000LL) want = 4000000000LL;         // 32-bit todo indices
-    if (want < (1LL << p.m0) + 16) want = (1LL << p.m0) + 16;
+    if (want < 16) want = 16;
     p.cap = want;
-    p.rec = (double *)ctx->get(SL_WORK0, (size_t)p.cap * (2 * dim + 2) * sizeof(double));
-    p.err = (double *)ctx->get(SL_WORK2, (size_t)p.cap * sizeof(double));
+    double *xb = (double *)ctx->get(SL_WORK1, (size_t)((hs::kXchg + 1) * (p.world + 1) + hs::kBins) * sizeof(double) + sizeof(hs::State) + 64);
+    if (!xb) return ib200_fail(ctx, IB200_ERR_OOM, "ib200_hcubature_single: scratch allocation failed");
+    const size_t need_rec = (size_t)p.cap * (2 * dim + 2) * sizeof(double), need_err = (size_t)p.cap * sizeof(double);
+    if (p.world > 1) {
+        if (!ctx->single_peers) ctx->single_peers = new hs_peer_maps();
+        hs_peer_maps *pc = static_cast<hs_peer_maps *>(ctx->single_peers);
+        // flag = store capacity, negated if this rank has to re-allocate an exported buffer
+        const bool regrow = need_rec > ctx->scratch[SL_STORE0].cap || need_err > ctx->scratch[SL_STORE1].cap;
+        std::vector<double> all;
+        if ((rc = hs_gather1(ctx, xb, p.world, regrow ? -(double)p.cap : (double)p.cap, all))) return rc;
+        bool any = false;
+        for (int q = 0; q < p.world; q++) {
+            if (fabs(all[q]) != (double)p.cap)
+                return ib200_fail(ctx, IB200_ERR_INVALID, "ib200_hcubature_single: the ranks disagree on the store capacity (pass the same store_boxes everywhere)");
+            any = any || all[q] < 0;
+        }
+        if (any && pc->valid) {
+            hs_close_peers(ctx);
+            if ((rc = hs_gather1(ctx, xb, p.world, 1.0, all))) return rc;          // every rank has closed its mappings
+        }
+    }
+    p.rec = (double *)ctx->get(SL_STORE0, need_rec);
+    p.err = (double *)ctx->get(SL_STORE1, need_err);
     p.todo = (unsigned *)ctx->get(SL_WORK3, (size_t)p.cap * sizeof(unsigned));
     p.partial = (double *)ctx->get(SL_WORK4, (size_t)p.grid * 4 * sizeof(double));
     p.bcount = (long long *)ctx->get(SL_WORK5, (size_t)(p.grid + 1) * sizeof(long long));
-    double *xb = (double *)ctx->get(SL_WORK1, (size_t)(hs::kXchg * (p.world + 1) + hs::kBins) * sizeof(double) + sizeof(hs::State) + 64);
     if (!p.rec || !p.err || !p.todo || !p.partial || !p.bcount || !xb)
         return ib200_fail(ctx, IB200_ERR_OOM, "ib200_hcubature_single: box store allocation failed (pass a smaller store_boxes)");
-    p.sendbuf = xb; p.recvbuf = xb + hs::kXchg; p.hist = reinterpret_cast<unsigned long long *>(xb + hs::kXchg * (p.world + 1));
-    p.st = reinterpret_cast<hs::State *>(xb + hs::kXchg * (p.world + 1) + hs::kBins);
+    // [send: 8 + 1 | recv: 8 * world + world | hist | state]
+    p.sendbuf = xb; p.recvbuf = xb + hs::kXchg + 1;
+    p.hist = reinterpret_cast<unsigned long long *>(xb + (hs::kXchg + 1) * (p.world + 1));
+    p.st = reinterpret_cast<hs::State *>(xb + (hs::kXchg + 1) * (p.world + 1) + hs::kBins);
+    for (int q = 0; q < hs::kMaxWorld; q++) { p.rec_peer[q] = p.rec; p.err_peer[q] = p.err; }
+    if (p.world > 1 && (rc = hs_map_peers(ctx, p))) return rc;
 
     double res[6] = {0, 0, 0, 0, 0, 0};
     rc = IB200_ERR_UNSUPPORTED;

@@ -79,15 +79,12 @@ def test_solve_sharded_world2_gloo():
         assert np.array_equal(u2, I2) and np.all(st2 == 0)
 
 
-def test_single_domain_initial_split_is_rank_independent():
-    """the single-domain driver pre-bisects the domain m0 times and deals sub-boxes round-robin: the union over ranks is
-    the same box set whatever the world size, so the oracle with the same m0 is the checker for any number of GPUs."""
+def test_round_oracle_presplit_variants_agree():
+    """orc_hcubature_rounds with a pre-bisected domain (m0 > 0) reaches the same integral within the tolerance as the
+    single-box start the driver uses on any number of ranks (replicated store: the refinement is rank-count independent)."""
     import oracle as O
     par = np.array([2.0, 3.0, 1.5, 0.3, 0.6, 0.5])
     base = O.hcubature_rounds("gauss", np.zeros(3), np.ones(3), par, reltol=1e-7, abstol=0.0, m0=0)
-    for world in (2, 4, 8):
-        m0 = 0
-        while (1 << m0) < 8 * world:
-            m0 += 1
+    for m0 in (4, 5, 6):
         I, E, s = O.hcubature_rounds("gauss", np.zeros(3), np.ones(3), par, reltol=1e-7, abstol=0.0, m0=m0)
         assert s["status"] == 0 and abs(I - base[0]) <= 1e-7 * abs(I) and E <= 1e-7 * abs(I)
