@@ -393,3 +393,19 @@ def test_solve_interface_single_domain(eng):
     assert sol.retcode == ib.ReturnCode.Success and isinstance(sol.u, float)
     assert abs(sol.u - genz_exact("genz_gaussian", par, 5)) <= 1e-6 * abs(sol.u) and sol.resid <= 1e-7 * abs(sol.u)
     assert sol.stats["status"] == 0 and sol.stats["rounds"] > 3
+
+
+def test_hcubature_single_two_gpus():
+    """one domain on 2 GPUs (replicated store, peer stores, NCCL all-gather per round): scripts/single_domain_mgpu.py under
+    torchrun checks identical refinement against the round oracle; skipped on a 1-GPU box"""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29531", os.path.join(root, "scripts", "single_domain_mgpu.py")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    out = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    assert out["world"] == 2 and all(c["ok"] and c["identical_refinement"] for c in out["cases"])
