@@ -95,6 +95,12 @@ int32_t     ib200_set_option(ib200_ctx *ctx, const char *key, int64_t value);
       ("No points to integrate", sampled.jl:55). */
 int32_t ib200_sampled(ib200_ctx *ctx, int32_t rule, const double *y, int64_t inner, int64_t n,
                       int64_t outer, double h, const double *x, double *out);
+/* Float32 samples on a Float32 grid ("Float32 type preservation", test/interface_tests.jl:524-539): weights and the
+   products w[i]*y[i] in float as in the reference, accumulation in double, result rounded to float.
+   Complex samples need no entry point of their own: the weights are real, so a Complex{Float64} array
+   [inner, n, outer] is the Float64 array [2*inner, n, outer] (test/interface_tests.jl:501-509). */
+int32_t ib200_sampled_f32(ib200_ctx *ctx, int32_t rule, const float *y, int64_t inner, int64_t n,
+                          int64_t outer, float h, const float *x, float *out);
 
 /* -- fixed rules: replaces evalrule(f,p,lb,ub,nodes,weights) src/quadrules.jl:1-19 under the
       automatic ChangeOfVariables (src/Integrals.jl:192-224), for a batch of problems.

@@ -23,7 +23,7 @@ ERR_NAMES = {-1: "IB200_ERR_INVALID", -2: "IB200_ERR_CUDA", -3: "IB200_ERR_OOM",
 # every symbol include/integrals_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = ["ib200_version", "ib200_create", "ib200_destroy", "ib200_last_error", "ib200_set_stream",
            "ib200_synchronize", "ib200_kernel_launches", "ib200_family_nparam", "ib200_last_kernel_ms",
-           "ib200_set_option", "ib200_sampled", "ib200_fixed_rule_tensor_batch", "ib200_fixed_rule_nodes_batch",
+           "ib200_set_option", "ib200_sampled", "ib200_sampled_f32", "ib200_fixed_rule_tensor_batch", "ib200_fixed_rule_nodes_batch",
            "ib200_gauss_legendre_batch", "ib200_quadgk_batch", "ib200_hcubature_batch", "ib200_measure_fp64_peak",
            "ib200_hcubature_single", "ib200_comm_unique_id", "ib200_comm_init", "ib200_comm_destroy"]
 
@@ -69,6 +69,7 @@ def load_library():
     L.ib200_gauss_legendre_batch.restype = i32
     L.ib200_quadgk_batch.argtypes = [vp, i32, i32, vp, vp, i32, vp, i32, i64, dp, dp, i64, vp, vp, vp, vp]
     L.ib200_quadgk_batch.restype = i32
+    L.ib200_sampled_f32.argtypes = [vp, i32, vp, i64, i64, i64, C.c_float, vp, vp]; L.ib200_sampled_f32.restype = i32
     L.ib200_hcubature_batch.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp, i32, i64, dp, dp, i64, i32, vp, vp, vp, vp]
     L.ib200_hcubature_batch.restype = i32
     L.ib200_hcubature_single.argtypes = [vp, i32, i32, i32, vp, vp, vp, i32, dp, dp, i64, i64, C.POINTER(dp), C.POINTER(dp), vp]
@@ -184,6 +185,18 @@ class Engine:
         return params, nparam, nprob, bpp
 
     # ---- sampled -----------------------------------------------------------------------------
+    def sampled_f32(self, rule, y, inner, n, outer, h=0.0, x=None, out=None):
+        """Float32 samples on a Float32 grid (ib200_sampled_f32); host arrays column-major float32 or torch float32 tensors."""
+        if not hasattr(y, "data_ptr"):
+            y = np.asarray(y, dtype=np.float32, order="F")
+        if x is not None and not hasattr(x, "data_ptr"):
+            x = np.ascontiguousarray(x, dtype=np.float32)
+        out = self._out(out, max(inner * outer, 1), np.float32)
+        yp, _k1 = _ptr(y); xp, _k2 = _ptr(x); op, _k3 = _ptr(out)
+        self._check(self.L.ib200_sampled_f32(self.h, RULE_IDS[rule] if isinstance(rule, str) else rule, yp, inner, n, outer,
+                                             float(h), xp, op))
+        return out
+
     def sampled(self, rule, y, inner, n, outer, h=0.0, x=None, out=None):
         y = _f64(y); x = _f64(x)
         out = self._out(out, max(inner * outer, 1))

@@ -19,11 +19,13 @@ namespace {
 
 constexpr int kThreads = 256;
 
-__global__ void weights_kernel(int rule, int64_t n, double h, const double *__restrict__ x, double *__restrict__ w) {
+// T = element type of the grid: the weights are formed in T arithmetic, as the reference's weight types do
+template <typename T>
+__global__ void weights_kernel(int rule, int64_t n, T h, const T *__restrict__ x, T *__restrict__ w) {
     const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // 0-based; formulas below use 1-based i
     if (i0 >= n) return;
     const int64_t i = i0 + 1;
-    double r;
+    T r;
     if (!x) {
         if (rule == IB200_RULE_TRAPEZOID) {                     // trapezoidal.jl:16-20
             r = (i == 1 || i == n) ? h / 2 : h;
@@ -42,7 +44,7 @@ __global__ void weights_kernel(int rule, int64_t n, double h, const double *__re
 #define B(k) x[(k)]
 #define E(k) x[n - 1 - (k)]
         const int64_t j = i - 1;
-        auto cube = [](double v) { return v * v * v; };
+        auto cube = [](T v) { return v * v * v; };
         if (i == 1) {
             r = (B(2) - B(0)) / 6 * (2 - (B(2) - B(1)) / (B(1) - B(0)));
         } else if ((n & 1) && i == n) {
@@ -77,13 +79,29 @@ __device__ __forceinline__ double ldg_stream1(const double *p) {
     asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
     return v;
 }
+__device__ __forceinline__ float2 ldg_stream2(const float *p) {
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ldg_stream1(const float *p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+template <typename T> struct Vec2;
+template <> struct Vec2<double> { using type = double2; };
+template <> struct Vec2<float> { using type = float2; };
 
 // inner >= 2.  Block = TX x TY threads (TX*TY == kThreads): tx walks the contiguous output axis in
 // VEC-wide pieces, ty strides the columns of this slab.  grid = (row tiles, slabs, outer).
-template <int VEC, int UNROLL>
+// T = double: the BASELINE path.  T = float (Float32 problems, test/interface_tests.jl:524-539): weights and products in
+// float like the reference, accumulation in double (the reference's sequential Float32 sum is less accurate, not more).
+template <typename T, int VEC, int UNROLL>
 __global__ void __launch_bounds__(kThreads)
-strided_kernel(const double *__restrict__ y, const double *__restrict__ w, double *__restrict__ partial,
+strided_kernel(const T *__restrict__ y, const T *__restrict__ w, double *__restrict__ partial,
                int64_t inner, int64_t n, int tx_count, int64_t cols_per_slab) {
+    using T2 = typename Vec2<T>::type;
     extern __shared__ double sm[];
     const int ty_count = kThreads / tx_count;
     const int tx = threadIdx.x % tx_count, ty = threadIdx.x / tx_count;
@@ -91,7 +109,7 @@ strided_kernel(const double *__restrict__ y, const double *__restrict__ w, doubl
     const int64_t slab = blockIdx.y, o = blockIdx.z, nslab = gridDim.y;
     const int64_t c0 = slab * cols_per_slab;
     const int64_t c1 = (c0 + cols_per_slab < n) ? c0 + cols_per_slab : n;
-    const double *yo = y + o * n * inner;
+    const T *yo = y + o * n * inner;
     double a0 = 0.0, a1 = 0.0;
     const bool act = j < inner;
     const bool act1 = (VEC == 2) && (j + 1 < inner);
@@ -99,11 +117,11 @@ strided_kernel(const double *__restrict__ y, const double *__restrict__ w, doubl
         int64_t i = c0 + ty;
         const int64_t step = ty_count;
         for (; i + (UNROLL - 1) * step < c1; i += UNROLL * step) {
-            double2 v[UNROLL]; double ww[UNROLL];
+            T2 v[UNROLL]; T ww[UNROLL];
 #pragma unroll
             for (int u = 0; u < UNROLL; u++) {
-                const double *p = yo + (i + u * step) * inner + j;
-                if (VEC == 2) v[u] = ldg_stream2(p); else { v[u].x = ldg_stream1(p); v[u].y = 0.0; }
+                const T *p = yo + (i + u * step) * inner + j;
+                if (VEC == 2) v[u] = ldg_stream2(p); else { v[u].x = ldg_stream1(p); v[u].y = 0; }
                 ww[u] = __ldg(w + i + u * step);
             }
 #pragma unroll
@@ -113,9 +131,9 @@ strided_kernel(const double *__restrict__ y, const double *__restrict__ w, doubl
             }
         }
         for (; i < c1; i += step) {
-            const double *p = yo + i * inner + j;
-            const double wi = __ldg(w + i);
-            if (VEC == 2) { const double2 v = ldg_stream2(p); a0 = a0 + wi * v.x; a1 = a1 + wi * v.y; }
+            const T *p = yo + i * inner + j;
+            const T wi = __ldg(w + i);
+            if (VEC == 2) { const T2 v = ldg_stream2(p); a0 = a0 + wi * v.x; a1 = a1 + wi * v.y; }
             else a0 = a0 + wi * ldg_stream1(p);
         }
     }
@@ -135,25 +153,26 @@ strided_kernel(const double *__restrict__ y, const double *__restrict__ w, doubl
 }
 
 // inner == 1: grid = (slabs, rows); a CTA streams its slab of one row.
-template <int UNROLL>
+template <typename T, int UNROLL>
 __global__ void __launch_bounds__(kThreads)
-contiguous_kernel(const double *__restrict__ y, const double *__restrict__ w, double *__restrict__ partial,
+contiguous_kernel(const T *__restrict__ y, const T *__restrict__ w, double *__restrict__ partial,
                   int64_t n, int64_t cols_per_slab, int vec_ok) {
+    using T2 = typename Vec2<T>::type;
     __shared__ double red[kThreads / 32];
     const int64_t slab = blockIdx.x, o = blockIdx.y, nslab = gridDim.x;
     const int64_t c0 = slab * cols_per_slab;
     const int64_t c1 = (c0 + cols_per_slab < n) ? c0 + cols_per_slab : n;
-    const double *yo = y + o * n;
+    const T *yo = y + o * n;
     double a0 = 0.0, a1 = 0.0;
-    if (vec_ok) {   // c0 even and row base 16-byte aligned
+    if (vec_ok) {   // c0 even and row base aligned to the 2-element vector
         int64_t i = c0 + 2 * threadIdx.x;
         const int64_t step = 2 * kThreads;
         for (; i + (UNROLL - 1) * step + 1 < c1; i += UNROLL * step) {
-            double2 v[UNROLL], ww[UNROLL];
+            T2 v[UNROLL], ww[UNROLL];
 #pragma unroll
             for (int u = 0; u < UNROLL; u++) {
                 v[u] = ldg_stream2(yo + i + u * step);
-                ww[u] = *reinterpret_cast<const double2 *>(w + i + u * step);
+                ww[u] = *reinterpret_cast<const T2 *>(w + i + u * step);
             }
 #pragma unroll
             for (int u = 0; u < UNROLL; u++) { a0 = a0 + ww[u].x * v[u].x; a1 = a1 + ww[u].y * v[u].y; }
@@ -179,7 +198,8 @@ contiguous_kernel(const double *__restrict__ y, const double *__restrict__ w, do
 }
 
 // out[o, j] = sum over slabs in increasing order
-__global__ void finish_kernel(const double *__restrict__ partial, double *__restrict__ out,
+template <typename T>
+__global__ void finish_kernel(const double *__restrict__ partial, T *__restrict__ out,
                               int64_t inner, int64_t nslab, int64_t total) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
@@ -187,13 +207,15 @@ __global__ void finish_kernel(const double *__restrict__ partial, double *__rest
     const double *p = partial + o * nslab * inner + j;
     double s = p[0];
     for (int64_t k = 1; k < nslab; k++) s += p[k * inner];
-    out[idx] = s;
+    out[idx] = (T)s;
 }
 
 }  // namespace
 
-extern "C" int32_t ib200_sampled(ib200_ctx *ctx, int32_t rule, const double *y, int64_t inner, int64_t n,
-                                 int64_t outer, double h, const double *x, double *out) {
+template <typename T>
+static int32_t sampled_impl(ib200_ctx *ctx, int32_t rule, const T *y, int64_t inner, int64_t n,
+                            int64_t outer, T h, const T *x, T *out) {
+    constexpr bool kF64 = sizeof(T) == 8;
     IB_REQUIRE(ctx, ctx != nullptr, "ib200_sampled: ctx is NULL");
     IB_REQUIRE(ctx, rule == IB200_RULE_TRAPEZOID || rule == IB200_RULE_SIMPSON, "ib200_sampled: unknown rule");
     IB_REQUIRE(ctx, inner >= 0 && outer >= 0 && n >= 0, "ib200_sampled: negative extent");
@@ -208,21 +230,21 @@ extern "C" int32_t ib200_sampled(ib200_ctx *ctx, int32_t rule, const double *y, 
     IB_REQUIRE(ctx, y != nullptr && out != nullptr, "ib200_sampled: y/out is NULL");
     IB_CUDA(ctx, cudaSetDevice(ctx->device));
 
-    DevIn<double> dy, dx; DevOut<double> dout;
+    DevIn<T> dy, dx; DevOut<T> dout;
     int32_t rc;
     if ((rc = dy.init(ctx, y, (size_t)(inner * n * outer), SL_IN0))) return rc;
     if ((rc = dx.init(ctx, x, x ? (size_t)n : 0, SL_IN1))) return rc;
     if ((rc = dout.init(ctx, out, (size_t)(inner * outer), SL_OUT0))) return rc;
-    double *w = (double *)ctx->get(SL_WORK0, (size_t)n * sizeof(double));
+    T *w = (T *)ctx->get(SL_WORK0, (size_t)n * sizeof(T));
     if (!w) return ib200_fail(ctx, IB200_ERR_OOM, "ib200_sampled: weight scratch allocation failed");
 
     ib200_time_begin(ctx);
-    weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(rule, n, h, dx.d, w);
+    weights_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(rule, n, h, dx.d, w);
     IB_LAUNCH_CHECK(ctx);
 
     const int64_t target_ctas = (int64_t)ctx->sm_count * 8;   // 8 x 256-thread CTAs resident per SM
     if (inner >= 2) {
-        const bool vec2 = (inner % 2 == 0) && (((uintptr_t)dy.d) % 16 == 0);
+        const bool vec2 = (inner % 2 == 0) && (((uintptr_t)dy.d) % (2 * sizeof(T)) == 0);
         const int VEC = vec2 ? 2 : 1;
         const int64_t pieces = (inner + VEC - 1) / VEC;
         int tx_count = 1;
@@ -238,17 +260,18 @@ extern "C" int32_t ib200_sampled(ib200_ctx *ctx, int32_t rule, const double *y, 
         IB_REQUIRE(ctx, outer <= 65535, "ib200_sampled: outer extent > 65535 not supported for inner >= 2");
         const int64_t cols_per_slab = (n + nslab - 1) / nslab;
         nslab = (n + cols_per_slab - 1) / cols_per_slab;
-        double *partial = (nslab == 1) ? dout.d
-                                       : (double *)ctx->get(SL_WORK1, (size_t)(outer * nslab * inner) * sizeof(double));
+        const bool direct = kF64 && nslab == 1;                 // one slab of doubles: the kernel writes the result itself
+        double *partial = direct ? reinterpret_cast<double *>(dout.d)
+                                 : (double *)ctx->get(SL_WORK1, (size_t)(outer * nslab * inner) * sizeof(double));
         if (!partial) return ib200_fail(ctx, IB200_ERR_OOM, "ib200_sampled: partial-sum scratch allocation failed");
         dim3 grid((unsigned)row_tiles, (unsigned)nslab, (unsigned)outer);
         const size_t smem = ty_count > 1 ? (size_t)kThreads * 2 * sizeof(double) : 0;
-        if (vec2) strided_kernel<2, 8><<<grid, kThreads, smem, ctx->stream>>>(dy.d, w, partial, inner, n, tx_count, cols_per_slab);
-        else      strided_kernel<1, 8><<<grid, kThreads, smem, ctx->stream>>>(dy.d, w, partial, inner, n, tx_count, cols_per_slab);
+        if (vec2) strided_kernel<T, 2, 8><<<grid, kThreads, smem, ctx->stream>>>(dy.d, w, partial, inner, n, tx_count, cols_per_slab);
+        else      strided_kernel<T, 1, 8><<<grid, kThreads, smem, ctx->stream>>>(dy.d, w, partial, inner, n, tx_count, cols_per_slab);
         IB_LAUNCH_CHECK(ctx);
-        if (nslab > 1) {
+        if (!direct) {
             const int64_t total = inner * outer;
-            finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(partial, dout.d, inner, nslab, total);
+            finish_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(partial, dout.d, inner, nslab, total);
             IB_LAUNCH_CHECK(ctx);
         }
     } else {
@@ -260,14 +283,15 @@ extern "C" int32_t ib200_sampled(ib200_ctx *ctx, int32_t rule, const double *y, 
         int64_t cols_per_slab = (n + nslab - 1) / nslab;
         cols_per_slab = (cols_per_slab + 1) & ~(int64_t)1;      // even, so slabs stay 16-byte aligned
         nslab = (n + cols_per_slab - 1) / cols_per_slab;
-        const int vec_ok = (((uintptr_t)dy.d) % 16 == 0) && (n % 2 == 0 || outer == 1) && (((uintptr_t)w) % 16 == 0);
-        double *partial = (nslab == 1) ? dout.d : (double *)ctx->get(SL_WORK1, (size_t)(outer * nslab) * sizeof(double));
+        const int vec_ok = (((uintptr_t)dy.d) % (2 * sizeof(T)) == 0) && (n % 2 == 0 || outer == 1) && (((uintptr_t)w) % 16 == 0);
+        const bool direct = kF64 && nslab == 1;
+        double *partial = direct ? reinterpret_cast<double *>(dout.d) : (double *)ctx->get(SL_WORK1, (size_t)(outer * nslab) * sizeof(double));
         if (!partial) return ib200_fail(ctx, IB200_ERR_OOM, "ib200_sampled: partial-sum scratch allocation failed");
         dim3 grid((unsigned)nslab, (unsigned)outer);
-        contiguous_kernel<4><<<grid, kThreads, 0, ctx->stream>>>(dy.d, w, partial, n, cols_per_slab, vec_ok);
+        contiguous_kernel<T, 4><<<grid, kThreads, 0, ctx->stream>>>(dy.d, w, partial, n, cols_per_slab, vec_ok);
         IB_LAUNCH_CHECK(ctx);
-        if (nslab > 1) {
-            finish_kernel<<<(unsigned)((outer + 255) / 256), 256, 0, ctx->stream>>>(partial, dout.d, 1, nslab, outer);
+        if (!direct) {
+            finish_kernel<T><<<(unsigned)((outer + 255) / 256), 256, 0, ctx->stream>>>(partial, dout.d, 1, nslab, outer);
             IB_LAUNCH_CHECK(ctx);
         }
     }
@@ -275,4 +299,14 @@ extern "C" int32_t ib200_sampled(ib200_ctx *ctx, int32_t rule, const double *y, 
     if ((rc = dout.finish(ctx))) return rc;
     if (dout.is_host()) IB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return IB200_OK;
+}
+
+extern "C" int32_t ib200_sampled(ib200_ctx *ctx, int32_t rule, const double *y, int64_t inner, int64_t n,
+                                 int64_t outer, double h, const double *x, double *out) {
+    return sampled_impl<double>(ctx, rule, y, inner, n, outer, h, x, out);
+}
+
+extern "C" int32_t ib200_sampled_f32(ib200_ctx *ctx, int32_t rule, const float *y, int64_t inner, int64_t n,
+                                     int64_t outer, float h, const float *x, float *out) {
+    return sampled_impl<float>(ctx, rule, y, inner, n, outer, h, x, out);
 }

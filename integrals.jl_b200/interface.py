@@ -98,15 +98,19 @@ class Range:
     """Uniform grid, the analogue of Julia's `range(start, stop, length=n)`: selects the uniform
     weight types (src/trapezoidal.jl:43, src/simpsons.jl:85)."""
 
-    def __init__(self, start, stop, length):
+    def __init__(self, start, stop, length, dtype=np.float64):
+        """dtype=np.float32 is Julia's `range(0f0, 1f0, length=n)`: a Float32 grid (Float32 weights)."""
+        self.dtype = np.dtype(dtype)
         self.start, self.stop, self.length = float(start), float(stop), int(length)
         self.step = (self.stop - self.start) / (self.length - 1) if self.length > 1 else 0.0
+        if self.dtype == np.float32:
+            self.step = float(np.float32(np.float32(self.stop) - np.float32(self.start)) / np.float32(self.length - 1)) if self.length > 1 else 0.0
 
     def __len__(self):
         return self.length
 
     def toarray(self):
-        return np.linspace(self.start, self.stop, self.length)
+        return np.linspace(self.start, self.stop, self.length).astype(self.dtype)
 
 
 class SampledIntegralProblem:
@@ -356,8 +360,14 @@ def _init_sampled(prob, alg, engine=None, **kws):
 
 
 def _solve_sampled(cache):
-    eng, y, x, dim = cache.cacheval, cache.y, cache.x, cache.dim
     object.__setattr__(cache, "isfresh", False)          # weights are recomputed on the device every solve
+    u = _sampled_u(cache.cacheval, cache.alg.rule, cache.y, cache.x, cache.dim)
+    prob = SampledIntegralProblem(cache.y, cache.x, cache.dim)
+    return IntegralSolution(u, None, prob, cache.alg, ReturnCode.Success)          # sampled.jl:166-167
+
+
+def _sampled_u(eng, rule, y, x, dim):
+    """evalrule(data, weights, dim) on the device for host arrays (float64 / float32 / complex) or device tensors."""
     if hasattr(y, "data_ptr"):
         # torch tensor (row-major): axes after `dim` are the contiguous ones == column-major `inner`
         if not y.is_contiguous():
@@ -366,10 +376,26 @@ def _solve_sampled(cache):
         inner = int(np.prod(shape[dim + 1:], dtype=np.int64)); outer = int(np.prod(shape[:dim], dtype=np.int64))
         out_shape = shape[:dim] + shape[dim + 1:]
     else:
-        y = np.asfortranarray(y, dtype=np.float64)
+        y = np.asarray(y)
+        xdt = x.dtype if isinstance(x, Range) else np.asarray(x).dtype
+        if np.iscomplexobj(y):
+            # Complex samples (test/interface_tests.jl:501-509): the weights are real, so Complex{Float64}[inner, n, outer]
+            # is integrated as Float64[2*inner, n, outer] (real and imaginary parts interleaved, the complex layout)
+            yr = np.empty((2,) + y.shape, dtype=np.float64, order="F")
+            yr[0] = y.real; yr[1] = y.imag
+            ur = np.asarray(_sampled_u(eng, rule, yr, x, dim + 1))
+            u = ur[0] + 1j * ur[1]
+            return complex(u) if np.ndim(u) == 0 else np.asfortranarray(u)
+        f32 = y.dtype == np.float32 and xdt == np.float32      # Float32 type preservation (test/interface_tests.jl:524-539)
+        y = np.asfortranarray(y, dtype=np.float32 if f32 else np.float64)
         shape = y.shape
         inner = int(np.prod(shape[:dim], dtype=np.int64)); outer = int(np.prod(shape[dim + 1:], dtype=np.int64))
         out_shape = shape[:dim] + shape[dim + 1:]
+        if f32:
+            n = shape[dim]
+            h, xs = (x.step, None) if isinstance(x, Range) else (0.0, np.ascontiguousarray(x, dtype=np.float32))
+            out = eng.sampled_f32(rule, y, inner, n, outer, h=h, x=xs)[:inner * outer]
+            return out.reshape(out_shape, order="F") if out_shape else np.float32(out[0])
     n = shape[dim]
     if isinstance(x, Range):
         h, xs = x.step, None
@@ -378,10 +404,7 @@ def _solve_sampled(cache):
     if hasattr(y, "data_ptr"):
         import torch
         out = torch.empty(max(inner * outer, 1), dtype=torch.float64, device=y.device)
-        eng.sampled(cache.alg.rule, y, inner, n, outer, h=h, x=xs, out=out)
-        u = out[:inner * outer].reshape(out_shape) if out_shape else out[0]
-    else:
-        out = eng.sampled(cache.alg.rule, y, inner, n, outer, h=h, x=xs)[:inner * outer]
-        u = out.reshape(out_shape, order="F") if out_shape else float(out[0])
-    prob = SampledIntegralProblem(cache.y, cache.x, dim)
-    return IntegralSolution(u, None, prob, cache.alg, ReturnCode.Success)          # sampled.jl:166-167
+        eng.sampled(rule, y, inner, n, outer, h=h, x=xs, out=out)
+        return out[:inner * outer].reshape(out_shape) if out_shape else out[0]
+    out = eng.sampled(rule, y, inner, n, outer, h=h, x=xs)[:inner * outer]
+    return out.reshape(out_shape, order="F") if out_shape else float(out[0])

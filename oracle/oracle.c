@@ -365,6 +365,71 @@ int orc_sampled_evalrule(int rule, const double *y, int64_t inner, int64_t n, in
     return 0;
 }
 
+/* Float32 samples on a Float32 grid (test/interface_tests.jl:524-539 "Float32 type preservation"): the reference's
+   generic code runs entirely in Float32 -- weights from a Float32 step / grid, products and the sequential sum in
+   Float32.  Same formulas as above in float arithmetic. */
+static float orc_w_f32(int rule, int64_t n, float h, const float *x0, int64_t i)
+{
+    if (!x0) {
+        if (rule == 0) return (i == 1 || i == n) ? h / 2 : h;
+        if (i == 1 || i == n) return 17 * h / 48;
+        if (i == 2 || i == n - 1) return 59 * h / 48;
+        if (i == 3 || i == n - 2) return 43 * h / 48;
+        if (i == 4 || i == n - 3) return 49 * h / 48;
+        return h;
+    }
+    if (rule == 0) {
+        if (i == 1) return (x0[1] - x0[0]) / 2;
+        if (i == n) return (x0[n - 1] - x0[n - 2]) / 2;
+        return (x0[i] - x0[i - 2]) / 2;
+    }
+#define B(k) x0[(k)]
+#define E(k) x0[n - 1 - (k)]
+#define CUBE(v) ((v) * (v) * (v))
+    int64_t j = i - 1;
+    if (i == 1) return (B(2) - B(0)) / 6 * (2 - (B(2) - B(1)) / (B(1) - B(0)));
+    if (n & 1) {
+        if (i == n) return (E(0) - E(2)) / 6 * (2 - (E(1) - E(2)) / (E(0) - E(1)));
+    } else {
+        if (i == n) return (E(0) - E(1)) * (2 * (E(0) - E(1)) + 3 * (E(1) - E(2))) / (E(0) - E(2)) / 6;
+        if (i == n - 1)
+            return (E(1) - E(3)) / 6 * (2 - (E(2) - E(3)) / (E(1) - E(2))) +
+                   (E(0) - E(1)) * ((E(0) - E(1)) + 3 * (E(1) - E(2))) / (E(1) - E(2)) / 6;
+        if (i == n - 2)
+            return CUBE(E(1) - E(3)) / (E(2) - E(3)) / (E(1) - E(2)) / 6 -
+                   CUBE(E(0) - E(1)) / (E(1) - E(2)) / (E(0) - E(2)) / 6;
+    }
+    if (j & 1) return CUBE(B(j + 1) - B(j - 1)) / (B(j) - B(j - 1)) / (B(j + 1) - B(j)) / 6;
+    return (B(j) - B(j - 2)) / 6 * (2 - (B(j - 1) - B(j - 2)) / (B(j) - B(j - 1))) +
+           (B(j + 2) - B(j)) / 6 * (2 - (B(j + 2) - B(j + 1)) / (B(j + 1) - B(j)));
+#undef B
+#undef E
+#undef CUBE
+}
+
+int orc_sampled_evalrule_f32(int rule, const float *y, int64_t inner, int64_t n, int64_t outer,
+                             float h, const float *x, float *out, float *w_out)
+{
+    if (n == 0) return -3;
+    if (rule != 0 && rule != 1) return -1;
+    if (x && ((rule == 1 && n <= 2) || n < 2)) return -2;
+    float *w = (float *)malloc(sizeof(float) * (size_t)n);
+    if (!w) return -4;
+    for (int64_t i = 1; i <= n; i++) w[i - 1] = orc_w_f32(rule, n, h, x, i);
+    for (int64_t o = 0; o < outer; o++) {
+        const float *yo = y + o * n * inner;
+        float *oo = out + o * inner;
+        for (int64_t j = 0; j < inner; j++) {
+            volatile float acc = w[0] * yo[j];                 /* volatile: no excess precision, one rounding per operation */
+            for (int64_t i = 1; i < n; i++) { volatile float pr = w[i] * yo[i * inner + j]; acc = acc + pr; }
+            oo[j] = acc;
+        }
+    }
+    if (w_out) memcpy(w_out, w, sizeof(float) * (size_t)n);
+    free(w);
+    return 0;
+}
+
 /* ------------------------------------------------------------------------------------------
  * QuadGK.jl (un-vendored dependency; compat "2.11", Project.toml:65), called at
  * src/Integrals.jl:327-335 with order = 7.  Restated from the package's published algorithm

@@ -79,6 +79,11 @@ int orc_sampled_weights(int rule, int64_t n, double h, const double *x, double *
 int orc_sampled_evalrule(int rule, const double *y, int64_t inner, int64_t n, int64_t outer,
                          double h, const double *x, double *out, int nthreads);
 
+/* the same reduction for Float32 samples on a Float32 grid, all arithmetic in float like the reference's generic code
+   (test/interface_tests.jl:524-539); w_out (may be NULL) receives the n float weights */
+int orc_sampled_evalrule_f32(int rule, const float *y, int64_t inner, int64_t n, int64_t outer,
+                             float h, const float *x, float *out, float *w_out);
+
 /* QuadGK.jl quadgk, order 7 (GK(7,15)), scalar integrand, norm = abs.
    status: 0 ok, 1 maxevals reached, 2 non-finite error estimate (QuadGK DomainError),
    3 endpoint roundoff stopped refinement */

@@ -157,6 +157,28 @@ def sampled_evalrule(rule, y, x=None, h=None, dim=-1, nthreads=1):
     return out if out.ndim else float(out)
 
 
+def sampled_evalrule_f32(rule, y, x=None, h=None, dim=-1):
+    """Float32 samples on a Float32 grid, every operation in float, sequential sum (the reference's generic code).
+    -> (result float32 array without axis `dim`, the float32 weights)."""
+    y = np.asfortranarray(y, dtype=np.float32)
+    dim = dim % y.ndim
+    n = y.shape[dim]
+    inner = int(np.prod(y.shape[:dim], dtype=np.int64)); outer = int(np.prod(y.shape[dim + 1:], dtype=np.int64))
+    out_shape = y.shape[:dim] + y.shape[dim + 1:]
+    out = np.empty(max(inner * outer, 1), dtype=np.float32); w = np.empty(n, dtype=np.float32)
+    xx = None if x is None else np.ascontiguousarray(x, dtype=np.float32)
+    fp = C.POINTER(C.c_float)
+    L = lib()
+    L.orc_sampled_evalrule_f32.argtypes = [C.c_int, fp, C.c_int64, C.c_int64, C.c_int64, C.c_float, fp, fp, fp]
+    rc = L.orc_sampled_evalrule_f32(0 if rule.startswith("trap") else 1, y.ctypes.data_as(fp), inner, n, outer,
+                                    np.float32(0.0 if h is None else h), None if xx is None else xx.ctypes.data_as(fp),
+                                    out.ctypes.data_as(fp), w.ctypes.data_as(fp))
+    if rc:
+        raise ValueError(f"orc_sampled_evalrule_f32 rc={rc}")
+    out = out[:inner * outer].reshape(out_shape, order="F")
+    return (out if out.ndim else np.float32(out)), w
+
+
 # ---- generic-callback solves (pin the oracle against the reference's own tests) --------------
 def _bounds(lb, ub):
     lb = _arr(np.atleast_1d(lb)); ub = _arr(np.atleast_1d(ub))

@@ -409,3 +409,43 @@ def test_hcubature_single_two_gpus():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     out = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
     assert out["world"] == 2 and all(c["ok"] and c["identical_refinement"] for c in out["cases"])
+
+
+# ------------------------------------------------------------------------------------- Float32 / complex samples
+@pytest.mark.parametrize("rule", ["trapezoid", "simpson"])
+@pytest.mark.parametrize("shape,dim", [((1000,), 0), ((257, 1001), 1), ((1001, 130), 0), ((6, 333, 5), 1), ((3, 7), 1)])
+@pytest.mark.parametrize("uniform", [True, False])
+def test_sampled_float32(eng, O, rule, shape, dim, uniform):
+    """Float32 type preservation (test/interface_tests.jl:524-539): float weights and products like the reference; the CUDA
+    path accumulates in double, so it must sit within the float rounding of the rule evaluated in double on the same
+    float weights, and within the sequential-float error bound of the reference-order oracle."""
+    rng = np.random.default_rng(13)
+    n = shape[dim]
+    y = np.asfortranarray((rng.random(shape) + 0.5).astype(np.float32))
+    x = None if uniform else (np.sort(rng.random(n)) * 2 + 0.1).astype(np.float32)
+    h = np.float32(0.37) if uniform else None
+    ref32, w = O.sampled_evalrule_f32(rule, y, x=x, h=h, dim=dim)
+    inner = int(np.prod(shape[:dim], dtype=np.int64)); outer = int(np.prod(shape[dim + 1:], dtype=np.int64))
+    got = eng.sampled_f32(rule, y, inner, n, outer, h=float(h) if uniform else 0.0, x=x)[:inner * outer]
+    assert got.dtype == np.float32
+    exact = np.tensordot(y.astype(np.float64), w.astype(np.float64), axes=([dim], [0])).ravel(order="F")     # same float weights, exact-ish sum
+    scale = np.tensordot(np.abs(y).astype(np.float64), np.abs(w).astype(np.float64), axes=([dim], [0])).ravel(order="F")
+    assert np.all(np.abs(got.astype(np.float64) - exact) <= 1.5 * 6e-8 * scale)                  # product rounding + final rounding
+    assert np.all(np.abs(got.astype(np.float64) - np.atleast_1d(ref32).ravel(order="F").astype(np.float64)) <= n * 6e-8 * scale)
+
+
+def test_sampled_float32_and_complex_through_solve(eng):
+    x32 = ib.Range(0.0, 1.0, 11, dtype=np.float32)                 # test/interface_tests.jl:526-538
+    y32 = np.sin(x32.toarray())
+    sol = ib.solve(ib.SampledIntegralProblem(y32, x32), ib.TrapezoidalB200(), engine=eng)
+    assert isinstance(sol.u, np.float32) and abs(float(sol.u) - (1 - math.cos(1.0))) < 2e-3
+    ym = np.asfortranarray(np.array([[math.sin(xi) * j for xi in x32.toarray()] for j in (1, 2, 3)], dtype=np.float32))
+    sol = ib.solve(ib.SampledIntegralProblem(ym, x32, dim=1), ib.TrapezoidalB200(), engine=eng)
+    assert sol.u.dtype == np.float32 and np.allclose(sol.u, sol.u[0] * np.array([1, 2, 3]), rtol=1e-6)
+    xc = ib.Range(0.0, 1.0, 11)                                    # test/interface_tests.jl:501-509
+    yc = np.sin(xc.toarray()) + 1j * np.cos(xc.toarray())
+    sol = ib.solve(ib.SampledIntegralProblem(yc, xc), ib.TrapezoidalB200(), engine=eng)
+    assert isinstance(sol.u, complex) and sol.u.real > 0 and sol.u.imag > 0
+    re = ib.solve(ib.SampledIntegralProblem(yc.real.copy(), xc), ib.TrapezoidalB200(), engine=eng).u
+    im = ib.solve(ib.SampledIntegralProblem(yc.imag.copy(), xc), ib.TrapezoidalB200(), engine=eng).u
+    assert abs(sol.u - complex(re, im)) <= 4e-16 * abs(sol.u)      # different summation trees (strided vs contiguous kernel)

@@ -138,3 +138,24 @@ def test_sampled_problem_shapes_and_errors():   # src/common.jl:319-343, src/sam
     assert cache.isfresh is True
     cache.solve()
     assert cache.isfresh is False and e.calls[-1][2]["h"] == 1.0
+
+
+def test_sampled_float32_and_complex_routing():   # test/interface_tests.jl:501-539
+    class E32(StubEngine):
+        def sampled_f32(self, rule, y, inner, n, outer, h=0.0, x=None, out=None):
+            self._rec("sampled_f32", rule, inner, n, outer, h=h, x=x, ydtype=y.dtype); return np.zeros(max(inner * outer, 1), np.float32)
+    e = E32()
+    y32 = np.sin(np.linspace(0, 1, 11)).astype(np.float32)
+    sol = ib.solve(ib.SampledIntegralProblem(y32, ib.Range(0.0, 1.0, 11, dtype=np.float32)), ib.TrapezoidalB200(), engine=e)
+    assert e.calls[-1][0] == "sampled_f32" and isinstance(sol.u, np.float32) and e.calls[-1][2]["h"] == pytest.approx(0.1, rel=1e-6)
+    sol = ib.solve(ib.SampledIntegralProblem(np.zeros((3, 11), np.float32), np.linspace(0, 1, 11, dtype=np.float32), dim=1), ib.SimpsonsB200(), engine=e)
+    assert e.calls[-1][0] == "sampled_f32" and sol.u.dtype == np.float32 and sol.u.shape == (3,)
+    # Float32 samples on a Float64 grid promote to Float64, as Float32 * Float64 does in the reference
+    ib.solve(ib.SampledIntegralProblem(y32, ib.Range(0.0, 1.0, 11)), ib.TrapezoidalB200(), engine=e)
+    assert e.calls[-1][0] == "sampled"
+    # complex samples: real weights -> the float64 kernel on [2*inner, n, outer]
+    yc = np.exp(1j * np.linspace(0, 1, 11))
+    sol = ib.solve(ib.SampledIntegralProblem(yc, ib.Range(0.0, 1.0, 11)), ib.TrapezoidalB200(), engine=e)
+    assert e.calls[-1][0] == "sampled" and e.calls[-1][1][1:] == (2, 11, 1) and isinstance(sol.u, complex)
+    sol = ib.solve(ib.SampledIntegralProblem(np.zeros((4, 11, 3), complex), ib.Range(0.0, 1.0, 11), dim=1), ib.SimpsonsB200(), engine=e)
+    assert e.calls[-1][1][1:] == (8, 11, 3) and sol.u.shape == (4, 3) and np.iscomplexobj(sol.u)

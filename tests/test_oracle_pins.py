@@ -277,3 +277,19 @@ def test_issue242_abstol_is_an_absolute_stop():  # interface_tests.jl:446-454 se
     I1, E1, n1, _ = O.solve_quadgk(lambda x: math.sin(64 * x), -2.0, 5.0, reltol=1e-10, abstol=1e-8)
     I2, E2, n2, _ = O.solve_quadgk(lambda x: math.sin(64 * x), -2.0, 5.0, reltol=1e-10, abstol=0.0)
     assert E1 <= 1e-8 and n2 > n1 and E2 <= 1e-10 * abs(I2)
+
+
+def test_sampled_float32_restatement():   # test/interface_tests.jl:524-539 semantics: all arithmetic in Float32
+    rng = np.random.default_rng(3)
+    for n in (3, 11, 12, 1000):
+        y = (rng.random(n) + 0.5).astype(np.float32)
+        x = (np.sort(rng.random(n)) * 2 + 0.1).astype(np.float32)
+        for rule in ("trapezoid", "simpson"):
+            for kw in (dict(h=np.float32(0.01)), dict(x=x)):
+                got, w = O.sampled_evalrule_f32(rule, y, **kw)
+                assert isinstance(got, np.float32) and w.dtype == np.float32
+                ref = O.sampled_evalrule(rule, y.astype(np.float64), **{k: (float(v) if k == "h" else v.astype(np.float64)) for k, v in kw.items()})
+                w64 = O.sampled_weights(rule, n, **{k: (float(v) if k == "h" else v.astype(np.float64)) for k, v in kw.items()})
+                # float weights/products/sequential sum vs the float64 rule on the same (float32-representable) inputs
+                cond = 30 if (rule == "simpson" and "x" in kw) else 4        # non-uniform Simpson weights cancel in float
+                assert abs(float(got) - ref) <= cond * n * 6e-8 * float(np.sum(np.abs(w64 * y)))
