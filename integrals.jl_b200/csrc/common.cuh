@@ -37,6 +37,7 @@ struct ib200_ctx {
     double opt_single_round_fraction = 0.5;  // hcub_single.cu: share of the stored boxes one round may bisect
     int64_t opt_hcub_capacity = 0;           // boxes per in-flight problem, 0 = derive from maxevals
     int64_t opt_sampled_slabs = 0;           // 0 = auto
+    int64_t opt_quadgk_mode = 0;             // 0 = auto, 1 = warp per problem, 2 = pair mode (thread per segment)
     int64_t opt_hcub_mode = 0;               // 0 = auto, 1 = warp per problem, 2 = pair mode (thread per box)
 
     // grow-only device scratch (the cacheval analogue: reused across calls)

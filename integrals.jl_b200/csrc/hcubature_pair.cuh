@@ -1,5 +1,6 @@
 // hcubature_pair.cuh -- batched adaptive Genz-Malik cubature, "pair mode": one THREAD per box,
 // two lanes (the two children of a bisection) per problem, 16 problems per warp.
+// With D == 1 the same machinery runs QuadGK's (7,15) Gauss-Kronrod bisection (ib200_quadgk_batch, large batches).
 //
 // Same algorithm and the same selection order as hcubature_impl.cuh (HCubature.jl as called at
 // src/Integrals.jl:380-393; oracle: orc_hcubature / gm_rule): largest error first, ties -> lowest
@@ -205,6 +206,61 @@ __device__ __forceinline__ void gm_rule_thread(const double *pc, int tr, const d
         else if (fabs(delta) <= deltaf && h[k] > hkd) { kdv = k; hkd = h[k]; }
     }
     Iout = Iv; Eout = Er; kdiv = kdv;
+}
+
+// ------------------------------------------------------------------------------------------------
+// D == 1: the pair machinery runs QuadGK (QuadGK.quadgk as called at src/Integrals.jl:327-335; oracle: orc_quadgk).
+// One application of the (7,15) Gauss-Kronrod rule to the segment (a, b) by one thread, summed in QuadGK's order
+// (symmetric pairs first; oracle gk_evalrule).
+// ------------------------------------------------------------------------------------------------
+template <int FAM, bool ALLFIN>
+__device__ __forceinline__ void gk_rule_thread(const double *pc, int tr, double a, double b, double &Iout, double &Eout) {
+    using F = ib::Family<FAM, 1>;
+    constexpr int NPAR = ib::fam_nparam(FAM, 1);
+    const double *par = pc, *lbs = pc + NPAR, *aux = lbs + 1;
+    const double jacc = aux[2];
+    double q[F::NQ];
+    F::prepare(par, q);
+    constexpr double X[7] = {-0.991455371120812639206854697526329, -0.949107912342758524526189684047851,
+                             -0.864864423359769072789712788640926, -0.741531185599394439863864773280788,
+                             -0.586087235467691130294144838258730, -0.405845151377397166906606412076961,
+                             -0.207784955007898467600689403773245};
+    constexpr double W[8] = {0.022935322010529224963732008058970, 0.063092092629978553290700663189204,
+                             0.104790010322250183839876322541518, 0.140653259715525918745189590510238,
+                             0.169004726639267902826583426598550, 0.190350578064785409913256402421014,
+                             0.204432940075298892414161999234649, 0.209482141084727828012999174891714};
+    constexpr double WG[4] = {0.129484966168869693270611432679082, 0.279705391489276667901467771423780,
+                              0.381830050505118944950369775488975, 0.417959183673469387755102040816327};
+    const double s = 0.5 * (b - a);
+    auto g = [&](double t) {
+        double u[1], J;
+        if (ALLFIN) { u[0] = lbs[0] + (1.0 + t) * aux[0]; J = jacc; }
+        else { ib::AxisMap m; ib::make_axis(lbs[0], aux[0], m); ib::t2ujac(tr, t, m, u[0], J); }
+        return F::eval(u, q) * J;
+    };
+    double fp[7], fm[7];
+#pragma unroll
+    for (int j = 0; j < 7; j++) { fp[j] = g(a + (1 + X[j]) * s); fm[j] = g(a + (1 - X[j]) * s); }
+    const double f0 = g(a + s);
+    double fg = fp[1] + fm[1], fk = fp[0] + fm[0];
+    double Ig = fg * WG[0];
+    double Ik = fg * W[1] + fk * W[0];
+#pragma unroll
+    for (int i = 2; i <= 3; i++) {
+        fg = fp[2 * i - 1] + fm[2 * i - 1];
+        fk = fp[2 * i - 2] + fm[2 * i - 2];
+        Ig += fg * WG[i - 1];
+        Ik += fg * W[2 * i - 1] + fk * W[2 * i - 2];
+    }
+    Ig += f0 * WG[3];
+    Ik += f0 * W[7] + (fp[6] + fm[6]) * W[6];
+    Iout = Ik * s;
+    Eout = fabs(Ik * s - Ig * s);
+}
+// QuadGK's check_endpoint_roundoff: does the rule evaluate at an endpoint of (a, b)?
+__device__ __forceinline__ bool gk_endpoint_roundoff(double a, double b) {
+    const double c = 0.5 * (b - a), x1 = -0.991455371120812639206854697526329;
+    return (a == a + (1 + x1) * c) || (b == a + (1 - x1) * c);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -445,13 +501,21 @@ hcub_pair_kernel(const Params p) {
             double akd = 0.0, bkd = 0.0;
 #pragma unroll
             for (int k = 0; k < D; k++) { a[k] = r[k]; b[k] = r[D + k]; if (k == kdp) { akd = r[k]; bkd = r[D + k]; } }
-            const double w = (bkd - akd) * 0.5;
-            // child 0 = upper half (a[kd] += w), child 1 = lower half (b[kd] -= w)
-#pragma unroll
-            for (int k = 0; k < D; k++) {
-                if (k == kdp) { if (half == 0) a[k] = akd + w; else b[k] = bkd - w; }
-            }
             have = true;
+            if (D == 1) {
+                // QuadGK: mid = (a + b) / 2; the pair evaluates (a, mid) and (mid, b); a segment that can no longer be
+                // bisected ends the refinement (check_endpoint_roundoff)
+                const double mid = (akd + bkd) / 2;
+                if (gk_endpoint_roundoff(akd, mid) || gk_endpoint_roundoff(mid, bkd)) { status = IB200_ST_ROUNDOFF; state = ST_FIN; have = false; }
+                if (half == 0) b[0] = mid; else a[0] = mid;
+            } else {
+                const double w = (bkd - akd) * 0.5;
+                // child 0 = upper half (a[kd] += w), child 1 = lower half (b[kd] -= w)
+#pragma unroll
+                for (int k = 0; k < D; k++) {
+                    if (k == kdp) { if (half == 0) a[k] = akd + w; else b[k] = bkd - w; }
+                }
+            }
         } else if (state == ST_INIT) {
             const int64_t myq = q + half;
             have = myq < qtotal;
@@ -469,7 +533,10 @@ hcub_pair_kernel(const Params p) {
 
         // ---- 4. the rule on this lane's box
         double Ic = 0.0, Ec = 0.0; int kc = 0;
-        if (have) gm_rule_thread<FAM, D, ALLFIN>(pc, p.tr, a, b, Ic, Ec, kc);
+        if (have) {
+            if constexpr (D == 1) gk_rule_thread<FAM, ALLFIN>(pc, p.tr, a[0], b[0], Ic, Ec);
+            else gm_rule_thread<FAM, D, ALLFIN>(pc, p.tr, a, b, Ic, Ec, kc);
+        }
 
         // ---- 5. bookkeeping (per pair)
         if (state == ST_REFINE || state == ST_INIT) {
@@ -487,8 +554,8 @@ hcub_pair_kernel(const Params p) {
             };
             if (state == ST_REFINE) {
                 nev += 2 * NP;
-                I += I1 + I2 - Ibox;
-                E += E1 + E2 - Ebox;
+                if (D == 1) { I = (I - Ibox) + I1 + I2; E = (E - Ebox) + E1 + E2; }     // QuadGK's order
+                else { I += I1 + I2 - Ibox; E += E1 + E2 - Ebox; }
                 const int s2 = nbox;
                 const int i = slot >> 5, j = slot >> 10, i2 = s2 >> 5, j2 = s2 >> 10;
                 // runner-ups of the two groups on the selected path (data prefetched into L2 before the evaluation)
@@ -572,7 +639,7 @@ int32_t launch_impl(ib200_ctx *ctx, int family, bool allfin, Params &p) {
     int32_t rc = IB200_ERR_UNSUPPORTED;
     ib200_dispatch_family(family, [&](auto famc) {
         constexpr int FAM = decltype(famc)::value;
-        if constexpr (ib::fam_dim_ok(FAM, D) && D >= 2) {
+        if constexpr (ib::fam_dim_ok(FAM, D)) {
             auto go = [&](auto kern) -> int32_t {
                 const size_t smem = ((size_t)kPairs * row_doubles(p.cap >> 10, pc_doubles<FAM, D>()) + (size_t)kBlock * 32 + (size_t)kPairs * 4) * sizeof(double);
                 if (smem > ctx->smem_optin) return ib200_fail(ctx, IB200_ERR_INVALID, "ib200_hcubature_batch: box capacity too large for shared memory");
@@ -588,12 +655,20 @@ int32_t launch_impl(ib200_ctx *ctx, int family, bool allfin, Params &p) {
                 if (blocks > (int64_t)ctx->sm_count * occ) blocks = (int64_t)ctx->sm_count * occ;
                 // the pools are sized by residency: shrink the grid until they fit in free HBM
                 const size_t per_pair = pool_bytes_per_pair(D, p.cap);
-                size_t fr = 0, tot = 0;
-                IB_CUDA(ctx, cudaMemGetInfo(&fr, &tot));
-                size_t held = 0;
-                for (int s : {SL_WORK0, SL_WORK2, SL_WORK3, SL_WORK4, SL_WORK5}) held += ctx->scratch[s].cap;
-                const size_t budget = (size_t)((double)(fr + held) * 0.85);
-                while (blocks > 1 && (size_t)blocks * kPairs * per_pair > budget) blocks = blocks > ctx->sm_count ? blocks - ctx->sm_count : blocks - 1;
+                const auto fits_held = [&](int64_t nb) {      // the pools this grid needs are already allocated
+                    const size_t pr = (size_t)nb * kPairs;
+                    return ctx->scratch[SL_WORK0].cap >= pr * p.cap * sizeof(double) &&
+                           ctx->scratch[SL_WORK2].cap >= pr * p.cap * (2 * D + 2) * sizeof(double) &&
+                           ctx->scratch[SL_WORK4].cap >= pr * (p.cap / kFan) * sizeof(double) && ctx->scratch[SL_WORK5].cap >= pr * (p.cap / kFan);
+                };
+                if (!fits_held(blocks)) {                      // (cudaMemGetInfo costs milliseconds: only when the pools have to grow)
+                    size_t fr = 0, tot = 0;
+                    IB_CUDA(ctx, cudaMemGetInfo(&fr, &tot));
+                    size_t held = 0;
+                    for (int s : {SL_WORK0, SL_WORK2, SL_WORK3, SL_WORK4, SL_WORK5}) held += ctx->scratch[s].cap;
+                    const size_t budget = (size_t)((double)(fr + held) * 0.85);
+                    while (blocks > 1 && (size_t)blocks * kPairs * per_pair > budget) blocks = blocks > ctx->sm_count ? blocks - ctx->sm_count : blocks - 1;
+                }
                 const size_t pairs = (size_t)blocks * kPairs;
                 p.keys = (double *)ctx->get(SL_WORK0, pairs * p.cap * sizeof(double));
                 p.rec = (double *)ctx->get(SL_WORK2, pairs * p.cap * (2 * D + 2) * sizeof(double));

@@ -21,6 +21,11 @@
 //     Selection order is the reference's (largest error first; ties -> lowest slot).
 #include "common.cuh"
 #include "family.cuh"
+#include "hcubature_pair.cuh"
+
+namespace hp {
+template <> int32_t launch<1>(ib200_ctx *, int, bool, Params &);
+}
 
 namespace {
 
@@ -213,6 +218,35 @@ extern "C" int32_t ib200_quadgk_batch(ib200_ctx *ctx, int32_t family, int32_t tr
     if ((rc = oE.init(ctx, out_E, (size_t)nprob, SL_OUT1))) return rc;
     if ((rc = oN.init(ctx, out_nevals, (size_t)nprob, SL_OUT2))) return rc;
     if ((rc = oS.init(ctx, out_status, (size_t)nprob, SL_OUT3))) return rc;
+
+    // large batches: pair mode (thread per segment, two lanes per problem, 16 problems per warp; hcubature_pair.cuh with
+    // D = 1).  ncu on the warp-per-problem kernel below (profiles/r01_quadgk_c1_*): 84 % of the issue slots busy with
+    // 360 warp instructions per refinement step, of which the 30 integrand evaluations are a small part.
+    // Measured (C1 sweep, kernel time): 65,536 problems 1.29 ms (warp) vs 1.49 ms (pair); 2^20 problems 18.9 vs 14.6 ms:
+    // a step is only 30 evaluations, so the pair kernel's per-step pool traffic weighs more than in the cubature case.
+    const bool use_pair = ctx->opt_quadgk_mode == 2 || (ctx->opt_quadgk_mode == 0 && nprob >= ((int64_t)1 << 18));
+    if (use_pair) {
+        int64_t need_seg = maxevals >= ((int64_t)1 << 40) ? 4096 : 2 + (maxevals > 15 ? (maxevals - 15 + 29) / 30 : 0);
+        if (ctx->opt_hcub_capacity > 0) need_seg = ctx->opt_hcub_capacity;
+        if (need_seg > 65536 - 1024) need_seg = 65536 - 1024;
+        unsigned long long *counter = (unsigned long long *)ctx->get(SL_WORK1, sizeof(unsigned long long));
+        if (!counter) return ib200_fail(ctx, IB200_ERR_OOM, "ib200_quadgk_batch: scratch allocation failed");
+        IB_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), ctx->stream));
+        hp::Params q;
+        q.params = dpar.d; q.nparam = nparam; q.nprob = nprob; q.lb = dlb.d; q.ub = dub.d; q.bpp = bpp; q.tr = transform;
+        q.rtol = reltol; q.atol = abstol; q.maxevals = maxevals; q.initdiv = 1;
+        q.cap = (int)((need_seg + 1023) / 1024 * 1024);
+        q.keys = q.l1 = q.rec = nullptr; q.l1off = nullptr; q.counter = counter;
+        q.order = nullptr; q.norder = nullptr;
+        q.out_I = oI.d; q.out_E = oE.d; q.out_nevals = oN.d; q.out_status = oS.d;
+        ctx->err.clear();
+        ib200_time_begin(ctx);
+        if ((rc = hp::launch<1>(ctx, family, allfin, q))) return rc;
+        ib200_time_end(ctx);
+        if ((rc = oI.finish(ctx)) || (rc = oE.finish(ctx)) || (rc = oN.finish(ctx)) || (rc = oS.finish(ctx))) return rc;
+        if (oI.is_host() || oE.is_host() || oN.is_host() || oS.is_host()) IB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return IB200_OK;
+    }
 
     // shared pool: 5 CTAs/SM target -> ~44 KB dynamic smem per CTA
     int ctas_per_sm = 4;

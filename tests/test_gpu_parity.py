@@ -179,7 +179,15 @@ def _check_adaptive(I, E, st, Iref, Eref, reltol, abstol, exact=None):
     assert np.all(ok | ((E <= 1e-14 * np.abs(I)) & (Eref <= 1e-14 * np.abs(Iref))))
 
 
-def test_quadgk_readme_example(eng):
+@pytest.fixture(params=[1, 2], ids=["warp_mode", "pair_mode"])
+def quadgk_mode(request, eng):
+    """run the test under both QuadGK kernels: 1 = warp per problem, 2 = pair mode (thread per segment, hcubature_pair.cuh D = 1)"""
+    eng.set_option("quadgk_mode", request.param)
+    yield request.param
+    eng.set_option("quadgk_mode", 0)
+
+
+def test_quadgk_readme_example(eng, quadgk_mode):
     I, E, ne, st = eng.quadgk_batch(F["sinxp"], np.array([-2.0]), np.array([5.0]), np.array([[1.7]]), reltol=1e-10)
     assert st[0] == 0 and ne[0] == 75
     assert I[0] == pytest.approx((math.cos(-3.4) - math.cos(8.5)) / 1.7, rel=1e-14)
@@ -187,7 +195,7 @@ def test_quadgk_readme_example(eng):
 
 
 @pytest.mark.parametrize("abstol", [1e-8, 1e-12])
-def test_quadgk_sweep_matches_oracle(eng, O, abstol):
+def test_quadgk_sweep_matches_oracle(eng, O, abstol, quadgk_mode):
     # config C1 at reduced size: p_k = 0.1 + 63.9 k/(n-1)
     n = 2048
     p = (0.1 + 63.9 * np.arange(n) / (n - 1)).reshape(1, n)
@@ -200,7 +208,7 @@ def test_quadgk_sweep_matches_oracle(eng, O, abstol):
 
 
 @pytest.mark.parametrize("tr", [0, 1, 2])
-def test_quadgk_infinite_domains(eng, O, tr):
+def test_quadgk_infinite_domains(eng, O, tr, quadgk_mode):
     trn = ["if_inf", "tan", "cot"][tr]
     cases = [(-INF, INF), (INF, -INF), (0.0, INF), (0.0, -INF), (-INF, 0.0), (INF, 0.0), (2.0, INF), (-INF, 2.0), (1.0, 4.0), (4.0, 1.0)]
     lb = np.array([c[0] for c in cases]); ub = np.array([c[1] for c in cases])
@@ -218,7 +226,7 @@ def test_quadgk_infinite_domains(eng, O, tr):
     assert abs(I[0] + 1.0) < 1e-3
 
 
-def test_quadgk_maxevals_and_status(eng, O):
+def test_quadgk_maxevals_and_status(eng, O, quadgk_mode):
     p = np.array([[50.0, 60.0]])
     I, E, ne, st = eng.quadgk_batch(F["sinxp"], np.array([-2.0]), np.array([5.0]), p, reltol=1e-12, abstol=0.0, maxevals=300)
     Ir, Er, ner, str_ = O.quadgk_batch("sinxp", -2.0, 5.0, p, reltol=1e-12, abstol=0.0, maxiters=300)
@@ -331,7 +339,7 @@ def test_golden_hcubature_closed_forms(eng, rec, hcub_mode):
 
 
 @pytest.mark.parametrize("rec", GOLD["exact_sinxp"], ids=lambda r: f"p{r['p']}")
-def test_golden_quadgk_closed_forms(eng, rec):
+def test_golden_quadgk_closed_forms(eng, rec, quadgk_mode):
     I, E, ne, st = eng.quadgk_batch(F["sinxp"], np.array([-2.0]), np.array([5.0]), np.array([[rec["p"]]]), reltol=1e-10, abstol=1e-13)
     assert st[0] == 0 and abs(I[0] - rec["exact"]) <= max(1e-13, 1e-10 * abs(rec["exact"]))
 
