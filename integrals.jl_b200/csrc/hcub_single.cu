@@ -177,7 +177,10 @@ eval_kernel(Params p) {
     __shared__ double s_par[NPAR + 3 * D];
     __shared__ double s_w[10];
     __shared__ unsigned s_pt[NP];
-    __shared__ double s_stage[kWarps][14 * D + 14 * D + NAX + D + 2 * D];
+    constexpr bool FUSE = F::kProd && !ALLFIN;      // product families: one table of T_k * J_k (finish is the identity)
+    constexpr bool SEPJ = !ALLFIN && !FUSE;         // sum families on infinite axes: separate Jacobian table
+    constexpr int DL = D / 2, DH = D - DL, NL = 1 << DL, NH = 1 << DH, NCORN = 1 << D;
+    __shared__ double s_stage[kWarps][14 * D + 14 * D + NAX + D + 2 * D + 2 * (NL + NH)];
     __shared__ double s_red[3 * kWarps];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     double *par = s_par, *lbs = s_par + NPAR, *ubs = lbs + D, *dens = ubs + D;
@@ -215,6 +218,7 @@ eval_kernel(Params p) {
     }
     const double finit = F::sep_init(par);
     double *tabT = s_stage[wib], *tabJ = tabT + 14 * D, *fst = tabJ + 14 * D, *hh = fst + NAX, *box = hh + D;
+    double *cornA = box + 2 * D, *cornJ = cornA + (NL + NH);     // half-products of the corner abscissae: [NL low | NH high]
 
     double sumI = 0.0, sumE = 0.0, maxE = 0.0;           // lane 0 accumulates this warp's boxes in todo order
     const long long ntodo = st->ntodo;
@@ -235,13 +239,30 @@ eval_kernel(Params p) {
             double u, jac;
             if (ALLFIN) { u = lbs[k] + (1.0 + tt) * dens[k]; jac = 1.0; }
             else { ib::AxisMap m; ib::make_axis(lbs[k], ubs[k], m); ib::t2ujac(p.tr, tt, m, u, jac); }
-            tabT[idx] = F::sep_term(k, u, par);
-            if (!ALLFIN) tabJ[idx] = jac;
+            const double T = F::sep_term(k, u, par);
+            tabT[idx] = FUSE ? T * jac : T;
+            if (SEPJ) tabJ[idx] = jac;
             if (o == 0) hh[k] = h;
         }
         __syncwarp();
+        // phase 1b: the 2^D corner points (+-lambda5 on every axis) are products of one entry per axis; tabulate the
+        // 2^(D/2) combinations of the low and of the high axes once, a corner is then ONE combination of each
+        for (int idx = lane; idx < NL + NH; idx += 32) {
+            const bool high = idx >= NL;
+            const int c = high ? idx - NL : idx, k0 = high ? DL : 0, nk = high ? DH : DL;
+            double acc = F::kProd ? 1.0 : 0.0, jac = 1.0;
+            for (int t = nk - 1; t >= 0; t--) {
+                const int ent = 7 * (k0 + t) + 5 + ((c >> t) & 1);
+                const double T = tabT[ent];
+                acc = F::kProd ? acc * T : acc + T;
+                if (SEPJ) jac *= tabJ[ent];
+            }
+            cornA[idx] = acc;
+            if (SEPJ) cornJ[idx] = jac;
+        }
+        __syncwarp();
         double sI = 0.0, sP = 0.0;
-        for (int q = lane; q < NP; q += 32) {                            // phase 2: points
+        for (int q = lane; q < NP - NCORN; q += 32) {                    // phase 2a: centre, axis and pair points
             const unsigned e = s_pt[q];
             double acc = finit, jac = 1.0;
 #pragma unroll
@@ -249,12 +270,19 @@ eval_kernel(Params p) {
                 const int sel = (e >> (3 * k)) & 7u;
                 const double T = tabT[7 * k + sel];
                 acc = F::kProd ? acc * T : acc + T;
-                if (!ALLFIN) { const double J = tabJ[7 * k + sel]; jac = (k == D - 1) ? J : jac * J; }
+                if (SEPJ) { const double J = tabJ[7 * k + sel]; jac = (k == D - 1) ? J : jac * J; }
             }
             const double f = F::sep_finish(acc, par) * (ALLFIN ? jacc : jac);
             if (q < NAX) fst[q] = f;
             const unsigned cls = e >> 24;
             sI = fma(s_w[cls], f, sI); sP = fma(s_w[5 + cls], f, sP);
+        }
+        for (int r = lane; r < NCORN; r += 32) {                         // phase 2b: corner points (rule weight class 4)
+            const int lo = r & (NL - 1), hi = NL + (r >> DL);
+            double acc = F::kProd ? finit * (cornA[hi] * cornA[lo]) : finit + (cornA[hi] + cornA[lo]);
+            const double jac = SEPJ ? cornJ[hi] * cornJ[lo] : 1.0;
+            const double f = F::sep_finish(acc, par) * (ALLFIN ? jacc : jac);
+            sI = fma(s_w[4], f, sI); sP = fma(s_w[9], f, sP);
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
@@ -353,7 +381,14 @@ decide_kernel(Params p) {
     State *st = p.st;
     if (st->done) return;
     __shared__ double s_cnt[kBins];
-    for (int b = threadIdx.x; b < kBins; b += kFin) { s_cnt[b] = (double)p.hist[b]; p.hist[b] = 0ull; }   // replicated store: local == global
+    __shared__ int s_bmin, s_bmax;
+    if (threadIdx.x == 0) { s_bmin = kBins; s_bmax = -1; }
+    __syncthreads();
+    for (int b = threadIdx.x; b < kBins; b += kFin) {            // replicated store: the local histogram is the global one
+        const unsigned long long c = p.hist[b];
+        s_cnt[b] = (double)c; p.hist[b] = 0ull;
+        if (c) { atomicMin(&s_bmin, b); atomicMax(&s_bmax, b); }
+    }
     __syncthreads();
     if (threadIdx.x != 0) return;
     double dI = 0.0, dE = 0.0, mx = 0.0;
@@ -375,30 +410,36 @@ decide_kernel(Params p) {
     if (ap >= (double)p.max_boxes || full > 0.0) { st->done = 1; st->status = IB200_ST_MAXEVALS; return; }
     st->bound = fmax(mx, st->theta);          // boxes left unsplit by the previous round are below its threshold
     double theta = 0.5 * st->bound;
+    // The three scans below are written for all kBins bins (oracle: orc_hcubature_rounds); empty bins change no sum, so
+    // only the occupied range [b0, b1] is walked, serially and in the same order -- the decision is bit-identical.
+    const int b0 = s_bmin, b1 = s_bmax < kBins - 2 ? s_bmax : kBins - 2;
     // (1) longest ascending prefix of bins whose lower-edge mass stays <= tol: bins 0..bh may stay unsplit
     //     edge(b) = 0 for b = 0, 2^(b-1023) otherwise
-    int bh = -1; double low = 0.0;
-    for (int b = 0; b < kBins - 1; b++) {
+    int bh = b0 - 1; double low = 0.0; bool broke = false;
+    for (int b = b0; b <= b1; b++) {
         const double c = s_cnt[b];
-        if (c != 0.0) { low += c * (b == 0 ? 0.0 : scalbn(1.0, b - 1023)); if (!(low <= tol)) break; }
+        if (c != 0.0) { low += c * (b == 0 ? 0.0 : scalbn(1.0, b - 1023)); if (!(low <= tol)) { broke = true; break; } }
         bh = b;
     }
+    if (!broke) bh = kBins - 2;
     // (2) budget: lowest bin bb such that bisecting every box in bins >= bb fits the remaining rule applications
     const double remaining = (double)p.max_boxes - ap;
-    int bb = kBins - 1; double above = 0.0;
-    for (int b = kBins - 2; b >= 0; b--) {
+    int bb = b1 + 1; double above = 0.0; broke = false;         // the (empty) bins above b1 have already lowered bb to b1 + 1
+    for (int b = b1; b >= b0; b--) {
         above += s_cnt[b];
-        if (2.0 * above > remaining) break;
+        if (2.0 * above > remaining) { broke = true; break; }
         bb = b;
     }
+    if (!broke) bb = 0;
     // (3) selectivity: at most `frac` of all stored boxes per round, largest errors first -- keeps the refinement
     //     close to the reference's worst-first order when the budget, not the tolerance, ends the solve
-    int bf = kBins - 1; double top = 0.0;
-    for (int b = kBins - 2; b >= 0; b--) {
+    int bf = b1 + 1; double top = 0.0; broke = false;
+    for (int b = b1; b >= b0; b--) {
         top += s_cnt[b];
-        if (top > p.frac * nb) break;
+        if (top > p.frac * nb) { broke = true; break; }
         bf = b;
     }
+    if (!broke) bf = 0;
     if (bf > bb) bb = bf;
     const int bs = (bh + 1 > bb) ? bh + 1 : bb;               // bisect bins >= bs
     const double theta_h = bs <= 0 ? 0.0 : (bs >= kBins - 1 ? 1.7976931348623157e308 : scalbn(1.0, bs - 1023));
