@@ -209,6 +209,135 @@ __device__ __forceinline__ void gm_rule_thread(const double *pc, int tr, const d
 }
 
 // ------------------------------------------------------------------------------------------------
+// Genz-Malik rule for the oscillatory family cos(2 pi u_1 + sum a_k x_k) on a finite domain, by angle addition.
+// Every point of the rule is the box centre moved by +-delta on at most two axes, or by +-delta_5 on all of them, so
+// its phase is S_c + sum(+-theta_k) with theta_k = a_k * (lambda h_k) * den_k.  One sincos of S_c and of the 3 D
+// angles theta_k(lambda_2, lambda_3, lambda_5) (13 in 4-D, evaluated four at a time in lock step) replaces the 2^D + 2 D^2
+// + 2 D + 1 cosines (57): a point then costs 2-7 multiply-adds.  The integrand is still formed at every point and
+// enters the sums of the reference's rule (f1 .. f5, fourth differences); values differ from cos-of-the-sum by ~1 ulp of 1.
+// SURVEY 8(d) strength-reduction caveat; measured on config 4: see DESIGN.md section 4.
+// ------------------------------------------------------------------------------------------------
+template <int D>
+__device__ __forceinline__ void gm_rule_thread_osc(const double *pc, const double (&a)[D], const double (&b)[D],
+                                                   double &Iout, double &Eout, int &kdiv) {
+    constexpr int NPAR = ib::fam_nparam(IB200_FAM_GENZ_OSC, D);
+    const double *par = pc, *lbs = pc + NPAR, *den = lbs + D;
+    const double finit = den[D], jacc = den[D + 1];
+    const double l2 = sqrt(9.0 / 70.0), l3 = sqrt(9.0 / 10.0), l5 = sqrt(9.0 / 19.0);
+    constexpr double twon = (double)(1 << D);
+    constexpr double w1 = twon * ((12824 - 9120 * D + 400 * D * D) / 19683.0);
+    constexpr double w2 = twon * (980 / 6561.0);
+    constexpr double w3 = twon * ((1820 - 400 * D) / 19683.0);
+    constexpr double w4 = twon * (200 / 19683.0);
+    constexpr double w5 = 6859 / 19683.0;
+    constexpr double w4p = twon * (25 / 729.0);
+    constexpr double w3p = twon * ((265 - 100 * D) / 1458.0);
+    constexpr double w2p = twon * (245 / 486.0);
+    constexpr double w1p = twon * ((729 - 950 * D + 50 * D * D) / 729.0);
+
+    double h[D], V = 1.0, S = finit;
+    double ang[3 * D + 1];                       // [theta_k(l2) | theta_k(l3) | theta_k(l5) | S_c]
+    {
+        double T0[D];
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            const double c = 0.5 * (a[k] + b[k]);
+            h[k] = 0.5 * fabs(b[k] - a[k]);
+            V = (k == 0) ? h[0] : V * h[k];
+            T0[k] = par[k] * (lbs[k] + (1.0 + c) * den[k]);
+            const double g = par[k] * den[k];
+            ang[k] = g * (h[k] * l2); ang[D + k] = g * (h[k] * l3); ang[2 * D + k] = g * (h[k] * l5);
+        }
+#pragma unroll
+        for (int k = D - 1; k >= 0; k--) S = S + T0[k];
+        ang[3 * D] = S;
+    }
+    double sn[3 * D + 1], cs[3 * D + 1];
+    {
+        constexpr int NA = 3 * D + 1;
+#pragma unroll
+        for (int g0 = 0; g0 < NA; g0 += 4) {
+            double x4[4], s4[4], c4[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) x4[j] = ang[g0 + j < NA ? g0 + j : NA - 1];
+            ib::sincos_bfN<4>(x4, s4, c4);
+#pragma unroll
+            for (int j = 0; j < 4; j++) if (g0 + j < NA) { sn[g0 + j] = s4[j]; cs[g0 + j] = c4[j]; }
+        }
+    }
+    const double cS = cs[3 * D], sS = sn[3 * D];
+    const double f1 = cS;
+    const double twelvef1 = 12 * f1;
+    // axis points: cos(S +- theta) = cS cos(theta) -+ sS sin(theta)
+    double divdiff[D], f2 = 0.0, f3 = 0.0;
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+        const double c2 = cS * cs[i], s2 = sS * sn[i], c3 = cS * cs[D + i], s3 = sS * sn[D + i];
+        const double f2i = (c2 - s2) + (c2 + s2);
+        const double f3i = (c3 - s3) + (c3 + s3);
+        f2 += f2i; f3 += f3i;
+        divdiff[i] = fabs(f3i + twelvef1 - 7 * f2i);
+    }
+    // pair points: S +- theta_i +- theta_j at lambda_3
+    double f4 = 0.0;
+#pragma unroll
+    for (int i = 0; i < D - 1; i++) {
+#pragma unroll
+        for (int j = i + 1; j < D; j++) {
+            const double cc = cs[D + i] * cs[D + j], ss = sn[D + i] * sn[D + j], sc = sn[D + i] * cs[D + j], csn = cs[D + i] * sn[D + j];
+            const double cp = cc - ss, cm = cc + ss, sp = sc + csn, sm = sc - csn;   // cos / sin of theta_i +- theta_j
+            const double A = cS * cp, B = sS * sp, C = cS * cm, Dd = sS * sm;
+            f4 += A - B;        // (+, +)
+            f4 += C - Dd;       // (+, -)
+            f4 += C + Dd;       // (-, +)
+            f4 += A + B;        // (-, -)
+        }
+    }
+    // corner points: S + sum_k +-theta_k(l5).  Unit vectors e^{i(+theta_{D-1} +- ... +- theta_0)} are built axis by axis (the
+    // combinations with -theta_{D-1} are their conjugates): 2^(D-1) complex numbers, two points each.
+    double f5 = 0.0;
+    {
+        double re[1 << (D - 1)], im[1 << (D - 1)];
+        re[0] = cs[2 * D + D - 1]; im[0] = sn[2 * D + D - 1];
+#pragma unroll
+        for (int k = D - 2; k >= 0; k--) {
+            const int m = 1 << (D - 2 - k);                     // combinations so far
+            const double ck = cs[2 * D + k], sk = sn[2 * D + k];
+#pragma unroll
+            for (int t = m - 1; t >= 0; t--) {
+                const double r0 = re[t], i0 = im[t];
+                const double rc = r0 * ck, is = i0 * sk, rs = r0 * sk, ic = i0 * ck;
+                re[2 * t] = rc - is; im[2 * t] = ic + rs;       // * e^{+i theta_k}
+                re[2 * t + 1] = rc + is; im[2 * t + 1] = ic - rs;   // * e^{-i theta_k}
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < (1 << (D - 1)); t++) {
+            const double A = cS * re[t], B = sS * im[t];
+            f5 += A - B;                                        // cos(S + phi_t)
+            f5 += A + B;                                        // cos(S - phi_t)
+        }
+    }
+    const double Vj = V * jacc;                                 // the constant Jacobian of the finite map, factored out of the sums
+    const double Iv = Vj * (w1 * f1 + w2 * f2 + w3 * f3 + w4 * f4 + w5 * f5);
+    const double Ip = Vj * (w1p * f1 + w2p * f2 + w3p * f3 + w4p * f4);
+    const double Er = fabs(Iv - Ip);
+    double p10 = 1.0;
+#pragma unroll
+    for (int k = 0; k < D; k++) p10 *= 10.0;
+    const double deltaf = Er / (p10 * V);
+    int kdv = 0; double maxdd = 0.0, hkd = h[0];
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+        const double dd = divdiff[k] * fabs(jacc);              // fourth differences of g = f * jacc
+        const double delta = dd - maxdd;
+        if (delta > deltaf) { kdv = k; maxdd = dd; hkd = h[k]; }
+        else if (fabs(delta) <= deltaf && h[k] > hkd) { kdv = k; hkd = h[k]; }
+    }
+    Iout = Iv; Eout = Er; kdiv = kdv;
+}
+
+// ------------------------------------------------------------------------------------------------
 // D == 1: the pair machinery runs QuadGK (QuadGK.quadgk as called at src/Integrals.jl:327-335; oracle: orc_quadgk).
 // One application of the (7,15) Gauss-Kronrod rule to the segment (a, b) by one thread, summed in QuadGK's order
 // (symmetric pairs first; oracle gk_evalrule).
@@ -535,6 +664,7 @@ hcub_pair_kernel(const Params p) {
         double Ic = 0.0, Ec = 0.0; int kc = 0;
         if (have) {
             if constexpr (D == 1) gk_rule_thread<FAM, ALLFIN>(pc, p.tr, a[0], b[0], Ic, Ec);
+            else if constexpr (FAM == IB200_FAM_GENZ_OSC && ALLFIN) gm_rule_thread_osc<D>(pc, a, b, Ic, Ec, kc);
             else gm_rule_thread<FAM, D, ALLFIN>(pc, p.tr, a, b, Ic, Ec, kc);
         }
 
