@@ -513,6 +513,57 @@ template <int D> struct Family<IB200_FAM_EXPLIN, D> {
 };
 
 // ------------------------------------------------------------------------------------------------
+// The separable terms of one axis at the 7 abscissae of the Genz-Malik rule, evaluated together.  Default: 7 calls of
+// sep_term.  Product peak: the 7 reciprocals 1 / (t_j^2 + a^-2) share ONE division (prefix products, one reciprocal,
+// back-substitution: 18 multiplies) -- ncu showed 33 divisions per box, each a MUFU.RCP64H + 8 FP64 instructions + a
+// guarded slow path, 29 % of the kernel's instructions (profiles/r01b_pair_genz_product_peak_*).  Exponential families:
+// the 7 exponentials run in lock step (independent polynomial chains side by side).
+// ------------------------------------------------------------------------------------------------
+template <int FAM, int D> struct Terms7 {
+    __device__ __forceinline__ static void run(int k, const double (&u)[7], const double *par, double (&T)[7]) {
+#pragma unroll
+        for (int j = 0; j < 7; j++) T[j] = Family<FAM, D>::sep_term(k, u[j], par);
+    }
+};
+template <int D> struct Terms7<IB200_FAM_GENZ_PROD, D> {
+    __device__ __forceinline__ static void run(int k, const double (&u)[7], const double *par, double (&T)[7]) {
+        const double ainv2 = 1.0 / (par[k] * par[k]);
+        double d[7], pre[7];
+        bool safe = ainv2 > 1e-40 && ainv2 < 1e40;           // products of 7 denominators stay far from over/underflow
+#pragma unroll
+        for (int j = 0; j < 7; j++) { const double t = u[j] - par[D + k]; d[j] = fma(t, t, ainv2); safe = safe && d[j] < 1e40; }
+        if (safe) {
+            pre[0] = d[0];
+#pragma unroll
+            for (int j = 1; j < 7; j++) pre[j] = pre[j - 1] * d[j];
+            double inv = 1.0 / pre[6];                        // 1 / (d0 ... d6)
+#pragma unroll
+            for (int j = 6; j >= 1; j--) { T[j] = inv * pre[j - 1]; inv = inv * d[j]; }
+            T[0] = inv;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 7; j++) T[j] = 1.0 / d[j];
+        }
+    }
+};
+template <int D> struct Terms7<IB200_FAM_GENZ_GAUSS, D> {
+    __device__ __forceinline__ static void run(int k, const double (&u)[7], const double *par, double (&T)[7]) {
+        double x[7];
+#pragma unroll
+        for (int j = 0; j < 7; j++) { const double t = par[k] * (u[j] - par[D + k]); x[j] = -(t * t); }
+        exp_bfN<7>(x, T);
+    }
+};
+template <int D> struct Terms7<IB200_FAM_GENZ_C0, D> {
+    __device__ __forceinline__ static void run(int k, const double (&u)[7], const double *par, double (&T)[7]) {
+        double x[7];
+#pragma unroll
+        for (int j = 0; j < 7; j++) x[j] = -(par[k] * fabs(u[j] - par[D + k]));
+        exp_bfN<7>(x, T);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
 // Transformed integrand g(t) = f(u(t), p) * prod_k jac_k(t_k)   (infinity_handling.jl:11-25).
 // ALLFIN: every axis finite -> u = lb + (1+t)*den, jac = prod den (precomputed constant jacc).
 // ------------------------------------------------------------------------------------------------

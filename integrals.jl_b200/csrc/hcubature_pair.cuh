@@ -89,13 +89,23 @@ __device__ __forceinline__ void gm_rule_thread(const double *pc, int tr, const d
         h[k] = 0.5 * fabs(b[k] - a[k]);
         V = (k == 0) ? h[0] : V * h[k];
     }
-    // separable term (and Jacobian factor) of abscissa t on axis k
-    auto term = [&](int k, double t, double &T, double &J) {
-        double u;
-        if (ALLFIN) { u = lbs[k] + (1.0 + t) * aux[k]; J = 1.0; }
-        else { ib::AxisMap m; ib::make_axis(lbs[k], aux[k], m); ib::t2ujac(tr, t, m, u, J); }
-        T = F::sep_term(k, u, par);
-    };
+    // separable terms (and Jacobian factors) of the 7 abscissae of every axis: c, c +- l2 h, c +- l3 h, c +- l5 h
+    // (family.cuh Terms7: one division per axis for the product peak, lock-step exponentials for the exp families)
+    double T0[D], J0[D], T2p[D], T2m[D], J2p[D], J2m[D], T3p[D], T3m[D], J3p[D], J3m[D], T5p[D], T5m[D], J5p[D], J5m[D];
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+        const double p2 = h[k] * l2, p3 = h[k] * l3, p5 = h[k] * l5;
+        const double t7[7] = {c[k], c[k] + p2, c[k] - p2, c[k] + p3, c[k] - p3, c[k] + p5, c[k] - p5};
+        double u7[7], j7[7], T7[7];
+#pragma unroll
+        for (int j = 0; j < 7; j++) {
+            if (ALLFIN) { u7[j] = lbs[k] + (1.0 + t7[j]) * aux[k]; j7[j] = 1.0; }
+            else { ib::AxisMap m; ib::make_axis(lbs[k], aux[k], m); ib::t2ujac(tr, t7[j], m, u7[j], j7[j]); }
+        }
+        ib::Terms7<FAM, D>::run(k, u7, par, T7);
+        T0[k] = T7[0]; T2p[k] = T7[1]; T2m[k] = T7[2]; T3p[k] = T7[3]; T3m[k] = T7[4]; T5p[k] = T7[5]; T5m[k] = T7[6];
+        J0[k] = j7[0]; J2p[k] = j7[1]; J2m[k] = j7[2]; J3p[k] = j7[3]; J3m[k] = j7[4]; J5p[k] = j7[5]; J5m[k] = j7[6];
+    }
     // f = finish(init (+|*) T_{D-1} ... (+|*) T_0) * jac ; folding from the last axis down lets the
     // compiler share prefixes between consecutive points (the first axis toggles fastest).  The
     // transcendental is applied to four points at a time in lock step (family.cuh sep_finishN).
@@ -113,9 +123,6 @@ __device__ __forceinline__ void gm_rule_thread(const double *pc, int tr, const d
         for (int j = 0; j < 4; j++) f[j] = f[j] * (ALLFIN ? jacc : jac[j]);
     };
 
-    double T0[D], J0[D];
-#pragma unroll
-    for (int k = 0; k < D; k++) term(k, c[k], T0[k], J0[k]);
     double f1;
     {
         double acc, jac;
@@ -124,20 +131,17 @@ __device__ __forceinline__ void gm_rule_thread(const double *pc, int tr, const d
     }
     const double twelvef1 = 12 * f1;
 
-    double T3p[D], T3m[D], J3p[D], J3m[D], divdiff[D];
+    double divdiff[D];
     double f2 = 0.0, f3 = 0.0;
 #pragma unroll
     for (int i = 0; i < D; i++) {
-        const double p2 = h[i] * l2, p3 = h[i] * l3;
         double Tt[D], Jt[D], acc[4], jac[4], f[4];
 #pragma unroll
         for (int k = 0; k < D; k++) { Tt[k] = T0[k]; Jt[k] = J0[k]; }
-        term(i, c[i] + p2, Tt[i], Jt[i]);
+        Tt[i] = T2p[i]; Jt[i] = J2p[i];
         fold(Tt, Jt, acc[0], jac[0]);
-        term(i, c[i] - p2, Tt[i], Jt[i]);
+        Tt[i] = T2m[i]; Jt[i] = J2m[i];
         fold(Tt, Jt, acc[1], jac[1]);
-        term(i, c[i] + p3, T3p[i], J3p[i]);
-        term(i, c[i] - p3, T3m[i], J3m[i]);
         Tt[i] = T3p[i]; Jt[i] = J3p[i];
         fold(Tt, Jt, acc[2], jac[2]);
         Tt[i] = T3m[i]; Jt[i] = J3m[i];
@@ -167,13 +171,6 @@ __device__ __forceinline__ void gm_rule_thread(const double *pc, int tr, const d
 #pragma unroll
             for (int s = 0; s < 4; s++) f4 += f[s];
         }
-    }
-    double T5p[D], T5m[D], J5p[D], J5m[D];
-#pragma unroll
-    for (int k = 0; k < D; k++) {
-        const double p5 = h[k] * l5;
-        term(k, c[k] + p5, T5p[k], J5p[k]);
-        term(k, c[k] - p5, T5m[k], J5m[k]);
     }
     double f5 = 0.0;
 #pragma unroll
