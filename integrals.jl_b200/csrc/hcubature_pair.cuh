@@ -17,11 +17,14 @@
 //     maxima (global), maxima of 1024-box blocks (shared).  Every level also stores WHERE its maximum
 //     sits, so the slot of the worst box falls out of the shared-memory scan alone and the only
 //     global load in front of the rule evaluation is the 16(d+1)-byte box record.  The two 32-entry
-//     groups on the selected path are L2-prefetched before the evaluation and scanned after it for
-//     their runner-ups (each lane scans half a group with 128-bit loads); the maxima along the path are
-//     then repaired from registers;
+//     groups on the selected path are staged into shared memory with cp.async while the rule runs and
+//     scanned after it for their runner-ups; the maxima along the path are then repaired from registers;
 //   * finished problems are re-summed by the whole warp (coalesced), then the pair pulls the next
-//     problem from the global atomic counter.
+//     problem from the global atomic counter -- in longest-expected-first order when a pilot pass ran
+//     (lpt_bucket below, hcubature.cu);
+//   * per-family rule specialisations: exponential families multiply per-axis factors, the 7 terms of
+//     an axis are evaluated together (family.cuh Terms7), the oscillatory family uses angle addition
+//     (gm_rule_thread_osc).
 #pragma once
 #include "hcubature_impl.cuh"
 
@@ -398,25 +401,7 @@ struct Cand { unsigned long long k; int idx; };
 __device__ __forceinline__ bool beats(const Cand &x, const Cand &y) {     // x strictly better than y
     return x.idx != NONE && (y.idx == NONE || x.k > y.k || (x.k == y.k && x.idx < y.idx));
 }
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// best entry of this lane's half (16 entries) of the 32-entry group at `base` of `arr` (n valid
-// entries overall), skipping group position `excl`; idx is the group position 0..31
-__device__ __forceinline__ Cand scan_half_excl(const double *arr, int base, int n, int half, int excl) {
-    Cand r; r.k = 0ULL; r.idx = NONE;
-    const int e0 = base + half * 16;
-    const double2 *p = reinterpret_cast<const double2 *>(arr + e0);
-    double2 v[8];
-#pragma unroll
-    for (int t = 0; t < 8; t++) if (e0 + 2 * t < n) v[t] = __ldcg(p + t);
-#pragma unroll
-    for (int t = 0; t < 8; t++) {
-        const int ia = half * 16 + 2 * t, ib_ = ia + 1;
-        if (e0 + 2 * t < n && ia != excl) { const unsigned long long k = dk(v[t].x); if (r.idx == NONE || k > r.k) { r.k = k; r.idx = ia; } }
-        if (e0 + 2 * t + 1 < n && ib_ != excl) { const unsigned long long k = dk(v[t].y); if (r.idx == NONE || k > r.k) { r.k = k; r.idx = ib_; } }
-    }
-    return r;
-}
 // The two 32-entry groups on the selected path are needed only AFTER the rule evaluation (runner-up scans).  They are
 // staged into this lane's shared-memory slot with cp.async while the rule runs, so the scans read shared memory instead
 // of waiting on L2/DRAM (ncu, profiles/r01_hcub_pair_prod_c4_*: 31 % of the stall samples sat on these loads).
@@ -432,7 +417,8 @@ __device__ __forceinline__ void stage_half(double *stage, const double *arr, int
 #pragma unroll
     for (int t = 0; t < 8; t++) if (e0 + 2 * t < n) cp_async16(stage + 2 * t, arr + e0 + 2 * t);
 }
-// scan_half_excl on staged data
+// best entry of this lane's half (16 entries) of a staged 32-entry group (n valid entries overall), skipping group
+// position `excl`; idx is the group position 0..31
 __device__ __forceinline__ Cand scan_staged_excl(const double *stage, int base, int n, int half, int excl) {
     Cand r; r.k = 0ULL; r.idx = NONE;
     const int e0 = base + half * 16;
