@@ -138,6 +138,9 @@ class Engine:
         self._check(self.L.ib200_synchronize(self.h))
 
     def set_stream(self, stream_ptr):
+        """Run the engine's kernels on the caller's CUDA stream (0 = back to the context's own stream).  Device-pointer
+        arguments are read on the engine's stream: either join the streams with this call (bench.py does) or synchronise
+        the producer (e.g. torch.cuda.synchronize()) before a solve."""
         self._check(self.L.ib200_set_stream(self.h, stream_ptr))
 
     def set_option(self, key, value):
