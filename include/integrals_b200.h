@@ -138,6 +138,18 @@ int32_t ib200_hcubature_batch(ib200_ctx *ctx, int32_t family, int32_t dim, int32
                               double reltol, double abstol, int64_t maxevals, int32_t initdiv,
                               double *out_I, double *out_E, int64_t *out_nevals, int32_t *out_status);
 
+/* -- vector-valued integrands: QuadGK.quadgk!(f!, result, lb, ub; ..., norm) as called from
+      __solvebp_call(::QuadGKJL) for array-valued integrands, src/Integrals.jl:316-326, with QuadGKJL.norm
+      (src/algorithms.jl:10-11,56; default LinearAlgebra.norm).  Component c of problem k is the registered family with
+      parameter column params[:, c, k] (params: nparam x ncomp x nprob, column-major); all components share the nodes and
+      the subdivision; a segment's error is norm(K - G) over the components; stop when E <= max(atol, rtol * norm(I)).
+      normkind: 0 = 2-norm, 1 = maximum norm.  1 <= ncomp <= 8.  out_I: ncomp x nprob; out_E, out_nevals, out_status: nprob. */
+int32_t ib200_quadgk_vec_batch(ib200_ctx *ctx, int32_t family, int32_t transform,
+                               const double *lb, const double *ub, int32_t bounds_per_problem,
+                               const double *params, int32_t nparam, int32_t ncomp, int64_t nprob,
+                               double reltol, double abstol, int64_t maxevals, int32_t normkind,
+                               double *out_I, double *out_E, int64_t *out_nevals, int32_t *out_status);
+
 /* -- one large domain (BASELINE config 5): the same HCubature call, src/Integrals.jl:386-393, for a single
       integral that is too expensive for one warp: region-parallel rounds on a device-resident box queue
       (csrc/hcub_single.cu).  With a communicator (ib200_comm_init) every rank of the job calls this with the

@@ -10,7 +10,7 @@ from ._lib import (Engine, IB200Error, FAMILY_IDS, TRANSFORM_IDS, RULE_IDS, SYMB
                    MAXEVALS_UNBOUNDED, default_engine, load_library)
 from .build import build_library
 from .integrands import (RegisteredIntegrand, SinXP, GenzOscillatory, GenzProductPeak, GenzCornerPeak, GenzGaussian,
-                         GenzC0, GenzDiscontinuous, CosProduct, GaussPoly, ExpLinear, GLTest, ALL_INTEGRANDS)
+                         GenzC0, GenzDiscontinuous, CosProduct, GaussPoly, ExpLinear, GLTest, VectorOf, ALL_INTEGRANDS)
 from .interface import (IntegralProblem, SampledIntegralProblem, IntegralSolution, IntegralCache, SampledIntegralCache,
                         Range, ReturnCode, CommonKwargError, ChangeOfVariables, transformation_if_inf,
                         transformation_tan_inf, transformation_cot_inf, QuadGKB200, HCubatureB200, QuadratureRuleB200,

@@ -24,7 +24,7 @@ ERR_NAMES = {-1: "IB200_ERR_INVALID", -2: "IB200_ERR_CUDA", -3: "IB200_ERR_OOM",
 SYMBOLS = ["ib200_version", "ib200_create", "ib200_destroy", "ib200_last_error", "ib200_set_stream",
            "ib200_synchronize", "ib200_kernel_launches", "ib200_family_nparam", "ib200_last_kernel_ms",
            "ib200_set_option", "ib200_sampled", "ib200_sampled_f32", "ib200_fixed_rule_tensor_batch", "ib200_fixed_rule_nodes_batch",
-           "ib200_gauss_legendre_batch", "ib200_quadgk_batch", "ib200_hcubature_batch", "ib200_measure_fp64_peak",
+           "ib200_gauss_legendre_batch", "ib200_quadgk_batch", "ib200_quadgk_vec_batch", "ib200_hcubature_batch", "ib200_measure_fp64_peak",
            "ib200_hcubature_single", "ib200_comm_unique_id", "ib200_comm_init", "ib200_comm_destroy"]
 
 
@@ -69,6 +69,8 @@ def load_library():
     L.ib200_gauss_legendre_batch.restype = i32
     L.ib200_quadgk_batch.argtypes = [vp, i32, i32, vp, vp, i32, vp, i32, i64, dp, dp, i64, vp, vp, vp, vp]
     L.ib200_quadgk_batch.restype = i32
+    L.ib200_quadgk_vec_batch.argtypes = [vp, i32, i32, vp, vp, i32, vp, i32, i32, i64, dp, dp, i64, i32, vp, vp, vp, vp]
+    L.ib200_quadgk_vec_batch.restype = i32
     L.ib200_sampled_f32.argtypes = [vp, i32, vp, i64, i64, i64, C.c_float, vp, vp]; L.ib200_sampled_f32.restype = i32
     L.ib200_hcubature_batch.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp, i32, i64, dp, dp, i64, i32, vp, vp, vp, vp]
     L.ib200_hcubature_batch.restype = i32
@@ -139,8 +141,9 @@ class Engine:
 
     def set_stream(self, stream_ptr):
         """Run the engine's kernels on the caller's CUDA stream (0 = back to the context's own stream).  Device-pointer
-        arguments are read on the engine's stream: either join the streams with this call (bench.py does) or synchronise
-        the producer (e.g. torch.cuda.synchronize()) before a solve."""
+        arguments are read on the engine's stream.  That stream is a blocking one, so producers on the legacy default stream
+        (torch's default) are ordered before the solve implicitly; producers on any other stream join it with this call
+        (bench.py does) or synchronise first."""
         self._check(self.L.ib200_set_stream(self.h, stream_ptr))
 
     def set_option(self, key, value):
@@ -251,6 +254,28 @@ class Engine:
         self._check(self.L.ib200_quadgk_batch(self.h, family, transform, a[0][0], a[1][0], bpp, a[2][0], nparam, nprob,
                                               float(reltol), float(abstol), int(min(maxevals, MAXEVALS_UNBOUNDED)),
                                               a[3][0], a[4][0], a[5][0], a[6][0]))
+        return out_I, out_E, out_nevals, out_status
+
+    def quadgk_vec_batch(self, family, lb, ub, params, reltol=1e-8, abstol=1e-8, maxevals=MAXEVALS_UNBOUNDED, transform=0, norm="2"):
+        """Vector-valued QuadGK: params nparam x ncomp x nprob (column-major; nparam x ncomp = one problem).
+        -> I (ncomp x nprob, column-major), E (nprob), nevals, status."""
+        params = np.asfortranarray(params, dtype=np.float64)
+        if params.ndim == 2:
+            params = params.reshape(params.shape + (1,), order="F")
+        nparam, ncomp, nprob = params.shape
+        lb = np.ascontiguousarray(np.atleast_1d(lb), dtype=np.float64); ub = np.ascontiguousarray(np.atleast_1d(ub), dtype=np.float64)
+        if lb.size == 1:
+            bpp = 0
+        elif lb.size == nprob:
+            bpp = 1
+        else:
+            raise ValueError(f"bounds must be scalars or have {nprob} entries")
+        out_I = np.empty((ncomp, nprob), order="F"); out_E = np.empty(nprob)
+        out_nevals = np.empty(nprob, dtype=np.int64); out_status = np.empty(nprob, dtype=np.int32)
+        self._check(self.L.ib200_quadgk_vec_batch(self.h, family, transform, lb.ctypes.data, ub.ctypes.data, bpp, params.ctypes.data, nparam,
+                                                  ncomp, nprob, float(reltol), float(abstol), int(min(maxevals, MAXEVALS_UNBOUNDED)),
+                                                  {"2": 0, "inf": 1}[norm], out_I.ctypes.data, out_E.ctypes.data, out_nevals.ctypes.data,
+                                                  out_status.ctypes.data))
         return out_I, out_E, out_nevals, out_status
 
     def hcubature_batch(self, family, dim, lb, ub, params, reltol=1e-8, abstol=1e-8, maxevals=MAXEVALS_UNBOUNDED,

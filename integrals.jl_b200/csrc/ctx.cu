@@ -30,7 +30,10 @@ extern "C" int32_t ib200_create(int32_t device, ib200_ctx **out) {
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
-    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+    // a BLOCKING stream: work the caller enqueued on the legacy default stream (torch's default, a plain CuArray
+    // computation) is ordered before the engine's kernels without an explicit synchronisation; callers on other
+    // streams use ib200_set_stream
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamDefault) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
         cudaGetLastError();
         delete ctx;

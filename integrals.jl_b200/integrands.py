@@ -164,3 +164,29 @@ class GLTest(RegisteredIntegrand):
 
 ALL_INTEGRANDS = [SinXP, GenzOscillatory, GenzProductPeak, GenzCornerPeak, GenzGaussian, GenzC0, GenzDiscontinuous,
                   CosProduct, GaussPoly, ExpLinear, GLTest]
+
+
+class VectorOf(RegisteredIntegrand):
+    """Vector-valued integrand built from one registered family: component c is `base` with parameter column
+    p[:, c].  `prob.p` is nparam x ncomp (one problem, `sol.u` a vector of ncomp) or nparam x ncomp x nprob (a batch,
+    `sol.u` ncomp x nprob).  The reference's counterpart is an array-valued integrand with an `integrand_prototype`
+    (src/Integrals.jl:226-239, 316-326): all components share nodes and subdivision, the error is a norm over them."""
+
+    def __init__(self, base):
+        if not isinstance(base, RegisteredIntegrand) or isinstance(base, VectorOf):
+            raise TypeError("VectorOf wraps one registered scalar integrand")
+        self.base = base
+        self.name = base.name
+
+    def nparam(self, dim):
+        return self.base.nparam(dim)
+
+    def supports_dim(self, dim):
+        return dim == 1 and self.base.supports_dim(1)
+
+    def __call__(self, x, p):
+        p = np.asarray(p, dtype=float)
+        return np.array([self.base(x, p[:, c]) for c in range(p.shape[1])])
+
+    def __repr__(self):
+        return f"VectorOf({self.base!r})"

@@ -26,7 +26,7 @@ import math
 import numpy as np
 
 from . import _lib
-from .integrands import RegisteredIntegrand
+from .integrands import RegisteredIntegrand, VectorOf
 
 ALLOWED_KEYWORDS = ("maxiters", "abstol", "reltol")          # src/Integrals.jl:142
 
@@ -144,10 +144,13 @@ class AbstractB200Algorithm:
 class QuadGKB200(AbstractB200Algorithm):
     """Adaptive Gauss-Kronrod, drop-in for QuadGKJL (src/algorithms.jl:51-56); order 7 only."""
 
-    def __init__(self, order=7):
+    def __init__(self, order=7, norm="2"):
+        """norm: "2" (LinearAlgebra.norm, the QuadGKJL default) or "inf"; only used by vector-valued integrands (VectorOf)."""
         if order != 7:
             raise ValueError("QuadGKB200 implements the (7,15) Gauss-Kronrod pair only")
-        self.order = order
+        if norm not in ("2", "inf"):
+            raise ValueError('QuadGKB200 supports norm = "2" or "inf"')
+        self.order, self.norm = order, norm
 
 
 class HCubatureB200(AbstractB200Algorithm):
@@ -282,6 +285,8 @@ def solve_cache(cache):
     eng = cache.cacheval
     prob = IntegralProblem(cache.f, cache.domain, cache.p, **cache.prob_kwargs)     # build_problem, common.jl:255-257
     inner, tr = cache.alg.alg, cache.alg.fu2gv.id
+    if isinstance(cache.f, VectorOf):
+        return _solve_vector(cache, prob, inner, tr)
     dim, lb, ub, p, nprob, scalar = _problem_shapes(prob)
     fam = cache.f.family
     if not cache.f.supports_dim(dim):
@@ -330,6 +335,24 @@ def solve_cache(cache):
     if scalar and not hasattr(I, "data_ptr"):
         I = float(I[0]); E = None if E is None else float(E[0])
     return IntegralSolution(I, E, prob, inner, ReturnCode.Success, None, stats)   # Success unconditionally, Integrals.jl:338,396
+
+
+def _solve_vector(cache, prob, inner, tr):
+    """array-valued integrand (src/Integrals.jl:316-326): QuadGK with a norm over the components"""
+    if not isinstance(inner, QuadGKB200):
+        raise TypeError("vector-valued registered integrands (VectorOf) are integrated by QuadGKB200")
+    lb, ub = prob.domain
+    if np.ndim(lb) > 1 or (np.ndim(lb) == 1 and np.size(lb) != 1 and np.ndim(prob.p) != 3):
+        raise ValueError("QuadGKB200 only accepts one-dimensional quadrature problems.")
+    p = np.asarray(prob.p, dtype=np.float64)
+    if p.ndim not in (2, 3):
+        raise ValueError("VectorOf needs p of shape nparam x ncomp (or nparam x ncomp x nprob)")
+    kw = cache.kwargs
+    I, E, ne, st = cache.cacheval.quadgk_vec_batch(cache.f.family, lb, ub, p, reltol=kw.get("reltol", 1e-8), abstol=kw.get("abstol", 1e-8),
+                                                   maxevals=kw.get("maxiters", _lib.MAXEVALS_UNBOUNDED), transform=tr, norm=inner.norm)
+    if p.ndim == 2:
+        return IntegralSolution(I[:, 0].copy(), float(E[0]), prob, inner, ReturnCode.Success, None, dict(nevals=ne, status=st))
+    return IntegralSolution(I, E, prob, inner, ReturnCode.Success, None, dict(nevals=ne, status=st))
 
 
 # ---------------------------------------------------------------------------------------------

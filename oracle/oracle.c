@@ -567,6 +567,145 @@ int orc_quadgk(orc_integrand f, void *user, double a, double b, double rtol, dou
 }
 
 /* ------------------------------------------------------------------------------------------
+ * QuadGK with a vector-valued integrand: the reference reaches it through
+ * quadgk!(f!, result, lb, ub; norm = alg.norm) (src/Integrals.jl:316-326; QuadGKJL.norm defaults to
+ * LinearAlgebra.norm, src/algorithms.jl:10-11,56).  The rule is applied component-wise, the error of a segment
+ * is norm(Ik*s - Ig*s), the stopping test E <= max(atol, rtol*norm(I)); everything else is orc_quadgk.
+ * normkind: 0 = 2-norm (LinearAlgebra.norm), 1 = maximum norm.
+ * ------------------------------------------------------------------------------------------ */
+#define ORC_MAXCOMP 16
+typedef struct { double a, b, E; double I[ORC_MAXCOMP]; } orc_vseg;
+
+static double vnorm(const double *v, int n, int kind)
+{
+    double r = 0.0;
+    if (kind == 1) { for (int i = 0; i < n; i++) if (fabs(v[i]) > r || isnan(v[i])) r = fabs(v[i]); return r; }
+    /* LinearAlgebra.norm (generic_norm2) rescales by the maximum to avoid overflow; for the magnitudes of integrals
+       a plain sqrt(sum of squares) differs from it by rounding only */
+    for (int i = 0; i < n; i++) r += v[i] * v[i];
+    return sqrt(r);
+}
+
+static orc_vseg gk_evalrule_vec(orc_vec_integrand f, void *user, int nc, double a, double b, int normkind)
+{
+#define X(i) GK_X[(i) - 1]
+#define W(i) GK_W[(i) - 1]
+#define WG(i) GK_WG[(i) - 1]
+    double s = 0.5 * (b - a), x, fa[ORC_MAXCOMP], fb[ORC_MAXCOMP], fg[ORC_MAXCOMP], fk[ORC_MAXCOMP], Ig[ORC_MAXCOMP], Ik[ORC_MAXCOMP];
+#define PAIR(dst, xi) do { x = a + (1 + (xi)) * s; f(&x, 1, user, fa); x = a + (1 - (xi)) * s; f(&x, 1, user, fb); \
+                           for (int c = 0; c < nc; c++) dst[c] = fa[c] + fb[c]; } while (0)
+    PAIR(fg, X(2)); PAIR(fk, X(1));
+    for (int c = 0; c < nc; c++) { Ig[c] = fg[c] * WG(1); Ik[c] = fg[c] * W(2) + fk[c] * W(1); }
+    for (int i = 2; i <= 3; i++) {
+        PAIR(fg, X(2 * i)); PAIR(fk, X(2 * i - 1));
+        for (int c = 0; c < nc; c++) { Ig[c] += fg[c] * WG(i); Ik[c] += fg[c] * W(2 * i) + fk[c] * W(2 * i - 1); }
+    }
+    double f0[ORC_MAXCOMP];
+    x = a + s; f(&x, 1, user, f0);
+    PAIR(fk, X(7));
+    for (int c = 0; c < nc; c++) { Ig[c] += f0[c] * WG(4); Ik[c] += f0[c] * W(8) + fk[c] * W(7); }
+#undef PAIR
+#undef X
+#undef W
+#undef WG
+    orc_vseg r; double d[ORC_MAXCOMP];
+    r.a = a; r.b = b;
+    for (int c = 0; c < nc; c++) { r.I[c] = Ik[c] * s; d[c] = Ik[c] * s - Ig[c] * s; }
+    r.E = vnorm(d, nc, normkind);
+    return r;
+}
+
+static void vseg_down(orc_vseg *xs, int64_t i, orc_vseg x, int64_t len)
+{
+    int64_t l;
+    while ((l = 2 * i) <= len) {
+        int64_t r = l + 1;
+        int64_t j = (r > len || xs[l].E > xs[r].E) ? l : r;
+        if (!(xs[j].E > x.E)) break;
+        xs[i] = xs[j]; i = j;
+    }
+    xs[i] = x;
+}
+static void vseg_up(orc_vseg *xs, int64_t i, orc_vseg x)
+{
+    int64_t j;
+    while ((j = i / 2) >= 1 && x.E > xs[j].E) { xs[i] = xs[j]; i = j; }
+    xs[i] = x;
+}
+
+int orc_quadgk_vec(orc_vec_integrand f, void *user, int nc, double a, double b, double rtol, double atol,
+                   int64_t maxevals, int normkind, double *Iout, double *Eout, int64_t *nevals_out)
+{
+    if (nc < 1 || nc > ORC_MAXCOMP) return -1;
+    int status = 0;
+    orc_vseg s0 = gk_evalrule_vec(f, user, nc, a, b, normkind);
+    double I[ORC_MAXCOMP], E = s0.E;
+    for (int c = 0; c < nc; c++) I[c] = s0.I[c];
+    int64_t numevals = 15, cap = 64, len = 1;
+    if (rtol == 0 && atol == 0) rtol = sqrt(2.220446049250313e-16);
+    orc_vseg *segs = (orc_vseg *)malloc(sizeof(orc_vseg) * (size_t)(cap + 1));
+    segs[1] = s0;
+    if (isnan(E) || isinf(E)) status = 2;
+    else if (!(numevals >= maxevals || E <= atol || E <= rtol * vnorm(I, nc, normkind))) {
+        while (E > atol && E > rtol * vnorm(I, nc, normkind) && numevals < maxevals) {
+            orc_vseg s = segs[1];
+            orc_vseg y = segs[len--];
+            if (len >= 1) vseg_down(segs, 1, y, len);
+            double mid = (s.a + s.b) / 2;
+            if (gk_endpoint_roundoff(s.a, mid) || gk_endpoint_roundoff(mid, s.b)) { len++; vseg_up(segs, len, s); status = 3; break; }
+            orc_vseg s1 = gk_evalrule_vec(f, user, nc, s.a, mid, normkind);
+            orc_vseg s2 = gk_evalrule_vec(f, user, nc, mid, s.b, normkind);
+            for (int c = 0; c < nc; c++) I[c] = (I[c] - s.I[c]) + s1.I[c] + s2.I[c];
+            E = (E - s.E) + s1.E + s2.E;
+            numevals += 30;
+            if (isnan(s1.E) || isinf(s1.E) || isnan(s2.E) || isinf(s2.E)) status = 2;
+            if (len + 2 > cap) { cap *= 2; segs = (orc_vseg *)realloc(segs, sizeof(orc_vseg) * (size_t)(cap + 1)); }
+            len++; vseg_up(segs, len, s1);
+            len++; vseg_up(segs, len, s2);
+            if (status == 2) break;
+        }
+    }
+    for (int c = 0; c < nc; c++) I[c] = segs[1].I[c];
+    E = segs[1].E;
+    for (int64_t i = 2; i <= len; i++) { for (int c = 0; c < nc; c++) I[c] += segs[i].I[c]; E += segs[i].E; }
+    free(segs);
+    if (status == 0 && !(E <= atol || E <= rtol * vnorm(I, nc, normkind)) && numevals >= maxevals) status = 1;
+    for (int c = 0; c < nc; c++) Iout[c] = I[c];
+    *Eout = E;
+    if (nevals_out) *nevals_out = numevals;
+    return status;
+}
+
+/* batch driver over the registered family: component c of problem k uses parameter column params[:, c, k]; the
+   automatic ChangeOfVariables (common.jl:97-103) is applied to every component */
+typedef struct { int fam, nc, nparam, tr; const double *par; double lb, ub; } orc_vecfam_user;
+static void orc_vecfam_eval(const double *t, int dim, void *user, double *out)
+{
+    (void)dim;
+    const orc_vecfam_user *u = (const orc_vecfam_user *)user;
+    double x, jac;
+    orc_t2ujac(u->tr, t[0], u->lb, u->ub, &x, &jac);
+    for (int c = 0; c < u->nc; c++) out[c] = orc_family_eval(u->fam, 1, &x, u->par + (size_t)c * u->nparam) * jac;
+}
+int orc_quadgk_vec_batch(int fam, const double *lb, const double *ub, int bpp, int tr,
+                         const double *params, int nparam, int ncomp, int64_t nprob,
+                         double reltol, double abstol, int64_t maxiters, int normkind,
+                         double *I, double *E, int64_t *nevals, int32_t *status, int nthreads)
+{
+    if (nthreads < 1) nthreads = 1;
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads)
+    for (int64_t k = 0; k < nprob; k++) {
+        orc_vecfam_user u = {fam, ncomp, nparam, tr, params + (size_t)k * nparam * ncomp, bpp ? lb[k] : lb[0], bpp ? ub[k] : ub[0]};
+        double tl, tu;
+        orc_u2t(u.lb, u.ub, &tl, &tu);
+        int64_t ne = 0;
+        status[k] = orc_quadgk_vec(orc_vecfam_eval, &u, ncomp, tl, tu, reltol, abstol, maxiters, normkind, I + (size_t)k * ncomp, &E[k], &ne);
+        nevals[k] = ne;
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
  * HCubature.jl (un-vendored dependency; compat "1.7", Project.toml:60), called at
  * src/Integrals.jl:380-393.  Restated from the published algorithm:
  * Genz-Malik degree-7 rule with embedded degree-5 rule for dim>=2, GK(7,15) for dim==1,

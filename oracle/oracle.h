@@ -89,6 +89,17 @@ int orc_sampled_evalrule_f32(int rule, const float *y, int64_t inner, int64_t n,
    3 endpoint roundoff stopped refinement */
 int orc_quadgk(orc_integrand f, void *user, double a, double b, double rtol, double atol,
                int64_t maxevals, double *I, double *E, int64_t *nevals, int64_t *nsegs);
+/* QuadGK with a vector-valued integrand and a norm (quadgk!(f!, result, ...; norm), src/Integrals.jl:316-326):
+   f writes ncomp values; normkind 0 = 2-norm (LinearAlgebra.norm, the QuadGKJL default), 1 = maximum norm */
+typedef void (*orc_vec_integrand)(const double *x, int dim, void *user, double *out);
+int orc_quadgk_vec(orc_vec_integrand f, void *user, int ncomp, double a, double b, double rtol, double atol,
+                   int64_t maxevals, int normkind, double *I, double *E, int64_t *nevals);
+/* params: nparam x ncomp x nprob (column-major); I: ncomp x nprob; E: nprob */
+int orc_quadgk_vec_batch(int fam, const double *lb, const double *ub, int bounds_per_problem, int tr,
+                         const double *params, int nparam, int ncomp, int64_t nprob,
+                         double reltol, double abstol, int64_t maxiters, int normkind,
+                         double *I, double *E, int64_t *nevals, int32_t *status, int nthreads);
+
 /* HCubature.jl hcubature (dim>=2 Genz-Malik) / hquadrature (dim==1, GK15), norm = abs */
 int orc_hcubature(orc_integrand f, void *user, int dim, const double *a, const double *b,
                   double rtol, double atol, int64_t maxevals, int initdiv,

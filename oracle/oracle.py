@@ -276,6 +276,26 @@ def quadgk_batch(fam, lb, ub, params, tr="if_inf", reltol=1e-8, abstol=1e-8, max
     return I, E, ne, st
 
 
+def quadgk_vec_batch(fam, lb, ub, params, tr="if_inf", reltol=1e-8, abstol=1e-8, maxiters=2**62, norm="2", nthreads=1):
+    """vector-valued QuadGK: params nparam x ncomp x nprob (Fortran order); -> I (ncomp x nprob), E, nevals, status"""
+    fam = FAM[fam] if isinstance(fam, str) else fam
+    params = np.asfortranarray(params, dtype=np.float64)
+    if params.ndim == 2:
+        params = params.reshape(params.shape + (1,), order="F")
+    nparam, ncomp, nprob = params.shape
+    lb = _arr(np.atleast_1d(lb)); ub = _arr(np.atleast_1d(ub))
+    bpp = 1 if lb.size == nprob and nprob > 1 else 0
+    I = np.empty((ncomp, nprob), order="F"); E = np.empty(nprob); ne = np.empty(nprob, np.int64); st = np.empty(nprob, np.int32)
+    L = lib()
+    L.orc_quadgk_vec_batch.argtypes = [C.c_int, _dp, _dp, C.c_int, C.c_int, _dp, C.c_int, C.c_int, C.c_int64, C.c_double, C.c_double,
+                                       C.c_int64, C.c_int, _dp, _dp, _i64p, _i32p, C.c_int]
+    rc = L.orc_quadgk_vec_batch(fam, _p(lb), _p(ub), bpp, TR[tr], params.ctypes.data_as(_dp), nparam, ncomp, nprob, reltol, abstol,
+                                maxiters, 0 if norm == "2" else 1, I.ctypes.data_as(_dp), _p(E), ne.ctypes.data_as(_i64p),
+                                st.ctypes.data_as(_i32p), nthreads)
+    assert rc == 0, rc
+    return I, E, ne, st
+
+
 def hcubature_batch(fam, lb, ub, params, tr="if_inf", reltol=1e-8, abstol=1e-8, maxiters=2**62, initdiv=1, nthreads=1):
     lb = np.asarray(lb, dtype=np.float64); dim = lb.shape[0]
     fam, params, nparam, nprob, lb, ub, bpp = _batch_common(fam, dim, lb, ub, params)

@@ -58,7 +58,6 @@ def test_c2_sampled_full_size_properties(eng):
         x = (torch.arange(i0, i1, dtype=torch.float64, device="cuda") * h)[:, None]
         y[i0:i1] = c0 + x * (c1 + x * (c2 + x * c3))
     out = torch.empty(m, dtype=torch.float64, device="cuda")
-    torch.cuda.synchronize()
     exact = (c0 + c1 / 2 + c2 / 3 + c3 / 4).cpu().numpy()
     scale = (c0.abs() + c1.abs() + c2.abs() + c3.abs()).cpu().numpy()     # >= sum |w_i y_i| / 1
     eng.sampled("simpson", y, m, n, 1, h=h, out=out); eng.synchronize()
@@ -70,8 +69,7 @@ def test_c2_sampled_full_size_properties(eng):
     assert np.all(np.abs(trap - exact)[lin] <= 1e-12 * scale[lin])        # exact on the linear rows
     assert np.all(np.abs(trap - exact)[~lin] <= 2 * h * h * scale[~lin])  # O(h^2) elsewhere
     # constant samples: both rules return (n - 1) h = 1 times the constant
-    y.fill_(2.5)
-    torch.cuda.synchronize()            # the engine works on its own stream (Engine.set_stream joins it to torch's)
+    y.fill_(2.5)                        # no synchronisation: the engine's stream is ordered after torch's default stream
     for rule in ("trapezoid", "simpson"):
         eng.sampled(rule, y, m, n, 1, h=h, out=out); eng.synchronize()
         assert np.all(np.abs(out.cpu().numpy() - 2.5) <= 1e-12 * 2.5)

@@ -457,3 +457,42 @@ def test_sampled_float32_and_complex_through_solve(eng):
     re = ib.solve(ib.SampledIntegralProblem(yc.real.copy(), xc), ib.TrapezoidalB200(), engine=eng).u
     im = ib.solve(ib.SampledIntegralProblem(yc.imag.copy(), xc), ib.TrapezoidalB200(), engine=eng).u
     assert abs(sol.u - complex(re, im)) <= 4e-16 * abs(sol.u)      # different summation trees (strided vs contiguous kernel)
+
+
+# ------------------------------------------------------------------------------------- vector-valued QuadGK
+@pytest.mark.parametrize("ncomp", [1, 3, 4, 5, 8])
+@pytest.mark.parametrize("norm", ["2", "inf"])
+def test_quadgk_vector_valued_matches_oracle(eng, O, ncomp, norm):
+    """ib200_quadgk_vec_batch against orc_quadgk_vec (QuadGK with an array-valued integrand and a norm, src/Integrals.jl:316-326):
+    same refinement (evaluation counts) except at rounding-level ties, components within 1e-13 of the oracle's, closed forms
+    within the tolerance that the norm of the whole vector sets"""
+    nprob = 96
+    rng = np.random.default_rng(5)
+    p = np.asfortranarray(0.1 + 40.0 * rng.random((1, ncomp, nprob)))
+    I, E, ne, st = eng.quadgk_vec_batch(F["sinxp"], -2.0, 5.0, p, reltol=1e-10, abstol=1e-12, norm=norm)
+    Ir, Er, ner, str_ = O.quadgk_vec_batch("sinxp", -2.0, 5.0, p, reltol=1e-10, abstol=1e-12, norm=norm, nthreads=O.max_threads())
+    assert np.array_equal(st, str_) and np.all(st == 0) and np.mean(ne == ner) > 0.95
+    nI = np.linalg.norm(Ir, axis=0) if norm == "2" else np.abs(Ir).max(axis=0)
+    same = ne == ner
+    assert np.all(np.abs(I - Ir)[:, same] <= 1e-13 * np.maximum(nI[same], 1e-2))
+    assert np.all(np.abs(I - Ir) <= np.maximum(1e-12, 1e-10 * nI)) and np.all((E <= 4 * Er + 1e-300) & (Er <= 4 * E + 1e-300))
+    exact = (np.cos(-2 * p[0]) - np.cos(5 * p[0])) / p[0]
+    assert np.all(np.abs(I - exact) <= np.maximum(1e-12, 1e-10 * nI))
+    if ncomp == 1:       # one component is the scalar solver
+        Is, Es, nes, sts = eng.quadgk_batch(F["sinxp"], np.array([-2.0]), np.array([5.0]), p[:, 0, :], reltol=1e-10, abstol=1e-12)
+        assert np.array_equal(ne, nes) and np.allclose(I[0], Is, rtol=1e-14, atol=0) and np.allclose(E, Es, rtol=1e-9)
+
+
+def test_quadgk_vector_valued_infinite_domain_and_solve(eng, O):
+    par = np.asfortranarray(np.array([[1.0, 0.0], [2.0, 0.5], [0.7, -0.3]]).T.reshape(2, 3, 1))    # Lorentzians a / (1 + a^2 (x-u)^2) -> pi a
+    for tr, trn in enumerate(["if_inf", "tan", "cot"]):
+        I, E, ne, st = eng.quadgk_vec_batch(F["genz_product_peak"], -INF, INF, par, reltol=1e-9, abstol=0.0, transform=tr)
+        Ir, Er, ner, _ = O.quadgk_vec_batch("prodpeak", -INF, INF, par, tr=trn, reltol=1e-9, abstol=0.0)
+        assert st[0] == 0 and np.allclose(I[:, 0], math.pi * np.array([1.0, 2.0, 0.7]), rtol=1e-8) and np.allclose(I, Ir, rtol=1e-11)
+    sol = ib.solve(ib.IntegralProblem(ib.VectorOf(ib.SinXP()), (-2.0, 5.0), np.array([[1.7, 3.3, 20.0]])), ib.QuadGKB200(), engine=eng, reltol=1e-10)
+    ps = np.array([1.7, 3.3, 20.0])
+    assert sol.u.shape == (3,) and np.allclose(sol.u, (np.cos(-2 * ps) - np.cos(5 * ps)) / ps, rtol=0, atol=1e-9) and sol.resid < 1e-8
+    with pytest.raises(ib.IB200Error, match="ncomp"):
+        eng.quadgk_vec_batch(F["sinxp"], -2.0, 5.0, np.ones((1, 9, 2)))
+    I, E, ne, st = eng.quadgk_vec_batch(F["sinxp"], -2.0, 5.0, np.array([[50.0, 60.0]]), reltol=1e-13, abstol=0.0, maxevals=300)
+    assert st[0] == 1 and ne[0] == 315

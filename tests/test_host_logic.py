@@ -159,3 +159,24 @@ def test_sampled_float32_and_complex_routing():   # test/interface_tests.jl:501-
     assert e.calls[-1][0] == "sampled" and e.calls[-1][1][1:] == (2, 11, 1) and isinstance(sol.u, complex)
     sol = ib.solve(ib.SampledIntegralProblem(np.zeros((4, 11, 3), complex), ib.Range(0.0, 1.0, 11), dim=1), ib.SimpsonsB200(), engine=e)
     assert e.calls[-1][1][1:] == (8, 11, 3) and sol.u.shape == (4, 3) and np.iscomplexobj(sol.u)
+
+
+def test_vector_valued_routing():    # src/Integrals.jl:316-326 (array-valued integrand, QuadGKJL.norm)
+    class EV(StubEngine):
+        def quadgk_vec_batch(self, fam, lb, ub, p, **k):
+            self._rec("quadgk_vec", fam, lb, ub, p, **k)
+            p = np.asarray(p); nc = p.shape[1]; n = p.shape[2] if p.ndim == 3 else 1
+            return np.zeros((nc, n), order="F"), np.zeros(n), np.zeros(n, np.int64), np.zeros(n, np.int32)
+    e = EV()
+    f = ib.VectorOf(ib.SinXP())
+    sol = ib.solve(ib.IntegralProblem(f, (-2.0, 5.0), np.array([[1.7, 3.3, 0.5]])), ib.QuadGKB200(norm="inf"), engine=e, reltol=1e-9)
+    name, a, k = e.calls[-1]
+    assert name == "quadgk_vec" and k["norm"] == "inf" and k["reltol"] == 1e-9 and sol.u.shape == (3,) and isinstance(sol.resid, float)
+    sol = ib.solve(ib.IntegralProblem(f, (-2.0, 5.0), np.zeros((1, 3, 7))), ib.QuadGKB200(), engine=e)
+    assert sol.u.shape == (3, 7) and sol.resid.shape == (7,) and e.calls[-1][2]["norm"] == "2"
+    with pytest.raises(TypeError, match="QuadGKB200"):
+        ib.solve(ib.IntegralProblem(f, (-2.0, 5.0), np.zeros((1, 3))), ib.GaussLegendreB200(n=4), engine=e)
+    with pytest.raises(ValueError):
+        ib.QuadGKB200(norm="1")
+    with pytest.raises(TypeError):
+        ib.VectorOf(ib.VectorOf(ib.SinXP()))

@@ -293,3 +293,23 @@ def test_sampled_float32_restatement():   # test/interface_tests.jl:524-539 sema
                 # float weights/products/sequential sum vs the float64 rule on the same (float32-representable) inputs
                 cond = 30 if (rule == "simpson" and "x" in kw) else 4        # non-uniform Simpson weights cancel in float
                 assert abs(float(got) - ref) <= cond * n * 6e-8 * float(np.sum(np.abs(w64 * y)))
+
+
+def test_quadgk_vector_valued_restatement():
+    """orc_quadgk_vec (quadgk! with a norm, src/Integrals.jl:316-326): one component reproduces the scalar solver exactly; several
+    components share the subdivision and each meets the closed form within the tolerance set by the norm of the whole vector"""
+    p1 = np.array([[20.0]]).reshape(1, 1, 1)
+    Iv, Ev, nev, stv = O.quadgk_vec_batch("sinxp", -2.0, 5.0, p1, reltol=1e-10, abstol=1e-12)
+    Is, Es, nes, sts = O.quadgk_batch("sinxp", -2.0, 5.0, np.array([[20.0]]), reltol=1e-10, abstol=1e-12)
+    assert Iv[0, 0] == Is[0] and Ev[0] == Es[0] and nev[0] == nes[0] and stv[0] == sts[0] == 0
+    ps = np.array([1.7, 3.3, 0.5, 20.0])
+    for norm in ("2", "inf"):
+        I, E, ne, st = O.quadgk_vec_batch("sinxp", -2.0, 5.0, ps.reshape(1, 4, 1), reltol=1e-10, abstol=0.0, norm=norm)
+        exact = (np.cos(-2 * ps) - np.cos(5 * ps)) / ps
+        nI = np.linalg.norm(exact) if norm == "2" else np.abs(exact).max()
+        assert st[0] == 0 and E[0] <= 1e-10 * nI * (1 + 1e-12) and np.all(np.abs(I[:, 0] - exact) <= 1e-10 * nI)
+        assert ne[0] < nes[0]            # the easy components ride on the subdivision the hard one needs -- but the norm test stops earlier
+    # Lorentzians over the real line through the automatic change of variables (test/inf_integral_tests.jl:85-150 integrands)
+    par = np.array([[1.0, 0.0], [2.0, 0.5]]).T.reshape(2, 2, 1)
+    I, E, ne, st = O.quadgk_vec_batch("prodpeak", -INF, INF, par, reltol=1e-9, abstol=0.0)
+    assert st[0] == 0 and np.allclose(I[:, 0], [math.pi * 1.0, math.pi * 2.0], rtol=1e-8)
