@@ -273,12 +273,12 @@ def main():
         return float(t.item())
 
     # -------------------------------------------------------------------------------- workloads
-    def make_c4():
+    def make_c4(scale=1.0):
         c = WL.C4; d = c["dim"]
         nper = args.nprob or c["nprob_per_family"]
         host, dev = {}, {}
         for fam in WL.GENZ:
-            par = WL.genz_params(fam, d, nper, seed=WL.SEED + 1000 * rank)
+            par = WL.genz_params(fam, d, nper, seed=WL.SEED + 1000 * rank, scale=scale)
             pinned = torch.from_numpy(np.ascontiguousarray(par.T)).pin_memory()        # [nprob, 2d] == 2d x nprob col-major
             host[fam] = pinned
             dev[fam] = dict(par=pinned.cuda(), I=torch.empty(nper, dtype=torch.float64, device="cuda"),
@@ -327,8 +327,10 @@ def main():
     ib_marker = {"genz_oscillatory": "GenzOscillatory", "genz_product_peak": "GenzProductPeak", "genz_corner_peak": "GenzCornerPeak",
                  "genz_gaussian": "GenzGaussian", "genz_c0": "GenzC0", "genz_discontinuous": "GenzDiscontinuous"}
 
-    def make_c1():
-        c = WL.C1
+    def make_c1(abstol=None):
+        c = dict(WL.C1)
+        if abstol is not None:
+            c["abstol"] = abstol
         n = args.nprob or c["nprob"]
         par = WL.c1_params(c["nprob"])[:, :n]
         pinned = torch.from_numpy(np.ascontiguousarray(par.T)).pin_memory()
@@ -375,22 +377,31 @@ def main():
                         h2d=n * 6 * 8, d2h=n * 8, kernel="tensor_kernel<GENZ_OSC,3>")
         return step, e2e_step, finish
 
-    def make_c2():
+    def make_c2(nonuniform=False, contiguous=False):
+        """default: the integration axis is the strided one (dim = 2 of a column-major 4096 x n array), uniform grid.
+        nonuniform: x_i = ((i-1)/(n-1))^1.5; contiguous: the transposed array, dim = 1 (inner = 1)."""
         m = WL.C2["m"]; n = args.nprob or WL.C2["n"]
-        y = torch.empty((n, m), dtype=torch.float64, device="cuda")         # row-major [n, m] == column-major m x n
         xs = torch.linspace(0, 1, n, dtype=torch.float64, device="cuda")
         jj = 1.0 + torch.arange(1, m + 1, dtype=torch.float64, device="cuda") / m
-        for i0 in range(0, n, 1 << 16):
-            i1 = min(n, i0 + (1 << 16))
-            y[i0:i1] = torch.sin(xs[i0:i1, None] * jj[None, :]) + 1.5
+        if contiguous:
+            y = torch.empty((m, n), dtype=torch.float64, device="cuda")     # row-major [m, n] == column-major n x m, dim = 1
+            for j0 in range(0, m, 64):
+                y[j0:j0 + 64] = torch.sin(jj[j0:j0 + 64, None] * xs[None, :]) + 1.5
+        else:
+            y = torch.empty((n, m), dtype=torch.float64, device="cuda")     # row-major [n, m] == column-major m x n, dim = 2
+            for i0 in range(0, n, 1 << 16):
+                i1 = min(n, i0 + (1 << 16))
+                y[i0:i1] = torch.sin(xs[i0:i1, None] * jj[None, :]) + 1.5
         out = torch.empty(m, dtype=torch.float64, device="cuda")
         h = 1.0 / (n - 1)
+        xg = xs ** 1.5 if nonuniform else None
+        inner, outer = (1, m) if contiguous else (m, 1)
         ne2e = min(n, 1 << 16)                                              # e2e on a 2 GiB host block (PCIe bound)
-        yh = y[:ne2e].cpu().pin_memory()
+        yh = None if (nonuniform or contiguous) else y[:ne2e].cpu().pin_memory()
 
         def step(record=False):
-            eng.sampled("trapezoid", y, m, n, 1, h=h, out=out)
-            eng.sampled("simpson", y, m, n, 1, h=h, out=out)
+            eng.sampled("trapezoid", y, inner, n, outer, h=h, x=xg, out=out)
+            eng.sampled("simpson", y, inner, n, outer, h=h, x=xg, out=out)
 
         def e2e_step():
             r = 0.0
@@ -428,7 +439,12 @@ def main():
                                     rounds=last["rounds"], boxes_stored=last["boxes"], status=last["status"], box_budget=budget))
         return step, e2e_step, finish
 
-    makers = {"c4": make_c4, "c1": make_c1, "c2": make_c2, "c3": make_c3, "c5": make_c5}
+    makers = {"c4": make_c4, "c1": make_c1, "c2": make_c2, "c3": make_c3, "c5": make_c5,
+              # side measurements SURVEY 8(d) asks for next to the configs (reported under "secondary" only)
+              "c1_abstol_1e-12": lambda: make_c1(abstol=1e-12), "c2_nonuniform_grid": lambda: make_c2(nonuniform=True),
+              "c2_contiguous_axis": lambda: make_c2(contiguous=True), "c4_reduced_difficulty_h/4": lambda: make_c4(scale=0.25)}
+    EXTRA_UNITS = {"c1_abstol_1e-12": "integrals/s", "c2_nonuniform_grid": "GB/s", "c2_contiguous_axis": "GB/s",
+                   "c4_reduced_difficulty_h/4": "integrals/s"}
 
     def run(workload, steps, warmup, with_e2e=True, sample_clocks=False):
         step, e2e_step, finish = makers[workload]()
@@ -506,25 +522,30 @@ def main():
 
     if rank == 0 and world == 1 and not args.no_secondary:
         sec = {}
-        for sw in METRIC:
+        for sw in list(METRIC) + list(EXTRA_UNITS):
             if sw == w:
                 continue
-            if sw == "c2" and torch.cuda.mem_get_info()[0] < (40 << 30):
+            if sw.startswith("c2") and torch.cuda.mem_get_info()[0] < (40 << 30):
                 continue
             try:
                 s = run(sw, 2, 3, with_e2e=False)
-                e = {"value": s["value"], "unit": METRIC[sw][1], "ms_per_step": s["ms_per_step"]}
+                e = {"value": s["value"], "unit": METRIC[sw][1] if sw in METRIC else EXTRA_UNITS[sw], "ms_per_step": s["ms_per_step"]}
                 if "result" in s["info"]:
                     e["result"] = s["info"]["result"]
-                if sw == "c2":
+                if "per_family" in s["info"]:
+                    e["frac_maxevals"] = {k: v["frac_maxevals"] for k, v in s["info"]["per_family"].items()}
+                if sw.startswith("c2"):
                     e["frac_of_measured_hbm"] = s["value"] / 6535.7
                 else:
                     e["fp64_tflops_nominal"] = s["info"]["flops"] / (s["ms_per_step"] * 1e-3) / 1e12
-                    e["frac_of_fp64_peak"] = e["fp64_tflops_nominal"] / fp64_peak
+                    e["nominal_frac_of_fp64_peak"] = e["fp64_tflops_nominal"] / fp64_peak
                 sec[sw] = e
             except Exception as ex:                          # a side measurement must not lose the headline
                 sec[sw] = {"error": str(ex)[:200]}
             torch.cuda.empty_cache()
+        sec["_note"] = ("fp64_tflops_nominal uses the algorithmic flop counts of SURVEY 8(d) (a throughput-equivalent figure: it exceeds 1 where a "
+                        "kernel executes fewer operations than the count assumes -- angle addition in c3, per-axis factor tables in c5); the executed "
+                        "FP64-pipe utilisation per kernel is the ncu figure in profiles/README.md (c1 31.8 %, c3 45.6 %, c5 38.1 %, c4 20-34 %)")
         line["secondary"] = sec
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
