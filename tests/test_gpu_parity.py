@@ -496,3 +496,14 @@ def test_quadgk_vector_valued_infinite_domain_and_solve(eng, O):
         eng.quadgk_vec_batch(F["sinxp"], -2.0, 5.0, np.ones((1, 9, 2)))
     I, E, ne, st = eng.quadgk_vec_batch(F["sinxp"], -2.0, 5.0, np.array([[50.0, 60.0]]), reltol=1e-13, abstol=0.0, maxevals=300)
     assert st[0] == 1 and ne[0] == 315
+
+
+def test_hcubature_product_peak_extreme_parameters(eng, O, hcub_mode):
+    """the shared-division evaluation of the product-peak terms (family.cuh Terms7) falls back to plain divisions when the
+    denominators could over/underflow in a product: tiny and huge a, against the oracle"""
+    lb, ub = np.zeros(2), np.ones(2)
+    par = np.asfortranarray(np.array([[1e-25, 3.0, 0.3, 0.6], [2.0, 1e-30, 0.5, 0.5], [1e30, 2.0, 0.25, 0.5], [5.0, 7.0, 0.4, 0.7]]).T)
+    I, E, ne, st = eng.hcubature_batch(F["genz_product_peak"], 2, lb, ub, par, reltol=1e-7, abstol=0.0, maxevals=200000)
+    Ir, Er, ner, str_ = O.hcubature_batch("prodpeak", lb, ub, par, reltol=1e-7, abstol=0.0, maxiters=200000)
+    assert np.array_equal(st, str_) and np.all(np.isfinite(I))
+    assert np.all(np.abs(I - Ir) <= 1e-7 * np.abs(Ir) + 1e-300)
