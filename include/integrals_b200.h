@@ -138,6 +138,17 @@ int32_t ib200_hcubature_batch(ib200_ctx *ctx, int32_t family, int32_t dim, int32
                               double reltol, double abstol, int64_t maxevals, int32_t initdiv,
                               double *out_I, double *out_E, int64_t *out_nevals, int32_t *out_status);
 
+/* -- the same solve with the Gauss-Kronrod rule of another order (QuadGKJL(order = n), src/algorithms.jl:51-56, forwarded
+      as `order = alg.order` at src/Integrals.jl:331-334).  x, w, wg: host arrays in the layout of QuadGK.kronrod(n) --
+      x[n+1] the non-positive Kronrod nodes in increasing order (x[n] = 0), w[n+1] their weights, wg[(n+1)/2] the Gauss
+      weights at x[1], x[3], ...  2 <= order <= 30. */
+int32_t ib200_quadgk_rule_batch(ib200_ctx *ctx, int32_t family, int32_t transform,
+                                const double *lb, const double *ub, int32_t bounds_per_problem,
+                                const double *params, int32_t nparam, int64_t nprob,
+                                double reltol, double abstol, int64_t maxevals,
+                                int32_t order, const double *x, const double *w, const double *wg,
+                                double *out_I, double *out_E, int64_t *out_nevals, int32_t *out_status);
+
 /* -- vector-valued integrands: QuadGK.quadgk!(f!, result, lb, ub; ..., norm) as called from
       __solvebp_call(::QuadGKJL) for array-valued integrands, src/Integrals.jl:316-326, with QuadGKJL.norm
       (src/algorithms.jl:10-11,56; default LinearAlgebra.norm).  Component c of problem k is the registered family with

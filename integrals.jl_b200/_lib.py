@@ -24,7 +24,7 @@ ERR_NAMES = {-1: "IB200_ERR_INVALID", -2: "IB200_ERR_CUDA", -3: "IB200_ERR_OOM",
 SYMBOLS = ["ib200_version", "ib200_create", "ib200_destroy", "ib200_last_error", "ib200_set_stream",
            "ib200_synchronize", "ib200_kernel_launches", "ib200_family_nparam", "ib200_last_kernel_ms",
            "ib200_set_option", "ib200_sampled", "ib200_sampled_f32", "ib200_fixed_rule_tensor_batch", "ib200_fixed_rule_nodes_batch",
-           "ib200_gauss_legendre_batch", "ib200_quadgk_batch", "ib200_quadgk_vec_batch", "ib200_hcubature_batch", "ib200_measure_fp64_peak",
+           "ib200_gauss_legendre_batch", "ib200_quadgk_batch", "ib200_quadgk_rule_batch", "ib200_quadgk_vec_batch", "ib200_hcubature_batch", "ib200_measure_fp64_peak",
            "ib200_hcubature_single", "ib200_comm_unique_id", "ib200_comm_init", "ib200_comm_destroy"]
 
 
@@ -69,6 +69,8 @@ def load_library():
     L.ib200_gauss_legendre_batch.restype = i32
     L.ib200_quadgk_batch.argtypes = [vp, i32, i32, vp, vp, i32, vp, i32, i64, dp, dp, i64, vp, vp, vp, vp]
     L.ib200_quadgk_batch.restype = i32
+    L.ib200_quadgk_rule_batch.argtypes = [vp, i32, i32, vp, vp, i32, vp, i32, i64, dp, dp, i64, i32, vp, vp, vp, vp, vp, vp, vp]
+    L.ib200_quadgk_rule_batch.restype = i32
     L.ib200_quadgk_vec_batch.argtypes = [vp, i32, i32, vp, vp, i32, vp, i32, i32, i64, dp, dp, i64, i32, vp, vp, vp, vp]
     L.ib200_quadgk_vec_batch.restype = i32
     L.ib200_sampled_f32.argtypes = [vp, i32, vp, i64, i64, i64, C.c_float, vp, vp]; L.ib200_sampled_f32.restype = i32
@@ -245,12 +247,20 @@ class Engine:
 
     # ---- adaptive ------------------------------------------------------------------------------
     def quadgk_batch(self, family, lb, ub, params, reltol=1e-8, abstol=1e-8, maxevals=MAXEVALS_UNBOUNDED, transform=0,
-                     out_I=None, out_E=None, out_nevals=None, out_status=None):
+                     out_I=None, out_E=None, out_nevals=None, out_status=None, rule=None):
+        """rule: None = the built-in (7,15) pair, or (x, w, wg) of another order in QuadGK.kronrod's layout (kronrod.kronrod(n))"""
         lb = _f64(lb); ub = _f64(ub); params = _f64(params)
         params, nparam, nprob, bpp = self._batch_shapes(params, lb, ub, 1)
         out_I = self._out(out_I, nprob); out_E = self._out(out_E, nprob)
         out_nevals = self._out(out_nevals, nprob, np.int64); out_status = self._out(out_status, nprob, np.int32)
         a = [_ptr(v) for v in (lb, ub, params, out_I, out_E, out_nevals, out_status)]
+        if rule is not None:
+            x, w, wg = (np.ascontiguousarray(v, dtype=np.float64) for v in rule)
+            self._check(self.L.ib200_quadgk_rule_batch(self.h, family, transform, a[0][0], a[1][0], bpp, a[2][0], nparam, nprob,
+                                                       float(reltol), float(abstol), int(min(maxevals, MAXEVALS_UNBOUNDED)),
+                                                       x.size - 1, x.ctypes.data, w.ctypes.data, wg.ctypes.data,
+                                                       a[3][0], a[4][0], a[5][0], a[6][0]))
+            return out_I, out_E, out_nevals, out_status
         self._check(self.L.ib200_quadgk_batch(self.h, family, transform, a[0][0], a[1][0], bpp, a[2][0], nparam, nprob,
                                               float(reltol), float(abstol), int(min(maxevals, MAXEVALS_UNBOUNDED)),
                                               a[3][0], a[4][0], a[5][0], a[6][0]))

@@ -111,7 +111,7 @@ extern "C" int32_t ib200_hcubature_batch(ib200_ctx *ctx, int32_t family, int32_t
         q.rtol = reltol; q.atol = abstol; q.maxevals = maxevals; q.initdiv = initdiv;
         q.cap = (int)((cap + 1023) / 1024 * 1024);
         q.keys = q.l1 = q.rec = nullptr; q.l1off = nullptr; q.counter = counter;
-        q.order = nullptr; q.norder = nullptr;
+        q.order = nullptr; q.norder = nullptr; q.gk_order = 0; q.gk_x = q.gk_w = q.gk_wg = nullptr;
         q.out_I = oI.d; q.out_E = oE.d; q.out_nevals = oN.d; q.out_status = oS.d;
         auto run = [&](hp::Params &pp) -> int32_t {
             switch (dim) {

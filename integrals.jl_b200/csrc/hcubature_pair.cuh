@@ -44,6 +44,8 @@ struct Params {
     unsigned char *l1off;       // [pairs][cap/32]       position (0..31) of that maximum in its group
     double *rec;                // [pairs][cap][2D+2]    a[D], b[D], I, split axis
     unsigned long long *counter;
+    int gk_order;               // D == 1 only: 0 = the built-in (7,15) pair, else the order n of the rule below
+    const double *gk_x, *gk_w, *gk_wg;   // QuadGK.kronrod(n) layout: x[n+1], w[n+1], wg[(n+1)/2] (device)
     const unsigned *order;      // problem indices in processing order (NULL: 0, 1, 2, ...), see lpt_* below
     const unsigned long long *norder;   // device-side length of `order` (NULL: nprob)
     double *out_I, *out_E; int64_t *out_nevals; int32_t *out_status;
@@ -386,9 +388,47 @@ __device__ __forceinline__ void gk_rule_thread(const double *pc, int tr, double 
     Iout = Ik * s;
     Eout = fabs(Ik * s - Ig * s);
 }
+// the same for a Gauss-Kronrod rule of any order n >= 2 (QuadGKJL(order = n)): tables in shared memory, QuadGK's evalrule
+// for any order (oracle gk_evalrule_n): even orders have no Gauss node at the centre
+constexpr int kGkMaxOrder = 30;
+template <int FAM, bool ALLFIN>
+__device__ __forceinline__ void gk_rule_thread_n(const double *pc, int tr, double a, double b, int n, const double *x, const double *w,
+                                                 const double *wg, double &Iout, double &Eout) {
+    using F = ib::Family<FAM, 1>;
+    constexpr int NPAR = ib::fam_nparam(FAM, 1);
+    const double *par = pc, *lbs = pc + NPAR, *aux = lbs + 1;
+    const double jacc = aux[2];
+    double q[F::NQ];
+    F::prepare(par, q);
+    const double s = 0.5 * (b - a);
+    auto g = [&](double t) {
+        double u[1], J;
+        if (ALLFIN) { u[0] = lbs[0] + (1.0 + t) * aux[0]; J = jacc; }
+        else { ib::AxisMap m; ib::make_axis(lbs[0], aux[0], m); ib::t2ujac(tr, t, m, u[0], J); }
+        return F::eval(u, q) * J;
+    };
+    auto pair = [&](int i) { return g(a + (1 + x[i - 1]) * s) + g(a + (1 - x[i - 1]) * s); };     // 1-based like the Julia source
+    const int lenx = n + 1, lenwg = (n + 1) / 2, n1 = 1 - (lenx & 1);
+    double fg = pair(2), fk = pair(1);
+    double Ig = fg * wg[0];
+    double Ik = fg * w[1] + fk * w[0];
+    for (int i = 2; i <= lenwg - n1; i++) {
+        fg = pair(2 * i); fk = pair(2 * i - 1);
+        Ig += fg * wg[i - 1];
+        Ik += fg * w[2 * i - 1] + fk * w[2 * i - 2];
+    }
+    if (n1 == 0) Ik += g(a + s) * w[lenx - 1];
+    else {
+        const double f0 = g(a + s);
+        Ig += f0 * wg[lenwg - 1];
+        Ik += f0 * w[lenx - 1] + pair(lenx - 1) * w[lenx - 2];
+    }
+    Iout = Ik * s;
+    Eout = fabs(Ik * s - Ig * s);
+}
 // QuadGK's check_endpoint_roundoff: does the rule evaluate at an endpoint of (a, b)?
-__device__ __forceinline__ bool gk_endpoint_roundoff(double a, double b) {
-    const double c = 0.5 * (b - a), x1 = -0.991455371120812639206854697526329;
+__device__ __forceinline__ bool gk_endpoint_roundoff(double a, double b, double x1 = -0.991455371120812639206854697526329) {
+    const double c = 0.5 * (b - a);
     return (a == a + (1 + x1) * c) || (b == a + (1 - x1) * c);
 }
 
@@ -447,11 +487,11 @@ template <int FAM, int D, bool ALLFIN>
 __global__ void __launch_bounds__(kBlock, HP_MINB)
 hcub_pair_kernel(const Params p) {
     using F = ib::Family<FAM, D>;
-    constexpr int NP = hc::gm_npoints(D);
     constexpr int NPAR = ib::fam_nparam(FAM, D);
     constexpr int PCD = pc_doubles<FAM, D>();
     constexpr int RECW = 2 * D + 2;
     extern __shared__ double sm[];
+    const int NP = (D == 1 && p.gk_order) ? 2 * p.gk_order + 1 : hc::gm_npoints(D);      // evaluations per rule application
     const int lane = threadIdx.x & 31, half = lane & 1;
     const unsigned full = 0xffffffffu;
     const unsigned pm = 3u << (lane & ~1);               // this pair's lanes
@@ -464,6 +504,12 @@ hcub_pair_kernel(const Params p) {
     double *par = pc, *lbs = pc + NPAR, *aux = lbs + D;
     double *stage = sm + (size_t)kPairs * row_doubles(n2max, PCD) + (size_t)threadIdx.x * 32;          // [keys half | l1 half]
     unsigned char *stage_off = reinterpret_cast<unsigned char *>(sm + (size_t)kPairs * row_doubles(n2max, PCD) + (size_t)kBlock * 32) + pib * 32;
+    double *gkt = sm + (size_t)kPairs * row_doubles(n2max, PCD) + (size_t)kBlock * 32 + (size_t)kPairs * 4;    // D == 1: x | w | wg of the rule
+    if (D == 1 && p.gk_order) {
+        for (int t = threadIdx.x; t <= p.gk_order; t += kBlock) { gkt[t] = p.gk_x[t]; gkt[kGkMaxOrder + 1 + t] = p.gk_w[t]; }
+        for (int t = threadIdx.x; t < (p.gk_order + 1) / 2; t += kBlock) gkt[2 * (kGkMaxOrder + 1) + t] = p.gk_wg[t];
+        __syncthreads();
+    }
 
     double *keys = p.keys + (size_t)gpair * p.cap;
     double *l1 = p.l1 + (size_t)gpair * (p.cap / kFan);
@@ -618,7 +664,8 @@ hcub_pair_kernel(const Params p) {
                 // QuadGK: mid = (a + b) / 2; the pair evaluates (a, mid) and (mid, b); a segment that can no longer be
                 // bisected ends the refinement (check_endpoint_roundoff)
                 const double mid = (akd + bkd) / 2;
-                if (gk_endpoint_roundoff(akd, mid) || gk_endpoint_roundoff(mid, bkd)) { status = IB200_ST_ROUNDOFF; state = ST_FIN; have = false; }
+                const double x1 = p.gk_order ? gkt[0] : -0.991455371120812639206854697526329;
+                if (gk_endpoint_roundoff(akd, mid, x1) || gk_endpoint_roundoff(mid, bkd, x1)) { status = IB200_ST_ROUNDOFF; state = ST_FIN; have = false; }
                 if (half == 0) b[0] = mid; else a[0] = mid;
             } else {
                 const double w = (bkd - akd) * 0.5;
@@ -646,7 +693,10 @@ hcub_pair_kernel(const Params p) {
         // ---- 4. the rule on this lane's box
         double Ic = 0.0, Ec = 0.0; int kc = 0;
         if (have) {
-            if constexpr (D == 1) gk_rule_thread<FAM, ALLFIN>(pc, p.tr, a[0], b[0], Ic, Ec);
+            if constexpr (D == 1) {
+                if (p.gk_order) gk_rule_thread_n<FAM, ALLFIN>(pc, p.tr, a[0], b[0], p.gk_order, gkt, gkt + kGkMaxOrder + 1, gkt + 2 * (kGkMaxOrder + 1), Ic, Ec);
+                else gk_rule_thread<FAM, ALLFIN>(pc, p.tr, a[0], b[0], Ic, Ec);
+            }
             else if constexpr (FAM == IB200_FAM_GENZ_OSC && ALLFIN) gm_rule_thread_osc<D>(pc, a, b, Ic, Ec, kc);
             else gm_rule_thread<FAM, D, ALLFIN>(pc, p.tr, a, b, Ic, Ec, kc);
         }
@@ -754,7 +804,8 @@ int32_t launch_impl(ib200_ctx *ctx, int family, bool allfin, Params &p) {
         constexpr int FAM = decltype(famc)::value;
         if constexpr (ib::fam_dim_ok(FAM, D)) {
             auto go = [&](auto kern) -> int32_t {
-                const size_t smem = ((size_t)kPairs * row_doubles(p.cap >> 10, pc_doubles<FAM, D>()) + (size_t)kBlock * 32 + (size_t)kPairs * 4) * sizeof(double);
+                const size_t smem = ((size_t)kPairs * row_doubles(p.cap >> 10, pc_doubles<FAM, D>()) + (size_t)kBlock * 32 + (size_t)kPairs * 4 +
+                                     (D == 1 ? 3 * (kGkMaxOrder + 1) : 0)) * sizeof(double);
                 if (smem > ctx->smem_optin) return ib200_fail(ctx, IB200_ERR_INVALID, "ib200_hcubature_batch: box capacity too large for shared memory");
                 IB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 int occ = 0;

@@ -190,11 +190,13 @@ quadgk_kernel(const double *__restrict__ params, int nparam, int64_t nprob,
 
 }  // namespace
 
-extern "C" int32_t ib200_quadgk_batch(ib200_ctx *ctx, int32_t family, int32_t transform,
-                                      const double *lb, const double *ub, int32_t bpp,
-                                      const double *params, int32_t nparam, int64_t nprob,
-                                      double reltol, double abstol, int64_t maxevals,
-                                      double *out_I, double *out_E, int64_t *out_nevals, int32_t *out_status) {
+// order == 0: the built-in (7,15) pair; otherwise the rule (x, w, wg) of that order in QuadGK.kronrod's layout (host pointers)
+static int32_t quadgk_impl(ib200_ctx *ctx, int32_t family, int32_t transform,
+                           const double *lb, const double *ub, int32_t bpp,
+                           const double *params, int32_t nparam, int64_t nprob,
+                           double reltol, double abstol, int64_t maxevals,
+                           int32_t order, const double *gx, const double *gw, const double *gwg,
+                           double *out_I, double *out_E, int64_t *out_nevals, int32_t *out_status) {
     IB_REQUIRE(ctx, ctx != nullptr, "ib200_quadgk_batch: ctx is NULL");
     IB_REQUIRE(ctx, family >= 0 && family < IB200_FAM_COUNT, "ib200_quadgk_batch: unknown integrand family");
     IB_REQUIRE(ctx, transform >= 0 && transform <= 2, "ib200_quadgk_batch: unknown transform id");
@@ -224,9 +226,10 @@ extern "C" int32_t ib200_quadgk_batch(ib200_ctx *ctx, int32_t family, int32_t tr
     // 360 warp instructions per refinement step, of which the 30 integrand evaluations are a small part.
     // Measured (C1 sweep, kernel time): 65,536 problems 1.29 ms (warp) vs 1.49 ms (pair); 2^20 problems 18.9 vs 14.6 ms:
     // a step is only 30 evaluations, so the pair kernel's per-step pool traffic weighs more than in the cubature case.
-    const bool use_pair = ctx->opt_quadgk_mode == 2 || (ctx->opt_quadgk_mode == 0 && nprob >= ((int64_t)1 << 18));
+    const bool use_pair = order != 0 || ctx->opt_quadgk_mode == 2 || (ctx->opt_quadgk_mode == 0 && nprob >= ((int64_t)1 << 18));
     if (use_pair) {
-        int64_t need_seg = maxevals >= ((int64_t)1 << 40) ? 4096 : 2 + (maxevals > 15 ? (maxevals - 15 + 29) / 30 : 0);
+        const int64_t npts = order ? 2 * (int64_t)order + 1 : 15;
+        int64_t need_seg = maxevals >= ((int64_t)1 << 40) ? 4096 : 2 + (maxevals > npts ? (maxevals - npts + 2 * npts - 1) / (2 * npts) : 0);
         if (ctx->opt_hcub_capacity > 0) need_seg = ctx->opt_hcub_capacity;
         if (need_seg > 65536 - 1024) need_seg = 65536 - 1024;
         unsigned long long *counter = (unsigned long long *)ctx->get(SL_WORK1, sizeof(unsigned long long));
@@ -238,6 +241,13 @@ extern "C" int32_t ib200_quadgk_batch(ib200_ctx *ctx, int32_t family, int32_t tr
         q.cap = (int)((need_seg + 1023) / 1024 * 1024);
         q.keys = q.l1 = q.rec = nullptr; q.l1off = nullptr; q.counter = counter;
         q.order = nullptr; q.norder = nullptr;
+        q.gk_order = order; q.gk_x = q.gk_w = q.gk_wg = nullptr;
+        DevIn<double> dgx, dgw, dgwg;
+        if (order) {
+            if ((rc = dgx.init(ctx, gx, (size_t)order + 1, SL_IN3)) || (rc = dgw.init(ctx, gw, (size_t)order + 1, SL_IN4)) ||
+                (rc = dgwg.init(ctx, gwg, (size_t)(order + 1) / 2, SL_IN5))) return rc;
+            q.gk_x = dgx.d; q.gk_w = dgw.d; q.gk_wg = dgwg.d;
+        }
         q.out_I = oI.d; q.out_E = oE.d; q.out_nevals = oN.d; q.out_status = oS.d;
         ctx->err.clear();
         ib200_time_begin(ctx);
@@ -295,4 +305,26 @@ extern "C" int32_t ib200_quadgk_batch(ib200_ctx *ctx, int32_t family, int32_t tr
     if ((rc = oI.finish(ctx)) || (rc = oE.finish(ctx)) || (rc = oN.finish(ctx)) || (rc = oS.finish(ctx))) return rc;
     if (oI.is_host() || oE.is_host() || oN.is_host() || oS.is_host()) IB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return IB200_OK;
+}
+
+extern "C" int32_t ib200_quadgk_batch(ib200_ctx *ctx, int32_t family, int32_t transform,
+                                      const double *lb, const double *ub, int32_t bpp,
+                                      const double *params, int32_t nparam, int64_t nprob,
+                                      double reltol, double abstol, int64_t maxevals,
+                                      double *out_I, double *out_E, int64_t *out_nevals, int32_t *out_status) {
+    return quadgk_impl(ctx, family, transform, lb, ub, bpp, params, nparam, nprob, reltol, abstol, maxevals, 0, nullptr, nullptr, nullptr,
+                       out_I, out_E, out_nevals, out_status);
+}
+
+extern "C" int32_t ib200_quadgk_rule_batch(ib200_ctx *ctx, int32_t family, int32_t transform,
+                                           const double *lb, const double *ub, int32_t bpp,
+                                           const double *params, int32_t nparam, int64_t nprob,
+                                           double reltol, double abstol, int64_t maxevals,
+                                           int32_t order, const double *x, const double *w, const double *wg,
+                                           double *out_I, double *out_E, int64_t *out_nevals, int32_t *out_status) {
+    IB_REQUIRE(ctx, ctx != nullptr, "ib200_quadgk_rule_batch: ctx is NULL");
+    IB_REQUIRE(ctx, order >= 2 && order <= hp::kGkMaxOrder, "ib200_quadgk_rule_batch: 2 <= order <= 30");
+    IB_REQUIRE(ctx, x && w && wg, "ib200_quadgk_rule_batch: NULL rule table");
+    return quadgk_impl(ctx, family, transform, lb, ub, bpp, params, nparam, nprob, reltol, abstol, maxevals, order, x, w, wg,
+                       out_I, out_E, out_nevals, out_status);
 }

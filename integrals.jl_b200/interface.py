@@ -142,15 +142,20 @@ class AbstractB200Algorithm:
 
 
 class QuadGKB200(AbstractB200Algorithm):
-    """Adaptive Gauss-Kronrod, drop-in for QuadGKJL (src/algorithms.jl:51-56); order 7 only."""
+    """Adaptive Gauss-Kronrod, drop-in for QuadGKJL (src/algorithms.jl:51-56).  order: 7 (default, built-in tables) or any
+    2..30 (tables from kronrod.kronrod(order), the analogue of QuadGK.kronrod)."""
 
     def __init__(self, order=7, norm="2"):
         """norm: "2" (LinearAlgebra.norm, the QuadGKJL default) or "inf"; only used by vector-valued integrands (VectorOf)."""
-        if order != 7:
-            raise ValueError("QuadGKB200 implements the (7,15) Gauss-Kronrod pair only")
+        if not 2 <= int(order) <= 30:
+            raise ValueError("QuadGKB200 supports Gauss-Kronrod orders 2..30")
         if norm not in ("2", "inf"):
             raise ValueError('QuadGKB200 supports norm = "2" or "inf"')
-        self.order, self.norm = order, norm
+        self.order, self.norm = int(order), norm
+        self.rule = None
+        if self.order != 7:
+            from .kronrod import kronrod
+            self.rule = kronrod(self.order)
 
 
 class HCubatureB200(AbstractB200Algorithm):
@@ -299,7 +304,8 @@ def solve_cache(cache):
     if isinstance(inner, QuadGKB200):
         if dim != 1:
             raise ValueError("QuadGKB200 only accepts one-dimensional quadrature problems.")    # Integrals.jl:263-266
-        I, E, ne, st = eng.quadgk_batch(fam, lb, ub, p, reltol=reltol, abstol=abstol, maxevals=maxiters, transform=tr)
+        extra = {} if inner.rule is None else {"rule": inner.rule}
+        I, E, ne, st = eng.quadgk_batch(fam, lb, ub, p, reltol=reltol, abstol=abstol, maxevals=maxiters, transform=tr, **extra)
         stats = dict(nevals=ne, status=st)
     elif isinstance(inner, HCubatureB200) and inner.single_domain:
         if not scalar or dim < 2:
@@ -341,6 +347,8 @@ def _solve_vector(cache, prob, inner, tr):
     """array-valued integrand (src/Integrals.jl:316-326): QuadGK with a norm over the components"""
     if not isinstance(inner, QuadGKB200):
         raise TypeError("vector-valued registered integrands (VectorOf) are integrated by QuadGKB200")
+    if inner.order != 7:
+        raise ValueError("vector-valued QuadGKB200 solves use the (7,15) pair")
     lb, ub = prob.domain
     if np.ndim(lb) > 1 or (np.ndim(lb) == 1 and np.size(lb) != 1 and np.ndim(prob.p) != 3):
         raise ValueError("QuadGKB200 only accepts one-dimensional quadrature problems.")

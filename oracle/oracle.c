@@ -567,6 +567,100 @@ int orc_quadgk(orc_integrand f, void *user, double a, double b, double rtol, dou
 }
 
 /* ------------------------------------------------------------------------------------------
+ * QuadGK with a Gauss-Kronrod rule of any order n >= 2 (QuadGKJL(order = n), src/algorithms.jl:51-56, forwarded as
+ * `order = alg.order` at src/Integrals.jl:331-334).  x, w, wg in QuadGK.kronrod(n)'s layout: x[0..n] the non-positive
+ * Kronrod nodes (x[n] = 0), w their weights, wg[0..(n+1)/2) the Gauss weights at x[1], x[3], ...  The rule is QuadGK's
+ * evalrule for any order (symmetric pairs first; even orders have no Gauss node at 0); the driver is orc_quadgk's.
+ * ------------------------------------------------------------------------------------------ */
+static orc_seg gk_evalrule_n(orc_integrand f, void *user, double a, double b, int n, const double *x, const double *w, const double *wg)
+{
+    const int lenx = n + 1, lenwg = (n + 1) / 2, n1 = 1 - (lenx & 1);     /* n1: 0 even order, 1 odd order */
+#define PAIRN(i) (f1d(f, user, a + (1 + x[(i) - 1]) * s) + f1d(f, user, a + (1 - x[(i) - 1]) * s))
+    double s = 0.5 * (b - a);
+    double fg = PAIRN(2), fk = PAIRN(1);
+    double Ig = fg * wg[0];
+    double Ik = fg * w[1] + fk * w[0];
+    for (int i = 2; i <= lenwg - n1; i++) {
+        fg = PAIRN(2 * i); fk = PAIRN(2 * i - 1);
+        Ig += fg * wg[i - 1];
+        Ik += fg * w[2 * i - 1] + fk * w[2 * i - 2];
+    }
+    if (n1 == 0) Ik += f1d(f, user, a + s) * w[lenx - 1];
+    else {
+        double f0 = f1d(f, user, a + s);
+        Ig += f0 * wg[lenwg - 1];
+        Ik += f0 * w[lenx - 1] + PAIRN(lenx - 1) * w[lenx - 2];
+    }
+#undef PAIRN
+    orc_seg r;
+    r.a = a; r.b = b; r.I = Ik * s; r.E = fabs(Ik * s - Ig * s);
+    return r;
+}
+
+int orc_quadgk_rule(orc_integrand f, void *user, double a, double b, double rtol, double atol, int64_t maxevals,
+                    int n, const double *x, const double *w, const double *wg, double *Iout, double *Eout, int64_t *nevals_out)
+{
+    if (n < 2 || n > 64) return -1;
+    const int64_t npts = 2 * (int64_t)n + 1;
+    int status = 0;
+    orc_seg s0 = gk_evalrule_n(f, user, a, b, n, x, w, wg);
+    double I = s0.I, E = s0.E;
+    int64_t numevals = npts, cap = 64, len = 1;
+    if (rtol == 0 && atol == 0) rtol = sqrt(2.220446049250313e-16);
+    orc_seg *segs = (orc_seg *)malloc(sizeof(orc_seg) * (size_t)(cap + 1));
+    segs[1] = s0;
+    if (isnan(E) || isinf(E)) status = 2;
+    else if (!(numevals >= maxevals || E <= atol || E <= rtol * fabs(I))) {
+        while (E > atol && E > rtol * fabs(I) && numevals < maxevals) {
+            orc_seg s = segs[1];
+            orc_seg y = segs[len--];
+            if (len >= 1) seg_percolate_down(segs, 1, y, len);
+            double mid = (s.a + s.b) / 2;
+            double c1 = 0.5 * (mid - s.a), c2 = 0.5 * (s.b - mid);            /* check_endpoint_roundoff with this rule's first node */
+            if (s.a == s.a + (1 + x[0]) * c1 || mid == s.a + (1 - x[0]) * c1 || mid == mid + (1 + x[0]) * c2 || s.b == mid + (1 - x[0]) * c2) {
+                len++; seg_percolate_up(segs, len, s); status = 3; break;
+            }
+            orc_seg s1 = gk_evalrule_n(f, user, s.a, mid, n, x, w, wg);
+            orc_seg s2 = gk_evalrule_n(f, user, mid, s.b, n, x, w, wg);
+            I = (I - s.I) + s1.I + s2.I;
+            E = (E - s.E) + s1.E + s2.E;
+            numevals += 2 * npts;
+            if (isnan(s1.E) || isinf(s1.E) || isnan(s2.E) || isinf(s2.E)) status = 2;
+            if (len + 2 > cap) { cap *= 2; segs = (orc_seg *)realloc(segs, sizeof(orc_seg) * (size_t)(cap + 1)); }
+            len++; seg_percolate_up(segs, len, s1);
+            len++; seg_percolate_up(segs, len, s2);
+            if (status == 2) break;
+        }
+    }
+    I = segs[1].I; E = segs[1].E;
+    for (int64_t i = 2; i <= len; i++) { I += segs[i].I; E += segs[i].E; }
+    free(segs);
+    if (status == 0 && !(E <= atol || E <= rtol * fabs(I)) && numevals >= maxevals) status = 1;
+    *Iout = I; *Eout = E;
+    if (nevals_out) *nevals_out = numevals;
+    return status;
+}
+
+int orc_quadgk_rule_batch(int fam, const double *lb, const double *ub, int bpp, int tr,
+                          const double *params, int nparam, int64_t nprob, double reltol, double abstol, int64_t maxiters,
+                          int n, const double *x, const double *w, const double *wg,
+                          double *I, double *E, int64_t *nevals, int32_t *status, int nthreads)
+{
+    if (nthreads < 1) nthreads = 1;
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads)
+    for (int64_t k = 0; k < nprob; k++) {
+        orc_family_user fu = {fam, 1, params + (size_t)k * nparam};
+        double l = bpp ? lb[k] : lb[0], u = bpp ? ub[k] : ub[0], tl, tu;
+        orc_cov c = {orc_family_integrand, &fu, 1, tr, &l, &u};
+        orc_u2t(l, u, &tl, &tu);
+        int64_t ne = 0;
+        status[k] = orc_quadgk_rule(orc_cov_eval, &c, tl, tu, reltol, abstol, maxiters, n, x, w, wg, &I[k], &E[k], &ne);
+        nevals[k] = ne;
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
  * QuadGK with a vector-valued integrand: the reference reaches it through
  * quadgk!(f!, result, lb, ub; norm = alg.norm) (src/Integrals.jl:316-326; QuadGKJL.norm defaults to
  * LinearAlgebra.norm, src/algorithms.jl:10-11,56).  The rule is applied component-wise, the error of a segment

@@ -89,6 +89,14 @@ int orc_sampled_evalrule_f32(int rule, const float *y, int64_t inner, int64_t n,
    3 endpoint roundoff stopped refinement */
 int orc_quadgk(orc_integrand f, void *user, double a, double b, double rtol, double atol,
                int64_t maxevals, double *I, double *E, int64_t *nevals, int64_t *nsegs);
+/* QuadGK with the Gauss-Kronrod rule of order n (QuadGKJL(order = n)); x, w, wg in QuadGK.kronrod(n)'s layout */
+int orc_quadgk_rule(orc_integrand f, void *user, double a, double b, double rtol, double atol, int64_t maxevals,
+                    int n, const double *x, const double *w, const double *wg, double *I, double *E, int64_t *nevals);
+int orc_quadgk_rule_batch(int fam, const double *lb, const double *ub, int bounds_per_problem, int tr,
+                          const double *params, int nparam, int64_t nprob, double reltol, double abstol, int64_t maxiters,
+                          int n, const double *x, const double *w, const double *wg,
+                          double *I, double *E, int64_t *nevals, int32_t *status, int nthreads);
+
 /* QuadGK with a vector-valued integrand and a norm (quadgk!(f!, result, ...; norm), src/Integrals.jl:316-326):
    f writes ncomp values; normkind 0 = 2-norm (LinearAlgebra.norm, the QuadGKJL default), 1 = maximum norm */
 typedef void (*orc_vec_integrand)(const double *x, int dim, void *user, double *out);

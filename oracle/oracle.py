@@ -276,6 +276,20 @@ def quadgk_batch(fam, lb, ub, params, tr="if_inf", reltol=1e-8, abstol=1e-8, max
     return I, E, ne, st
 
 
+def quadgk_rule_batch(fam, lb, ub, params, x, w, wg, tr="if_inf", reltol=1e-8, abstol=1e-8, maxiters=2**62, nthreads=1):
+    """QuadGK with the Gauss-Kronrod rule (x, w, wg) of order len(x) - 1 (QuadGK.kronrod layout)"""
+    fam, params, nparam, nprob, lb, ub, bpp = _batch_common(fam, 1, np.atleast_1d(lb), np.atleast_1d(ub), params)
+    x = _arr(x); w = _arr(w); wg = _arr(wg)
+    I = np.empty(nprob); E = np.empty(nprob); ne = np.empty(nprob, np.int64); st = np.empty(nprob, np.int32)
+    L = lib()
+    L.orc_quadgk_rule_batch.argtypes = [C.c_int, _dp, _dp, C.c_int, C.c_int, _dp, C.c_int, C.c_int64, C.c_double, C.c_double, C.c_int64,
+                                        C.c_int, _dp, _dp, _dp, _dp, _dp, _i64p, _i32p, C.c_int]
+    rc = L.orc_quadgk_rule_batch(fam, _p(lb), _p(ub), bpp, TR[tr], params.ctypes.data_as(_dp), nparam, nprob, reltol, abstol, maxiters,
+                                 x.size - 1, _p(x), _p(w), _p(wg), _p(I), _p(E), ne.ctypes.data_as(_i64p), st.ctypes.data_as(_i32p), nthreads)
+    assert rc == 0, rc
+    return I, E, ne, st
+
+
 def quadgk_vec_batch(fam, lb, ub, params, tr="if_inf", reltol=1e-8, abstol=1e-8, maxiters=2**62, norm="2", nthreads=1):
     """vector-valued QuadGK: params nparam x ncomp x nprob (Fortran order); -> I (ncomp x nprob), E, nevals, status"""
     fam = FAM[fam] if isinstance(fam, str) else fam

@@ -507,3 +507,39 @@ def test_hcubature_product_peak_extreme_parameters(eng, O, hcub_mode):
     Ir, Er, ner, str_ = O.hcubature_batch("prodpeak", lb, ub, par, reltol=1e-7, abstol=0.0, maxiters=200000)
     assert np.array_equal(st, str_) and np.all(np.isfinite(I))
     assert np.all(np.abs(I - Ir) <= 1e-7 * np.abs(Ir) + 1e-300)
+
+
+# ------------------------------------------------------------------------------------- QuadGK with other Gauss-Kronrod orders
+@pytest.mark.parametrize("order", [2, 3, 7, 10, 15, 21, 30])
+def test_quadgk_rule_orders_match_oracle(eng, O, order):
+    """QuadGKJL(order = n) (src/algorithms.jl:51-56): ib200_quadgk_rule_batch against orc_quadgk_rule with the same tables"""
+    from integrals_b200.kronrod import kronrod
+    x, w, wg = kronrod(order)
+    n = 512
+    # low orders need ~10^5 segments at 1e-10 (more than the 4096-segment pool of an unbounded-maxevals solve): easier sweep for them
+    pmax, reltol, abstol = (63.9, 1e-10, 1e-12) if order >= 7 else (8.0, 1e-7, 1e-9)
+    p = (0.1 + pmax * np.arange(n) / (n - 1)).reshape(1, n)
+    I, E, ne, st = eng.quadgk_batch(F["sinxp"], np.array([-2.0]), np.array([5.0]), p, reltol=reltol, abstol=abstol, rule=(x, w, wg))
+    Ir, Er, ner, str_ = O.quadgk_rule_batch("sinxp", -2.0, 5.0, p, x, w, wg, reltol=reltol, abstol=abstol, nthreads=O.max_threads())
+    exact = (np.cos(-2 * p[0]) - np.cos(5 * p[0])) / p[0]
+    _check_adaptive(I, E, st, Ir, Er, reltol, abstol, exact)
+    assert np.mean(ne == ner) > 0.97 and np.all(np.abs(I - Ir) <= 1e-13 * np.maximum(np.abs(Ir), 1e-2))
+    if order == 7:       # the table-driven rule reproduces the built-in (7,15) kernels
+        I7, E7, ne7, st7 = eng.quadgk_batch(F["sinxp"], np.array([-2.0]), np.array([5.0]), p, reltol=1e-10, abstol=1e-12)
+        assert np.mean(ne7 == ne) > 0.97 and np.all(np.abs(I - I7) <= 1e-13 * np.maximum(np.abs(I7), 1e-2))
+
+
+def test_quadgk_order_through_solve_and_infinite_domain(eng, O):
+    from integrals_b200.kronrod import kronrod
+    sol = ib.solve(ib.IntegralProblem(ib.SinXP(), (-2.0, 5.0), 1.7), ib.QuadGKB200(order=15), engine=eng, reltol=1e-10)
+    assert abs(sol.u - (math.cos(-3.4) - math.cos(8.5)) / 1.7) < 1e-12 and sol.stats["nevals"][0] == 31
+    x, w, wg = kronrod(10)
+    par = np.array([[0.7], [0.3]])
+    for tr, trn in enumerate(["if_inf", "tan", "cot"]):
+        I, E, ne, st = eng.quadgk_batch(F["genz_gaussian"], np.array([-INF]), np.array([INF]), par, reltol=1e-9, abstol=1e-12, transform=tr, rule=(x, w, wg))
+        Ir, Er, ner, _ = O.quadgk_rule_batch("gauss", -INF, INF, par, x, w, wg, tr=trn, reltol=1e-9, abstol=1e-12)
+        assert st[0] == 0 and abs(I[0] - math.sqrt(math.pi) / 0.7) < 1e-8 and abs(I[0] - Ir[0]) <= 1e-11 * abs(Ir[0])
+    with pytest.raises(ValueError):
+        ib.QuadGKB200(order=31)
+    with pytest.raises(ib.IB200Error, match="order"):
+        eng.quadgk_batch(F["sinxp"], np.array([-2.0]), np.array([5.0]), np.array([[1.0]]), rule=(np.zeros(2), np.zeros(2), np.zeros(1)))

@@ -313,3 +313,34 @@ def test_quadgk_vector_valued_restatement():
     par = np.array([[1.0, 0.0], [2.0, 0.5]]).T.reshape(2, 2, 1)
     I, E, ne, st = O.quadgk_vec_batch("prodpeak", -INF, INF, par, reltol=1e-9, abstol=0.0)
     assert st[0] == 0 and np.allclose(I[:, 0], [math.pi * 1.0, math.pi * 2.0], rtol=1e-8)
+
+
+def test_kronrod_tables_and_rule_orders():
+    """Gauss-Kronrod tables (integrals.jl_b200/kronrod.py, QuadGK.kronrod layout) and the oracle's rule of any order
+    (QuadGKJL(order = n), src/algorithms.jl:51-56): order 7 equals the built-in QUADPACK constants bit for bit, the Kronrod
+    rule integrates x^k exactly up to degree 3n+1, the embedded Gauss rule up to 2n-1, and every order meets the tolerance"""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from integrals_b200.kronrod import kronrod
+    x, w, wg = kronrod(7)
+    assert x[0] == -0.991455371120812639206854697526329 and w[7] == 0.209482141084727828012999174891714 and wg[3] == 0.417959183673469387755102040816327
+    for n in (2, 3, 7, 10, 15, 21, 30):
+        x, w, wg = kronrod(n)
+        assert len(x) == n + 1 and len(w) == n + 1 and len(wg) == (n + 1) // 2 and x[-1] == 0.0 and np.all(np.diff(x) > 0)
+        xs = np.concatenate([x, -x[:-1][::-1]]); ws = np.concatenate([w, w[:-1][::-1]])          # the full 2n+1 point rule
+        for k in range(0, 3 * n + 2, 2):
+            assert abs(np.sum(ws * xs ** k) - 2.0 / (k + 1)) < 5e-15
+        odd = n % 2 == 1
+        gx = np.concatenate([x[1::2], -x[1::2][::-1][(1 if odd else 0):]]); gw = np.concatenate([wg, wg[::-1][(1 if odd else 0):]])
+        assert len(gx) == n
+        for k in range(0, 2 * n, 2):
+            assert abs(np.sum(gw * gx ** k) - 2.0 / (k + 1)) < 5e-15
+    p = np.array([[1.7, 20.0, 50.0]])
+    exact = (np.cos(-2 * p[0]) - np.cos(5 * p[0])) / p[0]
+    I7, E7, ne7, st7 = O.quadgk_batch("sinxp", -2.0, 5.0, p, reltol=1e-10, abstol=1e-13)
+    for n in (2, 3, 7, 10, 15, 21, 30):
+        x, w, wg = kronrod(n)
+        I, E, ne, st = O.quadgk_rule_batch("sinxp", -2.0, 5.0, p, x, w, wg, reltol=1e-10, abstol=1e-13)
+        assert np.all(st == 0) and np.all(np.abs(I - exact) <= 1e-10 * np.abs(exact) + 1e-13) and np.all((ne - (2 * n + 1)) % (2 * (2 * n + 1)) == 0)
+        if n == 7:
+            assert np.array_equal(I, I7) and np.array_equal(E, E7) and np.array_equal(ne, ne7)
