@@ -327,10 +327,30 @@ def main():
     ib_marker = {"genz_oscillatory": "GenzOscillatory", "genz_product_peak": "GenzProductPeak", "genz_corner_peak": "GenzCornerPeak",
                  "genz_gaussian": "GenzGaussian", "genz_c0": "GenzC0", "genz_discontinuous": "GenzDiscontinuous"}
 
-    def make_c1(abstol=None):
+    def make_c1_vec(ncomp=4):
+        """the C1 sweep as 65,536/ncomp vector-valued problems of ncomp components each (shared subdivision, 2-norm)"""
+        c = WL.C1
+        n = (args.nprob or c["nprob"]) // ncomp
+        par = np.asfortranarray(WL.c1_params(c["nprob"])[:, :n * ncomp].reshape(1, ncomp, n, order="F"))
+        last = {}
+
+        def step(record=False):
+            I, E, ne, st = eng.quadgk_vec_batch(F["sinxp"], c["lb"], c["ub"], par, reltol=c["reltol"], abstol=c["abstol"])
+            last["ev"] = int(ne.sum())
+
+        def finish(kernel_ms_total):
+            return dict(units=n * ncomp, launches=1, flops=last["ev"] * ncomp * WL.quadgk_flops_per_eval(), evals=last["ev"] * ncomp, h2d=n * ncomp * 8, d2h=n * (ncomp * 8 + 20),
+                        kernel="quadgk_vec_kernel<SINXP,true,4> (host buffers: the vector entry point takes host arrays)")
+        return step, step, finish
+
+    def make_c1(abstol=None, order=7):
         c = dict(WL.C1)
         if abstol is not None:
             c["abstol"] = abstol
+        rule = None
+        if order != 7:
+            from integrals_b200.kronrod import kronrod
+            rule = kronrod(order)
         n = args.nprob or c["nprob"]
         par = WL.c1_params(c["nprob"])[:, :n]
         pinned = torch.from_numpy(np.ascontiguousarray(par.T)).pin_memory()
@@ -340,7 +360,8 @@ def main():
         lb, ub = np.array([c["lb"]]), np.array([c["ub"]])
 
         def step(record=False):
-            eng.quadgk_batch(F["sinxp"], lb, ub, dpar, reltol=c["reltol"], abstol=c["abstol"], out_I=oI, out_E=oE, out_nevals=oN, out_status=oS)
+            eng.quadgk_batch(F["sinxp"], lb, ub, dpar, reltol=c["reltol"], abstol=c["abstol"], out_I=oI, out_E=oE, out_nevals=oN, out_status=oS,
+                             rule=rule)
 
         def e2e_step():
             sol = ib.solve(ib.IntegralProblem(ib.SinXP(), (c["lb"], c["ub"]), pinned.numpy().T), ib.QuadGKB200(), engine=eng,
@@ -416,6 +437,27 @@ def main():
                         kernel="strided_kernel<2,8> (2 launches per step: trapezoid, Simpson; + weights and finish kernels)")
         return step, e2e_step, finish
 
+    def make_c2_f32():
+        """Float32 samples on a Float32 grid (ib200_sampled_f32), 4096 x 2^20, strided axis"""
+        m = WL.C2["m"]; n = args.nprob or WL.C2["n"]
+        xs = torch.linspace(0, 1, n, dtype=torch.float32, device="cuda")
+        jj = 1.0 + torch.arange(1, m + 1, dtype=torch.float32, device="cuda") / m
+        y = torch.empty((n, m), dtype=torch.float32, device="cuda")
+        for i0 in range(0, n, 1 << 16):
+            i1 = min(n, i0 + (1 << 16))
+            y[i0:i1] = torch.sin(xs[i0:i1, None] * jj[None, :]) + 1.5
+        out = torch.empty(m, dtype=torch.float32, device="cuda")
+        h = 1.0 / (n - 1)
+
+        def step(record=False):
+            eng.sampled_f32("trapezoid", y, m, n, 1, h=h, out=out)
+            eng.sampled_f32("simpson", y, m, n, 1, h=h, out=out)
+
+        def finish(kernel_ms_total):
+            by = 2 * (4.0 * m * n + 4 * m)
+            return dict(units=by / 1e9, launches=6, bytes=by, h2d=0, d2h=2 * 4 * m, kernel="strided_kernel<float,2,8>")
+        return step, step, finish
+
     def make_c5():
         lb, ub, par, exact = WL.c5_problem()
         budget = 1 << (args.nprob or 26)                # --nprob overrides log2 of the box budget
@@ -442,14 +484,22 @@ def main():
     makers = {"c4": make_c4, "c1": make_c1, "c2": make_c2, "c3": make_c3, "c5": make_c5,
               # side measurements SURVEY 8(d) asks for next to the configs (reported under "secondary" only)
               "c1_abstol_1e-12": lambda: make_c1(abstol=1e-12), "c2_nonuniform_grid": lambda: make_c2(nonuniform=True),
-              "c2_contiguous_axis": lambda: make_c2(contiguous=True), "c4_reduced_difficulty_h/4": lambda: make_c4(scale=0.25)}
+              "c2_contiguous_axis": lambda: make_c2(contiguous=True), "c4_reduced_difficulty_h/4": lambda: make_c4(scale=0.25),
+              # "next" rows of SURVEY 8(f), same measurement as their parent config
+              "c1_order_15": lambda: make_c1(order=15), "c1_vector_valued_4": make_c1_vec, "c2_float32": make_c2_f32}
     EXTRA_UNITS = {"c1_abstol_1e-12": "integrals/s", "c2_nonuniform_grid": "GB/s", "c2_contiguous_axis": "GB/s",
-                   "c4_reduced_difficulty_h/4": "integrals/s"}
+                   "c4_reduced_difficulty_h/4": "integrals/s", "c1_order_15": "integrals/s", "c1_vector_valued_4": "integrals/s",
+                   "c2_float32": "GB/s"}
 
     def run(workload, steps, warmup, with_e2e=True, sample_clocks=False):
         step, e2e_step, finish = makers[workload]()
+        tw = time.perf_counter()
         for _ in range(warmup):
             step()
+        torch.cuda.synchronize()
+        while time.perf_counter() - tw < 0.3:               # millisecond-scale workloads: keep warming until the clocks have ramped
+            step()
+            torch.cuda.synchronize()
         barrier()
         sampler = ClockSampler(local) if sample_clocks else None
         if sampler:
