@@ -497,7 +497,8 @@ def main():
         for _ in range(warmup):
             step()
         torch.cuda.synchronize()
-        while time.perf_counter() - tw < 0.3:               # millisecond-scale workloads: keep warming until the clocks have ramped
+        while world == 1 and time.perf_counter() - tw < 0.3:   # millisecond-scale workloads: keep warming until the clocks have ramped
+            # (single rank only: a time-based count could differ between ranks, and the c5 step contains a collective)
             step()
             torch.cuda.synchronize()
         barrier()
