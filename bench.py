@@ -216,7 +216,7 @@ def workload_config(w, args, **extra):
                "nprob_per_gpu": args.nprob or WL.C3["nprob"]}
     elif w == "c5":
         cfg = {"workload": "C5: one 8-D Genz Gaussian, axes 1-2 on (-inf, inf), axes 3-8 on [0,1], reltol 1e-9, abstol 0, fixed box budget",
-               "log2_box_budget": args.nprob or 26, "parallelism": f"one domain region-partitioned x{args.gpus}, one NCCL all-gather of 2056 words per round"}
+               "log2_box_budget": args.nprob or 26, "parallelism": f"one domain, evaluation partitioned x{args.gpus} over a replicated box store, results exchanged through peer inboxes (NVLink), one 8-double NCCL all-gather per round"}
     else:
         cfg = {"workload": "C2: TrapezoidalRule + SimpsonsRule on 4096 x 1,048,576 fp64 along dim 2 (32 GiB, > L2)",
                "n_per_gpu": args.nprob or WL.C2["n"]}

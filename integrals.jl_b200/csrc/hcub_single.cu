@@ -38,11 +38,12 @@
 // Multi-GPU (one process per GPU): the box store is REPLICATED, the evaluation is PARTITIONED.  Every rank holds the
 // whole store and runs the (cheap, HBM-streaming) histogram / decide / split bookkeeping redundantly on identical
 // data, so the stores stay bit-identical without any box migration.  The expensive part -- the rule on the round's
-// new boxes -- is dealt out box by box (todo index mod world), and the evaluation kernel writes each result (integral,
-// error, split axis: 24 bytes) straight into EVERY rank's store through peer pointers over NVLink (CUDA IPC mappings
-// of the peers' stores): compute and exchange are one kernel, the transfer overlaps the arithmetic box by box.  The
-// round's only collective is an 8-double NCCL all-gather of the partial sums, which doubles as the barrier that makes
-// the peer stores visible before the bookkeeping reads them.  The load is balanced by construction (every box costs
+// new boxes -- is dealt out box by box (todo index mod world).  A rank lists its results (slot, integral, error, split
+// axis: 32 bytes) compactly, a copy kernel pushes the list into every peer's inbox with coalesced 16-byte stores over
+// NVLink (CUDA IPC mappings of the peers' inboxes; two halves alternating with the round parity), and after the round's
+// only collective -- an 8-double NCCL all-gather of the partial sums, which doubles as the barrier that makes the inboxes
+// visible -- every rank scatters the peers' results into its own store.  (A first version stored each result straight
+// into every peer's store from the evaluation kernel: 8-byte remote stores, fine on 2-4 GPUs, slower than 4 GPUs on 8.)  The load is balanced by construction (every box costs
 // the same number of evaluations), whatever the shape of the integrand.
 //
 // Selection differs from the reference (all boxes above a threshold instead of the single worst), so
@@ -89,8 +90,13 @@ struct Params {
     double *sendbuf, *recvbuf;
     State *st;
     int rank, world;
-    double *rec_peer[kMaxWorld];   // every rank's box store (own entry = rec), CUDA IPC mappings
-    double *err_peer[kMaxWorld];
+    // result exchange (world > 1): this rank's results of a round are listed compactly in `outbox` ({slot, I, E, axis}: 32 B),
+    // copied with coalesced 16-byte stores into every peer's `inbox` (CUDA IPC mappings; two round-parity halves, one
+    // segment per sender) and applied to the peer's store after the round's all-gather
+    double *outbox;                // [obcap][4]
+    double *inbox;                 // [2][world][obcap][4]   (this rank's, exported)
+    double *inbox_peer[kMaxWorld]; // the peers' inboxes
+    long long obcap;
     int grid;
 };
 
@@ -309,10 +315,12 @@ eval_kernel(Params p) {
                 if (delta > deltaf) { kd = k; maxdd = dd; hkd = hh[k]; }
                 else if (fabs(delta) <= deltaf && hh[k] > hkd) { kd = k; hkd = hh[k]; }
             }
-            for (int q = 0; q < p.world; q++) {                  // the result goes into every rank's store (NVLink peer stores)
-                double *rq = p.rec_peer[q] + (size_t)slot * RECW;
-                rq[2 * D] = Iv; rq[2 * D + 1] = (double)kd;
-                p.err_peer[q][slot] = Er;
+            r[2 * D] = Iv; r[2 * D + 1] = (double)kd;
+            p.err[slot] = Er;
+            if (p.world > 1) {                                   // t == rank (mod world): entry t / world of this rank's list
+                double2 *ob = reinterpret_cast<double2 *>(p.outbox + (size_t)(t / p.world) * 4);
+                ob[0] = make_double2(__longlong_as_double((long long)slot), Iv);
+                ob[1] = make_double2(Er, (double)kd);
             }
             sumI += Iv; sumE += Er; maxE = fmax(maxE, Er);       // fmax drops NaN: non-finite E is caught through sumE
         }
@@ -355,6 +363,44 @@ __device__ __forceinline__ void fin_reduce3(double &v0, double &v1, double &v2, 
             v0 += __shfl_down_sync(0xffffffffu, v0, off);
             v1 += __shfl_down_sync(0xffffffffu, v1, off);
             v2 = fmax(v2, __shfl_down_sync(0xffffffffu, v2, off));
+        }
+    }
+}
+
+// number of boxes of a round that rank r evaluates (todo indices t == r mod world)
+__device__ __forceinline__ long long share_of(long long ntodo, int r, int world) { return ntodo > r ? (ntodo - r + world - 1) / world : 0; }
+
+// copy this rank's result list into every peer's inbox: coalesced 16-byte stores over NVLink
+__global__ void __launch_bounds__(kBlock)
+publish_kernel(Params p) {
+    const State *st = p.st;
+    if (st->done) return;
+    const long long n2 = 2 * share_of(st->ntodo, p.rank, p.world);                 // double2 elements
+    const size_t half = (size_t)(st->round & 1) * p.world * p.obcap * 4;
+    const double2 *src = reinterpret_cast<const double2 *>(p.outbox);
+    for (int q = 0; q < p.world; q++) {
+        if (q == p.rank) continue;
+        double2 *dst = reinterpret_cast<double2 *>(p.inbox_peer[q] + half + (size_t)p.rank * p.obcap * 4);
+        for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n2; i += (long long)gridDim.x * kBlock) dst[i] = src[i];
+    }
+}
+
+// after the round's all-gather: scatter the peers' results into this rank's store
+__global__ void __launch_bounds__(kBlock)
+apply_kernel(Params p, int recw) {
+    const State *st = p.st;
+    if (st->done) return;
+    const size_t half = (size_t)(st->round & 1) * p.world * p.obcap * 4;
+    for (int q = 0; q < p.world; q++) {
+        if (q == p.rank) continue;
+        const long long n = share_of(st->ntodo, q, p.world);
+        const double2 *src = reinterpret_cast<const double2 *>(p.inbox + half + (size_t)q * p.obcap * 4);
+        for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock) {
+            const double2 e0 = src[2 * i], e1 = src[2 * i + 1];
+            const size_t slot = (size_t)__double_as_longlong(e0.x);
+            double *r = p.rec + slot * recw;
+            r[recw - 2] = e0.y; r[recw - 1] = e1.y;
+            p.err[slot] = e1.x;
         }
     }
 }
@@ -601,7 +647,7 @@ resum_finish_kernel(Params p, double *out /* I, E, applied, boxes, rounds, statu
 }  // namespace hs
 
 // ---- peer mappings of the replicated stores -----------------------------------------------------------------
-// Every rank exports its two store allocations (scratch slots SL_STORE0/1, used by nothing else) with CUDA IPC; the
+// Every rank exports its result inbox (scratch slot SL_STORE0, used by nothing else) with CUDA IPC; the
 // handles travel in one NCCL all-gather.  Opening a mapping costs tens of milliseconds, so mappings are kept across
 // solves.  Exported memory must not be freed while a peer maps it: before a solve the ranks exchange "I have to
 // re-allocate my store" flags, and if any is set EVERY rank closes its mappings (and says so in a second all-gather)
@@ -632,11 +678,10 @@ static int32_t hs_map_peers(ib200_ctx *ctx, hs::Params &p) {
     using namespace hs;
     hs_peer_maps *pc = static_cast<hs_peer_maps *>(ctx->single_peers);
     if (!pc->valid) {
-        struct Msg { cudaIpcMemHandle_t h[2]; };
+        struct Msg { cudaIpcMemHandle_t h[1]; };
         static_assert(sizeof(Msg) % 8 == 0, "message is sent as doubles");
         Msg mine; memset(&mine, 0, sizeof(mine));
-        IB_CUDA(ctx, cudaIpcGetMemHandle(&mine.h[0], p.rec));
-        IB_CUDA(ctx, cudaIpcGetMemHandle(&mine.h[1], p.err));
+        IB_CUDA(ctx, cudaIpcGetMemHandle(&mine.h[0], p.inbox));
         char *dbuf = (char *)ctx->get(SL_IN4, sizeof(Msg) * (size_t)(p.world + 1));
         if (!dbuf) return ib200_fail(ctx, IB200_ERR_OOM, "ib200_hcubature_single: scratch allocation failed");
         std::vector<Msg> all((size_t)p.world);
@@ -647,12 +692,12 @@ static int32_t hs_map_peers(ib200_ctx *ctx, hs::Params &p) {
         IB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         for (int q = 0; q < p.world; q++) {
             if (q == p.rank) continue;
-            for (int k = 0; k < 2; k++) {
+            for (int k = 0; k < 1; k++) {
                 void *ptr = nullptr;
                 const cudaError_t e = cudaIpcOpenMemHandle(&ptr, all[q].h[k], cudaIpcMemLazyEnablePeerAccess);
                 if (e != cudaSuccess) {
                     cudaGetLastError();
-                    return ib200_fail(ctx, IB200_ERR_CUDA, std::string("ib200_hcubature_single: cudaIpcOpenMemHandle (peer store of rank ") +
+                    return ib200_fail(ctx, IB200_ERR_CUDA, std::string("ib200_hcubature_single: cudaIpcOpenMemHandle (inbox of rank ") +
                                                               std::to_string(q) + "): " + cudaGetErrorString(e));
                 }
                 pc->ptr[k][q] = ptr;
@@ -662,8 +707,7 @@ static int32_t hs_map_peers(ib200_ctx *ctx, hs::Params &p) {
     }
     for (int q = 0; q < p.world; q++) {
         if (q == p.rank) continue;
-        p.rec_peer[q] = static_cast<double *>(pc->ptr[0][q]);
-        p.err_peer[q] = static_cast<double *>(pc->ptr[1][q]);
+        p.inbox_peer[q] = static_cast<double *>(pc->ptr[0][q]);
     }
     return IB200_OK;
 }
@@ -742,20 +786,23 @@ static int32_t hs_run(ib200_ctx *ctx, hs::Params &p, double *out6_host) {
         }
         return IB200_OK;
     };
-    if ((rc = barrier())) { cudaFreeHost(done_h); return rc; }       // every rank's init_kernel has run before results arrive in its store
+    // (the inbox halves alternate with the round parity and a rank can be at most one all-gather ahead of its peers, so
+    //  the per-round all-gather is the only synchronisation the exchange needs)
+    if ((rc = barrier())) { cudaFreeHost(done_h); return rc; }       // no results of this solve land in an inbox a peer still reads for the previous one
     for (long long iter = 0; iter < (1LL << 40); iter++) {
         for (int r = 0; r < kRoundsPerCheck; r++) {
-            eval_kernel<FAM, D, ALLFIN><<<grid, kBlock, 0, s>>>(p);          // + peer stores of the results
+            eval_kernel<FAM, D, ALLFIN><<<grid, kBlock, 0, s>>>(p);          // this rank's share of the round
+            if (p.world > 1) publish_kernel<<<grid, kBlock, 0, s>>>(p);      // results -> every peer's inbox (NVLink, coalesced)
             eval_finish_kernel<<<1, kFin, 0, s>>>(p);
             if ((rc = exchange())) { cudaFreeHost(done_h); return rc; }      // partial sums; barrier: every rank's results have landed
+            if (p.world > 1) apply_kernel<<<grid, kBlock, 0, s>>>(p, 2 * D + 2);  // peers' results -> this rank's store
             hist_kernel<<<grid, kBlock, 0, s>>>(p);
             decide_kernel<<<1, kFin, 0, s>>>(p);
             count_kernel<D><<<grid, kBlock, 0, s>>>(p);
             scan_kernel<<<1, kFin, 0, s>>>(p);
             scatter_kernel<D><<<grid, kBlock, 0, s>>>(p);
             split_finish_kernel<<<1, 32, 0, s>>>(p);
-            if ((rc = barrier())) { cudaFreeHost(done_h); return rc; }       // nobody writes results into a store that is still being split
-            ctx->launches += 8;
+            ctx->launches += p.world > 1 ? 10 : 8;
         }
         if (cudaGetLastError() != cudaSuccess) { cudaFreeHost(done_h); return ib200_fail(ctx, IB200_ERR_CUDA, "ib200_hcubature_single: kernel launch failed"); }
         if (cudaMemcpyAsync(done_h, &p.st->done, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
@@ -812,7 +859,7 @@ extern "C" int32_t ib200_hcubature_single(ib200_ctx *ctx, int32_t family, int32_
     const size_t per_box = (size_t)(2 * dim + 2) * 8 + 8 + 4;
     size_t fr = 0, tot = 0;
     IB_CUDA(ctx, cudaMemGetInfo(&fr, &tot));
-    size_t held = ctx->scratch[SL_STORE0].cap + ctx->scratch[SL_STORE1].cap + ctx->scratch[SL_WORK3].cap;
+    size_t held = ctx->scratch[SL_WORK0].cap + ctx->scratch[SL_WORK2].cap + ctx->scratch[SL_WORK3].cap + ctx->scratch[SL_STORE0].cap + ctx->scratch[SL_STORE1].cap;
     long long cap_mem = (long long)(((double)(fr + held) * 0.7) / (double)per_box);
     // default store: what the budget can create on this rank (with 2x slack for imbalance), at most 2^26 boxes
     // (~10 GB in 8-D) unless the caller asks for more through store_boxes
@@ -825,11 +872,13 @@ extern "C" int32_t ib200_hcubature_single(ib200_ctx *ctx, int32_t family, int32_
     double *xb = (double *)ctx->get(SL_WORK1, (size_t)((hs::kXchg + 1) * (p.world + 1) + hs::kBins) * sizeof(double) + sizeof(hs::State) + 64);
     if (!xb) return ib200_fail(ctx, IB200_ERR_OOM, "ib200_hcubature_single: scratch allocation failed");
     const size_t need_rec = (size_t)p.cap * (2 * dim + 2) * sizeof(double), need_err = (size_t)p.cap * sizeof(double);
+    p.obcap = p.world > 1 ? p.cap / p.world + 1024 : 0;        // a round evaluates at most `cap` boxes, this rank 1/world of them
+    const size_t need_inbox = (size_t)2 * p.world * p.obcap * 4 * sizeof(double);
     if (p.world > 1) {
         if (!ctx->single_peers) ctx->single_peers = new hs_peer_maps();
         hs_peer_maps *pc = static_cast<hs_peer_maps *>(ctx->single_peers);
         // flag = store capacity, negated if this rank has to re-allocate an exported buffer
-        const bool regrow = need_rec > ctx->scratch[SL_STORE0].cap || need_err > ctx->scratch[SL_STORE1].cap;
+        const bool regrow = need_inbox > ctx->scratch[SL_STORE0].cap;
         std::vector<double> all;
         if ((rc = hs_gather1(ctx, xb, p.world, regrow ? -(double)p.cap : (double)p.cap, all))) return rc;
         bool any = false;
@@ -843,8 +892,14 @@ extern "C" int32_t ib200_hcubature_single(ib200_ctx *ctx, int32_t family, int32_
             if ((rc = hs_gather1(ctx, xb, p.world, 1.0, all))) return rc;          // every rank has closed its mappings
         }
     }
-    p.rec = (double *)ctx->get(SL_STORE0, need_rec);
-    p.err = (double *)ctx->get(SL_STORE1, need_err);
+    p.rec = (double *)ctx->get(SL_WORK0, need_rec);
+    p.err = (double *)ctx->get(SL_WORK2, need_err);
+    p.outbox = p.inbox = nullptr;
+    if (p.world > 1) {
+        p.inbox = (double *)ctx->get(SL_STORE0, need_inbox);
+        p.outbox = (double *)ctx->get(SL_STORE1, (size_t)p.obcap * 4 * sizeof(double));
+        if (!p.inbox || !p.outbox) return ib200_fail(ctx, IB200_ERR_OOM, "ib200_hcubature_single: exchange buffer allocation failed (pass a smaller store_boxes)");
+    }
     p.todo = (unsigned *)ctx->get(SL_WORK3, (size_t)p.cap * sizeof(unsigned));
     p.partial = (double *)ctx->get(SL_WORK4, (size_t)p.grid * 4 * sizeof(double));
     p.bcount = (long long *)ctx->get(SL_WORK5, (size_t)(p.grid + 1) * sizeof(long long));
@@ -854,7 +909,7 @@ extern "C" int32_t ib200_hcubature_single(ib200_ctx *ctx, int32_t family, int32_
     p.sendbuf = xb; p.recvbuf = xb + hs::kXchg + 1;
     p.hist = reinterpret_cast<unsigned long long *>(xb + (hs::kXchg + 1) * (p.world + 1));
     p.st = reinterpret_cast<hs::State *>(xb + (hs::kXchg + 1) * (p.world + 1) + hs::kBins);
-    for (int q = 0; q < hs::kMaxWorld; q++) { p.rec_peer[q] = p.rec; p.err_peer[q] = p.err; }
+    for (int q = 0; q < hs::kMaxWorld; q++) p.inbox_peer[q] = p.inbox;
     if (p.world > 1 && (rc = hs_map_peers(ctx, p))) return rc;
 
     double res[6] = {0, 0, 0, 0, 0, 0};
