@@ -21,8 +21,6 @@ Differences from the reference, all forced by "CUDA cannot run host closures":
   * `sol.stats` carries the per-problem evaluation counts and status codes the engine returns.
 There is no CPU solve path: every solve goes through libintegrals_b200.so on a B200.
 """
-import math
-
 import numpy as np
 
 from . import _lib

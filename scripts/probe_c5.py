@@ -1,11 +1,8 @@
 """BASELINE config 5 probe: one 8-D Genz Gaussian, axes 1-2 on (-inf, inf), axes 3-8 on [0,1], reltol 1e-9, abstol 0,
 at a sequence of box budgets (python scripts/probe_c5.py [log2 budgets...]); under torchrun it uses all ranks."""
 import json
-import math
 import os
 import sys
-
-import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch                      # noqa: E402

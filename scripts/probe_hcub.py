@@ -1,5 +1,5 @@
 """HCubature throughput probe at scale (4-D Genz families, C4 settings)."""
-import json, sys, time, os
+import json, sys, os
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tests"))
 import numpy as np, torch

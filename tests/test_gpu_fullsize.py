@@ -2,8 +2,6 @@
 (closed forms, exactness of the rules on polynomials, linearity, independence of a problem's result from the batch it is
 solved in) -- the oracle cannot run these sizes in test time.  Tolerances: 1e-12 * sum|w_i f_i| for fixed rules and sampled
 sums; the requested tolerance for adaptive solves (north star)."""
-import math
-
 import numpy as np
 import pytest
 

@@ -7,7 +7,6 @@ import numpy as np
 import pytest
 
 import integrals_b200 as ib
-from integrals_b200 import interface
 
 
 class StubEngine:
