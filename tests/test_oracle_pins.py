@@ -344,3 +344,17 @@ def test_kronrod_tables_and_rule_orders():
         assert np.all(st == 0) and np.all(np.abs(I - exact) <= 1e-10 * np.abs(exact) + 1e-13) and np.all((ne - (2 * n + 1)) % (2 * (2 * n + 1)) == 0)
         if n == 7:
             assert np.array_equal(I, I7) and np.array_equal(E, E7) and np.array_equal(ne, ne7)
+
+
+def test_vector_integrands_reference_known_answers():
+    """test/interface_tests.jl:261-285 ("Standard Single Dimension Vector Integrands", QuadGKJL): f = collect(1.0:nout) on (1, 3)
+    -> (ub - lb) * [1..nout]; through the registered family c * x^k * exp(-a^2 (x-u)^2) with a = 0, k = 0, c = 1..nout"""
+    for nout in (1, 2):
+        par = np.zeros((4, nout, 1), order="F")
+        par[3, :, 0] = np.arange(1, nout + 1)
+        I, E, ne, st = O.quadgk_vec_batch("gausspoly", 1.0, 3.0, par, reltol=1e-5, abstol=1e-5)
+        assert st[0] == 0 and ne[0] == 15 and np.allclose(I[:, 0], 2.0 * np.arange(1, nout + 1), rtol=1e-12)
+    # x^k components share one subdivision: exact for the (7,15) pair, one rule application
+    par = np.zeros((4, 3, 1), order="F"); par[2, :, 0] = [0, 1, 2]; par[3, :, 0] = 1.0
+    I, E, ne, st = O.quadgk_vec_batch("gausspoly", 1.0, 3.0, par, reltol=1e-10, abstol=0.0)
+    assert np.allclose(I[:, 0], [2.0, 4.0, 26.0 / 3.0], rtol=1e-14) and ne[0] == 15
