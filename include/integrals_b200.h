@@ -164,10 +164,12 @@ int32_t ib200_quadgk_vec_batch(ib200_ctx *ctx, int32_t family, int32_t transform
 /* -- one large domain (BASELINE config 5): the same HCubature call, src/Integrals.jl:386-393, for a single
       integral that is too expensive for one warp: region-parallel rounds on a device-resident box queue
       (csrc/hcub_single.cu).  With a communicator (ib200_comm_init) every rank of the job calls this with the
-      same arguments; the domain is partitioned by region and the ranks exchange (integral, error) partial sums
-      once per refinement round over NCCL.  max_boxes: budget of rule applications over all ranks (the analogue
-      of maxiters / points-per-rule); store_boxes: per-GPU box capacity; 0 = what the budget can create on
-      one rank, at most 2^26 boxes and 70 % of the free HBM (a full store ends the solve with IB200_ST_MAXEVALS).
+      same arguments; every rank keeps the whole box store, evaluates its share of each round's new boxes, pushes
+      the results into the peers' inboxes over NVLink (CUDA IPC) and the ranks exchange (integral, error) partial
+      sums once per refinement round over NCCL; every rank returns the same result bit for bit.  max_boxes: budget
+      of rule applications over all ranks (the analogue of maxiters / points-per-rule); store_boxes: box capacity
+      (the same on every rank); 0 = what the budget can create, at most 2^28 boxes (2^26 for an unbounded budget)
+      and 70 % of the free HBM (a full store ends the solve with IB200_ST_MAXEVALS).
       out_stats (may be NULL): int64[6] = integrand evaluations, rule applications, boxes stored, rounds,
       status (IB200_ST_*), world size. */
 int32_t ib200_hcubature_single(ib200_ctx *ctx, int32_t family, int32_t dim, int32_t transform,
