@@ -262,7 +262,9 @@ class IntegralCache:
         return solve_cache(self)
 
 
-def init(prob, alg, engine=None, **kws):
+def init(prob, alg, engine=None, sensealg=None, do_inf_transformation=None, verbose=None, **kws):
+    """init(prob, alg; sensealg, do_inf_transformation, verbose, kws...) (src/common.jl:79-133).  `sensealg` (AD), the
+    deprecated `do_inf_transformation` and `verbose` are accepted like the reference does and have no effect here."""
     if isinstance(prob, SampledIntegralProblem):
         return _init_sampled(prob, alg, engine, **kws)
     kwargs = {**prob.kwargs, **kws}                      # problem kwargs under solve kwargs, common.jl:87
@@ -380,7 +382,7 @@ class SampledIntegralCache:
         return solve_cache(self)
 
 
-def _init_sampled(prob, alg, engine=None, **kws):
+def _init_sampled(prob, alg, engine=None, verbose=None, **kws):
     if kws:
         raise ValueError("There are no keyword arguments allowed to `solve`")     # common.jl:325-326
     if not isinstance(alg, AbstractSampledB200Algorithm):

@@ -179,3 +179,10 @@ def test_vector_valued_routing():    # src/Integrals.jl:316-326 (array-valued in
         ib.QuadGKB200(norm="1")
     with pytest.raises(TypeError):
         ib.VectorOf(ib.VectorOf(ib.SinXP()))
+
+
+def test_init_named_keywords_are_accepted():   # src/common.jl:79-85: sensealg, do_inf_transformation, verbose are not "common kwargs"
+    e = StubEngine()
+    prob = ib.IntegralProblem(ib.SinXP(), (-2.0, 5.0), 1.7)
+    sol = ib.solve(prob, ib.QuadGKB200(), engine=e, reltol=1e-6, verbose=False, sensealg=None, do_inf_transformation=True)
+    assert sol.retcode == ib.ReturnCode.Success and e.calls[-1][2]["reltol"] == 1e-6
