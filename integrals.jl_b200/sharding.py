@@ -18,20 +18,32 @@ def shard_range(nprob, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def _slice_problem(prob, lo, hi):
+def shard_indices(nprob, rank, world, interleave=False):
+    """problem indices of rank `rank`: a contiguous block (default), or every world-th problem starting at `rank`.
+    Interleaving balances batches whose cost varies smoothly with the index (BASELINE config 1: the cost of
+    int sin(x p) grows with p, so contiguous blocks leave the last rank with the expensive end of the sweep)."""
+    if interleave:
+        if world < 1 or not 0 <= rank < world:
+            raise ValueError("bad rank/world")
+        return np.arange(rank, int(nprob), world)
+    lo, hi = shard_range(nprob, rank, world)
+    return np.arange(lo, hi)
+
+
+def _slice_problem(prob, idx):
     lb, ub = prob.domain
     p = np.asarray(prob.p, dtype=np.float64)
     if p.ndim < 2:
         raise ValueError("solve_sharded needs a batch: p must be nparam x nprob")
     lb = np.asarray(lb, dtype=np.float64); ub = np.asarray(ub, dtype=np.float64)
     if lb.ndim == 2:
-        lb, ub = lb[:, lo:hi], ub[:, lo:hi]
-    return prob.remake(p=np.asfortranarray(p[:, lo:hi]), domain=(lb, ub))
+        lb, ub = lb[:, idx], ub[:, idx]
+    return prob.remake(p=np.asfortranarray(p[:, idx]), domain=(lb, ub))
 
 
-def solve_sharded(prob, alg, group=None, local_solve=None, **kws):
-    """solve(prob, alg; kws...) with the columns of prob.p split across the ranks of `group`.
-    Every rank returns the full solution (u, resid, stats concatenated in problem order).
+def solve_sharded(prob, alg, group=None, local_solve=None, interleave=False, **kws):
+    """solve(prob, alg; kws...) with the columns of prob.p split across the ranks of `group` (contiguous blocks, or
+    round-robin with interleave=True).  Every rank returns the full solution (u, resid, stats in problem order).
     `local_solve(prob_block, alg, **kws)` defaults to interface.solve on this rank's GPU."""
     import torch
     import torch.distributed as dist
@@ -42,14 +54,14 @@ def solve_sharded(prob, alg, group=None, local_solve=None, **kws):
         return local_solve(prob, alg, **kws)
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     nprob = np.asarray(prob.p).shape[1]
-    lo, hi = shard_range(nprob, rank, world)
-    sol = local_solve(_slice_problem(prob, lo, hi), alg, **kws)
+    idx = shard_indices(nprob, rank, world, interleave)
+    sol = local_solve(_slice_problem(prob, idx), alg, **kws)
     backend = dist.get_backend(group)
     dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
     # pack [u, resid, nevals, status] per problem into one padded buffer -> one all_gather
-    maxn = max(shard_range(nprob, r, world)[1] - shard_range(nprob, r, world)[0] for r in range(world))
+    maxn = max(len(shard_indices(nprob, r, world, interleave)) for r in range(world))
     pack = np.zeros((4, maxn))
-    n = hi - lo
+    n = len(idx)
     pack[0, :n] = np.atleast_1d(sol.u)
     pack[1, :n] = np.nan if sol.resid is None else np.atleast_1d(sol.resid)
     if sol.stats is not None:
@@ -57,11 +69,10 @@ def solve_sharded(prob, alg, group=None, local_solve=None, **kws):
     mine = torch.from_numpy(pack).to(dev)
     parts = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(parts, mine, group=group)
-    cols = []
+    full = np.zeros((4, nprob))
     for r, t in enumerate(parts):
-        a, b = shard_range(nprob, r, world)
-        cols.append(t.cpu().numpy()[:, :b - a])
-    full = np.concatenate(cols, axis=1)
+        ir = shard_indices(nprob, r, world, interleave)
+        full[:, ir] = t.cpu().numpy()[:, :len(ir)]
     resid = None if sol.resid is None else full[1]
     stats = None if sol.stats is None else dict(nevals=full[2].astype(np.int64), status=full[3].astype(np.int32))
     return interface.IntegralSolution(full[0], resid, prob, sol.alg, sol.retcode, None, stats)

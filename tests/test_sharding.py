@@ -23,6 +23,14 @@ def test_shard_range_partitions():
         sharding.shard_range(10, 2, 2)
 
 
+def test_shard_indices_interleaved():
+    for n in (0, 1, 7, 65536):
+        for w in (1, 2, 3, 8):
+            parts = [sharding.shard_indices(n, r, w, interleave=True) for r in range(w)]
+            assert sorted(np.concatenate(parts).tolist()) == list(range(n)) and max(map(len, parts)) - min(map(len, parts)) <= 1
+            assert np.array_equal(np.concatenate([sharding.shard_indices(n, r, w) for r in range(w)]), np.arange(n))
+
+
 def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
     return p
@@ -52,6 +60,8 @@ def _worker(rank, world, port, q):
         par = np.asfortranarray(np.vstack([np.linspace(1, 3, 9), np.linspace(2, 1, 9), np.full(9, .3), np.full(9, .6)]))
         prob2 = ib.IntegralProblem(ib.GenzGaussian(), (np.zeros(2), np.ones(2)), par)
         sol2 = sharding.solve_sharded(prob2, ib.HCubatureB200(), local_solve=_oracle_solve, reltol=1e-7)
+        sol3 = sharding.solve_sharded(prob, ib.QuadGKB200(), local_solve=_oracle_solve, interleave=True, reltol=1e-10)
+        assert np.array_equal(sol3.u, sol.u) and np.array_equal(sol3.stats["nevals"], sol.stats["nevals"])     # same answers, other partition
         q.put((rank, sol.u, sol.resid, sol.stats["nevals"], sol2.u, sol2.stats["status"]))
     finally:
         dist.destroy_process_group()
