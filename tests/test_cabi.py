@@ -52,3 +52,33 @@ def test_no_gpu_fails_loudly():
         pytest.skip("a GPU is present")
     with pytest.raises(ib.IB200Error, match="no CUDA device|no CPU fallback"):
         ib.Engine(0)
+
+
+def test_ctypes_signatures_match_header():
+    """every prototype in include/integrals_b200.h has the same number of arguments as the ctypes binding declares, and
+    pointer / integer / floating arguments sit at the same positions"""
+    import ctypes as C
+    import re
+    import integrals_b200 as ib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "include", "integrals_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    L = ib.load_library()
+    checked = 0
+    for m in re.finditer(r"\b(?:int32_t|int64_t|double|void|const char \*)\s*\*?\s*(ib200_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+        name, args = m.group(1), m.group(2).strip()
+        fn = getattr(L, name)
+        if fn.argtypes is None:
+            continue
+        params = [] if args in ("", "void") else [a.strip() for a in args.split(",")]
+        assert len(params) == len(fn.argtypes), (name, params, fn.argtypes)
+        for par, ct in zip(params, fn.argtypes):
+            is_ptr = "*" in par
+            if is_ptr:
+                assert ct in (C.c_void_p, C.c_char_p) or hasattr(ct, "contents") or ct.__name__.startswith("LP_"), (name, par, ct)
+            elif par.startswith(("double", "float")):
+                assert ct in (C.c_double, C.c_float), (name, par, ct)
+            else:
+                assert ct in (C.c_int32, C.c_int64, C.c_int), (name, par, ct)
+        checked += 1
+    assert checked >= 15
