@@ -161,6 +161,17 @@ int32_t ib200_quadgk_vec_batch(ib200_ctx *ctx, int32_t family, int32_t transform
                                double reltol, double abstol, int64_t maxevals, int32_t normkind,
                                double *out_I, double *out_E, int64_t *out_nevals, int32_t *out_status);
 
+/* -- the same for N-D: HCubature.hcubature / hquadrature(f, lb, ub; norm, rtol, atol, maxevals, initdiv) with an array-valued
+      integrand, as called at src/Integrals.jl:380-393 with `norm = alg.norm` (HCubatureJL.norm, src/algorithms.jl:66-67,
+      108-115).  params: nparam x ncomp x nprob; the components share the points and the subdivision; a box's error is
+      norm(I - I') over the components, the split axis is chosen from the norms of the fourth differences; stop when
+      E <= max(rtol * norm(I), atol).  1 <= dim <= 8, 1 <= ncomp <= 8.  out_I: ncomp x nprob. */
+int32_t ib200_hcubature_vec_batch(ib200_ctx *ctx, int32_t family, int32_t dim, int32_t transform,
+                                  const double *lb, const double *ub, int32_t bounds_per_problem,
+                                  const double *params, int32_t nparam, int32_t ncomp, int64_t nprob,
+                                  double reltol, double abstol, int64_t maxevals, int32_t initdiv, int32_t normkind,
+                                  double *out_I, double *out_E, int64_t *out_nevals, int32_t *out_status);
+
 /* -- one large domain (BASELINE config 5): the same HCubature call, src/Integrals.jl:386-393, for a single
       integral that is too expensive for one warp: region-parallel rounds on a device-resident box queue
       (csrc/hcub_single.cu).  With a communicator (ib200_comm_init) every rank of the job calls this with the

@@ -24,7 +24,7 @@ ERR_NAMES = {-1: "IB200_ERR_INVALID", -2: "IB200_ERR_CUDA", -3: "IB200_ERR_OOM",
 SYMBOLS = ["ib200_version", "ib200_create", "ib200_destroy", "ib200_last_error", "ib200_set_stream",
            "ib200_synchronize", "ib200_kernel_launches", "ib200_family_nparam", "ib200_last_kernel_ms",
            "ib200_set_option", "ib200_sampled", "ib200_sampled_f32", "ib200_fixed_rule_tensor_batch", "ib200_fixed_rule_nodes_batch",
-           "ib200_gauss_legendre_batch", "ib200_quadgk_batch", "ib200_quadgk_rule_batch", "ib200_quadgk_vec_batch", "ib200_hcubature_batch", "ib200_measure_fp64_peak",
+           "ib200_gauss_legendre_batch", "ib200_quadgk_batch", "ib200_quadgk_rule_batch", "ib200_quadgk_vec_batch", "ib200_hcubature_batch", "ib200_hcubature_vec_batch", "ib200_measure_fp64_peak",
            "ib200_hcubature_single", "ib200_comm_unique_id", "ib200_comm_init", "ib200_comm_destroy"]
 
 
@@ -76,6 +76,8 @@ def load_library():
     L.ib200_sampled_f32.argtypes = [vp, i32, vp, i64, i64, i64, C.c_float, vp, vp]; L.ib200_sampled_f32.restype = i32
     L.ib200_hcubature_batch.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp, i32, i64, dp, dp, i64, i32, vp, vp, vp, vp]
     L.ib200_hcubature_batch.restype = i32
+    L.ib200_hcubature_vec_batch.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp, i32, i32, i64, dp, dp, i64, i32, i32, vp, vp, vp, vp]
+    L.ib200_hcubature_vec_batch.restype = i32
     L.ib200_hcubature_single.argtypes = [vp, i32, i32, i32, vp, vp, vp, i32, dp, dp, i64, i64, C.POINTER(dp), C.POINTER(dp), vp]
     L.ib200_hcubature_single.restype = i32
     L.ib200_comm_unique_id.argtypes = [vp]; L.ib200_comm_unique_id.restype = i32
@@ -301,6 +303,25 @@ class Engine:
                                                  a[3][0], a[4][0], a[5][0], a[6][0]))
         return out_I, out_E, out_nevals, out_status
 
+    def hcubature_vec_batch(self, family, dim, lb, ub, params, reltol=1e-8, abstol=1e-8, maxevals=MAXEVALS_UNBOUNDED, initdiv=1,
+                            transform=0, norm="2"):
+        """Vector-valued HCubature: params nparam x ncomp x nprob (column-major; nparam x ncomp = one problem); lb, ub of
+        length dim (shared) or dim x nprob.  -> I (ncomp x nprob, column-major), E (nprob), nevals, status."""
+        params = np.asfortranarray(params, dtype=np.float64)
+        if params.ndim == 2:
+            params = params.reshape(params.shape + (1,), order="F")
+        nparam, ncomp, nprob = params.shape
+        lb = np.asfortranarray(np.atleast_1d(lb), dtype=np.float64); ub = np.asfortranarray(np.atleast_1d(ub), dtype=np.float64)
+        if lb.shape != ub.shape or lb.shape[0] != dim or (lb.ndim == 2 and lb.shape[1] != nprob) or lb.ndim > 2:
+            raise ValueError(f"bounds must have {dim} entries or be {dim} x {nprob}")
+        bpp = 1 if lb.ndim == 2 else 0
+        out_I = np.empty((ncomp, nprob), order="F"); out_E = np.empty(nprob)
+        out_nevals = np.empty(nprob, dtype=np.int64); out_status = np.empty(nprob, dtype=np.int32)
+        self._check(self.L.ib200_hcubature_vec_batch(self.h, family, dim, transform, lb.ctypes.data, ub.ctypes.data, bpp, params.ctypes.data,
+                                                     nparam, ncomp, nprob, float(reltol), float(abstol),
+                                                     int(min(maxevals, MAXEVALS_UNBOUNDED)), int(initdiv), {"2": 0, "inf": 1}[norm],
+                                                     out_I.ctypes.data, out_E.ctypes.data, out_nevals.ctypes.data, out_status.ctypes.data))
+        return out_I, out_E, out_nevals, out_status
 
     def hcubature_single(self, family, dim, lb, ub, params, reltol=1e-8, abstol=1e-8, max_boxes=1 << 24, store_boxes=0,
                          transform=0):

@@ -170,7 +170,8 @@ class VectorOf(RegisteredIntegrand):
     """Vector-valued integrand built from one registered family: component c is `base` with parameter column
     p[:, c].  `prob.p` is nparam x ncomp (one problem, `sol.u` a vector of ncomp) or nparam x ncomp x nprob (a batch,
     `sol.u` ncomp x nprob).  The reference's counterpart is an array-valued integrand with an `integrand_prototype`
-    (src/Integrals.jl:226-239, 316-326): all components share nodes and subdivision, the error is a norm over them."""
+    (src/Integrals.jl:226-239, 316-326, 380-393): all components share nodes and subdivision, the error is a norm over them.
+    Integrated by QuadGKB200 (1-D) and HCubatureB200 (1..8-D)."""
 
     def __init__(self, base):
         if not isinstance(base, RegisteredIntegrand) or isinstance(base, VectorOf):
@@ -182,7 +183,7 @@ class VectorOf(RegisteredIntegrand):
         return self.base.nparam(dim)
 
     def supports_dim(self, dim):
-        return dim == 1 and self.base.supports_dim(1)
+        return self.base.supports_dim(dim)
 
     def __call__(self, x, p):
         p = np.asarray(p, dtype=float)

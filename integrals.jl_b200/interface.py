@@ -162,7 +162,12 @@ class HCubatureB200(AbstractB200Algorithm):
     (ib200_hcubature_single; all ranks of the engine's communicator take part); `maxiters` then bounds the
     integrand evaluations summed over all ranks, as it does for HCubatureJL."""
 
-    def __init__(self, initdiv=1, single_domain=False, store_boxes=0):
+    def __init__(self, initdiv=1, single_domain=False, store_boxes=0, norm="2"):
+        """norm: "2" (LinearAlgebra.norm, the HCubatureJL default, src/algorithms.jl:115) or "inf"; only used by vector-valued
+        integrands (VectorOf)."""
+        if norm not in ("2", "inf"):
+            raise ValueError('HCubatureB200 supports norm = "2" or "inf"')
+        self.norm = norm
         self.initdiv = int(initdiv)
         self.single_domain = bool(single_domain)
         self.store_boxes = int(store_boxes)
@@ -344,20 +349,30 @@ def solve_cache(cache):
 
 
 def _solve_vector(cache, prob, inner, tr):
-    """array-valued integrand (src/Integrals.jl:316-326): QuadGK with a norm over the components"""
-    if not isinstance(inner, QuadGKB200):
-        raise TypeError("vector-valued registered integrands (VectorOf) are integrated by QuadGKB200")
-    if inner.order != 7:
-        raise ValueError("vector-valued QuadGKB200 solves use the (7,15) pair")
-    lb, ub = prob.domain
-    if np.ndim(lb) > 1 or (np.ndim(lb) == 1 and np.size(lb) != 1 and np.ndim(prob.p) != 3):
-        raise ValueError("QuadGKB200 only accepts one-dimensional quadrature problems.")
+    """array-valued integrand: QuadGK (src/Integrals.jl:316-326) or HCubature (:380-393) with a norm over the components"""
     p = np.asarray(prob.p, dtype=np.float64)
     if p.ndim not in (2, 3):
         raise ValueError("VectorOf needs p of shape nparam x ncomp (or nparam x ncomp x nprob)")
     kw = cache.kwargs
-    I, E, ne, st = cache.cacheval.quadgk_vec_batch(cache.f.family, lb, ub, p, reltol=kw.get("reltol", 1e-8), abstol=kw.get("abstol", 1e-8),
-                                                   maxevals=kw.get("maxiters", _lib.MAXEVALS_UNBOUNDED), transform=tr, norm=inner.norm)
+    tol = dict(reltol=kw.get("reltol", 1e-8), abstol=kw.get("abstol", 1e-8), maxevals=kw.get("maxiters", _lib.MAXEVALS_UNBOUNDED))
+    lb, ub = prob.domain
+    if isinstance(inner, HCubatureB200):
+        if inner.single_domain:
+            raise ValueError("HCubatureB200(single_domain=True) integrates scalar integrands")
+        lb = np.atleast_1d(np.asarray(lb, dtype=np.float64)); ub = np.atleast_1d(np.asarray(ub, dtype=np.float64))
+        dim = lb.shape[0]
+        if not cache.f.supports_dim(dim):
+            raise ValueError(f"{cache.f!r} is not defined in {dim} dimensions")
+        I, E, ne, st = cache.cacheval.hcubature_vec_batch(cache.f.family, dim, lb, ub, p, initdiv=inner.initdiv, transform=tr,
+                                                          norm=inner.norm, **tol)
+    elif isinstance(inner, QuadGKB200):
+        if inner.order != 7:
+            raise ValueError("vector-valued QuadGKB200 solves use the (7,15) pair")
+        if np.ndim(lb) > 1 or (np.ndim(lb) == 1 and np.size(lb) != 1 and p.ndim != 3):
+            raise ValueError("QuadGKB200 only accepts one-dimensional quadrature problems.")
+        I, E, ne, st = cache.cacheval.quadgk_vec_batch(cache.f.family, lb, ub, p, transform=tr, norm=inner.norm, **tol)
+    else:
+        raise TypeError("vector-valued registered integrands (VectorOf) are integrated by QuadGKB200 or HCubatureB200")
     if p.ndim == 2:
         return IntegralSolution(I[:, 0].copy(), float(E[0]), prob, inner, ReturnCode.Success, None, dict(nevals=ne, status=st))
     return IntegralSolution(I, E, prob, inner, ReturnCode.Success, None, dict(nevals=ne, status=st))

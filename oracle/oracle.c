@@ -1004,6 +1004,259 @@ int orc_hcubature(orc_integrand f, void *user, int dim, const double *a, const d
 }
 
 /* ------------------------------------------------------------------------------------------
+ * HCubature with a vector-valued integrand and a norm: HCubatureJL.norm
+ * (src/algorithms.jl:66-67,108-115) is forwarded as `norm = alg.norm` at src/Integrals.jl:380-393.
+ * The rule is applied component-wise on shared points; a box's error is norm(I - I') over the
+ * components, the fourth differences that choose the split axis are norms too, the stopping test
+ * is E <= max(rtol*norm(I), atol); everything else is orc_hcubature.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct { double a[ORC_MAXDIM], b[ORC_MAXDIM], I[ORC_MAXCOMP], E; int kdiv; } orc_vbox;
+
+static void vaxpy(double *acc, const double *v, int nc) { for (int c = 0; c < nc; c++) acc[c] += v[c]; }
+
+static void gm_rule_vec(orc_vec_integrand f, void *user, int nc, int n, const double *a, const double *b, int normkind,
+                        double *Iout, double *Eout, int *kdiv_out)
+{
+    const double l2 = sqrt(9.0 / 70.0), l3 = sqrt(9.0 / 10.0), l4 = l3, l5 = sqrt(9.0 / 19.0);
+    const double twon = (double)(1 << n);
+    const double w1 = twon * ((12824 - 9120 * n + 400 * n * n) / 19683.0);
+    const double w2 = twon * (980 / 6561.0);
+    const double w3 = twon * ((1820 - 400 * n) / 19683.0);
+    const double w4 = twon * (200 / 19683.0);
+    const double w5 = 6859 / 19683.0;
+    const double w4p = twon * (25 / 729.0);
+    const double w3p = twon * ((265 - 100 * n) / 1458.0);
+    const double w2p = twon * (245 / 486.0);
+    const double w1p = twon * ((729 - 950 * n + 50 * n * n) / 729.0);
+
+    double c[ORC_MAXDIM], d[ORC_MAXDIM], x[ORC_MAXDIM], divdiff[ORC_MAXDIM];
+    double f1[ORC_MAXCOMP], f2[ORC_MAXCOMP] = {0}, f3[ORC_MAXCOMP] = {0}, f4[ORC_MAXCOMP] = {0}, f5[ORC_MAXCOMP] = {0};
+    double fa[ORC_MAXCOMP], fb[ORC_MAXCOMP], f2i[ORC_MAXCOMP], f3i[ORC_MAXCOMP], dd[ORC_MAXCOMP];
+    double V = 1.0;
+    for (int i = 0; i < n; i++) {
+        c[i] = 0.5 * (a[i] + b[i]);
+        d[i] = 0.5 * fabs(b[i] - a[i]);
+        V = (i == 0) ? d[i] : V * d[i];
+    }
+    for (int i = 0; i < n; i++) x[i] = c[i];
+    f(x, n, user, f1);
+    for (int i = 0; i < n; i++) {
+        double p2 = d[i] * l2, p3 = d[i] * l3;
+        x[i] = c[i] + p2; f(x, n, user, fa);
+        x[i] = c[i] - p2; f(x, n, user, fb);
+        for (int k = 0; k < nc; k++) f2i[k] = fa[k] + fb[k];
+        x[i] = c[i] + p3; f(x, n, user, fa);
+        x[i] = c[i] - p3; f(x, n, user, fb);
+        for (int k = 0; k < nc; k++) f3i[k] = fa[k] + fb[k];
+        x[i] = c[i];
+        vaxpy(f2, f2i, nc); vaxpy(f3, f3i, nc);
+        for (int k = 0; k < nc; k++) dd[k] = f3i[k] + 12 * f1[k] - 7 * f2i[k];
+        divdiff[i] = vnorm(dd, nc, normkind);
+    }
+    for (int i = 0; i < n - 1; i++)
+        for (int j = i + 1; j < n; j++) {
+            double pi_ = d[i] * l4, pj = d[j] * l4;
+            for (int s = 0; s < 4; s++) {
+                x[i] = (s & 2) ? c[i] - pi_ : c[i] + pi_;
+                x[j] = (s & 1) ? c[j] - pj : c[j] + pj;
+                f(x, n, user, fa); vaxpy(f4, fa, nc);
+            }
+            x[i] = c[i]; x[j] = c[j];
+        }
+    for (int s = 0; s < (1 << n); s++) {
+        for (int i = 0; i < n; i++) {
+            double p = d[i] * l5;
+            x[i] = ((s >> i) & 1) ? c[i] - p : c[i] + p;
+        }
+        f(x, n, user, fa); vaxpy(f5, fa, nc);
+    }
+    for (int k = 0; k < nc; k++) {
+        double I = V * (w1 * f1[k] + w2 * f2[k] + w3 * f3[k] + w4 * f4[k] + w5 * f5[k]);
+        double Ip = V * (w1p * f1[k] + w2p * f2[k] + w3p * f3[k] + w4p * f4[k]);
+        Iout[k] = I; dd[k] = I - Ip;
+    }
+    double E = vnorm(dd, nc, normkind);
+    int kdiv = 0;
+    double maxdivdiff = 0.0;
+    double deltaf = E / (pow(10.0, n) * V);
+    for (int i = 0; i < n; i++) {
+        double delta = divdiff[i] - maxdivdiff;
+        if (delta > deltaf) { kdiv = i; maxdivdiff = divdiff[i]; }
+        else if (fabs(delta) <= deltaf && d[i] > d[kdiv]) kdiv = i;
+    }
+    *Eout = E; *kdiv_out = kdiv;
+}
+
+/* HCubature's 1-D rule (GK(7,15) about the centre, signed half-width) on a vector */
+static void gk_rule_hc_vec(orc_vec_integrand f, void *user, int nc, double a, double b, int normkind, double *Iout, double *Eout, int *kdiv)
+{
+    double c = (a + b) * 0.5, D = (b - a) * 0.5, x;
+    double fa[ORC_MAXCOMP], fb[ORC_MAXCOMP], I[ORC_MAXCOMP], Ip[ORC_MAXCOMP], dd[ORC_MAXCOMP];
+    x = c; f(&x, 1, user, fa);
+    for (int k = 0; k < nc; k++) { I[k] = fa[k] * GK_W[7]; Ip[k] = fa[k] * GK_WG[3]; }
+    for (int i = 1; i <= 7; i++) {
+        double Dx = D * GK_X[i - 1];
+        x = c + Dx; f(&x, 1, user, fa);
+        x = c - Dx; f(&x, 1, user, fb);
+        for (int k = 0; k < nc; k++) {
+            double fx = fa[k] + fb[k];
+            I[k] += fx * GK_W[i - 1];
+            if ((i & 1) == 0) Ip[k] += fx * GK_WG[(i >> 1) - 1];
+        }
+    }
+    for (int k = 0; k < nc; k++) { I[k] *= D; Ip[k] *= D; Iout[k] = I[k]; dd[k] = I[k] - Ip[k]; }
+    *Eout = vnorm(dd, nc, normkind); *kdiv = 0;
+}
+
+static void cubrule_vec(orc_vec_integrand f, void *user, int nc, int dim, const double *a, const double *b, int normkind,
+                        double *I, double *E, int *kdiv)
+{
+    if (dim == 1) gk_rule_hc_vec(f, user, nc, a[0], b[0], normkind, I, E, kdiv);
+    else gm_rule_vec(f, user, nc, dim, a, b, normkind, I, E, kdiv);
+}
+
+/* the BinaryMaxHeap of orc_hcubature on vector boxes */
+static void vbox_bubble_up(orc_vbox *t, int64_t i)
+{
+    orc_vbox v = t[i];
+    while (i > 1) {
+        int64_t p = i >> 1;
+        if (!(v.E > t[p].E)) break;
+        t[i] = t[p]; i = p;
+    }
+    t[i] = v;
+}
+static void vbox_bubble_down(orc_vbox *t, int64_t i, int64_t n)
+{
+    orc_vbox v = t[i];
+    int swapped = 1;
+    int64_t last_parent = n >> 1;
+    while (swapped && i <= last_parent) {
+        int64_t lc = i << 1;
+        if (lc < n) {
+            int64_t rc = lc + 1;
+            if (t[rc].E > t[lc].E) {
+                if (t[rc].E > v.E) { t[i] = t[rc]; i = rc; } else swapped = 0;
+            } else {
+                if (t[lc].E > v.E) { t[i] = t[lc]; i = lc; } else swapped = 0;
+            }
+        } else {
+            if (t[lc].E > v.E) { t[i] = t[lc]; i = lc; } else swapped = 0;
+        }
+    }
+    t[i] = v;
+}
+
+int orc_hcubature_vec(orc_vec_integrand f, void *user, int nc, int dim, const double *a, const double *b,
+                      double rtol, double atol, int64_t maxevals, int initdiv, int normkind,
+                      double *Iout, double *Eout, int64_t *nevals_out)
+{
+    if (nc < 1 || nc > ORC_MAXCOMP || dim < 1 || dim > ORC_MAXDIM || initdiv < 1 || rtol < 0 || atol < 0 || maxevals < 0) return -1;
+    if (rtol == 0 && atol == 0) rtol = sqrt(2.220446049250313e-16);
+    const int64_t evals_per_box = dim == 1 ? 15 : 1 + 4 * dim + 2 * dim * (dim - 1) + (1 << dim);
+    int64_t numevals = evals_per_box, cap = 256, len = 0;
+    double Delta[ORC_MAXDIM], I[ORC_MAXCOMP];
+    orc_vbox first;
+    double prodD = 1.0;
+    for (int i = 0; i < dim; i++) {
+        Delta[i] = (b[i] - a[i]) / initdiv;
+        prodD *= Delta[i];
+        first.a[i] = a[i];
+        first.b[i] = initdiv == 1 ? b[i] : a[i] + Delta[i];
+    }
+    cubrule_vec(f, user, nc, dim, first.a, first.b, normkind, first.I, &first.E, &first.kdiv);
+    double E = first.E;
+    for (int c = 0; c < nc; c++) I[c] = first.I[c];
+    if (prodD == 0.0) { for (int c = 0; c < nc; c++) Iout[c] = I[c]; *Eout = E; if (nevals_out) *nevals_out = numevals; return 0; }
+    orc_vbox *t = (orc_vbox *)malloc(sizeof(orc_vbox) * (size_t)(cap + 1));
+    t[++len] = first;
+    if (initdiv > 1) {
+        int ci[ORC_MAXDIM] = {0};
+        int64_t total = 1;
+        for (int i = 0; i < dim; i++) total *= initdiv;
+        for (int64_t q = 1; q < total; q++) {
+            int k = 0;
+            while (++ci[k] == initdiv) { ci[k] = 0; k++; }
+            orc_vbox bx;
+            for (int i = 0; i < dim; i++) {
+                bx.a[i] = a[i] + ci[i] * Delta[i];
+                bx.b[i] = (ci[i] == initdiv - 1) ? b[i] : bx.a[i] + Delta[i];
+            }
+            cubrule_vec(f, user, nc, dim, bx.a, bx.b, normkind, bx.I, &bx.E, &bx.kdiv);
+            vaxpy(I, bx.I, nc); E += bx.E; numevals += evals_per_box;
+            if (len + 1 > cap) { cap *= 2; t = (orc_vbox *)realloc(t, sizeof(orc_vbox) * (size_t)(cap + 1)); }
+            t[++len] = bx; vbox_bubble_up(t, len);
+        }
+    }
+    int status = 0;
+    for (;;) {
+        if (E <= fmax(rtol * vnorm(I, nc, normkind), atol)) break;
+        if (numevals >= maxevals) { status = 1; break; }
+        if (!isfinite(E)) { status = 2; break; }
+        orc_vbox box = t[1];
+        if (len == 1) len = 0;
+        else { t[1] = t[len--]; vbox_bubble_down(t, 1, len); }
+        int k = box.kdiv;
+        double w = (box.b[k] - box.a[k]) * 0.5;
+        orc_vbox b1 = box, b2 = box;
+        b1.a[k] = box.a[k] + w;            /* upper half first */
+        cubrule_vec(f, user, nc, dim, b1.a, b1.b, normkind, b1.I, &b1.E, &b1.kdiv);
+        b2.b[k] = box.b[k] - w;
+        cubrule_vec(f, user, nc, dim, b2.a, b2.b, normkind, b2.I, &b2.E, &b2.kdiv);
+        numevals += 2 * evals_per_box;
+        for (int c = 0; c < nc; c++) I[c] += b1.I[c] + b2.I[c] - box.I[c];
+        E += b1.E + b2.E - box.E;
+        if (len + 2 > cap) { cap *= 2; t = (orc_vbox *)realloc(t, sizeof(orc_vbox) * (size_t)(cap + 1)); }
+        t[++len] = b1; vbox_bubble_up(t, len);
+        t[++len] = b2; vbox_bubble_up(t, len);
+    }
+    for (int c = 0; c < nc; c++) I[c] = 0.0;
+    E = 0.0;
+    for (int64_t i = 1; i <= len; i++) { vaxpy(I, t[i].I, nc); E += t[i].E; }
+    free(t);
+    for (int c = 0; c < nc; c++) Iout[c] = I[c];
+    *Eout = E;
+    if (nevals_out) *nevals_out = numevals;
+    return status;
+}
+
+/* batch driver over the registered family: component c of problem k uses parameter column params[:, c, k]; the
+   automatic ChangeOfVariables (common.jl:97-103) is shared by the components */
+typedef struct { int fam, nc, nparam, tr; const double *par; const double *lb, *ub; } orc_vecfam_nd_user;
+static void orc_vecfam_nd_eval(const double *t, int dim, void *user, double *out)
+{
+    const orc_vecfam_nd_user *u = (const orc_vecfam_nd_user *)user;
+    double x[ORC_MAXDIM], jac = 1.0;
+    for (int i = 0; i < dim; i++) {
+        double ji;
+        orc_t2ujac(u->tr, t[i], u->lb[i], u->ub[i], &x[i], &ji);
+        jac = (i == 0) ? ji : jac * ji;
+    }
+    for (int c = 0; c < u->nc; c++) out[c] = orc_family_eval(u->fam, dim, x, u->par + (size_t)c * u->nparam) * jac;
+}
+int orc_hcubature_vec_batch(int fam, int dim, const double *lb, const double *ub, int bpp, int tr,
+                            const double *params, int nparam, int ncomp, int64_t nprob,
+                            double reltol, double abstol, int64_t maxiters, int initdiv, int normkind,
+                            double *I, double *E, int64_t *nevals, int32_t *status, int nthreads)
+{
+    if (orc_family_nparam(fam, dim) != nparam || ncomp < 1 || ncomp > ORC_MAXCOMP) return -1;
+    if (nthreads < 1) nthreads = 1;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+    for (int64_t k = 0; k < nprob; k++) {
+        const double *l = bpp ? lb + k * dim : lb, *u = bpp ? ub + k * dim : ub;
+        orc_vecfam_nd_user fu = {fam, ncomp, nparam, tr, params + (size_t)k * nparam * ncomp, l, u};
+        double tl[ORC_MAXDIM], tu[ORC_MAXDIM];
+        for (int i = 0; i < dim; i++) orc_u2t(l[i], u[i], &tl[i], &tu[i]);
+        int64_t ne = 0;
+        int st = orc_hcubature_vec(orc_vecfam_nd_eval, &fu, ncomp, dim, tl, tu, reltol, abstol, maxiters, initdiv, normkind,
+                                   I + (size_t)k * ncomp, &E[k], &ne);
+        if (nevals) nevals[k] = ne;
+        if (status) status[k] = st;
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
  * Round-synchronous variant of the HCubature loop (NOT in the reference): the checker for
  * ib200_hcubature_single (csrc/hcub_single.cu), which replaces the strictly sequential "pop the
  * worst box" order of HCubature.hcubature (call site src/Integrals.jl:386-393) by rounds --

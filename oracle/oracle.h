@@ -112,6 +112,16 @@ int orc_quadgk_vec_batch(int fam, const double *lb, const double *ub, int bounds
 int orc_hcubature(orc_integrand f, void *user, int dim, const double *a, const double *b,
                   double rtol, double atol, int64_t maxevals, int initdiv,
                   double *I, double *E, int64_t *nevals, int64_t *nboxes);
+/* HCubature with a vector-valued integrand and a norm (HCubatureJL.norm, src/algorithms.jl:66-67,108-115; forwarded at
+   src/Integrals.jl:380-393): box error = norm(I - I'), fourth differences = norms, stop when E <= max(rtol*norm(I), atol) */
+int orc_hcubature_vec(orc_vec_integrand f, void *user, int ncomp, int dim, const double *a, const double *b,
+                      double rtol, double atol, int64_t maxevals, int initdiv, int normkind,
+                      double *I, double *E, int64_t *nevals);
+/* params: nparam x ncomp x nprob (column-major); I: ncomp x nprob; E: nprob */
+int orc_hcubature_vec_batch(int fam, int dim, const double *lb, const double *ub, int bounds_per_problem, int tr,
+                            const double *params, int nparam, int ncomp, int64_t nprob,
+                            double reltol, double abstol, int64_t maxiters, int initdiv, int normkind,
+                            double *I, double *E, int64_t *nevals, int32_t *status, int nthreads);
 /* one application of the cubature rule on box [a,b] (for unit tests) */
 void orc_cubrule(orc_integrand f, void *user, int dim, const double *a, const double *b,
                  double *I, double *E, int *kdiv);

@@ -321,6 +321,28 @@ def hcubature_batch(fam, lb, ub, params, tr="if_inf", reltol=1e-8, abstol=1e-8, 
     return I, E, ne, st
 
 
+def hcubature_vec_batch(fam, lb, ub, params, tr="if_inf", reltol=1e-8, abstol=1e-8, maxiters=2**62, initdiv=1, norm="2", nthreads=1):
+    """vector-valued HCubature: params nparam x ncomp x nprob (Fortran order); lb, ub of length dim (or dim x nprob)
+    -> I (ncomp x nprob), E, nevals, status"""
+    fam = FAM[fam] if isinstance(fam, str) else fam
+    params = np.asfortranarray(params, dtype=np.float64)
+    if params.ndim == 2:
+        params = params.reshape(params.shape + (1,), order="F")
+    nparam, ncomp, nprob = params.shape
+    lb = np.asfortranarray(np.atleast_1d(lb), dtype=np.float64); ub = np.asfortranarray(np.atleast_1d(ub), dtype=np.float64)
+    dim = lb.shape[0]
+    bpp = 1 if lb.ndim == 2 else 0
+    I = np.empty((ncomp, nprob), order="F"); E = np.empty(nprob); ne = np.empty(nprob, np.int64); st = np.empty(nprob, np.int32)
+    L = lib()
+    L.orc_hcubature_vec_batch.argtypes = [C.c_int, C.c_int, _dp, _dp, C.c_int, C.c_int, _dp, C.c_int, C.c_int, C.c_int64, C.c_double,
+                                          C.c_double, C.c_int64, C.c_int, C.c_int, _dp, _dp, _i64p, _i32p, C.c_int]
+    rc = L.orc_hcubature_vec_batch(fam, dim, _p(lb), _p(ub), bpp, TR[tr], params.ctypes.data_as(_dp), nparam, ncomp, nprob, reltol,
+                                   abstol, maxiters, initdiv, 0 if norm == "2" else 1, I.ctypes.data_as(_dp), _p(E),
+                                   ne.ctypes.data_as(_i64p), st.ctypes.data_as(_i32p), nthreads)
+    assert rc == 0, rc
+    return I, E, ne, st
+
+
 def hcubature_rounds(fam, lb, ub, params, tr="if_inf", reltol=1e-8, abstol=1e-8, max_boxes=1 << 24, m0=0):
     """Round-synchronous refinement of ONE integral (checker for Engine.hcubature_single).
     -> I, E, dict(rule_applications, boxes, rounds, status)."""

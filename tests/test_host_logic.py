@@ -175,6 +175,29 @@ def test_vector_valued_routing():    # src/Integrals.jl:316-326 (array-valued in
     assert sol.u.shape == (3, 7) and sol.resid.shape == (7,) and e.calls[-1][2]["norm"] == "2"
     with pytest.raises(TypeError, match="QuadGKB200"):
         ib.solve(ib.IntegralProblem(f, (-2.0, 5.0), np.zeros((1, 3))), ib.GaussLegendreB200(n=4), engine=e)
+    # HCubatureJL.norm (src/algorithms.jl:66-67,108-115; forwarded at src/Integrals.jl:380-393): N-D vector integrands
+    class EH(StubEngine):
+        def hcubature_vec_batch(self, fam, dim, lb, ub, p, **k):
+            self._rec("hcubature_vec", fam, dim, lb, ub, p, **k)
+            p = np.asarray(p); nc = p.shape[1]; n = p.shape[2] if p.ndim == 3 else 1
+            return np.zeros((nc, n), order="F"), np.zeros(n), np.zeros(n, np.int64), np.zeros(n, np.int32)
+    e = EH()
+    g = ib.VectorOf(ib.CosProduct())
+    sol = ib.solve(ib.IntegralProblem(g, (np.ones(2), 3 * np.ones(2)), np.ones((2, 2))), ib.HCubatureB200(norm="inf", initdiv=2), engine=e,
+                   reltol=1e-5, abstol=1e-5, maxiters=10**6)
+    name, a, k = e.calls[-1]
+    assert name == "hcubature_vec" and a[1] == 2 and k["norm"] == "inf" and k["initdiv"] == 2 and k["maxevals"] == 10**6
+    assert k["reltol"] == 1e-5 and k["abstol"] == 1e-5 and k["transform"] == 0 and sol.u.shape == (2,) and isinstance(sol.resid, float)
+    sol = ib.solve(ib.IntegralProblem(g, (np.ones(3), 3 * np.ones(3)), np.ones((3, 4, 5))), ib.HCubatureB200(), engine=e)
+    assert sol.u.shape == (4, 5) and sol.resid.shape == (5,) and e.calls[-1][2]["norm"] == "2" and sol.retcode == ib.ReturnCode.Success
+    sol = ib.solve(ib.IntegralProblem(ib.VectorOf(ib.SinXP()), (1.0, 3.0), np.ones((1, 2))), ib.HCubatureB200(), engine=e)   # hquadrature
+    assert e.calls[-1][1][1] == 1 and sol.u.shape == (2,)
+    with pytest.raises(ValueError, match="not defined in 2 dimensions"):
+        ib.solve(ib.IntegralProblem(ib.VectorOf(ib.SinXP()), (np.ones(2), 3 * np.ones(2)), np.ones((1, 2))), ib.HCubatureB200(), engine=e)
+    with pytest.raises(ValueError, match="single_domain"):
+        ib.solve(ib.IntegralProblem(g, (np.ones(2), 3 * np.ones(2)), np.ones((2, 2))), ib.HCubatureB200(single_domain=True), engine=e)
+    with pytest.raises(ValueError):
+        ib.HCubatureB200(norm="1")
     with pytest.raises(ValueError):
         ib.QuadGKB200(norm="1")
     with pytest.raises(TypeError):

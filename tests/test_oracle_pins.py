@@ -358,3 +358,53 @@ def test_vector_integrands_reference_known_answers():
     par = np.zeros((4, 3, 1), order="F"); par[2, :, 0] = [0, 1, 2]; par[3, :, 0] = 1.0
     I, E, ne, st = O.quadgk_vec_batch("gausspoly", 1.0, 3.0, par, reltol=1e-10, abstol=0.0)
     assert np.allclose(I[:, 0], [2.0, 4.0, 26.0 / 3.0], rtol=1e-14) and ne[0] == 15
+
+
+# ------------------------------------------------------------------------------------- vector-valued HCubature
+def test_hcubature_vector_valued_restatement():
+    """orc_hcubature_vec (HCubature with an array-valued integrand and `norm = alg.norm`, src/Integrals.jl:380-393;
+    HCubatureJL.norm, src/algorithms.jl:66-67,108-115): one component reproduces the scalar solver bit for bit (both norms,
+    Genz-Malik and the 1-D GK rule, initdiv > 1, infinite axes); several components share one subdivision and each meets its
+    closed form within the tolerance that the norm of the whole vector sets"""
+    rng = np.random.default_rng(7)
+    for fam, d, kw in (("gauss", 3, {}), ("osc", 2, {}), ("prodpeak", 4, {}), ("c0", 2, {}), ("gauss", 1, {}), ("corner", 3, dict(initdiv=2)),
+                       ("discont", 2, {})):
+        par = np.asfortranarray(np.vstack([rng.uniform(1, 4, (d, 4)), rng.uniform(0.1, 0.9, (d, 4))]))
+        I, E, ne, st = O.hcubature_batch(fam, np.zeros(d), np.ones(d), par, reltol=1e-7, abstol=0.0, maxiters=100000, **kw)
+        for norm in ("2", "inf"):
+            Iv, Ev, nev, stv = O.hcubature_vec_batch(fam, np.zeros(d), np.ones(d), par.reshape(2 * d, 1, 4, order="F"), reltol=1e-7, abstol=0.0,
+                                                     maxiters=100000, norm=norm, **kw)
+            assert np.array_equal(I, Iv[0]) and np.array_equal(E, Ev) and np.array_equal(ne, nev) and np.array_equal(st, stv)
+    par = np.array([[0.8, 1.3], [0.2, -0.4]])                      # exp(-a^2 (x-u)^2) over R^2: pi / (a1 a2)
+    I, E, ne, st = O.hcubature_batch("gauss", [-INF, -INF], [INF, INF], par.reshape(4, 1), reltol=1e-6, abstol=0.0)
+    Iv, Ev, nev, stv = O.hcubature_vec_batch("gauss", [-INF, -INF], [INF, INF], par.reshape(4, 1, 1), reltol=1e-6, abstol=0.0)
+    assert Iv[0, 0] == I[0] and Ev[0] == E[0] and nev[0] == ne[0] and abs(I[0] - math.pi / (0.8 * 1.3)) < 2e-6 * I[0]
+    # three Gaussians of different width on [0,1]^3
+    a = np.array([[1.0, 2.0, 3.0], [4.0, 2.0, 1.0], [6.0, 5.0, 4.0]]); u = np.array([[0.5, 0.4, 0.3], [0.2, 0.8, 0.5], [0.6, 0.5, 0.4]])
+    par = np.asfortranarray(np.concatenate([a, u], axis=1).T.reshape(6, 3, 1))
+    exact = np.array([math.prod(math.sqrt(math.pi) / (2 * ai) * (math.erf(ai * (1 - ui)) + math.erf(ai * ui)) for ai, ui in zip(a[c], u[c]))
+                      for c in range(3)])
+    for norm, nrm in (("2", np.linalg.norm(exact)), ("inf", np.abs(exact).max())):
+        I, E, ne, st = O.hcubature_vec_batch("gauss", np.zeros(3), np.ones(3), par, reltol=1e-8, abstol=0.0, norm=norm)
+        assert st[0] == 0 and E[0] <= 1e-8 * nrm * (1 + 1e-12) and np.all(np.abs(I[:, 0] - exact) <= 1e-8 * nrm)
+        # the shared subdivision is at least as fine as what the hardest component needs alone under the same absolute target
+        Is, Es, nes, _ = O.hcubature_batch("gauss", np.zeros(3), np.ones(3), par[:, 2, :], reltol=0.0, abstol=1e-8 * nrm)
+        assert ne[0] >= nes[0]
+    # maxevals and the evaluation count: 33 points per 3-D box, two boxes per refinement
+    I, E, ne, st = O.hcubature_vec_batch("gauss", np.zeros(3), np.ones(3), par, reltol=1e-14, abstol=0.0, maxiters=1000)
+    assert st[0] == 1 and ne[0] == 33 + 66 * 15
+
+
+def test_hcubature_vector_integrands_reference_known_answers():
+    """test/interface_tests.jl:287-312 ("Standard Vector Integrands", HCubatureJL, dim 1..2, nout 1..2, reltol = abstol = 1e-5):
+    f = collect(1.0:nout) on [1,3]^dim -> prod(ub - lb) * [1..nout]; prod(cos.(x)) -> prod(sin(3) - sin(1))"""
+    for dim in (1, 2):
+        lb, ub = np.ones(dim), 3 * np.ones(dim)
+        for nout in (1, 2):
+            par = np.zeros((3 * dim + 1, nout, 1), order="F")
+            par[3 * dim, :, 0] = np.arange(1, nout + 1)              # c * x^0 * exp(0)
+            I, E, ne, st = O.hcubature_vec_batch("gausspoly", lb, ub, par, reltol=1e-5, abstol=1e-5)
+            assert st[0] == 0 and ne[0] == (15 if dim == 1 else 17) and np.allclose(I[:, 0], 2.0 ** dim * np.arange(1, nout + 1), rtol=1e-13)
+            I, E, ne, st = O.hcubature_vec_batch("cosprod", lb, ub, np.ones((dim, nout, 1)), reltol=1e-5, abstol=1e-5)
+            assert st[0] == 0 and np.allclose(I[:, 0], (math.sin(3.0) - math.sin(1.0)) ** dim, rtol=1e-2)
+            assert np.all(np.abs(I[:, 0] - (math.sin(3.0) - math.sin(1.0)) ** dim) <= 1e-5)
