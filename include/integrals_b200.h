@@ -194,6 +194,32 @@ int32_t ib200_comm_unique_id(void *id128);
 int32_t ib200_comm_init(ib200_ctx *ctx, int32_t nranks, int32_t rank, const void *id128);
 int32_t ib200_comm_destroy(ib200_ctx *ctx);
 
+/* -- BatchIntegralFunction bridge: adaptive integration of ONE integral whose integrand is evaluated
+      by the CALLER on batches of points -- the engine-side half of BatchIntegralFunction (src/Integrals.jl:274-315, where
+      QuadGKJL hands QuadGK a BatchIntegrand; pts is dim x n, one point per column, values a vector of n).  The engine
+      keeps the box store, the rule's points, the weighted sums, error estimates, split axes and the refinement rounds of
+      ib200_hcubature_single on the device and hands out each round's points; there are no callbacks:
+          ib200_batch_open(ctx, dim, transform, lb, ub, reltol, abstol, max_boxes, store_boxes)
+          for (;;) { ib200_batch_next(ctx, &n); if (n == 0) break;
+                     ib200_batch_points(ctx, x, n);      x[dim x n] column-major, in the caller's ORIGINAL coordinates
+                     y[j] = f(x[:, j]) for j < n         (host loop, CuArray broadcast, ...)
+                     ib200_batch_values(ctx, y, n); }
+          ib200_batch_result(ctx, &I, &E, stats)
+      x and y may be host or device pointers (device x is complete when ib200_batch_points returns; device y must be complete --
+      its producer stream synchronised or shared through ib200_set_stream -- when ib200_batch_values is called).  The ChangeOfVariables of src/common.jl:97-103 stays inside the engine (the
+      Jacobians of a round's points are kept on the device and applied to the values).  Rule: Genz-Malik 7/5 (dim >= 2) or
+      GK(7,15) (1-D) per box, as HCubature; a round bisects every box the reference's worst-first loop would provably
+      bisect too (csrc/hcub_single.cu), so n grows geometrically and the number of rounds is O(log #boxes).  max_boxes:
+      budget of rule applications (maxiters / points per rule); store_boxes: box capacity (0 = derived from max_boxes, at
+      most 2^22).  One bridge solve per context at a time; other calls on the context may be interleaved.
+      out_stats (may be NULL): int64[6] = integrand evaluations, rule applications, boxes stored, rounds, status, 1. */
+int32_t ib200_batch_open(ib200_ctx *ctx, int32_t dim, int32_t transform, const double *lb, const double *ub,
+                         double reltol, double abstol, int64_t max_boxes, int64_t store_boxes);
+int32_t ib200_batch_next(ib200_ctx *ctx, int64_t *npoints);
+int32_t ib200_batch_points(ib200_ctx *ctx, double *x, int64_t npoints);
+int32_t ib200_batch_values(ib200_ctx *ctx, const double *y, int64_t npoints);
+int32_t ib200_batch_result(ib200_ctx *ctx, double *out_I, double *out_E, int64_t *out_stats);
+
 /* -- measurement helper: dependency-free DFMA chains on every SM; returns TFLOP/s (2 flops/DFMA).
       This is the FP64 roofline denominator. */
 int32_t ib200_measure_fp64_peak(ib200_ctx *ctx, double *tflops, double *ms);

@@ -25,7 +25,8 @@ SYMBOLS = ["ib200_version", "ib200_create", "ib200_destroy", "ib200_last_error",
            "ib200_synchronize", "ib200_kernel_launches", "ib200_family_nparam", "ib200_last_kernel_ms",
            "ib200_set_option", "ib200_sampled", "ib200_sampled_f32", "ib200_fixed_rule_tensor_batch", "ib200_fixed_rule_nodes_batch",
            "ib200_gauss_legendre_batch", "ib200_quadgk_batch", "ib200_quadgk_rule_batch", "ib200_quadgk_vec_batch", "ib200_hcubature_batch", "ib200_hcubature_vec_batch", "ib200_measure_fp64_peak",
-           "ib200_hcubature_single", "ib200_comm_unique_id", "ib200_comm_init", "ib200_comm_destroy"]
+           "ib200_hcubature_single", "ib200_batch_open", "ib200_batch_next", "ib200_batch_points", "ib200_batch_values",
+           "ib200_batch_result", "ib200_comm_unique_id", "ib200_comm_init", "ib200_comm_destroy"]
 
 
 class IB200Error(RuntimeError):
@@ -80,6 +81,11 @@ def load_library():
     L.ib200_hcubature_vec_batch.restype = i32
     L.ib200_hcubature_single.argtypes = [vp, i32, i32, i32, vp, vp, vp, i32, dp, dp, i64, i64, C.POINTER(dp), C.POINTER(dp), vp]
     L.ib200_hcubature_single.restype = i32
+    L.ib200_batch_open.argtypes = [vp, i32, i32, vp, vp, dp, dp, i64, i64]; L.ib200_batch_open.restype = i32
+    L.ib200_batch_next.argtypes = [vp, C.POINTER(i64)]; L.ib200_batch_next.restype = i32
+    L.ib200_batch_points.argtypes = [vp, vp, i64]; L.ib200_batch_points.restype = i32
+    L.ib200_batch_values.argtypes = [vp, vp, i64]; L.ib200_batch_values.restype = i32
+    L.ib200_batch_result.argtypes = [vp, C.POINTER(dp), C.POINTER(dp), vp]; L.ib200_batch_result.restype = i32
     L.ib200_comm_unique_id.argtypes = [vp]; L.ib200_comm_unique_id.restype = i32
     L.ib200_comm_init.argtypes = [vp, i32, i32, vp]; L.ib200_comm_init.restype = i32
     L.ib200_comm_destroy.argtypes = [vp]; L.ib200_comm_destroy.restype = i32
@@ -335,6 +341,67 @@ class Engine:
                                                   C.byref(I), C.byref(E), st.ctypes.data))
         return I.value, E.value, dict(nevals=int(st[0]), rule_applications=int(st[1]), boxes=int(st[2]), rounds=int(st[3]),
                                       status=int(st[4]), world=int(st[5]))
+
+    # ---- BatchIntegralFunction bridge: caller-evaluated integrand ----------------------------------
+    def batch_open(self, dim, lb, ub, reltol=1e-8, abstol=1e-8, max_boxes=1 << 20, store_boxes=0, transform=0):
+        lb = np.ascontiguousarray(np.atleast_1d(lb), dtype=np.float64); ub = np.ascontiguousarray(np.atleast_1d(ub), dtype=np.float64)
+        if lb.shape != (dim,) or ub.shape != (dim,):
+            raise ValueError(f"bounds must have {dim} entries")
+        self._check(self.L.ib200_batch_open(self.h, int(dim), int(transform), lb.ctypes.data, ub.ctypes.data, float(reltol), float(abstol),
+                                            int(min(max_boxes, MAXEVALS_UNBOUNDED)), int(store_boxes)))
+
+    def batch_next(self):
+        """number of points of the next round; 0 = the solve has finished"""
+        n = C.c_int64()
+        self._check(self.L.ib200_batch_next(self.h, C.byref(n)))
+        return n.value
+
+    def batch_points(self, x, n):
+        """fill x (dim x n column-major: numpy array of shape (n, dim) C-order / (dim, n) F-order, or a torch CUDA tensor (n, dim))"""
+        xp, _k = _ptr(x)
+        self._check(self.L.ib200_batch_points(self.h, xp, int(n)))
+
+    def batch_values(self, y, n):
+        yp, _k = _ptr(y)
+        self._check(self.L.ib200_batch_values(self.h, yp, int(n)))
+
+    def batch_result(self):
+        I = C.c_double(); E = C.c_double(); st = np.zeros(6, dtype=np.int64)
+        self._check(self.L.ib200_batch_result(self.h, C.byref(I), C.byref(E), st.ctypes.data))
+        return I.value, E.value, dict(nevals=int(st[0]), rule_applications=int(st[1]), boxes=int(st[2]), rounds=int(st[3]), status=int(st[4]))
+
+    def integrate_batch(self, f, dim, lb, ub, reltol=1e-8, abstol=1e-8, max_boxes=1 << 20, store_boxes=0, transform=0, device=False):
+        """Adaptive integral of a caller-evaluated batch integrand.  f(pts) -> values: pts is a float64 array of shape (dim, n)
+        ((n,) in 1-D), one point per column like the reference's BatchIntegralFunction; with device=True pts is a torch CUDA
+        tensor of shape (n, dim) ((n,) in 1-D; the same memory) and f returns a CUDA tensor of n values, no host copies.
+        -> I, E, stats."""
+        self.batch_open(dim, lb, ub, reltol=reltol, abstol=abstol, max_boxes=max_boxes, store_boxes=store_boxes, transform=transform)
+        batches = 0
+        while True:
+            n = self.batch_next()
+            if n == 0:
+                break
+            if device:
+                import torch
+                x = torch.empty((n, dim) if dim > 1 else (n,), dtype=torch.float64, device=torch.device("cuda", self.device))
+                self.batch_points(x, n)
+                self.synchronize()                          # the points are written on the engine's stream
+                y = f(x)
+                if not (hasattr(y, "is_cuda") and y.is_cuda and y.dtype == torch.float64 and y.numel() == n):
+                    raise ValueError(f"the batch integrand must return {n} float64 values on the device")
+                y = y.contiguous()
+                torch.cuda.current_stream(y.device).synchronize()
+            else:
+                x = np.empty((dim, n) if dim > 1 else (n,), dtype=np.float64, order="F")
+                self.batch_points(x, n)
+                y = np.ascontiguousarray(f(x), dtype=np.float64)
+                if y.shape != (n,):
+                    raise ValueError(f"the batch integrand must return {n} values, got shape {y.shape}")
+            self.batch_values(y, n)
+            batches += 1
+        I, E, stats = self.batch_result()
+        stats["batches"] = batches
+        return I, E, stats
 
     # ---- multi-GPU communicator (single-domain solve) ------------------------------------------
     def comm_unique_id(self):

@@ -30,6 +30,8 @@ struct ib200_ctx {
     void *comm = nullptr;                    // ncclComm_t of the multi-GPU single-domain solve (hcub_single.cu)
     int comm_rank = 0, comm_world = 1;
     void *single_peers = nullptr;            // hcub_single.cu: CUDA IPC mappings of the peers' box stores
+    void *batch = nullptr;                   // batch_bridge.cu: state of the open caller-evaluated solve
+    void (*batch_free)(void *) = nullptr;
     struct Buf { void *p = nullptr; size_t cap = 0; } scratch[SL_COUNT];
     // options
     int64_t opt_adaptive_warps_per_sm = 0;   // 0 = kernel default

@@ -49,6 +49,7 @@ extern "C" void ib200_destroy(ib200_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     ib200_comm_destroy(ctx);
+    if (ctx->batch && ctx->batch_free) { ctx->batch_free(ctx->batch); ctx->batch = nullptr; }
     for (auto &b : ctx->scratch) if (b.p) cudaFree(b.p);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);

@@ -70,14 +70,31 @@ transformation_cot_inf = _Transformation("transformation_cot_inf")   # :405-410
 # ---------------------------------------------------------------------------------------------
 # problems
 # ---------------------------------------------------------------------------------------------
+class BatchIntegralFunction:
+    """BatchIntegralFunction(f) (SciMLBase; used at src/Integrals.jl:274-315): f(pts, p) evaluates the integrand at a whole batch of
+    points -- pts has shape (dim, n), one point per column ((n,) in 1-D) -- and returns n values.  This is the one way to
+    integrate an arbitrary (host or device) closure with the B200 engine: the engine owns the points and the adaptive
+    refinement on the device (ib200_batch_*), the caller evaluates.  device=True: pts is a torch CUDA tensor of shape (n, dim)
+    ((n,) in 1-D; the same memory as the column-major dim x n matrix) and f returns a CUDA tensor -- no host copies."""
+
+    def __init__(self, f, device=False):
+        if not callable(f):
+            raise TypeError("BatchIntegralFunction wraps a callable f(pts, p)")
+        self.f, self.device = f, bool(device)
+
+    def __call__(self, pts, p):
+        return self.f(pts, p)
+
+
 class IntegralProblem:
     """IntegralProblem(f, domain, p=None, **kwargs).  domain = (lb, ub): scalars (1-D), vectors of
     length dim, or dim x nprob arrays (per-problem bounds).  p: nparam numbers or nparam x nprob."""
 
     def __init__(self, f, domain, p=None, **kwargs):
-        if not isinstance(f, RegisteredIntegrand):
+        if not isinstance(f, (RegisteredIntegrand, BatchIntegralFunction)):
             raise TypeError("the B200 engine integrates registered device-side integrands only "
-                            "(integrals_b200.integrands); arbitrary host closures cannot run on the device")
+                            "(integrals_b200.integrands) or a BatchIntegralFunction (caller-evaluated batches of points); "
+                            "arbitrary pointwise host closures cannot run on the device")
         if not (isinstance(domain, (tuple, list)) and len(domain) == 2):
             raise TypeError("domain must be a tuple (lb, ub)")
         self.f = f
@@ -295,6 +312,8 @@ def solve_cache(cache):
     eng = cache.cacheval
     prob = IntegralProblem(cache.f, cache.domain, cache.p, **cache.prob_kwargs)     # build_problem, common.jl:255-257
     inner, tr = cache.alg.alg, cache.alg.fu2gv.id
+    if isinstance(cache.f, BatchIntegralFunction):
+        return _solve_batch_function(cache, prob, inner, tr)
     if isinstance(cache.f, VectorOf):
         return _solve_vector(cache, prob, inner, tr)
     dim, lb, ub, p, nprob, scalar = _problem_shapes(prob)
@@ -346,6 +365,35 @@ def solve_cache(cache):
     if scalar and not hasattr(I, "data_ptr"):
         I = float(I[0]); E = None if E is None else float(E[0])
     return IntegralSolution(I, E, prob, inner, ReturnCode.Success, None, stats)   # Success unconditionally, Integrals.jl:338,396
+
+
+def _solve_batch_function(cache, prob, inner, tr):
+    """BatchIntegralFunction (src/Integrals.jl:274-315): the engine hands out each refinement round's points, `f(pts, p)`
+    evaluates them.  QuadGKB200 (1-D, GK(7,15) per segment) and HCubatureB200 (Genz-Malik per box) share the round driver."""
+    lb, ub = prob.domain
+    lb = np.atleast_1d(np.asarray(lb, dtype=np.float64)); ub = np.atleast_1d(np.asarray(ub, dtype=np.float64))
+    if lb.ndim != 1 or lb.shape != ub.shape:
+        raise ValueError("a BatchIntegralFunction problem has one domain: bounds of length dim")
+    dim = lb.shape[0]
+    if isinstance(inner, QuadGKB200):
+        if dim != 1:
+            raise ValueError("QuadGKB200 only accepts one-dimensional quadrature problems.")    # Integrals.jl:263-266
+        if inner.order != 7:
+            raise ValueError("BatchIntegralFunction solves use the (7,15) pair")
+    elif isinstance(inner, HCubatureB200):
+        if inner.initdiv != 1:
+            raise ValueError("BatchIntegralFunction solves do not take initdiv")
+    else:
+        raise TypeError("a BatchIntegralFunction is integrated by QuadGKB200 (1-D) or HCubatureB200")
+    kw = cache.kwargs
+    npts = 15 if dim == 1 else 1 + 4 * dim + 2 * dim * (dim - 1) + (1 << dim)
+    maxiters = kw.get("maxiters", _lib.MAXEVALS_UNBOUNDED)
+    max_boxes = max(1, min(int(maxiters), _lib.MAXEVALS_UNBOUNDED) // npts)
+    p = prob.p
+    I, E, stats = cache.cacheval.integrate_batch(lambda pts: cache.f(pts, p), dim, lb, ub, reltol=kw.get("reltol", 1e-8),
+                                                 abstol=kw.get("abstol", 1e-8), max_boxes=max_boxes,
+                                                 store_boxes=getattr(inner, "store_boxes", 0), transform=tr, device=cache.f.device)
+    return IntegralSolution(I, E, prob, inner, ReturnCode.Success, None, stats)
 
 
 def _solve_vector(cache, prob, inner, tr):

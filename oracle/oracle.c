@@ -1273,7 +1273,7 @@ int orc_hcubature_rounds(orc_integrand f, void *user, int dim, const double *a, 
                          double rtol, double atol, int64_t max_boxes, int m0,
                          double *Iout, double *Eout, int64_t *napplied_out, int64_t *nboxes_out, int64_t *rounds_out)
 {
-    if (dim < 2 || dim > ORC_MAXDIM || rtol < 0 || atol < 0 || max_boxes < 1 || m0 < 0 || m0 > 30) return -1;
+    if (dim < 1 || dim > ORC_MAXDIM || rtol < 0 || atol < 0 || max_boxes < 1 || m0 < 0 || m0 > 30) return -1;
     if (rtol == 0 && atol == 0) rtol = sqrt(2.220446049250313e-16);
     int64_t cap = (1LL << m0) + 1024, len = 0, ntodo = 0, applied = 0, rounds = 0;
     orc_box *t = (orc_box *)malloc(sizeof(orc_box) * (size_t)cap);
@@ -1295,7 +1295,7 @@ int orc_hcubature_rounds(orc_integrand f, void *user, int dim, const double *a, 
         double mx = 0.0;
         for (int64_t j = 0; j < ntodo; j++) {
             orc_box *bx = &t[todo[j]];
-            gm_rule(f, user, dim, bx->a, bx->b, &bx->I, &bx->E, &bx->kdiv);
+            orc_cubrule(f, user, dim, bx->a, bx->b, &bx->I, &bx->E, &bx->kdiv);   /* Genz-Malik, or GK(7,15) in 1-D */
             I += bx->I; E += bx->E; if (bx->E > mx) mx = bx->E;
         }
         applied += ntodo; rounds++; ntodo = 0;

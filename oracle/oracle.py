@@ -355,6 +355,22 @@ def hcubature_rounds(fam, lb, ub, params, tr="if_inf", reltol=1e-8, abstol=1e-8,
     return I.value, E.value, dict(rule_applications=na.value, boxes=nb.value, rounds=nr.value, status=st)
 
 
+def solve_hcubature_rounds(f, lb, ub, tr="if_inf", reltol=1e-8, abstol=1e-8, max_boxes=1 << 20, m0=0):
+    """Round-synchronous refinement of ONE integral of a Python callable f(x: ndarray[dim]) (1-D: x is a float): the checker of
+    the BatchIntegralFunction bridge (csrc/batch_bridge.cu).  -> I, E, dict(rule_applications, boxes, rounds, status)."""
+    cb = _wrap(f)
+    lb, ub, d = _bounds(lb, ub)
+    I = C.c_double(); E = C.c_double(); na = C.c_int64(); nb = C.c_int64(); nr = C.c_int64()
+    L = lib()
+    L.orc_solve_hcubature_rounds.argtypes = [_INTEGRAND, C.c_void_p, C.c_int, _dp, _dp, C.c_int, C.c_double, C.c_double, C.c_int64, C.c_int,
+                                             C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                             C.POINTER(C.c_int64)]
+    st = L.orc_solve_hcubature_rounds(cb, None, d, _p(lb), _p(ub), TR[tr], reltol, abstol, max_boxes, m0,
+                                      C.byref(I), C.byref(E), C.byref(na), C.byref(nb), C.byref(nr))
+    assert st >= 0, st
+    return I.value, E.value, dict(rule_applications=na.value, boxes=nb.value, rounds=nr.value, status=st)
+
+
 def fixed_tensor_batch(fam, lb, ub, params, x1d, w1d, tr="if_inf", nthreads=1):
     lb = np.asarray(lb, dtype=np.float64); dim = lb.shape[0]
     fam, params, nparam, nprob, lb, ub, bpp = _batch_common(fam, dim, lb, ub, params)

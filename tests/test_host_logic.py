@@ -209,3 +209,40 @@ def test_init_named_keywords_are_accepted():   # src/common.jl:79-85: sensealg, 
     prob = ib.IntegralProblem(ib.SinXP(), (-2.0, 5.0), 1.7)
     sol = ib.solve(prob, ib.QuadGKB200(), engine=e, reltol=1e-6, verbose=False, sensealg=None, do_inf_transformation=True)
     assert sol.retcode == ib.ReturnCode.Success and e.calls[-1][2]["reltol"] == 1e-6
+
+
+def test_batch_integral_function_routing():    # src/Integrals.jl:274-315 (BatchIntegralFunction); SURVEY 8(f) rank 3
+    class EB(StubEngine):
+        def integrate_batch(self, f, dim, lb, ub, **k):
+            self._rec("integrate_batch", f, dim, lb, ub, **k)
+            pts = np.zeros((dim, 4)) if dim > 1 else np.zeros(4)
+            self.values = f(pts)
+            return 1.5, 1e-9, dict(status=0, batches=1)
+    e = EB()
+    seen = {}
+
+    def f(pts, p):
+        seen["shape"], seen["p"] = pts.shape, p
+        return np.ones(pts.shape[-1])
+    sol = ib.solve(ib.IntegralProblem(ib.BatchIntegralFunction(f), (np.zeros(3), np.ones(3)), 2.5), ib.HCubatureB200(store_boxes=4096), engine=e,
+                   reltol=1e-6, abstol=1e-7, maxiters=33 * 1000 + 5)
+    name, a, k = e.calls[-1]
+    assert name == "integrate_batch" and a[1] == 3 and k["reltol"] == 1e-6 and k["abstol"] == 1e-7 and k["max_boxes"] == 1000
+    assert k["store_boxes"] == 4096 and k["transform"] == 0 and k["device"] is False and seen == {"shape": (3, 4), "p": 2.5}
+    assert sol.u == 1.5 and sol.resid == 1e-9 and sol.retcode == ib.ReturnCode.Success and sol.stats["batches"] == 1
+    sol = ib.solve(ib.IntegralProblem(ib.BatchIntegralFunction(f, device=True), (-2.0, np.inf)), ib.ChangeOfVariables(ib.transformation_tan_inf, ib.QuadGKB200()),
+                   engine=e, maxiters=100)
+    name, a, k = e.calls[-1]
+    assert a[1] == 1 and k["max_boxes"] == 6 and k["transform"] == 1 and k["device"] is True and seen["shape"] == (4,) and seen["p"] is None
+    with pytest.raises(ValueError, match="one-dimensional"):
+        ib.solve(ib.IntegralProblem(ib.BatchIntegralFunction(f), (np.zeros(2), np.ones(2))), ib.QuadGKB200(), engine=e)
+    with pytest.raises(ValueError, match="initdiv"):
+        ib.solve(ib.IntegralProblem(ib.BatchIntegralFunction(f), (np.zeros(2), np.ones(2))), ib.HCubatureB200(initdiv=2), engine=e)
+    with pytest.raises(TypeError, match="QuadGKB200"):
+        ib.solve(ib.IntegralProblem(ib.BatchIntegralFunction(f), (0.0, 1.0)), ib.GaussLegendreB200(n=4), engine=e)
+    with pytest.raises(ib.CommonKwargError):
+        ib.solve(ib.IntegralProblem(ib.BatchIntegralFunction(f), (0.0, 1.0)), ib.QuadGKB200(), engine=e, tol=1e-3)
+    with pytest.raises(TypeError):
+        ib.BatchIntegralFunction(3.0)
+    with pytest.raises(TypeError, match="BatchIntegralFunction"):
+        ib.IntegralProblem(lambda x, p: x, (0.0, 1.0))

@@ -408,3 +408,17 @@ def test_hcubature_vector_integrands_reference_known_answers():
             I, E, ne, st = O.hcubature_vec_batch("cosprod", lb, ub, np.ones((dim, nout, 1)), reltol=1e-5, abstol=1e-5)
             assert st[0] == 0 and np.allclose(I[:, 0], (math.sin(3.0) - math.sin(1.0)) ** dim, rtol=1e-2)
             assert np.all(np.abs(I[:, 0] - (math.sin(3.0) - math.sin(1.0)) ** dim) <= 1e-5)
+
+
+def test_round_synchronous_restatement_in_one_dimension():
+    """orc_hcubature_rounds with HCubature's 1-D rule (GK(7,15) per segment): the checker of the 1-D BatchIntegralFunction bridge.
+    README example: the rounds bisect exactly the segments QuadGK's worst-first loop bisects (75 evaluations, E = 5.69e-9);
+    infinite domain; agreement with the reference-order solver within the tolerance"""
+    I, E, st = O.solve_hcubature_rounds(lambda x: math.sin(1.7 * x), [-2.0], [5.0], reltol=1e-10, abstol=1e-8)
+    Iq, Eq, neq, stq = O.solve_quadgk(lambda x: math.sin(1.7 * x), -2.0, 5.0, reltol=1e-10, abstol=1e-8)
+    assert st["status"] == 0 and 15 * st["rule_applications"] == neq == 75 and abs(I - Iq) <= 1e-15 and abs(E - Eq) <= 1e-15
+    assert abs(I - (math.cos(-3.4) - math.cos(8.5)) / 1.7) < 1e-14
+    I, E, st = O.solve_hcubature_rounds(lambda x: math.exp(-x * x), [-INF], [INF], reltol=1e-9, abstol=0.0)
+    Ih, Eh, neh, sth = O.solve_hcubature(lambda x: math.exp(-x * x), [-INF], [INF], reltol=1e-9, abstol=0.0)
+    assert st["status"] == 0 and sth == 0 and abs(I - math.sqrt(math.pi)) <= 1e-9 * I and abs(I - Ih) <= 1e-9 * I and E <= 1e-9 * I
+    assert 15 * st["rule_applications"] <= 2 * neh
