@@ -481,15 +481,61 @@ def main():
                                     rounds=last["rounds"], boxes_stored=last["boxes"], status=last["status"], box_budget=budget))
         return step, e2e_step, finish
 
+    def make_c4_vec(ncomp=4, dim=3):
+        """vector-valued HCubature -- 16,384 problems of 4 Genz Gaussian components each in 3-D (the components
+        share points and subdivision, error = 2-norm over them), reduced difficulty (h/4)"""
+        n = args.nprob or 16384
+        par = np.asfortranarray(WL.genz_params("genz_gaussian", dim, n * ncomp, scale=0.25).reshape(2 * dim, ncomp, n, order="F"))
+        lb, ub = np.zeros(dim), np.ones(dim)
+        last = {}
+
+        def step(record=False):
+            I, E, ne, st = eng.hcubature_vec_batch(F["genz_gaussian"], dim, lb, ub, par, reltol=1e-6, abstol=1e-8, maxevals=400000)
+            last.update(ev=int(ne.sum()), capped=float((st != 0).mean()))
+
+        def finish(kernel_ms_total):
+            per_point = ncomp * (WL.FAMILY_FLOPS["genz_gaussian"](dim) + 1) + WL.TRANSFORM_FLOPS_FINITE * dim + 2 * dim
+            return dict(units=n * ncomp, launches=1, flops=last["ev"] * per_point, evals=last["ev"] * ncomp, h2d=par.nbytes, d2h=n * (ncomp * 8 + 20),
+                        kernel="hv::hcub_vec_kernel<genz_gaussian,3> (host buffers: the vector entry point takes host arrays)",
+                        extra=dict(problems=n, components=ncomp, points=last["ev"], frac_maxevals=last["capped"]))
+        return step, step, finish
+
+    def make_bridge(dim=4):
+        """one 4-D Genz Gaussian through the BatchIntegralFunction bridge -- the engine hands out each round's
+        points on the device, the integrand is a torch expression evaluated by the caller on the same buffers"""
+        par = WL.genz_params("genz_gaussian", dim, 1)[:, 0]
+        a = torch.tensor(par[:dim], dtype=torch.float64, device="cuda"); u = torch.tensor(par[dim:], dtype=torch.float64, device="cuda")
+        lb, ub = np.zeros(dim), np.ones(dim)
+        budget = 1 << (args.nprob or 18)
+        last = {}
+
+        def f(x):
+            t = a * (x - u)
+            return torch.exp(-(t * t).sum(dim=1))
+
+        def step(record=False):
+            I, E, st = eng.integrate_batch(f, dim, lb, ub, reltol=1e-9, abstol=0.0, max_boxes=budget, device=True)
+            last.update(I=I, E=E, **st)
+
+        def finish(kernel_ms_total):
+            ev = last["nevals"]
+            return dict(units=ev, global_units=True, launches=9 * last["batches"] + 3, flops=0.0, evals=ev, h2d=0, d2h=0,
+                        bytes=ev * (8 * (dim + 1) + 16),     # points_kernel writes D + 1 doubles per point, combine_kernel reads 2
+                        kernel="bb::points_kernel<4> / bb::combine_kernel<4> + 7 bookkeeping kernels per round; integrand: torch on the same stream",
+                        extra=dict(I=last["I"], rel_E=last["E"] / abs(last["I"]), rounds=last["rounds"], batches=last["batches"],
+                                   boxes=last["boxes"], status=last["status"], box_budget=budget))
+        return step, step, finish
+
     makers = {"c4": make_c4, "c1": make_c1, "c2": make_c2, "c3": make_c3, "c5": make_c5,
               # side measurements SURVEY 8(d) asks for next to the configs (reported under "secondary" only)
               "c1_abstol_1e-12": lambda: make_c1(abstol=1e-12), "c2_nonuniform_grid": lambda: make_c2(nonuniform=True),
               "c2_contiguous_axis": lambda: make_c2(contiguous=True), "c4_reduced_difficulty_h/4": lambda: make_c4(scale=0.25),
               # "next" rows of SURVEY 8(f), same measurement as their parent config
-              "c1_order_15": lambda: make_c1(order=15), "c1_vector_valued_4": make_c1_vec, "c2_float32": make_c2_f32}
+              "c1_order_15": lambda: make_c1(order=15), "c1_vector_valued_4": make_c1_vec, "c2_float32": make_c2_f32,
+              "hcubature_vector_valued_3d_4": make_c4_vec, "batch_bridge_device_integrand_4d": make_bridge}
     EXTRA_UNITS = {"c1_abstol_1e-12": "integrals/s", "c2_nonuniform_grid": "GB/s", "c2_contiguous_axis": "GB/s",
                    "c4_reduced_difficulty_h/4": "integrals/s", "c1_order_15": "integrals/s", "c1_vector_valued_4": "integrals/s",
-                   "c2_float32": "GB/s"}
+                   "c2_float32": "GB/s", "hcubature_vector_valued_3d_4": "integrals/s", "batch_bridge_device_integrand_4d": "points/s"}
 
     def run(workload, steps, warmup, with_e2e=True, sample_clocks=False):
         step, e2e_step, finish = makers[workload]()
@@ -585,8 +631,12 @@ def main():
                     e["result"] = s["info"]["result"]
                 if "per_family" in s["info"]:
                     e["frac_maxevals"] = {k: v["frac_maxevals"] for k, v in s["info"]["per_family"].items()}
+                if "extra" in s["info"]:
+                    e.update(s["info"]["extra"])
                 if sw.startswith("c2"):
                     e["frac_of_measured_hbm"] = s["value"] / 6535.7
+                elif "bytes" in s["info"]:                   # the bridge: HBM bytes of its own two kernels per point
+                    e["algorithmic_GBps"] = s["info"]["bytes"] / (s["ms_per_step"] * 1e-3) / 1e9
                 else:
                     e["fp64_tflops_nominal"] = s["info"]["flops"] / (s["ms_per_step"] * 1e-3) / 1e12
                     e["nominal_frac_of_fp64_peak"] = e["fp64_tflops_nominal"] / fp64_peak
