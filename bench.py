@@ -145,6 +145,9 @@ def cpu_c2_sample(O, WL, n, threads):
 
 # DRAM traffic per launch (bytes) of the dominant kernels at the default workload sizes, from `ncu --set full` (profiles/README.md)
 NCU_TRAFFIC = {"hp::hcub_pair_kernel<genz_product_peak,4,true>": 4.663001e12 + 1.771830e12}
+# executed FP64-pipe utilisation of the same kernels (sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active of the committed
+# captures): the figure that cannot exceed 1 -- `roofline.frac` counts the NOMINAL operations of SURVEY 8(d), which the kernels undercut
+NCU_FP64_PIPE = {"hp::hcub_pair_kernel<genz_product_peak,4,true>": (0.176, "profiles/r01_hcub_pair_prod_c4_full_summary.txt (before the Terms7 change; steady state after it: 0.202, profiles/r01b_pair_genz_product_peak_steady_full_summary.txt)")}
 
 FAM_ORC = {"sinxp": "sinxp", "genz_oscillatory": "osc", "genz_product_peak": "prodpeak", "genz_corner_peak": "corner",
            "genz_gaussian": "gauss", "genz_c0": "c0", "genz_discontinuous": "discont"}
@@ -602,6 +605,7 @@ def main():
                 "peak_source": "DFMA-chain microbenchmark run live on this GPU (ib200_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
                 "flops_model": "SURVEY 8(d) nominal FP64 operations per integrand evaluation x evaluations (DESIGN.md); the kernels execute fewer "
                                "(separable-term tables), so the executed-instruction FP64 pipe utilisation is the ncu figure in profiles/",
+                "executed_fp64_pipe_frac": NCU_FP64_PIPE.get(kname, (None, None))[0], "executed_fp64_pipe_source": NCU_FP64_PIPE.get(kname, (None, None))[1],
                 "kernel": kname, "kernel_ms": kms_, "evals_per_launch": kev, "gevals_per_s": kev / (kms_ * 1e-3) / 1e9,
                 "share_of_step": dom["share_of_step"] if dom else 1.0,
                 "whole_step": {"achieved": ach_step, "frac": ach_step / fp64_peak, "evals": info["evals"],
