@@ -422,3 +422,18 @@ def test_round_synchronous_restatement_in_one_dimension():
     Ih, Eh, neh, sth = O.solve_hcubature(lambda x: math.exp(-x * x), [-INF], [INF], reltol=1e-9, abstol=0.0)
     assert st["status"] == 0 and sth == 0 and abs(I - math.sqrt(math.pi)) <= 1e-9 * I and abs(I - Ih) <= 1e-9 * I and E <= 1e-9 * I
     assert 15 * st["rule_applications"] <= 2 * neh
+
+
+def test_quadgk_published_example_of_the_dependency():
+    """QuadGK.jl is not vendored in the reference (compat "2.11", Project.toml:65), so its own published example is the one
+    reference-EXECUTED vector available for the adaptive path: the package README's quick start
+        julia> integral, err = quadgk(x -> exp(-x^2), 0, 1, rtol=1e-8)
+        (0.746824132812427, 7.887024366937112e-13)
+    (quoted from the README; there is no network here to re-fetch it -- the agreement of all 16 digits of the error estimate,
+    a difference of two 15-point sums, is what identifies the quotation).  orc_quadgk returns exactly these doubles: the rule's
+    node / weight tables, the order of the Kronrod and Gauss sums and E = |K - G| are QuadGK's."""
+    I, E, ne, st = O.solve_quadgk(lambda x: math.exp(-x * x), 0.0, 1.0, reltol=1e-8, abstol=0.0)
+    assert (I, E, ne, st) == (0.746824132812427, 7.887024366937112e-13, 15, 0)
+    # the same integral through the registered family (c x^k exp(-a^2 (x-u)^2), a = 1) and the batch driver
+    Ib, Eb, neb, stb = O.quadgk_batch("gausspoly", 0.0, 1.0, np.array([[1.0], [0.0], [0.0], [1.0]]), reltol=1e-8, abstol=0.0)
+    assert Ib[0] == pytest.approx(0.746824132812427, rel=1e-15) and Eb[0] == pytest.approx(7.887024366937112e-13, rel=1e-3) and neb[0] == 15
