@@ -12,6 +12,12 @@
  * (src/Integrals.jl:327-335, 380-393) and on the closed-form answers the reference's
  * own tests use (tests/test_oracle_pins.py).  See DESIGN.md "Oracle".
  *
+ * PARITY PINNING: the reference is Julia and cannot run here (no Julia, no C sources to build
+ * into oracle/_ref), and its tests hold closed-form answers at loose tolerances only -- so at the
+ * <= 1e-12 level this oracle is "parity unpinned by reference execution", with one exception: the
+ * QuadGK.jl README's published output quadgk(x -> exp(-x^2), 0, 1, rtol=1e-8) =
+ * (0.746824132812427, 7.887024366937112e-13), which orc_quadgk reproduces bit for bit.
+ *
  * Build: make -C oracle   (gcc -O2 -ffp-contract=off -fopenmp; no -ffast-math:
  * the reference does separate multiplies and adds, src/sampled.jl:84).
  */
