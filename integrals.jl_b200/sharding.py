@@ -76,3 +76,57 @@ def solve_sharded(prob, alg, group=None, local_solve=None, interleave=False, **k
     resid = None if sol.resid is None else full[1]
     stats = None if sol.stats is None else dict(nevals=full[2].astype(np.int64), status=full[3].astype(np.int32))
     return interface.IntegralSolution(full[0], resid, prob, sol.alg, sol.retcode, None, stats)
+
+
+def sampled_shard_axis(shape, dim):
+    """the axis a sampled problem is split along: the longest axis other than the integration axis `dim` (ties -> the last,
+    i.e. the slowest-varying one in the column-major layout, so every rank's slab is one contiguous block)"""
+    axes = [k for k in range(len(shape)) if k != dim]
+    if not axes:
+        raise ValueError("a 1-D sampled problem has nothing to shard")
+    return max(axes, key=lambda k: (shape[k], k))
+
+
+def solve_sampled_sharded(prob, alg, group=None, local_solve=None):
+    """solve(SampledIntegralProblem(y, x; dim), alg) with the independent rows of `y` split across the ranks of `group`
+    (BASELINE config 2; SURVEY 8(e): the outputs are independent, so there is NO data-path collective -- every rank streams its
+    slab of `y` once; the per-rank result vectors are concatenated by one all_gather, control plane).  `prob.y` is the whole
+    host array on every rank (each rank uploads only its slab) -- or use shard_range directly when the data is generated on
+    the devices.  Every rank returns the full solution."""
+    import torch
+    import torch.distributed as dist
+    from . import interface
+    if local_solve is None:
+        local_solve = interface.solve
+    if not dist.is_initialized():
+        return local_solve(prob, alg)
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    y = np.asarray(prob.y)
+    ax = sampled_shard_axis(y.shape, prob.dim)
+    n = y.shape[ax]
+    lo, hi = shard_range(n, rank, world)
+    sl = [slice(None)] * y.ndim
+    sl[ax] = slice(lo, hi)
+    sol = local_solve(interface.SampledIntegralProblem(y[tuple(sl)], prob.x, prob.dim), alg)
+    out_ax = ax - (1 if ax > prob.dim else 0)                       # the integration axis is gone from the result
+    out_shape = tuple(v for k, v in enumerate(y.shape) if k != prob.dim)
+    mine = np.moveaxis(np.asarray(sol.u, dtype=np.result_type(sol.u, np.float32)).reshape(
+        tuple(hi - lo if k == out_ax else v for k, v in enumerate(out_shape))), out_ax, 0)
+    maxn = max(b - a for a, b in (shard_range(n, r, world) for r in range(world)))
+    pad = np.zeros((maxn,) + mine.shape[1:], dtype=mine.dtype)
+    pad[:hi - lo] = mine
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    cplx = np.iscomplexobj(pad)
+    t = torch.from_numpy(np.ascontiguousarray(pad.view(np.float64) if cplx else pad)).to(dev)
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t, group=group)
+    blocks = []
+    for r, part in enumerate(parts):
+        a, b = shard_range(n, r, world)
+        arr = part.cpu().numpy()
+        if cplx:
+            arr = arr.view(np.complex128)
+        blocks.append(arr[:b - a])
+    full = np.moveaxis(np.concatenate(blocks, axis=0), 0, out_ax)
+    return interface.IntegralSolution(np.asfortranarray(full), None, prob, sol.alg, sol.retcode)

@@ -89,6 +89,60 @@ def test_solve_sharded_world2_gloo():
         assert np.array_equal(u2, I2) and np.all(st2 == 0)
 
 
+def _oracle_sampled_solve(prob, alg):
+    import oracle as O
+    from integrals_b200 import interface
+    x = prob.x
+    kw = dict(h=x.step) if isinstance(x, ib.Range) else dict(x=np.asarray(x))
+    u = O.sampled_evalrule(alg.rule, np.asfortranarray(prob.y), dim=prob.dim, **kw)
+    return interface.IntegralSolution(u, None, prob, alg, interface.ReturnCode.Success)
+
+
+def _sampled_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(3)
+        out = []
+        for shape, dim in (((7, 101), 1), ((101, 7), 0), ((5, 64, 3), 1), ((4, 6, 33), 2)):
+            y = rng.standard_normal(shape) + 1.5
+            for alg, x in ((ib.TrapezoidalB200(), ib.Range(0.0, 1.0, shape[dim])), (ib.SimpsonsB200(), np.sort(rng.random(shape[dim])))):
+                sol = sharding.solve_sampled_sharded(ib.SampledIntegralProblem(y, x, dim=dim), alg, local_solve=_oracle_sampled_solve)
+                out.append(np.asarray(sol.u))
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_solve_sampled_sharded_world2_gloo():
+    """BASELINE config 2 across ranks: the rows of y are independent -> each rank integrates its slab, no data-path
+    collective; every rank ends with the full result, equal to the unsharded solve bit for bit"""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sampled_worker, args=(r, 2, port, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for pr in procs:
+        pr.join(60)
+        assert pr.exitcode == 0
+    rng = np.random.default_rng(3)
+    ref = []
+    for shape, dim in (((7, 101), 1), ((101, 7), 0), ((5, 64, 3), 1), ((4, 6, 33), 2)):
+        y = rng.standard_normal(shape) + 1.5
+        for alg, x in ((ib.TrapezoidalB200(), ib.Range(0.0, 1.0, shape[dim])), (ib.SimpsonsB200(), np.sort(rng.random(shape[dim])))):
+            ref.append(np.asarray(_oracle_sampled_solve(ib.SampledIntegralProblem(y, x, dim=dim), alg).u))
+    for rank, out in res:
+        assert len(out) == len(ref)
+        for a, b in zip(out, ref):
+            assert a.shape == b.shape and np.array_equal(a, b)
+    assert sharding.sampled_shard_axis((4096, 1 << 20), 1) == 0 and sharding.sampled_shard_axis((5, 64, 3), 1) == 0
+    assert sharding.sampled_shard_axis((4, 6, 33), 0) == 2
+
+
 def test_round_oracle_presplit_variants_agree():
     """orc_hcubature_rounds with a pre-bisected domain (m0 > 0) reaches the same integral within the tolerance as the
     single-box start the driver uses on any number of ranks (replicated store: the refinement is rank-count independent)."""
