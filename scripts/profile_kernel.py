@@ -1,5 +1,6 @@
 """One short invocation of a hot-path kernel for ncu (run it plain first, then under ncu).
-usage: profile_kernel.py hcub <family> <nprob> [dim] | quadgk <nprob> | fixed <family> <nprob> | sampled <n>"""
+usage: profile_kernel.py hcub <family> <nprob> [dim] | quadgk <nprob> | fixed <family> <nprob> | sampled <n> |
+       hcubvec <family> <nprob> [dim] [ncomp] | bridge [dim] [log2 box budget]"""
 import os, sys
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, R)
@@ -32,5 +33,17 @@ for rep in range(reps):
         n = int(sys.argv[2]); m = 4096
         y = torch.rand((n, m), dtype=torch.float64, device="cuda"); out = torch.empty(m, dtype=torch.float64, device="cuda")
         eng.sampled("trapezoid", y, m, n, 1, h=1.0 / (n - 1), out=out); eng.sampled("simpson", y, m, n, 1, h=1.0 / (n - 1), out=out)
+    elif kind == "hcubvec":      # vector-valued HCubature: hv::hcub_vec_kernel
+        fam, nprob = sys.argv[2], int(sys.argv[3]); d = int(sys.argv[4]) if len(sys.argv) > 4 else 3; nc = int(sys.argv[5]) if len(sys.argv) > 5 else 4
+        par = np.asfortranarray(WL.genz_params(fam, d, nprob * nc, scale=0.25).reshape(2 * d, nc, nprob, order="F"))
+        I, E, ne, st = eng.hcubature_vec_batch(F[fam], d, np.zeros(d), np.ones(d), par, reltol=1e-6, abstol=1e-8, maxevals=min(MAXEV, 400000))
+        print("points", int(ne.sum()), "capped", float((st != 0).mean()))
+    elif kind == "bridge":       # BatchIntegralFunction bridge (rank 3): bb::points_kernel / bb::combine_kernel, torch integrand on the device
+        d = int(sys.argv[2]) if len(sys.argv) > 2 else 4; budget = 1 << (int(sys.argv[3]) if len(sys.argv) > 3 else 18)
+        pr = WL.genz_params("genz_gaussian", d, 1)[:, 0]
+        a = torch.tensor(pr[:d], device="cuda"); u = torch.tensor(pr[d:], device="cuda")
+        I, E, st = eng.integrate_batch(lambda x: torch.exp(-((a * (x - u)) ** 2).sum(dim=1)), d, np.zeros(d), np.ones(d), reltol=1e-9, abstol=0.0,
+                                       max_boxes=budget, device=True)
+        print("I", I, "E", E, st)
     eng.synchronize()
     print(kind, "rep", rep, "kernel ms", eng.last_kernel_ms, flush=True)
