@@ -370,11 +370,15 @@ class Engine:
         self._check(self.L.ib200_batch_result(self.h, C.byref(I), C.byref(E), st.ctypes.data))
         return I.value, E.value, dict(nevals=int(st[0]), rule_applications=int(st[1]), boxes=int(st[2]), rounds=int(st[3]), status=int(st[4]))
 
-    def integrate_batch(self, f, dim, lb, ub, reltol=1e-8, abstol=1e-8, max_boxes=1 << 20, store_boxes=0, transform=0, device=False):
+    def integrate_batch(self, f, dim, lb, ub, reltol=1e-8, abstol=1e-8, max_boxes=1 << 20, store_boxes=0, transform=0, device=False,
+                        max_batch=None):
         """Adaptive integral of a caller-evaluated batch integrand.  f(pts) -> values: pts is a float64 array of shape (dim, n)
         ((n,) in 1-D), one point per column like the reference's BatchIntegralFunction; with device=True pts is a torch CUDA
         tensor of shape (n, dim) ((n,) in 1-D; the same memory) and f returns a CUDA tensor of n values, no host copies.
-        -> I, E, stats."""
+        max_batch (BatchIntegralFunction's max_batch): f is called on at most that many points at a time (a round is split on the
+        host side).  -> I, E, stats."""
+        if max_batch is not None and int(max_batch) < 1:
+            raise ValueError("max_batch must be positive")
         self.batch_open(dim, lb, ub, reltol=reltol, abstol=abstol, max_boxes=max_boxes, store_boxes=store_boxes, transform=transform)
         batches = 0
         while True:
@@ -386,7 +390,7 @@ class Engine:
                 x = torch.empty((n, dim) if dim > 1 else (n,), dtype=torch.float64, device=torch.device("cuda", self.device))
                 self.batch_points(x, n)
                 self.synchronize()                          # the points are written on the engine's stream
-                y = f(x)
+                y = f(x) if max_batch is None or n <= max_batch else torch.cat([f(x[i:i + max_batch]) for i in range(0, n, int(max_batch))])
                 if not (hasattr(y, "is_cuda") and y.is_cuda and y.dtype == torch.float64 and y.numel() == n):
                     raise ValueError(f"the batch integrand must return {n} float64 values on the device")
                 y = y.contiguous()
@@ -394,7 +398,10 @@ class Engine:
             else:
                 x = np.empty((dim, n) if dim > 1 else (n,), dtype=np.float64, order="F")
                 self.batch_points(x, n)
-                y = np.ascontiguousarray(f(x), dtype=np.float64)
+                if max_batch is None or n <= max_batch:
+                    y = np.ascontiguousarray(f(x), dtype=np.float64)
+                else:
+                    y = np.concatenate([np.ravel(np.asarray(f(x[..., i:i + max_batch]), dtype=np.float64)) for i in range(0, n, int(max_batch))])
                 if y.shape != (n,):
                     raise ValueError(f"the batch integrand must return {n} values, got shape {y.shape}")
             self.batch_values(y, n)

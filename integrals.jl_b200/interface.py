@@ -75,12 +75,16 @@ class BatchIntegralFunction:
     points -- pts has shape (dim, n), one point per column ((n,) in 1-D) -- and returns n values.  This is the one way to
     integrate an arbitrary (host or device) closure with the B200 engine: the engine owns the points and the adaptive
     refinement on the device (ib200_batch_*), the caller evaluates.  device=True: pts is a torch CUDA tensor of shape (n, dim)
-    ((n,) in 1-D; the same memory as the column-major dim x n matrix) and f returns a CUDA tensor -- no host copies."""
+    ((n,) in 1-D; the same memory as the column-major dim x n matrix) and f returns a CUDA tensor -- no host copies.
+    max_batch bounds the points per call of f (a round's batch is split on the host side)."""
 
-    def __init__(self, f, device=False):
+    def __init__(self, f, device=False, max_batch=None):
+        """max_batch: largest number of points per call of f (the reference's `max_batch`, default unbounded)"""
         if not callable(f):
             raise TypeError("BatchIntegralFunction wraps a callable f(pts, p)")
-        self.f, self.device = f, bool(device)
+        if max_batch is not None and int(max_batch) < 1:
+            raise ValueError("max_batch must be positive")
+        self.f, self.device, self.max_batch = f, bool(device), None if max_batch is None else int(max_batch)
 
     def __call__(self, pts, p):
         return self.f(pts, p)
@@ -392,7 +396,8 @@ def _solve_batch_function(cache, prob, inner, tr):
     p = prob.p
     I, E, stats = cache.cacheval.integrate_batch(lambda pts: cache.f(pts, p), dim, lb, ub, reltol=kw.get("reltol", 1e-8),
                                                  abstol=kw.get("abstol", 1e-8), max_boxes=max_boxes,
-                                                 store_boxes=getattr(inner, "store_boxes", 0), transform=tr, device=cache.f.device)
+                                                 store_boxes=getattr(inner, "store_boxes", 0), transform=tr, device=cache.f.device,
+                                                 **({} if cache.f.max_batch is None else {"max_batch": cache.f.max_batch}))
     return IntegralSolution(I, E, prob, inner, ReturnCode.Success, None, stats)
 
 

@@ -84,3 +84,20 @@ def test_host_loop_and_solve_routing_on_the_model():
     assert abs(sol.u - (math.cos(-3.4) - math.cos(8.5)) / 1.7) < 1e-14 and sol.stats["nevals"] == 75         # README.md:30-40
     with pytest.raises(ValueError, match="must return"):
         e.integrate_batch(lambda x: np.ones(3), 1, [0.0], [1.0])
+    # max_batch (BatchIntegralFunction's max_batch): same points, same result, f sees at most max_batch of them per call
+    sizes = []
+
+    def g(pts, p):
+        sizes.append(pts.shape[-1])
+        return np.cos(pts[0]) * np.cos(pts[1]) * np.cos(pts[2])
+    dom = (np.ones(3), 3 * np.ones(3))
+    whole = ib.solve(ib.IntegralProblem(ib.BatchIntegralFunction(g), dom), ib.HCubatureB200(), engine=e, reltol=1e-7, abstol=0.0)
+    n_whole = list(sizes); sizes.clear()
+    part = ib.solve(ib.IntegralProblem(ib.BatchIntegralFunction(g, max_batch=100), dom), ib.HCubatureB200(), engine=e, reltol=1e-7, abstol=0.0)
+    assert part.u == whole.u and part.resid == whole.resid and max(sizes) <= 100 and sum(sizes) == sum(n_whole) == whole.stats["nevals"]
+    assert max(n_whole) > 100
+    h = lambda x, p: np.sin(1.7 * x)
+    s1 = ib.solve(ib.IntegralProblem(ib.BatchIntegralFunction(h, max_batch=7), (-2.0, 5.0)), ib.QuadGKB200(), engine=e, reltol=1e-10)
+    assert abs(s1.u - (math.cos(-3.4) - math.cos(8.5)) / 1.7) < 1e-14
+    with pytest.raises(ValueError):
+        ib.BatchIntegralFunction(h, max_batch=0)
