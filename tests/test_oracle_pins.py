@@ -437,3 +437,28 @@ def test_quadgk_published_example_of_the_dependency():
     # the same integral through the registered family (c x^k exp(-a^2 (x-u)^2), a = 1) and the batch driver
     Ib, Eb, neb, stb = O.quadgk_batch("gausspoly", 0.0, 1.0, np.array([[1.0], [0.0], [0.0], [1.0]]), reltol=1e-8, abstol=0.0)
     assert Ib[0] == pytest.approx(0.746824132812427, rel=1e-15) and Eb[0] == pytest.approx(7.887024366937112e-13, rel=1e-3) and neb[0] == 15
+
+
+def test_genz_malik_rule_against_an_independent_implementation():
+    """HCubature.jl is not vendored and publishes no output vector, so the Genz-Malik rule of the oracle (gm_rule: degree-7 value and
+    the embedded degree-5 difference E = |I7 - I5|, Genz & Malik 1980 as HCubature.jl implements it) is pinned against an
+    INDEPENDENT implementation of the same published rule: SciPy's scipy.integrate._rules.GenzMalikCubature (nodes and weights built
+    from the paper by other authors).  Random boxes and Gaussians, d = 2..6: value and error estimate agree to rounding
+    (1e-15 x volume; E itself is a difference of two sums of that size)."""
+    rules = pytest.importorskip("scipy.integrate._rules")
+    rng = np.random.default_rng(0)
+    for d in (2, 3, 4, 5, 6):
+        rule = rules.GenzMalikCubature(d)
+        for _ in range(5):
+            a = rng.uniform(-1, 0.5, d); b = a + rng.uniform(0.1, 1.5, d)
+            al = rng.uniform(0.5, 3, d); u = rng.uniform(0, 1, d)
+            Is = float(rule.estimate(lambda x: np.exp(-np.sum((al * (x - u)) ** 2, axis=-1)), a, b))
+            Es = float(rule.estimate_error(lambda x: np.exp(-np.sum((al * (x - u)) ** 2, axis=-1)), a, b))
+            I, E, kd = O.cubrule(lambda x: math.exp(-sum((al[k] * (x[k] - u[k])) ** 2 for k in range(d))), a, b)
+            vol = float(np.prod(b - a))
+            assert abs(I - Is) <= 1e-15 * vol and abs(E - Es) <= 1e-15 * vol and 0 <= kd < d
+    # the (7,15) Kronrod value against SciPy's table (its error heuristic differs from QuadGK's |K - G| only in rounding here)
+    gk = rules.GaussKronrodQuadrature(15)
+    Ik, Ek = O.gk15(lambda x: math.exp(-x * x), 0.0, 1.0)
+    Isk = float(gk.estimate(lambda x: np.exp(-x[..., 0] ** 2), np.array([0.0]), np.array([1.0])))
+    assert abs(Ik - Isk) <= 4e-16
