@@ -462,3 +462,23 @@ def test_genz_malik_rule_against_an_independent_implementation():
     Ik, Ek = O.gk15(lambda x: math.exp(-x * x), 0.0, 1.0)
     Isk = float(gk.estimate(lambda x: np.exp(-x[..., 0] ** 2), np.array([0.0]), np.array([1.0])))
     assert abs(Ik - Isk) <= 4e-16
+
+
+def test_sampled_rules_against_numpy_and_scipy():
+    """independent cross-check of the sampled restatement (src/trapezoidal.jl:16-40, src/simpsons.jl:16-25): numpy's trapezoid on uniform
+    and non-uniform grids; SciPy's composite Simpson 1/3 rule on NON-uniform grids with an odd number of points (src/simpsons.jl:40-82;
+    the reference's uniform "Simpson" is the end-corrected 17-59-43-49 / 48 rule, which SciPy does not have); agreement to rounding
+    relative to sum |w y|"""
+    integrate = pytest.importorskip("scipy.integrate")
+    trapz = getattr(np, "trapezoid", None) or np.trapz
+    rng = np.random.default_rng(4)
+    for n in (2, 3, 10, 101, 1000):
+        y = np.asfortranarray(rng.standard_normal((5, n)) + 1.5)
+        x = np.sort(rng.random(n)) * 3.0 - 1.0
+        h = 0.37
+        scale = np.abs(y).sum(axis=1) * h
+        assert np.all(np.abs(O.sampled_evalrule("trapezoid", y, h=h, dim=1) - trapz(y, dx=h, axis=1)) <= 1e-14 * scale)
+        assert np.all(np.abs(O.sampled_evalrule("trapezoid", y, x=x, dim=1) - trapz(y, x=x, axis=1)) <= 1e-14 * np.abs(y).sum(axis=1) * 3.0)
+        if n % 2 == 1 and n >= 3:
+            ws = np.abs(O.sampled_weights("simpson", n, x=x))
+            assert np.all(np.abs(O.sampled_evalrule("simpson", y, x=x, dim=1) - integrate.simpson(y, x=x, axis=1)) <= 1e-13 * (np.abs(y) * ws).sum(axis=1))
