@@ -482,3 +482,18 @@ def test_sampled_rules_against_numpy_and_scipy():
         if n % 2 == 1 and n >= 3:
             ws = np.abs(O.sampled_weights("simpson", n, x=x))
             assert np.all(np.abs(O.sampled_evalrule("simpson", y, x=x, dim=1) - integrate.simpson(y, x=x, axis=1)) <= 1e-13 * (np.abs(y) * ws).sum(axis=1))
+
+
+def test_kronrod_tables_against_scipy():
+    """the generated Gauss-Kronrod tables (kronrod.kronrod(n), QuadGK.kronrod's layout) against SciPy's published 15- and 21-point
+    tables: identical Kronrod nodes and weights, Gauss weights to 1e-15"""
+    rules = pytest.importorskip("scipy.integrate._rules")
+    from integrals_b200.kronrod import kronrod
+    for npts, order in ((15, 7), (21, 10)):
+        r = rules.GaussKronrodQuadrature(npts)
+        nodes, weights = (np.asarray(v).ravel() for v in r.nodes_and_weights)
+        idx = np.argsort(nodes)
+        x, w, wg = kronrod(order)
+        assert np.array_equal(nodes[idx][:order + 1], x) and np.array_equal(weights[idx][:order + 1], w)
+        ln, lw = (np.asarray(v).ravel() for v in r.lower_nodes_and_weights)
+        assert np.allclose(lw[np.argsort(ln)][:len(wg)], wg, rtol=0, atol=2e-15)
