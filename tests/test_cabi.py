@@ -3,6 +3,7 @@ include/integrals_b200.h declares, and fails loudly (no fallback) when there is 
 import os
 import re
 
+import numpy as np
 import pytest
 
 import integrals_b200 as ib
@@ -82,3 +83,36 @@ def test_ctypes_signatures_match_header():
                 assert ct in (C.c_int32, C.c_int64, C.c_int), (name, par, ct)
         checked += 1
     assert checked >= 15
+
+
+def test_device_rule_tables_equal_the_pinned_tables():
+    """the Gauss-Kronrod (7,15) tables compiled into the CUDA kernels (csrc/quadgk.cu, quadgk_vec.cu, hcubature_impl.cuh) and into the
+    oracle are the same doubles as kronrod.kronrod(7) -- the tables pinned against QuadGK's published example and SciPy's table
+    (tests/test_oracle_pins.py); and every kernel file spells the Genz-Malik weights with the same integers (Genz & Malik 1980)"""
+    import re
+    from integrals_b200.kronrod import kronrod
+    x, w, wg = kronrod(7)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    num = r"[-+]?[0-9]*\.?[0-9]+(?:[eE][-+]?[0-9]+)?"
+
+    def tables(path, prefix, qual=r"(?:__constant__|static const) double"):
+        src = open(os.path.join(root, path)).read()
+        out = []
+        for name in ("x", "w", "wg"):
+            m = re.search(qual + r"\s+" + prefix + name + r"\[\d+\]\s*=\s*\{([^}]*)\}", src, re.I)
+            assert m, (path, prefix + name)
+            out.append(np.array([float(v) for v in re.findall(num, m.group(1))]))
+        return out
+    for path, prefix in (("integrals.jl_b200/csrc/quadgk.cu", "c_gk_"), ("integrals.jl_b200/csrc/quadgk_vec.cu", "v_gk_"),
+                         ("integrals.jl_b200/csrc/hcubature_impl.cuh", "c_"), ("oracle/oracle.c", "GK_")):
+        tx, tw, twg = tables(path, prefix)
+        assert np.array_equal(tx, x) and np.array_equal(tw, w) and np.array_equal(twg, wg), path
+    gm = ["12824 - 9120 * D + 400 * D * D", "980 / 6561.0", "1820 - 400 * D", "200 / 19683.0", "6859 / 19683.0",
+          "729 - 950 * D + 50 * D * D", "245 / 486.0", "265 - 100 * D", "25 / 729.0"]
+    for path in ("hcubature_impl.cuh", "hcubature_pair.cuh", "hcubature_vec.cuh", "hcub_rounds.cuh", "batch_bridge.cu"):
+        src = open(os.path.join(root, "integrals.jl_b200", "csrc", path)).read()
+        for term in gm:
+            assert term in src, (path, term)
+    osrc = open(os.path.join(root, "oracle", "oracle.c")).read()
+    for term in gm:
+        assert term.replace("D", "n") in osrc, term
