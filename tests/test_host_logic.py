@@ -246,3 +246,32 @@ def test_batch_integral_function_routing():    # src/Integrals.jl:274-315 (Batch
         ib.BatchIntegralFunction(3.0)
     with pytest.raises(TypeError, match="BatchIntegralFunction"):
         ib.IntegralProblem(lambda x, p: x, (0.0, 1.0))
+
+
+def test_sampled_nd_layout_property():
+    """evalrule over an arbitrary axis of an N-D array (src/sampled.jl:99-124): the host layer hands the engine Julia's column-major
+    [inner, n, outer] view; with the engine replaced by the oracle's kernel-equivalent on that flat view, solve() must equal numpy's
+    trapezoid along the same axis for every shape / axis (hypothesis)"""
+    hyp = pytest.importorskip("hypothesis")
+    st = pytest.importorskip("hypothesis.strategies")
+    import oracle as O
+    trapz = getattr(np, "trapezoid", None) or np.trapz
+
+    class OracleSampled(StubEngine):
+        def sampled(self, rule, y, inner, n, outer, h=0.0, x=None, out=None):
+            flat = np.ravel(np.asarray(y), order="F").reshape((inner, n, outer), order="F")      # the memory the C ABI would see
+            u = O.sampled_evalrule(rule, flat, h=None if x is not None else h, x=x, dim=1)
+            return np.ravel(np.atleast_1d(u), order="F")
+
+    @hyp.settings(max_examples=60, deadline=None)
+    @hyp.given(st.lists(st.integers(1, 5), min_size=1, max_size=4), st.integers(0, 3), st.integers(2, 9), st.booleans())
+    def check(shape, dim, n, uniform):
+        dim = dim % len(shape)
+        shape = list(shape); shape[dim] = n
+        rng = np.random.default_rng(sum(shape) + dim)
+        y = rng.standard_normal(shape)
+        x = ib.Range(0.0, 2.0, n) if uniform else np.sort(rng.random(n)) + np.arange(n)
+        sol = ib.solve(ib.SampledIntegralProblem(y, x, dim=dim), ib.TrapezoidalB200(), engine=OracleSampled())
+        ref = trapz(y, x=x.toarray() if uniform else x, axis=dim)
+        assert np.shape(sol.u) == np.shape(ref) and np.allclose(sol.u, ref, rtol=1e-12, atol=1e-12)
+    check()
