@@ -78,16 +78,28 @@ class BatchIntegralFunction:
     ((n,) in 1-D; the same memory as the column-major dim x n matrix) and f returns a CUDA tensor -- no host copies.
     max_batch bounds the points per call of f (a round's batch is split on the host side)."""
 
-    def __init__(self, f, device=False, max_batch=None):
-        """max_batch: largest number of points per call of f (the reference's `max_batch`, default unbounded)"""
+    def __init__(self, f, device=False, max_batch=None, inplace=False):
+        """max_batch: largest number of points per call of f (the reference's `max_batch`, default unbounded).
+        inplace=True: the reference's in-place style f(y, pts, p) (src/Integrals.jl:277-297) -- y is a preallocated vector of n values
+        (numpy, or a CUDA tensor with device=True) that f fills."""
         if not callable(f):
             raise TypeError("BatchIntegralFunction wraps a callable f(pts, p)")
         if max_batch is not None and int(max_batch) < 1:
             raise ValueError("max_batch must be positive")
         self.f, self.device, self.max_batch = f, bool(device), None if max_batch is None else int(max_batch)
+        self.inplace = bool(inplace)
 
     def __call__(self, pts, p):
-        return self.f(pts, p)
+        if not self.inplace:
+            return self.f(pts, p)
+        n = pts.shape[0] if self.device else pts.shape[-1]
+        if self.device:
+            import torch
+            y = torch.empty(n, dtype=torch.float64, device=pts.device)
+        else:
+            y = np.empty(n)
+        self.f(y, pts, p)
+        return y
 
 
 class IntegralProblem:

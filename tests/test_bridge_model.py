@@ -101,3 +101,14 @@ def test_host_loop_and_solve_routing_on_the_model():
     assert abs(s1.u - (math.cos(-3.4) - math.cos(8.5)) / 1.7) < 1e-14
     with pytest.raises(ValueError):
         ib.BatchIntegralFunction(h, max_batch=0)
+    # the reference's in-place style f(y, pts, p) (src/Integrals.jl:277-297)
+
+    def h_iip(y, x, p):
+        y[:] = np.sin(p * x)
+    s2 = ib.solve(ib.IntegralProblem(ib.BatchIntegralFunction(h_iip, inplace=True), (-2.0, 5.0), 1.7), ib.QuadGKB200(), engine=e, reltol=1e-10)
+    assert s2.u == s1.u and s2.resid == s1.resid
+
+    def g_iip(y, pts, p):
+        y[:] = np.cos(pts[0]) * np.cos(pts[1]) * np.cos(pts[2])
+    part2 = ib.solve(ib.IntegralProblem(ib.BatchIntegralFunction(g_iip, inplace=True, max_batch=64), dom), ib.HCubatureB200(), engine=e, reltol=1e-7, abstol=0.0)
+    assert part2.u == whole.u
