@@ -102,6 +102,27 @@ class BatchIntegralFunction:
         return y
 
 
+class IntegralFunction(BatchIntegralFunction):
+    """IntegralFunction(f) (SciMLBase; the reference's default wrapper of a closure f(x, p), src/Integrals.jl:327-335, 366-378): a
+    POINTWISE closure.  It cannot run on the device, so it is evaluated where the reference evaluates it -- in the caller's process --
+    one point at a time over the batches of points the engine hands out (the BatchIntegralFunction bridge); points, weighted sums,
+    error estimates and the refinement stay on the GPU.  x is a float in 1-D, else a vector of length dim.  An explicit opt-in: plain
+    callables are still rejected by IntegralProblem, because a per-point host loop is orders of magnitude slower than a registered
+    integrand or a vectorised BatchIntegralFunction."""
+
+    def __init__(self, f, max_batch=None):
+        if not callable(f):
+            raise TypeError("IntegralFunction wraps a callable f(x, p)")
+        self.point_f = f
+        BatchIntegralFunction.__init__(self, self._batch, device=False, max_batch=max_batch)
+
+    def _batch(self, pts, p):
+        f = self.point_f
+        if pts.ndim == 1:
+            return np.array([f(float(x), p) for x in pts], dtype=np.float64)
+        return np.array([f(pts[:, j], p) for j in range(pts.shape[1])], dtype=np.float64)
+
+
 class IntegralProblem:
     """IntegralProblem(f, domain, p=None, **kwargs).  domain = (lb, ub): scalars (1-D), vectors of
     length dim, or dim x nprob arrays (per-problem bounds).  p: nparam numbers or nparam x nprob."""

@@ -112,3 +112,24 @@ def test_host_loop_and_solve_routing_on_the_model():
         y[:] = np.cos(pts[0]) * np.cos(pts[1]) * np.cos(pts[2])
     part2 = ib.solve(ib.IntegralProblem(ib.BatchIntegralFunction(g_iip, inplace=True, max_batch=64), dom), ib.HCubatureB200(), engine=e, reltol=1e-7, abstol=0.0)
     assert part2.u == whole.u
+
+
+def test_pointwise_integral_function_on_the_model():
+    """IntegralFunction(f): the reference's pointwise closure f(x, p), evaluated by the caller at the engine's points; the reference's
+    scalar known answers (test/interface_tests.jl:129-187: f = 1 and prod(cos.(x)) on [1,3]^dim, reltol = abstol = 1e-5; README.md:30-40)"""
+    e = ModelEngine()
+    for dim in (1, 2, 3):
+        alg = ib.QuadGKB200() if dim == 1 else ib.HCubatureB200()
+        dom = (1.0, 3.0) if dim == 1 else (np.ones(dim), 3 * np.ones(dim))
+        sol = ib.solve(ib.IntegralProblem(ib.IntegralFunction(lambda x, p: 1.0), dom), alg, engine=e, reltol=1e-5, abstol=1e-5)
+        assert abs(sol.u - 2.0 ** dim) <= 1e-12
+        f = (lambda x, p: math.cos(x)) if dim == 1 else (lambda x, p: float(np.prod(np.cos(x))))
+        sol = ib.solve(ib.IntegralProblem(ib.IntegralFunction(f), dom), alg, engine=e, reltol=1e-5, abstol=1e-5)
+        assert abs(sol.u - (math.sin(3.0) - math.sin(1.0)) ** dim) <= 1e-5
+    sol = ib.solve(ib.IntegralProblem(ib.IntegralFunction(lambda x, p: math.sin(x * p)), (-2.0, 5.0), 1.7), ib.QuadGKB200(), engine=e, reltol=1e-10)
+    assert abs(sol.u - (math.cos(-3.4) - math.cos(8.5)) / 1.7) < 1e-14 and sol.stats["nevals"] == 75
+    # the same answer as the reference-order CPU restatement with the same closure
+    Iq, Eq, neq, stq = O.solve_quadgk(lambda x: math.sin(x * 1.7), -2.0, 5.0, reltol=1e-10, abstol=1e-8)
+    assert abs(sol.u - Iq) <= 1e-15 and abs(sol.resid - Eq) <= 1e-15
+    with pytest.raises(TypeError, match="registered"):
+        ib.IntegralProblem(lambda x, p: x, (0.0, 1.0))          # plain callables stay rejected: the opt-in is explicit
