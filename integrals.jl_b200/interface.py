@@ -12,10 +12,12 @@ extension a maintainer would add is in INTEGRATION.md.  What mirrors what:
   QuadGKB200 / HCubatureB200                      QuadGKJL / HCubatureJL, src/algorithms.jl:51-56, 108-115
   QuadratureRuleB200 / GaussLegendreB200          src/algorithms.jl:229-249, 289-298
   TrapezoidalB200 / SimpsonsB200                  src/algorithms_sampled.jl:44, 71
+  BatchIntegralFunction / IntegralFunction        SciMLBase wrappers as used at src/Integrals.jl:274-335
   IntegralSolution(u, resid, retcode, chi)        SciMLBase.build_solution call sites Integrals.jl:338, 396
 
 Differences from the reference, all forced by "CUDA cannot run host closures":
-  * `prob.f` must be a registered integrand marker (integrands.py);
+  * `prob.f` is a registered integrand marker (integrands.py; runs on the device), or a BatchIntegralFunction / IntegralFunction
+    (any closure: evaluated by the caller on the batches of points the engine hands out, src/Integrals.jl:274-315);
   * batches: `p` may be a matrix nparam x nprob (one problem per column) and the bounds may be
     dim x nprob; then `sol.u` and `sol.resid` are vectors of length nprob;
   * `sol.stats` carries the per-problem evaluation counts and status codes the engine returns.
