@@ -30,21 +30,27 @@ def shard_indices(nprob, rank, world, interleave=False):
     return np.arange(lo, hi)
 
 
+def _is_vector(prob):
+    from .integrands import VectorOf
+    return isinstance(prob.f, VectorOf)
+
+
 def _slice_problem(prob, idx):
+    """the sub-batch `idx`: the last axis of p is the problem axis (nparam x nprob; VectorOf: nparam x ncomp x nprob)"""
     lb, ub = prob.domain
     p = np.asarray(prob.p, dtype=np.float64)
-    if p.ndim < 2:
-        raise ValueError("solve_sharded needs a batch: p must be nparam x nprob")
+    if p.ndim < (3 if _is_vector(prob) else 2):
+        raise ValueError("solve_sharded needs a batch: p must be nparam x nprob (VectorOf: nparam x ncomp x nprob)")
     lb = np.asarray(lb, dtype=np.float64); ub = np.asarray(ub, dtype=np.float64)
     if lb.ndim == 2:
         lb, ub = lb[:, idx], ub[:, idx]
-    return prob.remake(p=np.asfortranarray(p[:, idx]), domain=(lb, ub))
+    return prob.remake(p=np.asfortranarray(p[..., idx]), domain=(lb, ub))
 
 
 def solve_sharded(prob, alg, group=None, local_solve=None, interleave=False, **kws):
-    """solve(prob, alg; kws...) with the columns of prob.p split across the ranks of `group` (contiguous blocks, or
-    round-robin with interleave=True).  Every rank returns the full solution (u, resid, stats in problem order).
-    `local_solve(prob_block, alg, **kws)` defaults to interface.solve on this rank's GPU."""
+    """solve(prob, alg; kws...) with the problems of prob.p (its last axis) split across the ranks of `group` (contiguous blocks,
+    or round-robin with interleave=True).  Every rank returns the full solution (u, resid, stats in problem order; for VectorOf
+    problems u is ncomp x nprob).  `local_solve(prob_block, alg, **kws)` defaults to interface.solve on this rank's GPU."""
     import torch
     import torch.distributed as dist
     from . import interface
@@ -53,29 +59,32 @@ def solve_sharded(prob, alg, group=None, local_solve=None, interleave=False, **k
     if not dist.is_initialized():
         return local_solve(prob, alg, **kws)
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    nprob = np.asarray(prob.p).shape[1]
+    nprob = np.asarray(prob.p).shape[-1]
     idx = shard_indices(nprob, rank, world, interleave)
     sol = local_solve(_slice_problem(prob, idx), alg, **kws)
     backend = dist.get_backend(group)
     dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
-    # pack [u, resid, nevals, status] per problem into one padded buffer -> one all_gather
-    maxn = max(len(shard_indices(nprob, r, world, interleave)) for r in range(world))
-    pack = np.zeros((4, maxn))
+    # pack [u (ncomp rows), resid, nevals, status] per problem into one padded buffer -> one all_gather
     n = len(idx)
-    pack[0, :n] = np.atleast_1d(sol.u)
-    pack[1, :n] = np.nan if sol.resid is None else np.atleast_1d(sol.resid)
+    u = np.asarray(sol.u, dtype=np.float64).reshape(-1, n) if n else np.zeros((np.asarray(prob.p).shape[1] if _is_vector(prob) else 1, 0))
+    nu = u.shape[0]
+    maxn = max(len(shard_indices(nprob, r, world, interleave)) for r in range(world))
+    pack = np.zeros((nu + 3, maxn))
+    pack[:nu, :n] = u
+    pack[nu, :n] = np.nan if sol.resid is None else np.atleast_1d(sol.resid)
     if sol.stats is not None:
-        pack[2, :n] = sol.stats["nevals"]; pack[3, :n] = sol.stats["status"]
+        pack[nu + 1, :n] = sol.stats["nevals"]; pack[nu + 2, :n] = sol.stats["status"]
     mine = torch.from_numpy(pack).to(dev)
     parts = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(parts, mine, group=group)
-    full = np.zeros((4, nprob))
+    full = np.zeros((nu + 3, nprob))
     for r, t in enumerate(parts):
         ir = shard_indices(nprob, r, world, interleave)
         full[:, ir] = t.cpu().numpy()[:, :len(ir)]
-    resid = None if sol.resid is None else full[1]
-    stats = None if sol.stats is None else dict(nevals=full[2].astype(np.int64), status=full[3].astype(np.int32))
-    return interface.IntegralSolution(full[0], resid, prob, sol.alg, sol.retcode, None, stats)
+    resid = None if sol.resid is None else full[nu]
+    stats = None if sol.stats is None else dict(nevals=full[nu + 1].astype(np.int64), status=full[nu + 2].astype(np.int32))
+    uo = np.asfortranarray(full[:nu]) if _is_vector(prob) else full[0]
+    return interface.IntegralSolution(uo, resid, prob, sol.alg, sol.retcode, None, stats)
 
 
 def sampled_shard_axis(shape, dim):

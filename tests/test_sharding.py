@@ -42,7 +42,9 @@ def _oracle_solve(prob, alg, **kw):
     from integrals_b200 import interface
     lb, ub = prob.domain
     p = np.asarray(prob.p)
-    if isinstance(alg, ib.QuadGKB200):
+    if isinstance(prob.f, ib.VectorOf):
+        I, E, ne, st = O.hcubature_vec_batch("gauss", np.asarray(lb), np.asarray(ub), p, reltol=kw.get("reltol", 1e-8), abstol=kw.get("abstol", 1e-8))
+    elif isinstance(alg, ib.QuadGKB200):
         I, E, ne, st = O.quadgk_batch("sinxp", lb, ub, p, reltol=kw.get("reltol", 1e-8), abstol=kw.get("abstol", 1e-8))
     else:
         I, E, ne, st = O.hcubature_batch("gauss", np.asarray(lb), np.asarray(ub), p, reltol=kw.get("reltol", 1e-8), abstol=kw.get("abstol", 1e-8))
@@ -62,6 +64,13 @@ def _worker(rank, world, port, q):
         sol2 = sharding.solve_sharded(prob2, ib.HCubatureB200(), local_solve=_oracle_solve, reltol=1e-7)
         sol3 = sharding.solve_sharded(prob, ib.QuadGKB200(), local_solve=_oracle_solve, interleave=True, reltol=1e-10)
         assert np.array_equal(sol3.u, sol.u) and np.array_equal(sol3.stats["nevals"], sol.stats["nevals"])     # same answers, other partition
+        # vector-valued batch (VectorOf: p is nparam x ncomp x nprob; the problem axis is the last one)
+        pv = np.asfortranarray(np.vstack([np.linspace(1, 3, 3 * 7), np.linspace(2, 1, 3 * 7), np.full(21, .3), np.full(21, .6)]).reshape(4, 3, 7, order="F"))
+        probv = ib.IntegralProblem(ib.VectorOf(ib.GenzGaussian()), (np.zeros(2), np.ones(2)), pv)
+        solv = sharding.solve_sharded(probv, ib.HCubatureB200(), local_solve=_oracle_solve, reltol=1e-7)
+        import oracle as O
+        Iv, Ev, nev, stv = O.hcubature_vec_batch("gauss", np.zeros(2), np.ones(2), pv, reltol=1e-7)
+        assert solv.u.shape == (3, 7) and np.array_equal(solv.u, Iv) and np.array_equal(solv.resid, Ev) and np.array_equal(solv.stats["nevals"], nev)
         q.put((rank, sol.u, sol.resid, sol.stats["nevals"], sol2.u, sol2.stats["status"]))
     finally:
         dist.destroy_process_group()
