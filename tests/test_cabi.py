@@ -116,3 +116,25 @@ def test_device_rule_tables_equal_the_pinned_tables():
     osrc = open(os.path.join(root, "oracle", "oracle.c")).read()
     for term in gm:
         assert term.replace("D", "n") in osrc, term
+
+
+def test_every_entry_point_rejects_a_null_context():
+    """error behaviour of the boundary (SURVEY 8(b) "Errors"): no entry point dereferences a NULL context -- each returns
+    IB200_ERR_INVALID and leaves a message naming itself for ib200_last_error(NULL).  (Argument validation only: nothing here needs a GPU.)"""
+    import ctypes as C
+    L = ib.load_library()
+    no_ctx = {"ib200_version", "ib200_family_nparam", "ib200_last_error", "ib200_comm_unique_id", "ib200_create", "ib200_destroy",
+              "ib200_kernel_launches", "ib200_last_kernel_ms"}
+    checked = 0
+    for name in ib.SYMBOLS:
+        if name in no_ctx:
+            continue
+        fn = getattr(L, name)
+        args = [0.0 if t in (C.c_double, C.c_float) else (0 if t in (C.c_int32, C.c_int64) else None) for t in fn.argtypes]
+        assert fn(*args) == -1, name
+        msg = L.ib200_last_error(None).decode()
+        assert msg.startswith(name if name != "ib200_sampled_f32" else "ib200_sampled") and "NULL" in msg, (name, msg)
+        checked += 1
+    assert checked >= 20
+    assert L.ib200_kernel_launches(None) == 0
+    L.ib200_destroy(None)                                   # a no-op
