@@ -275,3 +275,25 @@ def test_sampled_nd_layout_property():
         ref = trapz(y, x=x.toarray() if uniform else x, axis=dim)
         assert np.shape(sol.u) == np.shape(ref) and np.allclose(sol.u, ref, rtol=1e-12, atol=1e-12)
     check()
+
+
+def test_integrand_markers_evaluate_like_the_oracle_family():
+    """every registered marker is also callable, f(x, p), with the definition the device code and the oracle share (csrc/family.cuh,
+    orc_family_eval): the pointwise values agree to rounding for all 11 families, so the same problem object can be handed to a
+    generic (closure-based) solver for parity checks -- INTEGRATION.md does the same with callable structs in Julia"""
+    import oracle as O
+    from util_gpu import ORC_FAM
+    rng = np.random.default_rng(12)
+    for cls in ib.ALL_INTEGRANDS:
+        f = cls()
+        for dim in (1, 2, 3, 5):
+            if not f.supports_dim(dim):
+                continue
+            for _ in range(20):
+                x = rng.uniform(0.05, 0.95, dim)
+                if f.name == "gausspoly":
+                    p = np.concatenate([rng.uniform(0.5, 3, dim), rng.uniform(0, 1, dim), rng.integers(0, 4, dim).astype(float), [rng.uniform(0.5, 2)]])
+                else:
+                    p = rng.uniform(0.2, 3.0, f.nparam(dim))
+                got, ref = f(x if dim > 1 else x[0], p), O.family_eval(ORC_FAM[f.name], x, p)
+                assert abs(got - ref) <= 1e-13 * max(1.0, abs(ref)), (f.name, dim, got, ref)
