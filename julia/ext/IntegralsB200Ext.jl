@@ -1,74 +1,6 @@
-# INTEGRATION — binding libintegrals_b200.so into Integrals.jl
+# GENERATED from INTEGRATION.md (section 3: the package extension) by scripts/extract_julia_binding.py -- edit the document, not this file.
+# Binding of libintegrals_b200.so (C ABI: include/integrals_b200.h) into Integrals.jl; untested here (no Julia in the build image).
 
-The drop-in boundary is the C ABI in `include/integrals_b200.h`.  This file shows the
-reference-side binding a maintainer would add: a package extension (`ext/IntegralsB200Ext.jl`,
-registered like the other back-ends in `Project.toml:18-44`) plus the algorithm structs next to
-`src/algorithms_extension.jl`.  Julia is not installed in this image, so the code below is delivered
-as source (also written out as `julia/algorithms_b200.jl` and `julia/ext/IntegralsB200Ext.jl` by `scripts/extract_julia_binding.py`;
-`tests/test_cabi.py` checks every `ccall` against the header's prototypes) and is **untested here**; the same calls are exercised through the Python `ctypes`
-binding (`integrals.jl_b200/_lib.py`) by `tests/test_gpu_parity.py`, `tests/test_gpu_vector_cubature.py`, `tests/test_gpu_zz_batch_bridge.py` (kernels through the C ABI) and `tests/test_host_logic.py` (the solve-interface mirror).
-
-## 1. What replaces what
-
-| C entry point | replaces (reference file:line) | reached from |
-|---|---|---|
-| `ib200_quadgk_batch` | `QuadGK.quadgk(...)` call at `src/Integrals.jl:327-335` inside `__solvebp_call(::QuadGKJL)` `:252-339` | `__solvebp_call(cache, ::QuadGKB200, …)` |
-| `ib200_quadgk_rule_batch` | the same call with `order = alg.order ≠ 7`; the tables are `x, w, wg = QuadGK.kronrod(alg.order)` passed as they are | `__solvebp_call(cache, ::QuadGKB200, …)` |
-| `ib200_quadgk_vec_batch` | `QuadGK.quadgk!(f!, result, …; norm = alg.norm)` for array-valued integrands, `src/Integrals.jl:316-326` (`QuadGKJL.norm`, `src/algorithms.jl:10-11,56`) | `__solvebp_call(cache, ::QuadGKB200, …)` when `prob.f.f isa VectorOf` (p :: nparam × ncomp [× nprob]) |
-| `ib200_hcubature_vec_batch` | `HCubature.hcubature / hquadrature(…; norm = alg.norm)` for array-valued integrands, `src/Integrals.jl:380-393` (`HCubatureJL.norm`, `src/algorithms.jl:66-67,108-115`) | `__solvebp_call(cache, ::HCubatureB200, …)` when `prob.f.f isa VectorOf` |
-| `ib200_batch_open / next / points / values / result` | the engine-side half of `BatchIntegralFunction` (`src/Integrals.jl:274-315`: QuadGK's `BatchIntegrand`): the rule's points, weighted sums, error estimates and the refinement; Julia evaluates `f(pts, p)` on each round's batch | `__solvebp_call(cache, ::QuadGKB200 / ::HCubatureB200, …)` when `cache.f isa BatchIntegralFunction` |
-| `ib200_sampled_f32` | the same `evalrule` on `Float32` samples with a `Float32` grid (`test/interface_tests.jl:524-539`) | sampled solve when `eltype(y) == eltype(x) == Float32` |
-| `ib200_hcubature_batch` | `HCubature.hcubature / hquadrature` at `src/Integrals.jl:380-393` inside `__solvebp_call(::HCubatureJL)` `:347-397` | `__solvebp_call(cache, ::HCubatureB200, …)` |
-| `ib200_hcubature_single` | same call, one large domain spread over all GPUs | `HCubatureB200(single = true)` |
-| `ib200_fixed_rule_tensor_batch`, `ib200_fixed_rule_nodes_batch` | `evalrule(f,p,lb,ub,nodes,weights)` `src/quadrules.jl:1-19` called from `:25-52` | `__solvebp_call(cache, ::QuadratureRuleB200, …)` |
-| `ib200_gauss_legendre_batch` | `gauss_legendre` / `composite_gauss_legendre` `ext/IntegralsFastGaussQuadratureExt.jl:11-32` | `__solvebp_call(cache, ::GaussLegendreB200, …)` |
-| `ib200_sampled` | `evalrule(data, weights, dim)` `src/sampled.jl:51-124` with the weights of `src/trapezoidal.jl:16-45`, `src/simpsons.jl:16-87` | `__solvebp_call(cache::SampledIntegralCache, ::TrapezoidalB200 / ::SimpsonsB200)` |
-| transform id argument | `transformation_if_inf / _tan_inf / _cot_inf` `src/infinity_handling.jl:165-170,277-282,405-410` applied by `__solve(::ChangeOfVariables)` `src/Integrals.jl:192-224` | intercepted `__solve` below |
-| `ib200_create` / `ib200_destroy` | `init_cacheval` (`src/common.jl:40,105`; QuadGK segbuf `src/Integrals.jl:241-250`) | `init_cacheval(::AbstractB200Algorithm, prob)` |
-
-## 2. Algorithm structs (next to `src/algorithms_extension.jl:27`)
-
-```julia
-abstract type AbstractB200Algorithm <: AbstractIntegralCExtensionAlgorithm end
-
-struct QuadGKB200 <: AbstractB200Algorithm                          # like QuadGKJL(; order = 7, norm = norm)
-    order::Int              # 7: built-in tables; 2..30: QuadGK.kronrod(order) is passed to the engine
-    norm::Symbol            # :two (LinearAlgebra.norm) or :inf -- only used by vector-valued integrands (VectorOf)
-end
-QuadGKB200(; order = 7, norm = :two) = QuadGKB200(order, norm)
-struct HCubatureB200 <: AbstractB200Algorithm
-    initdiv::Int
-    single::Bool            # true: one domain region-partitioned over all GPUs
-end
-HCubatureB200(; initdiv = 1, single = false) = HCubatureB200(initdiv, single)
-struct QuadratureRuleB200{Q} <: AbstractB200Algorithm
-    q::Q; n::Int; tensor::Bool
-end
-QuadratureRuleB200(q; n = 250, tensor = false) = QuadratureRuleB200(q, n, tensor)
-struct GaussLegendreB200 <: AbstractB200Algorithm
-    nodes::Vector{Float64}; weights::Vector{Float64}; subintervals::Int
-end
-struct TrapezoidalB200 <: AbstractSampledIntegralAlgorithm end
-struct SimpsonsB200 <: AbstractSampledIntegralAlgorithm end
-
-# registered device-side integrands: callable structs, so the SAME problem also runs under
-# QuadGKJL / HCubatureJL for parity checks
-struct SinXP end;            (::SinXP)(x, p) = sin(x * p[1])
-struct GenzOscillatory end;  (::GenzOscillatory)(x, p) = (d = length(x); cos(2π * p[d + 1] + sum(p[i] * x[i] for i in 1:d)))
-struct GenzProductPeak end;  (::GenzProductPeak)(x, p) = (d = length(x); 1 / prod(p[i]^-2 + (x[i] - p[d + i])^2 for i in 1:d))
-struct GenzCornerPeak end;   (::GenzCornerPeak)(x, p) = (d = length(x); (1 + sum(p[i] * x[i] for i in 1:d))^(-(d + 1)))
-struct GenzGaussian end;     (::GenzGaussian)(x, p) = (d = length(x); exp(-sum((p[i] * (x[i] - p[d + i]))^2 for i in 1:d)))
-struct GenzC0 end;           (::GenzC0)(x, p) = (d = length(x); exp(-sum(p[i] * abs(x[i] - p[d + i]) for i in 1:d)))
-struct GenzDiscontinuous end
-(::GenzDiscontinuous)(x, p) = (d = length(x); (x[1] > p[d + 1] || (d > 1 && x[2] > p[d + 2])) ? 0.0 : exp(sum(p[i] * x[i] for i in 1:d)))
-family_id(::SinXP) = 0; family_id(::GenzOscillatory) = 1; family_id(::GenzProductPeak) = 2
-family_id(::GenzCornerPeak) = 3; family_id(::GenzGaussian) = 4; family_id(::GenzC0) = 5; family_id(::GenzDiscontinuous) = 6
-family_id(f) = throw(ArgumentError("the B200 back-end integrates registered integrands only; got $(typeof(f))"))
-```
-
-## 3. The extension (`ext/IntegralsB200Ext.jl`)
-
-```julia
 module IntegralsB200Ext
 using Integrals, SciMLBase
 using Integrals: IntegralCache, SampledIntegralCache, ChangeOfVariables, AbstractB200Algorithm,
@@ -232,48 +164,3 @@ function Integrals.__solvebp_call(cache::SampledIntegralCache, alg::Union{Trapez
     SciMLBase.build_solution(cache.prob, alg, out, nothing, retcode = ReturnCode.Success)   # like src/sampled.jl:166-167
 end
 end # module
-```
-
-Usage (mirrors `README.md:33-40`):
-
-```julia
-prob = IntegralProblem(SinXP(), (-2.0, 5.0), reshape(ps, 1, :))        # p :: 1 x 65536 => 65,536 problems
-sol  = solve(prob, QuadGKB200(); reltol = 1e-10)                        # sol.u, sol.resid :: Vector{Float64}
-sol  = solve(IntegralProblem(GenzGaussian(), (zeros(4), ones(4)), P4), HCubatureB200(); reltol = 1e-6)
-sol  = solve(SampledIntegralProblem(y, x; dim = 2), TrapezoidalB200())
-g    = BatchIntegralFunction((pts, p) -> vec(prod(cos.(p .* pts); dims = 1)))  # any closure, evaluated by the caller
-sol  = solve(IntegralProblem(g, (ones(3), 3ones(3)), 1.0), HCubatureB200(); reltol = 1e-8)
-```
-
-### Multi-GPU
-
-Batches shard by columns of `p` with no engine-side communication: each process (one per GPU) creates its own
-`B200Context(device)` and solves its block (`integrals.jl_b200/sharding.py` is the Python counterpart).  The
-single-domain solve needs the library's communicator, set up once per process:
-
-```julia
-id = zeros(UInt8, 128)
-rank == 0 && ccall((:ib200_comm_unique_id, lib), Int32, (Ptr{UInt8},), id)
-MPI.Bcast!(id, 0, comm)                                   # any broadcast of the 128 bytes will do
-check(ctx, ccall((:ib200_comm_init, lib), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{UInt8}), ctx.h, nranks, rank, id))
-# ... every rank: solve(prob, HCubatureB200(single = true); reltol, abstol, maxiters) with identical arguments ...
-ccall((:ib200_comm_destroy, lib), Int32, (Ptr{Cvoid},), ctx.h)      # collective
-```
-
-Every rank returns the same `(u, resid)` bit for bit (replicated box store; DESIGN.md §6).
-
-## 4. Python binding used in this repository
-
-`integrals.jl_b200/_lib.py` (`ctypes.CDLL`) declares the same signatures; `tests/test_cabi.py` checks
-that the library exports every symbol the header declares.  `integrals.jl_b200/interface.py`
-mirrors the Julia-side dispatch above line for line (`init` auto-wraps in `ChangeOfVariables`,
-merges problem kwargs under solve kwargs, rejects unknown kwargs with `CommonKwargError`, rejects
-kwargs for sampled problems, `retcode = Success` always).
-
-## 5. Error mapping
-
-| C return | message source | Julia side |
-|---|---|---|
-| `IB200_ERR_INVALID` (−1) | argument checks; messages reuse the reference's wording where one exists ("No points to integrate", `src/sampled.jl:55`; "only accepts one-dimensional quadrature problems", `src/Integrals.jl:264-266`; "The length of the grid must exceed 2 for simpsons rule.", `src/simpsons.jl:46`) | `ArgumentError` |
-| `IB200_ERR_CUDA`/`OOM`/`UNSUPPORTED`/`NCCL` | runtime | `ErrorException` |
-| per-problem `status` 0/1/2/3 | converged / budget / non-finite / QuadGK endpoint round-off | reference reports `Success` always (`src/Integrals.jl:338,396`); kept, the codes are extra information |

@@ -138,3 +138,33 @@ def test_every_entry_point_rejects_a_null_context():
     assert checked >= 20
     assert L.ib200_kernel_launches(None) == 0
     L.ib200_destroy(None)                                   # a no-op
+
+
+def test_julia_binding_files_match_the_document():
+    """julia/algorithms_b200.jl and julia/ext/IntegralsB200Ext.jl are INTEGRATION.md's code blocks written out as source, and every
+    `ccall((:name, lib), ...)` in them names a symbol the header declares, with the argument count of its prototype"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("extract_julia_binding", os.path.join(ROOT, "scripts", "extract_julia_binding.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    for rel, src in mod.render().items():
+        assert open(os.path.join(ROOT, rel)).read() == src, f"{rel} is stale: run scripts/extract_julia_binding.py"
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "integrals_b200.h")).read(), flags=re.S)
+    nargs = {}
+    for m in re.finditer(r"\b(ib200_\w+)\s*\(([^;]*?)\)\s*;", hdr, flags=re.S):
+        a = m.group(2).strip()
+        nargs[m.group(1)] = 0 if a in ("", "void") else a.count(",") + 1
+    jl = open(os.path.join(ROOT, "julia", "ext", "IntegralsB200Ext.jl")).read()
+    jl = "\n".join(line for line in jl.splitlines() if not line.lstrip().startswith("#"))      # comment lines sketch calls with "..."
+    seen = 0
+    for m in re.finditer(r"ccall\(\(:(ib200_\w+), lib\),\s*\w+,\s*\(", jl):
+        name = m.group(1)
+        assert name in nargs, name
+        i = m.end(); depth = 1; j = i
+        while depth:                                       # the argument-type tuple
+            depth += {"(": 1, ")": -1}.get(jl[j], 0); j += 1
+        types = re.sub(r"#=.*?=#", "", jl[i:j - 1], flags=re.S)
+        n = len([t for t in types.split(",") if t.strip()])
+        assert n == nargs[name], (name, n, nargs[name])
+        seen += 1
+    assert seen >= 10
