@@ -150,10 +150,12 @@ def test_julia_binding_files_match_the_document():
     for rel, src in mod.render().items():
         assert open(os.path.join(ROOT, rel)).read() == src, f"{rel} is stale: run scripts/extract_julia_binding.py"
     hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "integrals_b200.h")).read(), flags=re.S)
-    nargs = {}
+    nargs, kinds = {}, {}
     for m in re.finditer(r"\b(ib200_\w+)\s*\(([^;]*?)\)\s*;", hdr, flags=re.S):
         a = m.group(2).strip()
         nargs[m.group(1)] = 0 if a in ("", "void") else a.count(",") + 1
+        kinds[m.group(1)] = "" if a in ("", "void") else "".join(
+            "p" if "*" in t else ("f" if re.search(r"\b(double|float)\b", t) else "i") for t in a.split(","))
     jl = open(os.path.join(ROOT, "julia", "ext", "IntegralsB200Ext.jl")).read()
     jl = "\n".join(line for line in jl.splitlines() if not line.lstrip().startswith("#"))      # comment lines sketch calls with "..."
     seen = 0
@@ -164,7 +166,9 @@ def test_julia_binding_files_match_the_document():
         while depth:                                       # the argument-type tuple
             depth += {"(": 1, ")": -1}.get(jl[j], 0); j += 1
         types = re.sub(r"#=.*?=#", "", jl[i:j - 1], flags=re.S)
-        n = len([t for t in types.split(",") if t.strip()])
-        assert n == nargs[name], (name, n, nargs[name])
+        tl = [t.strip() for t in types.split(",") if t.strip()]
+        assert len(tl) == nargs[name], (name, len(tl), nargs[name])
+        got = "".join("p" if t.startswith(("Ptr{", "Ref{", "Cstring")) else ("f" if t in ("Float64", "Float32") else "i") for t in tl)
+        assert got == kinds[name], (name, got, kinds[name])       # pointers, integers and floats at the same positions
         seen += 1
     assert seen >= 10
