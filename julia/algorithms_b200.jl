@@ -8,11 +8,12 @@ struct QuadGKB200 <: AbstractB200Algorithm                          # like QuadG
     norm::Symbol            # :two (LinearAlgebra.norm) or :inf -- only used by vector-valued integrands (VectorOf)
 end
 QuadGKB200(; order = 7, norm = :two) = QuadGKB200(order, norm)
-struct HCubatureB200 <: AbstractB200Algorithm
+struct HCubatureB200 <: AbstractB200Algorithm                       # like HCubatureJL(; initdiv = 1, norm = norm)
     initdiv::Int
     single::Bool            # true: one domain region-partitioned over all GPUs
+    norm::Symbol            # :two or :inf -- only used by vector-valued integrands (VectorOf)
 end
-HCubatureB200(; initdiv = 1, single = false) = HCubatureB200(initdiv, single)
+HCubatureB200(; initdiv = 1, single = false, norm = :two) = HCubatureB200(initdiv, single, norm)
 struct QuadratureRuleB200{Q} <: AbstractB200Algorithm
     q::Q; n::Int; tensor::Bool
 end
@@ -35,4 +36,7 @@ struct GenzDiscontinuous end
 (::GenzDiscontinuous)(x, p) = (d = length(x); (x[1] > p[d + 1] || (d > 1 && x[2] > p[d + 2])) ? 0.0 : exp(sum(p[i] * x[i] for i in 1:d)))
 family_id(::SinXP) = 0; family_id(::GenzOscillatory) = 1; family_id(::GenzProductPeak) = 2
 family_id(::GenzCornerPeak) = 3; family_id(::GenzGaussian) = 4; family_id(::GenzC0) = 5; family_id(::GenzDiscontinuous) = 6
+# vector-valued integrand built from one registered family: component c uses the parameter column p[:, c]
+struct VectorOf{F} base::F end; (v::VectorOf)(x, p) = [v.base(x, view(p, :, c)) for c in axes(p, 2)]
+family_id(v::VectorOf) = family_id(v.base)
 family_id(f) = throw(ArgumentError("the B200 back-end integrates registered integrands only; got $(typeof(f))"))

@@ -2,8 +2,8 @@
 # Binding of libintegrals_b200.so (C ABI: include/integrals_b200.h) into Integrals.jl; untested here (no Julia in the build image).
 
 module IntegralsB200Ext
-using Integrals, SciMLBase
-using Integrals: IntegralCache, SampledIntegralCache, ChangeOfVariables, AbstractB200Algorithm,
+using Integrals, SciMLBase, QuadGK
+using Integrals: IntegralCache, VectorOf, SampledIntegralCache, ChangeOfVariables, AbstractB200Algorithm,
                  QuadGKB200, HCubatureB200, QuadratureRuleB200, GaussLegendreB200, TrapezoidalB200, SimpsonsB200,
                  transformation_if_inf, transformation_tan_inf, transformation_cot_inf, family_id
 const lib = "libintegrals_b200"          # on the loader path, built by `make -C integrals.jl_b200/csrc`
@@ -42,15 +42,26 @@ _bounds(lb, ub) = (collect(Float64, vec(collect(lb))), collect(Float64, vec(coll
 
 function Integrals.__solvebp_call(cache::IntegralCache, alg::QuadGKB200, sensealg, domain, p;
                                   transform = Int32(0), reltol = 1.0e-8, abstol = 1.0e-8, maxiters = typemax(Int))
+    cache.f isa BatchIntegralFunction && return solve_batchfn(cache, alg, domain, p; transform, reltol, abstol, maxiters)   # src/Integrals.jl:274
     lb, ub, bpp, dim = _bounds(domain...)
     dim == 1 || throw(ArgumentError("QuadGKB200 only accepts one-dimensional quadrature problems."))
+    cache.f.f isa VectorOf && return solve_vector(cache, alg, lb, ub, bpp, dim, p; transform, reltol, abstol, maxiters)      # src/Integrals.jl:316-326
     P = _mat(p); nprob = size(P, 2)
     I = Vector{Float64}(undef, nprob); E = similar(I); ne = Vector{Int64}(undef, nprob); st = Vector{Int32}(undef, nprob)
     ctx = cache.cacheval
-    GC.@preserve lb ub P I E ne st check(ctx, ccall((:ib200_quadgk_batch, lib), Int32,
-        (Ptr{Cvoid}, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Int32, Ptr{Float64}, Int32, Int64, Float64, Float64, Int64,
-         Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int32}),
-        ctx.h, family_id(cache.f.f), transform, lb, ub, bpp, P, size(P, 1), nprob, reltol, abstol, min(maxiters, 2^62), I, E, ne, st))
+    if alg.order == 7
+        GC.@preserve lb ub P I E ne st check(ctx, ccall((:ib200_quadgk_batch, lib), Int32,
+            (Ptr{Cvoid}, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Int32, Ptr{Float64}, Int32, Int64, Float64, Float64, Int64,
+             Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int32}),
+            ctx.h, family_id(cache.f.f), transform, lb, ub, bpp, P, size(P, 1), nprob, reltol, abstol, min(maxiters, 2^62), I, E, ne, st))
+    else                                                   # order = alg.order (src/Integrals.jl:331-334): QuadGK's own tables, as they are
+        x, w, wg = QuadGK.kronrod(alg.order)
+        GC.@preserve lb ub P I E ne st x w wg check(ctx, ccall((:ib200_quadgk_rule_batch, lib), Int32,
+            (Ptr{Cvoid}, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Int32, Ptr{Float64}, Int32, Int64, Float64, Float64, Int64,
+             Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int32}),
+            ctx.h, family_id(cache.f.f), transform, lb, ub, bpp, P, size(P, 1), nprob, reltol, abstol, min(maxiters, 2^62),
+            alg.order, x, w, wg, I, E, ne, st))
+    end
     prob = Integrals.build_problem(cache)
     u, r = p isa AbstractMatrix ? (I, E) : (I[1], E[1])
     SciMLBase.build_solution(prob, alg, u, r, retcode = ReturnCode.Success)     # like src/Integrals.jl:338
@@ -58,7 +69,10 @@ end
 
 function Integrals.__solvebp_call(cache::IntegralCache, alg::HCubatureB200, sensealg, domain, p;
                                   transform = Int32(0), reltol = 1.0e-8, abstol = 1.0e-8, maxiters = typemax(Int))
+    cache.f isa BatchIntegralFunction && return solve_batchfn(cache, alg, domain, p; transform, reltol, abstol, maxiters)
+    alg.single && return solve_single(cache, alg, domain, p; transform, reltol, abstol, maxiters)
     lb, ub, bpp, dim = _bounds(domain...)
+    cache.f.f isa VectorOf && return solve_vector(cache, alg, lb, ub, bpp, dim, p; transform, reltol, abstol, maxiters)      # norm = alg.norm, src/Integrals.jl:380-393
     P = _mat(p); nprob = size(P, 2)
     I = Vector{Float64}(undef, nprob); E = similar(I); ne = Vector{Int64}(undef, nprob); st = Vector{Int32}(undef, nprob)
     ctx = cache.cacheval
@@ -72,24 +86,33 @@ function Integrals.__solvebp_call(cache::IntegralCache, alg::HCubatureB200, sens
     SciMLBase.build_solution(prob, alg, u, r, retcode = ReturnCode.Success)     # like src/Integrals.jl:396
 end
 
-# other Gauss-Kronrod orders and vector-valued integrands use the same shape of call:
-#   alg.order != 7:   x, w, wg = QuadGK.kronrod(alg.order)       # the layout ib200_quadgk_rule_batch expects
-#                     ccall((:ib200_quadgk_rule_batch, lib), Int32, (..., Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, ...),
-#                           ..., alg.order, x, w, wg, I, E, ne, st)
-#   cache.f.f isa VectorOf:   P :: nparam x ncomp [x nprob];  I = Matrix{Float64}(undef, ncomp, nprob)
-#                     ccall((:ib200_quadgk_vec_batch, lib), Int32, (..., Int32 #=nparam=#, Int32 #=ncomp=#, Int64 #=nprob=#, Float64, Float64,
-#                           Int64, Int32 #=norm: 0 two, 1 inf=#, ...), ..., I, E, ne, st)   # sol.u = I[:, 1] (or I), sol.resid = E[1] (or E)
-
-#   the same under HCubatureB200 (norm = alg.norm, src/Integrals.jl:380-393):
-#                     ccall((:ib200_hcubature_vec_batch, lib), Int32, (Ptr{Cvoid}, Int32 #=family=#, Int32 #=dim=#, Int32 #=transform=#,
-#                           Ptr{Float64}, Ptr{Float64}, Int32, Ptr{Float64}, Int32 #=nparam=#, Int32 #=ncomp=#, Int64 #=nprob=#, Float64, Float64,
-#                           Int64, Int32 #=initdiv=#, Int32 #=norm=#, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int32}), ..., I, E, ne, st)
+# vector-valued integrands (VectorOf): p :: nparam x ncomp (one problem) or nparam x ncomp x nprob; the components share the nodes and
+# the subdivision, the error is a norm over them (QuadGKJL.norm / HCubatureJL.norm)
+function solve_vector(cache::IntegralCache, alg::Union{QuadGKB200, HCubatureB200}, lb, ub, bpp, dim, p; transform, reltol, abstol, maxiters)
+    P = p isa AbstractMatrix ? reshape(Array{Float64}(p), size(p, 1), size(p, 2), 1) : Array{Float64, 3}(p)
+    nparam, ncomp, nprob = size(P)
+    I = Matrix{Float64}(undef, ncomp, nprob); E = Vector{Float64}(undef, nprob); ne = Vector{Int64}(undef, nprob); st = Vector{Int32}(undef, nprob)
+    ctx = cache.cacheval
+    normkind = Int32(alg.norm === :inf ? 1 : 0)
+    if alg isa QuadGKB200
+        GC.@preserve lb ub P I E ne st check(ctx, ccall((:ib200_quadgk_vec_batch, lib), Int32,
+            (Ptr{Cvoid}, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Int32, Ptr{Float64}, Int32, Int32, Int64, Float64, Float64, Int64, Int32,
+             Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int32}),
+            ctx.h, family_id(cache.f.f), transform, lb, ub, bpp, P, nparam, ncomp, nprob, reltol, abstol, min(maxiters, 2^62), normkind, I, E, ne, st))
+    else
+        GC.@preserve lb ub P I E ne st check(ctx, ccall((:ib200_hcubature_vec_batch, lib), Int32,
+            (Ptr{Cvoid}, Int32, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Int32, Ptr{Float64}, Int32, Int32, Int64, Float64, Float64, Int64, Int32, Int32,
+             Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int32}),
+            ctx.h, family_id(cache.f.f), dim, transform, lb, ub, bpp, P, nparam, ncomp, nprob, reltol, abstol, min(maxiters, 2^62), alg.initdiv, normkind,
+            I, E, ne, st))
+    end
+    u, r = p isa AbstractMatrix ? (I[:, 1], E[1]) : (I, E)
+    SciMLBase.build_solution(Integrals.build_problem(cache), alg, u, r, retcode = ReturnCode.Success)
+end
 
 # BatchIntegralFunction (src/Integrals.jl:274-315): ANY Julia closure f(pts, p) -> values, evaluated by Julia on the batches of
 # points the engine hands out; the points of a round, the weighted sums, the error estimates and the refinement stay on the
 # device.  With CuArray buffers (pointer(x::CuArray)) nothing is copied; a host Array works the same way.
-# (the two __solvebp_call methods above start with `cache.f isa BatchIntegralFunction && return solve_batchfn(cache, alg, domain, p; ...)`,
-#  the branch the reference takes at src/Integrals.jl:274)
 function solve_batchfn(cache::IntegralCache, alg::Union{QuadGKB200, HCubatureB200}, domain, p;
                        transform = Int32(0), reltol = 1.0e-8, abstol = 1.0e-8, maxiters = typemax(Int))
     f = cache.f
