@@ -2,7 +2,7 @@
 // integrand is evaluated by the CALLER, a batch of points at a time.
 //
 // Reference: BatchIntegralFunction (src/Integrals.jl:274-315: QuadGKJL hands QuadGK a BatchIntegrand, f(y, u) on a vector
-// of points; test/interface_tests.jl:346-420 "Batched ... Integrands").  The registered-family kernels cannot run a Julia
+// of points; test/interface_tests.jl:189-258 "Batched ... Integrands").  The registered-family kernels cannot run a Julia
 // (or Python) closure, but a closure that maps `pts` (dim x n) to n values can run anywhere -- on the host, or as a
 // CuArray / torch broadcast on the same GPU.  So the engine keeps what is data-parallel and stateful on the device -- the
 // box store, the rule's points, the weighted sums, error estimates, split axes and the whole refinement bookkeeping of

@@ -2,7 +2,7 @@
 points and the adaptive refinement of one integral on the device, the CALLER evaluates the integrand on each round's batch
 (reference: BatchIntegralFunction under QuadGKJL, src/Integrals.jl:274-315).  Checker: orc_hcubature_rounds with the same
 integrand -- same rounds, boxes and rule applications, (I, E) equal to summation-order rounding -- closed forms, and the
-reference's batched-integrand known answers (test/interface_tests.jl:346-420).
+reference's batched-integrand known answers (test/interface_tests.jl:189-258).
 (The file name sorts this module after the other GPU modules.)"""
 import math
 
@@ -92,7 +92,7 @@ def test_bridge_infinite_domains_readme_example_and_budget(eng, O):
 
 def test_bridge_through_solve_and_call_order(eng):
     """solve(IntegralProblem(BatchIntegralFunction(f), domain, p), alg): the reference's batched-integrand known answers
-    (test/interface_tests.jl:346-420: f = 1 and prod(cos.(x)) on [1,3]^dim, reltol = abstol = 1e-5); protocol errors"""
+    (test/interface_tests.jl:189-258: f = 1 and prod(cos.(x)) on [1,3]^dim, reltol = abstol = 1e-5); protocol errors"""
     for dim in (1, 2, 3):
         alg = ib.QuadGKB200() if dim == 1 else ib.HCubatureB200()
         dom = (1.0, 3.0) if dim == 1 else (np.ones(dim), 3 * np.ones(dim))
