@@ -131,11 +131,22 @@ int32_t ib200_quadgk_batch(ib200_ctx *ctx, int32_t family, int32_t transform,
                            double reltol, double abstol, int64_t maxevals,
                            double *out_I, double *out_E, int64_t *out_nevals, int32_t *out_status);
 /* -- adaptive N-D: replaces HCubature.hcubature / hquadrature(f, lb, ub; rtol, atol, maxevals,
-      initdiv) as called at src/Integrals.jl:380-393 (__solvebp_call(::HCubatureJL) :347-397). */
+      initdiv) as called at src/Integrals.jl:380-393 (__solvebp_call(::HCubatureJL) :347-397).
+      mode: which refinement driver runs the reference's algorithm
+        IB200_HCUB_REFERENCE_ORDER  one box per step, largest error first -- the reference's own sequence of boxes
+                                    (csrc/hcubature_pair.cuh, hcubature_impl.cuh; 1 <= dim <= 8)
+        IB200_HCUB_ROUNDS           every box whose error is above a per-problem threshold is bisected in the same round
+                                    (csrc/hcubature_rb.cuh; 2 <= dim <= 5): same rule, split axis, stopping test and
+                                    closing sum, a different ORDER of refinement, hence different evaluation counts;
+                                    (I, E) agree with mode 0 within the requested tolerance.  maxevals is honoured as a
+                                    budget of rule applications, ceil(maxevals / points per rule); the last round may
+                                    overshoot it (a round always bisects the boxes within a factor 2 of the worst). */
+#define IB200_HCUB_REFERENCE_ORDER 0
+#define IB200_HCUB_ROUNDS          1
 int32_t ib200_hcubature_batch(ib200_ctx *ctx, int32_t family, int32_t dim, int32_t transform,
                               const double *lb, const double *ub, int32_t bounds_per_problem,
                               const double *params, int32_t nparam, int64_t nprob,
-                              double reltol, double abstol, int64_t maxevals, int32_t initdiv,
+                              double reltol, double abstol, int64_t maxevals, int32_t initdiv, int32_t mode,
                               double *out_I, double *out_E, int64_t *out_nevals, int32_t *out_status);
 
 /* -- the same solve with the Gauss-Kronrod rule of another order (QuadGKJL(order = n), src/algorithms.jl:51-56, forwarded

@@ -75,7 +75,7 @@ def load_library():
     L.ib200_quadgk_vec_batch.argtypes = [vp, i32, i32, vp, vp, i32, vp, i32, i32, i64, dp, dp, i64, i32, vp, vp, vp, vp]
     L.ib200_quadgk_vec_batch.restype = i32
     L.ib200_sampled_f32.argtypes = [vp, i32, vp, i64, i64, i64, C.c_float, vp, vp]; L.ib200_sampled_f32.restype = i32
-    L.ib200_hcubature_batch.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp, i32, i64, dp, dp, i64, i32, vp, vp, vp, vp]
+    L.ib200_hcubature_batch.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp, i32, i64, dp, dp, i64, i32, i32, vp, vp, vp, vp]
     L.ib200_hcubature_batch.restype = i32
     L.ib200_hcubature_vec_batch.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp, i32, i32, i64, dp, dp, i64, i32, i32, vp, vp, vp, vp]
     L.ib200_hcubature_vec_batch.restype = i32
@@ -107,11 +107,27 @@ def _ptr(a):
     return a.ctypes.data, a
 
 
-def _f64(a, order="F"):
-    """Host arrays are made float64 column-major; device tensors are passed through."""
-    if a is None or hasattr(a, "data_ptr"):
+def _f64(a, order="F", what="array"):
+    """Host arrays are made float64 column-major; device tensors are used in place and must already be float64 and
+    contiguous (the kernels read raw doubles)."""
+    if a is None:
+        return a
+    if hasattr(a, "data_ptr"):
+        _dev_check(a, "float64", what)
         return a
     return np.asarray(a, dtype=np.float64, order=order)
+
+
+def _dev_check(a, dtype, what="array"):
+    """A tensor passed by pointer: right element type, dense memory."""
+    got = str(getattr(a, "dtype", "")).replace("torch.", "")
+    if got != dtype:
+        raise TypeError(f"{what}: tensor arguments are passed by pointer and must be {dtype}, got {got}")
+    if hasattr(a, "is_contiguous") and not a.is_contiguous():
+        raise ValueError(f"{what}: tensor arguments must be contiguous")
+
+
+HCUB_MODES = {"reference_order": 0, "rounds": 1, 0: 0, 1: 1}
 
 
 MAXEVALS_UNBOUNDED = 2 ** 62   # the reference passes typemax(Int) (src/Integrals.jl:255,350)
@@ -176,6 +192,13 @@ class Engine:
     def _out(self, out, n, dtype=np.float64):
         if out is None:
             out = np.empty(n, dtype=dtype)
+        elif hasattr(out, "data_ptr"):
+            _dev_check(out, np.dtype(dtype).name, "output")
+            if out.numel() < n:
+                raise ValueError(f"output tensor has {out.numel()} elements, {n} needed")
+        else:
+            if out.dtype != np.dtype(dtype) or out.size < n or not (out.flags.c_contiguous or out.flags.f_contiguous):
+                raise ValueError(f"output array must be a dense {np.dtype(dtype).name} array of at least {n} elements")
         return out
 
     @staticmethod
@@ -190,7 +213,15 @@ class Engine:
         # bounds: `dim` numbers shared by all problems, or dim x nprob (1-D problems: a vector of nprob)
         nd = lb.dim() if hasattr(lb, "data_ptr") else lb.ndim
         nel = lb.numel() if hasattr(lb, "data_ptr") else lb.size
+        nel_u = ub.numel() if hasattr(ub, "data_ptr") else ub.size
+        if nel_u != nel:
+            raise ValueError(f"lb and ub differ in size ({nel} vs {nel_u})")
         if nd == 2:
+            # per-problem bounds: dim x nprob column-major (numpy (dim, nprob) F-order; torch (nprob, dim) row-major)
+            shp = tuple(lb.shape)
+            want = (nprob, dim) if hasattr(lb, "data_ptr") else (dim, nprob)
+            if shp != want or tuple(ub.shape) != want:
+                raise ValueError(f"per-problem bounds must be {dim} x {nprob}; got {shp}")
             bpp = 1
         elif nel == dim:
             bpp = 0
@@ -205,8 +236,12 @@ class Engine:
         """Float32 samples on a Float32 grid (ib200_sampled_f32); host arrays column-major float32 or torch float32 tensors."""
         if not hasattr(y, "data_ptr"):
             y = np.asarray(y, dtype=np.float32, order="F")
+        else:
+            _dev_check(y, "float32", "y")
         if x is not None and not hasattr(x, "data_ptr"):
             x = np.ascontiguousarray(x, dtype=np.float32)
+        elif x is not None:
+            _dev_check(x, "float32", "x")
         out = self._out(out, max(inner * outer, 1), np.float32)
         yp, _k1 = _ptr(y); xp, _k2 = _ptr(x); op, _k3 = _ptr(out)
         self._check(self.L.ib200_sampled_f32(self.h, RULE_IDS[rule] if isinstance(rule, str) else rule, yp, inner, n, outer,
@@ -297,7 +332,8 @@ class Engine:
         return out_I, out_E, out_nevals, out_status
 
     def hcubature_batch(self, family, dim, lb, ub, params, reltol=1e-8, abstol=1e-8, maxevals=MAXEVALS_UNBOUNDED,
-                        initdiv=1, transform=0, out_I=None, out_E=None, out_nevals=None, out_status=None):
+                        initdiv=1, transform=0, out_I=None, out_E=None, out_nevals=None, out_status=None, mode=0):
+        """mode: 0 / "reference_order" (one box per step, the reference's sequence) or 1 / "rounds" (csrc/hcubature_rb.cuh, 2 <= dim <= 5)"""
         lb = _f64(lb); ub = _f64(ub); params = _f64(params)
         params, nparam, nprob, bpp = self._batch_shapes(params, lb, ub, dim)
         out_I = self._out(out_I, nprob); out_E = self._out(out_E, nprob)
@@ -305,7 +341,7 @@ class Engine:
         a = [_ptr(v) for v in (lb, ub, params, out_I, out_E, out_nevals, out_status)]
         self._check(self.L.ib200_hcubature_batch(self.h, family, dim, transform, a[0][0], a[1][0], bpp, a[2][0], nparam,
                                                  nprob, float(reltol), float(abstol),
-                                                 int(min(maxevals, MAXEVALS_UNBOUNDED)), int(initdiv),
+                                                 int(min(maxevals, MAXEVALS_UNBOUNDED)), int(initdiv), HCUB_MODES[mode],
                                                  a[3][0], a[4][0], a[5][0], a[6][0]))
         return out_I, out_E, out_nevals, out_status
 

@@ -1,6 +1,7 @@
 // hcubature.cu -- C entry point of the batched adaptive cubature (kernels: hcubature_impl.cuh)
 #include "hcubature_impl.cuh"
 #include "hcubature_pair.cuh"
+#include "hcubature_rb.cuh"
 
 namespace hc {
 template <> int32_t launch<1>(ib200_ctx *, int, bool, Params &);
@@ -13,6 +14,13 @@ template <> int32_t launch<7>(ib200_ctx *, int, bool, Params &);
 template <> int32_t launch<8>(ib200_ctx *, int, bool, Params &);
 }
 namespace hp {
+template <> int32_t launch<2>(ib200_ctx *, int, bool, Params &);
+template <> int32_t launch<3>(ib200_ctx *, int, bool, Params &);
+template <> int32_t launch<4>(ib200_ctx *, int, bool, Params &);
+template <> int32_t launch<5>(ib200_ctx *, int, bool, Params &);
+}
+
+namespace hb {
 template <> int32_t launch<2>(ib200_ctx *, int, bool, Params &);
 template <> int32_t launch<3>(ib200_ctx *, int, bool, Params &);
 template <> int32_t launch<4>(ib200_ctx *, int, bool, Params &);
@@ -46,9 +54,11 @@ __global__ void lpt_scatter_kernel(const double *I, const double *E, const int32
 extern "C" int32_t ib200_hcubature_batch(ib200_ctx *ctx, int32_t family, int32_t dim, int32_t transform,
                                          const double *lb, const double *ub, int32_t bpp,
                                          const double *params, int32_t nparam, int64_t nprob,
-                                         double reltol, double abstol, int64_t maxevals, int32_t initdiv,
+                                         double reltol, double abstol, int64_t maxevals, int32_t initdiv, int32_t mode,
                                          double *out_I, double *out_E, int64_t *out_nevals, int32_t *out_status) {
     IB_REQUIRE(ctx, ctx != nullptr, "ib200_hcubature_batch: ctx is NULL");
+    IB_REQUIRE(ctx, mode == IB200_HCUB_REFERENCE_ORDER || mode == IB200_HCUB_ROUNDS, "ib200_hcubature_batch: mode must be 0 (reference order) or 1 (rounds)");
+    IB_REQUIRE(ctx, mode != IB200_HCUB_ROUNDS || (dim >= 2 && dim <= 5), "ib200_hcubature_batch: the round-based mode is built for 2 <= dim <= 5 (use mode 0)");
     IB_REQUIRE(ctx, family >= 0 && family < IB200_FAM_COUNT, "ib200_hcubature_batch: unknown integrand family");
     IB_REQUIRE(ctx, transform >= 0 && transform <= 2, "ib200_hcubature_batch: unknown transform id");
     IB_REQUIRE(ctx, ib::fam_dim_ok(family, dim), "ib200_hcubature_batch: dimension not supported for this family");
@@ -93,6 +103,37 @@ extern "C" int32_t ib200_hcubature_batch(ib200_ctx *ctx, int32_t family, int32_t
     unsigned long long *counter = (unsigned long long *)ctx->get(SL_WORK1, sizeof(unsigned long long));
     if (!counter) return ib200_fail(ctx, IB200_ERR_OOM, "ib200_hcubature_batch: scratch allocation failed");
     IB_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), ctx->stream));
+
+    if (mode == IB200_HCUB_ROUNDS) {
+        // round-based driver (hcubature_rb.cuh): budget in rule applications; a round bisects at least every box within a
+        // factor two of the worst, so the last round may overshoot the budget -- the arena holds that slack
+        hb::Params q;
+        q.params = dpar.d; q.nparam = nparam; q.nprob = nprob; q.lb = dlb.d; q.ub = dub.d; q.bpp = bpp; q.tr = transform;
+        q.rtol = reltol; q.atol = abstol; q.initdiv = initdiv; q.frac = ctx->opt_single_round_fraction;
+        q.max_apps = maxevals < ((int64_t)1 << 60) ? (maxevals + np - 1) / np : ((int64_t)1 << 60);
+        int64_t rcap = ctx->opt_hcub_capacity > 0 ? ctx->opt_hcub_capacity : 262144;
+        if (q.max_apps < ((int64_t)1 << 40)) {
+            const int64_t want = init_boxes + q.max_apps / 2 + q.max_apps / 8 + 1024;
+            if (want < rcap) rcap = want;
+        }
+        if (rcap < init_boxes + 64) rcap = init_boxes + 64;
+        q.cap = (int)((rcap + 127) / 128 * 128);
+        q.bounds = q.ival = q.err = nullptr; q.kdiv = nullptr; q.list = nullptr; q.counter = counter;
+        q.out_I = oI.d; q.out_E = oE.d; q.out_nevals = oN.d; q.out_status = oS.d;
+        ctx->err.clear();
+        ib200_time_begin(ctx);
+        switch (dim) {
+        case 2: rc = hb::launch<2>(ctx, family, allfin, q); break;
+        case 3: rc = hb::launch<3>(ctx, family, allfin, q); break;
+        case 4: rc = hb::launch<4>(ctx, family, allfin, q); break;
+        default: rc = hb::launch<5>(ctx, family, allfin, q); break;
+        }
+        if (rc) return rc;
+        ib200_time_end(ctx);
+        if ((rc = oI.finish(ctx)) || (rc = oE.finish(ctx)) || (rc = oN.finish(ctx)) || (rc = oS.finish(ctx))) return rc;
+        if (oI.is_host() || oE.is_host() || oN.is_host() || oS.is_host()) IB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return IB200_OK;
+    }
 
     hc::Params p;
     p.params = dpar.d; p.nparam = nparam; p.nprob = nprob; p.lb = dlb.d; p.ub = dub.d; p.bpp = bpp; p.tr = transform;

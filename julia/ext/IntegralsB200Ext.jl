@@ -21,6 +21,17 @@ check(ctx, rc) = rc == 0 ? nothing :
     (msg = unsafe_string(ccall((:ib200_last_error, lib), Cstring, (Ptr{Cvoid},), ctx.h));
      rc == -1 ? throw(ArgumentError(msg)) : error(msg))
 
+# per-problem status -> retcode.  The reference always reports Success (src/Integrals.jl:338,396) because QuadGK / HCubature only
+# return once the tolerance or the caller's maxiters is met.  The engine can also stop because its box / segment store is full;
+# that is NOT a successful solve under the reference's contract, so it is reported as MaxIters.  A non-finite estimate throws
+# like QuadGK's DomainError for the 1-D solver and is returned as it is for HCubature (which stops and returns, too).
+function retcode_of(alg, st::AbstractVector{Int32}, ne::AbstractVector{Int64}, maxiters; slack = 0)
+    alg isa QuadGKB200 && any(==(Int32(2)), st) &&
+        throw(DomainError(findfirst(==(Int32(2)), st), "integrand produced a non-finite value (problem index given)"))
+    capacity = any(i -> st[i] == 1 && ne[i] + slack < maxiters, eachindex(st))      # slack: budgets counted in whole rule applications
+    return capacity ? ReturnCode.MaxIters : ReturnCode.Success
+end
+
 transform_id(::typeof(transformation_if_inf)) = Int32(0)
 transform_id(::typeof(transformation_tan_inf)) = Int32(1)
 transform_id(::typeof(transformation_cot_inf)) = Int32(2)
@@ -64,7 +75,7 @@ function Integrals.__solvebp_call(cache::IntegralCache, alg::QuadGKB200, senseal
     end
     prob = Integrals.build_problem(cache)
     u, r = p isa AbstractMatrix ? (I, E) : (I[1], E[1])
-    SciMLBase.build_solution(prob, alg, u, r, retcode = ReturnCode.Success)     # like src/Integrals.jl:338
+    SciMLBase.build_solution(prob, alg, u, r, retcode = retcode_of(alg, st, ne, maxiters))     # Success like src/Integrals.jl:338
 end
 
 function Integrals.__solvebp_call(cache::IntegralCache, alg::HCubatureB200, sensealg, domain, p;
@@ -76,14 +87,15 @@ function Integrals.__solvebp_call(cache::IntegralCache, alg::HCubatureB200, sens
     P = _mat(p); nprob = size(P, 2)
     I = Vector{Float64}(undef, nprob); E = similar(I); ne = Vector{Int64}(undef, nprob); st = Vector{Int32}(undef, nprob)
     ctx = cache.cacheval
+    rounds = alg.refinement === :rounds || (alg.refinement === :auto && 2 <= dim <= 5)      # IB200_HCUB_ROUNDS is built for 2 <= dim <= 5
     GC.@preserve lb ub P I E ne st check(ctx, ccall((:ib200_hcubature_batch, lib), Int32,
-        (Ptr{Cvoid}, Int32, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Int32, Ptr{Float64}, Int32, Int64, Float64, Float64, Int64, Int32,
+        (Ptr{Cvoid}, Int32, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Int32, Ptr{Float64}, Int32, Int64, Float64, Float64, Int64, Int32, Int32,
          Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int32}),
         ctx.h, family_id(cache.f.f), dim, transform, lb, ub, bpp, P, size(P, 1), nprob, reltol, abstol, min(maxiters, 2^62),
-        alg.initdiv, I, E, ne, st))
+        alg.initdiv, rounds ? 1 : 0, I, E, ne, st))
     prob = Integrals.build_problem(cache)
     u, r = p isa AbstractMatrix ? (I, E) : (I[1], E[1])
-    SciMLBase.build_solution(prob, alg, u, r, retcode = ReturnCode.Success)     # like src/Integrals.jl:396
+    SciMLBase.build_solution(prob, alg, u, r, retcode = retcode_of(alg, st, ne, maxiters))     # Success like src/Integrals.jl:396
 end
 
 # vector-valued integrands (VectorOf): p :: nparam x ncomp (one problem) or nparam x ncomp x nprob; the components share the nodes and
@@ -107,7 +119,7 @@ function solve_vector(cache::IntegralCache, alg::Union{QuadGKB200, HCubatureB200
             I, E, ne, st))
     end
     u, r = p isa AbstractMatrix ? (I[:, 1], E[1]) : (I, E)
-    SciMLBase.build_solution(Integrals.build_problem(cache), alg, u, r, retcode = ReturnCode.Success)
+    SciMLBase.build_solution(Integrals.build_problem(cache), alg, u, r, retcode = retcode_of(alg, st, ne, maxiters))
 end
 
 # BatchIntegralFunction (src/Integrals.jl:274-315): ANY Julia closure f(pts, p) -> values, evaluated by Julia on the batches of
@@ -135,7 +147,8 @@ function solve_batchfn(cache::IntegralCache, alg::Union{QuadGKB200, HCubatureB20
     end
     I = Ref(0.0); E = Ref(0.0); stats = zeros(Int64, 6)
     GC.@preserve stats check(ctx, ccall((:ib200_batch_result, lib), Int32, (Ptr{Cvoid}, Ref{Float64}, Ref{Float64}, Ptr{Int64}), ctx.h, I, E, stats))
-    SciMLBase.build_solution(Integrals.build_problem(cache), alg, I[], E[], retcode = ReturnCode.Success)
+    SciMLBase.build_solution(Integrals.build_problem(cache), alg, I[], E[],
+                             retcode = retcode_of(alg, Int32[stats[5]], Int64[stats[1]], maxiters; slack = 2npts))
 end
 # (device y must be complete -- CUDA.synchronize() -- before ib200_batch_values; f.max_batch: split the round's points into views of at most
 #  max_batch columns and call f on each, as the Python mirror does -- the engine does not care how y was produced)
@@ -151,7 +164,8 @@ function solve_single(cache::IntegralCache, alg::HCubatureB200, domain, p; trans
         (Ptr{Cvoid}, Int32, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Float64, Float64, Int64, Int64,
          Ref{Float64}, Ref{Float64}, Ptr{Int64}),
         ctx.h, family_id(cache.f.f), dim, transform, lb, ub, P, length(P), reltol, abstol, max(1, min(maxiters, 2^62) ÷ npts), 0, I, E, stats))
-    SciMLBase.build_solution(Integrals.build_problem(cache), alg, I[], E[], retcode = ReturnCode.Success)
+    SciMLBase.build_solution(Integrals.build_problem(cache), alg, I[], E[],
+                             retcode = retcode_of(alg, Int32[stats[5]], Int64[stats[1]], maxiters; slack = 2npts))
 end
 
 function Integrals.__solvebp_call(cache::IntegralCache, alg::QuadratureRuleB200, sensealg, domain, p;
@@ -174,16 +188,48 @@ function Integrals.__solvebp_call(cache::IntegralCache, alg::QuadratureRuleB200,
     SciMLBase.build_solution(Integrals.build_problem(cache), alg, p isa AbstractMatrix ? I : I[1], nothing, retcode = ReturnCode.Success)
 end
 
-# sampled: y is a Julia Array (column-major) or a CuArray; x::AbstractRange selects the uniform weights
+# sampled (src/sampled.jl:127-168).  `init` calls init_cacheval(alg, prob) = find_weights(prob.x, alg) (src/sampled.jl:128-133) and
+# __solvebp_call recomputes cache.cacheval = find_weights(cache.x, alg) when the grid was replaced (cache.isfresh, src/common.jl:276-281).
+# The engine forms the weights on the device from the grid (uniform: from (n, h) alone), so the "weights" object of the B200 rules is
+# the handle of that grid: the context + the step of an AbstractRange, or a Float64 copy of the points that stays rooted here.
+struct B200SampledWeights
+    ctx::B200Context
+    h::Float64                 # step(x) for an AbstractRange (uniform weights, src/trapezoidal.jl:43, src/simpsons.jl:85)
+    xs::Vector{Float64}        # the grid points otherwise (empty for a range)
+end
+const default_ctx = Ref{Union{Nothing, B200Context}}(nothing)
+default_context() = (default_ctx[] === nothing && (default_ctx[] = B200Context()); default_ctx[]::B200Context)
+function Integrals.find_weights(x::AbstractVector, alg::Union{TrapezoidalB200, SimpsonsB200})
+    alg isa SimpsonsB200 && !(x isa AbstractRange) && length(x) <= 2 &&
+        throw(ArgumentError("The length of the grid must exceed 2 for simpsons rule."))          # src/simpsons.jl:46
+    x isa AbstractRange && return B200SampledWeights(default_context(), Float64(step(x)), Float64[])
+    return B200SampledWeights(default_context(), 0.0, collect(Float64, x))
+end
+# host Array: its own pointer.  Device arrays are passed by address too (the C ABI resolves host / device per pointer); CUDA.jl's
+# pointer(::CuArray) is a CuPtr, converted through its integer value.  CUDA.jl runs on per-task streams, so the engine joins the
+# caller's stream first (ib200_set_stream) -- see IntegralsB200CUDAExt below; without it only host arrays are accepted.
+dataptr(a::Array{Float64}) = pointer(a)
+dataptr(a) = throw(ArgumentError("TrapezoidalB200 / SimpsonsB200: y must be an Array{Float64} (or a CuArray{Float64} with CUDA.jl loaded); got $(typeof(a))"))
+join_stream(ctx, a) = nothing
 function Integrals.__solvebp_call(cache::SampledIntegralCache, alg::Union{TrapezoidalB200, SimpsonsB200}; kwargs...)
-    y, x, dim = cache.y, cache.x, Integrals.dimension(cache.dim)
-    inner = prod(size(y)[1:(dim - 1)]); n = size(y, dim); outer = prod(size(y)[(dim + 1):end])
+    if cache.isfresh                                                   # like src/sampled.jl:144-151
+        cache.cacheval = Integrals.find_weights(cache.x, alg)
+        cache.isfresh = false
+    end
+    w = cache.cacheval::B200SampledWeights
+    y, dim = cache.y, Integrals.dimension(cache.dim)
+    n = size(y, dim)
+    n == 0 && error("No points to integrate")                          # src/sampled.jl:55
+    inner = prod(size(y)[1:(dim - 1)]); outer = prod(size(y)[(dim + 1):end])
     out = similar(y, Float64, (size(y)[1:(dim - 1)]..., size(y)[(dim + 1):end]...))
-    h, xs = x isa AbstractRange ? (Float64(step(x)), Ptr{Float64}(C_NULL)) : (0.0, pointer(collect(Float64, x)))
-    ctx = cache.cacheval === nothing ? B200Context() : cache.cacheval
-    GC.@preserve y out x check(ctx, ccall((:ib200_sampled, lib), Int32,
+    xs = w.xs                                                          # a local binding: rooted by GC.@preserve for the whole ccall
+    xp = isempty(xs) ? Ptr{Float64}(C_NULL) : pointer(xs)
+    join_stream(w.ctx, y)
+    GC.@preserve y out xs check(w.ctx, ccall((:ib200_sampled, lib), Int32,
         (Ptr{Cvoid}, Int32, Ptr{Float64}, Int64, Int64, Int64, Float64, Ptr{Float64}, Ptr{Float64}),
-        ctx.h, alg isa SimpsonsB200 ? 1 : 0, pointer(y), inner, n, outer, h, xs, pointer(out)))
-    SciMLBase.build_solution(cache.prob, alg, out, nothing, retcode = ReturnCode.Success)   # like src/sampled.jl:166-167
+        w.ctx.h, alg isa SimpsonsB200 ? 1 : 0, dataptr(y), inner, n, outer, w.h, xp, dataptr(out)))
+    check(w.ctx, ccall((:ib200_synchronize, lib), Int32, (Ptr{Cvoid},), w.ctx.h))     # device outputs are asynchronous on the engine's stream
+    I = ndims(out) == 0 ? out[] : out
+    SciMLBase.build_solution(Integrals.build_problem(cache), alg, I, nothing, retcode = ReturnCode.Success)   # src/sampled.jl:166-167, src/common.jl:412
 end
 end # module

@@ -1269,26 +1269,14 @@ int orc_hcubature_vec_batch(int fam, int dim, const double *lb, const double *ub
  * before dealing sub-boxes to the ranks.  max_boxes: budget of rule applications.
  * ------------------------------------------------------------------------------------------ */
 double orc_round_fraction = 0.5;
-int orc_hcubature_rounds(orc_integrand f, void *user, int dim, const double *a, const double *b,
-                         double rtol, double atol, int64_t max_boxes, int m0,
-                         double *Iout, double *Eout, int64_t *napplied_out, int64_t *nboxes_out, int64_t *rounds_out)
+/* the rounds themselves, from a store of `len` unevaluated boxes (all of them in the todo list) */
+static int hcub_rounds_core(orc_integrand f, void *user, int dim, orc_box *t, int64_t cap, int64_t len,
+                            double rtol, double atol, int64_t max_boxes, int first_box_only,
+                            double *Iout, double *Eout, int64_t *napplied_out, int64_t *nboxes_out, int64_t *rounds_out)
 {
-    if (dim < 1 || dim > ORC_MAXDIM || rtol < 0 || atol < 0 || max_boxes < 1 || m0 < 0 || m0 > 30) return -1;
-    if (rtol == 0 && atol == 0) rtol = sqrt(2.220446049250313e-16);
-    int64_t cap = (1LL << m0) + 1024, len = 0, ntodo = 0, applied = 0, rounds = 0;
-    orc_box *t = (orc_box *)malloc(sizeof(orc_box) * (size_t)cap);
+    int64_t ntodo = 0, applied = 0, rounds = 0;
     int64_t *todo = (int64_t *)malloc(sizeof(int64_t) * (size_t)cap);
-    for (int64_t q = 0; q < (1LL << m0); q++) {
-        orc_box bx;
-        for (int i = 0; i < dim; i++) { bx.a[i] = a[i]; bx.b[i] = b[i]; }
-        for (int lev = 0; lev < m0; lev++) {
-            int k = lev % dim;
-            double w = (bx.b[k] - bx.a[k]) * 0.5;
-            if ((q >> lev) & 1) bx.a[k] = bx.a[k] + w; else bx.b[k] = bx.b[k] - w;
-        }
-        bx.I = 0.0; bx.E = 0.0; bx.kdiv = 0;
-        t[len] = bx; todo[ntodo++] = len; len++;
-    }
+    for (int64_t q = 0; q < len; q++) todo[ntodo++] = q;
     double I = 0.0, E = 0.0, theta = 0.0;
     int status = 0;
     for (;;) {
@@ -1299,6 +1287,7 @@ int orc_hcubature_rounds(orc_integrand f, void *user, int dim, const double *a, 
             I += bx->I; E += bx->E; if (bx->E > mx) mx = bx->E;
         }
         applied += ntodo; rounds++; ntodo = 0;
+        if (first_box_only) break;                       /* degenerate domain: HCubature returns after the first box */
         if (E <= fmax(rtol * fabs(I), atol)) break;
         if (!isfinite(E)) { status = 2; break; }
         if (applied >= max_boxes) { status = 1; break; }
@@ -1353,6 +1342,65 @@ int orc_hcubature_rounds(orc_integrand f, void *user, int dim, const double *a, 
     if (nboxes_out) *nboxes_out = len;
     if (rounds_out) *rounds_out = rounds;
     return status;
+}
+
+int orc_hcubature_rounds(orc_integrand f, void *user, int dim, const double *a, const double *b,
+                         double rtol, double atol, int64_t max_boxes, int m0,
+                         double *Iout, double *Eout, int64_t *napplied_out, int64_t *nboxes_out, int64_t *rounds_out)
+{
+    if (dim < 1 || dim > ORC_MAXDIM || rtol < 0 || atol < 0 || max_boxes < 1 || m0 < 0 || m0 > 30) return -1;
+    if (rtol == 0 && atol == 0) rtol = sqrt(2.220446049250313e-16);
+    int64_t cap = (1LL << m0) + 1024, len = 0;
+    orc_box *t = (orc_box *)malloc(sizeof(orc_box) * (size_t)cap);
+    for (int64_t q = 0; q < (1LL << m0); q++) {
+        orc_box bx;
+        for (int i = 0; i < dim; i++) { bx.a[i] = a[i]; bx.b[i] = b[i]; }
+        for (int lev = 0; lev < m0; lev++) {
+            int k = lev % dim;
+            double w = (bx.b[k] - bx.a[k]) * 0.5;
+            if ((q >> lev) & 1) bx.a[k] = bx.a[k] + w; else bx.b[k] = bx.b[k] - w;
+        }
+        bx.I = 0.0; bx.E = 0.0; bx.kdiv = 0;
+        t[len++] = bx;
+    }
+    return hcub_rounds_core(f, user, dim, t, cap, len, rtol, atol, max_boxes, 0, Iout, Eout, napplied_out, nboxes_out, rounds_out);
+}
+
+/* The same rounds as HCubature.hcubature's drop-in for a BATCH (checker of ib200_hcubature_batch, mode IB200_HCUB_ROUNDS,
+ * csrc/hcubature_rb.cuh): the initial store is HCubature's initdiv grid (CartesianIndices order, first index fastest, the
+ * box bounds of orc_hcubature), a degenerate domain returns after the first box, and maxevals is honoured as a budget of
+ * ceil(maxevals / points per rule) rule applications.  nevals = rule applications * points per rule. */
+int orc_hcubature_rounds_init(orc_integrand f, void *user, int dim, const double *a, const double *b,
+                              double rtol, double atol, int64_t maxevals, int initdiv,
+                              double *Iout, double *Eout, int64_t *nevals_out, int64_t *nboxes_out, int64_t *rounds_out)
+{
+    if (dim < 1 || dim > ORC_MAXDIM || initdiv < 1 || rtol < 0 || atol < 0 || maxevals < 0) return -1;
+    if (rtol == 0 && atol == 0) rtol = sqrt(2.220446049250313e-16);
+    const int64_t np = dim == 1 ? 15 : 1 + 4 * dim + 2 * dim * (dim - 1) + (1 << dim);
+    const int64_t max_apps = maxevals < (1LL << 60) ? (maxevals + np - 1) / np : (1LL << 60);
+    double Delta[ORC_MAXDIM], prodD = 1.0;
+    int64_t total = 1;
+    for (int i = 0; i < dim; i++) { Delta[i] = (b[i] - a[i]) / initdiv; prodD *= Delta[i]; total *= initdiv; }
+    const int degenerate = (prodD == 0.0);
+    if (degenerate) total = 1;
+    int64_t cap = total + 1024, len = 0;
+    orc_box *t = (orc_box *)malloc(sizeof(orc_box) * (size_t)cap);
+    int c[ORC_MAXDIM] = {0};
+    for (int64_t q = 0; q < total; q++) {
+        orc_box bx;
+        for (int i = 0; i < dim; i++) {
+            bx.a[i] = a[i] + c[i] * Delta[i];
+            bx.b[i] = (c[i] == initdiv - 1) ? b[i] : bx.a[i] + Delta[i];
+        }
+        bx.I = 0.0; bx.E = 0.0; bx.kdiv = 0;
+        t[len++] = bx;
+        int k = 0;
+        while (k < dim && ++c[k] == initdiv) { c[k] = 0; k++; }
+    }
+    int64_t applied = 0;
+    int st = hcub_rounds_core(f, user, dim, t, cap, len, rtol, atol, max_apps, degenerate, Iout, Eout, &applied, nboxes_out, rounds_out);
+    if (nevals_out) *nevals_out = applied * np;
+    return st;
 }
 
 int orc_solve_hcubature_rounds(orc_integrand f, void *user, int dim, const double *lb, const double *ub, int tr,
@@ -1476,6 +1524,29 @@ int orc_hcubature_batch(int fam, int dim, const double *lb, const double *ub, in
         int st = orc_solve_hcubature(orc_family_integrand, &fu, dim, l, u, tr, reltol, abstol, maxiters, initdiv, &I[k], &E[k], &ne);
         if (nevals) nevals[k] = ne;
         if (status) status[k] = st;
+    }
+    return 0;
+}
+
+int orc_hcubature_rounds_batch(int fam, int dim, const double *lb, const double *ub, int bpp, int tr,
+                               const double *params, int nparam, int64_t nprob,
+                               double reltol, double abstol, int64_t maxiters, int initdiv,
+                               double *I, double *E, int64_t *nevals, int32_t *status, int64_t *rounds, int nthreads)
+{
+    if (orc_family_nparam(fam, dim) != nparam) return -1;
+    if (nthreads < 1) nthreads = 1;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+    for (int64_t k = 0; k < nprob; k++) {
+        orc_family_user fu = {fam, dim, params + k * nparam};
+        const double *l = bpp ? lb + k * dim : lb, *u = bpp ? ub + k * dim : ub;
+        orc_cov c = {orc_family_integrand, &fu, dim, tr, l, u};
+        double tl[ORC_MAXDIM], tu[ORC_MAXDIM];
+        for (int i = 0; i < dim; i++) orc_u2t(l[i], u[i], &tl[i], &tu[i]);
+        int64_t ne = 0, nr = 0;
+        int st = orc_hcubature_rounds_init(orc_cov_eval, &c, dim, tl, tu, reltol, abstol, maxiters, initdiv, &I[k], &E[k], &ne, NULL, &nr);
+        if (nevals) nevals[k] = ne;
+        if (status) status[k] = st;
+        if (rounds) rounds[k] = nr;
     }
     return 0;
 }

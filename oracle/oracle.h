@@ -139,6 +139,11 @@ int orc_hcubature_rounds(orc_integrand f, void *user, int dim, const double *a, 
 int orc_solve_hcubature_rounds(orc_integrand f, void *user, int dim, const double *lb, const double *ub, int tr,
                                double reltol, double abstol, int64_t max_boxes, int m0,
                                double *I, double *E, int64_t *napplied, int64_t *nboxes, int64_t *rounds);
+/* the same rounds started from HCubature's initdiv grid with the budget given in evaluations (checker for
+   ib200_hcubature_batch, mode IB200_HCUB_ROUNDS; csrc/hcubature_rb.cuh) */
+int orc_hcubature_rounds_init(orc_integrand f, void *user, int dim, const double *a, const double *b,
+                              double rtol, double atol, int64_t maxevals, int initdiv,
+                              double *I, double *E, int64_t *nevals, int64_t *nboxes, int64_t *rounds);
 int orc_hcubature_rounds_family(int fam, int dim, const double *lb, const double *ub, int tr, const double *params,
                                 double reltol, double abstol, int64_t max_boxes, int m0,
                                 double *I, double *E, int64_t *napplied, int64_t *nboxes, int64_t *rounds);
@@ -170,6 +175,10 @@ int orc_hcubature_batch(int fam, int dim, const double *lb, const double *ub, in
                         const double *params, int nparam, int64_t nprob,
                         double reltol, double abstol, int64_t maxiters, int initdiv,
                         double *I, double *E, int64_t *nevals, int32_t *status, int nthreads);
+int orc_hcubature_rounds_batch(int fam, int dim, const double *lb, const double *ub, int bounds_per_problem, int tr,
+                               const double *params, int nparam, int64_t nprob,
+                               double reltol, double abstol, int64_t maxiters, int initdiv,
+                               double *I, double *E, int64_t *nevals, int32_t *status, int64_t *rounds, int nthreads);
 int orc_fixed_tensor_batch(int fam, int dim, const double *lb, const double *ub, int bounds_per_problem, int tr,
                            const double *params, int nparam, int64_t nprob,
                            const double *x1d, const double *w1d, int n1d, double *I, int nthreads);

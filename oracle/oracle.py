@@ -321,6 +321,22 @@ def hcubature_batch(fam, lb, ub, params, tr="if_inf", reltol=1e-8, abstol=1e-8, 
     return I, E, ne, st
 
 
+def hcubature_rounds_batch(fam, lb, ub, params, tr="if_inf", reltol=1e-8, abstol=1e-8, maxiters=2**62, initdiv=1, nthreads=1, fraction=0.5):
+    """Round-based refinement of a batch (checker of Engine.hcubature_batch(mode="rounds")) -> I, E, nevals, status, rounds"""
+    lb = np.asarray(lb, dtype=np.float64); dim = lb.shape[0]
+    fam, params, nparam, nprob, lb, ub, bpp = _batch_common(fam, dim, lb, ub, params)
+    I = np.empty(nprob); E = np.empty(nprob); ne = np.empty(nprob, np.int64); st = np.empty(nprob, np.int32); nr = np.empty(nprob, np.int64)
+    L = lib()
+    L.orc_hcubature_rounds_batch.argtypes = [C.c_int, C.c_int, _dp, _dp, C.c_int, C.c_int, _dp, C.c_int, C.c_int64, C.c_double, C.c_double,
+                                             C.c_int64, C.c_int, _dp, _dp, _i64p, _i32p, _i64p, C.c_int]
+    C.c_double.in_dll(L, "orc_round_fraction").value = fraction
+    rc = L.orc_hcubature_rounds_batch(fam, dim, _p(lb), _p(ub), bpp, TR[tr], params.ctypes.data_as(_dp), nparam, nprob,
+                                      reltol, abstol, min(maxiters, 2**62), initdiv, _p(I), _p(E), ne.ctypes.data_as(_i64p),
+                                      st.ctypes.data_as(_i32p), nr.ctypes.data_as(_i64p), nthreads)
+    assert rc == 0, rc
+    return I, E, ne, st, nr
+
+
 def hcubature_vec_batch(fam, lb, ub, params, tr="if_inf", reltol=1e-8, abstol=1e-8, maxiters=2**62, initdiv=1, norm="2", nthreads=1):
     """vector-valued HCubature: params nparam x ncomp x nprob (Fortran order); lb, ub of length dim (or dim x nprob)
     -> I (ncomp x nprob), E, nevals, status"""

@@ -17,7 +17,7 @@ for rep in range(reps):
         fam, nprob = sys.argv[2], int(sys.argv[3]); d = int(sys.argv[4]) if len(sys.argv) > 4 else 4
         par = torch.from_numpy(np.ascontiguousarray(WL.genz_params(fam, d, nprob).T)).cuda()
         oI = torch.empty(nprob, dtype=torch.float64, device="cuda")
-        eng.hcubature_batch(F[fam], d, np.zeros(d), np.ones(d), par, reltol=1e-6, abstol=1e-8, maxevals=MAXEV, out_I=oI,
+        eng.hcubature_batch(F[fam], d, np.zeros(d), np.ones(d), par, reltol=1e-6, abstol=1e-8, maxevals=MAXEV, out_I=oI, mode=int(os.environ.get("PK_MODE", "0")),
                             out_E=torch.empty_like(oI), out_nevals=torch.empty(nprob, dtype=torch.int64, device="cuda"),
                             out_status=torch.empty(nprob, dtype=torch.int32, device="cuda"))
     elif kind == "quadgk":

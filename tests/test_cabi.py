@@ -172,3 +172,56 @@ def test_julia_binding_files_match_the_document():
         assert got == kinds[name], (name, got, kinds[name])       # pointers, integers and floats at the same positions
         seen += 1
     assert seen >= 10
+
+
+REFERENCE = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "src")), reason="the reference tree is only present in the build container")
+def test_julia_extension_uses_only_names_the_reference_defines():
+    """grep-level check of the Julia extension against /root/reference/src: every `Integrals.<name>` it extends or calls is defined there,
+    every field it reads off IntegralCache / SampledIntegralCache / the problem types exists in that struct, the sampled algorithms get a
+    find_weights method (src/sampled.jl:128-133 calls it inside init) and the solution is built from build_problem(cache)
+    (SampledIntegralCache has no `prob` field, src/common.jl:264-274)."""
+    src = ""
+    for dp, _, fs in os.walk(os.path.join(REFERENCE, "src")):
+        for f in fs:
+            if f.endswith(".jl"):
+                src += open(os.path.join(dp, f)).read() + "\n"
+    jl = open(os.path.join(ROOT, "julia", "ext", "IntegralsB200Ext.jl")).read()
+    code = "\n".join(line.split(" #")[0] for line in jl.splitlines() if not line.lstrip().startswith("#"))
+    # functions of the reference the extension extends / calls
+    for name in sorted(set(re.findall(r"\bIntegrals\.(\w+)", code))):
+        assert re.search(r"\bfunction\s+" + name + r"\b|^\s*" + name + r"\(.*\)\s*=", src, flags=re.M) or re.search(r"\b(struct|abstract type)\s+" + name + r"\b", src), name
+    for name in ("init_cacheval", "__solvebp_call", "__solve", "find_weights", "build_problem", "dimension"):
+        assert re.search(r"\bIntegrals\." + name + r"\b", code), f"the extension never touches Integrals.{name}"
+
+    def fields(struct):
+        m = re.search(r"mutable struct " + struct + r"\b[^\n]*\n(.*?)\nend", src, flags=re.S)
+        assert m, struct
+        return set(re.findall(r"^\s*(\w+)::", m.group(1), flags=re.M))
+    sampled_fields, cache_fields = fields("SampledIntegralCache"), fields("IntegralCache")
+    assert {"y", "x", "dim", "isfresh", "cacheval"} <= sampled_fields and "prob" not in sampled_fields
+    # the sampled method only reads fields SampledIntegralCache has
+    m = re.search(r"function Integrals\.__solvebp_call\(cache::SampledIntegralCache.*?\nend\n", code, flags=re.S)
+    assert m
+    used = set(re.findall(r"\bcache\.(\w+)", m.group(0)))
+    assert used and used <= sampled_fields, used - sampled_fields
+    # ... and the IntegralCache methods only fields IntegralCache has
+    rest = code.replace(m.group(0), "")
+    used = set(re.findall(r"\bcache\.(\w+)", rest))
+    assert used and used <= cache_fields, used - cache_fields
+    # the defects of the first version stay fixed: weights through find_weights, solution through build_problem, the grid copy rooted
+    assert "Integrals.find_weights(x::AbstractVector, alg::Union{TrapezoidalB200, SimpsonsB200})" in code
+    assert "cache.prob" not in code and "pointer(collect(" not in code
+    assert re.search(r"GC\.@preserve y out xs", code)
+    # every reference type / function imported by name exists
+    imp = re.search(r"using Integrals:(.*?)\nconst lib", jl, flags=re.S).group(1)
+    new_names = {"AbstractB200Algorithm", "QuadGKB200", "HCubatureB200", "QuadratureRuleB200", "GaussLegendreB200", "TrapezoidalB200",
+                 "SimpsonsB200", "family_id", "VectorOf"}                         # defined by julia/algorithms_b200.jl
+    alg_src = open(os.path.join(ROOT, "julia", "algorithms_b200.jl")).read()
+    for name in [n.strip() for n in imp.replace("\n", " ").split(",") if n.strip()]:
+        if name in new_names:
+            assert re.search(r"\b(struct|abstract type)\s+" + name + r"\b|^" + name + r"\(", alg_src, flags=re.M), name
+        else:
+            assert re.search(r"\b(struct|function|abstract type)\s+" + name + r"\b", src), name

@@ -297,3 +297,37 @@ def test_integrand_markers_evaluate_like_the_oracle_family():
                     p = rng.uniform(0.2, 3.0, f.nparam(dim))
                 got, ref = f(x if dim > 1 else x[0], p), O.family_eval(ORC_FAM[f.name], x, p)
                 assert abs(got - ref) <= 1e-13 * max(1.0, abs(ref)), (f.name, dim, got, ref)
+
+
+def test_retcode_from_engine_status():
+    """status -> retcode: Success like the reference (src/Integrals.jl:338,396) when the tolerance or the caller's maxiters
+    ended the solve; MaxIters when the engine's own box / segment store filled up first; QuadGK's DomainError for a non-finite estimate"""
+    class E(StubEngine):
+        def __init__(self, st, ne):
+            super().__init__(); self.st, self.ne = st, ne
+
+        def quadgk_batch(self, fam, lb, ub, p, **k):
+            n = p.shape[1]
+            return np.zeros(n), np.zeros(n), np.full(n, self.ne, np.int64), np.full(n, self.st, np.int32)
+        hcubature_batch = lambda self, fam, dim, lb, ub, p, **k: self.quadgk_batch(fam, lb, ub, p, **k)
+    prob = ib.IntegralProblem(ib.SinXP(), (-2.0, 5.0), 1.7)
+    assert ib.solve(prob, ib.QuadGKB200(), engine=E(0, 75)).retcode == ib.ReturnCode.Success
+    assert ib.solve(prob, ib.QuadGKB200(), engine=E(1, 1005), maxiters=1000).retcode == ib.ReturnCode.Success      # the caller's budget
+    assert ib.solve(prob, ib.QuadGKB200(), engine=E(1, 250000)).retcode == ib.ReturnCode.MaxIters                  # the engine's capacity
+    assert ib.solve(prob, ib.QuadGKB200(), engine=E(3, 300)).retcode == ib.ReturnCode.Success                      # endpoint round-off: QuadGK returns
+    with pytest.raises(ib.DomainError):
+        ib.solve(prob, ib.QuadGKB200(), engine=E(2, 15))
+    p4 = ib.IntegralProblem(ib.GenzGaussian(), (np.zeros(4), np.ones(4)), np.ones((8, 3)))
+    assert ib.solve(p4, ib.HCubatureB200(), engine=E(2, 57)).retcode == ib.ReturnCode.Success                      # HCubature stops and returns
+    assert ib.solve(p4, ib.HCubatureB200(), engine=E(1, 57 * 1000)).retcode == ib.ReturnCode.MaxIters
+
+
+def test_hcubature_refinement_modes():
+    e = StubEngine()
+    p4 = ib.IntegralProblem(ib.GenzGaussian(), (np.zeros(4), np.ones(4)), np.ones((8, 3)))
+    ib.solve(p4, ib.HCubatureB200(), engine=e); assert e.calls[-1][2]["mode"] == "rounds"
+    ib.solve(p4, ib.HCubatureB200(refinement="reference_order"), engine=e); assert e.calls[-1][2]["mode"] == "reference_order"
+    p6 = ib.IntegralProblem(ib.GenzGaussian(), (np.zeros(6), np.ones(6)), np.ones((12, 3)))
+    ib.solve(p6, ib.HCubatureB200(), engine=e); assert e.calls[-1][2]["mode"] == "reference_order"     # rounds are built for 2 <= dim <= 5
+    with pytest.raises(ValueError):
+        ib.HCubatureB200(refinement="fastest")
