@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--nprob", type=int, default=0, help="override the problems per family/batch (smoke runs only)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the short c1/c2/c3 side measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--hcub-mode", default="rounds", choices=["rounds", "reference_order"],
+                    help="refinement driver of the c4 headline (ib200_hcubature_batch mode): rounds (default) or the reference's one-box-per-step order")
     return ap.parse_args()
 
 
@@ -143,11 +145,20 @@ def cpu_c2_sample(O, WL, n, threads):
     return 2 * (8.0 * m * n + 8 * m) / 1e9, dt        # GB
 
 
-# DRAM traffic per launch (bytes) of the dominant kernels at the default workload sizes, from `ncu --set full` (profiles/README.md)
-NCU_TRAFFIC = {"hp::hcub_pair_kernel<genz_product_peak,4,true>": 4.663001e12 + 1.771830e12}
-# executed FP64-pipe utilisation of the same kernels (sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active of the committed
-# captures): the figure that cannot exceed 1 -- `roofline.frac` counts the NOMINAL operations of SURVEY 8(d), which the kernels undercut
-NCU_FP64_PIPE = {"hp::hcub_pair_kernel<genz_product_peak,4,true>": (0.176, "profiles/r01_hcub_pair_prod_c4_full_summary.txt (before the Terms7 change; steady state after it: 0.202, profiles/r01b_pair_genz_product_peak_steady_full_summary.txt)")}
+def executed_table():
+    """profiles/r02_executed_fp64.json: executed FP64 instructions per integrand evaluation of every hot kernel, from the committed
+    `ncu --set full` captures (scripts/executed_fp64.py).  `roofline.achieved` = these counts x the run's evaluations / kernel time."""
+    path = os.path.join(ROOT, "profiles", "r02_executed_fp64.json")
+    return json.load(open(path)) if os.path.exists(path) else {}
+
+
+def host_cores():
+    """the cores this process may run on (NOT OMP_NUM_THREADS: torchrun exports OMP_NUM_THREADS=1 to every rank)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
 
 FAM_ORC = {"sinxp": "sinxp", "genz_oscillatory": "osc", "genz_product_peak": "prodpeak", "genz_corner_peak": "corner",
            "genz_gaussian": "gauss", "genz_c0": "c0", "genz_discontinuous": "discont"}
@@ -157,7 +168,8 @@ def cpu_leg(workload, scale=1.0):
     """-> (units, seconds, cores, sample description).  Sized for ~10-30 s of CPU work at scale 1."""
     import oracle as O
     import integrals_b200.workloads as WL
-    cores = O.max_threads()
+    O.use_baseline_build()                     # -O3 -march=native build of the same source, compiled on this machine (oracle/Makefile)
+    cores = host_cores()
     if workload == "c4":
         nper = max(8, int(32 * cores * scale))
         units, dt = cpu_c4_sample(O, WL, nper, cores)
@@ -196,11 +208,12 @@ def run_reference(args):
         u, dt, cores, sample = cpu_leg(args.workload, 0.25)
         tot_u += u; tot_t += dt
     v = tot_u / tot_t
+    import oracle as O
     print(json.dumps({"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
                       "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True,
                       "scaling": "strong" if args.workload == "c5" else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                       "config": workload_config(args.workload, args, sample=sample),
-                      "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+                      "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": "port", "sample": sample, "build": O.BASELINE_FLAGS},
                       "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
@@ -276,7 +289,7 @@ def main():
         return float(t.item())
 
     # -------------------------------------------------------------------------------- workloads
-    def make_c4(scale=1.0):
+    def make_c4(scale=1.0, hcub_mode=None):
         c = WL.C4; d = c["dim"]
         nper = args.nprob or c["nprob_per_family"]
         host, dev = {}, {}
@@ -290,12 +303,15 @@ def main():
                             S=torch.empty(nper, dtype=torch.int32, device="cuda"))
         lb, ub = np.zeros(d), np.ones(d)
         kms = {fam: 0.0 for fam in WL.GENZ}
+        mode = hcub_mode or args.hcub_mode
+        kname, kkey = ("hb::hcub_rb_kernel", "hcub_rb") if mode == "rounds" else ("hp::hcub_pair_kernel", "hcub_pair")
+        table = executed_table()
 
         def step(record=False):
             for fam in WL.GENZ:
                 b = dev[fam]
                 eng.hcubature_batch(F[fam], d, lb, ub, b["par"], reltol=c["reltol"], abstol=c["abstol"], maxevals=c["maxiters"],
-                                    initdiv=c["initdiv"], out_I=b["I"], out_E=b["E"], out_nevals=b["N"], out_status=b["S"])
+                                    initdiv=c["initdiv"], out_I=b["I"], out_E=b["E"], out_nevals=b["N"], out_status=b["S"], mode=mode)
                 if record:
                     kms[fam] += eng.last_kernel_ms
 
@@ -303,27 +319,34 @@ def main():
             res = 0.0
             for fam in WL.GENZ:
                 prob = ib.IntegralProblem(getattr(ib, ib_marker[fam])(), (lb, ub), host[fam].numpy().T)
-                sol = ib.solve(prob, ib.HCubatureB200(initdiv=c["initdiv"]), engine=eng, reltol=c["reltol"], abstol=c["abstol"],
+                sol = ib.solve(prob, ib.HCubatureB200(initdiv=c["initdiv"], refinement=mode), engine=eng, reltol=c["reltol"], abstol=c["abstol"],
                                maxiters=c["maxiters"])
                 res += float(sol.u[0])
             return res
 
         def finish(kernel_ms_total):
-            fl = 0.0; ev = 0; per = {}
+            fl = 0.0; ev = 0; per = {}; flx = 0.0; have_all = True
             for fam in WL.GENZ:
                 n_ev = int(dev[fam]["N"].sum().item())
                 ev += n_ev
                 fl += n_ev * WL.hcubature_flops_per_eval(fam, d)
-                per[fam] = {"kernel_ms": kms[fam] / args.steps, "integrals_per_s": nper / (kms[fam] / args.steps * 1e-3),
-                            "mean_evals": n_ev / nper, "frac_maxevals": float((dev[fam]["S"] == 1).double().mean().item())}
+                ex = table.get(f"{kkey}/{fam}/{d}")
+                have_all = have_all and ex is not None
+                flx += n_ev * (ex["flops_per_eval"] if ex else 0.0)
+                ms = kms[fam] / max(args.steps, 1)
+                per[fam] = {"kernel_ms": ms, "integrals_per_s": nper / (ms * 1e-3) if ms else None,
+                            "mean_evals": n_ev / nper, "frac_maxevals": float((dev[fam]["S"] == 1).double().mean().item()),
+                            "gevals_per_s": n_ev / (ms * 1e-3) / 1e9 if ms else None,
+                            "executed_fp64_tflops": n_ev * ex["flops_per_eval"] / (ms * 1e-3) / 1e12 if (ex and ms) else None,
+                            "executed_fp64_inst_per_eval": ex["fp64_inst_per_eval"] if ex else None}
             dom = max(WL.GENZ, key=lambda f: kms[f])
             dom_ev = int(dev[dom]["N"].sum().item())
-            return dict(units=6 * nper, launches=6, flops=fl, evals=ev, per_family=per,
+            return dict(units=6 * nper, launches=6, flops=fl, flops_executed=flx if have_all else None, evals=ev, per_family=per,
                         h2d=6 * nper * 2 * d * 8 + 6 * 2 * d * 8, d2h=6 * nper * (8 + 8 + 8 + 4),
-                        kernel="hp::hcub_pair_kernel<FAM,4,true> (6 launches per step, one per family)",
-                        dominant=dict(kernel=f"hp::hcub_pair_kernel<{dom},4,true>", ms=kms[dom] / args.steps, evals=dom_ev,
+                        kernel=f"{kname}<FAM,4,true> (6 launches per step, one per family)", refinement=mode,
+                        dominant=dict(kernel=f"{kname}<{dom},4,true>", key=f"{kkey}/{dom}/{d}", ms=kms[dom] / max(args.steps, 1), evals=dom_ev,
                                       flops=dom_ev * WL.hcubature_flops_per_eval(dom, d),
-                                      share_of_step=kms[dom] / max(sum(kms.values()), 1e-9),
+                                      share_of_step=kms[dom] / max(sum(kms.values()), 1e-9), nprob=nper,
                                       default_size=(nper == c["nprob_per_family"])))
         return step, e2e_step, finish
 
@@ -374,7 +397,7 @@ def main():
         def finish(kernel_ms_total):
             ev = int(oN.sum().item())
             return dict(units=n, launches=1, flops=ev * WL.quadgk_flops_per_eval(), evals=ev, h2d=n * 8 + 16, d2h=n * 28,
-                        kernel="quadgk_kernel<SINXP,true>")
+                        kernel="quadgk_kernel<SINXP,true>", key=f"quadgk/sinxp/order{order}", nprob=n)
         return step, e2e_step, finish
 
     def make_c3():
@@ -398,7 +421,7 @@ def main():
         def finish(kernel_ms_total):
             ev = n * c["n1d"] ** 3
             return dict(units=n, launches=1, flops=ev * WL.fixed_tensor_flops_per_eval(c["family"], 3), evals=ev,
-                        h2d=n * 6 * 8, d2h=n * 8, kernel="tensor_kernel<GENZ_OSC,3>")
+                        h2d=n * 6 * 8, d2h=n * 8, kernel="tensor_kernel<GENZ_OSC,3>", key="tensor/genz_oscillatory/3", nprob=n)
         return step, e2e_step, finish
 
     def make_c2(nonuniform=False, contiguous=False):
@@ -479,7 +502,7 @@ def main():
             ev = last["nevals"]
             return dict(units=last["rule_applications"], global_units=True, launches=8 * last["rounds"] + 4, evals=ev,
                         flops=ev * (WL.FAMILY_FLOPS["genz_gaussian"](8) + 2 * 20 + 6 * 4 + 2 * 8 + 1 + 30.0 / 401), h2d=8 * 32, d2h=8 * 8,
-                        kernel="hs::eval_kernel<genz_gaussian,8,false> (+ 7 bookkeeping kernels per refinement round)",
+                        kernel="hs::eval_kernel<genz_gaussian,8,false> (+ 7 bookkeeping kernels per refinement round)", key="hs_eval/genz_gaussian/8",
                         result=dict(I=last["I"], E=last["E"], rel_E=last["E"] / abs(last["I"]), true_rel_err=abs(last["I"] - exact) / abs(exact),
                                     rounds=last["rounds"], boxes_stored=last["boxes"], status=last["status"], box_budget=budget))
         return step, e2e_step, finish
@@ -530,13 +553,14 @@ def main():
         return step, step, finish
 
     makers = {"c4": make_c4, "c1": make_c1, "c2": make_c2, "c3": make_c3, "c5": make_c5,
+              "c4_reference_order": lambda: make_c4(hcub_mode="reference_order"),
               # side measurements SURVEY 8(d) asks for next to the configs (reported under "secondary" only)
               "c1_abstol_1e-12": lambda: make_c1(abstol=1e-12), "c2_nonuniform_grid": lambda: make_c2(nonuniform=True),
               "c2_contiguous_axis": lambda: make_c2(contiguous=True), "c4_reduced_difficulty_h/4": lambda: make_c4(scale=0.25),
               # "next" rows of SURVEY 8(f), same measurement as their parent config
               "c1_order_15": lambda: make_c1(order=15), "c1_vector_valued_4": make_c1_vec, "c2_float32": make_c2_f32,
               "hcubature_vector_valued_3d_4": make_c4_vec, "batch_bridge_device_integrand_4d": make_bridge}
-    EXTRA_UNITS = {"c1_abstol_1e-12": "integrals/s", "c2_nonuniform_grid": "GB/s", "c2_contiguous_axis": "GB/s",
+    EXTRA_UNITS = {"c4_reference_order": "integrals/s", "c1_abstol_1e-12": "integrals/s", "c2_nonuniform_grid": "GB/s", "c2_contiguous_axis": "GB/s",
                    "c4_reduced_difficulty_h/4": "integrals/s", "c1_order_15": "integrals/s", "c1_vector_valued_4": "integrals/s",
                    "c2_float32": "GB/s", "hcubature_vector_valued_3d_4": "integrals/s", "batch_bridge_device_integrand_4d": "points/s"}
 
@@ -592,24 +616,43 @@ def main():
         roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6.65 TB/s (of fallback)", "kernel": info["kernel"]}
     else:
-        ach_step = info["flops"] / (r["ms_per_step"] * 1e-3) / 1e12
+        # FP64 roofline from EXECUTED instructions: per-evaluation DFMA/DMUL/DADD counts of the committed ncu capture of
+        # this kernel (profiles/r02_executed_fp64.json) x the evaluations of this run / the kernel's CUDA-event time.  The nominal
+        # (algorithmic) count of SURVEY 8(d) is kept beside it: the kernels execute fewer operations than it assumes.
+        table = executed_table()
         dom = info.get("dominant")
         if dom:                         # the dominant kernel of the step: one launch, CUDA-event timed on the launching stream
-            ach, kname, kev, kms_ = dom["flops"] / (dom["ms"] * 1e-3) / 1e12, dom["kernel"], dom["evals"], dom["ms"]
+            kname, kev, kms_, nom_flops, key = dom["kernel"], dom["evals"], dom["ms"], dom["flops"], dom.get("key")
         else:
-            ach, kname, kev, kms_ = ach_step, info["kernel"], info["evals"], r["ms_per_step"]
-        # DRAM bytes of one launch of that kernel from the committed `ncu --set full` capture (profiles/); only valid at the default size
-        traffic = NCU_TRAFFIC.get(kname) if (dom is None or dom.get("default_size")) else None
-        roof = {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": traffic,
-                "traffic_source": "profiles/r01_hcub_pair_prod_c4_full_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum, one launch)" if traffic else None,
-                "peak_source": "DFMA-chain microbenchmark run live on this GPU (ib200_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
-                "flops_model": "SURVEY 8(d) nominal FP64 operations per integrand evaluation x evaluations (DESIGN.md); the kernels execute fewer "
-                               "(separable-term tables), so the executed-instruction FP64 pipe utilisation is the ncu figure in profiles/",
-                "executed_fp64_pipe_frac": NCU_FP64_PIPE.get(kname, (None, None))[0], "executed_fp64_pipe_source": NCU_FP64_PIPE.get(kname, (None, None))[1],
-                "kernel": kname, "kernel_ms": kms_, "evals_per_launch": kev, "gevals_per_s": kev / (kms_ * 1e-3) / 1e9,
-                "share_of_step": dom["share_of_step"] if dom else 1.0,
-                "whole_step": {"achieved": ach_step, "frac": ach_step / fp64_peak, "evals": info["evals"],
-                               "gevals_per_s": info["evals"] / (r["ms_per_step"] * 1e-3) / 1e9}}
+            kname, kev, kms_, nom_flops, key = info["kernel"], info["evals"], r["ms_per_step"], info["flops"], info.get("key")
+        ex = table.get(key) if key else None
+        sec_k = kms_ * 1e-3
+        nominal = nom_flops / sec_k / 1e12
+        ach = kev * ex["flops_per_eval"] / sec_k / 1e12 if ex else None
+        traffic = traffic_note = None
+        if ex and ex["capture"].get("dram_bytes_per_eval") is not None:
+            same = ex["capture"].get("nprob") == (dom or {}).get("nprob", info.get("nprob"))
+            traffic = ex["capture"]["dram_bytes"] if same else ex["capture"]["dram_bytes_per_eval"] * kev
+            traffic_note = (f"profiles/{ex['capture']['source']}: dram__bytes_read.sum + dram__bytes_write.sum of one launch"
+                            + ("" if same else f" of {ex['capture'].get('nprob')} problems, scaled by evaluations to this launch"))
+        roof = {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak if ach is not None else None,
+                "traffic": traffic, "traffic_source": traffic_note,
+                "flops_model": "EXECUTED FP64: (2 DFMA + DMUL + DADD thread instructions per integrand evaluation, from the ncu capture named in "
+                               "executed_source) x evaluations of this launch / CUDA-event kernel time" if ex else "executed counts missing for this kernel",
+                "executed_source": f"profiles/r02_executed_fp64.json[{key}] <- profiles/{ex['capture']['source']}" if ex else None,
+                "executed_flops_per_eval": ex["flops_per_eval"] if ex else None,
+                "fp64_pipe_frac": kev * ex["fp64_inst_per_eval"] / sec_k / (fp64_peak * 1e12 / 2) if ex else None,
+                "fp64_pipe_frac_note": "FP64 issue slots used (DFMA, DMUL and DADD take one slot each; peak = measured DFMA rate)",
+                "fp64_pipe_pct_in_capture_ncu": ex["capture"].get("fp64_pipe_pct_ncu") if ex else None,
+                "nominal_achieved": nominal, "nominal_frac": nominal / fp64_peak,
+                "nominal_note": "SURVEY 8(d) algorithmic operation count per evaluation x evaluations (exceeds the executed count: separable-term tables, angle addition)",
+                "peak_source": "builder-measured: DFMA-chain microbenchmark run live on this GPU (ib200_measure_fp64_peak; nominal 37.2); MEASURED_PEAKS.json has no FP64 entry",
+                "kernel": kname, "kernel_ms": kms_, "evals_per_launch": kev, "gevals_per_s": kev / sec_k / 1e9,
+                "share_of_step": dom["share_of_step"] if dom else 1.0}
+        if info.get("flops_executed"):
+            roof["whole_step"] = {"achieved": info["flops_executed"] / (r["ms_per_step"] * 1e-3) / 1e12,
+                                  "frac": info["flops_executed"] / (r["ms_per_step"] * 1e-3) / 1e12 / fp64_peak, "evals": info["evals"],
+                                  "gevals_per_s": info["evals"] / (r["ms_per_step"] * 1e-3) / 1e9}
     line = {"metric": metric, "value": r["value"], "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong" if w == "c5" else "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(w, args), "clocks": r["clocks"],
@@ -628,8 +671,10 @@ def main():
                 continue
             if sw.startswith("c2") and torch.cuda.mem_get_info()[0] < (40 << 30):
                 continue
+            if sw == "c4_reference_order" and args.hcub_mode == "reference_order":
+                continue
             try:
-                s = run(sw, 2, 3, with_e2e=False)
+                s = run(sw, 1, 1, with_e2e=False) if sw == "c4_reference_order" else run(sw, 2, 3, with_e2e=False)
                 e = {"value": s["value"], "unit": METRIC[sw][1] if sw in METRIC else EXTRA_UNITS[sw], "ms_per_step": s["ms_per_step"]}
                 if "result" in s["info"]:
                     e["result"] = s["info"]["result"]
@@ -642,21 +687,33 @@ def main():
                 elif "bytes" in s["info"]:                   # the bridge: HBM bytes of its own two kernels per point
                     e["algorithmic_GBps"] = s["info"]["bytes"] / (s["ms_per_step"] * 1e-3) / 1e9
                 else:
-                    e["fp64_tflops_nominal"] = s["info"]["flops"] / (s["ms_per_step"] * 1e-3) / 1e12
+                    tab = executed_table()
+                    inf = s["info"]
+                    ex = tab.get(inf.get("key") or (inf.get("dominant") or {}).get("key"))
+                    if inf.get("flops_executed"):              # c4: every family's own count
+                        e["fp64_tflops_executed"] = inf["flops_executed"] / (s["ms_per_step"] * 1e-3) / 1e12
+                    elif ex:
+                        e["fp64_tflops_executed"] = inf["evals"] * ex["flops_per_eval"] / (s["ms_per_step"] * 1e-3) / 1e12
+                        e["fp64_pipe_frac"] = inf["evals"] * ex["fp64_inst_per_eval"] / (s["ms_per_step"] * 1e-3) / (fp64_peak * 1e12 / 2)
+                    if "fp64_tflops_executed" in e:
+                        e["frac_of_fp64_peak"] = e["fp64_tflops_executed"] / fp64_peak
+                    e["fp64_tflops_nominal"] = inf["flops"] / (s["ms_per_step"] * 1e-3) / 1e12
                     e["nominal_frac_of_fp64_peak"] = e["fp64_tflops_nominal"] / fp64_peak
                 sec[sw] = e
             except Exception as ex:                          # a side measurement must not lose the headline
                 sec[sw] = {"error": str(ex)[:200]}
             torch.cuda.empty_cache()
-        sec["_note"] = ("fp64_tflops_nominal uses the algorithmic flop counts of SURVEY 8(d) (a throughput-equivalent figure: it exceeds 1 where a "
-                        "kernel executes fewer operations than the count assumes -- angle addition in c3, per-axis factor tables in c5); the executed "
-                        "FP64-pipe utilisation per kernel is the ncu figure in profiles/README.md (c1 31.8 %, c3 45.6 %, c5 38.1 %, c4 20-34 %)")
+        sec["_note"] = ("frac_of_fp64_peak / fp64_tflops_executed: EXECUTED FP64 instructions (per-evaluation counts of the committed ncu captures, "
+                        "profiles/r02_executed_fp64.json) x this run's evaluations / time -- cannot exceed 1.  fp64_tflops_nominal uses the algorithmic "
+                        "counts of SURVEY 8(d) and exceeds the peak where a kernel executes fewer operations than the count assumes (angle addition in "
+                        "c3, per-axis factor tables in c4 / c5)")
         line["secondary"] = sec
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         units, dt, cores, sample = cpu_leg(w)
+        import oracle as O
         line["cpu_baseline"] = {"value": units / dt, "unit": unit, "cores": cores, "kind": "port", "sample": sample,
-                                "seconds": dt}
+                                "seconds": dt, "build": O.BASELINE_FLAGS}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -118,7 +118,7 @@ extern "C" int32_t ib200_hcubature_batch(ib200_ctx *ctx, int32_t family, int32_t
         }
         if (rcap < init_boxes + 64) rcap = init_boxes + 64;
         q.cap = (int)((rcap + 127) / 128 * 128);
-        q.bounds = q.ival = q.err = nullptr; q.kdiv = nullptr; q.list = nullptr; q.counter = counter;
+        q.rec = q.err = nullptr; q.list = nullptr; q.counter = counter;
         q.out_I = oI.d; q.out_E = oE.d; q.out_nevals = oN.d; q.out_status = oS.d;
         ctx->err.clear();
         ib200_time_begin(ctx);

@@ -45,11 +45,9 @@ struct Params {
     int initdiv;
     double frac;                // largest share of a problem's stored boxes bisected in one round
     int cap;                    // boxes per warp arena
-    double *bounds;             // [warps][cap][2D]   a[D], b[D]
-    double *ival;               // [warps][cap]
-    double *err;                // [warps][cap]
-    unsigned char *kdiv;        // [warps][cap]       split axis
-    int *list;                  // [warps][cap]       slots selected for bisection in the current round
+    double *rec;                // [warps][cap][2D+2]   a[D], b[D], I, split axis  (16-byte aligned records)
+    double *err;                // [warps][cap]         the selection keys, scanned once per round
+    int *list;                  // [warps][cap]         slots selected for bisection in the current round
     unsigned long long *counter;
     double *out_I, *out_E; int64_t *out_nevals; int32_t *out_status;
 };
@@ -70,11 +68,15 @@ __device__ __forceinline__ double wmax(double v) {
     return v;
 }
 
-// per-warp shared-memory row: hist[kBins] (unsigned) | pc = par[NPAR] lbs[D] aux[D] finit jacc  (the layout gm_rule_thread reads)
-template <int FAM, int D> __host__ __device__ constexpr int row_doubles() { return kBins / 2 + hp::pc_doubles<FAM, D>() + 1; }
+// per-warp shared memory: hist[kBins] (unsigned) | occ[kBins/32] (bitmap of the occupied bins) | pc = par[NPAR] lbs[D] aux[D] finit jacc
+// (the layout gm_rule_thread reads) | stage[2][D+1][32] double2: the parent records of the current and the next pass (cp.async)
+template <int FAM, int D> __host__ __device__ constexpr int pc_padded() { return (hp::pc_doubles<FAM, D>() + 1) & ~1; }
+template <int FAM, int D> __host__ __device__ constexpr int row_doubles() {
+    return kBins / 2 + kBins / 64 + pc_padded<FAM, D>() + 2 * (D + 1) * 32 * 2;
+}
 
 #ifndef HB_MINB
-#define HB_MINB 2
+#define HB_MINB 3
 #endif
 template <int FAM, int D, bool ALLFIN>
 __global__ void __launch_bounds__(kBlock, HB_MINB)
@@ -82,19 +84,21 @@ hcub_rb_kernel(const Params p) {
     using F = ib::Family<FAM, D>;
     constexpr int NPAR = ib::fam_nparam(FAM, D);
     constexpr int NP = hc::gm_npoints(D);
+    constexpr int RECW = 2 * D + 2, NCH = D + 1;          // a record = NCH 16-byte chunks
     extern __shared__ double sm[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const unsigned full = 0xffffffffu;
     const unsigned lt = (1u << lane) - 1u;
     const int64_t gwarp = (int64_t)blockIdx.x * kWarps + wib;
-    unsigned *hist = reinterpret_cast<unsigned *>(sm + (size_t)wib * row_doubles<FAM, D>());
-    double *pc = sm + (size_t)wib * row_doubles<FAM, D>() + kBins / 2;
+    double *row = sm + (size_t)wib * row_doubles<FAM, D>();
+    unsigned *hist = reinterpret_cast<unsigned *>(row);
+    unsigned *occ = reinterpret_cast<unsigned *>(row + kBins / 2);
+    double *pc = row + kBins / 2 + kBins / 64;
+    double2 *stage = reinterpret_cast<double2 *>(pc + pc_padded<FAM, D>());     // [2][NCH][32]
     double *par = pc, *lbs = pc + NPAR, *aux = lbs + D;
 
-    double *bounds = p.bounds + (size_t)gwarp * p.cap * (2 * D);
-    double *ival = p.ival + (size_t)gwarp * p.cap;
+    double *rec = p.rec + (size_t)gwarp * p.cap * RECW;
     double *err = p.err + (size_t)gwarp * p.cap;
-    unsigned char *kdiv = p.kdiv + (size_t)gwarp * p.cap;
     int *list = p.list + (size_t)gwarp * p.cap;
 
     double rtol = p.rtol;
@@ -117,6 +121,7 @@ hcub_rb_kernel(const Params p) {
             lbs[k] = l; aux[k] = ALLFIN ? (u - l) * 0.5 : u;
         }
         for (int b = lane; b < kBins; b += 32) hist[b] = 0u;
+        for (int b = lane; b < kBins / 32; b += 32) occ[b] = 0u;
         __syncwarp();
         if (lane == 0) {
             double jacc = 1.0;
@@ -142,73 +147,97 @@ hcub_rb_kernel(const Params p) {
         const bool degenerate = (prodD == 0.0);
         if (degenerate) qtotal = 1;                 // HCubature returns after the first box
 
-        int nbox = qtotal, ntodo = qtotal, nsplit = 0, status = IB200_ST_CONVERGED;
-        int blo = kBins, bhi = -1;                  // occupied range of the histogram (a superset: bins may empty again)
+        int nbox = qtotal, ntodo = qtotal, nbox0 = 0, status = IB200_ST_CONVERGED;
         long long applied = 0;
-        double I = 0.0, E = 0.0, theta = 0.0;
+        double I = 0.0, E = 0.0, theta = 0.0, dE = 0.0;
         bool first = true;
 
+        // round 0: the boxes of the initial grid are written to the store unevaluated; the evaluation loop below then takes them
+        // like the children of a split (the same code path, so the rule is instantiated once)
+        for (int t = lane; t < qtotal; t += 32) {
+            double r[RECW];
+            int q = t;
+#pragma unroll
+            for (int k = 0; k < D; k++) {
+                const int cidx = q % p.initdiv; q /= p.initdiv;
+                const double Dl = (th[k] - tl[k]) / p.initdiv;
+                r[k] = tl[k] + cidx * Dl;
+                r[D + k] = (cidx == p.initdiv - 1) ? th[k] : r[k] + Dl;
+            }
+            r[2 * D] = 0.0; r[2 * D + 1] = 0.0;
+            double2 *dst = reinterpret_cast<double2 *>(rec + (size_t)t * RECW);
+#pragma unroll
+            for (int q2 = 0; q2 < NCH; q2++) dst[q2] = make_double2(r[2 * q2], r[2 * q2 + 1]);
+        }
+        __syncwarp();
+
         for (;;) {
-            // ---- evaluate: first round = the initial grid, later rounds = both halves of every selected box
-            double sI = 0.0, sE = 0.0, mx = 0.0;
-            int mylo = kBins, myhi = -1;
-            for (int t0 = 0; t0 < ntodo; t0 += 32) {
-                const int t = t0 + lane;
-                const bool have = t < ntodo;
-                double a[D], b[D];
-                int slot = 0;
-                if (have) {
-                    if (first) {
-                        slot = t;
-                        int r = t;
+            // ---- evaluate.  Round 0: the boxes of the initial grid (entry t = slot t).  Later rounds: both halves of every selected
+            //      box -- lanes 2r, 2r+1 take the children of list[r].  The records a pass needs are staged into shared memory with
+            //      cp.async while the previous pass is evaluated, and the list entries of the pass after that are in flight behind
+            //      them, so a pass does not wait for HBM (ncu on the first version: long_scoreboard was the top stall).
+            double sI = 0.0, sE = -dE, mx = 0.0;       // this lane's share of the round's new boxes (minus the parents' errors)
+            {
+                const int npass = (ntodo + 31) >> 5;
+                auto entry = [&](int t) { return first ? t : __ldcg(list + (t >> 1)); };
+                auto issue = [&](int src_slot, int buf) {        // record -> stage[buf][chunk][lane]
+                    const double2 *src = reinterpret_cast<const double2 *>(rec + (size_t)src_slot * RECW);
 #pragma unroll
-                        for (int k = 0; k < D; k++) {
-                            const int cidx = r % p.initdiv; r /= p.initdiv;
-                            const double Dl = (th[k] - tl[k]) / p.initdiv;
-                            a[k] = tl[k] + cidx * Dl;
-                            b[k] = (cidx == p.initdiv - 1) ? th[k] : a[k] + Dl;
-                        }
-                    } else {
-                        const int parent = list[t >> 1];
-                        const double2 *src = reinterpret_cast<const double2 *>(bounds + (size_t)parent * (2 * D));
-                        double r[2 * D];
+                    for (int q = 0; q < NCH; q++) hp::cp_async16(stage + ((size_t)buf * NCH + q) * 32 + lane, src + q);
+                };
+                int par_cur = lane < ntodo ? entry(lane) : 0;
+                if (lane < ntodo) issue(par_cur, 0);
+                hp::cp_async_commit();
+                int par_next = 32 + lane < ntodo ? entry(32 + lane) : 0;
+                for (int ps = 0; ps < npass; ps++) {
+                    const int t = (ps << 5) + lane;
+                    const bool have = t < ntodo;
+                    const int par_next2 = 64 + t < ntodo ? entry(64 + t) : 0;
+                    hp::cp_async_wait_all();
+                    double a[D], b[D], Ipar = 0.0;
+                    int kd = -1;
+                    if (have) {
+                        double r[RECW];
 #pragma unroll
-                        for (int q = 0; q < D; q++) { const double2 v = __ldcg(src + q); r[2 * q] = v.x; r[2 * q + 1] = v.y; }
-                        const int kd = kdiv[parent];
-                        double akd = 0.0, bkd = 0.0;
+                        for (int q = 0; q < NCH; q++) { const double2 v = stage[((size_t)(ps & 1) * NCH + q) * 32 + lane]; r[2 * q] = v.x; r[2 * q + 1] = v.y; }
 #pragma unroll
-                        for (int k = 0; k < D; k++) { a[k] = r[k]; b[k] = r[D + k]; if (k == kd) { akd = r[k]; bkd = r[D + k]; } }
-                        const double w = (bkd - akd) * 0.5;
+                        for (int k = 0; k < D; k++) { a[k] = r[k]; b[k] = r[D + k]; }
+                        Ipar = r[2 * D];
+                        if (!first) kd = (int)r[2 * D + 1];
+                    }
+                    if (32 + t < ntodo) issue(par_next, (ps + 1) & 1);
+                    hp::cp_async_commit();
+                    __syncwarp();            // every lane holds its parent's record before child 0 overwrites that slot
+                    if (have) {
                         // child 0 = upper half (a[kd] += w) keeps the parent's slot, child 1 = lower half (b[kd] -= w) is appended
 #pragma unroll
-                        for (int k = 0; k < D; k++) if (k == kd) { if ((t & 1) == 0) a[k] = akd + w; else b[k] = bkd - w; }
-                        slot = (t & 1) ? nbox - nsplit + (t >> 1) : parent;
+                        for (int k = 0; k < D; k++) if (k == kd) { const double w = (b[k] - a[k]) * 0.5; if ((t & 1) == 0) a[k] = a[k] + w; else b[k] = b[k] - w; }
+                        if (!first && (t & 1) == 0) sI -= Ipar;                   // the parent's integral leaves the sum
+                        const int slot = (first || (t & 1) == 0) ? par_cur : nbox0 + (t >> 1);
+                        double Ic, Ec; int kc = 0;
+                        if constexpr (FAM == IB200_FAM_GENZ_OSC && ALLFIN) hp::gm_rule_thread_osc<D>(pc, a, b, Ic, Ec, kc);
+                        else hp::gm_rule_thread<FAM, D, ALLFIN>(pc, p.tr, a, b, Ic, Ec, kc);
+                        double2 *dst = reinterpret_cast<double2 *>(rec + (size_t)slot * RECW);
+                        double r[RECW];
+#pragma unroll
+                        for (int k = 0; k < D; k++) { r[k] = a[k]; r[D + k] = b[k]; }
+                        r[2 * D] = Ic; r[2 * D + 1] = (double)kc;
+#pragma unroll
+                        for (int q = 0; q < NCH; q++) dst[q] = make_double2(r[2 * q], r[2 * q + 1]);
+                        err[slot] = Ec;
+                        const int bn = ebin(Ec);
+                        if (atomicAdd(&hist[bn], 1u) == 0u) atomicOr(&occ[bn >> 5], 1u << (bn & 31));
+                        sI += Ic; sE += Ec; mx = fmax(mx, Ec);       // fmax drops NaN: a non-finite E is caught through sE
                     }
-                }
-                __syncwarp();            // both children have read the parent's record before child 0 overwrites it
-                if (have) {
-                    double Ic, Ec; int kc = 0;
-                    if constexpr (FAM == IB200_FAM_GENZ_OSC && ALLFIN) hp::gm_rule_thread_osc<D>(pc, a, b, Ic, Ec, kc);
-                    else hp::gm_rule_thread<FAM, D, ALLFIN>(pc, p.tr, a, b, Ic, Ec, kc);
-                    double2 *dst = reinterpret_cast<double2 *>(bounds + (size_t)slot * (2 * D));
-                    double r[2 * D];
-#pragma unroll
-                    for (int k = 0; k < D; k++) { r[k] = a[k]; r[D + k] = b[k]; }
-#pragma unroll
-                    for (int q = 0; q < D; q++) dst[q] = make_double2(r[2 * q], r[2 * q + 1]);
-                    ival[slot] = Ic; err[slot] = Ec; kdiv[slot] = (unsigned char)kc;
-                    const int bn = ebin(Ec);
-                    atomicAdd(&hist[bn], 1u);
-                    mylo = min(mylo, bn); myhi = max(myhi, bn);
-                    sI += Ic; sE += Ec; mx = fmax(mx, Ec);       // fmax drops NaN: a non-finite E is caught through sE
+                    par_cur = par_next; par_next = par_next2;
                 }
             }
+            first = false;
+
+            // ---- close the round: sums over the new boxes
             sI = wsum(sI); sE = wsum(sE); mx = wmax(mx);
-            blo = min(blo, (int)__reduce_min_sync(full, (unsigned)mylo));
-            bhi = max(bhi, (int)__reduce_max_sync(full, (unsigned)(myhi + 1)) - 1);
             I += sI; E += sE;
             applied += ntodo;
-            first = false;
             __syncwarp();
 
             // ---- HCubature's stopping test
@@ -217,68 +246,81 @@ hcub_rb_kernel(const Params p) {
             if (!isfinite(E)) { status = IB200_ST_NONFINITE; break; }
             if (applied >= p.max_apps) { status = IB200_ST_MAXEVALS; break; }
 
-            // ---- threshold (csrc/hcub_rounds.cuh decide_kernel, per problem; every lane computes the same value)
+            // ---- threshold (csrc/hcub_rounds.cuh decide_kernel, per problem).  The three scans of the exponent histogram walk only
+            //      the OCCUPIED bins (bitmap), in the same order and with the same arithmetic as the scans over all bins; every lane
+            //      computes the same value.  Bin kBins-1 (inf / NaN keys) never takes part: a non-finite E has ended the solve above.
             theta = 0.5 * fmax(mx, theta);
             {
-                const int b0 = blo, b1 = bhi < kBins - 2 ? bhi : kBins - 2;
-                int bh = b0 - 1; double low = 0.0; bool broke = false;
-                for (int b = b0; b <= b1; b++) {
-                    const unsigned c = hist[b];
-                    if (c != 0u) { low += (double)c * bin_edge(b); if (!(low <= tol)) { broke = true; break; } }
-                    bh = b;
+                const unsigned long long words = (unsigned long long)__ballot_sync(full, occ[lane] != 0u) |
+                                                 ((unsigned long long)__ballot_sync(full, occ[32 + lane] != 0u) << 32);
+                int bh = kBins - 2;
+                {   // (1) ascending: longest prefix of bins whose lower-edge mass stays <= tol
+                    double low = 0.0; bool broke = false;
+                    unsigned long long ws = words;
+                    while (ws && !broke) {
+                        const int w = __ffsll((long long)ws) - 1; ws &= ws - 1;
+                        unsigned m = occ[w];
+                        while (m) {
+                            const int b = (w << 5) + __ffs((int)m) - 1; m &= m - 1;
+                            if (b > kBins - 2) break;
+                            low += (double)hist[b] * bin_edge(b);
+                            if (!(low <= tol)) { bh = b - 1; broke = true; break; }
+                        }
+                    }
                 }
-                if (!broke) bh = kBins - 2;
-                const double remaining = (double)p.max_apps - (double)applied;
-                int bb = b1 + 1; double above = 0.0; broke = false;
-                for (int b = b1; b >= b0; b--) {
-                    above += (double)hist[b];
-                    if (2.0 * above > remaining) { broke = true; break; }
-                    bb = b;
+                int bb = 0, bf = 0;
+                {   // (2) budget and (3) selectivity, descending: the lowest bin down to which bisecting everything still fits
+                    const double remaining = (double)p.max_apps - (double)applied, share = p.frac * (double)nbox;
+                    double above = 0.0; bool broke_b = false, broke_f = false;
+                    unsigned long long ws = words;
+                    while (ws && !(broke_b && broke_f)) {
+                        const int w = 63 - __clzll((long long)ws); ws &= ~(1ull << w);
+                        unsigned m = occ[w];
+                        while (m && !(broke_b && broke_f)) {
+                            const int b = (w << 5) + 31 - __clz((int)m); m &= ~(1u << (b & 31));
+                            if (b > kBins - 2) continue;
+                            above += (double)hist[b];
+                            if (!broke_b && 2.0 * above > remaining) { bb = b + 1; broke_b = true; }
+                            if (!broke_f && above > share) { bf = b + 1; broke_f = true; }
+                        }
+                    }
                 }
-                if (!broke) bb = 0;
-                int bf = b1 + 1; double top = 0.0; broke = false;
-                for (int b = b1; b >= b0; b--) {
-                    top += (double)hist[b];
-                    if (top > p.frac * (double)nbox) { broke = true; break; }
-                    bf = b;
-                }
-                if (!broke) bf = 0;
                 if (bf > bb) bb = bf;
                 const int bs = (bh + 1 > bb) ? bh + 1 : bb;
                 const double theta_h = bs <= 0 ? 0.0 : (bs >= kBins - 1 ? 1.7976931348623157e308 : bin_edge(bs));
                 theta = fmin(theta, theta_h);
             }
 
-            // ---- select: slots with error >= theta, in store order
-            nsplit = 0;
-            double dI = 0.0, dE = 0.0;
-            for (int i0 = 0; i0 < nbox; i0 += 128) {
-                double e[4];
+            // ---- select: slots with error >= theta, in store order (8 key loads in flight per lane)
+            int nsplit = 0;
+            dE = 0.0;
+            for (int i0 = 0; i0 < nbox; i0 += 256) {
+                double e[8];
 #pragma unroll
-                for (int u = 0; u < 4; u++) { const int i = i0 + 32 * u + lane; e[u] = i < nbox ? __ldcg(err + i) : -1.0; }
+                for (int u = 0; u < 8; u++) { const int i = i0 + 32 * u + lane; e[u] = i < nbox ? __ldcg(err + i) : -1.0; }
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
+                for (int u = 0; u < 8; u++) {
                     const int i = i0 + 32 * u + lane;
                     const bool flag = e[u] >= theta;
                     const unsigned bal = __ballot_sync(full, flag);
                     if (flag) {
                         list[nsplit + __popc(bal & lt)] = i;
-                        dI += __ldcg(ival + i); dE += e[u];
-                        atomicSub(&hist[ebin(e[u])], 1u);
+                        dE += e[u];
+                        const int bn = ebin(e[u]);
+                        if (atomicSub(&hist[bn], 1u) == 1u) atomicAnd(&occ[bn >> 5], ~(1u << (bn & 31)));
                     }
                     nsplit += __popc(bal);
                 }
             }
             if (nbox + nsplit > p.cap) { status = IB200_ST_MAXEVALS; break; }     // arena full: leave the boxes alone
-            dI = wsum(dI); dE = wsum(dE);
-            I -= dI; E -= dE;
+            nbox0 = nbox;
             nbox += nsplit; ntodo = 2 * nsplit;
             __syncwarp();                 // the split list is read across lanes
         }
 
         // ---- HCubature's closing sum over the store
         double pI = 0.0, pE = 0.0;
-        for (int s = lane; s < nbox; s += 32) { pI += __ldcg(ival + s); pE += __ldcg(err + s); }
+        for (int s = lane; s < nbox; s += 32) { pI += __ldcg(rec + (size_t)s * RECW + 2 * D); pE += __ldcg(err + s); }
         pI = wsum(pI); pE = wsum(pE);
         if (lane == 0) {
             p.out_I[prob] = pI;
@@ -289,7 +331,7 @@ hcub_rb_kernel(const Params p) {
     }
 }
 
-inline size_t arena_bytes_per_box(int D) { return (size_t)16 * D + 8 + 8 + 1 + 4; }
+inline size_t arena_bytes_per_box(int D) { return (size_t)8 * (2 * D + 2) + 8 + 4; }
 
 template <int D>
 int32_t launch(ib200_ctx *ctx, int family, bool allfin, Params &p);
@@ -313,12 +355,10 @@ int32_t launch_impl(ib200_ctx *ctx, int family, bool allfin, Params &p) {
                 int64_t blocks = (p.nprob + kWarps - 1) / kWarps;
                 if (blocks > (int64_t)ctx->sm_count * occ) blocks = (int64_t)ctx->sm_count * occ;
                 const size_t warps = (size_t)blocks * kWarps, cap = (size_t)p.cap;
-                p.bounds = (double *)ctx->get(SL_WORK2, warps * cap * 2 * D * sizeof(double));
-                p.ival = (double *)ctx->get(SL_WORK0, warps * cap * sizeof(double));
+                p.rec = (double *)ctx->get(SL_WORK2, warps * cap * (2 * D + 2) * sizeof(double));
                 p.err = (double *)ctx->get(SL_WORK4, warps * cap * sizeof(double));
                 p.list = (int *)ctx->get(SL_WORK3, warps * cap * sizeof(int));
-                p.kdiv = (unsigned char *)ctx->get(SL_WORK5, warps * cap);
-                if (!p.bounds || !p.ival || !p.err || !p.list || !p.kdiv)
+                if (!p.rec || !p.err || !p.list)
                     return ib200_fail(ctx, IB200_ERR_OOM, "ib200_hcubature_batch: box arena allocation failed (lower maxiters or the hcub_capacity option)");
                 kern<<<(unsigned)blocks, kBlock, smem, ctx->stream>>>(p);
                 IB_LAUNCH_CHECK(ctx);

@@ -1270,9 +1270,24 @@ int orc_hcubature_vec_batch(int fam, int dim, const double *lb, const double *ub
  * ------------------------------------------------------------------------------------------ */
 double orc_round_fraction = 0.5;
 /* the rounds themselves, from a store of `len` unevaluated boxes (all of them in the todo list) */
+static int hcub_rounds_core2(orc_integrand f, void *user, int dim, orc_box *t, int64_t cap, int64_t len,
+                             double rtol, double atol, int64_t max_boxes, int first_box_only, int64_t switch_boxes, double switch_factor,
+                             double *Iout, double *Eout, int64_t *napplied_out, int64_t *nboxes_out, int64_t *rounds_out,
+                             orc_box **store_out);
 static int hcub_rounds_core(orc_integrand f, void *user, int dim, orc_box *t, int64_t cap, int64_t len,
                             double rtol, double atol, int64_t max_boxes, int first_box_only,
                             double *Iout, double *Eout, int64_t *napplied_out, int64_t *nboxes_out, int64_t *rounds_out)
+{
+    return hcub_rounds_core2(f, user, dim, t, cap, len, rtol, atol, max_boxes, first_box_only, 0, 0.0, Iout, Eout, napplied_out, nboxes_out,
+                             rounds_out, NULL);
+}
+/* switch_boxes > 0: the two-level solve (orc_hcubature_two_level) -- stop with status 3 ("hand over") after the stopping test of a round
+   once the store holds >= switch_boxes boxes AND E <= switch_factor * tol (or the store holds >= 16 * switch_boxes boxes), and return the
+   store (unsplit, every box evaluated) through store_out instead of freeing it */
+static int hcub_rounds_core2(orc_integrand f, void *user, int dim, orc_box *t, int64_t cap, int64_t len,
+                             double rtol, double atol, int64_t max_boxes, int first_box_only, int64_t switch_boxes, double switch_factor,
+                             double *Iout, double *Eout, int64_t *napplied_out, int64_t *nboxes_out, int64_t *rounds_out,
+                             orc_box **store_out)
 {
     int64_t ntodo = 0, applied = 0, rounds = 0;
     int64_t *todo = (int64_t *)malloc(sizeof(int64_t) * (size_t)cap);
@@ -1291,6 +1306,8 @@ static int hcub_rounds_core(orc_integrand f, void *user, int dim, orc_box *t, in
         if (E <= fmax(rtol * fabs(I), atol)) break;
         if (!isfinite(E)) { status = 2; break; }
         if (applied >= max_boxes) { status = 1; break; }
+        if (switch_boxes > 0 && len >= switch_boxes &&
+            (E <= switch_factor * fmax(rtol * fabs(I), atol) || len >= 16 * switch_boxes)) { status = 3; break; }
         theta = 0.5 * fmax(mx, theta);
         {   /* threshold from the exponent histogram (see the header comment of csrc/hcub_single.cu) */
             double cnt[2048];
@@ -1336,12 +1353,95 @@ static int hcub_rounds_core(orc_integrand f, void *user, int dim, orc_box *t, in
     }
     I = 0.0; E = 0.0;
     for (int64_t i = 0; i < len; i++) { I += t[i].I; E += t[i].E; }
-    free(t); free(todo);
+    free(todo);
+    if (store_out) *store_out = t; else free(t);
     *Iout = I; *Eout = E;
     if (napplied_out) *napplied_out = applied;
     if (nboxes_out) *nboxes_out = len;
     if (rounds_out) *rounds_out = rounds;
     return status;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Two-level variant (NOT in the reference): the checker of ib200_hcubature_single for solves whose box store would outgrow the
+ * device.  Level 1 = the rounds above until the store holds switch_boxes boxes and the error is within switch_factor of the
+ * tolerance.  Level 2 = every stored box becomes an independent sub-problem, refined by the same rounds until ITS error is
+ * below ITS share of the tolerance, eps_i = (1 - 2^-6) tol * E_i^alpha / sum_j E_j^alpha (tol = max(rtol |I|, atol) with the
+ * level-1 estimate I); a sub-problem's boxes are summed and dropped when it is done, so memory is bounded by the level-1 store plus
+ * one sub-problem per worker, and the sub-problems need no communication (multi-GPU: dealt to the ranks, one sum at the end).
+ * sum eps_i < tol, so when every sub-problem converges E <= tol: HCubature's stopping test holds for the whole integral.
+ * Same rule, split axis and per-box error as HCubature; what differs from the reference is, again, only the ORDER of refinement.
+ * sub_max_boxes: budget of rule applications per sub-problem (the analogue of a full arena: status 1).
+ * ------------------------------------------------------------------------------------------ */
+int orc_hcubature_two_level(orc_integrand f, void *user, int dim, const double *a, const double *b,
+                            double rtol, double atol, int64_t max_boxes, int64_t switch_boxes, double switch_factor,
+                            int64_t sub_max_boxes, double alpha,
+                            double *Iout, double *Eout, int64_t *napplied_out, int64_t *nboxes_out, int64_t *rounds_out, int64_t *nsub_out)
+{
+    if (dim < 1 || dim > ORC_MAXDIM || rtol < 0 || atol < 0 || max_boxes < 1 || switch_boxes < 1) return -1;
+    if (rtol == 0 && atol == 0) rtol = sqrt(2.220446049250313e-16);
+    int64_t cap = 1024, applied = 0, len = 0, rounds = 0;
+    orc_box *t = (orc_box *)malloc(sizeof(orc_box) * (size_t)cap), *store = NULL;
+    for (int i = 0; i < dim; i++) { t[0].a[i] = a[i]; t[0].b[i] = b[i]; }
+    t[0].I = 0.0; t[0].E = 0.0; t[0].kdiv = 0;
+    double I = 0.0, E = 0.0;
+    int st = hcub_rounds_core2(f, user, dim, t, cap, 1, rtol, atol, max_boxes, 0, switch_boxes, switch_factor, &I, &E, &applied, &len, &rounds, &store);
+    if (nsub_out) *nsub_out = 0;
+    if (st != 3) {
+        free(store);
+        *Iout = I; *Eout = E;
+        if (napplied_out) *napplied_out = applied;
+        if (nboxes_out) *nboxes_out = len;
+        if (rounds_out) *rounds_out = rounds;
+        return st;
+    }
+    const double tol = fmax(rtol * fabs(I), atol) * (1.0 - 0.015625);
+    double wsum = 0.0;
+    for (int64_t i = 0; i < len; i++) wsum += pow(store[i].E, alpha);
+    double Is = 0.0, Es = 0.0;
+    int status = 0;
+    int64_t nsub = 0, boxes = 0;
+    for (int64_t i = 0; i < len; i++) {
+        const double eps = tol * (pow(store[i].E, alpha) / wsum);
+        if (store[i].E <= eps) { Is += store[i].I; Es += store[i].E; boxes++; continue; }
+        orc_box *tt = (orc_box *)malloc(sizeof(orc_box) * 1024);
+        tt[0] = store[i];
+        /* the box is already evaluated: its first round is its own bisection (err >= theta with theta = its error) -- restated
+           by starting the core on the two halves */
+        {
+            orc_box box = store[i];
+            int k = box.kdiv;
+            double w = (box.b[k] - box.a[k]) * 0.5;
+            orc_box b1 = box, b2 = box;
+            b1.a[k] = box.a[k] + w; b1.I = 0.0; b1.E = 0.0;
+            b2.b[k] = box.b[k] - w; b2.I = 0.0; b2.E = 0.0;
+            tt[0] = b1; tt[1] = b2;
+        }
+        double Ii = 0.0, Ei = 0.0; int64_t ap = 0, nb = 0, nr = 0;
+        int s2 = hcub_rounds_core(f, user, dim, tt, 1024, 2, 0.0, eps, sub_max_boxes, 0, &Ii, &Ei, &ap, &nb, &nr);
+        if (s2 != 0) status = s2 == 2 ? 2 : (status == 2 ? 2 : 1);
+        Is += Ii; Es += Ei; applied += ap; boxes += nb; nsub++;
+    }
+    free(store);
+    *Iout = Is; *Eout = Es;
+    if (napplied_out) *napplied_out = applied;
+    if (nboxes_out) *nboxes_out = boxes;
+    if (rounds_out) *rounds_out = rounds;
+    if (nsub_out) *nsub_out = nsub;
+    return status;
+}
+
+int orc_hcubature_two_level_family(int fam, int dim, const double *lb, const double *ub, int tr, const double *params,
+                                   double reltol, double abstol, int64_t max_boxes, int64_t switch_boxes, double switch_factor,
+                                   int64_t sub_max_boxes, double alpha,
+                                   double *I, double *E, int64_t *napplied, int64_t *nboxes, int64_t *rounds, int64_t *nsub)
+{
+    orc_family_user u = {fam, dim, params};
+    orc_cov c = {orc_family_integrand, &u, dim, tr, lb, ub};
+    double tl[ORC_MAXDIM], tu[ORC_MAXDIM];
+    for (int i = 0; i < dim; i++) orc_u2t(lb[i], ub[i], &tl[i], &tu[i]);
+    return orc_hcubature_two_level(orc_cov_eval, &c, dim, tl, tu, reltol, abstol, max_boxes, switch_boxes, switch_factor, sub_max_boxes, alpha,
+                                   I, E, napplied, nboxes, rounds, nsub);
 }
 
 int orc_hcubature_rounds(orc_integrand f, void *user, int dim, const double *a, const double *b,

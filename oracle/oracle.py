@@ -27,10 +27,38 @@ def build(force=False):
     return so
 
 
-def lib():
+BASELINE_FLAGS = "-O3 -march=native -ffp-contract=fast -fopenmp"
+
+
+def build_baseline():
+    """Compile the CPU-baseline build of the same source (-O3 -march=native; `make baseline`) ON THIS MACHINE, into a directory keyed
+    by the CPU's feature flags (so a library built for another machine is never loaded), and return its path."""
+    import hashlib
+    try:
+        flags = next(ln for ln in open("/proc/cpuinfo") if ln.startswith("flags"))
+    except (OSError, StopIteration):
+        flags = "unknown"
+    key = hashlib.sha1(flags.encode()).hexdigest()[:12]
+    so = os.path.join(_HERE, "_baseline", key, "liboracle_baseline.so")
+    src_m = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("oracle.c", "oracle.h", "Makefile"))
+    if not os.path.exists(so) or os.path.getmtime(so) < src_m:
+        subprocess.check_call(["make", "-C", _HERE, "-s", "baseline", f"BASELINE=_baseline/{key}/liboracle_baseline.so"],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return so
+
+
+def use_baseline_build():
+    """Switch this module to the -O3 -march=native build (bench.py's CPU legs only; the tests keep the parity build)."""
+    global _LIB
+    _LIB = None
+    lib(build_baseline())
+    return BASELINE_FLAGS
+
+
+def lib(path=None):
     global _LIB
     if _LIB is None:
-        L = C.CDLL(build())
+        L = C.CDLL(path or build())
         L.orc_family_eval.restype = C.c_double
         L.orc_family_eval.argtypes = [C.c_int, C.c_int, _dp, _dp]
         L.orc_family_nparam.restype = C.c_int

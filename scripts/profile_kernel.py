@@ -16,10 +16,16 @@ for rep in range(reps):
     if kind == "hcub":
         fam, nprob = sys.argv[2], int(sys.argv[3]); d = int(sys.argv[4]) if len(sys.argv) > 4 else 4
         par = torch.from_numpy(np.ascontiguousarray(WL.genz_params(fam, d, nprob).T)).cuda()
-        oI = torch.empty(nprob, dtype=torch.float64, device="cuda")
-        eng.hcubature_batch(F[fam], d, np.zeros(d), np.ones(d), par, reltol=1e-6, abstol=1e-8, maxevals=MAXEV, out_I=oI, mode=int(os.environ.get("PK_MODE", "0")),
-                            out_E=torch.empty_like(oI), out_nevals=torch.empty(nprob, dtype=torch.int64, device="cuda"),
-                            out_status=torch.empty(nprob, dtype=torch.int32, device="cuda"))
+        oI = torch.empty(nprob, dtype=torch.float64, device="cuda"); oN = torch.empty(nprob, dtype=torch.int64, device="cuda")
+        mode = int(os.environ.get("PK_MODE", "0"))
+        eng.hcubature_batch(F[fam], d, np.zeros(d), np.ones(d), par, reltol=1e-6, abstol=1e-8, maxevals=MAXEV, out_I=oI, mode=mode,
+                            out_E=torch.empty_like(oI), out_nevals=oN, out_status=torch.empty(nprob, dtype=torch.int32, device="cuda"))
+        eng.synchronize()
+        # the work of this launch, for scripts/executed_fp64.py (executed FP64 instructions per integrand evaluation)
+        os.makedirs("gpurun_out", exist_ok=True)
+        import json
+        json.dump({"kind": "hcub", "family": fam, "dim": d, "nprob": nprob, "mode": mode, "maxevals": MAXEV, "evals": int(oN.sum().item()),
+                   "kernel_ms": eng.last_kernel_ms}, open(f"gpurun_out/pk_hcub_{fam}_{nprob}_m{mode}.json", "w"))
     elif kind == "quadgk":
         n = int(sys.argv[2]); par = torch.from_numpy(np.ascontiguousarray(WL.c1_params(n).T)).cuda()
         oI = torch.empty(n, dtype=torch.float64, device="cuda")
