@@ -91,82 +91,69 @@ __device__ __forceinline__ void block_reduce3(double &v0, double &v1, double &v2
     }
 }
 
-// evaluate: one warp per todo box; Genz-Malik rule in two phases (per-axis term tables, then the points over the lanes)
+// ---- the Genz-Malik rule on ONE box by ONE warp, in two phases: per-axis term tables (the 7 abscissae of every axis through the
+//      variable transform and the family's separable term), then the points over the lanes.  Shared by the single-domain evaluation
+//      kernel below and by the warp-per-box variant of the round-based batch driver (hcubature_rb.cuh).
 template <int FAM, int D, bool ALLFIN>
-__global__ void __launch_bounds__(kBlock)
-eval_kernel(Params p) {
+struct WarpRule {
     using F = ib::Family<FAM, D>;
-    constexpr int NP = hc::gm_npoints(D);
-    constexpr int NAX = 1 + 4 * D;
-    constexpr int NPAR = ib::fam_nparam(FAM, D);
-    constexpr int RECW = 2 * D + 2;
-    const State *st = p.st;
-    if (st->done) return;
-    __shared__ double s_par[NPAR + 3 * D];
-    __shared__ double s_w[10];
-    __shared__ unsigned s_pt[NP];
-    constexpr bool FUSE = F::kProd && !ALLFIN;      // product families: one table of T_k * J_k (finish is the identity)
-    constexpr bool SEPJ = !ALLFIN && !FUSE;         // sum families on infinite axes: separate Jacobian table
-    constexpr int DL = D / 2, DH = D - DL, NL = 1 << DL, NH = 1 << DH, NCORN = 1 << D;
-    __shared__ double s_stage[kWarps][14 * D + 14 * D + NAX + D + 2 * D + 2 * (NL + NH)];
-    __shared__ double s_red[3 * kWarps];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    double *par = s_par, *lbs = s_par + NPAR, *ubs = lbs + D, *dens = ubs + D;
-    for (int t = threadIdx.x; t < NPAR; t += kBlock) par[t] = p.par[t];
-    for (int k = threadIdx.x; k < D; k += kBlock) { lbs[k] = p.lb[k]; ubs[k] = p.ub[k]; dens[k] = (p.ub[k] - p.lb[k]) * 0.5; }
-    const double l2 = sqrt(9.0 / 70.0), l3 = sqrt(9.0 / 10.0), l5 = sqrt(9.0 / 19.0);
-    if (threadIdx.x == 0) {
-        const double twon = (double)(1 << D);
-        s_w[0] = twon * ((12824 - 9120 * D + 400 * D * D) / 19683.0); s_w[1] = twon * (980 / 6561.0);
-        s_w[2] = twon * ((1820 - 400 * D) / 19683.0); s_w[3] = twon * (200 / 19683.0); s_w[4] = 6859 / 19683.0;
-        s_w[5] = twon * ((729 - 950 * D + 50 * D * D) / 729.0); s_w[6] = twon * (245 / 486.0);
-        s_w[7] = twon * ((265 - 100 * D) / 1458.0); s_w[8] = twon * (25 / 729.0); s_w[9] = 0.0;
-    }
-    for (int q = threadIdx.x; q < NP; q += kBlock) {       // point table: 3 bits per axis (abscissa id), class in bits 24-26
-        unsigned e = 0, cls = 0;
-        if (q == 0) cls = 0;
-        else if (q < 1 + 2 * D) { const int r = q - 1; cls = 1; e = (1u + (r & 1)) << (3 * (r >> 1)); }
-        else if (q < 1 + 4 * D) { const int r = q - 1 - 2 * D; cls = 2; e = (3u + (r & 1)) << (3 * (r >> 1)); }
-        else if (q < 1 + 4 * D + 2 * D * (D - 1)) {
-            int r = q - 1 - 4 * D; const int s = r & 3; r >>= 2;
-            int i = 0, j = 1;
-            for (int cnt = 0; cnt < r; cnt++) { if (++j == D) { ++i; j = i + 1; } }
-            cls = 3; e = ((3u + ((s >> 1) & 1)) << (3 * i)) | ((3u + (s & 1)) << (3 * j));
-        } else {
-            const unsigned r = q - (1 + 4 * D + 2 * D * (D - 1)); cls = 4;
-            for (int k = 0; k < D; k++) e |= (5u + ((r >> k) & 1u)) << (3 * k);
-        }
-        s_pt[q] = e | (cls << 24);
-    }
-    __syncthreads();
-    double jacc = 1.0;
-    if (ALLFIN) {
-#pragma unroll
-        for (int k = 0; k < D; k++) jacc = (k == 0) ? dens[0] : jacc * dens[k];
-    }
-    const double finit = F::sep_init(par);
-    double *tabT = s_stage[wib], *tabJ = tabT + 14 * D, *fst = tabJ + 14 * D, *hh = fst + NAX, *box = hh + D;
-    double *cornA = box + 2 * D, *cornJ = cornA + (NL + NH);     // half-products of the corner abscissae: [NL low | NH high]
+    static constexpr int NP = hc::gm_npoints(D);
+    static constexpr int NAX = 1 + 4 * D;
+    static constexpr int NPAR = ib::fam_nparam(FAM, D);
+    static constexpr bool FUSE = F::kProd && !ALLFIN;      // product families: one table of T_k * J_k (finish is the identity)
+    static constexpr bool SEPJ = !ALLFIN && !FUSE;         // sum families on infinite axes: separate Jacobian table
+    static constexpr int DL = D / 2, DH = D - DL, NL = 1 << DL, NH = 1 << DH, NCORN = 1 << D;
+    static constexpr int kStage = 14 * D + 14 * D + NAX + D + 2 * D + 2 * (NL + NH);       // doubles of per-warp staging
+    static constexpr int kProb = NPAR + 3 * D;                                              // par | lb | ub | den
 
-    double sumI = 0.0, sumE = 0.0, maxE = 0.0;           // lane 0 accumulates this warp's boxes in todo order
-    const long long ntodo = st->ntodo;
-    const long long nwarps = (long long)gridDim.x * kWarps;
-    for (long long t = ((long long)blockIdx.x * kWarps + wib) * p.world + p.rank; t < ntodo; t += nwarps * p.world) {
-        const unsigned slot = p.todo[t];
-        double *r = p.rec + (size_t)slot * RECW;
-        __syncwarp();
-        if (lane < 2 * D) box[lane] = r[lane];
-        __syncwarp();
+    // rule weights s_w[10] and the point table s_pt[NP] (3 bits per axis = abscissa id, class in bits 24-26): `nthreads` threads cooperate
+    __device__ static void setup_tables(double *s_w, unsigned *s_pt, int tid, int nthreads) {
+        if (tid == 0) {
+            const double twon = (double)(1 << D);
+            s_w[0] = twon * ((12824 - 9120 * D + 400 * D * D) / 19683.0); s_w[1] = twon * (980 / 6561.0);
+            s_w[2] = twon * ((1820 - 400 * D) / 19683.0); s_w[3] = twon * (200 / 19683.0); s_w[4] = 6859 / 19683.0;
+            s_w[5] = twon * ((729 - 950 * D + 50 * D * D) / 729.0); s_w[6] = twon * (245 / 486.0);
+            s_w[7] = twon * ((265 - 100 * D) / 1458.0); s_w[8] = twon * (25 / 729.0); s_w[9] = 0.0;
+        }
+        for (int q = tid; q < NP; q += nthreads) {
+            unsigned e = 0, cls = 0;
+            if (q == 0) cls = 0;
+            else if (q < 1 + 2 * D) { const int r = q - 1; cls = 1; e = (1u + (r & 1)) << (3 * (r >> 1)); }
+            else if (q < 1 + 4 * D) { const int r = q - 1 - 2 * D; cls = 2; e = (3u + (r & 1)) << (3 * (r >> 1)); }
+            else if (q < 1 + 4 * D + 2 * D * (D - 1)) {
+                int r = q - 1 - 4 * D; const int s = r & 3; r >>= 2;
+                int i = 0, j = 1;
+                for (int cnt = 0; cnt < r; cnt++) { if (++j == D) { ++i; j = i + 1; } }
+                cls = 3; e = ((3u + ((s >> 1) & 1)) << (3 * i)) | ((3u + (s & 1)) << (3 * j));
+            } else {
+                const unsigned r = q - (1 + 4 * D + 2 * D * (D - 1)); cls = 4;
+                for (int k = 0; k < D; k++) e |= (5u + ((r >> k) & 1u)) << (3 * k);
+            }
+            s_pt[q] = e | (cls << 24);
+        }
+    }
+
+    // box(stage) = the 2 D doubles a[D], b[D] of the box to evaluate, written by the caller (followed by __syncwarp)
+    __device__ static double *box(double *stage) { return stage + 14 * D + 14 * D + NAX + D; }
+
+    // prob = par[NPAR] | lb[D] | ub[D] | den[D] (shared or global); finit = F::sep_init(par); jacc = prod den (ALLFIN).
+    // Result (integral, error, split axis) valid in LANE 0.
+    __device__ static void eval(const double *prob, int tr, double finit, double jacc, const double *s_w, const unsigned *s_pt,
+                                double *stage, int lane, double &Iv, double &Er, int &kdiv) {
+        const double *par = prob, *lbs = prob + NPAR, *ubs = lbs + D, *dens = ubs + D;
+        const double l2 = sqrt(9.0 / 70.0), l3 = sqrt(9.0 / 10.0), l5 = sqrt(9.0 / 19.0);
+        double *tabT = stage, *tabJ = tabT + 14 * D, *fst = tabJ + 14 * D, *hh = fst + NAX, *bx = hh + D;
+        double *cornA = bx + 2 * D, *cornJ = cornA + (NL + NH);     // half-products of the corner abscissae: [NL low | NH high]
         for (int idx = lane; idx < 7 * D; idx += 32) {                  // phase 1: tables
             const int k = idx / 7, o = idx - 7 * k;
-            const double a = box[k], b = box[D + k];
+            const double a = bx[k], b = bx[D + k];
             const double c = 0.5 * (a + b), h = 0.5 * fabs(b - a);
             const double lam = o == 0 ? 0.0 : (o <= 2 ? l2 : (o <= 4 ? l3 : l5));
             const double dl = h * lam;
             const double tt = o == 0 ? c : ((o & 1) ? c + dl : c - dl);
             double u, jac;
             if (ALLFIN) { u = lbs[k] + (1.0 + tt) * dens[k]; jac = 1.0; }
-            else { ib::AxisMap m; ib::make_axis(lbs[k], ubs[k], m); ib::t2ujac(p.tr, tt, m, u, jac); }
+            else { ib::AxisMap m; ib::make_axis(lbs[k], ubs[k], m); ib::t2ujac(tr, tt, m, u, jac); }
             const double T = F::sep_term(k, u, par);
             tabT[idx] = FUSE ? T * jac : T;
             if (SEPJ) tabJ[idx] = jac;
@@ -218,11 +205,14 @@ eval_kernel(Params p) {
             sP += __shfl_xor_sync(0xffffffffu, sP, off);
         }
         __syncwarp();
+        Iv = 0.0; Er = 0.0; kdiv = 0;
         if (lane == 0) {
             double V = hh[0];
 #pragma unroll
             for (int k = 1; k < D; k++) V *= hh[k];
-            const double Iv = V * sI, Ip = V * sP, Er = fabs(Iv - Ip);
+            Iv = V * sI;
+            const double Ip = V * sP;
+            Er = fabs(Iv - Ip);
             double p10 = 1.0;
 #pragma unroll
             for (int k = 0; k < D; k++) p10 *= 10.0;
@@ -237,6 +227,52 @@ eval_kernel(Params p) {
                 if (delta > deltaf) { kd = k; maxdd = dd; hkd = hh[k]; }
                 else if (fabs(delta) <= deltaf && hh[k] > hkd) { kd = k; hkd = hh[k]; }
             }
+            kdiv = kd;
+        }
+    }
+};
+
+// evaluate: one warp per todo box (WarpRule above)
+template <int FAM, int D, bool ALLFIN>
+__global__ void __launch_bounds__(kBlock)
+eval_kernel(Params p) {
+    using W = WarpRule<FAM, D, ALLFIN>;
+    using F = ib::Family<FAM, D>;
+    constexpr int NPAR = W::NPAR, NP = W::NP;
+    constexpr int RECW = 2 * D + 2;
+    const State *st = p.st;
+    if (st->done) return;
+    __shared__ double s_par[W::kProb];
+    __shared__ double s_w[10];
+    __shared__ unsigned s_pt[NP];
+    __shared__ double s_stage[kWarps][W::kStage];
+    __shared__ double s_red[3 * kWarps];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double *par = s_par, *lbs = s_par + NPAR, *ubs = lbs + D, *dens = ubs + D;
+    for (int t = threadIdx.x; t < NPAR; t += kBlock) par[t] = p.par[t];
+    for (int k = threadIdx.x; k < D; k += kBlock) { lbs[k] = p.lb[k]; ubs[k] = p.ub[k]; dens[k] = (p.ub[k] - p.lb[k]) * 0.5; }
+    W::setup_tables(s_w, s_pt, threadIdx.x, kBlock);
+    __syncthreads();
+    double jacc = 1.0;
+    if (ALLFIN) {
+#pragma unroll
+        for (int k = 0; k < D; k++) jacc = (k == 0) ? dens[0] : jacc * dens[k];
+    }
+    const double finit = F::sep_init(par);
+    double *stage = s_stage[wib], *box = W::box(stage);
+
+    double sumI = 0.0, sumE = 0.0, maxE = 0.0;           // lane 0 accumulates this warp's boxes in todo order
+    const long long ntodo = st->ntodo;
+    const long long nwarps = (long long)gridDim.x * kWarps;
+    for (long long t = ((long long)blockIdx.x * kWarps + wib) * p.world + p.rank; t < ntodo; t += nwarps * p.world) {
+        const unsigned slot = p.todo[t];
+        double *r = p.rec + (size_t)slot * RECW;
+        __syncwarp();
+        if (lane < 2 * D) box[lane] = r[lane];
+        __syncwarp();
+        double Iv, Er; int kd;
+        W::eval(s_par, p.tr, finit, jacc, s_w, s_pt, stage, lane, Iv, Er, kd);
+        if (lane == 0) {
             r[2 * D] = Iv; r[2 * D + 1] = (double)kd;
             p.err[slot] = Er;
             if (p.world > 1) {                                   // t == rank (mod world): entry t / world of this rank's list

@@ -8,6 +8,6 @@ name=$1; unit=$2; fmad=$3; shift 3
 out=../../build_exp
 mkdir -p $out
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-O2 -Xptxas -v -fmad=$fmad "$@" -c $unit.cu -o $out/${unit}_$name.o 2> $out/${unit}_$name.ptxas.log
-objs=$(ls build/*.o | grep -v "build/$unit.o")
+objs=$(ls ../../gpurun_out/_build/*.o | grep -v "_build/$unit.o")
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $out/lib_$name.so $objs $out/${unit}_$name.o
 echo built $out/lib_$name.so

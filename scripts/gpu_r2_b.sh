@@ -7,10 +7,10 @@ export_rep() {
     ncu -i gpurun_out/$1.ncu-rep --page source --csv > gpurun_out/$1.source.csv 2>/dev/null
     rm -f gpurun_out/$1.ncu-rep
 }
-timeout 900 python -m pytest tests/test_gpu_rounds_batch.py -q --tb=short -s > gpurun_out/r2b_tests.log 2>&1
+timeout 900 python -m pytest tests/test_gpu_rounds_batch.py tests/test_gpu_parity.py -q --tb=short -s -k "rounds or c4_stated or single" > gpurun_out/r2b_tests.log 2>&1
 echo "tests rc=$?" >> gpurun_out/r2b_tests.log
 timeout 600 python scripts/probe_rb.py 262144 1 > gpurun_out/r2b_probe_full.log 2>&1
-for v in minb2 minb4; do
+for v in minb4; do
   IB200_LIB=build_exp/lib_$v.so timeout 300 python scripts/probe_rb.py 65536 1 genz_product_peak,genz_oscillatory,genz_gaussian,genz_c0 > gpurun_out/r2b_probe_$v.log 2>&1
 done
 timeout 300 python scripts/probe_rb.py 65536 1 genz_product_peak,genz_oscillatory,genz_gaussian,genz_c0 > gpurun_out/r2b_probe_minb3.log 2>&1
