@@ -192,8 +192,16 @@ int32_t ib200_hcubature_vec_batch(ib200_ctx *ctx, int32_t family, int32_t dim, i
       of rule applications over all ranks (the analogue of maxiters / points-per-rule); store_boxes: box capacity
       (the same on every rank); 0 = what the budget can create, at most 2^28 boxes (2^26 for an unbounded budget)
       and 70 % of the free HBM (a full store ends the solve with IB200_ST_MAXEVALS).
-      out_stats (may be NULL): int64[6] = integrand evaluations, rule applications, boxes stored, rounds,
-      status (IB200_ST_*), world size. */
+      TWO LEVELS.  A solve whose store reaches `single_switch_boxes` boxes (option, default 2^20) with the error within
+      `single_switch_factor` (default 4096) of the tolerance -- or 16 times that many boxes -- is finished in a second level: every
+      stored box becomes an independent sub-problem with the share eps_i = tol E_i^a / sum_j E_j^a (a = dim / (dim + 6)) of the
+      tolerance, refined by the round-based batch driver (csrc/hcubature_rb.cuh) in per-warp arenas that are re-used from box to box,
+      its boxes summed and dropped when it is done.  Memory is then bounded by the level-1 store however many boxes the integral needs
+      (BASELINE config 5 at reltol 1e-9 needs ~10^11), sum eps_i < tol guarantees HCubature's stopping test for the whole integral, and
+      the sub-problems need no communication: with a communicator the store is dealt to the ranks in chunks of 64 boxes and the chunk
+      sums are gathered once.  The result is the same double on every rank and for every number of ranks.
+      out_stats (may be NULL): int64[8] = integrand evaluations, rule applications, boxes (leaves of the whole refinement), level-1
+      rounds, status (IB200_ST_*), world size, level-1 boxes handed to level 2 (0 = single level), 0. */
 int32_t ib200_hcubature_single(ib200_ctx *ctx, int32_t family, int32_t dim, int32_t transform,
                                const double *lb, const double *ub, const double *params, int32_t nparam,
                                double reltol, double abstol, int64_t max_boxes, int64_t store_boxes,

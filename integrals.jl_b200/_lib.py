@@ -371,12 +371,12 @@ class Engine:
         Returns (I, E, stats dict)."""
         lb = np.ascontiguousarray(lb, dtype=np.float64); ub = np.ascontiguousarray(ub, dtype=np.float64)
         params = np.ascontiguousarray(np.ravel(params), dtype=np.float64)
-        I = C.c_double(); E = C.c_double(); st = np.zeros(6, dtype=np.int64)
+        I = C.c_double(); E = C.c_double(); st = np.zeros(8, dtype=np.int64)
         self._check(self.L.ib200_hcubature_single(self.h, family, dim, transform, lb.ctypes.data, ub.ctypes.data, params.ctypes.data,
                                                   params.size, float(reltol), float(abstol), int(max_boxes), int(store_boxes),
                                                   C.byref(I), C.byref(E), st.ctypes.data))
         return I.value, E.value, dict(nevals=int(st[0]), rule_applications=int(st[1]), boxes=int(st[2]), rounds=int(st[3]),
-                                      status=int(st[4]), world=int(st[5]))
+                                      status=int(st[4]), world=int(st[5]), level2_subproblems=int(st[6]))
 
     # ---- BatchIntegralFunction bridge: caller-evaluated integrand ----------------------------------
     def batch_open(self, dim, lb, ub, reltol=1e-8, abstol=1e-8, max_boxes=1 << 20, store_boxes=0, transform=0):

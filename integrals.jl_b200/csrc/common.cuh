@@ -14,6 +14,7 @@
 enum ScratchSlot { SL_IN0 = 0, SL_IN1, SL_IN2, SL_IN3, SL_IN4, SL_IN5, SL_OUT0, SL_OUT1, SL_OUT2, SL_OUT3,
                    SL_WORK0, SL_WORK1, SL_WORK2, SL_WORK3, SL_WORK4, SL_WORK5,
                    SL_STORE0, SL_STORE1,     // hcub_single.cu box store: exported to the peer ranks (CUDA IPC), never shared with other calls
+                   SL_ARENA0, SL_ARENA1, SL_ARENA2,   // hcubature_rb.cuh per-warp arenas of the level-2 sub-problems of ib200_hcubature_single
                    SL_COUNT };
 
 struct ib200_ctx {
@@ -37,6 +38,9 @@ struct ib200_ctx {
     int64_t opt_adaptive_warps_per_sm = 0;   // 0 = kernel default
     int64_t opt_hcub_lpt = 1;                // pair-mode HCubature: pilot pass + longest-expected-first ordering
     double opt_single_round_fraction = 0.5;  // hcub_single.cu: share of the stored boxes one round may bisect
+    int64_t opt_single_switch_boxes = 1 << 20;   // hcub_single.cu: level-1 store size at which a solve goes two-level (0 = never)
+    int64_t opt_single_switch_factor = 4096;     // ... provided the error is within this factor of the tolerance (or the store is 16x that size)
+    int64_t opt_single_arena_mib = 0;            // device memory for the level-2 arenas, MiB (0 = 70 % of what is free)
     int64_t opt_hcub_capacity = 0;           // boxes per in-flight problem, 0 = derive from maxevals
     int64_t opt_sampled_slabs = 0;           // 0 = auto
     int64_t opt_quadgk_mode = 0;             // 0 = auto, 1 = warp per problem, 2 = pair mode (thread per segment)

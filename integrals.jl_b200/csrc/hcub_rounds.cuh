@@ -49,7 +49,12 @@ struct Params {
     double *inbox_peer[kMaxWorld]; // the peers' inboxes
     long long obcap;
     int grid;
+    // two-level solve (hcub_single.cu): hand the store over to the batched sub-problem driver once it holds >= switch_boxes boxes
+    // and the error is within switch_factor of the tolerance (or it holds 16 x switch_boxes boxes); 0 = single level
+    long long switch_boxes = 0;
+    double switch_factor = 0.0;
 };
+constexpr int kStatusHandover = 4;            // internal: level 1 ended by the hand-over rule (never returned to the caller)
 
 // ---- kernels ---------------------------------------------------------------------------------------
 // the initial box: the whole transformed domain (identical on every rank)
@@ -412,6 +417,9 @@ decide_kernel(Params p) {
     if (E <= tol) { st->done = 1; st->status = IB200_ST_CONVERGED; return; }
     if (!isfinite(E)) { st->done = 1; st->status = IB200_ST_NONFINITE; return; }
     if (ap >= (double)p.max_boxes || full > 0.0) { st->done = 1; st->status = IB200_ST_MAXEVALS; return; }
+    if (p.switch_boxes > 0 && nb >= (double)p.switch_boxes && (E <= p.switch_factor * tol || nb >= 16.0 * (double)p.switch_boxes)) {
+        st->done = 1; st->status = kStatusHandover; return;
+    }
     st->bound = fmax(mx, st->theta);          // boxes left unsplit by the previous round are below its threshold
     double theta = 0.5 * st->bound;
     // The three scans below are written for all kBins bins (oracle: orc_hcubature_rounds); empty bins change no sum, so
@@ -602,5 +610,60 @@ resum_finish_kernel(Params p, double *out /* I, E, applied, boxes, rounds, statu
     }
 }
 
+// ---- two-level solve: the weights of the level-1 boxes, sum_i err_i^alpha, in a fixed order (chunks of the store per block, block
+//      partials folded by one block): the same double on every rank
+static __global__ void __launch_bounds__(kBlock)
+powsum_kernel(Params p, double alpha) {
+    __shared__ double s_red[3 * kWarps];
+    const long long n = p.st->nbox;
+    const long long chunk = (n + gridDim.x - 1) / gridDim.x;
+    const long long lo = (long long)blockIdx.x * chunk, hi = (lo + chunk < n) ? lo + chunk : n;
+    double s = 0.0, d1 = 0.0, d2 = 0.0;
+    for (long long i = lo + threadIdx.x; i < hi; i += kBlock) s += pow(p.err[i], alpha);
+    block_reduce3(s, d1, d2, s_red);
+    if (threadIdx.x == 0) p.partial[(size_t)blockIdx.x * 4] = s;
+}
+static __global__ void __launch_bounds__(kFin)
+powsum_finish_kernel(Params p, double *out) {
+    __shared__ double sh[96];
+    double s = 0.0, d1 = 0.0, d2 = 0.0;
+    for (int b = threadIdx.x; b < p.grid; b += kFin) s += p.partial[4 * b];
+    fin_reduce3(s, d1, d2, sh);
+    if (threadIdx.x == 0) out[0] = s;
+}
+// level-2 results -> per-chunk sums.  A chunk = kSubChunk consecutive boxes of the level-1 store, solved on ONE rank (chunk c on rank
+// c mod world), summed by one warp in a fixed order: the chunk sums, and so the final result, do not depend on the number of ranks.
+constexpr int kSubChunk = 64;
+static __global__ void __launch_bounds__(kBlock)
+chunk_sum_kernel(const double *sub_out /* [nlocal][4] */, long long nchunk_local, double *chunk_out /* [nchunk_local][4] */) {
+    const int lane = threadIdx.x & 31;
+    const long long c = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
+    if (c >= nchunk_local) return;
+    const double *o = sub_out + (size_t)c * kSubChunk * 4;
+    double sI = 0.0, sE = 0.0, sA = 0.0, mS = 0.0;
+    for (int j = lane; j < kSubChunk; j += 32) { sI += o[4 * j]; sE += o[4 * j + 1]; sA += o[4 * j + 2]; mS = fmax(mS, o[4 * j + 3]); }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        sI += __shfl_xor_sync(0xffffffffu, sI, off); sE += __shfl_xor_sync(0xffffffffu, sE, off);
+        sA += __shfl_xor_sync(0xffffffffu, sA, off); mS = fmax(mS, __shfl_xor_sync(0xffffffffu, mS, off));
+    }
+    if (lane == 0) { double *q = chunk_out + (size_t)c * 4; q[0] = sI; q[1] = sE; q[2] = sA; q[3] = mS; }
+}
+// all chunks in chunk order (chunk c sits at [c % world][c / world] of the gathered buffer), one block, fixed shape
+static __global__ void __launch_bounds__(kFin)
+chunk_total_kernel(const double *gathered, long long nchunk, long long nchunk_local, int world, double *out /* I, E, applications, status */) {
+    __shared__ double sh[96];
+    __shared__ double sh2[96];
+    const long long per = (nchunk + kFin - 1) / kFin;                        // consecutive chunks per thread
+    const long long lo = (long long)threadIdx.x * per, hi = (lo + per < nchunk) ? lo + per : nchunk;
+    double sI = 0.0, sE = 0.0, sA = 0.0, mS = 0.0, d = 0.0;
+    for (long long c = lo; c < hi; c++) {
+        const double *q = gathered + ((size_t)(c % world) * nchunk_local + (size_t)(c / world)) * 4;
+        sI += q[0]; sE += q[1]; sA += q[2]; mS = fmax(mS, q[3]);
+    }
+    fin_reduce3(sI, sE, mS, sh);
+    fin_reduce3(sA, d, d, sh2);
+    if (threadIdx.x == 0) { out[0] = sI; out[1] = sE; out[2] = sA; out[3] = mS; }
+}
 
 }  // namespace hs

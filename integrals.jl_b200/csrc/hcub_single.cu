@@ -51,8 +51,19 @@
 // both error estimates below it (tests/test_gpu_parity.py, oracle: orc_hcubature_rounds, which restates
 // this round scheme on the CPU and refines identically).
 #include "hcub_rounds.cuh"
+#include "hcubature_rb.cuh"
 #include <dlfcn.h>
 #include <vector>
+
+namespace hb {
+template <> int32_t launch<2>(ib200_ctx *, int, bool, Params &);
+template <> int32_t launch<3>(ib200_ctx *, int, bool, Params &);
+template <> int32_t launch<4>(ib200_ctx *, int, bool, Params &);
+template <> int32_t launch<5>(ib200_ctx *, int, bool, Params &);
+template <> int32_t launch<6>(ib200_ctx *, int, bool, Params &);
+template <> int32_t launch<7>(ib200_ctx *, int, bool, Params &);
+template <> int32_t launch<8>(ib200_ctx *, int, bool, Params &);
+}
 
 namespace hs {
 
@@ -267,6 +278,96 @@ static int32_t hs_run(ib200_ctx *ctx, hs::Params &p, double *out6_host) {
     return IB200_OK;
 }
 
+// ---- level 2 of the two-level solve ---------------------------------------------------------------------------------
+// Level 1 (hs_run) has handed over a store of n evaluated boxes (identical on every rank).  Every box becomes an independent
+// sub-problem with the share eps_i = tol E_i^alpha / sum_j E_j^alpha of the tolerance, refined by the round-based batch driver
+// (hcubature_rb.cuh) in per-warp arenas that are reused from box to box, so memory stays bounded however many boxes the integral
+// needs.  Chunks of 64 consecutive boxes are dealt to the ranks round-robin; there is NO communication until the chunk sums are
+// gathered once (one NCCL all-gather) and added in chunk order -- the same sum on every rank and for every number of ranks.
+// res6 in: level-1 (I, E, applications, boxes, rounds, status); out: the final values, res6[3] = leaf boxes of the whole refinement.
+static int32_t hs_level2(ib200_ctx *ctx, hs::Params &p, int family, int dim, bool allfin, const double *dpar, int nparam,
+                         double rtol, double atol, double *res6, int64_t *nsub_out) {
+    using namespace hs;
+    cudaStream_t s = ctx->stream;
+    const long long n = (long long)res6[3];
+    double rt = rtol;
+    if (rt == 0.0 && atol == 0.0) rt = 1.4901161193847656e-08;
+    const double tol = fmax(rt * fabs(res6[0]), atol) * (1.0 - 0.015625);
+    const double alpha = (double)dim / (double)(dim + 6);        // optimal split of an error budget among sub-problems whose error falls like N^(-6/dim)
+    double *scal = (double *)ctx->get(SL_OUT0, 16 * sizeof(double));
+    if (!scal) return ib200_fail(ctx, IB200_ERR_OOM, "scratch allocation failed");
+    powsum_kernel<<<p.grid, kBlock, 0, s>>>(p, alpha);
+    powsum_finish_kernel<<<1, kFin, 0, s>>>(p, scal);
+    ctx->launches += 2;
+    IB_LAUNCH_CHECK(ctx);
+    double wsum = 0.0;
+    IB_CUDA(ctx, cudaMemcpyAsync(&wsum, scal, sizeof(double), cudaMemcpyDeviceToHost, s));
+    IB_CUDA(ctx, cudaStreamSynchronize(s));
+    if (!(wsum > 0.0)) return ib200_fail(ctx, IB200_ERR_CUDA, "ib200_hcubature_single: level-2 weights are not positive (internal error)");
+
+    const long long nchunk = (n + kSubChunk - 1) / kSubChunk;
+    const long long nchunk_local_max = (nchunk + p.world - 1) / p.world;              // the same on every rank: the gathered buffer is regular
+    const long long nchunk_mine = nchunk > p.rank ? (nchunk - p.rank + p.world - 1) / p.world : 0;
+    hb::Params q;
+    q.params = dpar; q.nparam = nparam; q.nprob = nchunk_mine * kSubChunk; q.lb = p.lb; q.ub = p.ub; q.bpp = 0; q.tr = p.tr;
+    q.rtol = 0.0; q.atol = 0.0; q.initdiv = 1; q.frac = p.frac;
+    const double remaining = (double)p.max_boxes - res6[2];
+    double sub_budget = 8.0 * remaining / (double)n;
+    if (sub_budget < 4096.0) sub_budget = 4096.0;
+    q.max_apps = sub_budget < 1e18 ? (long long)sub_budget : ((long long)1 << 60);
+    size_t fr = 0, tot = 0;
+    IB_CUDA(ctx, cudaMemGetInfo(&fr, &tot));
+    const size_t held = ctx->scratch[SL_ARENA0].cap + ctx->scratch[SL_ARENA1].cap + ctx->scratch[SL_ARENA2].cap;
+    long long mib = ctx->opt_single_arena_mib > 0 ? ctx->opt_single_arena_mib : (long long)(((double)(fr + held) * 0.7) / 1048576.0);
+    if (mib < 16) mib = 16;
+    q.cap = (int)-mib;                                           // launch_impl turns the memory budget into boxes per warp
+    q.rec = q.err = nullptr; q.list = nullptr;
+    q.out_I = q.out_E = nullptr; q.out_nevals = nullptr; q.out_status = nullptr;
+    q.sub_rec = p.rec; q.sub_err = p.err; q.sub_tol = tol; q.sub_wsum = wsum; q.sub_alpha = alpha;
+    q.sub_rank = p.rank; q.sub_world = p.world; q.sub_n = n;
+    double *sub_out = (double *)ctx->get(SL_OUT1, (size_t)(nchunk_local_max * kSubChunk + 1) * 4 * sizeof(double));
+    double *chunks = (double *)ctx->get(SL_OUT2, (size_t)(nchunk_local_max + 1) * 4 * (size_t)(p.world + 1) * sizeof(double));
+    unsigned long long *counter = (unsigned long long *)ctx->get(SL_OUT3, sizeof(unsigned long long));
+    if (!sub_out || !chunks || !counter) return ib200_fail(ctx, IB200_ERR_OOM, "ib200_hcubature_single: level-2 scratch allocation failed");
+    IB_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), s));
+    IB_CUDA(ctx, cudaMemsetAsync(chunks, 0, (size_t)(nchunk_local_max + 1) * 4 * (size_t)(p.world + 1) * sizeof(double), s));
+    q.sub_out = sub_out; q.counter = counter;
+    int32_t rc = IB200_OK;
+    if (q.nprob > 0) {
+        switch (dim) {
+        case 2: rc = hb::launch<2>(ctx, family, allfin, q); break;
+        case 3: rc = hb::launch<3>(ctx, family, allfin, q); break;
+        case 4: rc = hb::launch<4>(ctx, family, allfin, q); break;
+        case 5: rc = hb::launch<5>(ctx, family, allfin, q); break;
+        case 6: rc = hb::launch<6>(ctx, family, allfin, q); break;
+        case 7: rc = hb::launch<7>(ctx, family, allfin, q); break;
+        default: rc = hb::launch<8>(ctx, family, allfin, q); break;
+        }
+        if (rc) return rc;
+        chunk_sum_kernel<<<(unsigned)((nchunk_mine + kWarps - 1) / kWarps), kBlock, 0, s>>>(sub_out, nchunk_mine, chunks);
+        IB_LAUNCH_CHECK(ctx);
+    }
+    // [mine: nchunk_local_max x 4 | gathered: world x nchunk_local_max x 4]
+    double *gathered = chunks + (size_t)(nchunk_local_max + 1) * 4;
+    if (p.world > 1) {
+        const int r = g_nccl.AllGather(chunks, gathered, (size_t)nchunk_local_max * 4, /*ncclDouble*/ 8, (ncclComm_t)ctx->comm, s);
+        if (r != 0) return ib200_fail(ctx, IB200_ERR_NCCL, std::string("ncclAllGather: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"));
+    } else {
+        gathered = chunks;
+    }
+    chunk_total_kernel<<<1, kFin, 0, s>>>(gathered, nchunk, nchunk_local_max, p.world, scal + 4);
+    IB_LAUNCH_CHECK(ctx);
+    double tot4[4] = {0, 0, 0, 0};
+    IB_CUDA(ctx, cudaMemcpyAsync(tot4, scal + 4, 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    IB_CUDA(ctx, cudaStreamSynchronize(s));
+    const double I = tot4[0], E = tot4[1];
+    int status = (int)tot4[3];
+    if (status == IB200_ST_CONVERGED && !(E <= fmax(rt * fabs(I), atol))) status = isfinite(E) ? IB200_ST_MAXEVALS : IB200_ST_NONFINITE;
+    res6[0] = I; res6[1] = E; res6[2] += tot4[2]; res6[3] = (double)n + 0.5 * tot4[2]; res6[5] = (double)status;
+    if (nsub_out) *nsub_out = (int64_t)n;
+    return IB200_OK;
+}
+
 extern "C" int32_t ib200_hcubature_single(ib200_ctx *ctx, int32_t family, int32_t dim, int32_t transform,
                                           const double *lb, const double *ub, const double *params, int32_t nparam,
                                           double reltol, double abstol, int64_t max_boxes, int64_t store_boxes,
@@ -293,6 +394,7 @@ extern "C" int32_t ib200_hcubature_single(ib200_ctx *ctx, int32_t family, int32_
     p.par = dpar.d; p.lb = dlb.d; p.ub = dub.d; p.tr = transform; p.rtol = reltol; p.atol = abstol; p.max_boxes = max_boxes;
     p.rank = ctx->comm ? ctx->comm_rank : 0; p.world = ctx->comm ? ctx->comm_world : 1;
     p.frac = ctx->opt_single_round_fraction;
+    p.switch_boxes = ctx->opt_single_switch_boxes; p.switch_factor = (double)ctx->opt_single_switch_factor;
     IB_REQUIRE(ctx, p.world <= hs::kMaxWorld, "ib200_hcubature_single: at most 8 ranks (one box of GPUs)");
     p.grid = ctx->sm_count * 4;
     if (p.grid > hs::kFin) p.grid = hs::kFin;              // scan_kernel scans the block counts in one block
@@ -369,6 +471,9 @@ extern "C" int32_t ib200_hcubature_single(ib200_ctx *ctx, int32_t family, int32_
     if (rc == IB200_ERR_UNSUPPORTED && ctx->err.empty())
         return ib200_fail(ctx, IB200_ERR_UNSUPPORTED, "ib200_hcubature_single: family/dimension not compiled in");
     if (rc) return rc;
+    int64_t nsub = 0;
+    if ((int)res[5] == hs::kStatusHandover &&
+        (rc = hs_level2(ctx, p, family, dim, allfin, dpar.d, nparam, reltol, abstol, res, &nsub))) return rc;
     ib200_time_end(ctx);
     *out_I = res[0];
     if (out_E) *out_E = res[1];
@@ -380,6 +485,8 @@ extern "C" int32_t ib200_hcubature_single(ib200_ctx *ctx, int32_t family, int32_
         out_stats[3] = (int64_t)res[4];           // refinement rounds
         out_stats[4] = (int64_t)res[5];           // status (IB200_ST_*)
         out_stats[5] = p.world;
+        out_stats[6] = nsub;                      // boxes of the level-1 store handed to level 2 (0: the solve stayed single-level)
+        out_stats[7] = 0;
     }
     return IB200_OK;
 }

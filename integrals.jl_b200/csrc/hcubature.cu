@@ -25,6 +25,9 @@ template <> int32_t launch<2>(ib200_ctx *, int, bool, Params &);
 template <> int32_t launch<3>(ib200_ctx *, int, bool, Params &);
 template <> int32_t launch<4>(ib200_ctx *, int, bool, Params &);
 template <> int32_t launch<5>(ib200_ctx *, int, bool, Params &);
+template <> int32_t launch<6>(ib200_ctx *, int, bool, Params &);
+template <> int32_t launch<7>(ib200_ctx *, int, bool, Params &);
+template <> int32_t launch<8>(ib200_ctx *, int, bool, Params &);
 }
 
 namespace hp {
@@ -58,7 +61,7 @@ extern "C" int32_t ib200_hcubature_batch(ib200_ctx *ctx, int32_t family, int32_t
                                          double *out_I, double *out_E, int64_t *out_nevals, int32_t *out_status) {
     IB_REQUIRE(ctx, ctx != nullptr, "ib200_hcubature_batch: ctx is NULL");
     IB_REQUIRE(ctx, mode == IB200_HCUB_REFERENCE_ORDER || mode == IB200_HCUB_ROUNDS, "ib200_hcubature_batch: mode must be 0 (reference order) or 1 (rounds)");
-    IB_REQUIRE(ctx, mode != IB200_HCUB_ROUNDS || (dim >= 2 && dim <= 5), "ib200_hcubature_batch: the round-based mode is built for 2 <= dim <= 5 (use mode 0)");
+    IB_REQUIRE(ctx, mode != IB200_HCUB_ROUNDS || dim >= 2, "ib200_hcubature_batch: the round-based mode is built for 2 <= dim <= 8 (use mode 0 in 1-D)");
     IB_REQUIRE(ctx, family >= 0 && family < IB200_FAM_COUNT, "ib200_hcubature_batch: unknown integrand family");
     IB_REQUIRE(ctx, transform >= 0 && transform <= 2, "ib200_hcubature_batch: unknown transform id");
     IB_REQUIRE(ctx, ib::fam_dim_ok(family, dim), "ib200_hcubature_batch: dimension not supported for this family");
@@ -119,6 +122,7 @@ extern "C" int32_t ib200_hcubature_batch(ib200_ctx *ctx, int32_t family, int32_t
         if (rcap < init_boxes + 64) rcap = init_boxes + 64;
         q.cap = (int)((rcap + 127) / 128 * 128);
         q.rec = q.err = nullptr; q.list = nullptr; q.counter = counter;
+        q.sub_rec = q.sub_err = nullptr; q.sub_out = nullptr; q.sub_tol = q.sub_wsum = q.sub_alpha = 0.0; q.sub_rank = 0; q.sub_world = 1;
         q.out_I = oI.d; q.out_E = oE.d; q.out_nevals = oN.d; q.out_status = oS.d;
         ctx->err.clear();
         ib200_time_begin(ctx);
@@ -126,7 +130,10 @@ extern "C" int32_t ib200_hcubature_batch(ib200_ctx *ctx, int32_t family, int32_t
         case 2: rc = hb::launch<2>(ctx, family, allfin, q); break;
         case 3: rc = hb::launch<3>(ctx, family, allfin, q); break;
         case 4: rc = hb::launch<4>(ctx, family, allfin, q); break;
-        default: rc = hb::launch<5>(ctx, family, allfin, q); break;
+        case 5: rc = hb::launch<5>(ctx, family, allfin, q); break;
+        case 6: rc = hb::launch<6>(ctx, family, allfin, q); break;
+        case 7: rc = hb::launch<7>(ctx, family, allfin, q); break;
+        default: rc = hb::launch<8>(ctx, family, allfin, q); break;
         }
         if (rc) return rc;
         ib200_time_end(ctx);

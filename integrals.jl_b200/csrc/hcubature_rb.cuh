@@ -1,4 +1,5 @@
-// hcubature_rb.cuh -- batched adaptive Genz-Malik cubature, ROUND-BASED driver (ib200_hcubature_batch, mode 1).
+// hcubature_rb.cuh -- batched adaptive Genz-Malik cubature, ROUND-BASED driver (ib200_hcubature_batch, mode 1; and the second
+// level of ib200_hcubature_single).
 //
 // Same call as the other two drivers: HCubature.hcubature(f, lb, ub; rtol, atol, maxevals, initdiv) as called at
 // src/Integrals.jl:380-393 under the automatic ChangeOfVariables (src/common.jl:97-103), for a batch of problems.
@@ -6,42 +7,51 @@
 // steps per 4-D problem, which is what bounds the reference-order drivers hcubature_pair.cuh / hcubature_impl.cuh).
 // Here a problem is refined in ROUNDS, the scheme of ib200_hcubature_single (csrc/hcub_single.cu) applied per problem:
 //
-//   round:  evaluate   the rule on every box created by the previous round -- one THREAD per box, 32 boxes per pass
+//   round:  evaluate   the rule on every box created by the previous round -- 2 <= dim <= 5: one THREAD per box, 32 boxes
+//                      per pass (hcubature_pair.cuh gm_rule_thread); dim >= 6: one box at a time by the whole WARP, the
+//                      2^d + 2 d^2 + 2 d + 1 points over the lanes (hcub_rounds.cuh WarpRule)
 //           test       E <= max(rtol*|I|, atol) (HCubature's test) / budget of rule applications / non-finite
 //           threshold  theta = min(half the largest error seen, theta_h): theta_h comes from the histogram of the
 //                      error estimates by binary exponent (2048 integer bins in shared memory, kept up to date
-//                      incrementally) -- every box outside the longest ascending-error prefix whose errors sum to <= tol
-//                      is bisected by the reference's worst-first loop too; the budget and the per-round share of the
-//                      store (hcub_single.cu: rules 2 and 3) cap the set from the other side
+//                      incrementally, with a bitmap of the occupied bins) -- every box outside the longest ascending-error
+//                      prefix whose errors sum to <= tol is bisected by the reference's worst-first loop too; the budget
+//                      and the per-round share of the store (hcub_single.cu: rules 2 and 3) cap the set from the other side
 //           select     one coalesced pass over the error keys of the problem's store: warp ballot + prefix popcount
 //                      compacts the slots with error >= theta into the split list (no atomics, deterministic order)
 //           split      child 0 (upper half along the parent's fourth-difference axis) takes the parent's slot, child 1
 //                      is appended at nbox + rank -- fused into the next round's evaluation pass
 //
 // One WARP owns one problem at a time (persistent grid, problems pulled from a global atomic counter); its box store
-// (bounds, integral, error, split axis: SoA) lives in a per-warp arena in HBM that is reused from problem to problem,
+// (records a, b, I, split axis + error keys) lives in a per-warp arena in HBM that is reused from problem to problem,
 // so device memory is sized by residency, not by the batch.  Everything a round needs is in registers / shared
 // memory of that warp; there is no host round trip, no grid-wide synchronisation and no floating-point atomic:
 // a problem's result is bit-identical whatever batch it is solved in.
 //
+// SUB-PROBLEM MODE (Params::sub_rec != nullptr): the "problems" are the boxes of the level-1 store of ONE integral
+// (ib200_hcubature_single, two-level solve).  Box i is refined by the same rounds until ITS error is below ITS share of the
+// tolerance, eps_i = tol * E_i^alpha / sum_j E_j^alpha; its boxes are summed and dropped when it is done.  The store is dealt to
+// the ranks in chunks of 64 consecutive boxes, round-robin; no communication.
+//
 // Selection differs from the reference (every box above a threshold instead of the single worst), so evaluation
 // counts differ (measured on BASELINE config 4: +5 .. +19 % evaluations); parity is on (I, E): oracle
-// orc_hcubature_rounds_batch (oracle/oracle.c) restates this scheme and refines identically, and both agree with the
-// reference-order orc_hcubature within the requested tolerance (tests/test_gpu_rounds_batch.py).
+// orc_hcubature_rounds_batch / orc_hcubature_two_level (oracle/oracle.c) restate this scheme and refine identically, and both
+// agree with the reference-order orc_hcubature within the requested tolerance (tests/test_gpu_rounds_batch.py).
 #pragma once
 #include "hcubature_pair.cuh"
+#include "hcub_rounds.cuh"
 
 namespace hb {
 
 constexpr int kWarps = 4;
 constexpr int kBlock = 32 * kWarps;
 constexpr int kBins = 2048;                   // one bin per binary exponent of a double
+constexpr int kMaxThreadDim = 5;              // thread-per-box rule up to this dimension, warp-per-box above
 
 struct Params {
     const double *params; int nparam; int64_t nprob;
     const double *lb, *ub; int bpp, tr;
     double rtol, atol;
-    long long max_apps;         // budget of rule applications: ceil(maxevals / points per rule)
+    long long max_apps;         // budget of rule applications per problem: ceil(maxevals / points per rule)
     int initdiv;
     double frac;                // largest share of a problem's stored boxes bisected in one round
     int cap;                    // boxes per warp arena
@@ -50,6 +60,14 @@ struct Params {
     int *list;                  // [warps][cap]         slots selected for bisection in the current round
     unsigned long long *counter;
     double *out_I, *out_E; int64_t *out_nevals; int32_t *out_status;
+    // sub-problem mode (level 2 of ib200_hcubature_single)
+    const double *sub_rec;      // [n][2D+2] records of the level-1 store (every box evaluated), or nullptr: batch mode
+    const double *sub_err;      // [n]
+    double sub_tol, sub_wsum, sub_alpha;
+    int sub_rank, sub_world;
+    long long sub_n;            // boxes in the level-1 store.  Chunks of hs::kSubChunk consecutive boxes are dealt to the ranks round-robin
+                                // (chunk c -> rank c mod world); nprob = this rank's chunks x kSubChunk
+    double *sub_out;            // [nprob][4]: integral, error, rule applications, status of this rank's sub-problems
 };
 
 __device__ __forceinline__ int ebin(double e) { return (int)(((unsigned long long)__double_as_longlong(e) >> 52) & 0x7ffull); }
@@ -68,20 +86,30 @@ __device__ __forceinline__ double wmax(double v) {
     return v;
 }
 
-// per-warp shared memory: hist[kBins] (unsigned) | occ[kBins/32] (bitmap of the occupied bins) | pc = par[NPAR] lbs[D] aux[D] finit jacc
-// (the layout gm_rule_thread reads) | stage[2][D+1][32] double2: the parent records of the current and the next pass (cp.async)
+// shared memory.  Per warp: hist[kBins] (unsigned) | occ[kBins/32] (bitmap of the occupied bins) | problem row | staging.
+//   thread-per-box: row = par[NPAR] lbs[D] aux[D] finit jacc (the layout gm_rule_thread reads); staging = [2][D+1][32] double2, the
+//                   parent records of the current and the next pass (cp.async)
+//   warp-per-box:   row = par[NPAR] lb[D] ub[D] den[D] (WarpRule::kProb); staging = WarpRule::kStage doubles + the parent record
+// Per block (warp-per-box only): the rule's weights and point table.
 template <int FAM, int D> __host__ __device__ constexpr int pc_padded() { return (hp::pc_doubles<FAM, D>() + 1) & ~1; }
-template <int FAM, int D> __host__ __device__ constexpr int row_doubles() {
-    return kBins / 2 + kBins / 64 + pc_padded<FAM, D>() + 2 * (D + 1) * 32 * 2;
+template <int FAM, int D, bool ALLFIN> __host__ __device__ constexpr int row_doubles() {
+    if (D <= kMaxThreadDim) return kBins / 2 + kBins / 64 + pc_padded<FAM, D>() + 2 * (D + 1) * 32 * 2;
+    using W = hs::WarpRule<FAM, D, ALLFIN>;
+    return kBins / 2 + kBins / 64 + ((W::kProb + 1) & ~1) + ((W::kStage + 1) & ~1) + 2 * D + 2;
+}
+template <int D> __host__ __device__ constexpr int block_doubles() {
+    return D <= kMaxThreadDim ? 0 : 10 + (hc::gm_npoints(D) + 1) / 2 + 1;
 }
 
 #ifndef HB_MINB
 #define HB_MINB 3
 #endif
 template <int FAM, int D, bool ALLFIN>
-__global__ void __launch_bounds__(kBlock, HB_MINB)
+__global__ void __launch_bounds__(kBlock, (D <= kMaxThreadDim ? HB_MINB : 4))
 hcub_rb_kernel(const Params p) {
     using F = ib::Family<FAM, D>;
+    using W = hs::WarpRule<FAM, D, ALLFIN>;
+    constexpr bool WB = D > kMaxThreadDim;                // warp per box
     constexpr int NPAR = ib::fam_nparam(FAM, D);
     constexpr int NP = hc::gm_npoints(D);
     constexpr int RECW = 2 * D + 2, NCH = D + 1;          // a record = NCH 16-byte chunks
@@ -90,27 +118,40 @@ hcub_rb_kernel(const Params p) {
     const unsigned full = 0xffffffffu;
     const unsigned lt = (1u << lane) - 1u;
     const int64_t gwarp = (int64_t)blockIdx.x * kWarps + wib;
-    double *row = sm + (size_t)wib * row_doubles<FAM, D>();
+    double *s_w = sm;                                                          // WB: [10]
+    unsigned *s_pt = reinterpret_cast<unsigned *>(sm + 10);                    // WB: [NP]
+    double *row = sm + block_doubles<D>() + (size_t)wib * row_doubles<FAM, D, ALLFIN>();
     unsigned *hist = reinterpret_cast<unsigned *>(row);
     unsigned *occ = reinterpret_cast<unsigned *>(row + kBins / 2);
     double *pc = row + kBins / 2 + kBins / 64;
+    // thread per box
     double2 *stage = reinterpret_cast<double2 *>(pc + pc_padded<FAM, D>());     // [2][NCH][32]
     double *par = pc, *lbs = pc + NPAR, *aux = lbs + D;
+    // warp per box
+    double *wstage = pc + ((W::kProb + 1) & ~1);
+    double *prec = wstage + ((W::kStage + 1) & ~1);                             // [RECW] the parent's record
+    if (WB) {
+        W::setup_tables(s_w, s_pt, threadIdx.x, kBlock);
+        __syncthreads();
+    }
 
     double *rec = p.rec + (size_t)gwarp * p.cap * RECW;
     double *err = p.err + (size_t)gwarp * p.cap;
     int *list = p.list + (size_t)gwarp * p.cap;
-
-    double rtol = p.rtol;
-    const double atol = p.atol;
-    if (rtol == 0.0 && atol == 0.0) rtol = 1.4901161193847656e-08;   // sqrt(eps), HCubature default
+    const bool sub = p.sub_rec != nullptr;
 
     for (;;) {
         unsigned long long pidx = 0;
         if (lane == 0) pidx = atomicAdd(p.counter, 1ULL);
         pidx = __shfl_sync(full, pidx, 0);
         if ((int64_t)pidx >= p.nprob) break;
-        const int64_t prob = (int64_t)pidx;
+        const int64_t prob = sub ? 0 : (int64_t)pidx;                            // parameter column
+        // sub mode: box of the level-1 store -- entry (pidx % chunk) of this rank's chunk number pidx / chunk
+        const int64_t sbox = (((int64_t)pidx / hs::kSubChunk) * p.sub_world + p.sub_rank) * hs::kSubChunk + (int64_t)pidx % hs::kSubChunk;
+        if (sub && sbox >= p.sub_n) {                                            // tail of the last chunk
+            if (lane == 0) { double *o = p.sub_out + (size_t)pidx * 4; o[0] = 0.0; o[1] = 0.0; o[2] = 0.0; o[3] = 0.0; }
+            continue;
+        }
 
         // ---- problem data -> this warp's shared row; empty histogram
         __syncwarp();
@@ -118,66 +159,93 @@ hcub_rb_kernel(const Params p) {
         for (int k = lane; k < D; k += 32) {
             const double l = p.bpp ? p.lb[prob * D + k] : p.lb[k];
             const double u = p.bpp ? p.ub[prob * D + k] : p.ub[k];
-            lbs[k] = l; aux[k] = ALLFIN ? (u - l) * 0.5 : u;
+            if (WB) { lbs[k] = l; lbs[D + k] = u; lbs[2 * D + k] = (u - l) * 0.5; }
+            else { lbs[k] = l; aux[k] = ALLFIN ? (u - l) * 0.5 : u; }
         }
         for (int b = lane; b < kBins; b += 32) hist[b] = 0u;
         for (int b = lane; b < kBins / 32; b += 32) occ[b] = 0u;
         __syncwarp();
-        if (lane == 0) {
-            double jacc = 1.0;
-            if (ALLFIN) {
+        double jacc = 1.0;
+        if (ALLFIN) {
 #pragma unroll
-                for (int k = 0; k < D; k++) jacc = (k == 0) ? aux[0] : jacc * aux[k];
+            for (int k = 0; k < D; k++) { const double den = WB ? lbs[2 * D + k] : aux[k]; jacc = (k == 0) ? den : jacc * den; }
+        }
+        const double finit = F::sep_init(par);
+        if (!WB && lane == 0) { aux[D] = finit; aux[D + 1] = jacc; }
+        __syncwarp();
+
+        double rtol = p.rtol, atol = p.atol;
+        int qtotal = 1;
+        bool degenerate = false;
+        if (sub) {
+            // ---- level 2: this box's share of the tolerance; already below it -> the box stands as it is
+            const double e_i = p.sub_err[sbox];
+            const double eps = p.sub_tol * (pow(e_i, p.sub_alpha) / p.sub_wsum);
+            const double *src = p.sub_rec + (size_t)sbox * RECW;
+            if (!(e_i > eps)) {
+                if (lane == 0) { double *o = p.sub_out + (size_t)pidx * 4; o[0] = src[2 * D]; o[1] = e_i; o[2] = 0.0; o[3] = 0.0; }
+                continue;
             }
-            aux[D] = F::sep_init(par); aux[D + 1] = jacc;
+            rtol = 0.0; atol = eps;
+            // the box is evaluated already: its first round is its own bisection -> the store starts with the two halves
+            if (lane < 2) {
+                double r[RECW];
+#pragma unroll
+                for (int k = 0; k < RECW; k++) r[k] = src[k];
+                const int kd = (int)r[2 * D + 1];
+#pragma unroll
+                for (int k = 0; k < D; k++) if (k == kd) { const double w = (r[D + k] - r[k]) * 0.5; if (lane == 0) r[k] = r[k] + w; else r[D + k] = r[D + k] - w; }
+                r[2 * D] = 0.0; r[2 * D + 1] = 0.0;
+                double2 *dst = reinterpret_cast<double2 *>(rec + (size_t)lane * RECW);
+#pragma unroll
+                for (int q = 0; q < NCH; q++) dst[q] = make_double2(r[2 * q], r[2 * q + 1]);
+            }
+            qtotal = 2;
+        } else {
+            if (rtol == 0.0 && atol == 0.0) rtol = 1.4901161193847656e-08;   // sqrt(eps), HCubature default
+            // ---- initial grid (HCubature initdiv; CartesianIndices order, first index fastest) -> slots 0 .. qtotal-1, unevaluated:
+            //      the evaluation loop below takes them like the children of a split (the rule is instantiated once)
+            double prodD = 1.0;
+            double tl[D], th[D];
+#pragma unroll
+            for (int k = 0; k < D; k++) {
+                tl[k] = -1.0; th[k] = 1.0;
+                if (!ALLFIN) { ib::AxisMap m; ib::make_axis(lbs[k], WB ? lbs[D + k] : aux[k], m); tl[k] = m.tlo; th[k] = m.thi; }
+                qtotal *= p.initdiv;
+                prodD *= (th[k] - tl[k]) / p.initdiv;
+            }
+            degenerate = (prodD == 0.0);
+            if (degenerate) qtotal = 1;                 // HCubature returns after the first box
+            for (int t = lane; t < qtotal; t += 32) {
+                double r[RECW];
+                int q = t;
+#pragma unroll
+                for (int k = 0; k < D; k++) {
+                    const int cidx = q % p.initdiv; q /= p.initdiv;
+                    const double Dl = (th[k] - tl[k]) / p.initdiv;
+                    r[k] = tl[k] + cidx * Dl;
+                    r[D + k] = (cidx == p.initdiv - 1) ? th[k] : r[k] + Dl;
+                }
+                r[2 * D] = 0.0; r[2 * D + 1] = 0.0;
+                double2 *dst = reinterpret_cast<double2 *>(rec + (size_t)t * RECW);
+#pragma unroll
+                for (int q2 = 0; q2 < NCH; q2++) dst[q2] = make_double2(r[2 * q2], r[2 * q2 + 1]);
+            }
         }
         __syncwarp();
 
-        // ---- initial grid (HCubature initdiv; CartesianIndices order, first index fastest) -> slots 0 .. qtotal-1
-        int qtotal = 1;
-        double prodD = 1.0;
-        double tl[D], th[D];
-#pragma unroll
-        for (int k = 0; k < D; k++) {
-            tl[k] = -1.0; th[k] = 1.0;
-            if (!ALLFIN) { ib::AxisMap m; ib::make_axis(lbs[k], aux[k], m); tl[k] = m.tlo; th[k] = m.thi; }
-            qtotal *= p.initdiv;
-            prodD *= (th[k] - tl[k]) / p.initdiv;
-        }
-        const bool degenerate = (prodD == 0.0);
-        if (degenerate) qtotal = 1;                 // HCubature returns after the first box
-
-        int nbox = qtotal, ntodo = qtotal, nbox0 = 0, status = IB200_ST_CONVERGED;
+        int nbox = qtotal, ntodo = qtotal, nsplit = 0, nbox0 = 0, status = IB200_ST_CONVERGED;
         long long applied = 0;
         double I = 0.0, E = 0.0, theta = 0.0, dE = 0.0;
         bool first = true;
 
-        // round 0: the boxes of the initial grid are written to the store unevaluated; the evaluation loop below then takes them
-        // like the children of a split (the same code path, so the rule is instantiated once)
-        for (int t = lane; t < qtotal; t += 32) {
-            double r[RECW];
-            int q = t;
-#pragma unroll
-            for (int k = 0; k < D; k++) {
-                const int cidx = q % p.initdiv; q /= p.initdiv;
-                const double Dl = (th[k] - tl[k]) / p.initdiv;
-                r[k] = tl[k] + cidx * Dl;
-                r[D + k] = (cidx == p.initdiv - 1) ? th[k] : r[k] + Dl;
-            }
-            r[2 * D] = 0.0; r[2 * D + 1] = 0.0;
-            double2 *dst = reinterpret_cast<double2 *>(rec + (size_t)t * RECW);
-#pragma unroll
-            for (int q2 = 0; q2 < NCH; q2++) dst[q2] = make_double2(r[2 * q2], r[2 * q2 + 1]);
-        }
-        __syncwarp();
-
         for (;;) {
-            // ---- evaluate.  Round 0: the boxes of the initial grid (entry t = slot t).  Later rounds: both halves of every selected
-            //      box -- lanes 2r, 2r+1 take the children of list[r].  The records a pass needs are staged into shared memory with
-            //      cp.async while the previous pass is evaluated, and the list entries of the pass after that are in flight behind
-            //      them, so a pass does not wait for HBM (ncu on the first version: long_scoreboard was the top stall).
+            // ---- evaluate.  Round 0: the boxes of the initial store (entry t = slot t).  Later rounds: both halves of every selected box.
             double sI = 0.0, sE = -dE, mx = 0.0;       // this lane's share of the round's new boxes (minus the parents' errors)
-            {
+            if constexpr (!WB) {
+                // thread per box: lanes 2r, 2r+1 take the children of list[r].  The records a pass needs are staged into shared memory
+                // with cp.async while the previous pass is evaluated, and the list entries of the pass after that are in flight behind
+                // them, so a pass does not wait for HBM (ncu on the first version: long_scoreboard was the top stall).
                 const int npass = (ntodo + 31) >> 5;
                 auto entry = [&](int t) { return first ? t : __ldcg(list + (t >> 1)); };
                 auto issue = [&](int src_slot, int buf) {        // record -> stage[buf][chunk][lane]
@@ -230,6 +298,61 @@ hcub_rb_kernel(const Params p) {
                         sI += Ic; sE += Ec; mx = fmax(mx, Ec);       // fmax drops NaN: a non-finite E is caught through sE
                     }
                     par_cur = par_next; par_next = par_next2;
+                }
+            } else {
+                // warp per box: one entry (round 0: a box; later: a parent = two boxes) at a time; the next entry's record is
+                // in flight in a register per lane while the rule runs
+                const int nit = first ? ntodo : nsplit;
+                double *box = W::box(wstage);
+                auto entry = [&](int r0) { return first ? r0 : __ldcg(list + r0); };
+                auto note = [&](double Ec) {                                      // lane 0
+                    const int bn = ebin(Ec);
+                    if (atomicAdd(&hist[bn], 1u) == 0u) atomicOr(&occ[bn >> 5], 1u << (bn & 31));
+                    sE += Ec; mx = fmax(mx, Ec);
+                };
+                int src_cur = nit > 0 ? entry(0) : 0;
+                double pre = (nit > 0 && lane < RECW) ? __ldcg(rec + (size_t)src_cur * RECW + lane) : 0.0;
+                int src_next = nit > 1 ? entry(1) : 0;
+                for (int r0 = 0; r0 < nit; r0++) {
+                    __syncwarp();
+                    if (lane < RECW) prec[lane] = pre;
+                    const int src_next2 = r0 + 2 < nit ? entry(r0 + 2) : 0;
+                    if (r0 + 1 < nit && lane < RECW) pre = __ldcg(rec + (size_t)src_next * RECW + lane);
+                    __syncwarp();
+                    if (first) {
+                        if (lane < 2 * D) box[lane] = prec[lane];
+                        __syncwarp();
+                        double Iv, Er; int kc;
+                        W::eval(pc, p.tr, finit, jacc, s_w, s_pt, wstage, lane, Iv, Er, kc);
+                        if (lane == 0) {
+                            rec[(size_t)src_cur * RECW + 2 * D] = Iv; rec[(size_t)src_cur * RECW + 2 * D + 1] = (double)kc;
+                            err[src_cur] = Er;
+                            sI += Iv; note(Er);
+                        }
+                    } else {
+                        const int kd = (int)prec[2 * D + 1];
+                        const double akd = prec[kd], bkd = prec[D + kd], w = (bkd - akd) * 0.5, Ipar = prec[2 * D];
+                        // child 0 = upper half (a[kd] += w) keeps the parent's slot
+                        if (lane < 2 * D) box[lane] = lane == kd ? akd + w : prec[lane];
+                        __syncwarp();
+                        double I0, E0; int k0;
+                        W::eval(pc, p.tr, finit, jacc, s_w, s_pt, wstage, lane, I0, E0, k0);
+                        __syncwarp();
+                        // child 1 = lower half (b[kd] -= w) is appended
+                        if (lane < 2 * D) box[lane] = lane == D + kd ? bkd - w : prec[lane];
+                        __syncwarp();
+                        double I1, E1; int k1;
+                        W::eval(pc, p.tr, finit, jacc, s_w, s_pt, wstage, lane, I1, E1, k1);
+                        const size_t s1 = (size_t)(nbox0 + r0);
+                        if (lane < 2 * D) rec[s1 * RECW + lane] = box[lane];
+                        if (lane == 0) {
+                            double *r = rec + (size_t)src_cur * RECW;
+                            r[kd] = akd + w; r[2 * D] = I0; r[2 * D + 1] = (double)k0; err[src_cur] = E0;
+                            rec[s1 * RECW + 2 * D] = I1; rec[s1 * RECW + 2 * D + 1] = (double)k1; err[s1] = E1;
+                            sI += (I0 + I1) - Ipar; note(E0); note(E1);
+                        }
+                    }
+                    src_cur = src_next; src_next = src_next2;
                 }
             }
             first = false;
@@ -292,7 +415,7 @@ hcub_rb_kernel(const Params p) {
             }
 
             // ---- select: slots with error >= theta, in store order (8 key loads in flight per lane)
-            int nsplit = 0;
+            nsplit = 0;
             dE = 0.0;
             for (int i0 = 0; i0 < nbox; i0 += 256) {
                 double e[8];
@@ -323,10 +446,15 @@ hcub_rb_kernel(const Params p) {
         for (int s = lane; s < nbox; s += 32) { pI += __ldcg(rec + (size_t)s * RECW + 2 * D); pE += __ldcg(err + s); }
         pI = wsum(pI); pE = wsum(pE);
         if (lane == 0) {
-            p.out_I[prob] = pI;
-            if (p.out_E) p.out_E[prob] = pE;
-            if (p.out_nevals) p.out_nevals[prob] = (int64_t)applied * NP;
-            if (p.out_status) p.out_status[prob] = status;
+            if (sub) {
+                double *o = p.sub_out + (size_t)pidx * 4;
+                o[0] = pI; o[1] = pE; o[2] = (double)applied; o[3] = (double)status;
+            } else {
+                p.out_I[prob] = pI;
+                if (p.out_E) p.out_E[prob] = pE;
+                if (p.out_nevals) p.out_nevals[prob] = (int64_t)applied * NP;
+                if (p.out_status) p.out_status[prob] = status;
+            }
         }
     }
 }
@@ -336,14 +464,16 @@ inline size_t arena_bytes_per_box(int D) { return (size_t)8 * (2 * D + 2) + 8 + 
 template <int D>
 int32_t launch(ib200_ctx *ctx, int family, bool allfin, Params &p);
 
+// Sizes the persistent grid from the kernel's occupancy, carves the per-warp arenas out of the context's scratch and launches.
+// p.cap <= 0: the arena capacity is chosen here -- as many boxes per warp as `-p.cap` bytes of device memory allow (sub-problem mode).
 template <int D>
 int32_t launch_impl(ib200_ctx *ctx, int family, bool allfin, Params &p) {
     int32_t rc = IB200_ERR_UNSUPPORTED;
     ib200_dispatch_family(family, [&](auto famc) {
         constexpr int FAM = decltype(famc)::value;
         if constexpr (ib::fam_dim_ok(FAM, D)) {
-            auto go = [&](auto kern) -> int32_t {
-                const size_t smem = (size_t)kWarps * row_doubles<FAM, D>() * sizeof(double);
+            auto go = [&](auto kern, size_t smem) -> int32_t {
+                if (smem > ctx->smem_optin) return ib200_fail(ctx, IB200_ERR_INVALID, "ib200_hcubature_batch: shared memory of the round-based kernel exceeds the device limit");
                 IB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 int occ = 0;
                 IB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlock, smem));
@@ -354,17 +484,28 @@ int32_t launch_impl(ib200_ctx *ctx, int family, bool allfin, Params &p) {
                 }
                 int64_t blocks = (p.nprob + kWarps - 1) / kWarps;
                 if (blocks > (int64_t)ctx->sm_count * occ) blocks = (int64_t)ctx->sm_count * occ;
-                const size_t warps = (size_t)blocks * kWarps, cap = (size_t)p.cap;
-                p.rec = (double *)ctx->get(SL_WORK2, warps * cap * (2 * D + 2) * sizeof(double));
-                p.err = (double *)ctx->get(SL_WORK4, warps * cap * sizeof(double));
-                p.list = (int *)ctx->get(SL_WORK3, warps * cap * sizeof(int));
+                if (blocks < 1) blocks = 1;
+                const size_t warps = (size_t)blocks * kWarps;
+                if (p.cap <= 0) {
+                    const size_t bytes = (size_t)(-(long long)p.cap) << 20;                  // MiB budget handed in by the caller
+                    long long c = (long long)(bytes / (warps * arena_bytes_per_box(D)));
+                    c = c > (1 << 22) ? (1 << 22) : c;
+                    if (c < 256) return ib200_fail(ctx, IB200_ERR_OOM, "ib200_hcubature_single: no device memory left for the level-2 arenas");
+                    p.cap = (int)(c / 128 * 128);
+                }
+                const size_t cap = (size_t)p.cap;
+                const bool sub = p.sub_rec != nullptr;                                       // level 2 keeps its arenas apart from the level-1 store
+                p.rec = (double *)ctx->get(sub ? SL_ARENA0 : SL_WORK2, warps * cap * (2 * D + 2) * sizeof(double));
+                p.err = (double *)ctx->get(sub ? SL_ARENA1 : SL_WORK4, warps * cap * sizeof(double));
+                p.list = (int *)ctx->get(sub ? SL_ARENA2 : SL_WORK3, warps * cap * sizeof(int));
                 if (!p.rec || !p.err || !p.list)
                     return ib200_fail(ctx, IB200_ERR_OOM, "ib200_hcubature_batch: box arena allocation failed (lower maxiters or the hcub_capacity option)");
                 kern<<<(unsigned)blocks, kBlock, smem, ctx->stream>>>(p);
                 IB_LAUNCH_CHECK(ctx);
                 return IB200_OK;
             };
-            rc = allfin ? go(hcub_rb_kernel<FAM, D, true>) : go(hcub_rb_kernel<FAM, D, false>);
+            rc = allfin ? go(hcub_rb_kernel<FAM, D, true>, (size_t)(block_doubles<D>() + kWarps * row_doubles<FAM, D, true>()) * sizeof(double))
+                        : go(hcub_rb_kernel<FAM, D, false>, (size_t)(block_doubles<D>() + kWarps * row_doubles<FAM, D, false>()) * sizeof(double));
         }
     });
     if (rc == IB200_ERR_UNSUPPORTED && ctx->err.empty())

@@ -159,7 +159,7 @@ end
 function solve_single(cache::IntegralCache, alg::HCubatureB200, domain, p; transform, reltol, abstol, maxiters)
     lb, ub, _, dim = _bounds(domain...)
     npts = 1 + 4dim + 2dim * (dim - 1) + 2^dim
-    I = Ref(0.0); E = Ref(0.0); stats = zeros(Int64, 6); P = collect(Float64, vec(p)); ctx = cache.cacheval
+    I = Ref(0.0); E = Ref(0.0); stats = zeros(Int64, 8); P = collect(Float64, vec(p)); ctx = cache.cacheval
     GC.@preserve lb ub P stats check(ctx, ccall((:ib200_hcubature_single, lib), Int32,
         (Ptr{Cvoid}, Int32, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Float64, Float64, Int64, Int64,
          Ref{Float64}, Ref{Float64}, Ptr{Int64}),
