@@ -136,7 +136,7 @@ int32_t ib200_quadgk_batch(ib200_ctx *ctx, int32_t family, int32_t transform,
         IB200_HCUB_REFERENCE_ORDER  one box per step, largest error first -- the reference's own sequence of boxes
                                     (csrc/hcubature_pair.cuh, hcubature_impl.cuh; 1 <= dim <= 8)
         IB200_HCUB_ROUNDS           every box whose error is above a per-problem threshold is bisected in the same round
-                                    (csrc/hcubature_rb.cuh; 2 <= dim <= 5): same rule, split axis, stopping test and
+                                    (csrc/hcubature_rb.cuh; 2 <= dim <= 8): same rule, split axis, stopping test and
                                     closing sum, a different ORDER of refinement, hence different evaluation counts;
                                     (I, E) agree with mode 0 within the requested tolerance.  maxevals is honoured as a
                                     budget of rule applications, ceil(maxevals / points per rule); the last round may

@@ -242,7 +242,7 @@ class HCubatureB200(AbstractB200Algorithm):
         refinement (batched scalar solves): "reference_order" = one box per step, largest error first -- HCubature's own sequence of
         boxes; "rounds" = every box above a per-problem threshold is bisected in the same round (csrc/hcubature_rb.cuh, 2 <= dim <= 5):
         same rule, split axis, stopping test and closing sum, 5-20 % more evaluations, several times the throughput; "auto" = rounds
-        where they are built, else reference order."""
+        where they are built (dim >= 2), else reference order."""
         if norm not in ("2", "inf"):
             raise ValueError('HCubatureB200 supports norm = "2" or "inf"')
         if refinement not in ("auto", "rounds", "reference_order"):
@@ -408,7 +408,7 @@ def solve_cache(cache):
                                              store_boxes=inner.store_boxes, transform=tr)
         return IntegralSolution(Iv, Ev, prob, inner, retcode_of(inner, stats.get("status", 0), stats.get("nevals", 0), maxiters, slack=2 * npts), None, stats)
     elif isinstance(inner, HCubatureB200):
-        rounds = inner.refinement == "rounds" or (inner.refinement == "auto" and 2 <= dim <= 5)
+        rounds = inner.refinement == "rounds" or (inner.refinement == "auto" and dim >= 2)
         I, E, ne, st = eng.hcubature_batch(fam, dim, lb, ub, p, reltol=reltol, abstol=abstol, maxevals=maxiters,
                                            initdiv=inner.initdiv, transform=tr, mode="rounds" if rounds else "reference_order")
         stats = dict(nevals=ne, status=st, refinement="rounds" if rounds else "reference_order")

@@ -12,7 +12,7 @@ struct HCubatureB200 <: AbstractB200Algorithm                       # like HCuba
     initdiv::Int
     single::Bool            # true: one domain region-partitioned over all GPUs
     norm::Symbol            # :two or :inf -- only used by vector-valued integrands (VectorOf)
-    refinement::Symbol      # :rounds (every box above a per-problem threshold per round; 2 <= dim <= 5), :reference_order (one box
+    refinement::Symbol      # :rounds (every box above a per-problem threshold per round; 2 <= dim <= 8), :reference_order (one box
 end                         # per step, HCubature's own sequence of boxes) or :auto (rounds where they are built)
 HCubatureB200(; initdiv = 1, single = false, norm = :two, refinement = :auto) = HCubatureB200(initdiv, single, norm, refinement)
 struct QuadratureRuleB200{Q} <: AbstractB200Algorithm

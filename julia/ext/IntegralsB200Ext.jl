@@ -87,7 +87,7 @@ function Integrals.__solvebp_call(cache::IntegralCache, alg::HCubatureB200, sens
     P = _mat(p); nprob = size(P, 2)
     I = Vector{Float64}(undef, nprob); E = similar(I); ne = Vector{Int64}(undef, nprob); st = Vector{Int32}(undef, nprob)
     ctx = cache.cacheval
-    rounds = alg.refinement === :rounds || (alg.refinement === :auto && 2 <= dim <= 5)      # IB200_HCUB_ROUNDS is built for 2 <= dim <= 5
+    rounds = alg.refinement === :rounds || (alg.refinement === :auto && 2 <= dim <= 8)      # IB200_HCUB_ROUNDS is built for 2 <= dim <= 8
     GC.@preserve lb ub P I E ne st check(ctx, ccall((:ib200_hcubature_batch, lib), Int32,
         (Ptr{Cvoid}, Int32, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Int32, Ptr{Float64}, Int32, Int64, Float64, Float64, Int64, Int32, Int32,
          Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int32}),

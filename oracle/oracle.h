@@ -139,6 +139,16 @@ int orc_hcubature_rounds(orc_integrand f, void *user, int dim, const double *a, 
 int orc_solve_hcubature_rounds(orc_integrand f, void *user, int dim, const double *lb, const double *ub, int tr,
                                double reltol, double abstol, int64_t max_boxes, int m0,
                                double *I, double *E, int64_t *napplied, int64_t *nboxes, int64_t *rounds);
+/* two-level refinement: rounds until the store holds switch_boxes boxes, then every box as an independent sub-problem with its share of
+   the tolerance (checker for ib200_hcubature_single's second level; see oracle.c) */
+int orc_hcubature_two_level(orc_integrand f, void *user, int dim, const double *a, const double *b,
+                            double rtol, double atol, int64_t max_boxes, int64_t switch_boxes, double switch_factor,
+                            int64_t sub_max_boxes, double alpha,
+                            double *I, double *E, int64_t *napplied, int64_t *nboxes, int64_t *rounds, int64_t *nsub);
+int orc_hcubature_two_level_family(int fam, int dim, const double *lb, const double *ub, int tr, const double *params,
+                                   double reltol, double abstol, int64_t max_boxes, int64_t switch_boxes, double switch_factor,
+                                   int64_t sub_max_boxes, double alpha,
+                                   double *I, double *E, int64_t *napplied, int64_t *nboxes, int64_t *rounds, int64_t *nsub);
 /* the same rounds started from HCubature's initdiv grid with the budget given in evaluations (checker for
    ib200_hcubature_batch, mode IB200_HCUB_ROUNDS; csrc/hcubature_rb.cuh) */
 int orc_hcubature_rounds_init(orc_integrand f, void *user, int dim, const double *a, const double *b,

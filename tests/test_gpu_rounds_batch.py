@@ -49,11 +49,11 @@ def _agree(I, E, st, Ir, Er, str_, reltol, abstol):
 
 
 @pytest.mark.parametrize("family", GENZ)
-@pytest.mark.parametrize("dim", [2, 3, 4, 5])
+@pytest.mark.parametrize("dim", [2, 3, 4, 5, 6, 8])
 def test_rounds_match_their_oracle(eng, O, family, dim):
     """mode 1 against the CPU restatement of the same round scheme: the same refinement (identical evaluation counts) except where
     a decision sits on a rounding-level tie (the kernel forms a point's value from per-axis table entries, with FMA contraction)"""
-    nprob = 24
+    nprob = 24 if dim <= 5 else 12          # dim <= 5: one thread per box; dim >= 6: one warp per box
     par = genz_params(family, dim, nprob, scale=0.25)
     lb, ub = np.zeros(dim), np.ones(dim)
     reltol, abstol, cap = 1e-6, 1e-8, 400000
@@ -119,8 +119,8 @@ def test_rounds_initdiv_infinite_and_degenerate(eng, O):
     I, E, ne, st = eng.hcubature_batch(F["genz_product_peak"], 4, np.zeros(4), np.ones(4), par, reltol=1e-12, abstol=0.0, maxevals=20000, mode="rounds")
     Ir, Er, ner, str_, _ = O.hcubature_rounds_batch("prodpeak", np.zeros(4), np.ones(4), par, reltol=1e-12, abstol=0.0, maxiters=20000)
     assert np.all(st == 1) and np.array_equal(str_, st) and np.all(ne >= 20000) and np.all(np.abs(I - Ir) <= np.minimum(E, Er))
-    with pytest.raises(ib.IB200Error):
-        eng.hcubature_batch(F["genz_gaussian"], 6, np.zeros(6), np.ones(6), genz_params("genz_gaussian", 6, 2), mode="rounds")
+    with pytest.raises(ib.IB200Error):          # 1-D (the Gauss-Kronrod rule) runs in reference order only
+        eng.hcubature_batch(F["genz_gaussian"], 1, np.zeros(1), np.ones(1), genz_params("genz_gaussian", 1, 2), mode="rounds")
 
 
 def test_rounds_result_independent_of_batch(eng):

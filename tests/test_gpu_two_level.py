@@ -1,0 +1,83 @@
+"""ib200_hcubature_single, TWO-LEVEL solves (the level-1 store handed to the batched sub-problem driver): parity with the CPU
+restatement orc_hcubature_two_level (same hand-over, same sub-problems, same shares of the tolerance), agreement with the closed
+form and with the single-level solve, independence of the result from how the sub-problems are scheduled.
+Replaces HCubature.hcubature as called at /root/reference/src/Integrals.jl:386-393 for one expensive integral (BASELINE config 5)."""
+import math
+
+import numpy as np
+import pytest
+
+import integrals_b200 as ib
+import integrals_b200.workloads as WL
+from util_gpu import F, genz_params, genz_exact
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def eng():
+    e = ib.Engine(0)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def O():
+    import oracle
+    return oracle
+
+
+def _two_level(eng, fam, dim, lb, ub, par, reltol, switch_boxes, switch_factor=4096, **kw):
+    eng.set_option("single_switch_boxes", switch_boxes)
+    eng.set_option("single_switch_factor", switch_factor)
+    return eng.hcubature_single(F[fam], dim, lb, ub, par, reltol=reltol, abstol=0.0, max_boxes=1 << 40, **kw)
+
+
+@pytest.mark.parametrize("dim,reltol,switch", [(3, 1e-10, 128), (4, 1e-9, 256), (6, 1e-7, 512)])
+def test_two_level_matches_its_oracle(eng, O, dim, reltol, switch):
+    par = genz_params("genz_gaussian", dim, 3, scale=0.5)[:, 1]
+    lb, ub = np.zeros(dim), np.ones(dim)
+    I, E, s = _two_level(eng, "genz_gaussian", dim, lb, ub, par, reltol, switch)
+    Ir, Er, sr = O.hcubature_two_level("gauss", lb, ub, par, reltol=reltol, abstol=0.0, max_boxes=1 << 40, switch_boxes=switch)
+    assert s["level2_subproblems"] > 0 and s["level2_subproblems"] == sr["level2_subproblems"]       # the same hand-over
+    assert s["status"] == 0 and sr["status"] == 0 and E <= reltol * abs(I)
+    assert abs(I - Ir) <= 1e-11 * abs(Ir) and abs(E - Er) <= 0.02 * Er
+    assert abs(s["rule_applications"] - sr["rule_applications"]) <= 0.02 * sr["rule_applications"]   # identical but for rounding-level ties
+    assert s["nevals"] == s["rule_applications"] * WL.gm_npoints(dim)
+    exact = genz_exact("genz_gaussian", par, dim)
+    assert abs(I - exact) <= 10 * reltol * abs(exact)
+    # single level (no hand-over) reaches the same answer within the tolerance
+    I1, E1, s1 = _two_level(eng, "genz_gaussian", dim, lb, ub, par, reltol, 0)
+    assert s1["level2_subproblems"] == 0 and s1["status"] == 0 and abs(I - I1) <= reltol * abs(I1)
+    assert s["rule_applications"] <= 2.0 * s1["rule_applications"]      # the price of bounded memory: < 2x the rule applications
+
+
+def test_two_level_infinite_axes_8d(eng, O):
+    """BASELINE config 5's integral (8-D Genz Gaussian, two infinite axes) at a tolerance the CPU restatement finishes in seconds"""
+    lb, ub, par, exact = WL.c5_problem()
+    reltol = 1e-3
+    I, E, s = _two_level(eng, "genz_gaussian", 8, lb, ub, par, reltol, 256)
+    Ir, Er, sr = O.hcubature_two_level("gauss", lb, ub, par, reltol=reltol, abstol=0.0, max_boxes=1 << 40, switch_boxes=256)
+    assert s["level2_subproblems"] == sr["level2_subproblems"] > 0 and s["status"] == 0 and sr["status"] == 0
+    assert E <= reltol * abs(I) and abs(I - Ir) <= 1e-10 * abs(Ir) and abs(I - exact) <= reltol * abs(exact)
+    assert abs(s["rule_applications"] - sr["rule_applications"]) <= 0.02 * sr["rule_applications"]
+
+
+def test_two_level_result_independent_of_scheduling(eng):
+    """a sub-problem's result depends on nothing but the sub-problem, and the chunk sums are added in chunk order: fewer resident warps
+    (another assignment of boxes to warps, another arena size) give bitwise the same (I, E)"""
+    par = genz_params("genz_gaussian", 4, 3, scale=0.5)[:, 0]
+    lb, ub = np.zeros(4), np.ones(4)
+    I, E, s = _two_level(eng, "genz_gaussian", 4, lb, ub, par, 1e-9, 256)
+    eng.set_option("adaptive_warps_per_sm", 4)
+    eng.set_option("single_arena_mib", 512)
+    I2, E2, s2 = _two_level(eng, "genz_gaussian", 4, lb, ub, par, 1e-9, 256)
+    assert (I, E, s["rule_applications"], s["boxes"]) == (I2, E2, s2["rule_applications"], s2["boxes"])
+
+
+def test_two_level_budget_and_capacity_are_reported(eng):
+    """a sub-problem that fills its arena ends with status MAXEVALS and the solve says so (never a silent success)"""
+    par = genz_params("genz_gaussian", 4, 3, scale=0.5)[:, 0]
+    eng.set_option("single_arena_mib", 16)          # a few hundred boxes per warp
+    I, E, s = _two_level(eng, "genz_gaussian", 4, np.zeros(4), np.ones(4), par, 1e-13, 64, switch_factor=10 ** 9)
+    assert s["status"] == 1 and s["level2_subproblems"] > 0 and E > 1e-13 * abs(I) and math.isfinite(I)
