@@ -263,8 +263,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     eng = ib.Engine(local)
-    if world > 1 and args.workload == "c5":
-        eng.comm_init_from_torch()                       # the library's own NCCL communicator (one rank per GPU)
+    if world > 1:
+        eng.comm_init_from_torch()                       # the library's own NCCL communicator (one rank per GPU): single-domain solves
     # one explicit stream for torch and the engine, so torch.cuda.Event brackets the engine's kernels
     # (the legacy default stream has handle 0, which ib200_set_stream reads as "the context's own stream")
     bench_stream = torch.cuda.Stream()
@@ -484,18 +484,26 @@ def main():
             return dict(units=by / 1e9, launches=6, bytes=by, h2d=0, d2h=2 * 4 * m, kernel="strided_kernel<float,2,8>")
         return step, step, finish
 
-    def make_c5():
+    def make_c5(reltol=None):
+        """reltol None: the stated tolerance (1e-9) at a fixed budget of rule applications, single level (status 1: a throughput figure).
+        reltol given: the two-level solve run TO that tolerance (status 0: a time-to-tolerance figure)."""
         lb, ub, par, exact = WL.c5_problem()
-        budget = 1 << (args.nprob or 26)                # --nprob overrides log2 of the box budget
+        to_tol = reltol is not None
+        budget = (1 << 40) if to_tol else 1 << (args.nprob or 26)                # --nprob overrides log2 of the box budget
+        rt = reltol if to_tol else WL.C5["reltol"]
         last = {}
 
         def step(record=False):
-            I, E, st = eng.hcubature_single(F["genz_gaussian"], 8, lb, ub, par, reltol=WL.C5["reltol"], abstol=WL.C5["abstol"], max_boxes=budget)
+            eng.set_option("single_switch_boxes", (1 << 20) if to_tol else 0)
+            I, E, st = eng.hcubature_single(F["genz_gaussian"], 8, lb, ub, par, reltol=rt, abstol=WL.C5["abstol"], max_boxes=budget)
+            eng.set_option("single_switch_boxes", 1 << 20)
             last.update(I=I, E=E, **st)
 
         def e2e_step():
+            eng.set_option("single_switch_boxes", (1 << 20) if to_tol else 0)
             sol = ib.solve(ib.IntegralProblem(ib.GenzGaussian(), (lb, ub), par), ib.HCubatureB200(single_domain=True), engine=eng,
-                           reltol=WL.C5["reltol"], abstol=WL.C5["abstol"], maxiters=budget * 401)
+                           reltol=rt, abstol=WL.C5["abstol"], maxiters=min(budget * 401, 1 << 62))
+            eng.set_option("single_switch_boxes", 1 << 20)
             return float(sol.u)
 
         def finish(kernel_ms_total):
@@ -504,7 +512,9 @@ def main():
                         flops=ev * (WL.FAMILY_FLOPS["genz_gaussian"](8) + 2 * 20 + 6 * 4 + 2 * 8 + 1 + 30.0 / 401), h2d=8 * 32, d2h=8 * 8,
                         kernel="hs::eval_kernel<genz_gaussian,8,false> (+ 7 bookkeeping kernels per refinement round)", key="hs_eval/genz_gaussian/8",
                         result=dict(I=last["I"], E=last["E"], rel_E=last["E"] / abs(last["I"]), true_rel_err=abs(last["I"] - exact) / abs(exact),
-                                    rounds=last["rounds"], boxes_stored=last["boxes"], status=last["status"], box_budget=budget))
+                                    reltol=rt, rounds=last["rounds"], boxes=last["boxes"], rule_applications=last["rule_applications"],
+                                    level2_subproblems=last.get("level2_subproblems", 0), status=last["status"],
+                                    box_budget=None if to_tol else budget))
         return step, e2e_step, finish
 
     def make_c4_vec(ncomp=4, dim=3):
@@ -553,6 +563,7 @@ def main():
         return step, step, finish
 
     makers = {"c4": make_c4, "c1": make_c1, "c2": make_c2, "c3": make_c3, "c5": make_c5,
+              "c5_to_tolerance_1e-7": lambda: make_c5(reltol=1e-7),
               "c4_reference_order": lambda: make_c4(hcub_mode="reference_order"),
               # side measurements SURVEY 8(d) asks for next to the configs (reported under "secondary" only)
               "c1_abstol_1e-12": lambda: make_c1(abstol=1e-12), "c2_nonuniform_grid": lambda: make_c2(nonuniform=True),
@@ -560,7 +571,7 @@ def main():
               # "next" rows of SURVEY 8(f), same measurement as their parent config
               "c1_order_15": lambda: make_c1(order=15), "c1_vector_valued_4": make_c1_vec, "c2_float32": make_c2_f32,
               "hcubature_vector_valued_3d_4": make_c4_vec, "batch_bridge_device_integrand_4d": make_bridge}
-    EXTRA_UNITS = {"c4_reference_order": "integrals/s", "c1_abstol_1e-12": "integrals/s", "c2_nonuniform_grid": "GB/s", "c2_contiguous_axis": "GB/s",
+    EXTRA_UNITS = {"c5_to_tolerance_1e-7": "boxes/s", "c4_reference_order": "integrals/s", "c1_abstol_1e-12": "integrals/s", "c2_nonuniform_grid": "GB/s", "c2_contiguous_axis": "GB/s",
                    "c4_reduced_difficulty_h/4": "integrals/s", "c1_order_15": "integrals/s", "c1_vector_valued_4": "integrals/s",
                    "c2_float32": "GB/s", "hcubature_vector_valued_3d_4": "integrals/s", "batch_bridge_device_integrand_4d": "points/s"}
 
@@ -674,7 +685,7 @@ def main():
             if sw == "c4_reference_order" and args.hcub_mode == "reference_order":
                 continue
             try:
-                s = run(sw, 1, 1, with_e2e=False) if sw == "c4_reference_order" else run(sw, 2, 3, with_e2e=False)
+                s = run(sw, 1, 1, with_e2e=False) if sw in ("c4_reference_order", "c5_to_tolerance_1e-7") else run(sw, 2, 3, with_e2e=False)
                 e = {"value": s["value"], "unit": METRIC[sw][1] if sw in METRIC else EXTRA_UNITS[sw], "ms_per_step": s["ms_per_step"]}
                 if "result" in s["info"]:
                     e["result"] = s["info"]["result"]
@@ -707,6 +718,65 @@ def main():
                         "profiles/r02_executed_fp64.json) x this run's evaluations / time -- cannot exceed 1.  fp64_tflops_nominal uses the algorithmic "
                         "counts of SURVEY 8(d) and exceeds the peak where a kernel executes fewer operations than the count assumes (angle addition in "
                         "c3, per-axis factor tables in c4 / c5)")
+        line["secondary"] = sec
+
+    if world > 1 and not args.no_secondary:
+        # every rank takes part; rank 0 reports.  (i) BASELINE config 5 through the library's NCCL communicator -- the single-domain path
+        # that the c4 headline never touches; (ii) strong scaling of the FIXED 6 x 2^18 C4 set through sharding.solve_sharded.
+        sec = {}
+
+        def bits(*vals):
+            t = torch.tensor([float(v) for v in vals], dtype=torch.float64, device="cuda")
+            parts = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(parts, t)
+            return all(torch.equal(parts[0].view(torch.int64), q.view(torch.int64)) for q in parts)
+
+        def c5_entry(name, reltol):
+            try:
+                step, _, finish = makers[name]() if reltol is None else make_c5(reltol=reltol)
+                step(); barrier()
+                t0 = time.perf_counter(); step(); torch.cuda.synchronize()
+                dt = maxrank(time.perf_counter() - t0)
+                info = finish(0.0); res = info["result"]
+                same = bits(res["I"], res["E"], res["rounds"], res["boxes"], res["rule_applications"])
+                e = {"ms": dt * 1e3, "value": res["rule_applications"] / dt, "unit": "boxes/s", "result": res, "identical_on_all_ranks": same}
+                if rank == 0:                                 # the same solve on ONE GPU (a second context without a communicator)
+                    solo = ib.Engine(local)
+                    solo.set_option("single_switch_boxes", (1 << 20) if reltol is not None else 0)
+                    lb5, ub5, par5, _ = WL.c5_problem()
+                    t0 = time.perf_counter()
+                    I1, E1, s1 = solo.hcubature_single(F["genz_gaussian"], 8, lb5, ub5, par5, reltol=res["reltol"], abstol=WL.C5["abstol"],
+                                                       max_boxes=res["box_budget"] or (1 << 40))
+                    e["single_gpu_ms_same_box"] = (time.perf_counter() - t0) * 1e3
+                    e["equals_single_gpu_bit_for_bit"] = (I1 == res["I"] and E1 == res["E"] and s1["rule_applications"] == res["rule_applications"])
+                    solo.close()
+                barrier()
+                return e
+            except Exception as ex:
+                return {"error": str(ex)[:300]}
+        sec["c5_stated_tolerance_fixed_budget"] = c5_entry("c5", None)
+        sec["c5_to_tolerance_1e-7"] = c5_entry("c5_to_tolerance_1e-7", 1e-7)
+        try:
+            from integrals_b200.sharding import solve_sharded
+            c = WL.C4; d = c["dim"]; nper = args.nprob or c["nprob_per_family"]
+            lb4, ub4 = np.zeros(d), np.ones(d)
+            pars = {fam: WL.genz_params(fam, d, nper) for fam in WL.GENZ}              # the SAME fixed set on every rank
+            def strong():
+                tot = 0.0
+                for fam in WL.GENZ:
+                    prob = ib.IntegralProblem(getattr(ib, ib_marker[fam])(), (lb4, ub4), pars[fam])
+                    sol = solve_sharded(prob, ib.HCubatureB200(refinement=args.hcub_mode), interleave=True, engine=eng, reltol=c["reltol"],
+                                        abstol=c["abstol"], maxiters=c["maxiters"])
+                    tot += float(sol.u.sum())
+                return tot
+            strong(); barrier()
+            t0 = time.perf_counter(); chk = strong(); torch.cuda.synchronize()
+            dt = maxrank(time.perf_counter() - t0)
+            sec["c4_strong_scaling_fixed_set"] = {"value": 6 * nper / dt, "unit": "integrals/s", "seconds": dt, "problems": 6 * nper,
+                                                  "same_sums_on_all_ranks": bits(chk),
+                                                  "how": "sharding.solve_sharded(interleave=True): problem k on rank k mod N, host inputs and outputs, one all_gather of the results per family"}
+        except Exception as ex:
+            sec["c4_strong_scaling_fixed_set"] = {"error": str(ex)[:300]}
         line["secondary"] = sec
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

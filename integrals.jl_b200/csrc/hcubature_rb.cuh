@@ -39,6 +39,7 @@
 #pragma once
 #include "hcubature_pair.cuh"
 #include "hcub_rounds.cuh"
+#include "gm_rule_thread2.cuh"
 
 namespace hb {
 
@@ -87,11 +88,11 @@ __device__ __forceinline__ double wmax(double v) {
 }
 
 // shared memory.  Per warp: hist[kBins] (unsigned) | occ[kBins/32] (bitmap of the occupied bins) | problem row | staging.
-//   thread-per-box: row = par[NPAR] lbs[D] aux[D] finit jacc (the layout gm_rule_thread reads); staging = [2][D+1][32] double2, the
+//   thread-per-box: row = par[NPAR] lbs[D] aux[D] finit jacc prep[D] (the layout gm_rule_thread / gm_rule_thread2 read); staging = [2][D+1][32] double2, the
 //                   parent records of the current and the next pass (cp.async)
 //   warp-per-box:   row = par[NPAR] lb[D] ub[D] den[D] (WarpRule::kProb); staging = WarpRule::kStage doubles + the parent record
 // Per block (warp-per-box only): the rule's weights and point table.
-template <int FAM, int D> __host__ __device__ constexpr int pc_padded() { return (hp::pc_doubles<FAM, D>() + 1) & ~1; }
+template <int FAM, int D> __host__ __device__ constexpr int pc_padded() { return (hp::pc_doubles<FAM, D>() + D + 1) & ~1; }   // + prep[D] (gm_rule_thread2.cuh)
 template <int FAM, int D, bool ALLFIN> __host__ __device__ constexpr int row_doubles() {
     if (D <= kMaxThreadDim) return kBins / 2 + kBins / 64 + pc_padded<FAM, D>() + 2 * (D + 1) * 32 * 2;
     using W = hs::WarpRule<FAM, D, ALLFIN>;
@@ -171,7 +172,7 @@ hcub_rb_kernel(const Params p) {
             for (int k = 0; k < D; k++) { const double den = WB ? lbs[2 * D + k] : aux[k]; jacc = (k == 0) ? den : jacc * den; }
         }
         const double finit = F::sep_init(par);
-        if (!WB && lane == 0) { aux[D] = finit; aux[D + 1] = jacc; }
+        if (!WB && lane == 0) { aux[D] = finit; aux[D + 1] = jacc; g2::Prep<FAM, D>::run(par, aux + D + 2); }
         __syncwarp();
 
         double rtol = p.rtol, atol = p.atol;
@@ -284,6 +285,7 @@ hcub_rb_kernel(const Params p) {
                         const int slot = (first || (t & 1) == 0) ? par_cur : nbox0 + (t >> 1);
                         double Ic, Ec; int kc = 0;
                         if constexpr (FAM == IB200_FAM_GENZ_OSC && ALLFIN) hp::gm_rule_thread_osc<D>(pc, a, b, Ic, Ec, kc);
+                        else if constexpr (ALLFIN) g2::gm_rule_thread2<FAM, D>(pc, a, b, Ic, Ec, kc);
                         else hp::gm_rule_thread<FAM, D, ALLFIN>(pc, p.tr, a, b, Ic, Ec, kc);
                         double2 *dst = reinterpret_cast<double2 *>(rec + (size_t)slot * RECW);
                         double r[RECW];

@@ -25,7 +25,7 @@ t0 = time.perf_counter()
 I, E, s = eng.hcubature_single(F["genz_gaussian"], 8, lb, ub, par, reltol=reltol, abstol=0.0, max_boxes=1 << 40)
 torch.cuda.synchronize()
 dt = time.perf_counter() - t0
-res = dict(reltol=reltol, world=world, rank=rank, seconds=dt, kernel_ms=eng.last_kernel_ms, I=I, E=E, rel_E=E / abs(I), true_rel_err=abs(I - exact) / abs(exact),
+res = dict(reltol=reltol, rank=rank, seconds=dt, kernel_ms=eng.last_kernel_ms, I=I, E=E, rel_E=E / abs(I), true_rel_err=abs(I - exact) / abs(exact),
            boxes_per_s=s["rule_applications"] / dt, **s)
 print(json.dumps(res), flush=True)
 if rank == 0:

@@ -38,3 +38,18 @@ def test_b200_arm_has_no_cpu_fallback():
         pytest.skip("a CUDA device is present")
     r = _run("--workload", "c1", "--steps", "1", "--warmup", "1", timeout=180)
     assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
+
+
+def test_reference_arm_uses_all_cores_under_torchrun_too():
+    """torch.distributed.run exports OMP_NUM_THREADS=1 to every rank; the reference arm must still use every core it may run on and the
+    same sample at every N (round-1 verdict: the N > 1 baselines had silently run on one core)"""
+    plain = _run("--impl", "reference", "--workload", "c1", "--steps", "1", "--warmup", "0")
+    env = dict(os.environ, RANK="0", WORLD_SIZE="8", LOCAL_RANK="0", OMP_NUM_THREADS="1")
+    tr = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c1", "--gpus", "8", "--steps", "1", "--warmup", "0"],
+                        capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert plain.returncode == 0 and tr.returncode == 0, tr.stderr[-2000:]
+    a, b = (json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"] for r in (plain, tr))
+    assert a["cores"] == b["cores"] == len(os.sched_getaffinity(0)) and a["sample"] == b["sample"]
+    assert "-O3" in a["build"] and "-march=native" in a["build"]
+    if a["cores"] > 1:
+        assert b["value"] > 0.4 * a["value"]          # really multi-threaded (a one-core run would be ~1 / cores of it)
