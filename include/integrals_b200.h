@@ -95,6 +95,14 @@ int32_t     ib200_set_option(ib200_ctx *ctx, const char *key, int64_t value);
       ("No points to integrate", sampled.jl:55). */
 int32_t ib200_sampled(ib200_ctx *ctx, int32_t rule, const double *y, int64_t inner, int64_t n,
                       int64_t outer, double h, const double *x, double *out);
+/* -- the same rule on a SLAB of the integration axis (one long sampled array spread over several GPUs along the
+      axis that is integrated).  y_slab holds the points offset .. offset + n_slab - 1 of a grid of n_total points ([inner, n_slab, outer]
+      column-major); the weights are those of the whole grid (end corrections only at the global ends; x, if given, is the whole grid of
+      n_total points).  Without a communicator `out` receives this slab's contribution; with one (ib200_comm_init) every rank calls this with
+      its own slab and the contributions are summed over the ranks by ONE all-reduce of inner x outer doubles (NCCL over NVLink), so every
+      rank returns the whole integral.  n_slab == 0 is allowed (a rank without points). */
+int32_t ib200_sampled_slab(ib200_ctx *ctx, int32_t rule, const double *y_slab, int64_t inner, int64_t n_slab, int64_t outer,
+                           int64_t n_total, int64_t offset, double h, const double *x, double *out);
 /* Float32 samples on a Float32 grid ("Float32 type preservation", test/interface_tests.jl:524-539): weights and the
    products w[i]*y[i] in float as in the reference, accumulation in double, result rounded to float.
    Complex samples need no entry point of their own: the weights are real, so a Complex{Float64} array
@@ -201,7 +209,8 @@ int32_t ib200_hcubature_vec_batch(ib200_ctx *ctx, int32_t family, int32_t dim, i
       the sub-problems need no communication: with a communicator the store is dealt to the ranks in chunks of 64 boxes and the chunk
       sums are gathered once.  The result is the same double on every rank and for every number of ranks.
       out_stats (may be NULL): int64[8] = integrand evaluations, rule applications, boxes (leaves of the whole refinement), level-1
-      rounds, status (IB200_ST_*), world size, level-1 boxes handed to level 2 (0 = single level), 0. */
+      rounds, status (IB200_ST_*), world size, level-1 boxes handed to level 2 (0 = single level), level-2 sub-problems of this rank that
+      did not converge (budget / full arena; the split is in ib200_last_error). */
 int32_t ib200_hcubature_single(ib200_ctx *ctx, int32_t family, int32_t dim, int32_t transform,
                                const double *lb, const double *ub, const double *params, int32_t nparam,
                                double reltol, double abstol, int64_t max_boxes, int64_t store_boxes,

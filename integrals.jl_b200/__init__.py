@@ -15,4 +15,4 @@ from .interface import (DomainError, retcode_of, IntegralProblem, IntegralFuncti
                         Range, ReturnCode, CommonKwargError, ChangeOfVariables, transformation_if_inf,
                         transformation_tan_inf, transformation_cot_inf, QuadGKB200, HCubatureB200, QuadratureRuleB200,
                         GaussLegendreB200, TrapezoidalB200, SimpsonsB200, init, solve, solve_cache)
-from .sharding import shard_range, shard_indices, solve_sharded, solve_sampled_sharded
+from .sharding import shard_range, shard_indices, solve_sharded, solve_sampled_sharded, solve_sampled_split_axis

@@ -23,7 +23,7 @@ ERR_NAMES = {-1: "IB200_ERR_INVALID", -2: "IB200_ERR_CUDA", -3: "IB200_ERR_OOM",
 # every symbol include/integrals_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = ["ib200_version", "ib200_create", "ib200_destroy", "ib200_last_error", "ib200_set_stream",
            "ib200_synchronize", "ib200_kernel_launches", "ib200_family_nparam", "ib200_last_kernel_ms",
-           "ib200_set_option", "ib200_sampled", "ib200_sampled_f32", "ib200_fixed_rule_tensor_batch", "ib200_fixed_rule_nodes_batch",
+           "ib200_set_option", "ib200_sampled", "ib200_sampled_slab", "ib200_sampled_f32", "ib200_fixed_rule_tensor_batch", "ib200_fixed_rule_nodes_batch",
            "ib200_gauss_legendre_batch", "ib200_quadgk_batch", "ib200_quadgk_rule_batch", "ib200_quadgk_vec_batch", "ib200_hcubature_batch", "ib200_hcubature_vec_batch", "ib200_measure_fp64_peak",
            "ib200_hcubature_single", "ib200_batch_open", "ib200_batch_next", "ib200_batch_points", "ib200_batch_values",
            "ib200_batch_result", "ib200_comm_unique_id", "ib200_comm_init", "ib200_comm_destroy"]
@@ -62,6 +62,7 @@ def load_library():
     L.ib200_last_kernel_ms.argtypes = [vp]; L.ib200_last_kernel_ms.restype = dp
     L.ib200_set_option.argtypes = [vp, C.c_char_p, i64]; L.ib200_set_option.restype = i32
     L.ib200_sampled.argtypes = [vp, i32, vp, i64, i64, i64, dp, vp, vp]; L.ib200_sampled.restype = i32
+    L.ib200_sampled_slab.argtypes = [vp, i32, vp, i64, i64, i64, i64, i64, dp, vp, vp]; L.ib200_sampled_slab.restype = i32
     L.ib200_fixed_rule_tensor_batch.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp, i32, i64, vp, vp, i32, vp]
     L.ib200_fixed_rule_tensor_batch.restype = i32
     L.ib200_fixed_rule_nodes_batch.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp, i32, i64, vp, vp, i64, vp]
@@ -248,6 +249,16 @@ class Engine:
                                              float(h), xp, op))
         return out
 
+    def sampled_slab(self, rule, y_slab, inner, n_slab, outer, n_total, offset, h=0.0, x=None, out=None):
+        """the points offset .. offset + n_slab - 1 of a grid of n_total points (a slab of the integration axis); with a communicator the
+        slabs' contributions are summed over the ranks (one all-reduce) and every rank gets the whole integral"""
+        y_slab = _f64(y_slab, what="y"); x = _f64(x, what="x")
+        out = self._out(out, max(inner * outer, 1))
+        yp, _k1 = _ptr(y_slab); xp, _k2 = _ptr(x); op, _k3 = _ptr(out)
+        self._check(self.L.ib200_sampled_slab(self.h, RULE_IDS[rule] if isinstance(rule, str) else rule, yp, inner, n_slab, outer,
+                                              int(n_total), int(offset), float(h), xp, op))
+        return out
+
     def sampled(self, rule, y, inner, n, outer, h=0.0, x=None, out=None):
         y = _f64(y); x = _f64(x)
         out = self._out(out, max(inner * outer, 1))
@@ -376,7 +387,8 @@ class Engine:
                                                   params.size, float(reltol), float(abstol), int(max_boxes), int(store_boxes),
                                                   C.byref(I), C.byref(E), st.ctypes.data))
         return I.value, E.value, dict(nevals=int(st[0]), rule_applications=int(st[1]), boxes=int(st[2]), rounds=int(st[3]),
-                                      status=int(st[4]), world=int(st[5]), level2_subproblems=int(st[6]))
+                                      status=int(st[4]), world=int(st[5]), level2_subproblems=int(st[6]), level2_unconverged=int(st[7]),
+                                      note=self.L.ib200_last_error(self.h).decode() if st[7] else "")
 
     # ---- BatchIntegralFunction bridge: caller-evaluated integrand ----------------------------------
     def batch_open(self, dim, lb, ub, reltol=1e-8, abstol=1e-8, max_boxes=1 << 20, store_boxes=0, transform=0):

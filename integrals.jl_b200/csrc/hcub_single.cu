@@ -76,6 +76,7 @@ struct Nccl {
     int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     int (*CommDestroy)(ncclComm_t) = nullptr;
     int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
     bool load(std::string &why) {
         if (h) return true;
@@ -89,6 +90,7 @@ struct Nccl {
         CommInitRank = (decltype(CommInitRank))dlsym(h, "ncclCommInitRank");
         CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
         AllGather = (decltype(AllGather))dlsym(h, "ncclAllGather");
+        AllReduce = (decltype(AllReduce))dlsym(h, "ncclAllReduce");
         GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
         if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllGather) { why = "libnccl is missing expected symbols"; h = nullptr; return false; }
         return true;
@@ -97,6 +99,16 @@ struct Nccl {
 static Nccl g_nccl;
 
 }  // namespace hs
+
+// sum of a device buffer of doubles over the ranks of the context's communicator, in place (sampled.cu: the integration axis split
+// across the ranks, SURVEY 8(e) row 2 -- ONE small all-reduce per solve)
+int32_t ib200_allreduce_sum_f64(ib200_ctx *ctx, double *dbuf, size_t count) {
+    if (!ctx->comm || ctx->comm_world <= 1 || count == 0) return IB200_OK;
+    if (!hs::g_nccl.AllReduce) return ib200_fail(ctx, IB200_ERR_NCCL, "ncclAllReduce not available");
+    const int r = hs::g_nccl.AllReduce(dbuf, dbuf, count, /*ncclDouble*/ 8, /*ncclSum*/ 0, (hs::ncclComm_t)ctx->comm, ctx->stream);
+    if (r != 0) return ib200_fail(ctx, IB200_ERR_NCCL, std::string("ncclAllReduce: ") + (hs::g_nccl.GetErrorString ? hs::g_nccl.GetErrorString(r) : "error"));
+    return IB200_OK;
+}
 
 // ---- peer mappings of the replicated stores -----------------------------------------------------------------
 // Every rank exports its result inbox (scratch slot SL_STORE0, used by nothing else) with CUDA IPC; the
@@ -286,7 +298,7 @@ static int32_t hs_run(ib200_ctx *ctx, hs::Params &p, double *out6_host) {
 // gathered once (one NCCL all-gather) and added in chunk order -- the same sum on every rank and for every number of ranks.
 // res6 in: level-1 (I, E, applications, boxes, rounds, status); out: the final values, res6[3] = leaf boxes of the whole refinement.
 static int32_t hs_level2(ib200_ctx *ctx, hs::Params &p, int family, int dim, bool allfin, const double *dpar, int nparam,
-                         double rtol, double atol, double *res6, int64_t *nsub_out) {
+                         double rtol, double atol, double *res6, int64_t *nsub_out, int64_t *diag_out) {
     using namespace hs;
     cudaStream_t s = ctx->stream;
     const long long n = (long long)res6[3];
@@ -327,9 +339,9 @@ static int32_t hs_level2(ib200_ctx *ctx, hs::Params &p, int family, int dim, boo
     q.sub_rank = p.rank; q.sub_world = p.world; q.sub_n = n;
     double *sub_out = (double *)ctx->get(SL_OUT1, (size_t)(nchunk_local_max * kSubChunk + 1) * 4 * sizeof(double));
     double *chunks = (double *)ctx->get(SL_OUT2, (size_t)(nchunk_local_max + 1) * 4 * (size_t)(p.world + 1) * sizeof(double));
-    unsigned long long *counter = (unsigned long long *)ctx->get(SL_OUT3, sizeof(unsigned long long));
+    unsigned long long *counter = (unsigned long long *)ctx->get(SL_OUT3, 4 * sizeof(unsigned long long));
     if (!sub_out || !chunks || !counter) return ib200_fail(ctx, IB200_ERR_OOM, "ib200_hcubature_single: level-2 scratch allocation failed");
-    IB_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), s));
+    IB_CUDA(ctx, cudaMemsetAsync(counter, 0, 4 * sizeof(unsigned long long), s));
     IB_CUDA(ctx, cudaMemsetAsync(chunks, 0, (size_t)(nchunk_local_max + 1) * 4 * (size_t)(p.world + 1) * sizeof(double), s));
     q.sub_out = sub_out; q.counter = counter;
     int32_t rc = IB200_OK;
@@ -358,8 +370,11 @@ static int32_t hs_level2(ib200_ctx *ctx, hs::Params &p, int family, int dim, boo
     chunk_total_kernel<<<1, kFin, 0, s>>>(gathered, nchunk, nchunk_local_max, p.world, scal + 4);
     IB_LAUNCH_CHECK(ctx);
     double tot4[4] = {0, 0, 0, 0};
+    unsigned long long diag[4] = {0, 0, 0, 0};
     IB_CUDA(ctx, cudaMemcpyAsync(tot4, scal + 4, 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    IB_CUDA(ctx, cudaMemcpyAsync(diag, counter, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     IB_CUDA(ctx, cudaStreamSynchronize(s));
+    if (diag_out) { diag_out[0] = (int64_t)diag[1]; diag_out[1] = (int64_t)diag[2]; diag_out[2] = (int64_t)diag[3]; diag_out[3] = (int64_t)q.cap; }
     const double I = tot4[0], E = tot4[1];
     int status = (int)tot4[3];
     if (status == IB200_ST_CONVERGED && !(E <= fmax(rt * fabs(I), atol))) status = isfinite(E) ? IB200_ST_MAXEVALS : IB200_ST_NONFINITE;
@@ -471,9 +486,12 @@ extern "C" int32_t ib200_hcubature_single(ib200_ctx *ctx, int32_t family, int32_
     if (rc == IB200_ERR_UNSUPPORTED && ctx->err.empty())
         return ib200_fail(ctx, IB200_ERR_UNSUPPORTED, "ib200_hcubature_single: family/dimension not compiled in");
     if (rc) return rc;
-    int64_t nsub = 0;
+    int64_t nsub = 0, diag[4] = {0, 0, 0, 0};
     if ((int)res[5] == hs::kStatusHandover &&
-        (rc = hs_level2(ctx, p, family, dim, allfin, dpar.d, nparam, reltol, abstol, res, &nsub))) return rc;
+        (rc = hs_level2(ctx, p, family, dim, allfin, dpar.d, nparam, reltol, abstol, res, &nsub, diag))) return rc;
+    if (diag[0] + diag[1] + diag[2] > 0)
+        ctx->err = "ib200_hcubature_single: level-2 sub-problems on this rank ended by their budget: " + std::to_string(diag[0]) + ", by a full arena (" +
+                   std::to_string(diag[3]) + " boxes): " + std::to_string(diag[1]) + ", non-finite: " + std::to_string(diag[2]);
     ib200_time_end(ctx);
     *out_I = res[0];
     if (out_E) *out_E = res[1];
@@ -486,7 +504,7 @@ extern "C" int32_t ib200_hcubature_single(ib200_ctx *ctx, int32_t family, int32_
         out_stats[4] = (int64_t)res[5];           // status (IB200_ST_*)
         out_stats[5] = p.world;
         out_stats[6] = nsub;                      // boxes of the level-1 store handed to level 2 (0: the solve stayed single-level)
-        out_stats[7] = 0;
+        out_stats[7] = diag[0] + diag[1] + diag[2];   // level-2 sub-problems of THIS rank that did not converge (why: ib200_last_error)
     }
     return IB200_OK;
 }

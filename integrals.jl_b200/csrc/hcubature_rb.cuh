@@ -59,7 +59,7 @@ struct Params {
     double *rec;                // [warps][cap][2D+2]   a[D], b[D], I, split axis  (16-byte aligned records)
     double *err;                // [warps][cap]         the selection keys, scanned once per round
     int *list;                  // [warps][cap]         slots selected for bisection in the current round
-    unsigned long long *counter;
+    unsigned long long *counter;    // [1] problem counter (+ [3] diagnostics in sub-problem mode)
     double *out_I, *out_E; int64_t *out_nevals; int32_t *out_status;
     // sub-problem mode (level 2 of ib200_hcubature_single)
     const double *sub_rec;      // [n][2D+2] records of the level-1 store (every box evaluated), or nullptr: batch mode
@@ -451,6 +451,9 @@ hcub_rb_kernel(const Params p) {
             if (sub) {
                 double *o = p.sub_out + (size_t)pidx * 4;
                 o[0] = pI; o[1] = pE; o[2] = (double)applied; o[3] = (double)status;
+                // diagnostics behind the counter: sub-problems ended by their budget / by a full arena / non-finite
+                if (status == IB200_ST_MAXEVALS) atomicAdd(p.counter + (applied >= p.max_apps ? 1 : 2), 1ULL);
+                else if (status == IB200_ST_NONFINITE) atomicAdd(p.counter + 3, 1ULL);
             } else {
                 p.out_I[prob] = pI;
                 if (p.out_E) p.out_E[prob] = pE;

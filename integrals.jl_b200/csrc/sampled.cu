@@ -20,10 +20,13 @@ namespace {
 constexpr int kThreads = 256;
 
 // T = element type of the grid: the weights are formed in T arithmetic, as the reference's weight types do
+// (n, x): the WHOLE grid; this launch writes the weights of the points off .. off + cnt - 1 to w[0 .. cnt) (a slab of the
+// integration axis; off = 0, cnt = n for a whole solve)
 template <typename T>
-__global__ void weights_kernel(int rule, int64_t n, T h, const T *__restrict__ x, T *__restrict__ w) {
-    const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // 0-based; formulas below use 1-based i
-    if (i0 >= n) return;
+__global__ void weights_kernel(int rule, int64_t n, T h, const T *__restrict__ x, T *__restrict__ w, int64_t off, int64_t cnt) {
+    const int64_t l0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l0 >= cnt) return;
+    const int64_t i0 = off + l0;                                        // 0-based; formulas below use 1-based i
     const int64_t i = i0 + 1;
     T r;
     if (!x) {
@@ -66,7 +69,7 @@ __global__ void weights_kernel(int rule, int64_t n, T h, const T *__restrict__ x
 #undef B
 #undef E
     }
-    w[i0] = r;
+    w[l0] = r;
 }
 
 __device__ __forceinline__ double2 ldg_stream2(const double *p) {
@@ -212,34 +215,43 @@ __global__ void finish_kernel(const double *__restrict__ partial, T *__restrict_
 
 }  // namespace
 
+// all-reduce (sum) of a device buffer over the ranks of the context's communicator (hcub_single.cu owns the NCCL binding)
+int32_t ib200_allreduce_sum_f64(ib200_ctx *ctx, double *dbuf, size_t count);
+
+// y holds the points off .. off + n - 1 of a grid of n_total points (a slab of the integration axis; the whole grid when
+// off == 0 and n == n_total); x, if given, is the WHOLE grid.
 template <typename T>
 static int32_t sampled_impl(ib200_ctx *ctx, int32_t rule, const T *y, int64_t inner, int64_t n,
-                            int64_t outer, T h, const T *x, T *out) {
+                            int64_t outer, T h, const T *x, T *out, int64_t n_total, int64_t off, bool reduce_ranks) {
     constexpr bool kF64 = sizeof(T) == 8;
     IB_REQUIRE(ctx, ctx != nullptr, "ib200_sampled: ctx is NULL");
     IB_REQUIRE(ctx, rule == IB200_RULE_TRAPEZOID || rule == IB200_RULE_SIMPSON, "ib200_sampled: unknown rule");
     IB_REQUIRE(ctx, inner >= 0 && outer >= 0 && n >= 0, "ib200_sampled: negative extent");
-    IB_REQUIRE(ctx, n != 0, "No points to integrate");                                  // sampled.jl:55,72,106
+    IB_REQUIRE(ctx, n_total != 0, "No points to integrate");                            // sampled.jl:55,72,106
+    IB_REQUIRE(ctx, off >= 0 && off + n <= n_total, "ib200_sampled_slab: the slab does not lie inside the grid");
     if (x) {
         if (rule == IB200_RULE_SIMPSON)
-            IB_REQUIRE(ctx, n > 2, "The length of the grid must exceed 2 for simpsons rule.");  // simpsons.jl:46
+            IB_REQUIRE(ctx, n_total > 2, "The length of the grid must exceed 2 for simpsons rule.");  // simpsons.jl:46
         else
-            IB_REQUIRE(ctx, n >= 2, "ib200_sampled: a non-uniform trapezoid grid needs at least 2 points");
+            IB_REQUIRE(ctx, n_total >= 2, "ib200_sampled: a non-uniform trapezoid grid needs at least 2 points");
     }
     if (inner * outer == 0) return IB200_OK;
-    IB_REQUIRE(ctx, y != nullptr && out != nullptr, "ib200_sampled: y/out is NULL");
+    IB_REQUIRE(ctx, (y != nullptr || n == 0) && out != nullptr, "ib200_sampled: y/out is NULL");
     IB_CUDA(ctx, cudaSetDevice(ctx->device));
 
     DevIn<T> dy, dx; DevOut<T> dout;
     int32_t rc;
     if ((rc = dy.init(ctx, y, (size_t)(inner * n * outer), SL_IN0))) return rc;
-    if ((rc = dx.init(ctx, x, x ? (size_t)n : 0, SL_IN1))) return rc;
+    if ((rc = dx.init(ctx, x, x ? (size_t)n_total : 0, SL_IN1))) return rc;
     if ((rc = dout.init(ctx, out, (size_t)(inner * outer), SL_OUT0))) return rc;
-    T *w = (T *)ctx->get(SL_WORK0, (size_t)n * sizeof(T));
+    T *w = (T *)ctx->get(SL_WORK0, (size_t)(n > 0 ? n : 1) * sizeof(T));
     if (!w) return ib200_fail(ctx, IB200_ERR_OOM, "ib200_sampled: weight scratch allocation failed");
 
     ib200_time_begin(ctx);
-    weights_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(rule, n, h, dx.d, w);
+    if (n == 0) {                                               // an empty slab contributes nothing
+        IB_CUDA(ctx, cudaMemsetAsync(dout.d, 0, (size_t)(inner * outer) * sizeof(T), ctx->stream));
+    } else {
+    weights_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(rule, n_total, h, dx.d, w, off, n);
     IB_LAUNCH_CHECK(ctx);
 
     const int64_t target_ctas = (int64_t)ctx->sm_count * 8;   // 8 x 256-thread CTAs resident per SM
@@ -257,18 +269,22 @@ static int32_t sampled_impl(ib200_ctx *ctx, int32_t rule, const T *y, int64_t in
         if (nslab > (n + min_cols - 1) / min_cols) nslab = (n + min_cols - 1) / min_cols;
         if (nslab < 1) nslab = 1;
         if (nslab > 65535) nslab = 65535;
-        IB_REQUIRE(ctx, outer <= 65535, "ib200_sampled: outer extent > 65535 not supported for inner >= 2");
         const int64_t cols_per_slab = (n + nslab - 1) / nslab;
         nslab = (n + cols_per_slab - 1) / cols_per_slab;
         const bool direct = kF64 && nslab == 1;                 // one slab of doubles: the kernel writes the result itself
         double *partial = direct ? reinterpret_cast<double *>(dout.d)
                                  : (double *)ctx->get(SL_WORK1, (size_t)(outer * nslab * inner) * sizeof(double));
         if (!partial) return ib200_fail(ctx, IB200_ERR_OOM, "ib200_sampled: partial-sum scratch allocation failed");
-        dim3 grid((unsigned)row_tiles, (unsigned)nslab, (unsigned)outer);
         const size_t smem = ty_count > 1 ? (size_t)kThreads * 2 * sizeof(double) : 0;
-        if (vec2) strided_kernel<T, 2, 8><<<grid, kThreads, smem, ctx->stream>>>(dy.d, w, partial, inner, n, tx_count, cols_per_slab);
-        else      strided_kernel<T, 1, 8><<<grid, kThreads, smem, ctx->stream>>>(dy.d, w, partial, inner, n, tx_count, cols_per_slab);
-        IB_LAUNCH_CHECK(ctx);
+        for (int64_t o0 = 0; o0 < outer; o0 += 65535) {          // gridDim.z <= 65535: the outer extent goes in chunks (any shape, like the reference)
+            const int64_t oc = outer - o0 < 65535 ? outer - o0 : 65535;
+            dim3 grid((unsigned)row_tiles, (unsigned)nslab, (unsigned)oc);
+            const T *yc = dy.d + o0 * n * inner;
+            double *pc = partial + o0 * nslab * inner;
+            if (vec2) strided_kernel<T, 2, 8><<<grid, kThreads, smem, ctx->stream>>>(yc, w, pc, inner, n, tx_count, cols_per_slab);
+            else      strided_kernel<T, 1, 8><<<grid, kThreads, smem, ctx->stream>>>(yc, w, pc, inner, n, tx_count, cols_per_slab);
+            IB_LAUNCH_CHECK(ctx);
+        }
         if (!direct) {
             const int64_t total = inner * outer;
             finish_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(partial, dout.d, inner, nslab, total);
@@ -279,7 +295,6 @@ static int32_t sampled_impl(ib200_ctx *ctx, int32_t rule, const T *y, int64_t in
         const int64_t min_cols = 2 * kThreads * 8;
         if (nslab > (n + min_cols - 1) / min_cols) nslab = (n + min_cols - 1) / min_cols;
         if (nslab < 1) nslab = 1;
-        IB_REQUIRE(ctx, outer <= 65535, "ib200_sampled: more than 65535 rows not supported for inner == 1");
         int64_t cols_per_slab = (n + nslab - 1) / nslab;
         cols_per_slab = (cols_per_slab + 1) & ~(int64_t)1;      // even, so slabs stay 16-byte aligned
         nslab = (n + cols_per_slab - 1) / cols_per_slab;
@@ -287,12 +302,22 @@ static int32_t sampled_impl(ib200_ctx *ctx, int32_t rule, const T *y, int64_t in
         const bool direct = kF64 && nslab == 1;
         double *partial = direct ? reinterpret_cast<double *>(dout.d) : (double *)ctx->get(SL_WORK1, (size_t)(outer * nslab) * sizeof(double));
         if (!partial) return ib200_fail(ctx, IB200_ERR_OOM, "ib200_sampled: partial-sum scratch allocation failed");
-        dim3 grid((unsigned)nslab, (unsigned)outer);
-        contiguous_kernel<T, 4><<<grid, kThreads, 0, ctx->stream>>>(dy.d, w, partial, n, cols_per_slab, vec_ok);
-        IB_LAUNCH_CHECK(ctx);
+        for (int64_t o0 = 0; o0 < outer; o0 += 65535) {          // gridDim.y <= 65535: rows in chunks
+            const int64_t oc = outer - o0 < 65535 ? outer - o0 : 65535;
+            dim3 grid((unsigned)nslab, (unsigned)oc);
+            contiguous_kernel<T, 4><<<grid, kThreads, 0, ctx->stream>>>(dy.d + o0 * n, w, partial + o0 * nslab, n, cols_per_slab,
+                                                                       vec_ok && ((o0 * n) % 2 == 0));
+            IB_LAUNCH_CHECK(ctx);
+        }
         if (!direct) {
             finish_kernel<T><<<(unsigned)((outer + 255) / 256), 256, 0, ctx->stream>>>(partial, dout.d, 1, nslab, outer);
             IB_LAUNCH_CHECK(ctx);
+        }
+    }
+    }   // n > 0
+    if (reduce_ranks && ctx->comm) {
+        if constexpr (kF64) {
+            if ((rc = ib200_allreduce_sum_f64(ctx, reinterpret_cast<double *>(dout.d), (size_t)(inner * outer)))) return rc;
         }
     }
     ib200_time_end(ctx);
@@ -303,10 +328,20 @@ static int32_t sampled_impl(ib200_ctx *ctx, int32_t rule, const T *y, int64_t in
 
 extern "C" int32_t ib200_sampled(ib200_ctx *ctx, int32_t rule, const double *y, int64_t inner, int64_t n,
                                  int64_t outer, double h, const double *x, double *out) {
-    return sampled_impl<double>(ctx, rule, y, inner, n, outer, h, x, out);
+    IB_REQUIRE(ctx, ctx != nullptr, "ib200_sampled: ctx is NULL");
+    IB_REQUIRE(ctx, n != 0, "No points to integrate");
+    return sampled_impl<double>(ctx, rule, y, inner, n, outer, h, x, out, n, 0, false);
 }
 
 extern "C" int32_t ib200_sampled_f32(ib200_ctx *ctx, int32_t rule, const float *y, int64_t inner, int64_t n,
                                      int64_t outer, float h, const float *x, float *out) {
-    return sampled_impl<float>(ctx, rule, y, inner, n, outer, h, x, out);
+    IB_REQUIRE(ctx, ctx != nullptr, "ib200_sampled: ctx is NULL");
+    IB_REQUIRE(ctx, n != 0, "No points to integrate");
+    return sampled_impl<float>(ctx, rule, y, inner, n, outer, h, x, out, n, 0, false);
+}
+
+extern "C" int32_t ib200_sampled_slab(ib200_ctx *ctx, int32_t rule, const double *y_slab, int64_t inner, int64_t n_slab,
+                                      int64_t outer, int64_t n_total, int64_t offset, double h, const double *x, double *out) {
+    IB_REQUIRE(ctx, ctx != nullptr, "ib200_sampled_slab: ctx is NULL");
+    return sampled_impl<double>(ctx, rule, y_slab, inner, n_slab, outer, h, x, out, n_total, offset, true);
 }

@@ -96,6 +96,53 @@ def sampled_shard_axis(shape, dim):
     return max(axes, key=lambda k: (shape[k], k))
 
 
+def _engine_slab(engine):
+    """this rank's slab through ib200_sampled_slab (no library communicator: the partials are summed by torch.distributed)"""
+    def local_slab(prob, alg, lo, hi):
+        from . import interface, _lib
+        eng = engine or _lib.default_engine()
+        y = np.asarray(prob.y, dtype=np.float64)
+        sl = [slice(None)] * y.ndim
+        sl[prob.dim] = slice(lo, hi)
+        ys = np.asfortranarray(y[tuple(sl)])
+        shape = y.shape
+        inner = int(np.prod(shape[:prob.dim], dtype=np.int64)); outer = int(np.prod(shape[prob.dim + 1:], dtype=np.int64))
+        x = prob.x
+        h, xs = (x.step, None) if isinstance(x, interface.Range) else (0.0, np.ascontiguousarray(x, dtype=np.float64))
+        out = eng.sampled_slab(alg.rule, ys, inner, hi - lo, outer, shape[prob.dim], lo, h=h, x=xs)[:inner * outer]
+        return out.reshape(shape[:prob.dim] + shape[prob.dim + 1:], order="F")
+    return local_slab
+
+
+def solve_sampled_split_axis(prob, alg, group=None, local_slab=None, engine=None):
+    """solve(SampledIntegralProblem(y, x; dim), alg) with the INTEGRATION axis cut into one contiguous slab per rank (SURVEY 8(e) row 2,
+    the preferred split for BASELINE config 2: every rank streams one contiguous block; it is also the only way to spread a single long
+    vector, src/sampled.jl:51-64).  Rank r integrates the points shard_range(n, r, world) with the weights of the WHOLE grid
+    (ib200_sampled_slab: end corrections only at the global ends) and the partial results -- 32 KiB at config 2 -- are summed by ONE
+    all-reduce.  `local_slab(prob, alg, lo, hi)` -> this rank's contribution (default: the engine on this rank's GPU).  Every rank
+    returns the whole solution.  The sum over the slabs is formed in another order than the unsharded solve's: results agree to
+    rounding (<= 1e-12 sum|w y|), not bit for bit."""
+    import torch
+    import torch.distributed as dist
+    from . import interface
+    if local_slab is None:
+        local_slab = _engine_slab(engine)
+    y = np.asarray(prob.y)
+    n = y.shape[prob.dim]
+    if not dist.is_initialized():
+        u = np.asarray(local_slab(prob, alg, 0, n))
+        return interface.IntegralSolution(u if u.ndim else float(u), None, prob, alg, interface.ReturnCode.Success)
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    lo, hi = shard_range(n, rank, world)
+    part = np.array(local_slab(prob, alg, lo, hi), dtype=np.float64, order="C")        # (ascontiguousarray would turn a scalar into shape (1,))
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    t = torch.from_numpy(part.reshape(-1).copy()).to(dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)          # the one collective of the solve
+    u = t.cpu().numpy().reshape(part.shape)
+    return interface.IntegralSolution(np.asfortranarray(u) if u.ndim else float(u), None, prob, alg, interface.ReturnCode.Success)
+
+
 def solve_sampled_sharded(prob, alg, group=None, local_solve=None):
     """solve(SampledIntegralProblem(y, x; dim), alg) with the independent rows of `y` split across the ranks of `group`
     (BASELINE config 2; SURVEY 8(e): the outputs are independent, so there is NO data-path collective -- every rank streams its

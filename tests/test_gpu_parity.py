@@ -543,3 +543,42 @@ def test_quadgk_order_through_solve_and_infinite_domain(eng, O):
         ib.QuadGKB200(order=31)
     with pytest.raises(ib.IB200Error, match="order"):
         eng.quadgk_batch(F["sinxp"], np.array([-2.0]), np.array([5.0]), np.array([[1.0]]), rule=(np.zeros(2), np.zeros(2), np.zeros(1)))
+
+
+# ------------------------------------------------------------------------------------- sampled: slabs of the integration axis, long outer extents
+@pytest.mark.parametrize("rule", ["trapezoid", "simpson"])
+@pytest.mark.parametrize("uniform", [True, False])
+def test_sampled_slabs_of_the_integration_axis_add_up(eng, O, rule, uniform):
+    """ib200_sampled_slab (SURVEY 8(e) row 2): the integration axis cut into slabs, each integrated with the weights of the WHOLE grid;
+    the slab contributions add up to the unsharded solve (<= 1e-12 sum|w y|), for matrices and for a single long vector"""
+    rng = np.random.default_rng(21)
+    for shape, dim in (((64, 4097), 1), ((5000,), 0), ((3, 501, 4), 1)):
+        n = shape[dim]
+        y = np.asfortranarray(rng.standard_normal(shape) + 1.5)
+        x = None if uniform else np.sort(rng.random(n)) * 2.0 + 0.1
+        h = 0.37 if uniform else 0.0
+        inner = int(np.prod(shape[:dim], dtype=np.int64)); outer = int(np.prod(shape[dim + 1:], dtype=np.int64))
+        whole = eng.sampled(rule, y, inner, n, outer, h=h, x=x)[:inner * outer]
+        ref = np.atleast_1d(O.sampled_evalrule(rule, y, x=x, h=h if uniform else None, dim=dim)).ravel(order="F")
+        w = O.sampled_weights(rule, n, h=h if uniform else None, x=x)
+        scale = np.atleast_1d(np.tensordot(np.abs(y), np.abs(w), axes=([dim], [0]))).ravel(order="F")
+        cuts = [0, 1, 3, n // 3, n // 3, n - 2, n]                       # short, empty and end slabs included
+        tot = np.zeros(inner * outer)
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            sl = [slice(None)] * len(shape); sl[dim] = slice(lo, hi)
+            tot += eng.sampled_slab(rule, np.asfortranarray(y[tuple(sl)]), inner, hi - lo, outer, n, lo, h=h, x=x)[:inner * outer]
+        assert np.all(np.abs(tot - whole) <= 1e-12 * scale) and np.all(np.abs(tot - ref) <= 1e-12 * scale)
+    with pytest.raises(ib.IB200Error):
+        eng.sampled_slab(rule, y, inner, n, outer, n - 1, 0, h=0.1)      # the slab must lie inside the grid
+
+
+def test_sampled_any_outer_extent(eng, O):
+    """the reference's evalrule takes any shape (src/sampled.jl:99-124): more than 65535 columns along the non-integrated axes"""
+    rng = np.random.default_rng(22)
+    y = np.asfortranarray(rng.standard_normal((40, 70001)) + 1.5)        # integrate the first (column-major) axis: inner = 1, outer = 70001
+    got = eng.sampled("simpson", y, 1, 40, 70001, h=0.1)[:70001]
+    ref = O.sampled_evalrule("simpson", y, h=0.1, dim=0)
+    assert np.allclose(got, ref, rtol=1e-13, atol=1e-13)
+    y3 = np.asfortranarray(rng.standard_normal((2, 9, 66000)) + 1.5)     # inner = 2, outer = 66000
+    got = eng.sampled("trapezoid", y3, 2, 9, 66000, h=0.1)[:2 * 66000].reshape((2, 66000), order="F")
+    assert np.allclose(got, O.sampled_evalrule("trapezoid", y3, h=0.1, dim=1), rtol=1e-13, atol=1e-13)

@@ -161,3 +161,57 @@ def test_round_oracle_presplit_variants_agree():
     for m0 in (4, 5, 6):
         I, E, s = O.hcubature_rounds("gauss", np.zeros(3), np.ones(3), par, reltol=1e-7, abstol=0.0, m0=m0)
         assert s["status"] == 0 and abs(I - base[0]) <= 1e-7 * abs(I) and E <= 1e-7 * abs(I)
+
+
+def _oracle_slab(prob, alg, lo, hi):
+    """this rank's slab of the integration axis with the weights of the WHOLE grid (CPU restatement of ib200_sampled_slab)"""
+    import oracle as O
+    x = prob.x
+    n = np.asarray(prob.y).shape[prob.dim]
+    w = O.sampled_weights(alg.rule, n, h=x.step) if isinstance(x, ib.Range) else O.sampled_weights(alg.rule, n, x=np.asarray(x))
+    y = np.moveaxis(np.asarray(prob.y, dtype=np.float64), prob.dim, -1)
+    return np.tensordot(y[..., lo:hi], w[lo:hi], axes=([-1], [0]))
+
+
+def _split_axis_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(4)
+        out = []
+        for shape, dim in (((1001,), 0), ((7, 101), 1), ((5, 64, 3), 1), ((3, 2), 1)):
+            y = rng.standard_normal(shape) + 1.5
+            for alg, x in ((ib.TrapezoidalB200(), ib.Range(0.0, 1.0, shape[dim])), (ib.SimpsonsB200(), ib.Range(0.0, 2.0, shape[dim])),
+                           (ib.TrapezoidalB200(), np.sort(rng.random(shape[dim])))):
+                sol = sharding.solve_sampled_split_axis(ib.SampledIntegralProblem(y, x, dim=dim), alg, local_slab=_oracle_slab)
+                out.append(np.asarray(sol.u))
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_solve_sampled_split_axis_world2_gloo():
+    """the integration axis cut into one slab per rank + ONE all-reduce of the partial results (preferred variant):
+    a single long vector shards too, end corrections only at the global ends, every rank gets the whole answer"""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_split_axis_worker, args=(r, 2, port, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for pr in procs:
+        pr.join(60)
+        assert pr.exitcode == 0
+    rng = np.random.default_rng(4)
+    ref = []
+    for shape, dim in (((1001,), 0), ((7, 101), 1), ((5, 64, 3), 1), ((3, 2), 1)):
+        y = rng.standard_normal(shape) + 1.5
+        for alg, x in ((ib.TrapezoidalB200(), ib.Range(0.0, 1.0, shape[dim])), (ib.SimpsonsB200(), ib.Range(0.0, 2.0, shape[dim])),
+                       (ib.TrapezoidalB200(), np.sort(rng.random(shape[dim])))):
+            ref.append(np.asarray(_oracle_sampled_solve(ib.SampledIntegralProblem(y, x, dim=dim), alg).u))
+    assert np.array_equal(res[0][1], res[1][1]) if False else all(np.array_equal(a, b) for a, b in zip(res[0][1], res[1][1]))   # the same on both ranks
+    for a, b in zip(res[0][1], ref):
+        assert a.shape == b.shape and np.allclose(a, b, rtol=1e-13, atol=1e-13)
