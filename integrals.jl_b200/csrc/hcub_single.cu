@@ -375,9 +375,16 @@ static int32_t hs_level2(ib200_ctx *ctx, hs::Params &p, int family, int dim, boo
     IB_CUDA(ctx, cudaMemcpyAsync(diag, counter, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     IB_CUDA(ctx, cudaStreamSynchronize(s));
     if (diag_out) { diag_out[0] = (int64_t)diag[1]; diag_out[1] = (int64_t)diag[2]; diag_out[2] = (int64_t)diag[3]; diag_out[3] = (int64_t)q.cap; }
+    // the arenas took most of the free HBM: hand it back, so that the next call on this context (a batch with its own pools) finds it
+    for (int sl : {SL_ARENA0, SL_ARENA1, SL_ARENA2}) {
+        if (ctx->scratch[sl].p) { cudaFree(ctx->scratch[sl].p); ctx->scratch[sl].p = nullptr; ctx->scratch[sl].cap = 0; }
+    }
+    // HCubature's stopping test on the WHOLE integral decides: a few sub-problems whose level-1 error estimate was far too small get a
+    // share they cannot meet and end at their arena / budget, but the others finish below their shares (bisection is discrete), so the
+    // sum usually passes -- their leftover error is part of E.  Only if it does not is the solve reported as unconverged.
     const double I = tot4[0], E = tot4[1];
-    int status = (int)tot4[3];
-    if (status == IB200_ST_CONVERGED && !(E <= fmax(rt * fabs(I), atol))) status = isfinite(E) ? IB200_ST_MAXEVALS : IB200_ST_NONFINITE;
+    int status = IB200_ST_CONVERGED;
+    if (!(E <= fmax(rt * fabs(I), atol))) status = isfinite(E) ? IB200_ST_MAXEVALS : IB200_ST_NONFINITE;
     res6[0] = I; res6[1] = E; res6[2] += tot4[2]; res6[3] = (double)n + 0.5 * tot4[2]; res6[5] = (double)status;
     if (nsub_out) *nsub_out = (int64_t)n;
     return IB200_OK;
@@ -489,7 +496,7 @@ extern "C" int32_t ib200_hcubature_single(ib200_ctx *ctx, int32_t family, int32_
     int64_t nsub = 0, diag[4] = {0, 0, 0, 0};
     if ((int)res[5] == hs::kStatusHandover &&
         (rc = hs_level2(ctx, p, family, dim, allfin, dpar.d, nparam, reltol, abstol, res, &nsub, diag))) return rc;
-    if (diag[0] + diag[1] + diag[2] > 0)
+    if (diag[0] + diag[1] + diag[2] > 0)          // a note, not an error: the status comes from the stopping test on the whole integral
         ctx->err = "ib200_hcubature_single: level-2 sub-problems on this rank ended by their budget: " + std::to_string(diag[0]) + ", by a full arena (" +
                    std::to_string(diag[3]) + " boxes): " + std::to_string(diag[1]) + ", non-finite: " + std::to_string(diag[2]);
     ib200_time_end(ctx);

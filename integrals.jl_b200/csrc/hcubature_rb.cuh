@@ -416,25 +416,37 @@ hcub_rb_kernel(const Params p) {
                 theta = fmin(theta, theta_h);
             }
 
-            // ---- select: slots with error >= theta, in store order (8 key loads in flight per lane)
+            // ---- select: slots with error >= theta, in store order.  The pass is a latency-bound stream of the problem's keys (ncu: a fifth
+            //      of the stall samples of the product-peak kernel sat on its first compare), so the keys of the NEXT 512 boxes are already
+            //      in flight while the current 512 are compacted (16 independent loads per lane, double buffered)
             nsplit = 0;
             dE = 0.0;
-            for (int i0 = 0; i0 < nbox; i0 += 256) {
-                double e[8];
+            {
+                constexpr int KU = 16;
+                double en[KU];
 #pragma unroll
-                for (int u = 0; u < 8; u++) { const int i = i0 + 32 * u + lane; e[u] = i < nbox ? __ldcg(err + i) : -1.0; }
+                for (int u = 0; u < KU; u++) { const int i = 32 * u + lane; en[u] = i < nbox ? __ldcg(err + i) : -1.0; }
+                for (int i0 = 0; i0 < nbox; i0 += 32 * KU) {
+                    double e[KU];
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int i = i0 + 32 * u + lane;
-                    const bool flag = e[u] >= theta;
-                    const unsigned bal = __ballot_sync(full, flag);
-                    if (flag) {
-                        list[nsplit + __popc(bal & lt)] = i;
-                        dE += e[u];
-                        const int bn = ebin(e[u]);
-                        if (atomicSub(&hist[bn], 1u) == 1u) atomicAnd(&occ[bn >> 5], ~(1u << (bn & 31)));
+                    for (int u = 0; u < KU; u++) e[u] = en[u];
+                    if (i0 + 32 * KU < nbox) {
+#pragma unroll
+                        for (int u = 0; u < KU; u++) { const int i = i0 + 32 * KU + 32 * u + lane; en[u] = i < nbox ? __ldcg(err + i) : -1.0; }
                     }
-                    nsplit += __popc(bal);
+#pragma unroll
+                    for (int u = 0; u < KU; u++) {
+                        const int i = i0 + 32 * u + lane;
+                        const bool flag = e[u] >= theta;
+                        const unsigned bal = __ballot_sync(full, flag);
+                        if (flag) {
+                            list[nsplit + __popc(bal & lt)] = i;
+                            dE += e[u];
+                            const int bn = ebin(e[u]);
+                            if (atomicSub(&hist[bn], 1u) == 1u) atomicAnd(&occ[bn >> 5], ~(1u << (bn & 31)));
+                        }
+                        nsplit += __popc(bal);
+                    }
                 }
             }
             if (nbox + nsplit > p.cap) { status = IB200_ST_MAXEVALS; break; }     // arena full: leave the boxes alone
@@ -445,7 +457,17 @@ hcub_rb_kernel(const Params p) {
 
         // ---- HCubature's closing sum over the store
         double pI = 0.0, pE = 0.0;
-        for (int s = lane; s < nbox; s += 32) { pI += __ldcg(rec + (size_t)s * RECW + 2 * D); pE += __ldcg(err + s); }
+        {
+            int s = lane;
+            for (; s + 7 * 32 < nbox; s += 8 * 32) {             // 16 loads in flight per lane, added in slot order
+                double vi[8], ve[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) { vi[u] = __ldcg(rec + (size_t)(s + 32 * u) * RECW + 2 * D); ve[u] = __ldcg(err + s + 32 * u); }
+#pragma unroll
+                for (int u = 0; u < 8; u++) { pI += vi[u]; pE += ve[u]; }
+            }
+            for (; s < nbox; s += 32) { pI += __ldcg(rec + (size_t)s * RECW + 2 * D); pE += __ldcg(err + s); }
+        }
         pI = wsum(pI); pE = wsum(pE);
         if (lane == 0) {
             if (sub) {

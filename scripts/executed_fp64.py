@@ -17,8 +17,10 @@ def main(raw, work, key, out="profiles/r02_executed_fp64.json"):
     rows = list(csv.reader(open(raw)))
     hdr = rows[0]
     d = dict(zip(hdr, rows[2]))
+    units = dict(zip(hdr, rows[1]))
     w = json.load(open(work))
-    g = lambda k: float(d[k].replace(",", ""))
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12, "ms": 1e6, "us": 1e3, "ns": 1.0, "s": 1e9, "msecond": 1e6, "usecond": 1e3, "nsecond": 1.0, "second": 1e9}
+    g = lambda k: float(d[k].replace(",", "")) * scale.get(units.get(k, ""), 1.0)      # bytes and nanoseconds whatever unit ncu chose
     def count(op):
         k = f"smsp__sass_thread_inst_executed_op_{op}_pred_on.sum"
         if k in d and d[k] != "":
