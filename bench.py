@@ -777,6 +777,40 @@ def main():
                                                   "how": "sharding.solve_sharded(interleave=True): problem k on rank k mod N, host inputs and outputs, one all_gather of the results per family"}
         except Exception as ex:
             sec["c4_strong_scaling_fixed_set"] = {"error": str(ex)[:300]}
+        try:
+            # BASELINE config 2 with the INTEGRATION axis cut into one slab per GPU: every rank streams its contiguous
+            # slab (generated on its device) and the 4096 partial results are summed by ONE NCCL all-reduce inside ib200_sampled_slab
+            m = WL.C2["m"]; ntot = args.nprob or WL.C2["n"]
+            lo, hi = (ntot * rank) // world, (ntot * (rank + 1)) // world
+            xs = torch.linspace(0, 1, ntot, dtype=torch.float64, device="cuda")[lo:hi]
+            jj = 1.0 + torch.arange(1, m + 1, dtype=torch.float64, device="cuda") / m
+            ys = torch.empty((hi - lo, m), dtype=torch.float64, device="cuda")
+            for i0 in range(0, hi - lo, 1 << 16):
+                i1 = min(hi - lo, i0 + (1 << 16))
+                ys[i0:i1] = torch.sin(xs[i0:i1, None] * jj[None, :]) + 1.5
+            out = torch.empty(m, dtype=torch.float64, device="cuda")
+            hh = 1.0 / (ntot - 1)
+            def split_step():
+                eng.sampled_slab("trapezoid", ys, m, hi - lo, 1, ntot, lo, h=hh, out=out)
+                eng.sampled_slab("simpson", ys, m, hi - lo, 1, ntot, lo, h=hh, out=out)
+            for _ in range(3):
+                split_step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(4):
+                flush.fill_(1); split_step()
+            torch.cuda.synchronize()
+            dt = maxrank(time.perf_counter() - t0) / 4
+            # Simpson of sin(x j') + 1.5 over [0, 1], row j' = 1 + j/m: closed form
+            jh = jj.cpu().numpy(); exact = (1 - np.cos(jh)) / jh + 1.5
+            errmax = float(np.max(np.abs(out.cpu().numpy() - exact)))
+            by = 2 * (8.0 * m * ntot + 8 * m)
+            sec["c2_split_integration_axis"] = {"value": by / dt / 1e9, "unit": "GB/s", "ms_per_step": dt * 1e3, "frac_of_measured_hbm_x_gpus": by / dt / 1e9 / (6535.7 * world),
+                                                "max_abs_err_vs_closed_form": errmax, "same_result_on_all_ranks": bits(*out[:8].tolist()),
+                                                "how": "each rank: ib200_sampled_slab on its 4096 x n/N slab (device resident) + one ncclAllReduce of 4096 doubles per rule"}
+            del ys
+        except Exception as ex:
+            sec["c2_split_integration_axis"] = {"error": str(ex)[:300]}
         line["secondary"] = sec
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -436,6 +436,7 @@ hcub_rb_kernel(const Params p) {
                     }
 #pragma unroll
                     for (int u = 0; u < KU; u++) {
+                        if (i0 + 32 * u >= nbox) break;                // (uniform) short stores: no work for the empty part of the batch
                         const int i = i0 + 32 * u + lane;
                         const bool flag = e[u] >= theta;
                         const unsigned bal = __ballot_sync(full, flag);
