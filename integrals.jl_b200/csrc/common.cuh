@@ -41,9 +41,10 @@ struct ib200_ctx {
     int64_t opt_single_switch_boxes = 1 << 20;   // hcub_single.cu: level-1 store size at which a solve goes two-level (0 = never)
     int64_t opt_single_switch_factor = 4096;     // ... provided the error is within this factor of the tolerance (or the store is 16x that size)
     int64_t opt_single_arena_mib = 0;            // device memory for the level-2 arenas, MiB (0 = 70 % of what is free)
+    int64_t opt_single_sub_boxes = 1 << 17;      // boxes a level-2 sub-problem may hold (its warp's arena)
     int64_t opt_hcub_capacity = 0;           // boxes per in-flight problem, 0 = derive from maxevals
     int64_t opt_sampled_slabs = 0;           // 0 = auto
-    int64_t opt_quadgk_mode = 0;             // 0 = auto, 1 = warp per problem, 2 = pair mode (thread per segment)
+    int64_t opt_quadgk_mode = 0;             // 0 = auto, 1 = warp per problem, 2 = pair mode (thread per segment), 3 = thread per problem
     int64_t opt_hcub_mode = 0;               // 0 = auto, 1 = warp per problem, 2 = pair mode (thread per box)
 
     // grow-only device scratch (the cacheval analogue: reused across calls)

@@ -56,13 +56,13 @@
 #include <vector>
 
 namespace hb {
-template <> int32_t launch<2>(ib200_ctx *, int, bool, Params &);
-template <> int32_t launch<3>(ib200_ctx *, int, bool, Params &);
-template <> int32_t launch<4>(ib200_ctx *, int, bool, Params &);
-template <> int32_t launch<5>(ib200_ctx *, int, bool, Params &);
-template <> int32_t launch<6>(ib200_ctx *, int, bool, Params &);
-template <> int32_t launch<7>(ib200_ctx *, int, bool, Params &);
-template <> int32_t launch<8>(ib200_ctx *, int, bool, Params &);
+template <> int32_t launch<2>(ib200_ctx *, int, bool, Params &, long long);
+template <> int32_t launch<3>(ib200_ctx *, int, bool, Params &, long long);
+template <> int32_t launch<4>(ib200_ctx *, int, bool, Params &, long long);
+template <> int32_t launch<5>(ib200_ctx *, int, bool, Params &, long long);
+template <> int32_t launch<6>(ib200_ctx *, int, bool, Params &, long long);
+template <> int32_t launch<7>(ib200_ctx *, int, bool, Params &, long long);
+template <> int32_t launch<8>(ib200_ctx *, int, bool, Params &, long long);
 }
 
 namespace hs {
@@ -332,7 +332,9 @@ static int32_t hs_level2(ib200_ctx *ctx, hs::Params &p, int family, int dim, boo
     const size_t held = ctx->scratch[SL_ARENA0].cap + ctx->scratch[SL_ARENA1].cap + ctx->scratch[SL_ARENA2].cap;
     long long mib = ctx->opt_single_arena_mib > 0 ? ctx->opt_single_arena_mib : (long long)(((double)(fr + held) * 0.7) / 1048576.0);
     if (mib < 16) mib = 16;
-    q.cap = (int)-mib;                                           // launch_impl turns the memory budget into boxes per warp
+    // a FIXED arena per warp (option single_sub_boxes): a sub-problem that outgrows it ends there whatever the free memory or the
+    // number of ranks -- launch_impl fits the grid, not the arena, into the `mib` budget -- so the solve is reproducible across both
+    q.cap = (int)((ctx->opt_single_sub_boxes + 127) / 128 * 128);
     q.rec = q.err = nullptr; q.list = nullptr;
     q.out_I = q.out_E = nullptr; q.out_nevals = nullptr; q.out_status = nullptr;
     q.sub_rec = p.rec; q.sub_err = p.err; q.sub_tol = tol; q.sub_wsum = wsum; q.sub_alpha = alpha;
@@ -347,13 +349,13 @@ static int32_t hs_level2(ib200_ctx *ctx, hs::Params &p, int family, int dim, boo
     int32_t rc = IB200_OK;
     if (q.nprob > 0) {
         switch (dim) {
-        case 2: rc = hb::launch<2>(ctx, family, allfin, q); break;
-        case 3: rc = hb::launch<3>(ctx, family, allfin, q); break;
-        case 4: rc = hb::launch<4>(ctx, family, allfin, q); break;
-        case 5: rc = hb::launch<5>(ctx, family, allfin, q); break;
-        case 6: rc = hb::launch<6>(ctx, family, allfin, q); break;
-        case 7: rc = hb::launch<7>(ctx, family, allfin, q); break;
-        default: rc = hb::launch<8>(ctx, family, allfin, q); break;
+        case 2: rc = hb::launch<2>(ctx, family, allfin, q, mib); break;
+        case 3: rc = hb::launch<3>(ctx, family, allfin, q, mib); break;
+        case 4: rc = hb::launch<4>(ctx, family, allfin, q, mib); break;
+        case 5: rc = hb::launch<5>(ctx, family, allfin, q, mib); break;
+        case 6: rc = hb::launch<6>(ctx, family, allfin, q, mib); break;
+        case 7: rc = hb::launch<7>(ctx, family, allfin, q, mib); break;
+        default: rc = hb::launch<8>(ctx, family, allfin, q, mib); break;
         }
         if (rc) return rc;
         chunk_sum_kernel<<<(unsigned)((nchunk_mine + kWarps - 1) / kWarps), kBlock, 0, s>>>(sub_out, nchunk_mine, chunks);

@@ -21,13 +21,13 @@ template <> int32_t launch<5>(ib200_ctx *, int, bool, Params &);
 }
 
 namespace hb {
-template <> int32_t launch<2>(ib200_ctx *, int, bool, Params &);
-template <> int32_t launch<3>(ib200_ctx *, int, bool, Params &);
-template <> int32_t launch<4>(ib200_ctx *, int, bool, Params &);
-template <> int32_t launch<5>(ib200_ctx *, int, bool, Params &);
-template <> int32_t launch<6>(ib200_ctx *, int, bool, Params &);
-template <> int32_t launch<7>(ib200_ctx *, int, bool, Params &);
-template <> int32_t launch<8>(ib200_ctx *, int, bool, Params &);
+template <> int32_t launch<2>(ib200_ctx *, int, bool, Params &, long long);
+template <> int32_t launch<3>(ib200_ctx *, int, bool, Params &, long long);
+template <> int32_t launch<4>(ib200_ctx *, int, bool, Params &, long long);
+template <> int32_t launch<5>(ib200_ctx *, int, bool, Params &, long long);
+template <> int32_t launch<6>(ib200_ctx *, int, bool, Params &, long long);
+template <> int32_t launch<7>(ib200_ctx *, int, bool, Params &, long long);
+template <> int32_t launch<8>(ib200_ctx *, int, bool, Params &, long long);
 }
 
 namespace hp {
@@ -127,13 +127,13 @@ extern "C" int32_t ib200_hcubature_batch(ib200_ctx *ctx, int32_t family, int32_t
         ctx->err.clear();
         ib200_time_begin(ctx);
         switch (dim) {
-        case 2: rc = hb::launch<2>(ctx, family, allfin, q); break;
-        case 3: rc = hb::launch<3>(ctx, family, allfin, q); break;
-        case 4: rc = hb::launch<4>(ctx, family, allfin, q); break;
-        case 5: rc = hb::launch<5>(ctx, family, allfin, q); break;
-        case 6: rc = hb::launch<6>(ctx, family, allfin, q); break;
-        case 7: rc = hb::launch<7>(ctx, family, allfin, q); break;
-        default: rc = hb::launch<8>(ctx, family, allfin, q); break;
+        case 2: rc = hb::launch<2>(ctx, family, allfin, q, 0); break;
+        case 3: rc = hb::launch<3>(ctx, family, allfin, q, 0); break;
+        case 4: rc = hb::launch<4>(ctx, family, allfin, q, 0); break;
+        case 5: rc = hb::launch<5>(ctx, family, allfin, q, 0); break;
+        case 6: rc = hb::launch<6>(ctx, family, allfin, q, 0); break;
+        case 7: rc = hb::launch<7>(ctx, family, allfin, q, 0); break;
+        default: rc = hb::launch<8>(ctx, family, allfin, q, 0); break;
         }
         if (rc) return rc;
         ib200_time_end(ctx);

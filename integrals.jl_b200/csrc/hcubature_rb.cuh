@@ -490,12 +490,13 @@ hcub_rb_kernel(const Params p) {
 inline size_t arena_bytes_per_box(int D) { return (size_t)8 * (2 * D + 2) + 8 + 4; }
 
 template <int D>
-int32_t launch(ib200_ctx *ctx, int family, bool allfin, Params &p);
+int32_t launch(ib200_ctx *ctx, int family, bool allfin, Params &p, long long arena_mib = 0);
 
 // Sizes the persistent grid from the kernel's occupancy, carves the per-warp arenas out of the context's scratch and launches.
-// p.cap <= 0: the arena capacity is chosen here -- as many boxes per warp as `-p.cap` bytes of device memory allow (sub-problem mode).
+// arena_mib > 0 (sub-problem mode): device memory the arenas may take -- the GRID shrinks to fit, never the arena of a warp, so a
+// sub-problem meets the same capacity (and gives the same result) whatever the free memory or the number of ranks.
 template <int D>
-int32_t launch_impl(ib200_ctx *ctx, int family, bool allfin, Params &p) {
+int32_t launch_impl(ib200_ctx *ctx, int family, bool allfin, Params &p, long long arena_mib) {
     int32_t rc = IB200_ERR_UNSUPPORTED;
     ib200_dispatch_family(family, [&](auto famc) {
         constexpr int FAM = decltype(famc)::value;
@@ -513,14 +514,12 @@ int32_t launch_impl(ib200_ctx *ctx, int family, bool allfin, Params &p) {
                 int64_t blocks = (p.nprob + kWarps - 1) / kWarps;
                 if (blocks > (int64_t)ctx->sm_count * occ) blocks = (int64_t)ctx->sm_count * occ;
                 if (blocks < 1) blocks = 1;
-                const size_t warps = (size_t)blocks * kWarps;
-                if (p.cap <= 0) {
-                    const size_t bytes = (size_t)(-(long long)p.cap) << 20;                  // MiB budget handed in by the caller
-                    long long c = (long long)(bytes / (warps * arena_bytes_per_box(D)));
-                    c = c > (1 << 22) ? (1 << 22) : c;
-                    if (c < 256) return ib200_fail(ctx, IB200_ERR_OOM, "ib200_hcubature_single: no device memory left for the level-2 arenas");
-                    p.cap = (int)(c / 128 * 128);
+                if (arena_mib > 0) {
+                    const long long fit = (long long)(((size_t)arena_mib << 20) / ((size_t)kWarps * (size_t)p.cap * arena_bytes_per_box(D)));
+                    if (fit < 1) return ib200_fail(ctx, IB200_ERR_OOM, "ib200_hcubature_single: no device memory left for the level-2 arenas (lower the single_sub_boxes option)");
+                    if (blocks > fit) blocks = fit;
                 }
+                const size_t warps = (size_t)blocks * kWarps;
                 const size_t cap = (size_t)p.cap;
                 const bool sub = p.sub_rec != nullptr;                                       // level 2 keeps its arenas apart from the level-1 store
                 p.rec = (double *)ctx->get(sub ? SL_ARENA0 : SL_WORK2, warps * cap * (2 * D + 2) * sizeof(double));

@@ -1,5 +1,5 @@
 // hcubature_rb_d5.cu -- instantiates the round-based batched adaptive cubature kernels for dimension 5 (see hcubature_rb.cuh)
 #include "hcubature_rb.cuh"
 namespace hb {
-template <> int32_t launch<5>(ib200_ctx *ctx, int family, bool allfin, Params &p) { return launch_impl<5>(ctx, family, allfin, p); }
+template <> int32_t launch<5>(ib200_ctx *ctx, int family, bool allfin, Params &p, long long arena_mib) { return launch_impl<5>(ctx, family, allfin, p, arena_mib); }
 }

@@ -188,6 +188,132 @@ quadgk_kernel(const double *__restrict__ params, int nparam, int64_t nprob,
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Thread-per-problem variant (large batches).  ncu on the warp-per-problem kernel above (profiles/r01_quadgk_c1_*): 84 % of the
+// issue slots busy with 360 warp instructions per refinement step, of which the 30 integrand evaluations are the smaller part --
+// shuffle reductions, the pool scan and the REDUX arg-max are paid per step by 32 lanes for ONE problem.  Here a LANE owns a
+// problem: it evaluates both 15-point rules of a bisection itself (sums in QuadGK's own order, so a segment's (I, E) are the oracle's
+// doubles), keeps its segments in a lane-interleaved pool (error keys of the first 64 segments in shared memory, so the arg-max scan
+// is a conflict-free LDS stream; records and further keys in HBM, coalesced because the lanes of a warp walk the slots together)
+// and pulls the next problem from the global counter as soon as it is done, independently of its neighbours.
+// Same algorithm and selection order as above: largest error first, ties -> lowest slot, I and E updated by difference, final re-sum.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTpBlock = 128;
+constexpr int kTpKeys = 64;          // error keys per lane in shared memory
+
+template <int FAM, bool ALLFIN>
+__device__ __forceinline__ void gk15_thread(const ib::Problem<FAM, 1, ALLFIN> &P, double a, double b, double &Iout, double &Eout) {
+    const double s = 0.5 * (b - a);
+    auto g = [&](double fac) { double t[1] = {a + fac * s}; return P(t); };
+    double fp[7], fm[7];
+#pragma unroll
+    for (int j = 0; j < 7; j++) { fp[j] = g(1 + c_gk_x[j]); fm[j] = g(1 - c_gk_x[j]); }
+    const double f0 = g(1.0);
+    // QuadGK's evalrule (oracle gk_evalrule): symmetric pairs first, Gauss nodes are the odd ones
+    double fg = fp[1] + fm[1], fk = fp[0] + fm[0];
+    double Ig = fg * c_gk_wg[0];
+    double Ik = fg * c_gk_w[1] + fk * c_gk_w[0];
+#pragma unroll
+    for (int i = 2; i <= 3; i++) {
+        fg = fp[2 * i - 1] + fm[2 * i - 1];
+        fk = fp[2 * i - 2] + fm[2 * i - 2];
+        Ig += fg * c_gk_wg[i - 1];
+        Ik += fg * c_gk_w[2 * i - 1] + fk * c_gk_w[2 * i - 2];
+    }
+    Ig += f0 * c_gk_wg[3];
+    Ik += f0 * c_gk_w[7] + (fp[6] + fm[6]) * c_gk_w[6];
+    Iout = Ik * s;
+    Eout = fabs(Ik * s - Ig * s);
+}
+
+template <int FAM, bool ALLFIN>
+__global__ void __launch_bounds__(kTpBlock, 3)
+quadgk_tp_kernel(const double *__restrict__ params, int nparam, int64_t nprob,
+                 const double *__restrict__ lb, const double *__restrict__ ub, int bpp, int tr,
+                 double rtol, double atol, int64_t maxevals, int cap, double *__restrict__ arena,
+                 unsigned long long *__restrict__ counter,
+                 double *__restrict__ out_I, double *__restrict__ out_E, int64_t *__restrict__ out_nevals,
+                 int32_t *__restrict__ out_status) {
+    extern __shared__ double sm[];                                  // keys[kTpKeys][kTpBlock]
+    const int tid = threadIdx.x;
+    const unsigned full = 0xffffffffu;
+    double *keyS = sm + tid;
+    // lane-interleaved pools of this block: [slot][thread]
+    double *gA = arena + (size_t)blockIdx.x * 4 * cap * kTpBlock + tid;
+    double *gB = gA + (size_t)cap * kTpBlock, *gI = gB + (size_t)cap * kTpBlock, *gE = gI + (size_t)cap * kTpBlock;
+    auto key_ld = [&](int s) { return s < kTpKeys ? keyS[s * kTpBlock] : gE[(size_t)s * kTpBlock]; };
+    auto key_st = [&](int s, double e) { if (s < kTpKeys) keyS[s * kTpBlock] = e; else gE[(size_t)s * kTpBlock] = e; };
+
+    if (rtol == 0.0 && atol == 0.0) rtol = 1.4901161193847656e-08;   // sqrt(eps(Float64))
+
+    ib::Problem<FAM, 1, ALLFIN> P;
+    bool have = false, exhausted = false;
+    int64_t prob = -1, nev = 0;
+    int nseg = 0, status = IB200_ST_CONVERGED;
+    double I = 0.0, E = 0.0;
+
+    for (;;) {
+        if (!have && !exhausted) {
+            const unsigned long long pidx = atomicAdd(counter, 1ULL);
+            if ((int64_t)pidx >= nprob) exhausted = true;
+            else {
+                prob = (int64_t)pidx;
+                const double l = bpp ? lb[prob] : lb[0], u = bpp ? ub[prob] : ub[0];
+                P.load(params + prob * nparam, &l, &u, tr);
+                double tlo = -1.0, thi = 1.0;
+                if (!ALLFIN) { tlo = P.ax[0].tlo; thi = P.ax[0].thi; }
+                gk15_thread<FAM, ALLFIN>(P, tlo, thi, I, E);
+                gA[0] = tlo; gB[0] = thi; gI[0] = I; key_st(0, E);
+                nev = 15; nseg = 1; status = IB200_ST_CONVERGED; have = true;
+            }
+        }
+        if (__all_sync(full, !have)) break;                          // every lane of the warp is out of work
+        bool refine = false;
+        if (have) {
+            if (!isfinite(E)) status = IB200_ST_NONFINITE;
+            else if (!(E <= atol || E <= rtol * fabs(I))) {
+                if (nev >= maxevals || nseg + 1 > cap) status = IB200_ST_MAXEVALS;
+                else refine = status == IB200_ST_CONVERGED;
+            }
+        }
+        if (refine) {
+            // --- the segment with the largest error (ties -> lowest slot)
+            double best = -1.0; int slot = 0;
+            for (int s = 0; s < nseg; s++) { const double e = key_ld(s); if (e > best) { best = e; slot = s; } }
+            const double sa = gA[(size_t)slot * kTpBlock], sb = gB[(size_t)slot * kTpBlock], sI = gI[(size_t)slot * kTpBlock];
+            const double mid = (sa + sb) / 2;
+            if (endpoint_roundoff(sa, mid) || endpoint_roundoff(mid, sb)) { status = IB200_ST_ROUNDOFF; refine = false; }
+            else {
+                double I1, E1, I2, E2;
+                gk15_thread<FAM, ALLFIN>(P, sa, mid, I1, E1);
+                gk15_thread<FAM, ALLFIN>(P, mid, sb, I2, E2);
+                I = (I - sI) + I1 + I2;
+                E = (E - best) + E1 + E2;
+                nev += 30;
+                gB[(size_t)slot * kTpBlock] = mid; gI[(size_t)slot * kTpBlock] = I1; key_st(slot, E1);
+                gA[(size_t)nseg * kTpBlock] = mid; gB[(size_t)nseg * kTpBlock] = sb; gI[(size_t)nseg * kTpBlock] = I2; key_st(nseg, E2);
+                nseg++;
+                if (!isfinite(E1) || !isfinite(E2)) status = IB200_ST_NONFINITE;
+            }
+        }
+        if (have && !refine) {
+            // --- done: re-sum over all segments in slot order (QuadGK's closing sum), results out, this lane is free again
+            if (nseg > 1) {
+                double pI = 0.0, pE = 0.0;
+                for (int s = 0; s < nseg; s++) { pI += gI[(size_t)s * kTpBlock]; pE += key_ld(s); }
+                I = pI; E = pE;
+                if (status == IB200_ST_CONVERGED && !(E <= atol || E <= rtol * fabs(I)) && nev >= maxevals) status = IB200_ST_MAXEVALS;
+            }
+            out_I[prob] = I;
+            if (out_E) out_E[prob] = E;
+            if (out_nevals) out_nevals[prob] = nev;
+            if (out_status) out_status[prob] = status;
+            have = false;
+        }
+    }
+}
+
 }  // namespace
 
 // order == 0: the built-in (7,15) pair; otherwise the rule (x, w, wg) of that order in QuadGK.kronrod's layout (host pointers)
@@ -252,6 +378,46 @@ static int32_t quadgk_impl(ib200_ctx *ctx, int32_t family, int32_t transform,
         ctx->err.clear();
         ib200_time_begin(ctx);
         if ((rc = hp::launch<1>(ctx, family, allfin, q))) return rc;
+        ib200_time_end(ctx);
+        if ((rc = oI.finish(ctx)) || (rc = oE.finish(ctx)) || (rc = oN.finish(ctx)) || (rc = oS.finish(ctx))) return rc;
+        if (oI.is_host() || oE.is_host() || oN.is_host() || oS.is_host()) IB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return IB200_OK;
+    }
+
+    // thread per problem (quadgk_tp_kernel): batches large enough to give every lane of the GPU a problem of its own
+    const bool use_tp = ctx->opt_quadgk_mode == 3 || (ctx->opt_quadgk_mode == 0 && nprob >= 8192);
+    if (use_tp) {
+        int64_t need_seg = maxevals >= ((int64_t)1 << 40) ? 2048 : 2 + (maxevals > 15 ? (maxevals - 15 + 29) / 30 : 0);
+        if (ctx->opt_hcub_capacity > 0) need_seg = ctx->opt_hcub_capacity;
+        if (need_seg < kTpKeys) need_seg = kTpKeys;
+        if (need_seg > 8192) need_seg = 8192;
+        const int cap = (int)need_seg;
+        const size_t smem = (size_t)kTpKeys * kTpBlock * sizeof(double);
+        int64_t blocks = (nprob + kTpBlock - 1) / kTpBlock;
+        const int64_t maxb = (int64_t)ctx->sm_count * 3;
+        if (blocks > maxb) blocks = maxb;
+        double *arena = (double *)ctx->get(SL_WORK0, (size_t)blocks * 4 * (size_t)cap * kTpBlock * sizeof(double));
+        unsigned long long *counter = (unsigned long long *)ctx->get(SL_WORK1, sizeof(unsigned long long));
+        if (!arena || !counter) return ib200_fail(ctx, IB200_ERR_OOM, "ib200_quadgk_batch: scratch allocation failed");
+        IB_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), ctx->stream));
+        bool launched = false;
+        cudaError_t attr_err = cudaSuccess;
+        ib200_time_begin(ctx);
+        ib200_dispatch_family(family, [&](auto famc) {
+            constexpr int FAM = decltype(famc)::value;
+            if constexpr (ib::fam_dim_ok(FAM, 1)) {
+                auto go = [&](auto kern) {
+                    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    kern<<<(unsigned)blocks, kTpBlock, smem, ctx->stream>>>(dpar.d, nparam, nprob, dlb.d, dub.d, bpp, transform,
+                                                                          reltol, abstol, maxevals, cap, arena, counter, oI.d, oE.d, oN.d, oS.d);
+                    launched = true;
+                };
+                if (allfin) go(quadgk_tp_kernel<FAM, true>); else go(quadgk_tp_kernel<FAM, false>);
+            }
+        });
+        if (attr_err != cudaSuccess) { cudaGetLastError(); return ib200_fail(ctx, IB200_ERR_CUDA, "cudaFuncSetAttribute failed"); }
+        if (!launched) return ib200_fail(ctx, IB200_ERR_UNSUPPORTED, "ib200_quadgk_batch: family not compiled in for dim 1");
+        IB_LAUNCH_CHECK(ctx);
         ib200_time_end(ctx);
         if ((rc = oI.finish(ctx)) || (rc = oE.finish(ctx)) || (rc = oN.finish(ctx)) || (rc = oS.finish(ctx))) return rc;
         if (oI.is_host() || oE.is_host() || oN.is_host() || oS.is_host()) IB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

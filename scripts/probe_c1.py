@@ -10,7 +10,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 par = torch.from_numpy(np.ascontiguousarray(WL.c1_params(n).T)).cuda()
 oI = torch.empty(n, dtype=torch.float64, device="cuda"); oE = torch.empty_like(oI)
 oN = torch.empty(n, dtype=torch.int64, device="cuda"); oS = torch.empty(n, dtype=torch.int32, device="cuda")
-for mode in (1, 2):
+for mode in (1, 2, 3):
     eng.set_option("quadgk_mode", mode)
     for rep in range(4):
         eng.quadgk_batch(F["sinxp"], np.array([-2.0]), np.array([5.0]), par, reltol=1e-10, abstol=1e-8, out_I=oI, out_E=oE, out_nevals=oN, out_status=oS)

@@ -179,9 +179,10 @@ def _check_adaptive(I, E, st, Iref, Eref, reltol, abstol, exact=None):
     assert np.all(ok | ((E <= 1e-14 * np.abs(I)) & (Eref <= 1e-14 * np.abs(Iref))))
 
 
-@pytest.fixture(params=[1, 2], ids=["warp_mode", "pair_mode"])
+@pytest.fixture(params=[1, 2, 3], ids=["warp_mode", "pair_mode", "thread_mode"])
 def quadgk_mode(request, eng):
-    """run the test under both QuadGK kernels: 1 = warp per problem, 2 = pair mode (thread per segment, hcubature_pair.cuh D = 1)"""
+    """run the test under the three QuadGK kernels: 1 = warp per problem, 2 = pair mode (thread per segment, hcubature_pair.cuh D = 1),
+    3 = thread per problem (quadgk_tp_kernel, the default for batches >= 8192)"""
     eng.set_option("quadgk_mode", request.param)
     yield request.param
     eng.set_option("quadgk_mode", 0)

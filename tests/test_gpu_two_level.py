@@ -72,7 +72,7 @@ def test_two_level_result_independent_of_scheduling(eng):
     lb, ub = np.zeros(4), np.ones(4)
     I, E, s = _two_level(eng, "genz_gaussian", 4, lb, ub, par, 1e-9, 256)
     eng.set_option("adaptive_warps_per_sm", 4)
-    eng.set_option("single_arena_mib", 512)
+    eng.set_option("single_arena_mib", 2048)        # the GRID shrinks to fit the memory, a sub-problem's arena does not
     I2, E2, s2 = _two_level(eng, "genz_gaussian", 4, lb, ub, par, 1e-9, 256)
     assert (I, E, s["rule_applications"], s["boxes"]) == (I2, E2, s2["rule_applications"], s2["boxes"])
 
@@ -81,7 +81,7 @@ def test_two_level_budget_and_capacity_are_reported(eng):
     """sub-problems that fill their arenas leave their error in E: the stopping test on the whole integral then fails and the solve says
     so (status MAXEVALS, the count of unconverged sub-problems and why) -- never a silent success"""
     par = genz_params("genz_gaussian", 4, 3, scale=0.5)[:, 0]
-    eng.set_option("single_arena_mib", 16)          # a few hundred boxes per warp
+    eng.set_option("single_sub_boxes", 512)         # a small arena per sub-problem
     I, E, s = _two_level(eng, "genz_gaussian", 4, np.zeros(4), np.ones(4), par, 1e-13, 64, switch_factor=10 ** 9)
     assert s["status"] == 1 and s["level2_subproblems"] > 0 and E > 1e-13 * abs(I) and math.isfinite(I)
     assert s["level2_unconverged"] > 0 and "full arena" in s["note"]
