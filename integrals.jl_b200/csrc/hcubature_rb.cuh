@@ -418,11 +418,15 @@ hcub_rb_kernel(const Params p) {
 
             // ---- select: slots with error >= theta, in store order.  The pass is a latency-bound stream of the problem's keys (ncu: a fifth
             //      of the stall samples of the product-peak kernel sat on its first compare), so the keys of the NEXT 512 boxes are already
-            //      in flight while the current 512 are compacted (16 independent loads per lane, double buffered)
+            //      in flight while the current ones are compacted (HB_KU = 8 independent loads per lane, double buffered; measured against 16 and against
+            //      no double buffering: 8 wins on the families with smaller stores, 16 only on the product peak)
             nsplit = 0;
             dE = 0.0;
             {
-                constexpr int KU = 16;
+#ifndef HB_KU
+#define HB_KU 8
+#endif
+                constexpr int KU = HB_KU;
                 double en[KU];
 #pragma unroll
                 for (int u = 0; u < KU; u++) { const int i = 32 * u + lane; en[u] = i < nbox ? __ldcg(err + i) : -1.0; }
@@ -430,7 +434,15 @@ hcub_rb_kernel(const Params p) {
                     double e[KU];
 #pragma unroll
                     for (int u = 0; u < KU; u++) e[u] = en[u];
+#ifdef HB_NODB
+                    if (i0 > 0) {
+#pragma unroll
+                        for (int u = 0; u < KU; u++) { const int i = i0 + 32 * u + lane; e[u] = i < nbox ? __ldcg(err + i) : -1.0; }
+                    }
+                    if (false) {
+#else
                     if (i0 + 32 * KU < nbox) {
+#endif
 #pragma unroll
                         for (int u = 0; u < KU; u++) { const int i = i0 + 32 * KU + 32 * u + lane; en[u] = i < nbox ? __ldcg(err + i) : -1.0; }
                     }

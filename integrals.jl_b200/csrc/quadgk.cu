@@ -205,11 +205,34 @@ constexpr int kTpKeys = 64;          // error keys per lane in shared memory
 template <int FAM, bool ALLFIN>
 __device__ __forceinline__ void gk15_thread(const ib::Problem<FAM, 1, ALLFIN> &P, double a, double b, double &Iout, double &Eout) {
     const double s = 0.5 * (b - a);
-    auto g = [&](double fac) { double t[1] = {a + fac * s}; return P(t); };
-    double fp[7], fm[7];
+    double fp[7], fm[7], f0;
+    if constexpr (FAM == IB200_FAM_SINXP && ALLFIN) {
+        // sin(x p) on a finite interval: the 15 sines in lock step, five at a time (family.cuh sin_bfN) -- libm's sin carries a
+        // slow-path branch per call that keeps ptxas from interleaving the independent polynomial chains
+        double arg[15], val[15];
 #pragma unroll
-    for (int j = 0; j < 7; j++) { fp[j] = g(1 + c_gk_x[j]); fm[j] = g(1 - c_gk_x[j]); }
-    const double f0 = g(1.0);
+        for (int j = 0; j < 15; j++) {
+            const double fac = j < 7 ? 1 + c_gk_x[j] : (j < 14 ? 1 - c_gk_x[j - 7] : 1.0);
+            arg[j] = (P.lb[0] + (1.0 + (a + fac * s)) * P.den[0]) * P.q[0];
+        }
+#pragma unroll
+        for (int g0 = 0; g0 < 15; g0 += 5) {
+            double x5[5], o5[5];
+#pragma unroll
+            for (int j = 0; j < 5; j++) x5[j] = arg[g0 + j];
+            ib::sin_bfN<5>(x5, o5);
+#pragma unroll
+            for (int j = 0; j < 5; j++) val[g0 + j] = o5[j] * P.jacc;
+        }
+#pragma unroll
+        for (int j = 0; j < 7; j++) { fp[j] = val[j]; fm[j] = val[7 + j]; }
+        f0 = val[14];
+    } else {
+        auto g = [&](double fac) { double t[1] = {a + fac * s}; return P(t); };
+#pragma unroll
+        for (int j = 0; j < 7; j++) { fp[j] = g(1 + c_gk_x[j]); fm[j] = g(1 - c_gk_x[j]); }
+        f0 = g(1.0);
+    }
     // QuadGK's evalrule (oracle gk_evalrule): symmetric pairs first, Gauss nodes are the odd ones
     double fg = fp[1] + fm[1], fk = fp[0] + fm[0];
     double Ig = fg * c_gk_wg[0];
