@@ -40,13 +40,17 @@
 #include "hcubature_pair.cuh"
 #include "hcub_rounds.cuh"
 #include "gm_rule_thread2.cuh"
+#include "gm_rule_thread3.cuh"
 
 namespace hb {
 
 constexpr int kWarps = 4;
 constexpr int kBlock = 32 * kWarps;
 constexpr int kBins = 2048;                   // one bin per binary exponent of a double
-constexpr int kMaxThreadDim = 5;              // thread-per-box rule up to this dimension, warp-per-box above
+constexpr int kMaxThreadDim = 5;              // thread-per-box rule up to this dimension; above it for the product families only
+// warp per box: 6 .. 8 dimensions, families whose value is finish(sum of terms) (oscillatory, corner peak, exp(a.x)); the product
+// families have a thread-per-box rule up to 8-D (gm_rule_thread3.cuh)
+template <int FAM, int D> __host__ __device__ constexpr bool warp_box() { return D > kMaxThreadDim && !ib::Family<FAM, D>::kProd; }
 
 struct Params {
     const double *params; int nparam; int64_t nprob;
@@ -94,23 +98,26 @@ __device__ __forceinline__ double wmax(double v) {
 // Per block (warp-per-box only): the rule's weights and point table.
 template <int FAM, int D> __host__ __device__ constexpr int pc_padded() { return (hp::pc_doubles<FAM, D>() + D + 1) & ~1; }   // + prep[D] (gm_rule_thread2.cuh)
 template <int FAM, int D, bool ALLFIN> __host__ __device__ constexpr int row_doubles() {
-    if (D <= kMaxThreadDim) return kBins / 2 + kBins / 64 + pc_padded<FAM, D>() + 2 * (D + 1) * 32 * 2;
+    if (!warp_box<FAM, D>()) return kBins / 2 + kBins / 64 + pc_padded<FAM, D>() + 2 * (D + 1) * 32 * 2;
     using W = hs::WarpRule<FAM, D, ALLFIN>;
     return kBins / 2 + kBins / 64 + ((W::kProb + 1) & ~1) + ((W::kStage + 1) & ~1) + 2 * D + 2;
 }
-template <int D> __host__ __device__ constexpr int block_doubles() {
-    return D <= kMaxThreadDim ? 0 : 10 + (hc::gm_npoints(D) + 1) / 2 + 1;
+template <int FAM, int D> __host__ __device__ constexpr int block_doubles() {
+    return !warp_box<FAM, D>() ? 0 : 10 + (hc::gm_npoints(D) + 1) / 2 + 1;
 }
 
 #ifndef HB_MINB
 #define HB_MINB 3
 #endif
+#ifndef HB_MINB_HD
+#define HB_MINB_HD 3            // thread per box in 6 .. 8 dimensions
+#endif
 template <int FAM, int D, bool ALLFIN>
-__global__ void __launch_bounds__(kBlock, (D <= kMaxThreadDim ? HB_MINB : 4))
+__global__ void __launch_bounds__(kBlock, (D <= kMaxThreadDim ? HB_MINB : (warp_box<FAM, D>() ? 4 : HB_MINB_HD)))
 hcub_rb_kernel(const Params p) {
     using F = ib::Family<FAM, D>;
     using W = hs::WarpRule<FAM, D, ALLFIN>;
-    constexpr bool WB = D > kMaxThreadDim;                // warp per box
+    constexpr bool WB = warp_box<FAM, D>();               // warp per box
     constexpr int NPAR = ib::fam_nparam(FAM, D);
     constexpr int NP = hc::gm_npoints(D);
     constexpr int RECW = 2 * D + 2, NCH = D + 1;          // a record = NCH 16-byte chunks
@@ -121,7 +128,7 @@ hcub_rb_kernel(const Params p) {
     const int64_t gwarp = (int64_t)blockIdx.x * kWarps + wib;
     double *s_w = sm;                                                          // WB: [10]
     unsigned *s_pt = reinterpret_cast<unsigned *>(sm + 10);                    // WB: [NP]
-    double *row = sm + block_doubles<D>() + (size_t)wib * row_doubles<FAM, D, ALLFIN>();
+    double *row = sm + block_doubles<FAM, D>() + (size_t)wib * row_doubles<FAM, D, ALLFIN>();
     unsigned *hist = reinterpret_cast<unsigned *>(row);
     unsigned *occ = reinterpret_cast<unsigned *>(row + kBins / 2);
     double *pc = row + kBins / 2 + kBins / 64;
@@ -284,7 +291,8 @@ hcub_rb_kernel(const Params p) {
                         if (!first && (t & 1) == 0) sI -= Ipar;                   // the parent's integral leaves the sum
                         const int slot = (first || (t & 1) == 0) ? par_cur : nbox0 + (t >> 1);
                         double Ic, Ec; int kc = 0;
-                        if constexpr (FAM == IB200_FAM_GENZ_OSC && ALLFIN) hp::gm_rule_thread_osc<D>(pc, a, b, Ic, Ec, kc);
+                        if constexpr (D > kMaxThreadDim) g3::gm_rule_thread3<FAM, D, ALLFIN>(pc, p.tr, a, b, stage + (size_t)(ps & 1) * NCH * 32 + lane, Ic, Ec, kc);
+                        else if constexpr (FAM == IB200_FAM_GENZ_OSC && ALLFIN) hp::gm_rule_thread_osc<D>(pc, a, b, Ic, Ec, kc);
                         else if constexpr (ALLFIN) g2::gm_rule_thread2<FAM, D>(pc, a, b, Ic, Ec, kc);
                         else hp::gm_rule_thread<FAM, D, ALLFIN>(pc, p.tr, a, b, Ic, Ec, kc);
                         double2 *dst = reinterpret_cast<double2 *>(rec + (size_t)slot * RECW);
@@ -543,8 +551,8 @@ int32_t launch_impl(ib200_ctx *ctx, int family, bool allfin, Params &p, long lon
                 IB_LAUNCH_CHECK(ctx);
                 return IB200_OK;
             };
-            rc = allfin ? go(hcub_rb_kernel<FAM, D, true>, (size_t)(block_doubles<D>() + kWarps * row_doubles<FAM, D, true>()) * sizeof(double))
-                        : go(hcub_rb_kernel<FAM, D, false>, (size_t)(block_doubles<D>() + kWarps * row_doubles<FAM, D, false>()) * sizeof(double));
+            rc = allfin ? go(hcub_rb_kernel<FAM, D, true>, (size_t)(block_doubles<FAM, D>() + kWarps * row_doubles<FAM, D, true>()) * sizeof(double))
+                        : go(hcub_rb_kernel<FAM, D, false>, (size_t)(block_doubles<FAM, D>() + kWarps * row_doubles<FAM, D, false>()) * sizeof(double));
         }
     });
     if (rc == IB200_ERR_UNSUPPORTED && ctx->err.empty())

@@ -18,7 +18,10 @@ for rep in range(reps):
         par = torch.from_numpy(np.ascontiguousarray(WL.genz_params(fam, d, nprob).T)).cuda()
         oI = torch.empty(nprob, dtype=torch.float64, device="cuda"); oN = torch.empty(nprob, dtype=torch.int64, device="cuda")
         mode = int(os.environ.get("PK_MODE", "0"))
-        eng.hcubature_batch(F[fam], d, np.zeros(d), np.ones(d), par, reltol=1e-6, abstol=1e-8, maxevals=MAXEV, out_I=oI, mode=mode,
+        lbp, ubp = np.zeros(d), np.ones(d)
+        if os.environ.get("PK_INF"):             # two infinite axes (the shape of BASELINE config 5)
+            lbp[:2] = -np.inf; ubp[:2] = np.inf
+        eng.hcubature_batch(F[fam], d, lbp, ubp, par, reltol=1e-6, abstol=1e-8, maxevals=MAXEV, out_I=oI, mode=mode,
                             out_E=torch.empty_like(oI), out_nevals=oN, out_status=torch.empty(nprob, dtype=torch.int32, device="cuda"))
         eng.synchronize()
         # the work of this launch, for scripts/executed_fp64.py (executed FP64 instructions per integrand evaluation)

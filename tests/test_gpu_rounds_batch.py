@@ -49,11 +49,11 @@ def _agree(I, E, st, Ir, Er, str_, reltol, abstol):
 
 
 @pytest.mark.parametrize("family", GENZ)
-@pytest.mark.parametrize("dim", [2, 3, 4, 5, 6, 8])
+@pytest.mark.parametrize("dim", [2, 3, 4, 5, 6, 7, 8])
 def test_rounds_match_their_oracle(eng, O, family, dim):
     """mode 1 against the CPU restatement of the same round scheme: the same refinement (identical evaluation counts) except where
     a decision sits on a rounding-level tie (the kernel forms a point's value from per-axis table entries, with FMA contraction)"""
-    nprob = 24 if dim <= 5 else 12          # dim <= 5: one thread per box; dim >= 6: one warp per box
+    nprob = 24 if dim <= 5 else 12          # dim <= 5: one thread per box; dim >= 6: thread per box (product families) / warp per box
     par = genz_params(family, dim, nprob, scale=0.25)
     lb, ub = np.zeros(dim), np.ones(dim)
     reltol, abstol, cap = 1e-6, 1e-8, 400000
@@ -121,6 +121,30 @@ def test_rounds_initdiv_infinite_and_degenerate(eng, O):
     assert np.all(st == 1) and np.array_equal(str_, st) and np.all(ne >= 20000) and np.all(np.abs(I - Ir) <= np.minimum(E, Er))
     with pytest.raises(ib.IB200Error):          # 1-D (the Gauss-Kronrod rule) runs in reference order only
         eng.hcubature_batch(F["genz_gaussian"], 1, np.zeros(1), np.ones(1), genz_params("genz_gaussian", 1, 2), mode="rounds")
+
+
+@pytest.mark.parametrize("family", ["genz_gaussian", "genz_product_peak", "genz_c0"])
+@pytest.mark.parametrize("dim", [6, 7, 8])
+def test_rounds_high_dim_infinite_axes(eng, O, family, dim):
+    """6 .. 8 dimensions with infinite and semi-infinite axes (the thread-per-box rule of gm_rule_thread3.cuh with the Jacobian folded
+    into the per-axis terms) against the CPU restatement of the same rounds and against the reference order"""
+    nprob = 6
+    par = genz_params(family, dim, nprob, scale=0.25)
+    par[:dim] = np.maximum(par[:dim], 0.6)                     # decay fast enough on the infinite axes
+    lb, ub = np.zeros(dim), np.ones(dim)
+    lb[0], ub[0] = -np.inf, np.inf
+    ub[1] = np.inf
+    lb[dim - 1] = -np.inf
+    reltol, abstol, cap = 1e-4, 0.0, 600000
+    for trn, tr in (("if_inf", 0), ("tan", 1)):
+        I, E, ne, st = eng.hcubature_batch(F[family], dim, lb, ub, par, reltol=reltol, abstol=abstol, maxevals=cap, transform=tr, mode="rounds")
+        Ir, Er, ner, str_, _ = O.hcubature_rounds_batch(ORC_FAM[family], lb, ub, par, tr=trn, reltol=reltol, abstol=abstol, maxiters=cap,
+                                                       nthreads=O.max_threads())
+        assert np.mean(ne == ner) >= 0.5 and np.mean(st == str_) >= 0.8
+        ok_conv, ok_cap, ok_E = _agree(I, E, st, Ir, Er, str_, reltol, abstol)
+        assert np.all(ok_conv) and np.all(ok_cap) and np.all(ok_E)
+        same = ne == ner
+        assert np.all(np.abs(I - Ir)[same] <= 1e-10 * np.abs(Ir[same]))
 
 
 def test_rounds_result_independent_of_batch(eng):
