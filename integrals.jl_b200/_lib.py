@@ -388,7 +388,7 @@ class Engine:
                                                   C.byref(I), C.byref(E), st.ctypes.data))
         return I.value, E.value, dict(nevals=int(st[0]), rule_applications=int(st[1]), boxes=int(st[2]), rounds=int(st[3]),
                                       status=int(st[4]), world=int(st[5]), level2_subproblems=int(st[6]), level2_unconverged=int(st[7]),
-                                      note=self.L.ib200_last_error(self.h).decode() if st[7] else "")
+                                      note=self.L.ib200_last_error(self.h).decode() if (st[7] or st[6]) else "")
 
     # ---- BatchIntegralFunction bridge: caller-evaluated integrand ----------------------------------
     def batch_open(self, dim, lb, ub, reltol=1e-8, abstol=1e-8, max_boxes=1 << 20, store_boxes=0, transform=0):

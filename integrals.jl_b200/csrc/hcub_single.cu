@@ -67,6 +67,85 @@ template <> int32_t launch<8>(ib200_ctx *, int, bool, Params &, long long);
 
 namespace hs {
 
+// evaluate, THREAD per todo box: 6 .. 8 dimensions, product families (the rule of gm_rule_thread3.cuh).  The warp-per-box kernel
+// (hcub_rounds.cuh eval_kernel) spends a box's 401 points on 32 lanes through shared-memory tables (ncu: issue 72 %, FP64 pipe 38 %,
+// LSU 46 %); here a lane owns a box and the rule runs in its registers.  Same outputs (record, error key, outbox entry, block partial).
+constexpr int kEvalThreads = 128;
+template <int FAM, int D, bool ALLFIN>
+__global__ void __launch_bounds__(kEvalThreads, 3)
+eval_thread_kernel(Params p) {
+    using F = ib::Family<FAM, D>;
+    constexpr int NPAR = ib::fam_nparam(FAM, D);
+    constexpr int RECW = 2 * D + 2;
+    const State *st = p.st;
+    if (st->done) return;
+    __shared__ double s_pc[NPAR + 3 * D + 2];                 // par | lbs | aux (ALLFIN: half-widths, else ub) | finit | jacc | prep
+    __shared__ double2 s_scr[D * kEvalThreads];
+    __shared__ double s_red[3 * (kEvalThreads / 32)];
+    double *par = s_pc, *lbs = par + NPAR, *aux = lbs + D;
+    for (int t = threadIdx.x; t < NPAR; t += kEvalThreads) par[t] = p.par[t];
+    for (int k = threadIdx.x; k < D; k += kEvalThreads) { lbs[k] = p.lb[k]; aux[k] = ALLFIN ? (p.ub[k] - p.lb[k]) * 0.5 : p.ub[k]; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double jacc = 1.0;
+        if (ALLFIN) { for (int k = 0; k < D; k++) jacc = (k == 0) ? aux[0] : jacc * aux[k]; }
+        aux[D] = F::sep_init(par); aux[D + 1] = jacc;
+        g2::Prep<FAM, D>::run(par, aux + D + 2);
+    }
+    __syncthreads();
+    double2 *scr = s_scr + (size_t)(threadIdx.x >> 5) * D * 32 + (threadIdx.x & 31);
+
+    double sumI = 0.0, sumE = 0.0, maxE = 0.0;                // this thread's boxes in todo order
+    const long long ntodo = st->ntodo;
+    const long long nthreads = (long long)gridDim.x * kEvalThreads;
+    for (long long t = ((long long)blockIdx.x * kEvalThreads + threadIdx.x) * p.world + p.rank; t < ntodo; t += nthreads * p.world) {
+        const unsigned slot = p.todo[t];
+        double *r = p.rec + (size_t)slot * RECW;
+        double a[D], b[D];
+        {
+            const double2 *r2 = reinterpret_cast<const double2 *>(r);
+            double v[2 * D];
+#pragma unroll
+            for (int q = 0; q < D; q++) { const double2 w = r2[q]; v[2 * q] = w.x; v[2 * q + 1] = w.y; }
+#pragma unroll
+            for (int k = 0; k < D; k++) { a[k] = v[k]; b[k] = v[D + k]; }
+        }
+        double Iv, Er; int kd;
+        g3::gm_rule_thread3<FAM, D, ALLFIN>(s_pc, p.tr, a, b, scr, Iv, Er, kd);
+        *reinterpret_cast<double2 *>(r + 2 * D) = make_double2(Iv, (double)kd);
+        p.err[slot] = Er;
+        if (p.world > 1) {                                   // t == rank (mod world): entry t / world of this rank's list
+            double2 *ob = reinterpret_cast<double2 *>(p.outbox + (size_t)(t / p.world) * 4);
+            ob[0] = make_double2(__longlong_as_double((long long)slot), Iv);
+            ob[1] = make_double2(Er, (double)kd);
+        }
+        sumI += Iv; sumE += Er; maxE = fmax(maxE, Er);       // fmax drops NaN: non-finite E is caught through sumE
+    }
+    // block sums in a fixed shape (lanes, then warps in order)
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        sumI += __shfl_down_sync(0xffffffffu, sumI, off);
+        sumE += __shfl_down_sync(0xffffffffu, sumE, off);
+        maxE = fmax(maxE, __shfl_down_sync(0xffffffffu, maxE, off));
+    }
+    constexpr int NW = kEvalThreads / 32;
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { s_red[w] = sumI; s_red[NW + w] = sumE; s_red[2 * NW + w] = maxE; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double v0 = s_red[0], v1 = s_red[NW], v2 = s_red[2 * NW];
+        for (int k = 1; k < NW; k++) { v0 += s_red[k]; v1 += s_red[NW + k]; v2 = fmax(v2, s_red[2 * NW + k]); }
+        double *o = p.partial + (size_t)blockIdx.x * 4; o[0] = v0; o[1] = v1; o[2] = v2;
+    }
+}
+
+// one round's evaluation: thread per box where that rule exists, warp per box otherwise
+template <int FAM, int D, bool ALLFIN>
+static void launch_eval(const Params &p, int grid, cudaStream_t s) {
+    if constexpr (D > hb::kMaxThreadDim && ib::Family<FAM, D>::kProd) eval_thread_kernel<FAM, D, ALLFIN><<<grid, kEvalThreads, 0, s>>>(p);
+    else eval_kernel<FAM, D, ALLFIN><<<grid, kBlock, 0, s>>>(p);
+}
+
 // ---- nccl, loaded lazily (torch's copy when it is already in the process) ------------------------
 typedef struct ncclComm *ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
@@ -255,7 +334,7 @@ static int32_t hs_run(ib200_ctx *ctx, hs::Params &p, double *out6_host) {
     if ((rc = barrier())) { cudaFreeHost(done_h); return rc; }       // no results of this solve land in an inbox a peer still reads for the previous one
     for (long long iter = 0; iter < (1LL << 40); iter++) {
         for (int r = 0; r < kRoundsPerCheck; r++) {
-            eval_kernel<FAM, D, ALLFIN><<<grid, kBlock, 0, s>>>(p);          // this rank's share of the round
+            launch_eval<FAM, D, ALLFIN>(p, grid, s);                         // this rank's share of the round
             if (p.world > 1) publish_kernel<<<grid, kBlock, 0, s>>>(p);      // results -> every peer's inbox (NVLink, coalesced)
             eval_finish_kernel<<<1, kFin, 0, s>>>(p);
             if ((rc = exchange())) { cudaFreeHost(done_h); return rc; }      // partial sums; barrier: every rank's results have landed
@@ -341,9 +420,9 @@ static int32_t hs_level2(ib200_ctx *ctx, hs::Params &p, int family, int dim, boo
     q.sub_rank = p.rank; q.sub_world = p.world; q.sub_n = n;
     double *sub_out = (double *)ctx->get(SL_OUT1, (size_t)(nchunk_local_max * kSubChunk + 1) * 4 * sizeof(double));
     double *chunks = (double *)ctx->get(SL_OUT2, (size_t)(nchunk_local_max + 1) * 4 * (size_t)(p.world + 1) * sizeof(double));
-    unsigned long long *counter = (unsigned long long *)ctx->get(SL_OUT3, 4 * sizeof(unsigned long long));
+    unsigned long long *counter = (unsigned long long *)ctx->get(SL_OUT3, 8 * sizeof(unsigned long long));
     if (!sub_out || !chunks || !counter) return ib200_fail(ctx, IB200_ERR_OOM, "ib200_hcubature_single: level-2 scratch allocation failed");
-    IB_CUDA(ctx, cudaMemsetAsync(counter, 0, 4 * sizeof(unsigned long long), s));
+    IB_CUDA(ctx, cudaMemsetAsync(counter, 0, 8 * sizeof(unsigned long long), s));
     IB_CUDA(ctx, cudaMemsetAsync(chunks, 0, (size_t)(nchunk_local_max + 1) * 4 * (size_t)(p.world + 1) * sizeof(double), s));
     q.sub_out = sub_out; q.counter = counter;
     int32_t rc = IB200_OK;
@@ -372,11 +451,14 @@ static int32_t hs_level2(ib200_ctx *ctx, hs::Params &p, int family, int dim, boo
     chunk_total_kernel<<<1, kFin, 0, s>>>(gathered, nchunk, nchunk_local_max, p.world, scal + 4);
     IB_LAUNCH_CHECK(ctx);
     double tot4[4] = {0, 0, 0, 0};
-    unsigned long long diag[4] = {0, 0, 0, 0};
+    unsigned long long diag[6] = {0, 0, 0, 0, 0, 0};
     IB_CUDA(ctx, cudaMemcpyAsync(tot4, scal + 4, 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
-    IB_CUDA(ctx, cudaMemcpyAsync(diag, counter, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    IB_CUDA(ctx, cudaMemcpyAsync(diag, counter, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     IB_CUDA(ctx, cudaStreamSynchronize(s));
-    if (diag_out) { diag_out[0] = (int64_t)diag[1]; diag_out[1] = (int64_t)diag[2]; diag_out[2] = (int64_t)diag[3]; diag_out[3] = (int64_t)q.cap; }
+    if (diag_out) {
+        diag_out[0] = (int64_t)diag[1]; diag_out[1] = (int64_t)diag[2]; diag_out[2] = (int64_t)diag[3]; diag_out[3] = (int64_t)q.cap;
+        diag_out[4] = (int64_t)diag[4]; diag_out[5] = (int64_t)diag[5];
+    }
     // the arenas took most of the free HBM: hand it back, so that the next call on this context (a batch with its own pools) finds it
     for (int sl : {SL_ARENA0, SL_ARENA1, SL_ARENA2}) {
         if (ctx->scratch[sl].p) { cudaFree(ctx->scratch[sl].p); ctx->scratch[sl].p = nullptr; ctx->scratch[sl].cap = 0; }
@@ -495,12 +577,13 @@ extern "C" int32_t ib200_hcubature_single(ib200_ctx *ctx, int32_t family, int32_
     if (rc == IB200_ERR_UNSUPPORTED && ctx->err.empty())
         return ib200_fail(ctx, IB200_ERR_UNSUPPORTED, "ib200_hcubature_single: family/dimension not compiled in");
     if (rc) return rc;
-    int64_t nsub = 0, diag[4] = {0, 0, 0, 0};
+    int64_t nsub = 0, diag[6] = {0, 0, 0, 0, 0, 0};
     if ((int)res[5] == hs::kStatusHandover &&
         (rc = hs_level2(ctx, p, family, dim, allfin, dpar.d, nparam, reltol, abstol, res, &nsub, diag))) return rc;
-    if (diag[0] + diag[1] + diag[2] > 0)          // a note, not an error: the status comes from the stopping test on the whole integral
+    if (diag[0] + diag[1] + diag[2] + diag[4] > 0)  // a note, not an error: the status comes from the stopping test on the whole integral
         ctx->err = "ib200_hcubature_single: level-2 sub-problems on this rank ended by their budget: " + std::to_string(diag[0]) + ", by a full arena (" +
-                   std::to_string(diag[3]) + " boxes): " + std::to_string(diag[1]) + ", non-finite: " + std::to_string(diag[2]);
+                   std::to_string(diag[3]) + " boxes): " + std::to_string(diag[1]) + ", non-finite: " + std::to_string(diag[2]) +
+                   "; converged boxes retired from full arenas: " + std::to_string(diag[5]) + " in " + std::to_string(diag[4]) + " sub-problems";
     ib200_time_end(ctx);
     *out_I = res[0];
     if (out_E) *out_E = res[1];

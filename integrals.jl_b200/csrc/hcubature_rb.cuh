@@ -63,7 +63,8 @@ struct Params {
     double *rec;                // [warps][cap][2D+2]   a[D], b[D], I, split axis  (16-byte aligned records)
     double *err;                // [warps][cap]         the selection keys, scanned once per round
     int *list;                  // [warps][cap]         slots selected for bisection in the current round
-    unsigned long long *counter;    // [1] problem counter (+ [3] diagnostics in sub-problem mode)
+    unsigned long long *counter;    // [1] problem counter (+ [5] diagnostics in sub-problem mode: ended by budget / full arena / non-finite, sub-problems
+                                    //     that retired boxes, boxes retired)
     double *out_I, *out_E; int64_t *out_nevals; int32_t *out_status;
     // sub-problem mode (level 2 of ib200_hcubature_single)
     const double *sub_rec;      // [n][2D+2] records of the level-1 store (every box evaluated), or nullptr: batch mode
@@ -245,6 +246,8 @@ hcub_rb_kernel(const Params p) {
         int nbox = qtotal, ntodo = qtotal, nsplit = 0, nbox0 = 0, status = IB200_ST_CONVERGED;
         long long applied = 0;
         double I = 0.0, E = 0.0, theta = 0.0, dE = 0.0;
+        double Iret = 0.0, Eret = 0.0;          // sub-problem mode: sums over the boxes retired from a full arena
+        long long nretired = 0;
         bool first = true;
 
         for (;;) {
@@ -379,6 +382,14 @@ hcub_rb_kernel(const Params p) {
             if (!isfinite(E)) { status = IB200_ST_NONFINITE; break; }
             if (applied >= p.max_apps) { status = IB200_ST_MAXEVALS; break; }
 
+            // ---- threshold + selection, at most twice per round: when the selected boxes would overflow a sub-problem's arena, the boxes
+            //      that have converged are RETIRED first (only their sums are kept) and the round is decided again
+            const double theta_in = theta;
+            bool overflow = false;
+            double th_hi = 0.0, th_lo = 0.0;
+            int quota = 0;
+            for (int attempt = 0; ; attempt++) {
+            theta = theta_in;
             // ---- threshold (csrc/hcub_rounds.cuh decide_kernel, per problem).  The three scans of the exponent histogram walk only
             //      the OCCUPIED bins (bitmap), in the same order and with the same arithmetic as the scans over all bins; every lane
             //      computes the same value.  Bin kBins-1 (inf / NaN keys) never takes part: a non-finite E has ended the solve above.
@@ -397,7 +408,7 @@ hcub_rb_kernel(const Params p) {
                             const int b = (w << 5) + __ffs((int)m) - 1; m &= m - 1;
                             if (b > kBins - 2) break;
                             low += (double)hist[b] * bin_edge(b);
-                            if (!(low <= tol)) { bh = b - 1; broke = true; break; }
+                            if (!(low <= tol - Eret)) { bh = b - 1; broke = true; break; }      // what is retired can no longer be refined
                         }
                     }
                 }
@@ -422,6 +433,30 @@ hcub_rb_kernel(const Params p) {
                 const int bs = (bh + 1 > bb) ? bh + 1 : bb;
                 const double theta_h = bs <= 0 ? 0.0 : (bs >= kBins - 1 ? 1.7976931348623157e308 : bin_edge(bs));
                 theta = fmin(theta, theta_h);
+                // (4) second attempt of a round (after a retirement): the selection must fit the ROOM left in the arena.  Bins are taken
+                //     whole from the top while they fit; of the bin that does not fit any more, the first `quota` boxes in store order
+                if (attempt > 0) {
+                    const int room = p.cap - nbox;
+                    if (room < p.cap / 64) { overflow = true; break; }             // not worth a round: the arena stays full
+                    th_hi = theta; th_lo = theta; quota = 0;
+                    double up = 0.0; bool crossed = false;
+                    unsigned long long ws = words;
+                    while (ws && !crossed) {
+                        const int w = 63 - __clzll((long long)ws); ws &= ~(1ull << w);
+                        unsigned m = occ[w];
+                        while (m && !crossed) {
+                            const int b = (w << 5) + 31 - __clz((int)m); m &= ~(1u << (b & 31));
+                            if (b > kBins - 2) continue;
+                            const double c = (double)hist[b];
+                            if (up + c > (double)room) {
+                                th_hi = fmax(theta, b + 1 >= kBins - 1 ? 1.7976931348623157e308 : bin_edge(b + 1));
+                                th_lo = fmax(theta, bin_edge(b));
+                                quota = room - (int)up;
+                                crossed = true;
+                            } else up += c;
+                        }
+                    }
+                }
             }
 
             // ---- select: slots with error >= theta, in store order.  The pass is a latency-bound stream of the problem's keys (ncu: a fifth
@@ -430,6 +465,27 @@ hcub_rb_kernel(const Params p) {
             //      no double buffering: 8 wins on the families with smaller stores, 16 only on the product peak)
             nsplit = 0;
             dE = 0.0;
+            if (attempt > 0) {
+                // the capped selection of a second attempt (rare; plain loop): error >= th_hi, and the first `quota` boxes of [th_lo, th_hi)
+                int nlo = 0;
+                for (int i0 = 0; i0 < nbox; i0 += 32) {
+                    const int i = i0 + lane;
+                    const double e = i < nbox ? __ldcg(err + i) : -1.0;
+                    const bool hi = e >= th_hi;
+                    const bool lo = !hi && e >= th_lo;
+                    const unsigned bl = __ballot_sync(full, lo);
+                    const bool flag = hi || (lo && nlo + __popc(bl & lt) < quota);
+                    nlo += __popc(bl);
+                    const unsigned bal = __ballot_sync(full, flag);
+                    if (flag) {
+                        list[nsplit + __popc(bal & lt)] = i;
+                        dE += e;
+                        const int bn = ebin(e);
+                        if (atomicSub(&hist[bn], 1u) == 1u) atomicAnd(&occ[bn >> 5], ~(1u << (bn & 31)));
+                    }
+                    nsplit += __popc(bal);
+                }
+            } else
             {
 #ifndef HB_KU
 #define HB_KU 8
@@ -470,7 +526,76 @@ hcub_rb_kernel(const Params p) {
                     }
                 }
             }
-            if (nbox + nsplit > p.cap) { status = IB200_ST_MAXEVALS; break; }     // arena full: leave the boxes alone
+            if (attempt > 0 && nsplit == 0) { overflow = true; break; }            // a full arena and nothing left to retire
+            if (nbox + nsplit <= p.cap) break;
+            if (!sub || attempt > 0) { overflow = true; break; }                   // arena full: leave the boxes alone
+            // ---- retirement.  Boxes with the smallest errors leave the store; their integrals and errors stay in (I, E) and in the
+            //      closing sum through (Iret, Eret).  Retired error cannot be refined away, so a retirement may take at most a quarter
+            //      of the tolerance still unspent, measured by the UPPER edges of the histogram bins (a bound on the retired sum): every
+            //      box below theta_r = that bin edge goes.  Never a box selected for bisection (theta_r <= theta).  The histogram is
+            //      rebuilt from the boxes that stay (the selection pass has taken the selected ones out of it).
+            {
+                __syncwarp();
+                const double R = 0.25 * (tol - Eret);
+                const unsigned long long words = (unsigned long long)__ballot_sync(full, occ[lane] != 0u) |
+                                                 ((unsigned long long)__ballot_sync(full, occ[32 + lane] != 0u) << 32);
+                int br = -1;
+                {
+                    double acc = 0.0; bool broke = false;
+                    unsigned long long ws = words;
+                    while (ws && !broke) {
+                        const int w = __ffsll((long long)ws) - 1; ws &= ws - 1;
+                        unsigned m = occ[w];
+                        while (m) {
+                            const int b = (w << 5) + __ffs((int)m) - 1; m &= m - 1;
+                            if (b > kBins - 3) { broke = true; break; }
+                            acc += (double)hist[b] * bin_edge(b + 1);
+                            if (!(acc <= R)) { broke = true; break; }
+                            br = b;
+                        }
+                    }
+                }
+                const double theta_r = fmin(br < 0 ? 0.0 : bin_edge(br + 1), theta);
+                __syncwarp();
+                for (int b = lane; b < kBins; b += 32) hist[b] = 0u;
+                for (int b = lane; b < kBins / 32; b += 32) occ[b] = 0u;
+                __syncwarp();
+                int kept = 0;
+                double rI = 0.0, rE = 0.0;
+                for (int i0 = 0; i0 < nbox; i0 += 32) {
+                    const int i = i0 + lane;
+                    const bool have = i < nbox;
+                    const double e = have ? __ldcg(err + i) : 0.0;
+                    const bool keep = have && e >= theta_r;
+                    double r[RECW];
+                    if (keep) {
+                        const double2 *src = reinterpret_cast<const double2 *>(rec + (size_t)i * RECW);
+#pragma unroll
+                        for (int q = 0; q < NCH; q++) { const double2 v = __ldcg(src + q); r[2 * q] = v.x; r[2 * q + 1] = v.y; }
+                    } else if (have) { rI += __ldcg(rec + (size_t)i * RECW + 2 * D); rE += e; }
+                    const unsigned bal = __ballot_sync(full, keep);
+                    __syncwarp();                                       // every lane has read its box before a slot of this batch is overwritten
+                    if (keep) {
+                        const int j = kept + __popc(bal & lt);          // j <= i: a slot this pass has already read
+                        if (j != i) {
+                            double2 *dst = reinterpret_cast<double2 *>(rec + (size_t)j * RECW);
+#pragma unroll
+                            for (int q = 0; q < NCH; q++) dst[q] = make_double2(r[2 * q], r[2 * q + 1]);
+                            err[j] = e;
+                        }
+                        const int bn = ebin(e);
+                        if (atomicAdd(&hist[bn], 1u) == 0u) atomicOr(&occ[bn >> 5], 1u << (bn & 31));
+                    }
+                    kept += __popc(bal);
+                    __syncwarp();
+                }
+                Iret += wsum(rI); Eret += wsum(rE);
+                nretired += nbox - kept;
+                nbox = kept;
+                __syncwarp();
+            }
+            }
+            if (overflow) { status = IB200_ST_MAXEVALS; break; }
             nbox0 = nbox;
             nbox += nsplit; ntodo = 2 * nsplit;
             __syncwarp();                 // the split list is read across lanes
@@ -489,9 +614,10 @@ hcub_rb_kernel(const Params p) {
             }
             for (; s < nbox; s += 32) { pI += __ldcg(rec + (size_t)s * RECW + 2 * D); pE += __ldcg(err + s); }
         }
-        pI = wsum(pI); pE = wsum(pE);
+        pI = wsum(pI) + Iret; pE = wsum(pE) + Eret;
         if (lane == 0) {
             if (sub) {
+                if (nretired > 0) { atomicAdd(p.counter + 4, 1ULL); atomicAdd(p.counter + 5, (unsigned long long)nretired); }
                 double *o = p.sub_out + (size_t)pidx * 4;
                 o[0] = pI; o[1] = pE; o[2] = (double)applied; o[3] = (double)status;
                 // diagnostics behind the counter: sub-problems ended by their budget / by a full arena / non-finite

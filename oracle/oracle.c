@@ -1269,28 +1269,44 @@ int orc_hcubature_vec_batch(int fam, int dim, const double *lb, const double *ub
  * before dealing sub-boxes to the ranks.  max_boxes: budget of rule applications.
  * ------------------------------------------------------------------------------------------ */
 double orc_round_fraction = 0.5;
+/* level-2 sub-problems of orc_hcubature_two_level: boxes a sub-problem's store may hold (0 = unbounded) -- the arena of
+   csrc/hcubature_rb.cuh (option single_sub_boxes), with converged-box retirement when it fills; orc_last_retired = boxes retired by the last solve */
+int64_t orc_sub_arena = 0;
+int64_t orc_last_retired = 0;
+double orc_retire_fraction = 0.25;
 /* the rounds themselves, from a store of `len` unevaluated boxes (all of them in the todo list) */
 static int hcub_rounds_core2(orc_integrand f, void *user, int dim, orc_box *t, int64_t cap, int64_t len,
                              double rtol, double atol, int64_t max_boxes, int first_box_only, int64_t switch_boxes, double switch_factor,
+                             int64_t arena, int64_t *nretired_out,
                              double *Iout, double *Eout, int64_t *napplied_out, int64_t *nboxes_out, int64_t *rounds_out,
                              orc_box **store_out);
 static int hcub_rounds_core(orc_integrand f, void *user, int dim, orc_box *t, int64_t cap, int64_t len,
                             double rtol, double atol, int64_t max_boxes, int first_box_only,
                             double *Iout, double *Eout, int64_t *napplied_out, int64_t *nboxes_out, int64_t *rounds_out)
 {
-    return hcub_rounds_core2(f, user, dim, t, cap, len, rtol, atol, max_boxes, first_box_only, 0, 0.0, Iout, Eout, napplied_out, nboxes_out,
+    return hcub_rounds_core2(f, user, dim, t, cap, len, rtol, atol, max_boxes, first_box_only, 0, 0.0, 0, NULL, Iout, Eout, napplied_out, nboxes_out,
                              rounds_out, NULL);
 }
 /* switch_boxes > 0: the two-level solve (orc_hcubature_two_level) -- stop with status 3 ("hand over") after the stopping test of a round
    once the store holds >= switch_boxes boxes AND E <= switch_factor * tol (or the store holds >= 16 * switch_boxes boxes), and return the
-   store (unsplit, every box evaluated) through store_out instead of freeing it */
+   store (unsplit, every box evaluated) through store_out instead of freeing it.
+   arena > 0: the store may hold at most `arena` boxes (a level-2 sub-problem's arena, csrc/hcubature_rb.cuh).  When the boxes selected by
+   a round would not fit, the converged boxes are RETIRED first -- every box whose error lies below theta_r leaves the store, its integral
+   and error stay in the sums -- and the round is decided again; theta_r is the upper edge of the last occupied exponent bin up to which the
+   bins' counts x upper edges sum to <= orc_retire_fraction of the tolerance still unspent (tol - retired error), and never above the split
+   threshold.  The second selection is capped by the room left (whole bins from the top, then the first boxes of the next bin in store
+   order).  If less than 1/64 of the arena is free after a retirement, or nothing can be selected, the solve ends with status 1 (arena full). */
 static int hcub_rounds_core2(orc_integrand f, void *user, int dim, orc_box *t, int64_t cap, int64_t len,
                              double rtol, double atol, int64_t max_boxes, int first_box_only, int64_t switch_boxes, double switch_factor,
+                             int64_t arena, int64_t *nretired_out,
                              double *Iout, double *Eout, int64_t *napplied_out, int64_t *nboxes_out, int64_t *rounds_out,
                              orc_box **store_out)
 {
+    double Iret = 0.0, Eret = 0.0;
+    int64_t nretired = 0;
     int64_t ntodo = 0, applied = 0, rounds = 0;
     int64_t *todo = (int64_t *)malloc(sizeof(int64_t) * (size_t)cap);
+    char *sel = (char *)malloc((size_t)cap);
     for (int64_t q = 0; q < len; q++) todo[ntodo++] = q;
     double I = 0.0, E = 0.0, theta = 0.0;
     int status = 0;
@@ -1308,15 +1324,19 @@ static int hcub_rounds_core2(orc_integrand f, void *user, int dim, orc_box *t, i
         if (applied >= max_boxes) { status = 1; break; }
         if (switch_boxes > 0 && len >= switch_boxes &&
             (E <= switch_factor * fmax(rtol * fabs(I), atol) || len >= 16 * switch_boxes)) { status = 3; break; }
-        theta = 0.5 * fmax(mx, theta);
+        const double theta_in = theta;
+        int64_t nsplit = 0;
+        int overflow = 0;
+        for (int attempt = 0; ; attempt++) {
+        theta = 0.5 * fmax(mx, theta_in);
+        const double tol = fmax(rtol * fabs(I), atol);
+        double cnt[2048];
         {   /* threshold from the exponent histogram (see the header comment of csrc/hcub_single.cu) */
-            double cnt[2048];
             for (int b2 = 0; b2 < 2048; b2++) cnt[b2] = 0.0;
             for (int64_t i = 0; i < len; i++) { uint64_t bits; memcpy(&bits, &t[i].E, 8); cnt[(bits >> 52) & 0x7ff] += 1.0; }
-            const double tol = fmax(rtol * fabs(I), atol);
             int bh = -1; double low = 0.0;
             for (int b2 = 0; b2 < 2047; b2++) {
-                if (cnt[b2] != 0.0) { low += cnt[b2] * (b2 == 0 ? 0.0 : scalbn(1.0, b2 - 1023)); if (!(low <= tol)) break; }
+                if (cnt[b2] != 0.0) { low += cnt[b2] * (b2 == 0 ? 0.0 : scalbn(1.0, b2 - 1023)); if (!(low <= tol - Eret)) break; }
                 bh = b2;
             }
             const double remaining = (double)max_boxes - (double)applied;
@@ -1330,16 +1350,68 @@ static int hcub_rounds_core2(orc_integrand f, void *user, int dim, orc_box *t, i
             const double theta_h = bs <= 0 ? 0.0 : (bs >= 2047 ? 1.7976931348623157e308 : scalbn(1.0, bs - 1023));
             theta = fmin(theta, theta_h);
         }
-        int64_t nsplit = 0;
-        for (int64_t i = 0; i < len; i++) if (t[i].E >= theta) nsplit++;
+        /* (4) second attempt (after a retirement): the selection must fit the room left in the arena.  Bins are taken whole from the top
+           while they fit; of the bin that does not fit any more, the first `quota` boxes in store order are taken */
+        double th_hi = theta, th_lo = theta;
+        int64_t quota = 0;
+        if (attempt > 0) {
+            const int64_t room = arena - len;
+            if (room < arena / 64) { overflow = 1; break; }          /* not worth a round: the arena stays full */
+            double up = 0.0;
+            for (int b2 = 2046; b2 >= 0; b2--) {
+                if (cnt[b2] == 0.0) continue;
+                if (up + cnt[b2] > (double)room) {
+                    th_hi = fmax(theta, b2 + 1 >= 2047 ? 1.7976931348623157e308 : scalbn(1.0, b2 + 1 - 1023));
+                    th_lo = fmax(theta, b2 == 0 ? 0.0 : scalbn(1.0, b2 - 1023));
+                    quota = room - (int64_t)up;
+                    break;
+                }
+                up += cnt[b2];
+            }
+        }
+        nsplit = 0;
+        {
+            int64_t nlo = 0;
+            for (int64_t i = 0; i < len; i++) {
+                int take = t[i].E >= th_hi;
+                if (!take && t[i].E >= th_lo) { take = nlo < quota; nlo++; }
+                sel[i] = (char)take;
+                nsplit += take;
+            }
+        }
+        if (attempt > 0 && nsplit == 0) { overflow = 1; break; }
+        if (arena <= 0 || len + nsplit <= arena) break;
+        if (attempt > 0) { overflow = 1; break; }
+        {   /* retirement (see above); the histogram without the selected boxes, as the kernel's selection pass leaves it */
+            for (int64_t i = 0; i < len; i++) if (sel[i]) { uint64_t bits; memcpy(&bits, &t[i].E, 8); cnt[(bits >> 52) & 0x7ff] -= 1.0; }
+            const double R = orc_retire_fraction * (tol - Eret);
+            int br = -1; double acc = 0.0;
+            for (int b2 = 0; b2 <= 2045; b2++) {
+                if (cnt[b2] == 0.0) continue;
+                acc += cnt[b2] * scalbn(1.0, b2 + 1 - 1023);
+                if (!(acc <= R)) break;
+                br = b2;
+            }
+            const double theta_r = fmin(br < 0 ? 0.0 : scalbn(1.0, br + 1 - 1023), theta);
+            int64_t kept = 0;
+            for (int64_t i = 0; i < len; i++) {
+                if (t[i].E >= theta_r) { if (kept != i) t[kept] = t[i]; kept++; }
+                else { Iret += t[i].I; Eret += t[i].E; }
+            }
+            nretired += len - kept;
+            len = kept;
+        }
+        }
+        if (overflow) { status = 1; break; }
         if (len + nsplit > cap) {
             cap = 2 * (len + nsplit);
             t = (orc_box *)realloc(t, sizeof(orc_box) * (size_t)cap);
             todo = (int64_t *)realloc(todo, sizeof(int64_t) * (size_t)cap);
+            sel = (char *)realloc(sel, (size_t)cap);
         }
         const int64_t n0 = len;
         for (int64_t i = 0; i < n0; i++) {
-            if (!(t[i].E >= theta)) continue;
+            if (!sel[i]) continue;
             orc_box box = t[i];
             I -= box.I; E -= box.E;
             int k = box.kdiv;
@@ -1353,7 +1425,9 @@ static int hcub_rounds_core2(orc_integrand f, void *user, int dim, orc_box *t, i
     }
     I = 0.0; E = 0.0;
     for (int64_t i = 0; i < len; i++) { I += t[i].I; E += t[i].E; }
-    free(todo);
+    I += Iret; E += Eret;
+    if (nretired_out) *nretired_out = nretired;
+    free(todo); free(sel);
     if (store_out) *store_out = t; else free(t);
     *Iout = I; *Eout = E;
     if (napplied_out) *napplied_out = applied;
@@ -1385,7 +1459,8 @@ int orc_hcubature_two_level(orc_integrand f, void *user, int dim, const double *
     for (int i = 0; i < dim; i++) { t[0].a[i] = a[i]; t[0].b[i] = b[i]; }
     t[0].I = 0.0; t[0].E = 0.0; t[0].kdiv = 0;
     double I = 0.0, E = 0.0;
-    int st = hcub_rounds_core2(f, user, dim, t, cap, 1, rtol, atol, max_boxes, 0, switch_boxes, switch_factor, &I, &E, &applied, &len, &rounds, &store);
+    int st = hcub_rounds_core2(f, user, dim, t, cap, 1, rtol, atol, max_boxes, 0, switch_boxes, switch_factor, 0, NULL, &I, &E, &applied, &len, &rounds, &store);
+    orc_last_retired = 0;
     if (nsub_out) *nsub_out = 0;
     if (st != 3) {
         free(store);
@@ -1418,7 +1493,9 @@ int orc_hcubature_two_level(orc_integrand f, void *user, int dim, const double *
             tt[0] = b1; tt[1] = b2;
         }
         double Ii = 0.0, Ei = 0.0; int64_t ap = 0, nb = 0, nr = 0;
-        int s2 = hcub_rounds_core(f, user, dim, tt, 1024, 2, 0.0, eps, sub_max_boxes, 0, &Ii, &Ei, &ap, &nb, &nr);
+        int64_t nret = 0;
+        int s2 = hcub_rounds_core2(f, user, dim, tt, 1024, 2, 0.0, eps, sub_max_boxes, 0, 0, 0.0, orc_sub_arena, &nret, &Ii, &Ei, &ap, &nb, &nr, NULL);
+        orc_last_retired += nret;
         if (s2 != 0) status = s2 == 2 ? 2 : (status == 2 ? 2 : 1);
         Is += Ii; Es += Ei; applied += ap; boxes += nb; nsub++;
     }

@@ -400,9 +400,10 @@ def hcubature_rounds(fam, lb, ub, params, tr="if_inf", reltol=1e-8, abstol=1e-8,
 
 
 def hcubature_two_level(fam, lb, ub, params, tr="if_inf", reltol=1e-8, abstol=1e-8, max_boxes=1 << 30, switch_boxes=1 << 20, switch_factor=4096.0,
-                        sub_max_boxes=1 << 40, alpha=None):
+                        sub_max_boxes=1 << 40, alpha=None, sub_arena=0):
     """Two-level refinement of ONE integral (checker for Engine.hcubature_single when the level-1 store is handed over):
-    -> I, E, dict(rule_applications, boxes, rounds, status, level2_subproblems)"""
+    -> I, E, dict(rule_applications, boxes, rounds, status, level2_subproblems, retired_boxes).
+    sub_arena > 0: boxes a sub-problem's store may hold (the engine's single_sub_boxes option), with converged-box retirement."""
     lb = _arr(lb); ub = _arr(ub); params = _arr(np.ravel(params))
     fam = FAM[fam] if isinstance(fam, str) else fam
     d = lb.size
@@ -411,10 +412,15 @@ def hcubature_two_level(fam, lb, ub, params, tr="if_inf", reltol=1e-8, abstol=1e
     L = lib()
     L.orc_hcubature_two_level_family.argtypes = [C.c_int, C.c_int, _dp, _dp, C.c_int, _dp, C.c_double, C.c_double, C.c_int64, C.c_int64, C.c_double,
                                                  C.c_int64, C.c_double, _dp, _dp, _i64p, _i64p, _i64p, _i64p]
-    st = L.orc_hcubature_two_level_family(fam, d, _p(lb), _p(ub), TR[tr], _p(params), reltol, abstol, max_boxes, switch_boxes, switch_factor,
-                                          sub_max_boxes, alpha, C.byref(I), C.byref(E), C.byref(na), C.byref(nb), C.byref(nr), C.byref(ns))
+    C.c_int64.in_dll(L, "orc_sub_arena").value = int(sub_arena)
+    try:
+        st = L.orc_hcubature_two_level_family(fam, d, _p(lb), _p(ub), TR[tr], _p(params), reltol, abstol, max_boxes, switch_boxes, switch_factor,
+                                              sub_max_boxes, alpha, C.byref(I), C.byref(E), C.byref(na), C.byref(nb), C.byref(nr), C.byref(ns))
+    finally:
+        C.c_int64.in_dll(L, "orc_sub_arena").value = 0
     assert st >= 0, st
-    return I.value, E.value, dict(rule_applications=na.value, boxes=nb.value, rounds=nr.value, status=st, level2_subproblems=ns.value)
+    return I.value, E.value, dict(rule_applications=na.value, boxes=nb.value, rounds=nr.value, status=st, level2_subproblems=ns.value,
+                                  retired_boxes=C.c_int64.in_dll(L, "orc_last_retired").value)
 
 
 def solve_hcubature_rounds(f, lb, ub, tr="if_inf", reltol=1e-8, abstol=1e-8, max_boxes=1 << 20, m0=0):

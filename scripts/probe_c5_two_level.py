@@ -17,6 +17,8 @@ if world > 1:
 reltol = float(sys.argv[1])
 if len(sys.argv) > 2: eng.set_option("single_switch_boxes", int(sys.argv[2]))
 if len(sys.argv) > 3: eng.set_option("single_arena_mib", int(sys.argv[3]))
+if os.environ.get("C5_SWITCH_FACTOR"): eng.set_option("single_switch_factor", int(os.environ["C5_SWITCH_FACTOR"]))
+if os.environ.get("C5_SUB_BOXES"): eng.set_option("single_sub_boxes", int(os.environ["C5_SUB_BOXES"]))
 lb, ub, par, exact = WL.c5_problem()
 F = ib.FAMILY_IDS
 eng.hcubature_single(F["genz_gaussian"], 8, lb, ub, par, reltol=1e-4, abstol=0.0, max_boxes=1 << 40)     # warm-up

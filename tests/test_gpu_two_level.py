@@ -65,6 +65,31 @@ def test_two_level_infinite_axes_8d(eng, O):
     assert abs(s["rule_applications"] - sr["rule_applications"]) <= 0.1 * sr["rule_applications"]
 
 
+@pytest.mark.parametrize("arena", [2048, 512])
+def test_two_level_retirement_from_a_full_arena(eng, O, arena):
+    """sub-problems that outgrow their arena retire their converged boxes (only the sums are kept) and go on: the same refinement as the
+    CPU restatement with the same arena (orc_hcubature_two_level, sub_arena), and -- with room to work in -- the tolerance is still met"""
+    par = genz_params("genz_gaussian", 4, 3, scale=0.5)[:, 0]
+    lb, ub = np.zeros(4), np.ones(4)
+    reltol = 1e-9
+    eng.set_option("single_sub_boxes", arena)
+    try:
+        I, E, s = _two_level(eng, "genz_gaussian", 4, lb, ub, par, reltol, 64)
+    finally:
+        eng.set_option("single_sub_boxes", 1 << 17)
+    Ir, Er, sr = O.hcubature_two_level("gauss", lb, ub, par, reltol=reltol, abstol=0.0, max_boxes=1 << 40, switch_boxes=64, sub_arena=arena)
+    assert sr["retired_boxes"] > 0 and "retired" in s["note"] and s["level2_subproblems"] == sr["level2_subproblems"]
+    assert abs(I - Ir) <= 1e-11 * abs(Ir) and abs(E - Er) <= 0.02 * Er
+    assert abs(s["rule_applications"] - sr["rule_applications"]) <= 0.02 * sr["rule_applications"]
+    exact = genz_exact("genz_gaussian", par, 4)
+    assert abs(I - exact) <= 10 * reltol * abs(exact)
+    if arena >= 2048:
+        assert s["status"] == 0 and E <= reltol * abs(I)
+        # against the unbounded store: the same answer within the tolerance, for about the same work
+        I0, E0, s0 = _two_level(eng, "genz_gaussian", 4, lb, ub, par, reltol, 64)
+        assert abs(I - I0) <= reltol * abs(I0) and s["rule_applications"] <= 1.1 * s0["rule_applications"]
+
+
 def test_two_level_result_independent_of_scheduling(eng):
     """a sub-problem's result depends on nothing but the sub-problem, and the chunk sums are added in chunk order: fewer resident warps
     (another assignment of boxes to warps, another arena size) give bitwise the same (I, E)"""
