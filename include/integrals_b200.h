@@ -192,6 +192,28 @@ int32_t ib200_hcubature_vec_batch(ib200_ctx *ctx, int32_t family, int32_t dim, i
                                   double reltol, double abstol, int64_t maxevals, int32_t initdiv, int32_t normkind,
                                   double *out_I, double *out_E, int64_t *out_nevals, int32_t *out_status);
 
+/* -- parameter sensitivities: I and dI/dp_s for chosen parameters s of a registered family, computed as ONE
+      vector-valued integral of [f, df/dp_s1, ..., df/dp_sm] on shared nodes and subdivision.  Replaces differentiating solve() through
+      the integrand: ext/IntegralsForwardDiffExt.jl:55-134 ("a vector-valued integral of the primal and dual simultaneously"; with
+      QuadGKJL / HCubatureJL the dual numbers flow through the quadrature, whose norm sees the value only -> normkind 2) and
+      ext/IntegralsZygoteExt.jl:144-178 (dI/dp as a vector-valued integral of df/dp with the same algorithm -> normkind 0 or 1).
+      params: nparam x nprob (ONE column per problem); sens_idx[nsens]: 0-based indices into the parameter column, 1 <= nsens <= 7;
+      normkind: 0 = 2-norm over all components, 1 = maximum norm, 2 = the value alone drives the refinement.
+      out_I: (1 + nsens) x nprob, column k = [I, dI/dp_s1, ...] of problem k.  The discontinuous Genz family is rejected (the integral
+      of its pointwise derivative is not the derivative of its integral). */
+int32_t ib200_quadgk_sens_batch(ib200_ctx *ctx, int32_t family, int32_t transform,
+                                const double *lb, const double *ub, int32_t bounds_per_problem,
+                                const double *params, int32_t nparam, int64_t nprob,
+                                const int32_t *sens_idx, int32_t nsens,
+                                double reltol, double abstol, int64_t maxevals, int32_t normkind,
+                                double *out_I, double *out_E, int64_t *out_nevals, int32_t *out_status);
+int32_t ib200_hcubature_sens_batch(ib200_ctx *ctx, int32_t family, int32_t dim, int32_t transform,
+                                   const double *lb, const double *ub, int32_t bounds_per_problem,
+                                   const double *params, int32_t nparam, int64_t nprob,
+                                   const int32_t *sens_idx, int32_t nsens,
+                                   double reltol, double abstol, int64_t maxevals, int32_t initdiv, int32_t normkind,
+                                   double *out_I, double *out_E, int64_t *out_nevals, int32_t *out_status);
+
 /* -- one large domain (BASELINE config 5): the same HCubature call, src/Integrals.jl:386-393, for a single
       integral that is too expensive for one warp: region-parallel rounds on a device-resident box queue
       (csrc/hcub_single.cu).  With a communicator (ib200_comm_init) every rank of the job calls this with the

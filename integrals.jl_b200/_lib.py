@@ -24,7 +24,7 @@ ERR_NAMES = {-1: "IB200_ERR_INVALID", -2: "IB200_ERR_CUDA", -3: "IB200_ERR_OOM",
 SYMBOLS = ["ib200_version", "ib200_create", "ib200_destroy", "ib200_last_error", "ib200_set_stream",
            "ib200_synchronize", "ib200_kernel_launches", "ib200_family_nparam", "ib200_last_kernel_ms",
            "ib200_set_option", "ib200_sampled", "ib200_sampled_slab", "ib200_sampled_f32", "ib200_fixed_rule_tensor_batch", "ib200_fixed_rule_nodes_batch",
-           "ib200_gauss_legendre_batch", "ib200_quadgk_batch", "ib200_quadgk_rule_batch", "ib200_quadgk_vec_batch", "ib200_hcubature_batch", "ib200_hcubature_vec_batch", "ib200_measure_fp64_peak",
+           "ib200_gauss_legendre_batch", "ib200_quadgk_batch", "ib200_quadgk_rule_batch", "ib200_quadgk_vec_batch", "ib200_hcubature_batch", "ib200_hcubature_vec_batch", "ib200_quadgk_sens_batch", "ib200_hcubature_sens_batch", "ib200_measure_fp64_peak",
            "ib200_hcubature_single", "ib200_batch_open", "ib200_batch_next", "ib200_batch_points", "ib200_batch_values",
            "ib200_batch_result", "ib200_comm_unique_id", "ib200_comm_init", "ib200_comm_destroy"]
 
@@ -80,6 +80,10 @@ def load_library():
     L.ib200_hcubature_batch.restype = i32
     L.ib200_hcubature_vec_batch.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp, i32, i32, i64, dp, dp, i64, i32, i32, vp, vp, vp, vp]
     L.ib200_hcubature_vec_batch.restype = i32
+    L.ib200_quadgk_sens_batch.argtypes = [vp, i32, i32, vp, vp, i32, vp, i32, i64, vp, i32, dp, dp, i64, i32, vp, vp, vp, vp]
+    L.ib200_quadgk_sens_batch.restype = i32
+    L.ib200_hcubature_sens_batch.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp, i32, i64, vp, i32, dp, dp, i64, i32, i32, vp, vp, vp, vp]
+    L.ib200_hcubature_sens_batch.restype = i32
     L.ib200_hcubature_single.argtypes = [vp, i32, i32, i32, vp, vp, vp, i32, dp, dp, i64, i64, C.POINTER(dp), C.POINTER(dp), vp]
     L.ib200_hcubature_single.restype = i32
     L.ib200_batch_open.argtypes = [vp, i32, i32, vp, vp, dp, dp, i64, i64]; L.ib200_batch_open.restype = i32
@@ -374,6 +378,42 @@ class Engine:
                                                      nparam, ncomp, nprob, float(reltol), float(abstol),
                                                      int(min(maxevals, MAXEVALS_UNBOUNDED)), int(initdiv), {"2": 0, "inf": 1}[norm],
                                                      out_I.ctypes.data, out_E.ctypes.data, out_nevals.ctypes.data, out_status.ctypes.data))
+        return out_I, out_E, out_nevals, out_status
+
+    def sens_batch(self, family, dim, lb, ub, params, wrt, reltol=1e-8, abstol=1e-8, maxevals=MAXEVALS_UNBOUNDED, initdiv=1, transform=0,
+                   norm="value", rule="hcubature"):
+        """Parameter sensitivities: I and dI/dp[wrt] of every problem as ONE vector-valued integral [f, df/dp...] (ib200_quadgk_sens_batch for
+        rule = "quadgk", 1-D; ib200_hcubature_sens_batch otherwise).  params: nparam x nprob; wrt: 1..7 parameter indices (0-based);
+        norm: "value" (the value alone drives the refinement, as dual numbers flowing through the reference's quadrature do), "2" or "inf"
+        (a norm over value and derivatives).  -> out ((1 + len(wrt)) x nprob, column-major: row 0 = I, rows 1.. = dI/dp), E, nevals, status."""
+        params = np.asfortranarray(params, dtype=np.float64)
+        if params.ndim == 1:
+            params = params.reshape(-1, 1, order="F")
+        nparam, nprob = params.shape
+        idx = np.ascontiguousarray(wrt, dtype=np.int32)
+        if idx.ndim != 1 or not 1 <= idx.size <= 7:
+            raise ValueError("wrt: 1 to 7 parameter indices per call")
+        lb = np.asfortranarray(np.atleast_1d(lb), dtype=np.float64); ub = np.asfortranarray(np.atleast_1d(ub), dtype=np.float64)
+        nk = {"2": 0, "inf": 1, "value": 2}[norm]
+        out_I = np.empty((1 + idx.size, nprob), order="F"); out_E = np.empty(nprob)
+        out_nevals = np.empty(nprob, dtype=np.int64); out_status = np.empty(nprob, dtype=np.int32)
+        if rule == "quadgk":
+            if dim != 1:
+                raise ValueError("QuadGKB200 only accepts one-dimensional quadrature problems.")
+            lb = lb.ravel(); ub = ub.ravel()
+            if lb.size not in (1, nprob) or ub.size != lb.size:
+                raise ValueError(f"bounds must be scalars or have {nprob} entries")
+            self._check(self.L.ib200_quadgk_sens_batch(self.h, family, transform, lb.ctypes.data, ub.ctypes.data, int(lb.size != 1), params.ctypes.data,
+                                                       nparam, nprob, idx.ctypes.data, idx.size, float(reltol), float(abstol),
+                                                       int(min(maxevals, MAXEVALS_UNBOUNDED)), nk, out_I.ctypes.data, out_E.ctypes.data,
+                                                       out_nevals.ctypes.data, out_status.ctypes.data))
+        else:
+            if lb.shape != ub.shape or lb.shape[0] != dim or (lb.ndim == 2 and lb.shape[1] != nprob) or lb.ndim > 2:
+                raise ValueError(f"bounds must have {dim} entries or be {dim} x {nprob}")
+            self._check(self.L.ib200_hcubature_sens_batch(self.h, family, dim, transform, lb.ctypes.data, ub.ctypes.data, int(lb.ndim == 2),
+                                                          params.ctypes.data, nparam, nprob, idx.ctypes.data, idx.size, float(reltol), float(abstol),
+                                                          int(min(maxevals, MAXEVALS_UNBOUNDED)), int(initdiv), nk, out_I.ctypes.data,
+                                                          out_E.ctypes.data, out_nevals.ctypes.data, out_status.ctypes.data))
         return out_I, out_E, out_nevals, out_status
 
     def hcubature_single(self, family, dim, lb, ub, params, reltol=1e-8, abstol=1e-8, max_boxes=1 << 24, store_boxes=0,

@@ -39,7 +39,9 @@ struct ib200_ctx {
     int64_t opt_hcub_lpt = 1;                // pair-mode HCubature: pilot pass + longest-expected-first ordering
     double opt_single_round_fraction = 0.5;  // hcub_single.cu: share of the stored boxes one round may bisect
     int64_t opt_single_switch_boxes = 1 << 20;   // hcub_single.cu: level-1 store size at which a solve goes two-level (0 = never)
-    int64_t opt_single_switch_factor = 4096;     // ... provided the error is within this factor of the tolerance (or the store is 16x that size)
+    int64_t opt_single_switch_factor = 0;        // ... provided the error is within this factor of the tolerance (or the store is 64x that size);
+                                                 // 0 = automatic: min(4096, (arena / 16)^(6/dim)) -- a sub-problem needs about (E/tol)^(dim/6) rule
+                                                 // applications, and the average one should fill a sixteenth of its arena at most (hcub_single.cu)
     int64_t opt_single_arena_mib = 0;            // device memory for the level-2 arenas, MiB (0 = 70 % of what is free)
     int64_t opt_single_sub_boxes = 1 << 17;      // boxes a level-2 sub-problem may hold (its warp's arena)
     int64_t opt_hcub_capacity = 0;           // boxes per in-flight problem, 0 = derive from maxevals

@@ -100,7 +100,7 @@ extern "C" int32_t ib200_set_option(ib200_ctx *ctx, const char *key, int64_t val
         ctx->opt_single_round_fraction = (double)value / 100.0;
     }
     else if (k == "single_switch_boxes") ctx->opt_single_switch_boxes = value < 0 ? 0 : value;
-    else if (k == "single_switch_factor") ctx->opt_single_switch_factor = value < 1 ? 1 : value;
+    else if (k == "single_switch_factor") ctx->opt_single_switch_factor = value < 0 ? 0 : value;
     else if (k == "single_arena_mib") ctx->opt_single_arena_mib = value < 0 ? 0 : value;
     else if (k == "single_sub_boxes") ctx->opt_single_sub_boxes = value < 256 ? 256 : (value > (1 << 22) ? (1 << 22) : value);
     else return ib200_fail(ctx, IB200_ERR_INVALID, "ib200_set_option: unknown key " + k);

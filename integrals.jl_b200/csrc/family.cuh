@@ -661,4 +661,159 @@ struct Problem {
     }
 };
 
+// ------------------------------------------------------------------------------------------------
+// Parameter sensitivities: value and gradient of a family with respect to its RAW parameters at one point,
+// out = [f, df/dpar[0], ..., df/dpar[nparam-1]].  The reference differentiates solve() through the integrand -- ForwardDiff duals
+// flowing through the quadrature (ext/IntegralsForwardDiffExt.jl:55-134: "a vector-valued integral of the primal and dual
+// simultaneously") or a second, vector-valued integral of df/dp (ext/IntegralsZygoteExt.jl:144-178); here the derivative of a registered
+// family is written out and integrated as extra components by the vector-valued kernels (ib200_quadgk_sens_batch,
+// ib200_hcubature_sens_batch).  Oracle: orc_family_grad.  The discontinuous family has no entry: the integral of its pointwise
+// derivative is not the derivative of its integral (the support moves with u).
+// ------------------------------------------------------------------------------------------------
+struct SensIdx { int n; int idx[7]; };       // n > 0: sensitivity mode of the vector-valued kernels, components [f, df/dpar[idx[0]], ...]
+template <int FAM, int D> struct Grad {
+    static constexpr bool ok = false;
+    __device__ static void run(const double (&)[D], const double *, double *) {}
+};
+template <int D> struct Grad<IB200_FAM_SINXP, D> {
+    static constexpr bool ok = true;
+    __device__ static void run(const double (&x)[D], const double *par, double *out) {
+        double sn, cs; sincos(x[0] * par[0], &sn, &cs);
+        out[0] = sn; out[1] = x[0] * cs;
+    }
+};
+template <int D> struct Grad<IB200_FAM_GLTEST, D> {
+    static constexpr bool ok = true;
+    __device__ static void run(const double (&x)[D], const double *par, double *out) {
+        const double e = exp_bf(x[0]);
+        out[0] = fma(5.0, x[0], sin(x[0])) - par[0] * e; out[1] = -e;
+    }
+};
+template <int D> struct Grad<IB200_FAM_GENZ_OSC, D> {
+    static constexpr bool ok = true;
+    __device__ static void run(const double (&x)[D], const double *par, double *out) {
+        double s = IB_TWO_PI * par[D];
+#pragma unroll
+        for (int i = 0; i < D; i++) s = fma(par[i], x[i], s);
+        double sn, cs; sincos(s, &sn, &cs);
+        out[0] = cs;
+#pragma unroll
+        for (int i = 0; i < D; i++) { out[1 + i] = -(x[i] * sn); out[1 + D + i] = 0.0; }
+        out[1 + D] = -(IB_TWO_PI * sn);
+    }
+};
+template <int D> struct Grad<IB200_FAM_GENZ_PROD, D> {
+    static constexpr bool ok = true;
+    __device__ static void run(const double (&x)[D], const double *par, double *out) {
+        double T[D], f = 1.0;
+#pragma unroll
+        for (int i = 0; i < D; i++) { const double t = x[i] - par[D + i]; T[i] = 1.0 / fma(t, t, 1.0 / (par[i] * par[i])); f *= T[i]; }
+        out[0] = f;
+#pragma unroll
+        for (int i = 0; i < D; i++) {
+            const double t = x[i] - par[D + i], a = par[i];
+            out[1 + i] = f * (2.0 * T[i]) / (a * a * a);
+            out[1 + D + i] = f * (2.0 * t * T[i]);
+        }
+    }
+};
+template <int D> struct Grad<IB200_FAM_GENZ_CORN, D> {
+    static constexpr bool ok = true;
+    __device__ static void run(const double (&x)[D], const double *par, double *out) {
+        double s = 1.0;
+#pragma unroll
+        for (int i = 0; i < D; i++) s = fma(par[i], x[i], s);
+        const double r = 1.0 / s; double f = r;
+#pragma unroll
+        for (int i = 0; i < D; i++) f *= r;
+        out[0] = f;
+        const double g = -(double)(D + 1) * f * r;
+#pragma unroll
+        for (int i = 0; i < D; i++) { out[1 + i] = g * x[i]; out[1 + D + i] = 0.0; }
+    }
+};
+template <int D> struct Grad<IB200_FAM_GENZ_GAUSS, D> {
+    static constexpr bool ok = true;
+    __device__ static void run(const double (&x)[D], const double *par, double *out) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; i++) { const double t = par[i] * (x[i] - par[D + i]); s = fma(t, t, s); }
+        const double f = exp_bf(-s);
+        out[0] = f;
+#pragma unroll
+        for (int i = 0; i < D; i++) {
+            const double d = x[i] - par[D + i], a = par[i];
+            out[1 + i] = -2.0 * a * d * d * f;
+            out[1 + D + i] = 2.0 * a * a * d * f;
+        }
+    }
+};
+template <int D> struct Grad<IB200_FAM_GENZ_C0, D> {
+    static constexpr bool ok = true;
+    __device__ static void run(const double (&x)[D], const double *par, double *out) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; i++) s = fma(par[i], fabs(x[i] - par[D + i]), s);
+        const double f = exp_bf(-s);
+        out[0] = f;
+#pragma unroll
+        for (int i = 0; i < D; i++) {
+            const double d = x[i] - par[D + i];
+            out[1 + i] = -fabs(d) * f;
+            out[1 + D + i] = (d > 0.0 ? par[i] : (d < 0.0 ? -par[i] : 0.0)) * f;
+        }
+    }
+};
+template <int D> struct Grad<IB200_FAM_COSPROD, D> {
+    static constexpr bool ok = true;
+    __device__ static void run(const double (&x)[D], const double *par, double *out) {
+        double sn[D], cs[D], f = 1.0;
+#pragma unroll
+        for (int i = 0; i < D; i++) { sincos(par[i] * x[i], &sn[i], &cs[i]); f *= cs[i]; }
+        out[0] = f;
+#pragma unroll
+        for (int i = 0; i < D; i++) {
+            double o = -(x[i] * sn[i]);
+#pragma unroll
+            for (int k = 0; k < D; k++) if (k != i) o *= cs[k];
+            out[1 + i] = o;
+        }
+    }
+};
+template <int D> struct Grad<IB200_FAM_GAUSSPOLY, D> {
+    static constexpr bool ok = true;
+    __device__ static void run(const double (&x)[D], const double *par, double *out) {
+        double s = 0.0, pr = 1.0;
+#pragma unroll
+        for (int i = 0; i < D; i++) {
+            const double t = par[i] * (x[i] - par[D + i]);
+            s = fma(t, t, s);
+            const int ki = (int)par[2 * D + i];
+            for (int j = 0; j < ki; j++) pr *= x[i];
+        }
+        const double g = pr * exp_bf(-s), f = par[3 * D] * g;
+        out[0] = f;
+#pragma unroll
+        for (int i = 0; i < D; i++) {
+            const double d = x[i] - par[D + i], a = par[i];
+            out[1 + i] = -2.0 * a * d * d * f;
+            out[1 + D + i] = 2.0 * a * a * d * f;
+            out[1 + 2 * D + i] = 0.0;                 // the monomial exponents are integers: no derivative
+        }
+        out[1 + 3 * D] = g;
+    }
+};
+template <int D> struct Grad<IB200_FAM_EXPLIN, D> {
+    static constexpr bool ok = true;
+    __device__ static void run(const double (&x)[D], const double *par, double *out) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; i++) s = fma(par[i], x[i], s);
+        const double f = exp_bf(s);
+        out[0] = f;
+#pragma unroll
+        for (int i = 0; i < D; i++) out[1 + i] = x[i] * f;
+    }
+};
+
 }  // namespace ib

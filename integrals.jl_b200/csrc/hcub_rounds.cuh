@@ -50,7 +50,7 @@ struct Params {
     long long obcap;
     int grid;
     // two-level solve (hcub_single.cu): hand the store over to the batched sub-problem driver once it holds >= switch_boxes boxes
-    // and the error is within switch_factor of the tolerance (or it holds 16 x switch_boxes boxes); 0 = single level
+    // and the error is within switch_factor of the tolerance (or it holds 64 x switch_boxes boxes); 0 = single level
     long long switch_boxes = 0;
     double switch_factor = 0.0;
 };
@@ -417,7 +417,7 @@ decide_kernel(Params p) {
     if (E <= tol) { st->done = 1; st->status = IB200_ST_CONVERGED; return; }
     if (!isfinite(E)) { st->done = 1; st->status = IB200_ST_NONFINITE; return; }
     if (ap >= (double)p.max_boxes || full > 0.0) { st->done = 1; st->status = IB200_ST_MAXEVALS; return; }
-    if (p.switch_boxes > 0 && nb >= (double)p.switch_boxes && (E <= p.switch_factor * tol || nb >= 16.0 * (double)p.switch_boxes)) {
+    if (p.switch_boxes > 0 && nb >= (double)p.switch_boxes && (E <= p.switch_factor * tol || nb >= 64.0 * (double)p.switch_boxes)) {
         st->done = 1; st->status = kStatusHandover; return;
     }
     st->bound = fmax(mx, st->theta);          // boxes left unsplit by the previous round are below its threshold

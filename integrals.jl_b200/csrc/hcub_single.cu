@@ -501,6 +501,14 @@ extern "C" int32_t ib200_hcubature_single(ib200_ctx *ctx, int32_t family, int32_
     p.rank = ctx->comm ? ctx->comm_rank : 0; p.world = ctx->comm ? ctx->comm_world : 1;
     p.frac = ctx->opt_single_round_fraction;
     p.switch_boxes = ctx->opt_single_switch_boxes; p.switch_factor = (double)ctx->opt_single_switch_factor;
+    if (ctx->opt_single_switch_factor <= 0) {
+        // automatic hand-over: level 2 works best when its sub-problems fit their arenas with room to spare.  A sub-problem handed over at
+        // E = F tol needs about F^(dim/6) rule applications (the error of the degree-7 rule falls like N^(-6/dim) at worst; measured on
+        // BASELINE config 5: F = 4096 in 8-D gives sub-problems of ~1.5e5 applications on average, more than an arena of 131072 boxes holds,
+        // and 12 % of them end there) -> F = (arena / 16)^(6/dim), at most 4096
+        const double f = pow((double)ctx->opt_single_sub_boxes / 16.0, 6.0 / (double)dim);
+        p.switch_factor = f < 4096.0 ? (f < 16.0 ? 16.0 : f) : 4096.0;
+    }
     IB_REQUIRE(ctx, p.world <= hs::kMaxWorld, "ib200_hcubature_single: at most 8 ranks (one box of GPUs)");
     p.grid = ctx->sm_count * 4;
     if (p.grid > hs::kFin) p.grid = hs::kFin;              // scan_kernel scans the block counts in one block

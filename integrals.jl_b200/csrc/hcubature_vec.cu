@@ -12,18 +12,56 @@ template <> int32_t launch<7>(ib200_ctx *, int, Params &);
 template <> int32_t launch<8>(ib200_ctx *, int, Params &);
 }
 
+static int32_t hcubature_vec_impl(ib200_ctx *ctx, int32_t family, int32_t dim, int32_t transform,
+                                  const double *lb, const double *ub, int32_t bpp,
+                                  const double *params, int32_t nparam, int32_t ncomp, int64_t nprob,
+                                  double reltol, double abstol, int64_t maxevals, int32_t initdiv, int32_t normkind, const ib::SensIdx sens,
+                                  double *out_I, double *out_E, int64_t *out_nevals, int32_t *out_status);
+
 extern "C" int32_t ib200_hcubature_vec_batch(ib200_ctx *ctx, int32_t family, int32_t dim, int32_t transform,
                                              const double *lb, const double *ub, int32_t bpp,
                                              const double *params, int32_t nparam, int32_t ncomp, int64_t nprob,
                                              double reltol, double abstol, int64_t maxevals, int32_t initdiv, int32_t normkind,
                                              double *out_I, double *out_E, int64_t *out_nevals, int32_t *out_status) {
     IB_REQUIRE(ctx, ctx != nullptr, "ib200_hcubature_vec_batch: ctx is NULL");
+    IB_REQUIRE(ctx, normkind == 0 || normkind == 1, "ib200_hcubature_vec_batch: norm must be 0 (2-norm) or 1 (maximum norm)");
+    ib::SensIdx none; none.n = 0;
+    return hcubature_vec_impl(ctx, family, dim, transform, lb, ub, bpp, params, nparam, ncomp, nprob, reltol, abstol, maxevals, initdiv, normkind,
+                              none, out_I, out_E, out_nevals, out_status);
+}
+
+// I and dI/dp as one vector-valued integral [f, df/dp_s...] (see ib::Grad, family.cuh)
+extern "C" int32_t ib200_hcubature_sens_batch(ib200_ctx *ctx, int32_t family, int32_t dim, int32_t transform,
+                                              const double *lb, const double *ub, int32_t bpp,
+                                              const double *params, int32_t nparam, int64_t nprob,
+                                              const int32_t *sens_idx, int32_t nsens,
+                                              double reltol, double abstol, int64_t maxevals, int32_t initdiv, int32_t normkind,
+                                              double *out_I, double *out_E, int64_t *out_nevals, int32_t *out_status) {
+    IB_REQUIRE(ctx, ctx != nullptr, "ib200_hcubature_sens_batch: ctx is NULL");
+    IB_REQUIRE(ctx, family >= 0 && family < IB200_FAM_COUNT, "ib200_hcubature_sens_batch: unknown integrand family");
+    IB_REQUIRE(ctx, nsens >= 1 && nsens <= 7 && sens_idx != nullptr, "ib200_hcubature_sens_batch: 1 <= nsens <= 7 parameters to differentiate with respect to");
+    IB_REQUIRE(ctx, normkind >= 0 && normkind <= 2, "ib200_hcubature_sens_batch: norm must be 0 (2-norm), 1 (maximum norm) or 2 (value only)");
+    IB_REQUIRE(ctx, family != IB200_FAM_GENZ_DISC, "ib200_hcubature_sens_batch: the discontinuous family has no parameter sensitivities (its support moves with u)");
+    ib::SensIdx si; si.n = nsens;
+    for (int s = 0; s < 7; s++) {
+        si.idx[s] = s < nsens ? sens_idx[s] : 0;
+        IB_REQUIRE(ctx, si.idx[s] >= 0 && si.idx[s] < nparam, "ib200_hcubature_sens_batch: parameter index out of range");
+    }
+    return hcubature_vec_impl(ctx, family, dim, transform, lb, ub, bpp, params, nparam, 1 + nsens, nprob, reltol, abstol, maxevals, initdiv, normkind,
+                              si, out_I, out_E, out_nevals, out_status);
+}
+
+static int32_t hcubature_vec_impl(ib200_ctx *ctx, int32_t family, int32_t dim, int32_t transform,
+                                  const double *lb, const double *ub, int32_t bpp,
+                                  const double *params, int32_t nparam, int32_t ncomp, int64_t nprob,
+                                  double reltol, double abstol, int64_t maxevals, int32_t initdiv, int32_t normkind, const ib::SensIdx sens,
+                                  double *out_I, double *out_E, int64_t *out_nevals, int32_t *out_status) {
+    IB_REQUIRE(ctx, ctx != nullptr, "ib200_hcubature_vec_batch: ctx is NULL");
     IB_REQUIRE(ctx, family >= 0 && family < IB200_FAM_COUNT, "ib200_hcubature_vec_batch: unknown integrand family");
     IB_REQUIRE(ctx, transform >= 0 && transform <= 2, "ib200_hcubature_vec_batch: unknown transform id");
     IB_REQUIRE(ctx, ib::fam_dim_ok(family, dim), "ib200_hcubature_vec_batch: dimension not supported for this family");
     IB_REQUIRE(ctx, nparam == ib::fam_nparam(family, dim), "ib200_hcubature_vec_batch: nparam does not match the family");
     IB_REQUIRE(ctx, ncomp >= 1 && ncomp <= hv::NC, "ib200_hcubature_vec_batch: 1 <= ncomp <= 8 components");
-    IB_REQUIRE(ctx, normkind == 0 || normkind == 1, "ib200_hcubature_vec_batch: norm must be 0 (2-norm) or 1 (maximum norm)");
     IB_REQUIRE(ctx, !(reltol < 0) && !(abstol < 0), "invalid negative tolerance");        // HCubature ArgumentError
     IB_REQUIRE(ctx, maxevals >= 0, "invalid negative maxevals");
     IB_REQUIRE(ctx, initdiv >= 1, "initdiv must be positive");
@@ -38,7 +76,7 @@ extern "C" int32_t ib200_hcubature_vec_batch(ib200_ctx *ctx, int32_t family, int
     int32_t rc;
     if ((rc = dlb.init(ctx, lb, nb, SL_IN0))) return rc;
     if ((rc = dub.init(ctx, ub, nb, SL_IN1))) return rc;
-    if ((rc = dpar.init(ctx, params, (size_t)nparam * ncomp * nprob, SL_IN2))) return rc;
+    if ((rc = dpar.init(ctx, params, (size_t)nparam * (sens.n > 0 ? 1 : ncomp) * nprob, SL_IN2))) return rc;
     if ((rc = oI.init(ctx, out_I, (size_t)ncomp * nprob, SL_OUT0))) return rc;
     if ((rc = oE.init(ctx, out_E, (size_t)nprob, SL_OUT1))) return rc;
     if ((rc = oN.init(ctx, out_nevals, (size_t)nprob, SL_OUT2))) return rc;
@@ -66,7 +104,7 @@ extern "C" int32_t ib200_hcubature_vec_batch(ib200_ctx *ctx, int32_t family, int
 
     hv::Params p;
     p.params = dpar.d; p.nparam = nparam; p.ncomp = ncomp; p.nprob = nprob; p.lb = dlb.d; p.ub = dub.d; p.bpp = bpp; p.tr = transform;
-    p.rtol = reltol; p.atol = abstol; p.maxevals = maxevals; p.initdiv = initdiv; p.normkind = normkind; p.cap = (int)cap;
+    p.rtol = reltol; p.atol = abstol; p.maxevals = maxevals; p.initdiv = initdiv; p.normkind = normkind; p.sens = sens; p.cap = (int)cap;
     p.keys = p.ivals = p.recs = nullptr; p.counter = counter;
     p.out_I = oI.d; p.out_E = oE.d; p.out_nevals = oN.d; p.out_status = oS.d;
 

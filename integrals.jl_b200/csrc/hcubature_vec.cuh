@@ -28,6 +28,7 @@ struct Params {
     const double *params; int nparam; int ncomp; int64_t nprob;
     const double *lb, *ub; int bpp, tr;
     double rtol, atol; int64_t maxevals; int initdiv; int normkind;
+    ib::SensIdx sens;           // sens.n > 0: sensitivities -- params is nparam x nprob, components [f, df/dpar[idx[0]], ...] (ib::Grad)
     int cap;                    // boxes per warp (multiple of kGroup)
     double *keys;               // [warps][cap]          error of every box
     double *ivals;              // [warps][cap][ncomp]   integral of every box
@@ -38,6 +39,7 @@ struct Params {
 
 __device__ __forceinline__ double vnorm(const double (&v)[NC], int nc, int kind) {
     double r = 0.0;
+    if (kind == 2) return fabs(v[0]);          // the first component alone (sensitivities: a ForwardDiff.Dual's norm is its value's)
     if (kind == 1) {
 #pragma unroll
         for (int c = 0; c < NC; c++) if (c < nc) { const double t = fabs(v[c]); if (t > r || isnan(t)) r = t; }
@@ -133,11 +135,15 @@ hcub_vec_kernel(const Params p) {
 
         // ---- problem data -> shared: prepared parameters of every component, bounds
         __syncwarp();
-        for (int c = lane; c < ncomp; c += 32) {
-            double q[NQ];
-            F::prepare(p.params + ((size_t)prob * ncomp + c) * p.nparam, q);
+        if (p.sens.n > 0) {        // sensitivities: one RAW parameter column per problem
+            for (int t = lane; t < p.nparam; t += 32) qs[t] = p.params[(size_t)prob * p.nparam + t];
+        } else {
+            for (int c = lane; c < ncomp; c += 32) {
+                double q[NQ];
+                F::prepare(p.params + ((size_t)prob * ncomp + c) * p.nparam, q);
 #pragma unroll
-            for (int t = 0; t < NQ; t++) qs[c * NQ + t] = q[t];
+                for (int t = 0; t < NQ; t++) qs[c * NQ + t] = q[t];
+            }
         }
         if (lane < D) {
             lbs[lane] = p.bpp ? p.lb[prob * D + lane] : p.lb[lane];
@@ -151,6 +157,16 @@ hcub_vec_kernel(const Params p) {
         };
         // every component at the point x, times the Jacobian
         auto eval_all = [&](const double (&x)[D], double jac, double (&f)[NC]) {
+            if constexpr (ib::Grad<FAM, D>::ok) {
+                if (p.sens.n > 0) {
+                    double go[1 + ib::fam_nparam(FAM, D)];
+                    ib::Grad<FAM, D>::run(x, qs, go);
+                    f[0] = go[0] * jac;
+#pragma unroll
+                    for (int c = 1; c < NC; c++) f[c] = c < ncomp ? go[1 + p.sens.idx[c - 1]] * jac : 0.0;
+                    return;
+                }
+            }
 #pragma unroll
             for (int c = 0; c < NC; c++) {
                 f[c] = 0.0;

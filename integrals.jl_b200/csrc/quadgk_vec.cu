@@ -65,6 +65,7 @@ __device__ __forceinline__ bool v_endpoint_roundoff(double a, double b) {
 template <int NC>
 __device__ __forceinline__ double vnorm(const double (&v)[NC], int nc, int kind) {
     double r = 0.0;
+    if (kind == 2) return fabs(v[0]);          // the first component alone (sensitivities: a ForwardDiff.Dual's norm is its value's)
     if (kind == 1) {
 #pragma unroll
         for (int c = 0; c < NC; c++) if (c < nc) { const double t = fabs(v[c]); if (t > r || isnan(t)) r = t; }
@@ -79,7 +80,7 @@ template <int FAM, bool ALLFIN, int NC>
 __global__ void __launch_bounds__(kBlock, 1)
 quadgk_vec_kernel(const double *__restrict__ params, int nparam, int ncomp, int64_t nprob,
                   const double *__restrict__ lb, const double *__restrict__ ub, int bpp, int tr,
-                  double rtol, double atol, int64_t maxevals, int normkind, int capS, int capG, double *__restrict__ arena,
+                  double rtol, double atol, int64_t maxevals, int normkind, const ib::SensIdx sens, int capS, int capG, double *__restrict__ arena,
                   unsigned long long *__restrict__ counter,
                   double *__restrict__ out_I, double *__restrict__ out_E, int64_t *__restrict__ out_nevals,
                   int32_t *__restrict__ out_status) {
@@ -119,11 +120,15 @@ quadgk_vec_kernel(const double *__restrict__ params, int nparam, int ncomp, int6
         const double den = (u_ - l) * 0.5;
         const double tlo = ALLFIN ? -1.0 : ax.tlo, thi = ALLFIN ? 1.0 : ax.thi;
         __syncwarp();
-        for (int c = lane; c < ncomp; c += 32) {
-            double q[NQ];
-            Fm::prepare(params + ((size_t)prob * ncomp + c) * nparam, q);
+        if (sens.n > 0) {          // sensitivities: ONE parameter column per problem, kept raw (ib::Grad differentiates with respect to it)
+            for (int t = lane; t < nparam; t += 32) qs[t] = params[(size_t)prob * nparam + t];
+        } else {
+            for (int c = lane; c < ncomp; c += 32) {
+                double q[NQ];
+                Fm::prepare(params + ((size_t)prob * ncomp + c) * nparam, q);
 #pragma unroll
-            for (int t = 0; t < NQ; t++) qs[c * NQ + t] = q[t];
+                for (int t = 0; t < NQ; t++) qs[c * NQ + t] = q[t];
+            }
         }
         __syncwarp();
 
@@ -139,12 +144,25 @@ quadgk_vec_kernel(const double *__restrict__ params, int nparam, int ncomp, int6
                 double x[1], jac;
                 if (ALLFIN) { x[0] = l + (1.0 + t) * den; jac = den; }
                 else ib::t2ujac(tr, t, ax, x[0], jac);
+                bool done = false;
+                if constexpr (ib::Grad<FAM, 1>::ok) {
+                    if (sens.n > 0) {
+                        double go[1 + ib::fam_nparam(FAM, 1)];
+                        ib::Grad<FAM, 1>::run(x, qs, go);
+                        g[0] = go[0] * jac;
 #pragma unroll
-                for (int c = 0; c < NC; c++) if (c < ncomp) {
-                    double q[NQ];
+                        for (int c = 1; c < NC; c++) if (c < ncomp) g[c] = go[1 + sens.idx[c - 1]] * jac;
+                        done = true;
+                    }
+                }
+                if (!done) {
 #pragma unroll
-                    for (int t2 = 0; t2 < NQ; t2++) q[t2] = qs[c * NQ + t2];
-                    g[c] = Fm::eval(x, q) * jac;
+                    for (int c = 0; c < NC; c++) if (c < ncomp) {
+                        double q[NQ];
+#pragma unroll
+                        for (int t2 = 0; t2 < NQ; t2++) q[t2] = qs[c * NQ + t2];
+                        g[c] = Fm::eval(x, q) * jac;
+                    }
                 }
             }
 #pragma unroll
@@ -241,18 +259,56 @@ quadgk_vec_kernel(const double *__restrict__ params, int nparam, int ncomp, int6
 
 }  // namespace
 
+static int32_t quadgk_vec_impl(ib200_ctx *ctx, int32_t family, int32_t transform,
+                               const double *lb, const double *ub, int32_t bpp,
+                               const double *params, int32_t nparam, int32_t ncomp, int64_t nprob,
+                               double reltol, double abstol, int64_t maxevals, int32_t normkind, const ib::SensIdx sens,
+                               double *out_I, double *out_E, int64_t *out_nevals, int32_t *out_status);
+
 extern "C" int32_t ib200_quadgk_vec_batch(ib200_ctx *ctx, int32_t family, int32_t transform,
                                           const double *lb, const double *ub, int32_t bpp,
                                           const double *params, int32_t nparam, int32_t ncomp, int64_t nprob,
                                           double reltol, double abstol, int64_t maxevals, int32_t normkind,
                                           double *out_I, double *out_E, int64_t *out_nevals, int32_t *out_status) {
     IB_REQUIRE(ctx, ctx != nullptr, "ib200_quadgk_vec_batch: ctx is NULL");
+    IB_REQUIRE(ctx, normkind == 0 || normkind == 1, "ib200_quadgk_vec_batch: norm must be 0 (2-norm) or 1 (maximum norm)");
+    ib::SensIdx none; none.n = 0;
+    return quadgk_vec_impl(ctx, family, transform, lb, ub, bpp, params, nparam, ncomp, nprob, reltol, abstol, maxevals, normkind, none,
+                           out_I, out_E, out_nevals, out_status);
+}
+
+// I and dI/dp as one vector-valued integral [f, df/dp_s...] (see ib::Grad, family.cuh)
+extern "C" int32_t ib200_quadgk_sens_batch(ib200_ctx *ctx, int32_t family, int32_t transform,
+                                           const double *lb, const double *ub, int32_t bpp,
+                                           const double *params, int32_t nparam, int64_t nprob,
+                                           const int32_t *sens_idx, int32_t nsens,
+                                           double reltol, double abstol, int64_t maxevals, int32_t normkind,
+                                           double *out_I, double *out_E, int64_t *out_nevals, int32_t *out_status) {
+    IB_REQUIRE(ctx, ctx != nullptr, "ib200_quadgk_sens_batch: ctx is NULL");
+    IB_REQUIRE(ctx, family >= 0 && family < IB200_FAM_COUNT, "ib200_quadgk_sens_batch: unknown integrand family");
+    IB_REQUIRE(ctx, nsens >= 1 && nsens <= 7 && sens_idx != nullptr, "ib200_quadgk_sens_batch: 1 <= nsens <= 7 parameters to differentiate with respect to");
+    IB_REQUIRE(ctx, normkind >= 0 && normkind <= 2, "ib200_quadgk_sens_batch: norm must be 0 (2-norm), 1 (maximum norm) or 2 (value only)");
+    IB_REQUIRE(ctx, family != IB200_FAM_GENZ_DISC, "ib200_quadgk_sens_batch: the discontinuous family has no parameter sensitivities (its support moves with u)");
+    ib::SensIdx si; si.n = nsens;
+    for (int s = 0; s < 7; s++) {
+        si.idx[s] = s < nsens ? sens_idx[s] : 0;
+        IB_REQUIRE(ctx, si.idx[s] >= 0 && si.idx[s] < nparam, "ib200_quadgk_sens_batch: parameter index out of range");
+    }
+    return quadgk_vec_impl(ctx, family, transform, lb, ub, bpp, params, nparam, 1 + nsens, nprob, reltol, abstol, maxevals, normkind, si,
+                           out_I, out_E, out_nevals, out_status);
+}
+
+static int32_t quadgk_vec_impl(ib200_ctx *ctx, int32_t family, int32_t transform,
+                               const double *lb, const double *ub, int32_t bpp,
+                               const double *params, int32_t nparam, int32_t ncomp, int64_t nprob,
+                               double reltol, double abstol, int64_t maxevals, int32_t normkind, const ib::SensIdx sens,
+                               double *out_I, double *out_E, int64_t *out_nevals, int32_t *out_status) {
+    IB_REQUIRE(ctx, ctx != nullptr, "ib200_quadgk_vec_batch: ctx is NULL");
     IB_REQUIRE(ctx, family >= 0 && family < IB200_FAM_COUNT, "ib200_quadgk_vec_batch: unknown integrand family");
     IB_REQUIRE(ctx, transform >= 0 && transform <= 2, "ib200_quadgk_vec_batch: unknown transform id");
     IB_REQUIRE(ctx, ib::fam_dim_ok(family, 1) && nparam == ib::fam_nparam(family, 1),
                "QuadGKB200 only accepts one-dimensional quadrature problems.");          // Integrals.jl:263-266
     IB_REQUIRE(ctx, ncomp >= 1 && ncomp <= 8, "ib200_quadgk_vec_batch: 1 <= ncomp <= 8 components");
-    IB_REQUIRE(ctx, normkind == 0 || normkind == 1, "ib200_quadgk_vec_batch: norm must be 0 (2-norm) or 1 (maximum norm)");
     IB_REQUIRE(ctx, !(reltol < 0) && !(abstol < 0), "ib200_quadgk_vec_batch: negative tolerance");
     IB_REQUIRE(ctx, nprob >= 0, "ib200_quadgk_vec_batch: negative nprob");
     if (nprob == 0) return IB200_OK;
@@ -266,7 +322,7 @@ extern "C" int32_t ib200_quadgk_vec_batch(ib200_ctx *ctx, int32_t family, int32_
     int32_t rc;
     if ((rc = dlb.init(ctx, lb, nb, SL_IN0))) return rc;
     if ((rc = dub.init(ctx, ub, nb, SL_IN1))) return rc;
-    if ((rc = dpar.init(ctx, params, (size_t)nparam * ncomp * nprob, SL_IN2))) return rc;
+    if ((rc = dpar.init(ctx, params, (size_t)nparam * (sens.n > 0 ? 1 : ncomp) * nprob, SL_IN2))) return rc;
     if ((rc = oI.init(ctx, out_I, (size_t)ncomp * nprob, SL_OUT0))) return rc;
     if ((rc = oE.init(ctx, out_E, (size_t)nprob, SL_OUT1))) return rc;
     if ((rc = oN.init(ctx, out_nevals, (size_t)nprob, SL_OUT2))) return rc;
@@ -301,7 +357,7 @@ extern "C" int32_t ib200_quadgk_vec_batch(ib200_ctx *ctx, int32_t family, int32_
                 const size_t smem = (size_t)kWarps * ((size_t)(3 + nc_t) * capS + (size_t)nc_t * ib::Family<FAM, 1>::NQ) * sizeof(double);
                 attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 kern<<<(unsigned)blocks, kBlock, smem, ctx->stream>>>(dpar.d, nparam, ncomp, nprob, dlb.d, dub.d, bpp, transform,
-                                                                     reltol, abstol, maxevals, normkind, capS, (int)capG, arena, counter,
+                                                                     reltol, abstol, maxevals, normkind, sens, capS, (int)capG, arena, counter,
                                                                      oI.d, oE.d, oN.d, oS.d);
                 launched = true;
             };

@@ -199,8 +199,9 @@ class SampledIntegralProblem:
 
 
 class IntegralSolution:
-    def __init__(self, u, resid, prob, alg, retcode=ReturnCode.Success, chi=None, stats=None):
+    def __init__(self, u, resid, prob, alg, retcode=ReturnCode.Success, chi=None, stats=None, du_dp=None):
         self.u, self.resid, self.prob, self.alg, self.retcode, self.chi, self.stats = u, resid, prob, alg, retcode, chi, stats
+        self.du_dp = du_dp          # parameter sensitivities (sensealg = ParameterSensitivities): len(wrt) [x nprob]
 
     def __repr__(self):
         return f"IntegralSolution(u={self.u!r}, resid={self.resid!r}, retcode={self.retcode})"
@@ -211,6 +212,21 @@ class IntegralSolution:
 # ---------------------------------------------------------------------------------------------
 class AbstractB200Algorithm:
     pass
+
+
+class ParameterSensitivities:
+    """`sensealg` for solve / init: return dI/dp next to I (`sol.du_dp`).  The reference differentiates solve() through the integrand --
+    ForwardDiff duals flowing through QuadGKJL / HCubatureJL (ext/IntegralsForwardDiffExt.jl:14-50: the quadrature's norm sees the value
+    only -> control = "value"), or the vector-valued integral of df/dp that the Zygote rule solves with the same algorithm
+    (ext/IntegralsZygoteExt.jl:144-178 -> control = "2" / "inf": a norm over value and derivatives).  Here the derivative of a registered
+    family is written out on the device (csrc/family.cuh Grad) and integrated as extra components on the nodes and subdivision of I.
+    wrt: parameter indices (0-based rows of `p`); None = every parameter.  More than 7 are solved in groups of 7."""
+
+    def __init__(self, wrt=None, control="value"):
+        if control not in ("value", "2", "inf"):
+            raise ValueError('ParameterSensitivities: control is "value", "2" or "inf"')
+        self.wrt = None if wrt is None else [int(i) for i in wrt]
+        self.control = control
 
 
 class QuadGKB200(AbstractB200Algorithm):
@@ -331,10 +347,11 @@ class IntegralCache:
     """init(prob, alg; kwargs...) result (src/common.jl:1-12).  `cacheval` is the engine context: its
     device scratch is reused by every solve (QuadGK segbuf / HCubature buffer analogue)."""
 
-    def __init__(self, prob, alg, kwargs, engine):
+    def __init__(self, prob, alg, kwargs, engine, sensealg=None):
         self.f, self.domain, self.p = prob.f, prob.domain, prob.p
         self.prob_kwargs = prob.kwargs
         self.alg, self.kwargs, self.cacheval = alg, kwargs, engine
+        self.sensealg = sensealg
 
     @property
     def lb(self):
@@ -349,8 +366,9 @@ class IntegralCache:
 
 
 def init(prob, alg, engine=None, sensealg=None, do_inf_transformation=None, verbose=None, **kws):
-    """init(prob, alg; sensealg, do_inf_transformation, verbose, kws...) (src/common.jl:79-133).  `sensealg` (AD), the
-    deprecated `do_inf_transformation` and `verbose` are accepted like the reference does and have no effect here."""
+    """init(prob, alg; sensealg, do_inf_transformation, verbose, kws...) (src/common.jl:79-133).  `sensealg`: a ParameterSensitivities
+    makes the solve return dI/dp as well (the reference's AD back-ends, which cannot see through a device-side integrand, are otherwise
+    accepted and ignored); the deprecated `do_inf_transformation` and `verbose` are accepted like the reference does and have no effect."""
     if isinstance(prob, SampledIntegralProblem):
         return _init_sampled(prob, alg, engine, **kws)
     kwargs = {**prob.kwargs, **kws}                      # problem kwargs under solve kwargs, common.jl:87
@@ -361,7 +379,7 @@ def init(prob, alg, engine=None, sensealg=None, do_inf_transformation=None, verb
         alg = ChangeOfVariables(transformation_if_inf, alg)   # always for tuple domains, common.jl:97-103
     if not isinstance(alg.alg, AbstractB200Algorithm):
         raise TypeError(f"{type(alg.alg).__name__} is not a B200 integration algorithm")
-    return IntegralCache(prob, alg, kwargs, engine or _lib.default_engine())
+    return IntegralCache(prob, alg, kwargs, engine or _lib.default_engine(), sensealg if isinstance(sensealg, ParameterSensitivities) else None)
 
 
 def solve(prob, alg=None, engine=None, **kws):
@@ -380,6 +398,8 @@ def solve_cache(cache):
         return _solve_batch_function(cache, prob, inner, tr)
     if isinstance(cache.f, VectorOf):
         return _solve_vector(cache, prob, inner, tr)
+    if getattr(cache, "sensealg", None) is not None:
+        return _solve_sensitivities(cache, prob, inner, tr)
     dim, lb, ub, p, nprob, scalar = _problem_shapes(prob)
     fam = cache.f.family
     if not cache.f.supports_dim(dim):
@@ -433,6 +453,48 @@ def solve_cache(cache):
     if scalar and not hasattr(I, "data_ptr"):
         I = float(I[0]); E = None if E is None else float(E[0])
     return IntegralSolution(I, E, prob, inner, retcode, None, stats)   # Success (Integrals.jl:338,396) unless the engine's store filled up
+
+
+def _solve_sensitivities(cache, prob, inner, tr):
+    """I and dI/dp as one vector-valued integral (ParameterSensitivities; engine.sens_batch)"""
+    sa = cache.sensealg
+    dim, lb, ub, p, nprob, scalar = _problem_shapes(prob)
+    if hasattr(p, "data_ptr") or hasattr(lb, "data_ptr"):
+        raise TypeError("parameter sensitivities take host (numpy) parameters and bounds")
+    if not cache.f.supports_dim(dim):
+        raise ValueError(f"{cache.f!r} is not defined in {dim} dimensions")
+    if isinstance(inner, QuadGKB200):
+        if dim != 1:
+            raise ValueError("QuadGKB200 only accepts one-dimensional quadrature problems.")    # Integrals.jl:263-266
+        if inner.order != 7:
+            raise ValueError("parameter sensitivities use the (7,15) pair")
+        rule, extra = "quadgk", {}
+    elif isinstance(inner, HCubatureB200) and not inner.single_domain:
+        rule, extra = "hcubature", {"initdiv": inner.initdiv}
+    else:
+        raise TypeError("parameter sensitivities are computed by QuadGKB200 and HCubatureB200")
+    kw = cache.kwargs
+    maxiters = kw.get("maxiters", _lib.MAXEVALS_UNBOUNDED)
+    nparam = p.shape[0]
+    wrt = list(range(nparam)) if sa.wrt is None else sa.wrt
+    if not wrt or any(not 0 <= i < nparam for i in wrt):
+        raise ValueError(f"ParameterSensitivities: wrt indexes the {nparam} parameters of {cache.f!r}")
+    I = E = ne = st = None
+    dI = np.empty((len(wrt), nprob), order="F")
+    for g0 in range(0, len(wrt), 7):                     # the kernels carry up to 8 components: the value + 7 derivatives per pass
+        grp = wrt[g0:g0 + 7]
+        out, Eg, neg, stg = cache.cacheval.sens_batch(cache.f.family, dim, lb, ub, p, grp, reltol=kw.get("reltol", 1e-8), abstol=kw.get("abstol", 1e-8),
+                                                      maxevals=maxiters, transform=tr, norm=sa.control, rule=rule, **extra)
+        dI[g0:g0 + len(grp)] = out[1:]
+        if I is None:
+            I, E, ne, st = out[0].copy(), Eg, neg, stg
+        else:                                            # the worst of the groups
+            E = np.maximum(E, Eg); ne = np.maximum(ne, neg); st = np.maximum(st, stg)
+    retcode = retcode_of(inner, st, ne, maxiters)
+    stats = dict(nevals=ne, status=st, wrt=wrt, control=sa.control)
+    if scalar:
+        return IntegralSolution(float(I[0]), float(E[0]), prob, inner, retcode, None, stats, du_dp=dI[:, 0].copy())
+    return IntegralSolution(I, E, prob, inner, retcode, None, stats, du_dp=dI)
 
 
 def _solve_batch_function(cache, prob, inner, tr):

@@ -121,6 +121,116 @@ double orc_family_eval(int fam, int dim, const double *x, const double *par)
     }
 }
 
+/* value and gradient with respect to the raw parameters at one point: out = [f, df/dpar[0..nparam-1]] (the
+   derivative the reference obtains by differentiating the integrand, ext/IntegralsForwardDiffExt.jl:55-134,
+   ext/IntegralsZygoteExt.jl:144-178).  Returns -1 for families without one (discontinuous: its support moves with u). */
+int orc_family_grad(int fam, int dim, const double *x, const double *par, double *out)
+{
+    const double *a = par, *u = par + dim;
+    switch (fam) {
+    case ORC_FAM_SINXP:
+        out[0] = sin(x[0] * par[0]); out[1] = x[0] * cos(x[0] * par[0]);
+        return 0;
+    case ORC_FAM_GLTEST:
+        out[0] = fma(5.0, x[0], sin(x[0])) - par[0] * exp(x[0]); out[1] = -exp(x[0]);
+        return 0;
+    case ORC_FAM_GENZ_OSC: {
+        double s = ORC_TWO_PI * u[0];
+        for (int i = 0; i < dim; i++) s = fma(a[i], x[i], s);
+        out[0] = cos(s);
+        for (int i = 0; i < dim; i++) { out[1 + i] = -(x[i] * sin(s)); out[1 + dim + i] = 0.0; }
+        out[1 + dim] = -(ORC_TWO_PI * sin(s));
+        return 0;
+    }
+    case ORC_FAM_GENZ_PRODPEAK: {
+        double T[ORC_MAXDIM], f = 1.0;
+        for (int i = 0; i < dim; i++) { double t = x[i] - u[i]; T[i] = 1.0 / fma(t, t, 1.0 / (a[i] * a[i])); f *= T[i]; }
+        out[0] = f;
+        for (int i = 0; i < dim; i++) {
+            double t = x[i] - u[i];
+            out[1 + i] = f * (2.0 * T[i]) / (a[i] * a[i] * a[i]);
+            out[1 + dim + i] = f * (2.0 * t * T[i]);
+        }
+        return 0;
+    }
+    case ORC_FAM_GENZ_CORNER: {
+        double s = 1.0;
+        for (int i = 0; i < dim; i++) s = fma(a[i], x[i], s);
+        double r = 1.0 / s, f = r;
+        for (int i = 0; i < dim; i++) f *= r;
+        out[0] = f;
+        double g = -(double)(dim + 1) * f * r;
+        for (int i = 0; i < dim; i++) { out[1 + i] = g * x[i]; out[1 + dim + i] = 0.0; }
+        return 0;
+    }
+    case ORC_FAM_GENZ_GAUSS: {
+        double s = 0.0;
+        for (int i = 0; i < dim; i++) { double t = a[i] * (x[i] - u[i]); s = fma(t, t, s); }
+        double f = exp(-s);
+        out[0] = f;
+        for (int i = 0; i < dim; i++) {
+            double d = x[i] - u[i];
+            out[1 + i] = -2.0 * a[i] * d * d * f;
+            out[1 + dim + i] = 2.0 * a[i] * a[i] * d * f;
+        }
+        return 0;
+    }
+    case ORC_FAM_GENZ_C0: {
+        double s = 0.0;
+        for (int i = 0; i < dim; i++) s = fma(a[i], fabs(x[i] - u[i]), s);
+        double f = exp(-s);
+        out[0] = f;
+        for (int i = 0; i < dim; i++) {
+            double d = x[i] - u[i];
+            out[1 + i] = -fabs(d) * f;
+            out[1 + dim + i] = (d > 0.0 ? a[i] : (d < 0.0 ? -a[i] : 0.0)) * f;
+        }
+        return 0;
+    }
+    case ORC_FAM_COSPROD: {
+        double f = 1.0;
+        for (int i = 0; i < dim; i++) f *= cos(par[i] * x[i]);
+        out[0] = f;
+        for (int i = 0; i < dim; i++) {
+            double o = -(x[i] * sin(par[i] * x[i]));
+            for (int k = 0; k < dim; k++) if (k != i) o *= cos(par[k] * x[k]);
+            out[1 + i] = o;
+        }
+        return 0;
+    }
+    case ORC_FAM_GAUSSPOLY: {
+        const double *k = par + 2 * dim;
+        double s = 0.0, pr = 1.0;
+        for (int i = 0; i < dim; i++) {
+            double t = a[i] * (x[i] - u[i]);
+            s = fma(t, t, s);
+            int ki = (int)k[i];
+            for (int j = 0; j < ki; j++) pr *= x[i];
+        }
+        double g = pr * exp(-s), f = par[3 * dim] * g;
+        out[0] = f;
+        for (int i = 0; i < dim; i++) {
+            double d = x[i] - u[i];
+            out[1 + i] = -2.0 * a[i] * d * d * f;
+            out[1 + dim + i] = 2.0 * a[i] * a[i] * d * f;
+            out[1 + 2 * dim + i] = 0.0;
+        }
+        out[1 + 3 * dim] = g;
+        return 0;
+    }
+    case ORC_FAM_EXPLIN: {
+        double s = 0.0;
+        for (int i = 0; i < dim; i++) s = fma(par[i], x[i], s);
+        double f = exp(s);
+        out[0] = f;
+        for (int i = 0; i < dim; i++) out[1 + i] = x[i] * f;
+        return 0;
+    }
+    default:
+        return -1;
+    }
+}
+
 double orc_family_integrand(const double *x, int dim, void *user)
 {
     const orc_family_user *fu = (const orc_family_user *)user;
@@ -674,6 +784,7 @@ static double vnorm(const double *v, int n, int kind)
 {
     double r = 0.0;
     if (kind == 1) { for (int i = 0; i < n; i++) if (fabs(v[i]) > r || isnan(v[i])) r = fabs(v[i]); return r; }
+    if (kind == 2) return fabs(v[0]);   /* the first component alone: a ForwardDiff.Dual's norm is the norm of its value */
     /* LinearAlgebra.norm (generic_norm2) rescales by the maximum to avoid overflow; for the magnitudes of integrals
        a plain sqrt(sum of squares) differs from it by rounding only */
     for (int i = 0; i < n; i++) r += v[i] * v[i];
@@ -1257,6 +1368,79 @@ int orc_hcubature_vec_batch(int fam, int dim, const double *lb, const double *ub
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Parameter sensitivities: I and dI/dp_s for chosen parameters s, as ONE vector-valued integral of
+ * [f, df/dp_s1, ...] on shared nodes and subdivision -- the reference's ForwardDiff path ("a vector-valued integral of the primal and dual
+ * simultaneously", ext/IntegralsForwardDiffExt.jl:55-134; with QuadGKJL / HCubatureJL the duals flow through the quadrature and its norm
+ * sees the value only: normkind 2) and its Zygote path (a vector-valued integral of df/dp, ext/IntegralsZygoteExt.jl:144-178: normkind 0).
+ * Checker of ib200_quadgk_sens_batch / ib200_hcubature_sens_batch.  params: nparam x nprob; I: (1 + nsens) x nprob.
+ * ------------------------------------------------------------------------------------------ */
+#define ORC_MAXPARAM 32
+typedef struct { int fam, dim, nparam, tr, nsens; const int *idx; const double *par; const double *lb, *ub; } orc_sens_user;
+static void orc_sens_eval(const double *t, int dim, void *user, double *out)
+{
+    const orc_sens_user *u = (const orc_sens_user *)user;
+    double x[ORC_MAXDIM], jac = 1.0, g[1 + ORC_MAXPARAM];
+    for (int i = 0; i < dim; i++) {
+        double ji;
+        orc_t2ujac(u->tr, t[i], u->lb[i], u->ub[i], &x[i], &ji);
+        jac = (i == 0) ? ji : jac * ji;
+    }
+    orc_family_grad(u->fam, dim, x, u->par, g);
+    out[0] = g[0] * jac;
+    for (int s = 0; s < u->nsens; s++) out[1 + s] = g[1 + u->idx[s]] * jac;
+}
+static int sens_args_ok(int fam, int dim, int nparam, const int *idx, int nsens)
+{
+    double x[ORC_MAXDIM] = {0}, par[ORC_MAXPARAM] = {0}, g[1 + ORC_MAXPARAM];
+    for (int i = 0; i < ORC_MAXPARAM; i++) par[i] = 1.0;
+    if (orc_family_nparam(fam, dim) != nparam || nparam > ORC_MAXPARAM || nsens < 0 || 1 + nsens > ORC_MAXCOMP) return 0;
+    for (int s = 0; s < nsens; s++) if (idx[s] < 0 || idx[s] >= nparam) return 0;
+    return orc_family_grad(fam, dim, x, par, g) == 0;
+}
+int orc_quadgk_sens_batch(int fam, const double *lb, const double *ub, int bpp, int tr,
+                          const double *params, int nparam, int64_t nprob, const int *idx, int nsens,
+                          double reltol, double abstol, int64_t maxiters, int normkind,
+                          double *I, double *E, int64_t *nevals, int32_t *status, int nthreads)
+{
+    if (!sens_args_ok(fam, 1, nparam, idx, nsens)) return -1;
+    if (nthreads < 1) nthreads = 1;
+    const int nc = 1 + nsens;
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads)
+    for (int64_t k = 0; k < nprob; k++) {
+        const double l = bpp ? lb[k] : lb[0], uu = bpp ? ub[k] : ub[0];
+        orc_sens_user u = {fam, 1, nparam, tr, nsens, idx, params + (size_t)k * nparam, &l, &uu};
+        double tl, tu;
+        orc_u2t(l, uu, &tl, &tu);
+        int64_t ne = 0;
+        status[k] = orc_quadgk_vec(orc_sens_eval, &u, nc, tl, tu, reltol, abstol, maxiters, normkind, I + (size_t)k * nc, &E[k], &ne);
+        nevals[k] = ne;
+    }
+    return 0;
+}
+int orc_hcubature_sens_batch(int fam, int dim, const double *lb, const double *ub, int bpp, int tr,
+                             const double *params, int nparam, int64_t nprob, const int *idx, int nsens,
+                             double reltol, double abstol, int64_t maxiters, int initdiv, int normkind,
+                             double *I, double *E, int64_t *nevals, int32_t *status, int nthreads)
+{
+    if (!sens_args_ok(fam, dim, nparam, idx, nsens)) return -1;
+    if (nthreads < 1) nthreads = 1;
+    const int nc = 1 + nsens;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+    for (int64_t k = 0; k < nprob; k++) {
+        const double *l = bpp ? lb + k * dim : lb, *uu = bpp ? ub + k * dim : ub;
+        orc_sens_user u = {fam, dim, nparam, tr, nsens, idx, params + (size_t)k * nparam, l, uu};
+        double tl[ORC_MAXDIM], tu[ORC_MAXDIM];
+        for (int i = 0; i < dim; i++) orc_u2t(l[i], uu[i], &tl[i], &tu[i]);
+        int64_t ne = 0;
+        int st = orc_hcubature_vec(orc_sens_eval, &u, nc, dim, tl, tu, reltol, abstol, maxiters, initdiv, normkind,
+                                   I + (size_t)k * nc, &E[k], &ne);
+        if (nevals) nevals[k] = ne;
+        if (status) status[k] = st;
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
  * Round-synchronous variant of the HCubature loop (NOT in the reference): the checker for
  * ib200_hcubature_single (csrc/hcub_single.cu), which replaces the strictly sequential "pop the
  * worst box" order of HCubature.hcubature (call site src/Integrals.jl:386-393) by rounds --
@@ -1288,7 +1472,7 @@ static int hcub_rounds_core(orc_integrand f, void *user, int dim, orc_box *t, in
                              rounds_out, NULL);
 }
 /* switch_boxes > 0: the two-level solve (orc_hcubature_two_level) -- stop with status 3 ("hand over") after the stopping test of a round
-   once the store holds >= switch_boxes boxes AND E <= switch_factor * tol (or the store holds >= 16 * switch_boxes boxes), and return the
+   once the store holds >= switch_boxes boxes AND E <= switch_factor * tol (or the store holds >= 64 * switch_boxes boxes), and return the
    store (unsplit, every box evaluated) through store_out instead of freeing it.
    arena > 0: the store may hold at most `arena` boxes (a level-2 sub-problem's arena, csrc/hcubature_rb.cuh).  When the boxes selected by
    a round would not fit, the converged boxes are RETIRED first -- every box whose error lies below theta_r leaves the store, its integral
@@ -1323,7 +1507,7 @@ static int hcub_rounds_core2(orc_integrand f, void *user, int dim, orc_box *t, i
         if (!isfinite(E)) { status = 2; break; }
         if (applied >= max_boxes) { status = 1; break; }
         if (switch_boxes > 0 && len >= switch_boxes &&
-            (E <= switch_factor * fmax(rtol * fabs(I), atol) || len >= 16 * switch_boxes)) { status = 3; break; }
+            (E <= switch_factor * fmax(rtol * fabs(I), atol) || len >= 64 * switch_boxes)) { status = 3; break; }
         const double theta_in = theta;
         int64_t nsplit = 0;
         int overflow = 0;

@@ -204,4 +204,15 @@ int orc_max_threads(void);
 #ifdef __cplusplus
 }
 #endif
+/* parameter sensitivities: value + gradient of a family at a point, and I, dI/dp as one vector-valued integral */
+int orc_family_grad(int fam, int dim, const double *x, const double *par, double *out);
+int orc_quadgk_sens_batch(int fam, const double *lb, const double *ub, int bounds_per_problem, int tr,
+                          const double *params, int nparam, int64_t nprob, const int *idx, int nsens,
+                          double reltol, double abstol, int64_t maxiters, int normkind,
+                          double *I, double *E, int64_t *nevals, int32_t *status, int nthreads);
+int orc_hcubature_sens_batch(int fam, int dim, const double *lb, const double *ub, int bounds_per_problem, int tr,
+                             const double *params, int nparam, int64_t nprob, const int *idx, int nsens,
+                             double reltol, double abstol, int64_t maxiters, int initdiv, int normkind,
+                             double *I, double *E, int64_t *nevals, int32_t *status, int nthreads);
+
 #endif

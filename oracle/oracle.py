@@ -387,6 +387,47 @@ def hcubature_vec_batch(fam, lb, ub, params, tr="if_inf", reltol=1e-8, abstol=1e
     return I, E, ne, st
 
 
+def family_grad(fam, x, params):
+    """[f, df/dparams...] of a registered family at the point x (orc_family_grad); None for a family without sensitivities"""
+    fam = FAM[fam] if isinstance(fam, str) else fam
+    x = _arr(np.atleast_1d(x)); params = _arr(np.ravel(params))
+    out = np.empty(1 + params.size)
+    L = lib()
+    L.orc_family_grad.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp]
+    return out if L.orc_family_grad(fam, x.size, _p(x), _p(params), _p(out)) == 0 else None
+
+
+def sens_batch(fam, lb, ub, params, wrt, tr="if_inf", reltol=1e-8, abstol=1e-8, maxiters=2**62, initdiv=1, norm="value", rule="hcubature", nthreads=1):
+    """I and dI/dp[wrt] as one vector-valued integral [f, df/dp...] (checker of Engine.sens_batch): params nparam x nprob;
+    -> out ((1 + len(wrt)) x nprob), E, nevals, status"""
+    fam = FAM[fam] if isinstance(fam, str) else fam
+    params = np.asfortranarray(params, dtype=np.float64)
+    if params.ndim == 1:
+        params = params.reshape(-1, 1, order="F")
+    nparam, nprob = params.shape
+    idx = np.ascontiguousarray(wrt, dtype=np.int32)
+    lb = np.asfortranarray(np.atleast_1d(lb), dtype=np.float64); ub = np.asfortranarray(np.atleast_1d(ub), dtype=np.float64)
+    nk = {"2": 0, "inf": 1, "value": 2}[norm]
+    I = np.empty((1 + idx.size, nprob), order="F"); E = np.empty(nprob); ne = np.empty(nprob, np.int64); st = np.empty(nprob, np.int32)
+    L = lib()
+    ip = idx.ctypes.data_as(C.POINTER(C.c_int))
+    if rule == "quadgk":
+        lb = lb.ravel(); ub = ub.ravel()
+        L.orc_quadgk_sens_batch.argtypes = [C.c_int, _dp, _dp, C.c_int, C.c_int, _dp, C.c_int, C.c_int64, C.POINTER(C.c_int), C.c_int, C.c_double,
+                                            C.c_double, C.c_int64, C.c_int, _dp, _dp, _i64p, _i32p, C.c_int]
+        rc = L.orc_quadgk_sens_batch(fam, _p(lb), _p(ub), int(lb.size != 1), TR[tr], params.ctypes.data_as(_dp), nparam, nprob, ip, idx.size,
+                                     reltol, abstol, maxiters, nk, I.ctypes.data_as(_dp), _p(E), ne.ctypes.data_as(_i64p), st.ctypes.data_as(_i32p), nthreads)
+    else:
+        dim = lb.shape[0]
+        L.orc_hcubature_sens_batch.argtypes = [C.c_int, C.c_int, _dp, _dp, C.c_int, C.c_int, _dp, C.c_int, C.c_int64, C.POINTER(C.c_int), C.c_int,
+                                               C.c_double, C.c_double, C.c_int64, C.c_int, C.c_int, _dp, _dp, _i64p, _i32p, C.c_int]
+        rc = L.orc_hcubature_sens_batch(fam, dim, _p(lb), _p(ub), int(lb.ndim == 2), TR[tr], params.ctypes.data_as(_dp), nparam, nprob, ip, idx.size,
+                                        reltol, abstol, maxiters, initdiv, nk, I.ctypes.data_as(_dp), _p(E), ne.ctypes.data_as(_i64p),
+                                        st.ctypes.data_as(_i32p), nthreads)
+    assert rc == 0, rc
+    return I, E, ne, st
+
+
 def hcubature_rounds(fam, lb, ub, params, tr="if_inf", reltol=1e-8, abstol=1e-8, max_boxes=1 << 24, m0=0):
     """Round-synchronous refinement of ONE integral (checker for Engine.hcubature_single).
     -> I, E, dict(rule_applications, boxes, rounds, status)."""

@@ -331,3 +331,33 @@ def test_hcubature_refinement_modes():
     ib.solve(p1, ib.HCubatureB200(), engine=e); assert e.calls[-1][2]["mode"] == "reference_order"     # rounds are built for dim >= 2
     with pytest.raises(ValueError):
         ib.HCubatureB200(refinement="fastest")
+
+
+def test_parameter_sensitivities_routing():
+    """sensealg = ParameterSensitivities (the reference passes `sensealg` through init, src/common.jl:79-133, and differentiates solve in
+    ext/IntegralsForwardDiffExt.jl / ext/IntegralsZygoteExt.jl): one engine call per group of 7 parameters, shapes of sol.u / sol.du_dp"""
+    class ES(StubEngine):
+        def sens_batch(self, fam, dim, lb, ub, p, wrt, **k):
+            self._rec("sens", fam, dim, lb, ub, p, list(wrt), **k); n = p.shape[1]
+            out = np.zeros((1 + len(wrt), n), order="F"); out[1:] = np.asarray(wrt, float)[:, None]
+            return out, np.zeros(n), np.zeros(n, np.int64), np.zeros(n, np.int32)
+    e = ES()
+    par = np.full((8, 5), 1.0)                           # 4-D Genz Gaussian: 8 parameters, 5 problems
+    prob = ib.IntegralProblem(ib.GenzGaussian(), (np.zeros(4), np.ones(4)), par)
+    sol = ib.solve(prob, ib.HCubatureB200(initdiv=2), engine=e, sensealg=ib.ParameterSensitivities(), reltol=1e-7)
+    sens = [c for c in e.calls if c[0] == "sens"]
+    assert [c[1][5] for c in sens] == [[0, 1, 2, 3, 4, 5, 6], [7]]                  # 8 parameters: groups of 7 + 1
+    assert all(c[2]["norm"] == "value" and c[2]["rule"] == "hcubature" and c[2]["initdiv"] == 2 and c[2]["reltol"] == 1e-7 for c in sens)
+    assert sol.u.shape == (5,) and sol.du_dp.shape == (8, 5) and np.array_equal(sol.du_dp[:, 0], np.arange(8.0))
+    # one problem, chosen parameters, a norm over value and derivatives; QuadGK in 1-D
+    e.calls.clear()
+    sol = ib.solve(ib.IntegralProblem(ib.SinXP(), (-2.0, 5.0), np.array([1.7])), ib.QuadGKB200(), engine=e,
+                   sensealg=ib.ParameterSensitivities(wrt=[0], control="2"))
+    assert e.calls[-1][2]["rule"] == "quadgk" and e.calls[-1][2]["norm"] == "2" and isinstance(sol.u, float) and sol.du_dp.shape == (1,)
+    with pytest.raises(ValueError, match="wrt"):
+        ib.solve(ib.IntegralProblem(ib.SinXP(), (-2.0, 5.0), np.array([1.7])), ib.QuadGKB200(), engine=e, sensealg=ib.ParameterSensitivities(wrt=[3]))
+    with pytest.raises(TypeError, match="QuadGKB200 and HCubatureB200"):
+        ib.solve(ib.IntegralProblem(ib.SinXP(), (-2.0, 5.0), np.array([1.7])), ib.GaussLegendreB200(n=4), engine=e, sensealg=ib.ParameterSensitivities())
+    # any other sensealg (the reference's AD back-ends) is accepted and ignored
+    sol = ib.solve(ib.IntegralProblem(ib.SinXP(), (-2.0, 5.0), np.array([1.7])), ib.QuadGKB200(), engine=e, sensealg="ReCallVJP(ZygoteVJP())")
+    assert sol.du_dp is None and e.calls[-1][0] == "quadgk"

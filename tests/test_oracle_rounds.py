@@ -67,3 +67,23 @@ def test_two_level_reaches_the_tolerance_in_bounded_extra_work(dim, reltol, swit
     I3, E3, s3 = O.hcubature_two_level("gauss", lb, ub, par, reltol=1e-4, abstol=0.0, switch_boxes=1 << 30)
     I4, E4, s4 = O.hcubature_rounds("gauss", lb, ub, par, reltol=1e-4, abstol=0.0, max_boxes=1 << 40)
     assert (I3, E3, s3["rule_applications"], s3["level2_subproblems"]) == (I4, E4, s4["rule_applications"], 0)
+
+
+def test_two_level_retirement_keeps_the_answer_in_bounded_arenas():
+    """converged-box retirement (sub_arena): sub-problems that outgrow their arena drop the boxes that have converged and go on.  With a
+    workable arena the whole solve still meets its tolerance with about the same work as the unbounded store; the retired error is part
+    of E (never lost), so a solve that cannot finish says so through E and the status."""
+    par = genz_params("genz_gaussian", 4, 3, scale=0.5)[:, 0]
+    lb, ub = np.zeros(4), np.ones(4)
+    reltol = 1e-9
+    exact = genz_exact("genz_gaussian", par, 4)
+    I0, E0, s0 = O.hcubature_two_level("gauss", lb, ub, par, reltol=reltol, abstol=0.0, max_boxes=1 << 40, switch_boxes=64)
+    assert s0["status"] == 0 and s0["retired_boxes"] == 0
+    I1, E1, s1 = O.hcubature_two_level("gauss", lb, ub, par, reltol=reltol, abstol=0.0, max_boxes=1 << 40, switch_boxes=64, sub_arena=2048)
+    assert s1["status"] == 0 and s1["retired_boxes"] > 0 and E1 <= reltol * abs(I1)
+    assert abs(I1 - I0) <= reltol * abs(I0) and abs(I1 - exact) <= 10 * reltol * abs(exact)
+    assert s1["rule_applications"] <= 1.1 * s0["rule_applications"]
+    # an arena far too small: some sub-problems end with a full arena -- reported (status 1), E carries what is left, I stays accurate
+    I2, E2, s2 = O.hcubature_two_level("gauss", lb, ub, par, reltol=reltol, abstol=0.0, max_boxes=1 << 40, switch_boxes=64, sub_arena=128)
+    assert s2["status"] == 1 and s2["retired_boxes"] > s1["retired_boxes"] and E2 > E1
+    assert abs(I2 - exact) <= E2
