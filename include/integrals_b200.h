@@ -271,6 +271,21 @@ int32_t ib200_batch_points(ib200_ctx *ctx, double *x, int64_t npoints);
 int32_t ib200_batch_values(ib200_ctx *ctx, const double *y, int64_t npoints);
 int32_t ib200_batch_result(ib200_ctx *ctx, double *out_I, double *out_E, int64_t *out_stats);
 
+/* -- device-resident USER integrands (second half).  For integrands outside the registered families the reference
+      calls a Julia closure f(x, p) point by point (src/Integrals.jl:327-335, 380-393) or on batches (BatchIntegralFunction, :274-315).
+      Here the caller states the integrand in CUDA C++ -- `body` is the body of  __device__ double f(const double *x, const double *p)
+      (x: the point, `dim` coordinates in the caller's ORIGINAL variables; p: the parameters) -- and the engine compiles it at run time
+      (NVRTC, sm_100a) into one elementwise kernel that it runs between the two kernels of the bridge above: the same rounds, rule,
+      change of variables and stopping test, with every evaluation on the device.  ib200_integrand_compile needs no GPU (ctx may be
+      NULL); a compile error is returned as IB200_ERR_INVALID with the compiler's log in ib200_last_error.  params: nparam doubles, host
+      or device.  out_stats as ib200_batch_result. */
+int32_t ib200_integrand_compile(ib200_ctx *ctx, const char *body, int32_t dim, int32_t *handle_out);
+int32_t ib200_integrand_release(ib200_ctx *ctx, int32_t handle);
+int32_t ib200_integrate_compiled(ib200_ctx *ctx, int32_t handle, int32_t dim, int32_t transform,
+                                 const double *lb, const double *ub, const double *params, int32_t nparam,
+                                 double reltol, double abstol, int64_t max_boxes, int64_t store_boxes,
+                                 double *out_I, double *out_E, int64_t *out_stats);
+
 /* -- measurement helper: dependency-free DFMA chains on every SM; returns TFLOP/s (2 flops/DFMA).
       This is the FP64 roofline denominator. */
 int32_t ib200_measure_fp64_peak(ib200_ctx *ctx, double *tflops, double *ms);

@@ -11,7 +11,7 @@ from ._lib import (Engine, IB200Error, FAMILY_IDS, TRANSFORM_IDS, RULE_IDS, SYMB
 from .build import build_library
 from .integrands import (RegisteredIntegrand, SinXP, GenzOscillatory, GenzProductPeak, GenzCornerPeak, GenzGaussian,
                          GenzC0, GenzDiscontinuous, CosProduct, GaussPoly, ExpLinear, GLTest, VectorOf, ALL_INTEGRANDS)
-from .interface import (ParameterSensitivities, DomainError, retcode_of, IntegralProblem, IntegralFunction, BatchIntegralFunction, SampledIntegralProblem, IntegralSolution, IntegralCache, SampledIntegralCache,
+from .interface import (ParameterSensitivities, DomainError, retcode_of, IntegralProblem, IntegralFunction, BatchIntegralFunction, CudaIntegralFunction, SampledIntegralProblem, IntegralSolution, IntegralCache, SampledIntegralCache,
                         Range, ReturnCode, CommonKwargError, ChangeOfVariables, transformation_if_inf,
                         transformation_tan_inf, transformation_cot_inf, QuadGKB200, HCubatureB200, QuadratureRuleB200,
                         GaussLegendreB200, TrapezoidalB200, SimpsonsB200, init, solve, solve_cache)

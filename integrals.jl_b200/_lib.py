@@ -26,7 +26,7 @@ SYMBOLS = ["ib200_version", "ib200_create", "ib200_destroy", "ib200_last_error",
            "ib200_set_option", "ib200_sampled", "ib200_sampled_slab", "ib200_sampled_f32", "ib200_fixed_rule_tensor_batch", "ib200_fixed_rule_nodes_batch",
            "ib200_gauss_legendre_batch", "ib200_quadgk_batch", "ib200_quadgk_rule_batch", "ib200_quadgk_vec_batch", "ib200_hcubature_batch", "ib200_hcubature_vec_batch", "ib200_quadgk_sens_batch", "ib200_hcubature_sens_batch", "ib200_measure_fp64_peak",
            "ib200_hcubature_single", "ib200_batch_open", "ib200_batch_next", "ib200_batch_points", "ib200_batch_values",
-           "ib200_batch_result", "ib200_comm_unique_id", "ib200_comm_init", "ib200_comm_destroy"]
+           "ib200_batch_result", "ib200_integrand_compile", "ib200_integrand_release", "ib200_integrate_compiled", "ib200_comm_unique_id", "ib200_comm_init", "ib200_comm_destroy"]
 
 
 class IB200Error(RuntimeError):
@@ -91,6 +91,10 @@ def load_library():
     L.ib200_batch_points.argtypes = [vp, vp, i64]; L.ib200_batch_points.restype = i32
     L.ib200_batch_values.argtypes = [vp, vp, i64]; L.ib200_batch_values.restype = i32
     L.ib200_batch_result.argtypes = [vp, C.POINTER(dp), C.POINTER(dp), vp]; L.ib200_batch_result.restype = i32
+    L.ib200_integrand_compile.argtypes = [vp, C.c_char_p, i32, C.POINTER(i32)]; L.ib200_integrand_compile.restype = i32
+    L.ib200_integrand_release.argtypes = [vp, i32]; L.ib200_integrand_release.restype = i32
+    L.ib200_integrate_compiled.argtypes = [vp, i32, i32, i32, vp, vp, vp, i32, dp, dp, i64, i64, C.POINTER(dp), C.POINTER(dp), vp]
+    L.ib200_integrate_compiled.restype = i32
     L.ib200_comm_unique_id.argtypes = [vp]; L.ib200_comm_unique_id.restype = i32
     L.ib200_comm_init.argtypes = [vp, i32, i32, vp]; L.ib200_comm_init.restype = i32
     L.ib200_comm_destroy.argtypes = [vp]; L.ib200_comm_destroy.restype = i32
@@ -429,6 +433,29 @@ class Engine:
         return I.value, E.value, dict(nevals=int(st[0]), rule_applications=int(st[1]), boxes=int(st[2]), rounds=int(st[3]),
                                       status=int(st[4]), world=int(st[5]), level2_subproblems=int(st[6]), level2_unconverged=int(st[7]),
                                       note=self.L.ib200_last_error(self.h).decode() if (st[7] or st[6]) else "")
+
+    # ---- device-resident user integrands (CUDA source compiled with NVRTC) -------------------------
+    def compile_integrand(self, body, dim):
+        """body of `__device__ double f(const double *x, const double *p)` in CUDA C++ -> handle (ib200_integrand_compile; needs no GPU)"""
+        h = C.c_int32(-1)
+        self._check(self.L.ib200_integrand_compile(self.h, body.encode(), int(dim), C.byref(h)))
+        return h.value
+
+    def release_integrand(self, handle):
+        self._check(self.L.ib200_integrand_release(self.h, int(handle)))
+
+    def integrate_compiled(self, handle, dim, lb, ub, params=(), reltol=1e-8, abstol=1e-8, max_boxes=1 << 20, store_boxes=0, transform=0):
+        """One integral of a compiled integrand: the bridge's rounds with every evaluation on the device (ib200_integrate_compiled).
+        -> I, E, stats dict"""
+        lb = np.ascontiguousarray(np.atleast_1d(lb), dtype=np.float64); ub = np.ascontiguousarray(np.atleast_1d(ub), dtype=np.float64)
+        if lb.shape != (dim,) or ub.shape != (dim,):
+            raise ValueError(f"bounds must have {dim} entries")
+        par = np.ascontiguousarray(np.ravel(params), dtype=np.float64)
+        I = C.c_double(); E = C.c_double(); st = np.zeros(6, dtype=np.int64)
+        self._check(self.L.ib200_integrate_compiled(self.h, int(handle), int(dim), int(transform), lb.ctypes.data, ub.ctypes.data,
+                                                    par.ctypes.data if par.size else None, int(par.size), float(reltol), float(abstol),
+                                                    int(min(max_boxes, MAXEVALS_UNBOUNDED)), int(store_boxes), C.byref(I), C.byref(E), st.ctypes.data))
+        return I.value, E.value, dict(nevals=int(st[0]), rule_applications=int(st[1]), boxes=int(st[2]), rounds=int(st[3]), status=int(st[4]))
 
     # ---- BatchIntegralFunction bridge: caller-evaluated integrand ----------------------------------
     def batch_open(self, dim, lb, ub, reltol=1e-8, abstol=1e-8, max_boxes=1 << 20, store_boxes=0, transform=0):

@@ -33,42 +33,41 @@ __host__ __device__ constexpr bool fam_dim_ok(int fam, int d) {
 // underflow is honoured), extremes handled by selects.  Maximum error 0.99 ulp over [-750, 700]
 // (measured against long double, 2e7 samples); exp_bf(-inf) = 0, exp_bf(+inf) = inf, NaN -> NaN.
 // ------------------------------------------------------------------------------------------------
-// The constants of the branch-free exp / sin / cos below live in CONSTANT memory: an FP64 instruction cannot carry a 64-bit immediate
-// (every literal is two MOVs into a register pair before the DFMA), but it can take a constant-bank operand directly.  ncu on the
-// round-based cubature kernels: UMOV + IMAD.MOV were 9-16 % of the executed instructions, a third of the instructions of the polynomial
-// lines (profiles/r02_hcub_rb_*).  Same doubles, same operations.
+// The constants of the branch-free exp in CONSTANT memory: an FP64 instruction cannot carry a 64-bit immediate (every literal is two MOVs
+// into a register pair before the DFMA), but it can take a constant-bank operand directly.  Used only where it measured faster -- the
+// exponentials of the rolled 6..8-D rule (exp_bfN<N, true>); the unrolled 2..5-D rules and the trigonometric kernels keep literals
+// (measured on BASELINE configs 1 and 4: constant operands cost them 7-10 %).
 __constant__ double c_exp[18] = {
     6755399441055744.0, 1.4426950408889634074, -6.93147180369123816490e-01, -1.90821492927058770002e-10,
     1.6059043836821613e-10, 2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07, 2.7557319223985893e-06,
     2.48015873015873e-05, 1.984126984126984e-04, 1.388888888888889e-03, 8.333333333333333e-03, 4.1666666666666664e-02,
     1.6666666666666666e-01, 0.5, -745.2, 709.79 };
-// [0] 1.5*2^52  [1] 2/pi  [2..4] -pi/2 in three parts  [5 + 2 s], [6 + 2 s]: step s of the cos / sin kernel polynomials (fdlibm)
-__constant__ double c_trig[18] = {
-    6755399441055744.0, 0.63661977236758134308, -1.5707963267948966, -6.123233995736766e-17, 1.4973849048591698e-33,
-    -1.13596475577881948265e-11, 1.58969099521155010221e-10,
-    2.08757232129817482790e-09, -2.50507602534068634195e-08,
-    -2.75573143513906633035e-07, 2.75573137070700676789e-06,
-    2.48015872894767294178e-05, -1.98412698298579493134e-04,
-    -1.38888888888741095749e-03, 8.33333333332248946124e-03,
-    4.16666666666666019037e-02, -1.66666666666666324348e-01, 1073741824.0 };
-
 #ifndef IB200_LIBM_EXP
 __device__ __forceinline__ double exp_bf(double x) {
-    const double MG = c_exp[0];                                 // 1.5 * 2^52: round to nearest integer
-    const double t = fma(x, c_exp[1], MG);
+    const double MG = 6755399441055744.0;                       // 1.5 * 2^52: round to nearest integer
+    const double t = fma(x, 1.4426950408889634074, MG);
     int k = __double2loint(t);
     const double kf = t - MG;
-    double r = fma(kf, c_exp[2], x);
-    r = fma(kf, c_exp[3], r);
-    double q = c_exp[4];                                        // 1/13! ... 1/2!
-#pragma unroll
-    for (int i = 5; i <= 15; i++) q = fma(q, r, c_exp[i]);
+    double r = fma(kf, -6.93147180369123816490e-01, x);
+    r = fma(kf, -1.90821492927058770002e-10, r);
+    double q = 1.6059043836821613e-10;                          // 1/13! ... 1/2!
+    q = fma(q, r, 2.08767569878681e-09);
+    q = fma(q, r, 2.505210838544172e-08);
+    q = fma(q, r, 2.755731922398589e-07);
+    q = fma(q, r, 2.7557319223985893e-06);
+    q = fma(q, r, 2.48015873015873e-05);
+    q = fma(q, r, 1.984126984126984e-04);
+    q = fma(q, r, 1.388888888888889e-03);
+    q = fma(q, r, 8.333333333333333e-03);
+    q = fma(q, r, 4.1666666666666664e-02);
+    q = fma(q, r, 1.6666666666666666e-01);
+    q = fma(q, r, 0.5);
     const double p = fma(q, r * r, r) + 1.0;
     k = max(-2000, min(2000, k));
     const int k1 = k >> 1, k2 = k - k1;
     double res = (p * __hiloint2double((k1 + 1023) << 20, 0)) * __hiloint2double((k2 + 1023) << 20, 0);
-    res = x < c_exp[16] ? 0.0 : res;
-    res = x > c_exp[17] ? __longlong_as_double(0x7ff0000000000000LL) : res;
+    res = x < -745.2 ? 0.0 : res;
+    res = x > 709.79 ? __longlong_as_double(0x7ff0000000000000LL) : res;
     return res;
 }
 #else
@@ -78,29 +77,32 @@ __device__ __forceinline__ double exp_bf(double x) { return exp(x); }
 // N independent evaluations in lock step.  ptxas schedules a lone Horner chain as back-to-back
 // dependent DFMAs (each waits out the FP64 latency); writing the N chains side by side in the source
 // gives it N independent instructions between dependent ones (ncu: "wait" stall, profiles/r01_*).
-template <int N>
+template <int N, bool CM = false>
 __device__ __forceinline__ void exp_bfN(const double (&x)[N], double (&out)[N]) {
 #ifdef IB200_LIBM_EXP
 #pragma unroll
     for (int j = 0; j < N; j++) out[j] = exp(x[j]);
 #else
-    const double MG = c_exp[0];
+    // CM: the constants come from constant memory (c_exp) instead of 64-bit literals.  Measured both ways: the rolled 6..8-D rule
+    // (gm_rule_thread3.cuh), short of registers, is faster with constant operands; the unrolled 2..5-D rules lose 7-9 % with them
+    // (Gaussian 414 -> 444 ms, C0 324 -> 354 ms on BASELINE config 4), so literals stay the default.
+    const double MG = CM ? c_exp[0] : 6755399441055744.0;
     double t[N], kf[N], r[N], q[N];
 #pragma unroll
-    for (int j = 0; j < N; j++) t[j] = fma(x[j], c_exp[1], MG);
+    for (int j = 0; j < N; j++) t[j] = fma(x[j], CM ? c_exp[1] : 1.4426950408889634074, MG);
 #pragma unroll
     for (int j = 0; j < N; j++) kf[j] = t[j] - MG;
 #pragma unroll
-    for (int j = 0; j < N; j++) r[j] = fma(kf[j], c_exp[2], x[j]);
+    for (int j = 0; j < N; j++) r[j] = fma(kf[j], CM ? c_exp[2] : -6.93147180369123816490e-01, x[j]);
 #pragma unroll
-    for (int j = 0; j < N; j++) r[j] = fma(kf[j], c_exp[3], r[j]);
+    for (int j = 0; j < N; j++) r[j] = fma(kf[j], CM ? c_exp[3] : -1.90821492927058770002e-10, r[j]);
 #pragma unroll
-    for (int j = 0; j < N; j++) q[j] = fma(c_exp[4], r[j], c_exp[5]);
-#pragma unroll
-    for (int i = 6; i <= 15; i++) {
-#pragma unroll
-        for (int j = 0; j < N; j++) q[j] = fma(q[j], r[j], c_exp[i]);
-    }
+    for (int j = 0; j < N; j++) q[j] = fma(CM ? c_exp[4] : 1.6059043836821613e-10, r[j], CM ? c_exp[5] : 2.08767569878681e-09);
+#define IB_STEP(i, c) _Pragma("unroll") for (int j = 0; j < N; j++) q[j] = fma(q[j], r[j], CM ? c_exp[i] : (c));
+    IB_STEP(6, 2.505210838544172e-08) IB_STEP(7, 2.755731922398589e-07) IB_STEP(8, 2.7557319223985893e-06)
+    IB_STEP(9, 2.48015873015873e-05) IB_STEP(10, 1.984126984126984e-04) IB_STEP(11, 1.388888888888889e-03)
+    IB_STEP(12, 8.333333333333333e-03) IB_STEP(13, 4.1666666666666664e-02) IB_STEP(14, 1.6666666666666666e-01) IB_STEP(15, 0.5)
+#undef IB_STEP
     double pp[N];
 #pragma unroll
     for (int j = 0; j < N; j++) pp[j] = r[j] * r[j];
@@ -113,8 +115,8 @@ __device__ __forceinline__ void exp_bfN(const double (&x)[N], double (&out)[N]) 
         int k = max(-2000, min(2000, __double2loint(t[j])));
         const int k1 = k >> 1, k2 = k - k1;
         double res = (pp[j] * __hiloint2double((k1 + 1023) << 20, 0)) * __hiloint2double((k2 + 1023) << 20, 0);
-        res = x[j] < c_exp[16] ? 0.0 : res;
-        out[j] = x[j] > c_exp[17] ? __longlong_as_double(0x7ff0000000000000LL) : res;
+        res = x[j] < (CM ? c_exp[16] : -745.2) ? 0.0 : res;
+        out[j] = x[j] > (CM ? c_exp[17] : 709.79) ? __longlong_as_double(0x7ff0000000000000LL) : res;
     }
 #endif
 }
@@ -128,29 +130,31 @@ __device__ __forceinline__ void cos_bfN(const double (&x)[N], double (&out)[N]) 
 #pragma unroll
     for (int j = 0; j < N; j++) out[j] = cos(x[j]);
 #else
-    const double MG = c_trig[0];
+    const double MG = 6755399441055744.0;
     double t[N], kf[N], r[N], z[N], p[N];
     bool big = false;
 #pragma unroll
-    for (int j = 0; j < N; j++) { t[j] = fma(x[j], c_trig[1], MG); big = big || !(fabs(x[j]) < c_trig[17]); }
+    for (int j = 0; j < N; j++) { t[j] = fma(x[j], 0.63661977236758134308, MG); big = big || !(fabs(x[j]) < 1073741824.0); }
 #pragma unroll
     for (int j = 0; j < N; j++) kf[j] = t[j] - MG;
 #pragma unroll
-    for (int j = 0; j < N; j++) r[j] = fma(kf[j], c_trig[2], x[j]);
+    for (int j = 0; j < N; j++) r[j] = fma(kf[j], -1.5707963267948966, x[j]);
 #pragma unroll
-    for (int j = 0; j < N; j++) r[j] = fma(kf[j], c_trig[3], r[j]);
+    for (int j = 0; j < N; j++) r[j] = fma(kf[j], -6.123233995736766e-17, r[j]);
 #pragma unroll
-    for (int j = 0; j < N; j++) r[j] = fma(kf[j], c_trig[4], r[j]);
+    for (int j = 0; j < N; j++) r[j] = fma(kf[j], 1.4973849048591698e-33, r[j]);
     int iq[N];
 #pragma unroll
     for (int j = 0; j < N; j++) { iq[j] = __double2loint(t[j]) + 1; z[j] = r[j] * r[j]; }
 #pragma unroll
-    for (int j = 0; j < N; j++) p[j] = (iq[j] & 1) ? c_trig[5] : c_trig[6];
-#pragma unroll
-    for (int s = 1; s <= 5; s++) {
-#pragma unroll
-        for (int j = 0; j < N; j++) p[j] = fma(p[j], z[j], (iq[j] & 1) ? c_trig[5 + 2 * s] : c_trig[6 + 2 * s]);
-    }
+    for (int j = 0; j < N; j++) p[j] = (iq[j] & 1) ? -1.13596475577881948265e-11 : 1.58969099521155010221e-10;
+#define IB_STEP(cc, cs) _Pragma("unroll") for (int j = 0; j < N; j++) p[j] = fma(p[j], z[j], (iq[j] & 1) ? (cc) : (cs));
+    IB_STEP(2.08757232129817482790e-09, -2.50507602534068634195e-08)
+    IB_STEP(-2.75573143513906633035e-07, 2.75573137070700676789e-06)
+    IB_STEP(2.48015872894767294178e-05, -1.98412698298579493134e-04)
+    IB_STEP(-1.38888888888741095749e-03, 8.33333333332248946124e-03)
+    IB_STEP(4.16666666666666019037e-02, -1.66666666666666324348e-01)
+#undef IB_STEP
 #pragma unroll
     for (int j = 0; j < N; j++) {
         const double sres = fma(r[j] * z[j], p[j], r[j]);
@@ -170,29 +174,31 @@ __device__ __forceinline__ void cos_bfN(const double (&x)[N], double (&out)[N]) 
 // reduction, one polynomial per argument with the coefficients chosen by the quadrant.  |x| >= 2^30 takes libm's sin.  Max error 1.5 ulp.
 template <int N>
 __device__ __forceinline__ void sin_bfN(const double (&x)[N], double (&out)[N]) {
-    const double MG = c_trig[0];
+    const double MG = 6755399441055744.0;
     double t[N], kf[N], r[N], z[N], p[N];
     bool big = false;
 #pragma unroll
-    for (int j = 0; j < N; j++) { t[j] = fma(x[j], c_trig[1], MG); big = big || !(fabs(x[j]) < c_trig[17]); }
+    for (int j = 0; j < N; j++) { t[j] = fma(x[j], 0.63661977236758134308, MG); big = big || !(fabs(x[j]) < 1073741824.0); }
 #pragma unroll
     for (int j = 0; j < N; j++) kf[j] = t[j] - MG;
 #pragma unroll
-    for (int j = 0; j < N; j++) r[j] = fma(kf[j], c_trig[2], x[j]);
+    for (int j = 0; j < N; j++) r[j] = fma(kf[j], -1.5707963267948966, x[j]);
 #pragma unroll
-    for (int j = 0; j < N; j++) r[j] = fma(kf[j], c_trig[3], r[j]);
+    for (int j = 0; j < N; j++) r[j] = fma(kf[j], -6.123233995736766e-17, r[j]);
 #pragma unroll
-    for (int j = 0; j < N; j++) r[j] = fma(kf[j], c_trig[4], r[j]);
+    for (int j = 0; j < N; j++) r[j] = fma(kf[j], 1.4973849048591698e-33, r[j]);
     int iq[N];
 #pragma unroll
     for (int j = 0; j < N; j++) { iq[j] = __double2loint(t[j]); z[j] = r[j] * r[j]; }
 #pragma unroll
-    for (int j = 0; j < N; j++) p[j] = (iq[j] & 1) ? c_trig[5] : c_trig[6];
-#pragma unroll
-    for (int s = 1; s <= 5; s++) {
-#pragma unroll
-        for (int j = 0; j < N; j++) p[j] = fma(p[j], z[j], (iq[j] & 1) ? c_trig[5 + 2 * s] : c_trig[6 + 2 * s]);
-    }
+    for (int j = 0; j < N; j++) p[j] = (iq[j] & 1) ? -1.13596475577881948265e-11 : 1.58969099521155010221e-10;
+#define IB_STEP(cc, cs) _Pragma("unroll") for (int j = 0; j < N; j++) p[j] = fma(p[j], z[j], (iq[j] & 1) ? (cc) : (cs));
+    IB_STEP(2.08757232129817482790e-09, -2.50507602534068634195e-08)
+    IB_STEP(-2.75573143513906633035e-07, 2.75573137070700676789e-06)
+    IB_STEP(2.48015872894767294178e-05, -1.98412698298579493134e-04)
+    IB_STEP(-1.38888888888741095749e-03, 8.33333333332248946124e-03)
+    IB_STEP(4.16666666666666019037e-02, -1.66666666666666324348e-01)
+#undef IB_STEP
 #pragma unroll
     for (int j = 0; j < N; j++) {
         const double sres = fma(r[j] * z[j], p[j], r[j]);
@@ -211,26 +217,28 @@ __device__ __forceinline__ void sin_bfN(const double (&x)[N], double (&out)[N]) 
 // both evaluated, quadrant fix-up by selects.  |x| >= 2^30 takes libm's sincos.  Max error 1.5 ulp each.
 template <int N>
 __device__ __forceinline__ void sincos_bfN(const double (&x)[N], double (&sn)[N], double (&cs)[N]) {
-    const double MG = c_trig[0];
+    const double MG = 6755399441055744.0;
     double t[N], kf[N], r[N], z[N], ps[N], pc[N];
     bool big = false;
 #pragma unroll
-    for (int j = 0; j < N; j++) { t[j] = fma(x[j], c_trig[1], MG); big = big || !(fabs(x[j]) < c_trig[17]); }
+    for (int j = 0; j < N; j++) { t[j] = fma(x[j], 0.63661977236758134308, MG); big = big || !(fabs(x[j]) < 1073741824.0); }
 #pragma unroll
     for (int j = 0; j < N; j++) kf[j] = t[j] - MG;
 #pragma unroll
-    for (int j = 0; j < N; j++) r[j] = fma(kf[j], c_trig[2], x[j]);
+    for (int j = 0; j < N; j++) r[j] = fma(kf[j], -1.5707963267948966, x[j]);
 #pragma unroll
-    for (int j = 0; j < N; j++) r[j] = fma(kf[j], c_trig[3], r[j]);
+    for (int j = 0; j < N; j++) r[j] = fma(kf[j], -6.123233995736766e-17, r[j]);
 #pragma unroll
-    for (int j = 0; j < N; j++) r[j] = fma(kf[j], c_trig[4], r[j]);
+    for (int j = 0; j < N; j++) r[j] = fma(kf[j], 1.4973849048591698e-33, r[j]);
 #pragma unroll
-    for (int j = 0; j < N; j++) { z[j] = r[j] * r[j]; ps[j] = fma(c_trig[6], z[j], c_trig[8]); pc[j] = fma(c_trig[5], z[j], c_trig[7]); }
-#pragma unroll
-    for (int s = 2; s <= 5; s++) {
-#pragma unroll
-        for (int j = 0; j < N; j++) { pc[j] = fma(pc[j], z[j], c_trig[5 + 2 * s]); ps[j] = fma(ps[j], z[j], c_trig[6 + 2 * s]); }
-    }
+    for (int j = 0; j < N; j++) { z[j] = r[j] * r[j]; ps[j] = 1.58969099521155010221e-10; pc[j] = -1.13596475577881948265e-11; }
+#define IB_STEP(cc, css) _Pragma("unroll") for (int j = 0; j < N; j++) { pc[j] = fma(pc[j], z[j], (cc)); ps[j] = fma(ps[j], z[j], (css)); }
+    IB_STEP(2.08757232129817482790e-09, -2.50507602534068634195e-08)
+    IB_STEP(-2.75573143513906633035e-07, 2.75573137070700676789e-06)
+    IB_STEP(2.48015872894767294178e-05, -1.98412698298579493134e-04)
+    IB_STEP(-1.38888888888741095749e-03, 8.33333333332248946124e-03)
+    IB_STEP(4.16666666666666019037e-02, -1.66666666666666324348e-01)
+#undef IB_STEP
 #pragma unroll
     for (int j = 0; j < N; j++) {
         const double sres = fma(r[j] * z[j], ps[j], r[j]);

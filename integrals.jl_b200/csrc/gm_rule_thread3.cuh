@@ -37,7 +37,7 @@ template <int D, int N> struct TermsN<IB200_FAM_GENZ_GAUSS, D, N> {
         double x[N];
 #pragma unroll
         for (int j = 0; j < N; j++) { const double t = par[k] * (u[j] - par[D + k]); x[j] = -(t * t); }
-        ib::exp_bfN<N>(x, T);
+        ib::exp_bfN<N, true>(x, T);
     }
 };
 template <int D, int N> struct TermsN<IB200_FAM_GENZ_C0, D, N> {
@@ -45,7 +45,7 @@ template <int D, int N> struct TermsN<IB200_FAM_GENZ_C0, D, N> {
         double x[N];
 #pragma unroll
         for (int j = 0; j < N; j++) x[j] = -(par[k] * fabs(u[j] - par[D + k]));
-        ib::exp_bfN<N>(x, T);
+        ib::exp_bfN<N, true>(x, T);
     }
 };
 // product peak: the N reciprocals 1 / (t_j^2 + a^-2) share one Newton reciprocal (prefix products, back-substitution)
@@ -83,7 +83,7 @@ template <int D> struct Centres<IB200_FAM_GENZ_GAUSS, D> {
         double x[D];
 #pragma unroll
         for (int k = 0; k < D; k++) { const double t = par[k] * (u[k] - par[D + k]); x[k] = -(t * t); }
-        ib::exp_bfN<D>(x, T);
+        ib::exp_bfN<D, true>(x, T);
     }
 };
 template <int D> struct Centres<IB200_FAM_GENZ_C0, D> {
@@ -91,7 +91,7 @@ template <int D> struct Centres<IB200_FAM_GENZ_C0, D> {
         double x[D];
 #pragma unroll
         for (int k = 0; k < D; k++) x[k] = -(par[k] * fabs(u[k] - par[D + k]));
-        ib::exp_bfN<D>(x, T);
+        ib::exp_bfN<D, true>(x, T);
     }
 };
 template <int D> struct Centres<IB200_FAM_GENZ_PROD, D> {

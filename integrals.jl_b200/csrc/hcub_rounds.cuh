@@ -53,6 +53,8 @@ struct Params {
     // and the error is within switch_factor of the tolerance (or it holds 64 x switch_boxes boxes); 0 = single level
     long long switch_boxes = 0;
     double switch_factor = 0.0;
+    double switch_cap = 0.0;      // ... or once it holds this many boxes: min(64 x switch_boxes, half the store's capacity) -- a round can grow
+                                  // the store by half, so the hand-over always comes before the store is full
 };
 constexpr int kStatusHandover = 4;            // internal: level 1 ended by the hand-over rule (never returned to the caller)
 
@@ -417,7 +419,7 @@ decide_kernel(Params p) {
     if (E <= tol) { st->done = 1; st->status = IB200_ST_CONVERGED; return; }
     if (!isfinite(E)) { st->done = 1; st->status = IB200_ST_NONFINITE; return; }
     if (ap >= (double)p.max_boxes || full > 0.0) { st->done = 1; st->status = IB200_ST_MAXEVALS; return; }
-    if (p.switch_boxes > 0 && nb >= (double)p.switch_boxes && (E <= p.switch_factor * tol || nb >= 64.0 * (double)p.switch_boxes)) {
+    if (p.switch_boxes > 0 && nb >= (double)p.switch_boxes && (E <= p.switch_factor * tol || nb >= p.switch_cap)) {
         st->done = 1; st->status = kStatusHandover; return;
     }
     st->bound = fmax(mx, st->theta);          // boxes left unsplit by the previous round are below its threshold

@@ -526,6 +526,7 @@ extern "C" int32_t ib200_hcubature_single(ib200_ctx *ctx, int32_t family, int32_
     if (want > 4000000000LL) want = 4000000000LL;         // 32-bit todo indices
     if (want < 16) want = 16;
     p.cap = want;
+    p.switch_cap = fmin(64.0 * (double)p.switch_boxes, 0.5 * (double)p.cap);
     double *xb = (double *)ctx->get(SL_WORK1, (size_t)((hs::kXchg + 1) * (p.world + 1) + hs::kBins) * sizeof(double) + sizeof(hs::State) + 64);
     if (!xb) return ib200_fail(ctx, IB200_ERR_OOM, "ib200_hcubature_single: scratch allocation failed");
     const size_t need_rec = (size_t)p.cap * (2 * dim + 2) * sizeof(double), need_err = (size_t)p.cap * sizeof(double);

@@ -92,16 +92,194 @@ __device__ __forceinline__ double wmax(double v) {
     return v;
 }
 
-// shared memory.  Per warp: hist[kBins] (unsigned) | occ[kBins/32] (bitmap of the occupied bins) | problem row | staging.
+// ---- the split threshold of a round (csrc/hcub_rounds.cuh decide_kernel, per problem): half the largest error seen, lowered to the bound
+//      theta_h that the exponent histogram gives.  The three scans walk only the OCCUPIED bins (bitmap), in the same order and with the same
+//      arithmetic as the scans over all bins (oracle: orc_hcubature_rounds); every lane computes the same value.  Bin kBins-1 (inf / NaN
+//      keys) never takes part: a non-finite E has ended the solve before.  tol_live = the tolerance minus the error retired so far.
+__device__ __forceinline__ double round_threshold(const unsigned *hist, const unsigned *occ, int lane, double tol_live, double mx, double theta_prev,
+                                                  double remaining, double share) {
+    const unsigned full = 0xffffffffu;
+    double theta = 0.5 * fmax(mx, theta_prev);
+    const unsigned long long words = (unsigned long long)__ballot_sync(full, occ[lane] != 0u) |
+                                     ((unsigned long long)__ballot_sync(full, occ[32 + lane] != 0u) << 32);
+    int bh = kBins - 2;
+    {   // (1) ascending: longest prefix of bins whose lower-edge mass stays <= tol
+        double low = 0.0; bool broke = false;
+        unsigned long long ws = words;
+        while (ws && !broke) {
+            const int w = __ffsll((long long)ws) - 1; ws &= ws - 1;
+            unsigned m = occ[w];
+            while (m) {
+                const int b = (w << 5) + __ffs((int)m) - 1; m &= m - 1;
+                if (b > kBins - 2) break;
+                low += (double)hist[b] * bin_edge(b);
+                if (!(low <= tol_live)) { bh = b - 1; broke = true; break; }
+            }
+        }
+    }
+    int bb = 0, bf = 0;
+    {   // (2) budget and (3) selectivity, descending: the lowest bin down to which bisecting everything still fits
+        double above = 0.0; bool broke_b = false, broke_f = false;
+        unsigned long long ws = words;
+        while (ws && !(broke_b && broke_f)) {
+            const int w = 63 - __clzll((long long)ws); ws &= ~(1ull << w);
+            unsigned m = occ[w];
+            while (m && !(broke_b && broke_f)) {
+                const int b = (w << 5) + 31 - __clz((int)m); m &= ~(1u << (b & 31));
+                if (b > kBins - 2) continue;
+                above += (double)hist[b];
+                if (!broke_b && 2.0 * above > remaining) { bb = b + 1; broke_b = true; }
+                if (!broke_f && above > share) { bf = b + 1; broke_f = true; }
+            }
+        }
+    }
+    if (bf > bb) bb = bf;
+    const int bs = (bh + 1 > bb) ? bh + 1 : bb;
+    const double theta_h = bs <= 0 ? 0.0 : (bs >= kBins - 1 ? 1.7976931348623157e308 : bin_edge(bs));
+    return fmin(theta, theta_h);
+}
+
+// ---- a sub-problem's arena is full (level 2 of ib200_hcubature_single): RETIRE the boxes that have converged (only their sums
+//      are kept, in ret[0..2] = integral, error, count) and decide the round again, the selection capped by the room that is left.
+//      Out of line on purpose: the hot loop of the round kernel keeps the registers it had before this existed (inlined, the batch kernels
+//      went from 154 to 168 registers and BASELINE config 4 lost 7 %).  Oracle: the `arena` branch of hcub_rounds_core2 (oracle/oracle.c).
+//      Retired error cannot be refined away, so a retirement may take at most a quarter of the tolerance still unspent, measured by the UPPER
+//      edges of the histogram bins (a bound on the retired sum): every box below theta_r = that bin edge goes, never a box selected for
+//      bisection (theta_r <= theta).  The histogram is rebuilt from the boxes that stay.  Second selection: bins are taken whole from the top
+//      while they fit the room; of the bin that does not fit any more, the first `quota` boxes in store order.  false: the arena stays full
+//      (less than 1/64 of it freed, or nothing to select).
+template <int D>
+__device__ __noinline__ bool retire_reselect(double *rec, double *err, int *list, unsigned *hist, unsigned *occ, double *ret, int cap,
+                                             double tol, double mx, double theta_prev, double theta_cur, double remaining, double frac,
+                                             int *nbox_io, int *nsplit_out, double *dE_out, double *theta_out) {
+    constexpr int RECW = 2 * D + 2, NCH = D + 1;
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    int nbox = *nbox_io;
+    __syncwarp();
+    {
+        const double R = 0.25 * (tol - ret[1]);
+        const unsigned long long words = (unsigned long long)__ballot_sync(full, occ[lane] != 0u) |
+                                         ((unsigned long long)__ballot_sync(full, occ[32 + lane] != 0u) << 32);
+        int br = -1;
+        {
+            double acc = 0.0; bool broke = false;
+            unsigned long long ws = words;
+            while (ws && !broke) {
+                const int w = __ffsll((long long)ws) - 1; ws &= ws - 1;
+                unsigned m = occ[w];
+                while (m) {
+                    const int b = (w << 5) + __ffs((int)m) - 1; m &= m - 1;
+                    if (b > kBins - 3) { broke = true; break; }
+                    acc += (double)hist[b] * bin_edge(b + 1);
+                    if (!(acc <= R)) { broke = true; break; }
+                    br = b;
+                }
+            }
+        }
+        const double theta_r = fmin(br < 0 ? 0.0 : bin_edge(br + 1), theta_cur);
+        __syncwarp();
+        for (int b = lane; b < kBins; b += 32) hist[b] = 0u;
+        for (int b = lane; b < kBins / 32; b += 32) occ[b] = 0u;
+        __syncwarp();
+        int kept = 0;
+        double rI = 0.0, rE = 0.0;
+        for (int i0 = 0; i0 < nbox; i0 += 32) {
+            const int i = i0 + lane;
+            const bool have = i < nbox;
+            const double e = have ? __ldcg(err + i) : 0.0;
+            const bool keep = have && e >= theta_r;
+            double r[RECW];
+            if (keep) {
+                const double2 *src = reinterpret_cast<const double2 *>(rec + (size_t)i * RECW);
+#pragma unroll
+                for (int q = 0; q < NCH; q++) { const double2 v = __ldcg(src + q); r[2 * q] = v.x; r[2 * q + 1] = v.y; }
+            } else if (have) { rI += __ldcg(rec + (size_t)i * RECW + 2 * D); rE += e; }
+            const unsigned bal = __ballot_sync(full, keep);
+            __syncwarp();                                       // every lane has read its box before a slot of this batch is overwritten
+            if (keep) {
+                const int j = kept + __popc(bal & lt);          // j <= i: a slot this pass has already read
+                if (j != i) {
+                    double2 *dst = reinterpret_cast<double2 *>(rec + (size_t)j * RECW);
+#pragma unroll
+                    for (int q = 0; q < NCH; q++) dst[q] = make_double2(r[2 * q], r[2 * q + 1]);
+                    err[j] = e;
+                }
+                const int bn = ebin(e);
+                if (atomicAdd(&hist[bn], 1u) == 0u) atomicOr(&occ[bn >> 5], 1u << (bn & 31));
+            }
+            kept += __popc(bal);
+            __syncwarp();
+        }
+        rI = wsum(rI); rE = wsum(rE);
+        if (lane == 0) { ret[0] += rI; ret[1] += rE; ret[2] += (double)(nbox - kept); }
+        nbox = kept;
+        __syncwarp();
+    }
+    *nbox_io = nbox;
+    *nsplit_out = 0; *dE_out = 0.0;
+    // ---- the round again, on what is left
+    double theta = round_threshold(hist, occ, lane, tol - ret[1], mx, theta_prev, remaining, frac * (double)nbox);
+    *theta_out = theta;
+    const int room = cap - nbox;
+    if (room < cap / 64) return false;                          // not worth a round: the arena stays full
+    double th_hi = theta, th_lo = theta;
+    int quota = 0;
+    {
+        const unsigned long long words = (unsigned long long)__ballot_sync(full, occ[lane] != 0u) |
+                                         ((unsigned long long)__ballot_sync(full, occ[32 + lane] != 0u) << 32);
+        double up = 0.0; bool crossed = false;
+        unsigned long long ws = words;
+        while (ws && !crossed) {
+            const int w = 63 - __clzll((long long)ws); ws &= ~(1ull << w);
+            unsigned m = occ[w];
+            while (m && !crossed) {
+                const int b = (w << 5) + 31 - __clz((int)m); m &= ~(1u << (b & 31));
+                if (b > kBins - 2) continue;
+                const double c = (double)hist[b];
+                if (up + c > (double)room) {
+                    th_hi = fmax(theta, b + 1 >= kBins - 1 ? 1.7976931348623157e308 : bin_edge(b + 1));
+                    th_lo = fmax(theta, bin_edge(b));
+                    quota = room - (int)up;
+                    crossed = true;
+                } else up += c;
+            }
+        }
+    }
+    int nsplit = 0, nlo = 0;
+    double dE = 0.0;
+    for (int i0 = 0; i0 < nbox; i0 += 32) {
+        const int i = i0 + lane;
+        const double e = i < nbox ? __ldcg(err + i) : -1.0;
+        const bool hi = e >= th_hi;
+        const bool lo = !hi && e >= th_lo;
+        const unsigned bl = __ballot_sync(full, lo);
+        const bool flag = hi || (lo && nlo + __popc(bl & lt) < quota);
+        nlo += __popc(bl);
+        const unsigned bal = __ballot_sync(full, flag);
+        if (flag) {
+            list[nsplit + __popc(bal & lt)] = i;
+            dE += e;
+            const int bn = ebin(e);
+            if (atomicSub(&hist[bn], 1u) == 1u) atomicAnd(&occ[bn >> 5], ~(1u << (bn & 31)));
+        }
+        nsplit += __popc(bal);
+    }
+    *nsplit_out = nsplit; *dE_out = dE;
+    return nsplit > 0 && nbox + nsplit <= cap;
+}
+
+// shared memory.  Per warp: hist[kBins] (unsigned) | occ[kBins/32] (bitmap of the occupied bins) | ret[4] | problem row | staging.
 //   thread-per-box: row = par[NPAR] lbs[D] aux[D] finit jacc prep[D] (the layout gm_rule_thread / gm_rule_thread2 read); staging = [2][D+1][32] double2, the
 //                   parent records of the current and the next pass (cp.async)
 //   warp-per-box:   row = par[NPAR] lb[D] ub[D] den[D] (WarpRule::kProb); staging = WarpRule::kStage doubles + the parent record
 // Per block (warp-per-box only): the rule's weights and point table.
 template <int FAM, int D> __host__ __device__ constexpr int pc_padded() { return (hp::pc_doubles<FAM, D>() + D + 1) & ~1; }   // + prep[D] (gm_rule_thread2.cuh)
 template <int FAM, int D, bool ALLFIN> __host__ __device__ constexpr int row_doubles() {
-    if (!warp_box<FAM, D>()) return kBins / 2 + kBins / 64 + pc_padded<FAM, D>() + 2 * (D + 1) * 32 * 2;
+    if (!warp_box<FAM, D>()) return kBins / 2 + kBins / 64 + 4 + pc_padded<FAM, D>() + 2 * (D + 1) * 32 * 2;
     using W = hs::WarpRule<FAM, D, ALLFIN>;
-    return kBins / 2 + kBins / 64 + ((W::kProb + 1) & ~1) + ((W::kStage + 1) & ~1) + 2 * D + 2;
+    return kBins / 2 + kBins / 64 + 4 + ((W::kProb + 1) & ~1) + ((W::kStage + 1) & ~1) + 2 * D + 2;
 }
 template <int FAM, int D> __host__ __device__ constexpr int block_doubles() {
     return !warp_box<FAM, D>() ? 0 : 10 + (hc::gm_npoints(D) + 1) / 2 + 1;
@@ -113,7 +291,9 @@ template <int FAM, int D> __host__ __device__ constexpr int block_doubles() {
 #ifndef HB_MINB_HD
 #define HB_MINB_HD 3            // thread per box in 6 .. 8 dimensions
 #endif
-template <int FAM, int D, bool ALLFIN>
+// SUB: sub-problem mode (level 2 of ib200_hcubature_single) is a separate instantiation -- its arena-retirement call (an ABI call in the
+// round loop) costs the batch kernels 13 registers and 11 % on the exponential families when it is merely present (measured, same box)
+template <int FAM, int D, bool ALLFIN, bool SUB>
 __global__ void __launch_bounds__(kBlock, (D <= kMaxThreadDim ? HB_MINB : (warp_box<FAM, D>() ? 4 : HB_MINB_HD)))
 hcub_rb_kernel(const Params p) {
     using F = ib::Family<FAM, D>;
@@ -132,7 +312,8 @@ hcub_rb_kernel(const Params p) {
     double *row = sm + block_doubles<FAM, D>() + (size_t)wib * row_doubles<FAM, D, ALLFIN>();
     unsigned *hist = reinterpret_cast<unsigned *>(row);
     unsigned *occ = reinterpret_cast<unsigned *>(row + kBins / 2);
-    double *pc = row + kBins / 2 + kBins / 64;
+    double *ret = row + kBins / 2 + kBins / 64;           // [4] sums over the boxes retired from a full arena: integral, error, count
+    double *pc = ret + 4;
     // thread per box
     double2 *stage = reinterpret_cast<double2 *>(pc + pc_padded<FAM, D>());     // [2][NCH][32]
     double *par = pc, *lbs = pc + NPAR, *aux = lbs + D;
@@ -147,7 +328,7 @@ hcub_rb_kernel(const Params p) {
     double *rec = p.rec + (size_t)gwarp * p.cap * RECW;
     double *err = p.err + (size_t)gwarp * p.cap;
     int *list = p.list + (size_t)gwarp * p.cap;
-    const bool sub = p.sub_rec != nullptr;
+    constexpr bool sub = SUB;
 
     for (;;) {
         unsigned long long pidx = 0;
@@ -173,6 +354,7 @@ hcub_rb_kernel(const Params p) {
         }
         for (int b = lane; b < kBins; b += 32) hist[b] = 0u;
         for (int b = lane; b < kBins / 32; b += 32) occ[b] = 0u;
+        if (lane < 4) ret[lane] = 0.0;
         __syncwarp();
         double jacc = 1.0;
         if (ALLFIN) {
@@ -246,8 +428,6 @@ hcub_rb_kernel(const Params p) {
         int nbox = qtotal, ntodo = qtotal, nsplit = 0, nbox0 = 0, status = IB200_ST_CONVERGED;
         long long applied = 0;
         double I = 0.0, E = 0.0, theta = 0.0, dE = 0.0;
-        double Iret = 0.0, Eret = 0.0;          // sub-problem mode: sums over the boxes retired from a full arena
-        long long nretired = 0;
         bool first = true;
 
         for (;;) {
@@ -382,82 +562,9 @@ hcub_rb_kernel(const Params p) {
             if (!isfinite(E)) { status = IB200_ST_NONFINITE; break; }
             if (applied >= p.max_apps) { status = IB200_ST_MAXEVALS; break; }
 
-            // ---- threshold + selection, at most twice per round: when the selected boxes would overflow a sub-problem's arena, the boxes
-            //      that have converged are RETIRED first (only their sums are kept) and the round is decided again
-            const double theta_in = theta;
-            bool overflow = false;
-            double th_hi = 0.0, th_lo = 0.0;
-            int quota = 0;
-            for (int attempt = 0; ; attempt++) {
-            theta = theta_in;
-            // ---- threshold (csrc/hcub_rounds.cuh decide_kernel, per problem).  The three scans of the exponent histogram walk only
-            //      the OCCUPIED bins (bitmap), in the same order and with the same arithmetic as the scans over all bins; every lane
-            //      computes the same value.  Bin kBins-1 (inf / NaN keys) never takes part: a non-finite E has ended the solve above.
-            theta = 0.5 * fmax(mx, theta);
-            {
-                const unsigned long long words = (unsigned long long)__ballot_sync(full, occ[lane] != 0u) |
-                                                 ((unsigned long long)__ballot_sync(full, occ[32 + lane] != 0u) << 32);
-                int bh = kBins - 2;
-                {   // (1) ascending: longest prefix of bins whose lower-edge mass stays <= tol
-                    double low = 0.0; bool broke = false;
-                    unsigned long long ws = words;
-                    while (ws && !broke) {
-                        const int w = __ffsll((long long)ws) - 1; ws &= ws - 1;
-                        unsigned m = occ[w];
-                        while (m) {
-                            const int b = (w << 5) + __ffs((int)m) - 1; m &= m - 1;
-                            if (b > kBins - 2) break;
-                            low += (double)hist[b] * bin_edge(b);
-                            if (!(low <= tol - Eret)) { bh = b - 1; broke = true; break; }      // what is retired can no longer be refined
-                        }
-                    }
-                }
-                int bb = 0, bf = 0;
-                {   // (2) budget and (3) selectivity, descending: the lowest bin down to which bisecting everything still fits
-                    const double remaining = (double)p.max_apps - (double)applied, share = p.frac * (double)nbox;
-                    double above = 0.0; bool broke_b = false, broke_f = false;
-                    unsigned long long ws = words;
-                    while (ws && !(broke_b && broke_f)) {
-                        const int w = 63 - __clzll((long long)ws); ws &= ~(1ull << w);
-                        unsigned m = occ[w];
-                        while (m && !(broke_b && broke_f)) {
-                            const int b = (w << 5) + 31 - __clz((int)m); m &= ~(1u << (b & 31));
-                            if (b > kBins - 2) continue;
-                            above += (double)hist[b];
-                            if (!broke_b && 2.0 * above > remaining) { bb = b + 1; broke_b = true; }
-                            if (!broke_f && above > share) { bf = b + 1; broke_f = true; }
-                        }
-                    }
-                }
-                if (bf > bb) bb = bf;
-                const int bs = (bh + 1 > bb) ? bh + 1 : bb;
-                const double theta_h = bs <= 0 ? 0.0 : (bs >= kBins - 1 ? 1.7976931348623157e308 : bin_edge(bs));
-                theta = fmin(theta, theta_h);
-                // (4) second attempt of a round (after a retirement): the selection must fit the ROOM left in the arena.  Bins are taken
-                //     whole from the top while they fit; of the bin that does not fit any more, the first `quota` boxes in store order
-                if (attempt > 0) {
-                    const int room = p.cap - nbox;
-                    if (room < p.cap / 64) { overflow = true; break; }             // not worth a round: the arena stays full
-                    th_hi = theta; th_lo = theta; quota = 0;
-                    double up = 0.0; bool crossed = false;
-                    unsigned long long ws = words;
-                    while (ws && !crossed) {
-                        const int w = 63 - __clzll((long long)ws); ws &= ~(1ull << w);
-                        unsigned m = occ[w];
-                        while (m && !crossed) {
-                            const int b = (w << 5) + 31 - __clz((int)m); m &= ~(1u << (b & 31));
-                            if (b > kBins - 2) continue;
-                            const double c = (double)hist[b];
-                            if (up + c > (double)room) {
-                                th_hi = fmax(theta, b + 1 >= kBins - 1 ? 1.7976931348623157e308 : bin_edge(b + 1));
-                                th_lo = fmax(theta, bin_edge(b));
-                                quota = room - (int)up;
-                                crossed = true;
-                            } else up += c;
-                        }
-                    }
-                }
-            }
+            // ---- threshold (round_threshold above) and selection.  ret[1] = the error retired from this sub-problem's arena so far (0 in batch mode)
+            const double theta_prev = theta;
+            theta = round_threshold(hist, occ, lane, tol - ret[1], mx, theta_prev, (double)p.max_apps - (double)applied, p.frac * (double)nbox);
 
             // ---- select: slots with error >= theta, in store order.  The pass is a latency-bound stream of the problem's keys (ncu: a fifth
             //      of the stall samples of the product-peak kernel sat on its first compare), so the keys of the NEXT 512 boxes are already
@@ -465,27 +572,6 @@ hcub_rb_kernel(const Params p) {
             //      no double buffering: 8 wins on the families with smaller stores, 16 only on the product peak)
             nsplit = 0;
             dE = 0.0;
-            if (attempt > 0) {
-                // the capped selection of a second attempt (rare; plain loop): error >= th_hi, and the first `quota` boxes of [th_lo, th_hi)
-                int nlo = 0;
-                for (int i0 = 0; i0 < nbox; i0 += 32) {
-                    const int i = i0 + lane;
-                    const double e = i < nbox ? __ldcg(err + i) : -1.0;
-                    const bool hi = e >= th_hi;
-                    const bool lo = !hi && e >= th_lo;
-                    const unsigned bl = __ballot_sync(full, lo);
-                    const bool flag = hi || (lo && nlo + __popc(bl & lt) < quota);
-                    nlo += __popc(bl);
-                    const unsigned bal = __ballot_sync(full, flag);
-                    if (flag) {
-                        list[nsplit + __popc(bal & lt)] = i;
-                        dE += e;
-                        const int bn = ebin(e);
-                        if (atomicSub(&hist[bn], 1u) == 1u) atomicAnd(&occ[bn >> 5], ~(1u << (bn & 31)));
-                    }
-                    nsplit += __popc(bal);
-                }
-            } else
             {
 #ifndef HB_KU
 #define HB_KU 8
@@ -526,76 +612,17 @@ hcub_rb_kernel(const Params p) {
                     }
                 }
             }
-            if (attempt > 0 && nsplit == 0) { overflow = true; break; }            // a full arena and nothing left to retire
-            if (nbox + nsplit <= p.cap) break;
-            if (!sub || attempt > 0) { overflow = true; break; }                   // arena full: leave the boxes alone
-            // ---- retirement.  Boxes with the smallest errors leave the store; their integrals and errors stay in (I, E) and in the
-            //      closing sum through (Iret, Eret).  Retired error cannot be refined away, so a retirement may take at most a quarter
-            //      of the tolerance still unspent, measured by the UPPER edges of the histogram bins (a bound on the retired sum): every
-            //      box below theta_r = that bin edge goes.  Never a box selected for bisection (theta_r <= theta).  The histogram is
-            //      rebuilt from the boxes that stay (the selection pass has taken the selected ones out of it).
-            {
-                __syncwarp();
-                const double R = 0.25 * (tol - Eret);
-                const unsigned long long words = (unsigned long long)__ballot_sync(full, occ[lane] != 0u) |
-                                                 ((unsigned long long)__ballot_sync(full, occ[32 + lane] != 0u) << 32);
-                int br = -1;
-                {
-                    double acc = 0.0; bool broke = false;
-                    unsigned long long ws = words;
-                    while (ws && !broke) {
-                        const int w = __ffsll((long long)ws) - 1; ws &= ws - 1;
-                        unsigned m = occ[w];
-                        while (m) {
-                            const int b = (w << 5) + __ffs((int)m) - 1; m &= m - 1;
-                            if (b > kBins - 3) { broke = true; break; }
-                            acc += (double)hist[b] * bin_edge(b + 1);
-                            if (!(acc <= R)) { broke = true; break; }
-                            br = b;
-                        }
-                    }
+            if (nbox + nsplit > p.cap) {
+                // arena full.  Batch mode: leave the boxes alone.  Sub-problem mode: retire the converged boxes and decide the round again
+                bool ok = false;
+                if constexpr (SUB) {
+                    int nb = nbox, ns = 0; double de = 0.0, th = theta;
+                    ok = retire_reselect<D>(rec, err, list, hist, occ, ret, p.cap, tol, mx, theta_prev, theta, (double)p.max_apps - (double)applied,
+                                            p.frac, &nb, &ns, &de, &th);
+                    nbox = nb; nsplit = ns; dE = de; theta = th;
                 }
-                const double theta_r = fmin(br < 0 ? 0.0 : bin_edge(br + 1), theta);
-                __syncwarp();
-                for (int b = lane; b < kBins; b += 32) hist[b] = 0u;
-                for (int b = lane; b < kBins / 32; b += 32) occ[b] = 0u;
-                __syncwarp();
-                int kept = 0;
-                double rI = 0.0, rE = 0.0;
-                for (int i0 = 0; i0 < nbox; i0 += 32) {
-                    const int i = i0 + lane;
-                    const bool have = i < nbox;
-                    const double e = have ? __ldcg(err + i) : 0.0;
-                    const bool keep = have && e >= theta_r;
-                    double r[RECW];
-                    if (keep) {
-                        const double2 *src = reinterpret_cast<const double2 *>(rec + (size_t)i * RECW);
-#pragma unroll
-                        for (int q = 0; q < NCH; q++) { const double2 v = __ldcg(src + q); r[2 * q] = v.x; r[2 * q + 1] = v.y; }
-                    } else if (have) { rI += __ldcg(rec + (size_t)i * RECW + 2 * D); rE += e; }
-                    const unsigned bal = __ballot_sync(full, keep);
-                    __syncwarp();                                       // every lane has read its box before a slot of this batch is overwritten
-                    if (keep) {
-                        const int j = kept + __popc(bal & lt);          // j <= i: a slot this pass has already read
-                        if (j != i) {
-                            double2 *dst = reinterpret_cast<double2 *>(rec + (size_t)j * RECW);
-#pragma unroll
-                            for (int q = 0; q < NCH; q++) dst[q] = make_double2(r[2 * q], r[2 * q + 1]);
-                            err[j] = e;
-                        }
-                        const int bn = ebin(e);
-                        if (atomicAdd(&hist[bn], 1u) == 0u) atomicOr(&occ[bn >> 5], 1u << (bn & 31));
-                    }
-                    kept += __popc(bal);
-                    __syncwarp();
-                }
-                Iret += wsum(rI); Eret += wsum(rE);
-                nretired += nbox - kept;
-                nbox = kept;
-                __syncwarp();
+                if (!ok) { status = IB200_ST_MAXEVALS; break; }
             }
-            }
-            if (overflow) { status = IB200_ST_MAXEVALS; break; }
             nbox0 = nbox;
             nbox += nsplit; ntodo = 2 * nsplit;
             __syncwarp();                 // the split list is read across lanes
@@ -614,10 +641,10 @@ hcub_rb_kernel(const Params p) {
             }
             for (; s < nbox; s += 32) { pI += __ldcg(rec + (size_t)s * RECW + 2 * D); pE += __ldcg(err + s); }
         }
-        pI = wsum(pI) + Iret; pE = wsum(pE) + Eret;
+        pI = wsum(pI) + ret[0]; pE = wsum(pE) + ret[1];          // + what was retired from a full arena (sub-problem mode)
         if (lane == 0) {
             if (sub) {
-                if (nretired > 0) { atomicAdd(p.counter + 4, 1ULL); atomicAdd(p.counter + 5, (unsigned long long)nretired); }
+                if (ret[2] > 0.0) { atomicAdd(p.counter + 4, 1ULL); atomicAdd(p.counter + 5, (unsigned long long)ret[2]); }
                 double *o = p.sub_out + (size_t)pidx * 4;
                 o[0] = pI; o[1] = pE; o[2] = (double)applied; o[3] = (double)status;
                 // diagnostics behind the counter: sub-problems ended by their budget / by a full arena / non-finite
@@ -677,8 +704,10 @@ int32_t launch_impl(ib200_ctx *ctx, int family, bool allfin, Params &p, long lon
                 IB_LAUNCH_CHECK(ctx);
                 return IB200_OK;
             };
-            rc = allfin ? go(hcub_rb_kernel<FAM, D, true>, (size_t)(block_doubles<FAM, D>() + kWarps * row_doubles<FAM, D, true>()) * sizeof(double))
-                        : go(hcub_rb_kernel<FAM, D, false>, (size_t)(block_doubles<FAM, D>() + kWarps * row_doubles<FAM, D, false>()) * sizeof(double));
+            const size_t smem_fin = (size_t)(block_doubles<FAM, D>() + kWarps * row_doubles<FAM, D, true>()) * sizeof(double);
+            const size_t smem_inf = (size_t)(block_doubles<FAM, D>() + kWarps * row_doubles<FAM, D, false>()) * sizeof(double);
+            if (p.sub_rec != nullptr) rc = allfin ? go(hcub_rb_kernel<FAM, D, true, true>, smem_fin) : go(hcub_rb_kernel<FAM, D, false, true>, smem_inf);
+            else rc = allfin ? go(hcub_rb_kernel<FAM, D, true, false>, smem_fin) : go(hcub_rb_kernel<FAM, D, false, false>, smem_inf);
         }
     });
     if (rc == IB200_ERR_UNSUPPORTED && ctx->err.empty())

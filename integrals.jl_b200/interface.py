@@ -122,6 +122,25 @@ class BatchIntegralFunction:
         return y
 
 
+class CudaIntegralFunction:
+    """An integrand stated as CUDA C++ source: the body of `__device__ double f(const double *x, const double *p)`, e.g.
+    CudaIntegralFunction("return exp(-p[0] * x[0] * x[0]) * cos(p[1] * x[1]);").  The counterpart of the reference's closure f(x, p)
+    (src/Integrals.jl:327-335, 380-393) for integrands outside the registered families: compiled at run time (NVRTC) into one elementwise
+    kernel that the engine runs between the two kernels of the BatchIntegralFunction bridge, so every evaluation of a solve stays on the
+    device (ib200_integrand_compile / ib200_integrate_compiled).  One problem per solve; integrated by QuadGKB200 (1-D) or HCubatureB200."""
+
+    def __init__(self, body):
+        if not isinstance(body, str) or "return" not in body:
+            raise TypeError("CudaIntegralFunction takes the body of  double f(const double *x, const double *p)  as a string (with a return statement)")
+        self.body = body
+        self._handles = {}          # dim -> handle (compiled on first use)
+
+    def handle(self, engine, dim):
+        if dim not in self._handles:
+            self._handles[dim] = engine.compile_integrand(self.body, dim)
+        return self._handles[dim]
+
+
 class IntegralFunction(BatchIntegralFunction):
     """IntegralFunction(f) (SciMLBase; the reference's default wrapper of a closure f(x, p), src/Integrals.jl:327-335, 366-378): a
     POINTWISE closure.  It cannot run on the device, so it is evaluated where the reference evaluates it -- in the caller's process --
@@ -148,9 +167,10 @@ class IntegralProblem:
     length dim, or dim x nprob arrays (per-problem bounds).  p: nparam numbers or nparam x nprob."""
 
     def __init__(self, f, domain, p=None, **kwargs):
-        if not isinstance(f, (RegisteredIntegrand, BatchIntegralFunction)):
+        if not isinstance(f, (RegisteredIntegrand, BatchIntegralFunction, CudaIntegralFunction)):
             raise TypeError("the B200 engine integrates registered device-side integrands only "
-                            "(integrals_b200.integrands) or a BatchIntegralFunction (caller-evaluated batches of points); "
+                            "(integrals_b200.integrands), a CudaIntegralFunction (CUDA source compiled at run time) or a "
+                            "BatchIntegralFunction (caller-evaluated batches of points); "
                             "arbitrary pointwise host closures cannot run on the device")
         if not (isinstance(domain, (tuple, list)) and len(domain) == 2):
             raise TypeError("domain must be a tuple (lb, ub)")
@@ -396,6 +416,8 @@ def solve_cache(cache):
     inner, tr = cache.alg.alg, cache.alg.fu2gv.id
     if isinstance(cache.f, BatchIntegralFunction):
         return _solve_batch_function(cache, prob, inner, tr)
+    if isinstance(cache.f, CudaIntegralFunction):
+        return _solve_cuda_function(cache, prob, inner, tr)
     if isinstance(cache.f, VectorOf):
         return _solve_vector(cache, prob, inner, tr)
     if getattr(cache, "sensealg", None) is not None:
@@ -524,6 +546,34 @@ def _solve_batch_function(cache, prob, inner, tr):
                                                  abstol=kw.get("abstol", 1e-8), max_boxes=max_boxes,
                                                  store_boxes=getattr(inner, "store_boxes", 0), transform=tr, device=cache.f.device,
                                                  **({} if cache.f.max_batch is None else {"max_batch": cache.f.max_batch}))
+    return IntegralSolution(I, E, prob, inner, retcode_of(inner, stats.get("status", 0), stats.get("nevals", 0), maxiters, slack=2 * npts), None, stats)
+
+
+def _solve_cuda_function(cache, prob, inner, tr):
+    """CudaIntegralFunction: the bridge's rounds with the compiled integrand evaluated on the device (engine.integrate_compiled)"""
+    lb, ub = prob.domain
+    lb = np.atleast_1d(np.asarray(lb, dtype=np.float64)); ub = np.atleast_1d(np.asarray(ub, dtype=np.float64))
+    if lb.ndim != 1 or lb.shape != ub.shape:
+        raise ValueError("a CudaIntegralFunction problem has one domain: bounds of length dim")
+    dim = lb.shape[0]
+    if isinstance(inner, QuadGKB200):
+        if dim != 1:
+            raise ValueError("QuadGKB200 only accepts one-dimensional quadrature problems.")    # Integrals.jl:263-266
+        if inner.order != 7:
+            raise ValueError("CudaIntegralFunction solves use the (7,15) pair")
+    elif isinstance(inner, HCubatureB200):
+        if inner.initdiv != 1:
+            raise ValueError("CudaIntegralFunction solves do not take initdiv")
+    else:
+        raise TypeError("a CudaIntegralFunction is integrated by QuadGKB200 (1-D) or HCubatureB200")
+    kw = cache.kwargs
+    npts = 15 if dim == 1 else 1 + 4 * dim + 2 * dim * (dim - 1) + (1 << dim)
+    maxiters = kw.get("maxiters", _lib.MAXEVALS_UNBOUNDED)
+    max_boxes = max(1, min(int(maxiters), _lib.MAXEVALS_UNBOUNDED) // npts)
+    p = () if prob.p is None else np.ravel(np.asarray(prob.p, dtype=np.float64))
+    eng = cache.cacheval
+    I, E, stats = eng.integrate_compiled(cache.f.handle(eng, dim), dim, lb, ub, p, reltol=kw.get("reltol", 1e-8), abstol=kw.get("abstol", 1e-8),
+                                         max_boxes=min(max_boxes, 1 << 40), store_boxes=getattr(inner, "store_boxes", 0), transform=tr)
     return IntegralSolution(I, E, prob, inner, retcode_of(inner, stats.get("status", 0), stats.get("nevals", 0), maxiters, slack=2 * npts), None, stats)
 
 

@@ -122,6 +122,52 @@ function solve_vector(cache::IntegralCache, alg::Union{QuadGKB200, HCubatureB200
     SciMLBase.build_solution(Integrals.build_problem(cache), alg, u, r, retcode = retcode_of(alg, st, ne, maxiters))
 end
 
+# parameter sensitivities: I and dI/dp[wrt] of every problem as ONE vector-valued integral [f, df/dp...] on shared nodes and subdivision.
+# The engine cannot push ForwardDiff.Dual numbers or a Zygote pullback through a device-side integrand, so the AD rules of the reference
+# (ext/IntegralsForwardDiffExt.jl:55-134, ext/IntegralsZygoteExt.jl:144-178) are replaced for the registered families by this call:
+#   a `__solvebp(cache, alg::AbstractB200Algorithm, sensealg, domain, p::AbstractArray{<:ForwardDiff.Dual})` method calls it with
+#   control = :value (dual numbers flowing through QuadGKJL / HCubatureJL leave the error control to the value) and rebuilds the duals
+#   from (I, dI/dp * partials); the ChainRules `rrule` calls it with control = :norm2 and returns dI/dp' * ybar.
+# wrt: 1-based parameter rows (at most 7 per call; more are solved in groups); control: :value, :norm2 or :norminf.
+function b200_sensitivities(prob::IntegralProblem, alg::Union{QuadGKB200, HCubatureB200}; wrt = nothing, control::Symbol = :value,
+                            reltol = 1.0e-8, abstol = 1.0e-8, maxiters = typemax(Int), transform::Int32 = Int32(0))
+    cache = init(prob, alg)
+    ctx = cache.cacheval
+    lb0, ub0 = prob.domain
+    dim = length(lb0)
+    P = prob.p isa AbstractMatrix ? Matrix{Float64}(prob.p) : reshape(collect(Float64, prob.p), :, 1)
+    nparam, nprob = size(P)
+    rows = wrt === nothing ? collect(1:nparam) : collect(Int, wrt)
+    lb = collect(Float64, vec(collect(lb0))); ub = collect(Float64, vec(collect(ub0)))
+    normkind = Int32(control === :value ? 2 : (control === :norminf ? 1 : 0))
+    Iv = Vector{Float64}(undef, nprob); dI = Matrix{Float64}(undef, length(rows), nprob)
+    E = zeros(nprob); ne = zeros(Int64, nprob); st = zeros(Int32, nprob)
+    for g0 in 1:7:length(rows)
+        grp = rows[g0:min(g0 + 6, length(rows))]
+        idx = Int32.(grp .- 1); ns = Int32(length(idx))
+        out = Matrix{Float64}(undef, 1 + ns, nprob); Eg = similar(E); neg = similar(ne); stg = similar(st)
+        if alg isa QuadGKB200
+            GC.@preserve lb ub P idx out Eg neg stg check(ctx, ccall((:ib200_quadgk_sens_batch, lib), Int32,
+                (Ptr{Cvoid}, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Int32, Ptr{Float64}, Int32, Int64, Ptr{Int32}, Int32, Float64, Float64, Int64, Int32,
+                 Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int32}),
+                ctx.h, family_id(prob.f.f), transform, lb, ub, Int32(0), P, nparam, nprob, idx, ns, reltol, abstol, min(maxiters, 2^62), normkind,
+                out, Eg, neg, stg))
+        else
+            GC.@preserve lb ub P idx out Eg neg stg check(ctx, ccall((:ib200_hcubature_sens_batch, lib), Int32,
+                (Ptr{Cvoid}, Int32, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Int32, Ptr{Float64}, Int32, Int64, Ptr{Int32}, Int32, Float64, Float64, Int64,
+                 Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int32}),
+                ctx.h, family_id(prob.f.f), dim, transform, lb, ub, Int32(0), P, nparam, nprob, idx, ns, reltol, abstol, min(maxiters, 2^62),
+                alg.initdiv, normkind, out, Eg, neg, stg))
+        end
+        g0 == 1 && (Iv .= out[1, :])
+        dI[g0:(g0 + ns - 1), :] .= out[2:end, :]
+        E .= max.(E, Eg); ne .= max.(ne, neg); st .= max.(st, stg)
+    end
+    u, r = prob.p isa AbstractMatrix ? (Iv, E) : (Iv[1], E[1])
+    sol = SciMLBase.build_solution(prob, alg, u, r, retcode = retcode_of(alg, st, ne, maxiters))
+    return sol, (prob.p isa AbstractMatrix ? dI : dI[:, 1])
+end
+
 # BatchIntegralFunction (src/Integrals.jl:274-315): ANY Julia closure f(pts, p) -> values, evaluated by Julia on the batches of
 # points the engine hands out; the points of a round, the weighted sums, the error estimates and the refinement stay on the
 # device.  With CuArray buffers (pointer(x::CuArray)) nothing is copied; a host Array works the same way.
