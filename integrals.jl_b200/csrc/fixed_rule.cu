@@ -18,6 +18,9 @@
 namespace {
 
 constexpr int kBlock = 256;
+#ifndef IB200_TENSOR_ROWS
+#define IB200_TENSOR_ROWS 8      // items per thread and pass in the angle-addition loop of tensor_kernel (measured, see there)
+#endif
 
 __device__ __forceinline__ double block_reduce_sum(double v, double *red /* >= kBlock/32 doubles */) {
 #pragma unroll
@@ -80,6 +83,50 @@ tensor_kernel(const double *__restrict__ params, int nparam, int64_t nprob,
         const double init = F::sep_init(par);
         const double2 *tin = tab + (size_t)(D - 1) * n;
         double total = 0.0;
+        if constexpr (kAngle) {
+            // Oscillatory family: cos(phi + theta_j) = cos(phi) cos(theta_j) - sin(phi) sin(theta_j): phi (the outer axes' phase) costs one
+            // sincos per item, every node of the innermost axis one multiply and two FMAs (angle addition from per-axis
+            // tables; the integrand is still formed at every node of the rule).  A thread takes kRows items at a time through the same
+            // inner loop, so the table entries of a node ({cos, sin} and w * jac: two shared-memory loads) serve kRows nodes -- ncu on
+            // the one-item version: LSU 54.7 % against FP64 45.6 %, the loads, not the arithmetic, set the time
+            // (profiles/r01b_tensor_c3_b_full_summary.txt; with 4 items: LSU 17 %, FP64 pipe 53.7 %, profiles/r02_tensor_c3_rows4_full_summary.txt).
+            // isplit is a power of two <= kBlock, so the items of a thread share their chunk.
+            // Measured on BASELINE config 3 (65,536 integrals): 1 item per pass 7.36 ms, 2 or 4 items 5.95 ms, 8 items 5.67 ms.  Full groups of
+            // kRows items first, single items for what is left (small rules have fewer items than kRows per thread).
+            auto rows = [&](auto rc, int64_t it0) {
+                constexpr int R = decltype(rc)::value;
+                double qs[R], qc[R], wo[R], s0[R];
+                const int c = (int)(it0 % isplit);
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    int64_t o = (it0 + (int64_t)r * kBlock) / isplit;
+                    double acc = init, w = 1.0;
+#pragma unroll
+                    for (int k = 0; k < D - 1; k++) {
+                        const int ik = (int)(o % n); o /= n;
+                        const double2 e = tab[k * n + ik];
+                        acc = acc + e.x;
+                        w *= e.y;
+                    }
+                    sincos(acc, &qs[r], &qc[r]);
+                    wo[r] = w;
+                    s0[r] = 0.0;
+                }
+                const int k0 = c * chunk, k1 = min(n, k0 + chunk);
+                for (int k = k0; k < k1; k++) {
+                    const double2 cj = cs[k];
+                    const double wj = tin[k].y;
+#pragma unroll
+                    for (int r = 0; r < R; r++) s0[r] = fma(wj, fma(qc[r], cj.x, -(qs[r] * cj.y)), s0[r]);
+                }
+#pragma unroll
+                for (int r = 0; r < R; r++) total = fma(wo[r], s0[r], total);
+            };
+            constexpr int kRows = IB200_TENSOR_ROWS;
+            int64_t it0 = threadIdx.x;
+            for (; it0 + (int64_t)(kRows - 1) * kBlock < items; it0 += (int64_t)kRows * kBlock) rows(std::integral_constant<int, kRows>{}, it0);
+            for (; it0 < items; it0 += kBlock) rows(std::integral_constant<int, 1>{}, it0);
+        } else
         for (int64_t it = threadIdx.x; it < items; it += kBlock) {
             int64_t o = it / isplit;
             const int c = (int)(it - o * isplit);
@@ -94,20 +141,6 @@ tensor_kernel(const double *__restrict__ params, int nparam, int64_t nprob,
             const int k0 = c * chunk, k1 = min(n, k0 + chunk);
             double s0 = 0.0, s1 = 0.0;
             int k = k0;
-            if constexpr (kAngle) {
-                // cos(phi + theta_j) = cos(phi) cos(theta_j) - sin(phi) sin(theta_j): phi (the outer axes' phase) costs one
-                // sincos per item, every node of the innermost axis one multiply and one FMA (angle addition
-                // from per-axis tables; the integrand is still formed at every node of the rule)
-                double qs, qc;
-                sincos(acc, &qs, &qc);
-                for (; k + 1 < k1; k += 2) {
-                    const double2 c0 = cs[k], c1 = cs[k + 1];
-                    const double f0 = fma(qc, c0.x, -(qs * c0.y)), f1 = fma(qc, c1.x, -(qs * c1.y));
-                    s0 = fma(tin[k].y, f0, s0);
-                    s1 = fma(tin[k + 1].y, f1, s1);
-                }
-                if (k < k1) { const double2 c0 = cs[k]; s0 = fma(tin[k].y, fma(qc, c0.x, -(qs * c0.y)), s0); k++; }
-            }
             for (; k + 1 < k1; k += 2) {
                 const double2 e0 = tin[k], e1 = tin[k + 1];
                 const double a0 = F::kProd ? acc * e0.x : acc + e0.x;
