@@ -172,8 +172,10 @@ __device__ __forceinline__ void cos_bfN(const double (&x)[N], double (&out)[N]) 
 
 // Branch-free sin of N arguments in lock step: cos_bfN with the quadrant counted from 0 instead of 1 (sin x = cos(x - pi/2)): the same
 // reduction, one polynomial per argument with the coefficients chosen by the quadrant.  |x| >= 2^30 takes libm's sin.  Max error 1.5 ulp.
+// sin_bfN_fast: the branch-free part alone; true when some |x| >= 2^30 (or NaN) and the caller has to redo the group through libm
+// (see sincos_bfN_fast: one out-of-line slow path per caller instead of one inlined per group).
 template <int N>
-__device__ __forceinline__ void sin_bfN(const double (&x)[N], double (&out)[N]) {
+__device__ __forceinline__ bool sin_bfN_fast(const double (&x)[N], double (&out)[N]) {
     const double MG = 6755399441055744.0;
     double t[N], kf[N], r[N], z[N], p[N];
     bool big = false;
@@ -207,16 +209,27 @@ __device__ __forceinline__ void sin_bfN(const double (&x)[N], double (&out)[N]) 
         const double res = (iq[j] & 1) ? cres : sres;
         out[j] = (iq[j] & 2) ? -res : res;
     }
-    if (big) {
+    return big;
+}
+template <int N>
+__device__ __forceinline__ void sin_bfN(const double (&x)[N], double (&out)[N]) {
+    if (sin_bfN_fast<N>(x, out)) {
 #pragma unroll
         for (int j = 0; j < N; j++) out[j] = sin(x[j]);
     }
 }
+// libm's sin of n arguments, out of line (the cold path of callers of sin_bfN_fast)
+static __device__ __noinline__ void sin_libm_n(const double *x, double *out, int n) {
+    for (int j = 0; j < n; j++) out[j] = sin(x[j]);
+}
 
 // Branch-free sin and cos of N arguments in lock step: the reduction and the two fdlibm kernel polynomials of cos_bfN,
 // both evaluated, quadrant fix-up by selects.  |x| >= 2^30 takes libm's sincos.  Max error 1.5 ulp each.
+// sincos_bfN_fast: the branch-free part alone; returns true when some |x| >= 2^30 (or NaN) and the caller has to redo the group
+// through libm.  Callers that evaluate many groups in straight-line code (the angle-addition Genz-Malik rule) collect the flag and
+// keep ONE out-of-line slow path, so that libm's Payne-Hanek code does not sit between the groups in the instruction stream.
 template <int N>
-__device__ __forceinline__ void sincos_bfN(const double (&x)[N], double (&sn)[N], double (&cs)[N]) {
+__device__ __forceinline__ bool sincos_bfN_fast(const double (&x)[N], double (&sn)[N], double (&cs)[N]) {
     const double MG = 6755399441055744.0;
     double t[N], kf[N], r[N], z[N], ps[N], pc[N];
     bool big = false;
@@ -249,10 +262,18 @@ __device__ __forceinline__ void sincos_bfN(const double (&x)[N], double (&sn)[N]
         sn[j] = (q & 2) ? -s0 : s0;
         cs[j] = ((q + 1) & 2) ? -c0 : c0;
     }
-    if (big) {
+    return big;
+}
+template <int N>
+__device__ __forceinline__ void sincos_bfN(const double (&x)[N], double (&sn)[N], double (&cs)[N]) {
+    if (sincos_bfN_fast<N>(x, sn, cs)) {
 #pragma unroll
         for (int j = 0; j < N; j++) sincos(x[j], &sn[j], &cs[j]);
     }
+}
+// libm's sincos of n arguments, out of line (the cold path of callers of sincos_bfN_fast)
+static __device__ __noinline__ void sincos_libm_n(const double *x, double *sn, double *cs, int n) {
+    for (int j = 0; j < n; j++) sincos(x[j], &sn[j], &cs[j]);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -257,14 +257,26 @@ __device__ __forceinline__ void gm_rule_thread_osc(const double *pc, const doubl
     double sn[3 * D + 1], cs[3 * D + 1];
     {
         constexpr int NA = 3 * D + 1;
+        bool big = false;
 #pragma unroll
         for (int g0 = 0; g0 < NA; g0 += 4) {
             double x4[4], s4[4], c4[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) x4[j] = ang[g0 + j < NA ? g0 + j : NA - 1];
-            ib::sincos_bfN<4>(x4, s4, c4);
+            big = ib::sincos_bfN_fast<4>(x4, s4, c4) || big;
 #pragma unroll
             for (int j = 0; j < 4; j++) if (g0 + j < NA) { sn[g0 + j] = s4[j]; cs[g0 + j] = c4[j]; }
+        }
+        if (big) {
+            // an angle of 2^30 or more (or NaN): all of them through libm, in ONE out-of-line call.  Inlined per group, libm's slow
+            // paths sat between the groups and stretched the rule's straight-line code to 37 KB -- more than the 32 KB instruction
+            // cache level holds (ncu: no_instruction was 24 % of the stall samples of the 4-D oscillatory kernel)
+            double tx[NA], ts[NA], tc[NA];
+#pragma unroll
+            for (int j = 0; j < NA; j++) tx[j] = ang[j];
+            ib::sincos_libm_n(tx, ts, tc, NA);
+#pragma unroll
+            for (int j = 0; j < NA; j++) { sn[j] = ts[j]; cs[j] = tc[j]; }
         }
     }
     const double cS = cs[3 * D], sS = sn[3 * D];

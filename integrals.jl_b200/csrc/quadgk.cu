@@ -215,14 +215,23 @@ __device__ __forceinline__ void gk15_thread(const ib::Problem<FAM, 1, ALLFIN> &P
             const double fac = j < 7 ? 1 + c_gk_x[j] : (j < 14 ? 1 - c_gk_x[j - 7] : 1.0);
             arg[j] = (P.lb[0] + (1.0 + (a + fac * s)) * P.den[0]) * P.q[0];
         }
+        bool big = false;
 #pragma unroll
         for (int g0 = 0; g0 < 15; g0 += 5) {
             double x5[5], o5[5];
 #pragma unroll
             for (int j = 0; j < 5; j++) x5[j] = arg[g0 + j];
-            ib::sin_bfN<5>(x5, o5);
+            big = ib::sin_bfN_fast<5>(x5, o5) || big;
 #pragma unroll
             for (int j = 0; j < 5; j++) val[g0 + j] = o5[j] * P.jacc;
+        }
+        if (big) {                    // an argument of 2^30 or more: libm, in one out-of-line call (keeps 15 inlined slow paths out of the refinement loop)
+            double tx[15], to[15];
+#pragma unroll
+            for (int j = 0; j < 15; j++) tx[j] = arg[j];
+            ib::sin_libm_n(tx, to, 15);
+#pragma unroll
+            for (int j = 0; j < 15; j++) val[j] = to[j] * P.jacc;
         }
 #pragma unroll
         for (int j = 0; j < 7; j++) { fp[j] = val[j]; fm[j] = val[7 + j]; }

@@ -510,6 +510,42 @@ def test_hcubature_product_peak_extreme_parameters(eng, O, hcub_mode):
     assert np.all(np.abs(I - Ir) <= 1e-7 * np.abs(Ir) + 1e-300)
 
 
+# ------------------------------------------------------------------------------------- arguments of 2^30 and more: libm, out of line
+def test_quadgk_arguments_beyond_2_pow_30_take_libm(eng, O, quadgk_mode):
+    """|x p| >= 2^30: the lock-step sines (family.cuh sin_bfN_fast) report it and the rule is redone by libm's sin -- ONE out-of-line
+    call in the thread-per-problem kernel.  Two levels of the rule (45 evaluations) against the oracle, beside ordinary problems."""
+    p = np.array([[1.7, 3.0e9, 0.5, 8.0e11, 2.0 ** 28, 40.0]])
+    I, E, ne, st = eng.quadgk_batch(F["sinxp"], np.array([-2.0]), np.array([5.0]), p, reltol=1e-10, abstol=1e-12, maxevals=45)
+    Ir, Er, ner, str_ = O.quadgk_batch("sinxp", -2.0, 5.0, p, reltol=1e-10, abstol=1e-12, maxiters=45)
+    assert np.array_equal(ne, ner) and np.array_equal(st, str_) and np.all(np.isfinite(I)) and np.all(np.isfinite(E))
+    assert np.all(np.abs(I - Ir) <= 2e-13 * 7.0) and np.all(np.abs(E - Er) <= 2e-13 * 7.0)
+    if quadgk_mode == 3:       # a whole batch through the thread-per-problem kernel: lanes with and without large arguments side by side
+        n = 8192
+        pb = np.full((1, n), 1.7); pb[0, ::97] = 3.0e9; pb[0, 5::1013] = 8.0e11
+        Ib, Eb, neb, stb = eng.quadgk_batch(F["sinxp"], np.array([-2.0]), np.array([5.0]), pb, reltol=1e-10, abstol=1e-12, maxevals=45)
+        big = pb[0] > 1e9
+        assert np.all(Ib[~big] == I[0]) and np.all(Ib[pb[0] == 3.0e9] == I[1]) and np.all(Ib[pb[0] == 8.0e11] == I[3]) and np.all(neb[big] == 45)
+
+
+@pytest.mark.parametrize("mode", ["rounds", "reference_order"])
+def test_hcubature_oscillatory_angles_beyond_2_pow_30(eng, O, mode):
+    """the angle-addition rule of the oscillatory family (hcubature_pair.cuh gm_rule_thread_osc, both thread-per-box drivers): a step
+    angle or centre phase of 2^30 or more sends all 3d + 1 angles through libm's sincos (one out-of-line call).  At such arguments
+    the reference's cos(sum) itself carries the rounding of the sum (|phase| eps ~ 1e-6), so those problems are only checked to be
+    finite, bounded by the volume and reproducible; the ordinary problems of the same batch still match the oracle."""
+    lb, ub = np.zeros(4), np.ones(4)
+    three = np.array([[2.0e10, 1.0, 1.0, 1.0, 0.3, 0.0, 0.0, 0.0], [3.0, 2.0, 1.0, 0.5, 0.25, 0.0, 0.0, 0.0],
+                      [1.0, 1.0, 6.0e9, 1.0, 0.7, 0.0, 0.0, 0.0]]).T
+    reps = 1500                                            # 4500 problems: the reference-order driver takes its thread-per-box kernel
+    par = np.asfortranarray(np.tile(three, (1, reps)))     # columns 0, 1, 2, 0, 1, 2, ...
+    I, E, ne, st = eng.hcubature_batch(F["genz_oscillatory"], 4, lb, ub, par, reltol=1e-6, abstol=1e-8, maxevals=57 * 3, mode=mode)
+    Ir, Er, ner, str_ = O.hcubature_batch("osc", lb, ub, np.asfortranarray(three), reltol=1e-6, abstol=1e-8, maxiters=57 * 3)
+    assert np.all(np.isfinite(I)) and np.all(np.isfinite(E)) and np.all(np.abs(I) <= 1.0 + 1e-9)
+    for k in range(3):
+        assert np.all(I[k::3] == I[k]) and np.all(E[k::3] == E[k]) and np.all(ne[k::3] == ne[k])
+    assert abs(I[1] - Ir[1]) <= 1e-12 and abs(E[1] - Er[1]) <= 1e-12 and ne[1] == ner[1] and st[1] == str_[1]
+
+
 # ------------------------------------------------------------------------------------- QuadGK with other Gauss-Kronrod orders
 @pytest.mark.parametrize("order", [2, 3, 7, 10, 15, 21, 30])
 def test_quadgk_rule_orders_match_oracle(eng, O, order):
