@@ -83,7 +83,9 @@ int32_t     ib200_family_nparam(int32_t family, int32_t dim);   /* doubles per p
 double      ib200_last_kernel_ms(ib200_ctx *ctx);
 /* optional knobs: key in {"adaptive_warps_per_sm","hcub_capacity","sampled_slabs","hcub_mode",
    "hcub_lpt", "quadgk_mode" (0 auto, 1 warp per problem, 2 thread per segment, 3 thread per problem), "single_round_percent",
-   "single_switch_boxes", "single_switch_factor", "single_sub_boxes", "single_arena_mib" (ib200_hcubature_single, two-level solves)} */
+   "single_switch_boxes", "single_switch_factor", "single_sub_boxes", "single_arena_mib" (ib200_hcubature_single, two-level solves),
+   "hcub_compact" (round-based batches: 1 = 32-byte dyadic box records where they apply [default], 0 = full records; same results),
+   "hcub_compact_level" (1..31, halvings per axis such a record may hold before the problem goes to the full-record kernel)} */
 int32_t     ib200_set_option(ib200_ctx *ctx, const char *key, int64_t value);
 
 /* -- sampled data: replaces evalrule(data, weights, dim) src/sampled.jl:51-124 with the weights of

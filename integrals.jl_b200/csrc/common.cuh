@@ -48,6 +48,8 @@ struct ib200_ctx {
     int64_t opt_sampled_slabs = 0;           // 0 = auto
     int64_t opt_quadgk_mode = 0;             // 0 = auto, 1 = warp per problem, 2 = pair mode (thread per segment), 3 = thread per problem
     int64_t opt_hcub_mode = 0;               // 0 = auto, 1 = warp per problem, 2 = pair mode (thread per box)
+    int64_t opt_hcub_compact = 1;            // round-based driver: 32-byte dyadic box records where they apply (hcubature_rb.cuh kCptBytes); 0 = full records
+    int64_t opt_hcub_compact_level = 31;     // halvings per axis a compact record may hold (tests lower it to exercise the hand-back)
 
     // grow-only device scratch (the cacheval analogue: reused across calls)
     void *get(ScratchSlot s, size_t bytes) {

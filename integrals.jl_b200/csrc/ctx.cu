@@ -94,6 +94,11 @@ extern "C" int32_t ib200_set_option(ib200_ctx *ctx, const char *key, int64_t val
     else if (k == "sampled_slabs") ctx->opt_sampled_slabs = value;
     else if (k == "hcub_mode") ctx->opt_hcub_mode = value;
     else if (k == "hcub_lpt") ctx->opt_hcub_lpt = value;
+    else if (k == "hcub_compact") ctx->opt_hcub_compact = value;
+    else if (k == "hcub_compact_level") {
+        if (value < 1 || value > 31) return ib200_fail(ctx, IB200_ERR_INVALID, "ib200_set_option: hcub_compact_level must be 1..31");
+        ctx->opt_hcub_compact_level = value;
+    }
     else if (k == "quadgk_mode") ctx->opt_quadgk_mode = value;
     else if (k == "single_round_percent") {                 // hcub_single.cu: 1..100, share of the boxes one round may bisect
         if (value < 1 || value > 100) return ib200_fail(ctx, IB200_ERR_INVALID, "ib200_set_option: single_round_percent must be 1..100");

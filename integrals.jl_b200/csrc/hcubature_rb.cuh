@@ -74,7 +74,27 @@ struct Params {
     long long sub_n;            // boxes in the level-1 store.  Chunks of hs::kSubChunk consecutive boxes are dealt to the ranks round-robin
                                 // (chunk c -> rank c mod world); nprob = this rank's chunks x kSubChunk
     double *sub_out;            // [nprob][4]: integral, error, rule applications, status of this rank's sub-problems
+    // compact-record launches (CPT, below): problems whose boxes outgrow the compact form are handed back through ovf_list / ovf_count and
+    // solved by a second launch of the full-record kernel, which takes its problems from order[0 .. *norder)
+    const unsigned *order = nullptr; const unsigned long long *norder = nullptr;
+    unsigned *ovf_list = nullptr; unsigned long long *ovf_count = nullptr;
+    int cpt_max_level = 31;     // halvings per axis a compact record may hold (<= kCptMaxLevel; an option so that tests reach the hand-back)
 };
+
+// ---- COMPACT RECORDS (batch mode, finite domains, initdiv = 1, thread per box in 2..5 dimensions).  Every box of such a solve comes
+//      from halving [-1, 1]^D, so its corners are dyadic: a_k = -1 + i_k 2^(1-l_k), b_k = a_k + 2^(1-l_k) with the level l_k = number of
+//      halvings along axis k and i_k < 2^l_k.  Up to l_k = 31 these are EXACTLY the doubles the successive a + (b - a)/2, b - (b - a)/2 of
+//      the full-record kernel (and of the reference) produce -- every intermediate is representable -- so a box can be stored as
+//      (i_k, l_k) and decoded with one FMA per axis: 32 bytes = ONE sector instead of 80 bytes across 3.5 sectors in 4-D.  The 4-D
+//      product-peak kernel moves with its DRAM bytes (4 TB/s of scattered 16..80-byte pieces; padding its records to 96 B cost 9 %), and
+//      the record traffic was 60 % of them.
+//      Layout: uint4 {i_0, i_1, i_2, i_3} | uint2 {meta, i_4} | double I;   meta = l_0 | l_1 << 5 | ... | l_4 << 20 | split axis << 28.
+//      A problem that would halve a box a 32nd time along one axis is abandoned and listed in ovf_list (see Params).
+constexpr int kCptBytes = 32;
+constexpr int kCptMaxLevel = 31;
+#ifndef HB_COMPACT
+#define HB_COMPACT 1
+#endif
 
 __device__ __forceinline__ int ebin(double e) { return (int)(((unsigned long long)__double_as_longlong(e) >> 52) & 0x7ffull); }
 // lower edge of exponent bin b: 0 for b = 0, 2^(b-1023) otherwise (== scalbn(1.0, b - 1023) of the oracle)
@@ -293,9 +313,10 @@ template <int FAM, int D> __host__ __device__ constexpr int block_doubles() {
 #endif
 // SUB: sub-problem mode (level 2 of ib200_hcubature_single) is a separate instantiation -- its arena-retirement call (an ABI call in the
 // round loop) costs the batch kernels 13 registers and 11 % on the exponential families when it is merely present (measured, same box)
-template <int FAM, int D, bool ALLFIN, bool SUB>
+template <int FAM, int D, bool ALLFIN, bool SUB, bool CPT = false>
 __global__ void __launch_bounds__(kBlock, (D <= kMaxThreadDim ? HB_MINB : (warp_box<FAM, D>() ? 4 : HB_MINB_HD)))
 hcub_rb_kernel(const Params p) {
+    static_assert(!CPT || (ALLFIN && !SUB && D <= kMaxThreadDim), "compact records: batch mode, finite domains, thread per box");
     using F = ib::Family<FAM, D>;
     using W = hs::WarpRule<FAM, D, ALLFIN>;
     constexpr bool WB = warp_box<FAM, D>();               // warp per box
@@ -326,6 +347,7 @@ hcub_rb_kernel(const Params p) {
     }
 
     double *rec = p.rec + (size_t)gwarp * p.cap * RECW;
+    unsigned char *recb = reinterpret_cast<unsigned char *>(p.rec) + (size_t)gwarp * p.cap * kCptBytes;     // CPT: this warp's compact records
     double *err = p.err + (size_t)gwarp * p.cap;
     int *list = p.list + (size_t)gwarp * p.cap;
     constexpr bool sub = SUB;
@@ -334,8 +356,8 @@ hcub_rb_kernel(const Params p) {
         unsigned long long pidx = 0;
         if (lane == 0) pidx = atomicAdd(p.counter, 1ULL);
         pidx = __shfl_sync(full, pidx, 0);
-        if ((int64_t)pidx >= p.nprob) break;
-        const int64_t prob = sub ? 0 : (int64_t)pidx;                            // parameter column
+        if (p.norder ? pidx >= *p.norder : (int64_t)pidx >= p.nprob) break;
+        const int64_t prob = sub ? 0 : (p.order ? (int64_t)p.order[pidx] : (int64_t)pidx);   // parameter column
         // sub mode: box of the level-1 store -- entry (pidx % chunk) of this rank's chunk number pidx / chunk
         const int64_t sbox = (((int64_t)pidx / hs::kSubChunk) * p.sub_world + p.sub_rank) * hs::kSubChunk + (int64_t)pidx % hs::kSubChunk;
         if (sub && sbox >= p.sub_n) {                                            // tail of the last chunk
@@ -392,6 +414,12 @@ hcub_rb_kernel(const Params p) {
                 for (int q = 0; q < NCH; q++) dst[q] = make_double2(r[2 * q], r[2 * q + 1]);
             }
             qtotal = 2;
+        } else if constexpr (CPT) {
+            if (rtol == 0.0 && atol == 0.0) rtol = 1.4901161193847656e-08;   // sqrt(eps), HCubature default
+            if (lane == 0) {                                                // the root box [-1, 1]^D: all indices and levels zero
+                uint4 *dst = reinterpret_cast<uint4 *>(recb);
+                dst[0] = make_uint4(0u, 0u, 0u, 0u); dst[1] = make_uint4(0u, 0u, 0u, 0u);
+            }
         } else {
             if (rtol == 0.0 && atol == 0.0) rtol = 1.4901161193847656e-08;   // sqrt(eps), HCubature default
             // ---- initial grid (HCubature initdiv; CartesianIndices order, first index fastest) -> slots 0 .. qtotal-1, unevaluated:
@@ -429,6 +457,7 @@ hcub_rb_kernel(const Params p) {
         long long applied = 0;
         double I = 0.0, E = 0.0, theta = 0.0, dE = 0.0;
         bool first = true;
+        bool ovf = false;                                  // CPT: a box of this lane cannot be halved again in compact form
 
         for (;;) {
             // ---- evaluate.  Round 0: the boxes of the initial store (entry t = slot t).  Later rounds: both halves of every selected box.
@@ -440,9 +469,15 @@ hcub_rb_kernel(const Params p) {
                 const int npass = (ntodo + 31) >> 5;
                 auto entry = [&](int t) { return first ? t : __ldcg(list + (t >> 1)); };
                 auto issue = [&](int src_slot, int buf) {        // record -> stage[buf][chunk][lane]
-                    const double2 *src = reinterpret_cast<const double2 *>(rec + (size_t)src_slot * RECW);
+                    if constexpr (CPT) {
+                        const double2 *src = reinterpret_cast<const double2 *>(recb + (size_t)src_slot * kCptBytes);
+                        hp::cp_async16(stage + ((size_t)buf * NCH + 0) * 32 + lane, src);
+                        hp::cp_async16(stage + ((size_t)buf * NCH + 1) * 32 + lane, src + 1);
+                    } else {
+                        const double2 *src = reinterpret_cast<const double2 *>(rec + (size_t)src_slot * RECW);
 #pragma unroll
-                    for (int q = 0; q < NCH; q++) hp::cp_async16(stage + ((size_t)buf * NCH + q) * 32 + lane, src + q);
+                        for (int q = 0; q < NCH; q++) hp::cp_async16(stage + ((size_t)buf * NCH + q) * 32 + lane, src + q);
+                    }
                 };
                 int par_cur = lane < ntodo ? entry(lane) : 0;
                 if (lane < ntodo) issue(par_cur, 0);
@@ -455,22 +490,48 @@ hcub_rb_kernel(const Params p) {
                     hp::cp_async_wait_all();
                     double a[D], b[D], Ipar = 0.0;
                     int kd = -1;
+                    unsigned cidx[CPT ? D : 1], cmeta = 0u;          // CPT: the child's indices and levels
                     if (have) {
-                        double r[RECW];
+                        if constexpr (CPT) {
+                            const uint4 c0 = *reinterpret_cast<const uint4 *>(stage + ((size_t)(ps & 1) * NCH + 0) * 32 + lane);
+                            const uint4 c1 = *reinterpret_cast<const uint4 *>(stage + ((size_t)(ps & 1) * NCH + 1) * 32 + lane);
+                            const unsigned pidx4[5] = {c0.x, c0.y, c0.z, c0.w, c1.y};
+                            Ipar = __hiloint2double((int)c1.w, (int)c1.z);
+                            cmeta = c1.x & 0x0fffffffu;
+                            if (!first) kd = (int)(c1.x >> 28);
+                            const unsigned up = (t & 1) == 0 ? 1u : 0u;             // child 0 = upper half
 #pragma unroll
-                        for (int q = 0; q < NCH; q++) { const double2 v = stage[((size_t)(ps & 1) * NCH + q) * 32 + lane]; r[2 * q] = v.x; r[2 * q + 1] = v.y; }
+                            for (int k = 0; k < D; k++) {
+                                const unsigned lev = (cmeta >> (5 * k)) & 31u;
+                                const bool mine = (k == kd);
+                                if (mine && lev >= (unsigned)p.cpt_max_level) ovf = true;
+                                const unsigned nlev = mine ? lev + 1u : lev;
+                                cidx[k] = mine ? 2u * pidx4[k] + up : pidx4[k];
+                                if (mine) cmeta += 1u << (5 * k);
+                                // a = -1 + i 2^(1-l), b = a + 2^(1-l): exact (see the note at kCptBytes)
+                                const double w = __hiloint2double((int)((1024u - nlev) << 20), 0);
+                                a[k] = fma((double)cidx[k], w, -1.0);
+                                b[k] = a[k] + w;
+                            }
+                        } else {
+                            double r[RECW];
 #pragma unroll
-                        for (int k = 0; k < D; k++) { a[k] = r[k]; b[k] = r[D + k]; }
-                        Ipar = r[2 * D];
-                        if (!first) kd = (int)r[2 * D + 1];
+                            for (int q = 0; q < NCH; q++) { const double2 v = stage[((size_t)(ps & 1) * NCH + q) * 32 + lane]; r[2 * q] = v.x; r[2 * q + 1] = v.y; }
+#pragma unroll
+                            for (int k = 0; k < D; k++) { a[k] = r[k]; b[k] = r[D + k]; }
+                            Ipar = r[2 * D];
+                            if (!first) kd = (int)r[2 * D + 1];
+                        }
                     }
                     if (32 + t < ntodo) issue(par_next, (ps + 1) & 1);
                     hp::cp_async_commit();
                     __syncwarp();            // every lane holds its parent's record before child 0 overwrites that slot
                     if (have) {
                         // child 0 = upper half (a[kd] += w) keeps the parent's slot, child 1 = lower half (b[kd] -= w) is appended
+                        if constexpr (!CPT) {
 #pragma unroll
-                        for (int k = 0; k < D; k++) if (k == kd) { const double w = (b[k] - a[k]) * 0.5; if ((t & 1) == 0) a[k] = a[k] + w; else b[k] = b[k] - w; }
+                            for (int k = 0; k < D; k++) if (k == kd) { const double w = (b[k] - a[k]) * 0.5; if ((t & 1) == 0) a[k] = a[k] + w; else b[k] = b[k] - w; }
+                        }
                         if (!first && (t & 1) == 0) sI -= Ipar;                   // the parent's integral leaves the sum
                         const int slot = (first || (t & 1) == 0) ? par_cur : nbox0 + (t >> 1);
                         double Ic, Ec; int kc = 0;
@@ -478,13 +539,20 @@ hcub_rb_kernel(const Params p) {
                         else if constexpr (FAM == IB200_FAM_GENZ_OSC && ALLFIN) hp::gm_rule_thread_osc<D>(pc, a, b, Ic, Ec, kc);
                         else if constexpr (ALLFIN) g2::gm_rule_thread2<FAM, D>(pc, a, b, Ic, Ec, kc);
                         else hp::gm_rule_thread<FAM, D, ALLFIN>(pc, p.tr, a, b, Ic, Ec, kc);
-                        double2 *dst = reinterpret_cast<double2 *>(rec + (size_t)slot * RECW);
-                        double r[RECW];
+                        if constexpr (CPT) {
+                            uint4 *dst = reinterpret_cast<uint4 *>(recb + (size_t)slot * kCptBytes);
+                            dst[0] = make_uint4(cidx[0], cidx[1], D > 2 ? cidx[D > 2 ? 2 : 0] : 0u, D > 3 ? cidx[D > 3 ? 3 : 0] : 0u);
+                            dst[1] = make_uint4(cmeta | ((unsigned)kc << 28), D > 4 ? cidx[D > 4 ? 4 : 0] : 0u,
+                                                (unsigned)__double2loint(Ic), (unsigned)__double2hiint(Ic));
+                        } else {
+                            double2 *dst = reinterpret_cast<double2 *>(rec + (size_t)slot * RECW);
+                            double r[RECW];
 #pragma unroll
-                        for (int k = 0; k < D; k++) { r[k] = a[k]; r[D + k] = b[k]; }
-                        r[2 * D] = Ic; r[2 * D + 1] = (double)kc;
+                            for (int k = 0; k < D; k++) { r[k] = a[k]; r[D + k] = b[k]; }
+                            r[2 * D] = Ic; r[2 * D + 1] = (double)kc;
 #pragma unroll
-                        for (int q = 0; q < NCH; q++) dst[q] = make_double2(r[2 * q], r[2 * q + 1]);
+                            for (int q = 0; q < NCH; q++) dst[q] = make_double2(r[2 * q], r[2 * q + 1]);
+                        }
                         err[slot] = Ec;
                         const int bn = ebin(Ec);
                         if (atomicAdd(&hist[bn], 1u) == 0u) atomicOr(&occ[bn >> 5], 1u << (bn & 31));
@@ -555,6 +623,7 @@ hcub_rb_kernel(const Params p) {
             I += sI; E += sE;
             applied += ntodo;
             __syncwarp();
+            if constexpr (CPT) { if (__any_sync(full, ovf)) { status = -1; break; } }      // handed back to the full-record kernel
 
             // ---- HCubature's stopping test
             const double tol = fmax(rtol * fabs(I), atol);
@@ -628,9 +697,26 @@ hcub_rb_kernel(const Params p) {
             __syncwarp();                 // the split list is read across lanes
         }
 
+        if constexpr (CPT) {
+            if (status < 0) {
+                if (lane == 0) { const unsigned long long i = atomicAdd(p.ovf_count, 1ULL); p.ovf_list[i] = (unsigned)prob; }
+                continue;
+            }
+        }
         // ---- HCubature's closing sum over the store
         double pI = 0.0, pE = 0.0;
-        {
+        if constexpr (CPT) {
+            const double *ri = reinterpret_cast<const double *>(recb + 24);      // I of slot s: ri[4 s]
+            int s = lane;
+            for (; s + 7 * 32 < nbox; s += 8 * 32) {
+                double vi[8], ve[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) { vi[u] = __ldcg(ri + (size_t)(s + 32 * u) * 4); ve[u] = __ldcg(err + s + 32 * u); }
+#pragma unroll
+                for (int u = 0; u < 8; u++) { pI += vi[u]; pE += ve[u]; }
+            }
+            for (; s < nbox; s += 32) { pI += __ldcg(ri + (size_t)s * 4); pE += __ldcg(err + s); }
+        } else {
             int s = lane;
             for (; s + 7 * 32 < nbox; s += 8 * 32) {             // 16 loads in flight per lane, added in slot order
                 double vi[8], ve[8];
@@ -674,7 +760,7 @@ int32_t launch_impl(ib200_ctx *ctx, int family, bool allfin, Params &p, long lon
     ib200_dispatch_family(family, [&](auto famc) {
         constexpr int FAM = decltype(famc)::value;
         if constexpr (ib::fam_dim_ok(FAM, D)) {
-            auto go = [&](auto kern, size_t smem) -> int32_t {
+            auto go2 = [&](auto kern, size_t smem, Params &p) -> int32_t {
                 if (smem > ctx->smem_optin) return ib200_fail(ctx, IB200_ERR_INVALID, "ib200_hcubature_batch: shared memory of the round-based kernel exceeds the device limit");
                 IB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 int occ = 0;
@@ -704,10 +790,30 @@ int32_t launch_impl(ib200_ctx *ctx, int family, bool allfin, Params &p, long lon
                 IB_LAUNCH_CHECK(ctx);
                 return IB200_OK;
             };
+            auto go = [&](auto kern, size_t smem) -> int32_t { return go2(kern, smem, p); };
             const size_t smem_fin = (size_t)(block_doubles<FAM, D>() + kWarps * row_doubles<FAM, D, true>()) * sizeof(double);
             const size_t smem_inf = (size_t)(block_doubles<FAM, D>() + kWarps * row_doubles<FAM, D, false>()) * sizeof(double);
             if (p.sub_rec != nullptr) rc = allfin ? go(hcub_rb_kernel<FAM, D, true, true>, smem_fin) : go(hcub_rb_kernel<FAM, D, false, true>, smem_inf);
-            else rc = allfin ? go(hcub_rb_kernel<FAM, D, true, false>, smem_fin) : go(hcub_rb_kernel<FAM, D, false, false>, smem_inf);
+            else if (!allfin) rc = go(hcub_rb_kernel<FAM, D, false, false>, smem_inf);
+            else {
+                bool compact = false;
+                if constexpr (D <= kMaxThreadDim && HB_COMPACT) compact = p.initdiv == 1 && p.nprob < ((int64_t)1 << 32) && ctx->opt_hcub_compact != 0;
+                if (!compact) rc = go(hcub_rb_kernel<FAM, D, true, false>, smem_fin);
+                else if constexpr (D <= kMaxThreadDim && HB_COMPACT) rc = [&]() -> int32_t {
+                    // compact records first (see kCptBytes); the problems it hands back -- a box halved 32 times along one axis -- are solved by
+                    // the full-record kernel right behind it, from the device-side list, in the same arenas (sized for the full records)
+                    unsigned long long *aux = (unsigned long long *)ctx->get(SL_WORK5, 2 * sizeof(unsigned long long) + (size_t)p.nprob * sizeof(unsigned));
+                    if (!aux) return ib200_fail(ctx, IB200_ERR_OOM, "ib200_hcubature_batch: scratch allocation failed");
+                    IB_CUDA(ctx, cudaMemsetAsync(aux, 0, 2 * sizeof(unsigned long long), ctx->stream));
+                    p.ovf_count = aux; p.ovf_list = reinterpret_cast<unsigned *>(aux + 2);
+                    p.cpt_max_level = (int)ctx->opt_hcub_compact_level;
+                    const int32_t rc1 = go(hcub_rb_kernel<FAM, D, true, false, true>, smem_fin);
+                    if (rc1 != IB200_OK) return rc1;
+                    Params q = p;
+                    q.order = p.ovf_list; q.norder = p.ovf_count; q.counter = aux + 1; q.ovf_list = nullptr; q.ovf_count = nullptr;
+                    return go2(hcub_rb_kernel<FAM, D, true, false>, smem_fin, q);
+                }();
+            }
         }
     });
     if (rc == IB200_ERR_UNSUPPORTED && ctx->err.empty())

@@ -11,6 +11,8 @@ eng = ib.Engine(0); F = ib.FAMILY_IDS
 nprob = int(sys.argv[1]); d = 4
 fams = sys.argv[2:] or ["genz_product_peak", "genz_oscillatory", "genz_gaussian", "genz_c0"]
 tag = os.path.basename(os.environ.get("IB200_LIB", "baseline"))
+if os.environ.get("PV_COMPACT"): eng.set_option("hcub_compact", int(os.environ["PV_COMPACT"])); tag += " compact=" + os.environ["PV_COMPACT"]
+if os.environ.get("PV_LEVEL"): eng.set_option("hcub_compact_level", int(os.environ["PV_LEVEL"])); tag += " level=" + os.environ["PV_LEVEL"]
 for fam in fams:
     par = torch.from_numpy(np.ascontiguousarray(WL.genz_params(fam, d, nprob).T)).cuda()
     oI = torch.empty(nprob, dtype=torch.float64, device="cuda"); oE = torch.empty_like(oI)
@@ -21,4 +23,4 @@ for fam in fams:
                             out_E=oE, out_nevals=oN, out_status=oS)
         eng.synchronize(); ms.append(eng.last_kernel_ms)
     h = hashlib.sha1(oI.cpu().numpy().tobytes() + oE.cpu().numpy().tobytes() + oN.cpu().numpy().tobytes() + oS.cpu().numpy().tobytes()).hexdigest()[:12]
-    print(f"{tag:16s} {fam:20s} ms {ms[1]:9.3f} {ms[2]:9.3f}  evals {int(oN.sum().item()):15d}  hash {h}", flush=True)
+    print(f"{tag:26s} {fam:20s} ms {ms[1]:9.3f} {ms[2]:9.3f}  evals {int(oN.sum().item()):15d}  hash {h}", flush=True)
