@@ -226,3 +226,18 @@ def test_julia_extension_uses_only_names_the_reference_defines():
             assert re.search(r"\b(struct|abstract type)\s+" + name + r"\b|^" + name + r"\(", alg_src, flags=re.M), name
         else:
             assert re.search(r"\b(struct|function|abstract type)\s+" + name + r"\b", src), name
+
+
+def test_every_option_key_the_library_accepts_is_documented_in_the_header():
+    """ib200_set_option: the keys handled in csrc/ctx.cu and the list in include/integrals_b200.h stay in step"""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "integrals.jl_b200", "csrc", "ctx.cu")).read()
+    body = src[src.index("ib200_set_option(ib200_ctx *ctx"):]
+    body = body[:body.index("unknown key")]
+    keys = set(re.findall(r'k == "([a-z_0-9]+)"', body))
+    assert {"hcub_mode", "quadgk_mode", "hcub_compact", "hcub_compact_level", "single_sub_boxes"} <= keys
+    header = open(os.path.join(root, "include", "integrals_b200.h")).read()
+    missing = sorted(k for k in keys if f'"{k}"' not in header)
+    assert not missing, missing
