@@ -343,7 +343,9 @@ def main():
             dom_ev = int(dev[dom]["N"].sum().item())
             return dict(units=6 * nper, launches=6, flops=fl, flops_executed=flx if have_all else None, evals=ev, per_family=per,
                         h2d=6 * nper * 2 * d * 8 + 6 * 2 * d * 8, d2h=6 * nper * (8 + 8 + 8 + 4),
-                        kernel=f"{kname}<FAM,4,true> (6 launches per step, one per family)", refinement=mode,
+                        kernel=f"{kname}<FAM,4,true> (one launch per family and step" + (
+                            "; rounds mode: compact 32-byte box records, and a full-record launch behind each that picks up handed-back problems)"
+                            if mode == "rounds" else ")"), refinement=mode,
                         dominant=dict(kernel=f"{kname}<{dom},4,true>", key=f"{kkey}/{dom}/{d}", ms=kms[dom] / max(args.steps, 1), evals=dom_ev,
                                       flops=dom_ev * WL.hcubature_flops_per_eval(dom, d),
                                       share_of_step=kms[dom] / max(sum(kms.values()), 1e-9), nprob=nper,
